@@ -1,0 +1,345 @@
+"""Known-answer tests taken from the reference's OWN unit tests, re-encoded against
+the CPU oracle.  Each test cites the reference test file:line that holds the expected value."""
+import numpy as np
+import pytest
+
+from oracle import py_restatement as pr
+
+EXT = 4  # orc.SCORER_EXTERNAL
+
+
+def _pool(orc, role=None, kv=None, waiting=None, running=None, ext=None, n=None):
+    n = n or len(role if role is not None else kv if kv is not None else waiting)
+    role = role if role is not None else [orc.ROLE_NONE] * n
+    kv = kv if kv is not None else [0.0] * n
+    waiting = waiting if waiting is not None else [0] * n
+    return orc.PoolState(role, kv, waiting, running, ext)
+
+
+# ---- B.1 #1-#3: scheduling/scheduler_profile_test.go:64-108, :172 -------------------------------------
+def test_weighted_sum_same_weight(orc):
+    # two test scorers return 0.3 and 0.8 for every endpoint; filters keep pod1, pod2 of 3
+    pool = _pool(orc, role=[orc.ROLE_NONE, orc.ROLE_NONE, orc.ROLE_ABSENT], ext=[[0.3] * 3, [0.8] * 3])
+    prof = orc.make_profile(orc.FILTER_NONE, [(EXT, 1.0, 0), (EXT, 1.0, 1)])
+    scores, mx, pick, aset = orc.profile_run(prof, pool, [0, 0, 0], 0)
+    assert mx == 1.1                       # exact `!=` check at scheduler_profile_test.go:172
+    assert aset == [0, 1] and pick == 0
+    assert scores[2] == -1.0               # filtered out
+
+
+def test_weighted_sum_different_weights(orc):
+    pool = _pool(orc, role=[orc.ROLE_NONE, orc.ROLE_NONE, orc.ROLE_ABSENT], ext=[[0.3] * 3, [0.8] * 3])
+    prof = orc.make_profile(orc.FILTER_NONE, [(EXT, 60.0, 0), (EXT, 40.0, 1)])
+    _, mx, _, _ = orc.profile_run(prof, pool, [0, 0, 0], 0)
+    assert mx == 50                        # scheduler_profile_test.go:80-94
+
+
+def test_filter_all_is_error(orc):
+    pool = _pool(orc, role=[orc.ROLE_DECODE] * 3)
+    prof = orc.make_profile(orc.FILTER_PREFILL, [(EXT, 1.0, 0)])
+    _, _, pick, aset = orc.profile_run(prof, pool, [0, 0, 0], 0)
+    assert aset == [] and pick == -1       # scheduler_profile_test.go:96-108 -> "no endpoints available"
+    d = orc.schedule(prof, None, pool, [0, 0, 0], 0, 16, 0, 0)
+    assert d.status == -1
+
+
+# ---- B.1 #4: clamp, scheduler_profile_test.go:350-413 --------------------------------------------------
+def test_enforce_score_range(orc):
+    vals = [-0.5, 1.5, 0.0, 1.0, 0.5]
+    pool = _pool(orc, n=5, ext=[vals])
+    prof = orc.make_profile(orc.FILTER_NONE, [(EXT, 1.0, 0)])
+    scores, _, _, _ = orc.profile_run(prof, pool, [0] * 5, 0)
+    assert list(scores) == [0.0, 1.0, 0.0, 1.0, 0.5]
+    # Run with (-0.5, 1.5) -> total 1.0
+    pool = _pool(orc, n=1, ext=[[-0.5], [1.5]])
+    prof = orc.make_profile(orc.FILTER_NONE, [(EXT, 1.0, 0), (EXT, 1.0, 1)])
+    _, mx, _, _ = orc.profile_run(prof, pool, [0], 0)
+    assert mx == 1.0
+
+
+# ---- B.1 #6/#7: scheduling/scheduler_test.go:67-141 ----------------------------------------------------
+def test_default_scheduler_kat(orc):
+    # pods (q,kv): (0,0.2) (0,0.2)+critical active (10,0.8); lora-affinity tiers (lora_affinity.go:76-100):
+    # pod1: foo,bar active, max 2 -> no slot, not waiting -> 0.0 ; pod2: active -> 1.0 ; pod3: 1 of 2 -> 0.8
+    pool = _pool(orc, kv=[0.2, 0.2, 0.8], waiting=[0, 0, 10], ext=[[0.0, 1.0, 0.8]])
+    prof = orc.make_profile(orc.FILTER_NONE, [(orc.SCORER_KV_UTIL, 1.0, 0), (orc.SCORER_QUEUE, 1.0, 0),
+                                              (orc.SCORER_PREFIX, 1.0, 0), (EXT, 1.0, 0)])
+    scores, mx, pick, aset = orc.profile_run(prof, pool, [0, 0, 0], 0)
+    assert pick == 1 and aset == [1]
+    assert mx == 2.8                       # scheduler_test.go:125 Score: 2.8
+    d = orc.schedule(prof, None, pool, [0, 0, 0], 0, 16, 0, 0)
+    assert (d.status, d.pick, d.score) == (0, 1, 2.8)
+
+
+def test_no_candidates_is_error(orc):
+    pool = orc.PoolState(np.zeros(0, np.uint8), np.zeros(0), np.zeros(0, np.int32))
+    prof = orc.make_profile(orc.FILTER_NONE, [(orc.SCORER_KV_UTIL, 1.0, 0)])
+    d = orc.schedule(prof, None, pool, np.zeros(0, np.int32), 0, 16, 0, 0)
+    assert d.status == -1                  # scheduler_test.go:67-75
+
+
+# ---- B.1 #8-#11: scorer unit tests --------------------------------------------------------------------
+def test_prefix_scorer(orc):
+    pool = _pool(orc, n=2)
+    out = orc.score_column((orc.SCORER_PREFIX, 1.0, 0), pool, [1, 1], [5, 2], 10)
+    assert list(out) == [0.5, 0.2]         # scorer/prefix/plugin_test.go:31-44 (exact assert.Equal)
+    assert list(orc.score_column((orc.SCORER_PREFIX, 1.0, 0), pool, [1, 1], [5, 2], 0)) == [0.0, 0.0]
+
+
+def test_kv_util_scorer(orc):
+    kv = [0.8, 0.5, 0.0, 0.6, 1.0]
+    pool = _pool(orc, kv=kv)
+    out = orc.score_column((orc.SCORER_KV_UTIL, 1.0, 0), pool, [1] * 5, [0] * 5, 0)
+    assert out == pytest.approx([0.2, 0.5, 1.0, 0.4, 0.0], abs=1e-4)   # kvcache_utilization_test.go:36-79
+    assert list(out) == [1 - x for x in kv]
+
+
+def test_queue_scorer(orc):
+    pool = _pool(orc, waiting=[10, 5, 0])
+    out = orc.score_column((orc.SCORER_QUEUE, 1.0, 0), pool, [1, 1, 1], [0] * 3, 0)
+    assert list(out) == [0.0, 0.5, 1.0]    # queuedepth/queue_test.go:36-67
+    pool = _pool(orc, waiting=[7, 7, 7])
+    assert list(orc.score_column((orc.SCORER_QUEUE, 1.0, 0), pool, [1, 1, 1], [0] * 3, 0)) == [1.0] * 3
+    # min/max are over the CANDIDATES only (queue.go:79-91)
+    pool = _pool(orc, waiting=[10, 5, 0])
+    out = orc.score_column((orc.SCORER_QUEUE, 1.0, 0), pool, [1, 1, 0], [0] * 3, 0)
+    assert list(out) == [0.0, 1.0, 0.0]
+
+
+def test_load_aware_scorer(orc):
+    pool = _pool(orc, waiting=[2, 0, 15])
+    out = orc.score_column((orc.SCORER_LOAD_AWARE, 1.0, 10), pool, [1, 1, 1], [0] * 3, 0)
+    assert list(out) == [0.4, 0.5, 0.0]    # loadaware/load_aware_test.go:38-60 (exact cmp.Diff)
+    out = orc.score_column((orc.SCORER_LOAD_AWARE, 1.0, 0), pool, [1, 1, 1], [0] * 3, 0)   # <=0 -> 128
+    assert list(out) == [0.5 * (1.0 - 2 / 128.0), 0.5, 0.5 * (1.0 - 15 / 128.0)]
+
+
+# ---- B.1 #12: picker/maxscore/picker_test.go:43-110 -- ties are a SET ----------------------------------
+def test_max_score_picker_tie_set(orc):
+    pool = _pool(orc, n=4, ext=[[0.5, 0.9, 0.9, 0.1]])
+    prof = orc.make_profile(orc.FILTER_NONE, [(EXT, 1.0, 0)])
+    _, mx, pick, aset = orc.profile_run(prof, pool, [0] * 4, 0)
+    assert mx == 0.9 and aset == [1, 2] and pick == 1
+
+
+# ---- B.1 #13-#15, #20: prefix producer + indexer -------------------------------------------------------
+def test_produce_empty_index(orc):
+    ix = orc.Indexer()
+    hashes = orc.hash_prompt(b"aaaabbbb", b"test-model1", 1, 256)
+    counts, walked = ix.match_longest_prefix(hashes, 2)
+    assert len(hashes) == 2 and list(counts) == [0, 0] and walked == 0    # plugin_test.go:37-82
+
+
+def test_prerequest_then_partial_match(orc):
+    """plugin_test.go:174-226: index 'aaaaaa' for pod1 (primary) and pod3 (prefill); 'aaaabbbb' then
+    matches 1/2 on pod1 and pod3, 0/2 on pod2."""
+    ix = orc.Indexer()
+    h1 = orc.hash_prompt(b"aaaaaa", b"test-model1", 1, 256)
+    ix.add(h1, 0)
+    ix.add(h1, 2)
+    h3 = orc.hash_prompt(b"aaaabbbb", b"test-model1", 1, 256)
+    counts, walked = ix.match_longest_prefix(h3, 3)
+    assert list(counts) == [1, 0, 1] and walked == 1 and len(h3) == 2
+
+
+def test_indexer_add_and_get(orc):
+    ix = orc.Indexer(3)                    # indexer_test.go:27-55: server limit 2 beats default 3
+    ix.add([1], 7, 2)
+    assert ix.lru_len(7) == 1 and ix.get(1) == {7}
+    ix.add([2], 7, 2)
+    assert ix.lru_len(7) == 2
+    ix.add([3], 7, 2)
+    assert ix.lru_len(7) == 2
+    assert ix.get(4) == set()
+    assert ix.get(1) == set()              # evicted (oldest)
+    assert ix.get(2) == {7} and ix.get(3) == {7}
+
+
+def test_indexer_remove_pod_and_eviction(orc):
+    size = 10                              # indexer_test.go:57-113
+    ix = orc.Indexer(size)
+    for j in range(size):
+        ix.add([j], 1)
+        ix.add([j], 2)
+    assert ix.lru_len(1) == size and ix.lru_len(2) == size
+    for j in range(size):
+        assert ix.get(j) == {1, 2}
+    ix.add([size], 1)                      # evicts hash 0 from server 1
+    assert ix.lru_len(1) == size
+    assert ix.get(0) == {2}
+    ix.remove_pod(2)
+    assert ix.get(0) == set()
+    hs, sv = ix.export()
+    assert len(hs) == size and set(sv.tolist()) == {1}
+    assert ix.pods() == [1]
+
+
+def test_indexer_lru_refresh_and_overflow(orc):
+    ix = orc.Indexer(3)
+    ix.add([1, 2, 3], 0)
+    ix.add([1], 0)                         # refresh 1 -> order (old->new) 2,3,1
+    ix.add([4], 0)                         # evicts 2
+    assert ix.get(2) == set() and ix.get(1) == {0} and ix.get(3) == {0} and ix.get(4) == {0}
+    # len(hashes) > capacity: the second loop re-inserts hashes the LRU just evicted (indexer.go:76-83)
+    ix2 = orc.Indexer(2)
+    ix2.add([10, 11, 12], 5)
+    assert ix2.lru_len(5) == 2
+    assert ix2.get(10) == {5} and ix2.get(11) == {5} and ix2.get(12) == {5}
+
+
+def test_indexer_random_vs_python_restatement(orc):
+    import random
+    rng = random.Random(3)
+    ix = orc.Indexer(5)
+    py = pr.Indexer(5)
+    for step in range(3000):
+        op = rng.random()
+        srv = rng.randrange(6)
+        if op < 0.8:
+            hs = [rng.randrange(40) for _ in range(rng.randint(1, 8))]
+            cap = rng.choice([0, 3, 7])
+            ix.add(hs, srv, cap)
+            py.add(hs, srv, cap)
+        elif op < 0.9:
+            ix.remove_pod(srv)
+            py.remove_pod(srv)
+        if step % 50 == 0:
+            for h in range(40):
+                assert ix.get(h) == py.get(h), (step, h)
+            q = [rng.randrange(40) for _ in range(6)]
+            counts, _ = ix.match_longest_prefix(q, 6)
+            want = py.match_longest_prefix(q)
+            assert {i: int(c) for i, c in enumerate(counts) if c} == want
+
+
+def test_match_global_stop_rule(orc):
+    """the walk stops at the first block NO server holds; a server missing an earlier block
+    still counts later ones (plugin.go:214-230)."""
+    ix = orc.Indexer()
+    ix.load_pairs([100, 101, 102, 101, 102, 104], [0, 0, 0, 1, 1, 1])
+    counts, walked = ix.match_longest_prefix([100, 101, 102, 103, 104], 2)
+    assert list(counts) == [3, 2] and walked == 3
+    # servers outside the candidate range keep the walk alive (App. C.5)
+    ix.load_pairs([103], [9])
+    counts, walked = ix.match_longest_prefix([100, 101, 102, 103, 104], 2)
+    assert list(counts) == [3, 3] and walked == 5
+
+
+# ---- B.1 #21: role filters, filter/bylabel/roles.go:46-70 ----------------------------------------------
+def test_role_filters(orc):
+    L = orc.lib()
+    names = {orc.ROLE_NONE: None, orc.ROLE_DECODE: "decode", orc.ROLE_PREFILL: "prefill",
+             orc.ROLE_PREFILL_DECODE: "prefill-decode", orc.ROLE_BOTH: "both", orc.ROLE_ENCODE: "encode",
+             orc.ROLE_ENCODE_PREFILL: "encode-prefill", orc.ROLE_ENCODE_PREFILL_DECODE: "encode-prefill-decode",
+             orc.ROLE_OTHER: "something-else"}
+    for fk, fname in ((orc.FILTER_DECODE, "decode"), (orc.FILTER_PREFILL, "prefill"), (orc.FILTER_ENCODE, "encode"),
+                      (orc.FILTER_NONE, "none")):
+        for role, label in names.items():
+            assert bool(L.orc_role_filter_keeps(fk, role)) == pr.role_filter(fname, label), (fname, label)
+        assert not L.orc_role_filter_keeps(fk, orc.ROLE_ABSENT)
+    assert L.orc_role_filter_keeps(orc.FILTER_DECODE, orc.ROLE_NONE)         # unlabeled pod serves decode
+    assert not L.orc_role_filter_keeps(orc.FILTER_PREFILL, orc.ROLE_NONE)
+    assert not L.orc_role_filter_keeps(orc.FILTER_DECODE, orc.ROLE_PREFILL)
+
+
+# ---- B.1 #22: disagg/prefix_based_pd_decider_test.go:203-265 -------------------------------------------
+@pytest.mark.parametrize("nct,tokens,match,want", [
+    (0, 10, 5, False),     # threshold zero disables
+    (20, 10, 0, False),    # input shorter than threshold
+    (5, 10, 8, False),     # non-cached suffix below threshold
+    (5, 10, 5, True),      # suffix equals threshold
+    (3, 10, 2, True),      # suffix above threshold
+    (1, 10, 10, False),    # fully cached
+    (5, 10, 0, True),      # no hit
+])
+def test_pd_decider(orc, nct, tokens, match, want):
+    # makeRequestWithTokens(n): prompt of n*4 chars; makeTestEndpoint(m): matchBlocks=m, blockSizeTokens=1
+    assert orc.pd_decide(nct, tokens * 4, match, 1) is want
+    assert pr.pd_decide(nct, tokens * 4, match, 1) is want
+
+
+# ---- B.1 #23: TestPDSchedule, disagg/scheduler_test.go:34-297 ------------------------------------------
+def _pd_profiles(orc):
+    prefill = orc.make_profile(orc.FILTER_PREFILL, [(orc.SCORER_PREFIX, 50.0, 0)])
+    decode = orc.make_profile(orc.FILTER_DECODE, [(orc.SCORER_LOAD_AWARE, 1.0, 128), (orc.SCORER_PREFIX, 0.0, 0)])
+    return decode, prefill
+
+
+def _pd(orc, roles, waiting, prompt, cached):
+    decode, prefill = _pd_profiles(orc)
+    pool = _pool(orc, role=roles, waiting=waiting)
+    tokens = len(prompt) // 4
+    match = [tokens if cached else 0] * len(roles)
+    return orc.schedule(decode, prefill, pool, match, tokens, 1, len(prompt), 2)
+
+
+def test_pd_schedule(orc):
+    P, D, N = orc.ROLE_PREFILL, orc.ROLE_DECODE, orc.ROLE_NONE
+    # one decode endpoint, long prompt -> decode only? no prefill candidates: prefill run fails, tolerated
+    d = _pd(orc, [D], [0], "12345678901", False)
+    assert (d.status, d.pick, d.prefill_pick) == (0, 0, -1)
+    # one prefill endpoint -> error (no decode workers)
+    d = _pd(orc, [P], [0], "12345678901", False)
+    assert d.status == -1
+    # 1P1D long prompt -> decode=ep2(idx1), prefill=ep1(idx0); second call fully cached -> decode only
+    d = _pd(orc, [P, D], [0, 0], "12345678906", False)
+    assert (d.status, d.pick, d.prefill_pick) == (0, 1, 0)
+    d = _pd(orc, [P, D], [0, 0], "12345678906", True)
+    assert (d.status, d.pick, d.prefill_pick, d.prefill_ran) == (0, 1, -1, 0)
+    # 1P1D short prompt ("12345" -> 1 token < NCT 2) -> decode only
+    d = _pd(orc, [P, D], [0, 0], "12345", False)
+    assert (d.status, d.pick, d.prefill_pick) == (0, 1, -1)
+    # TestRolesWithNoDecode: unlabeled pod serves decode, ep1 prefill
+    d = _pd(orc, [P, N], [0, 2], "12345678901", False)
+    assert (d.status, d.pick, d.prefill_pick) == (0, 1, 0)
+    # 1P2D: ep2 (q0 -> 0.5) beats unlabeled (q2 -> 0.4921875)
+    d = _pd(orc, [P, D, N], [0, 0, 2], "1234567890123456789012345678901234567890", False)
+    assert (d.status, d.pick, d.prefill_pick) == (0, 1, 0)
+    assert d.score == 0.5
+    d = _pd(orc, [P, D, N], [0, 0, 2], "1234567890123456789012345678901234567890", True)
+    assert (d.status, d.pick, d.prefill_pick) == (0, 1, -1)
+    scores, _, _, _ = orc.profile_run(_pd_profiles(orc)[0], _pool(orc, role=[P, D, N], waiting=[0, 0, 2]), [0] * 3, 10)
+    assert scores[2] == 0.4921875
+
+
+# ---- B.1 #25: ext-proc end-to-end pick, test/integration/epp/common_tests.go:287-300 -------------------
+def test_integration_select_lower_queue_and_kv(orc):
+    # pods (q,kv) (3,0.2) (0,0.1) (10,0.2); default config queue 2 / kv 2 / prefix 3 (defaults.go:47-49)
+    pool = _pool(orc, kv=[0.2, 0.1, 0.2], waiting=[3, 0, 10])
+    prof = orc.make_profile(orc.FILTER_NONE, [(orc.SCORER_QUEUE, 2.0, 0), (orc.SCORER_KV_UTIL, 2.0, 0),
+                                              (orc.SCORER_PREFIX, 3.0, 0)])
+    _, _, pick, aset = orc.profile_run(prof, pool, [0, 0, 0], 0)
+    assert pick == 1 and aset == [1]
+
+
+# ---- cross-check profile_run against the independent Python restatement --------------------------------
+def test_profile_run_random_vs_python_restatement(orc):
+    import random
+    rng = random.Random(11)
+    kinds = {orc.SCORER_PREFIX: "prefix", orc.SCORER_KV_UTIL: "kv", orc.SCORER_QUEUE: "queue",
+             orc.SCORER_LOAD_AWARE: "load", orc.SCORER_RUNNING: "running"}
+    labels = {orc.ROLE_NONE: None, orc.ROLE_DECODE: "decode", orc.ROLE_PREFILL: "prefill",
+              orc.ROLE_BOTH: "both", orc.ROLE_ENCODE: "encode"}
+    fnames = {orc.FILTER_NONE: "none", orc.FILTER_DECODE: "decode", orc.FILTER_PREFILL: "prefill"}
+    for _ in range(200):
+        n = rng.randint(1, 40)
+        roles = [rng.choice(list(labels)) for _ in range(n)]
+        kv = [rng.choice([0.0, 1.0, rng.random(), rng.randrange(1001) / 1000.0]) for _ in range(n)]
+        waiting = [rng.choice([0, 0, rng.randint(1, 200)]) for _ in range(n)]
+        running = [rng.randint(0, 50) for _ in range(n)]
+        total = rng.choice([0, 1, 7, 256])
+        match = [rng.randint(0, total) for _ in range(n)]
+        sc = [(rng.choice(list(kinds)), rng.choice([0.0, 1.0, 2.0, 3.0, 0.37, 50.0]), rng.choice([0, 10, 128]))
+              for _ in range(rng.randint(1, 5))]
+        fk = rng.choice(list(fnames))
+        pool = _pool(orc, role=roles, kv=kv, waiting=waiting, running=running)
+        scores, mx, pick, aset = orc.profile_run(orc.make_profile(fk, sc), pool, match, total)
+        eps = [{"role": labels[r], "kv": kv[i], "waiting": waiting[i], "running": running[i]} for i, r in enumerate(roles)]
+        want = pr.profile_run(fnames[fk], [(kinds[k], w, p) for k, w, p in sc], eps, match, total)
+        if want is None:
+            assert aset == []
+            continue
+        acc, wmx, wset = want
+        assert mx == wmx and aset == wset and pick == wset[0]
+        for i in range(n):
+            assert scores[i] == (acc[i] if i in acc else -1.0)
