@@ -1,0 +1,278 @@
+/*
+ * epp_engine.h -- C ABI of libepp_engine.so, the B200-native Endpoint-Picker scoring engine.
+ *
+ * The reference (llm-d/llm-d-inference-scheduler @ 520af478, pure Go, CGO_ENABLED=0) has NO FFI; this
+ * header is the boundary the build introduces.  Every entry point names the reference
+ * interface it replaces (file:line relative to the reference root).  A thin cgo shim (go/eppcuda/,
+ * INTEGRATION.md) binds exactly these symbols and keeps the Go plugin interfaces unchanged:
+ *
+ *   requestcontrol.DataProducer.Produce   pkg/epp/framework/interface/requestcontrol/plugins.go:69-72
+ *   scheduling.Filter / Scorer / Picker    pkg/epp/framework/interface/scheduling/plugins.go:59-78
+ *   requestcontrol.PreRequest              pkg/epp/framework/interface/requestcontrol/plugins.go:36-39
+ *   Scheduler.Schedule                     pkg/epp/scheduling/scheduler.go:54-102
+ *
+ * Conventions: plain C, no exceptions cross the boundary.  Every function returns int32_t: 0 = EPP_OK,
+ * negative = epp_status error; epp_last_error() returns a thread-local message.  The caller owns every
+ * host buffer and may free it on return (cgo forbids retaining Go pointers); the engine owns all device
+ * memory.  Every entry point is thread-safe (calls on one engine are serialised internally; goroutines
+ * should batch requests before calling).  Handles are opaque.
+ *
+ * Endpoint identity: the reference keys servers by NamespacedName strings.  The shim maps each endpoint
+ * to a dense SLOT id in [0, max_endpoints); all arrays below are indexed by slot id.
+ *
+ * Batch semantics: the reference schedules one request at a time; a batch evaluates
+ * all R requests against ONE frozen snapshot (pool state + prefix index).  Index updates (PreRequest)
+ * are applied between batches.
+ *
+ * Tie rule: the reference's max-score picker returns a uniformly random member of the arg-max set
+ * (picker/maxscore/picker.go:91-102).  The engine returns the LOWEST slot id of that set, the bit pattern
+ * of the max score and the size of the set.
+ */
+#ifndef EPP_ENGINE_H
+#define EPP_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define EPP_API __attribute__((visibility("default")))
+#else
+#define EPP_API
+#endif
+
+#define EPP_ABI_VERSION 1
+#define EPP_MAX_SCORERS 8
+#define EPP_NO_ENDPOINT 0xFFFFFFFFu
+
+typedef struct epp_engine epp_engine;
+
+typedef enum {
+    EPP_OK = 0,
+    EPP_ERR_INVALID = -1,     /* bad argument / configuration                                       */
+    EPP_ERR_CUDA = -2,        /* a CUDA runtime call failed (message has the CUDA error string)     */
+    EPP_ERR_NO_DEVICE = -3,   /* no usable CUDA device: the engine NEVER falls back to a CPU path   */
+    EPP_ERR_CAPACITY = -4,    /* batch / index larger than the configured or available capacity     */
+    EPP_ERR_STATE = -5,       /* call order violation (e.g. schedule before pool_set)               */
+    EPP_ERR_NCCL = -6
+} epp_status;
+
+/* Scorer kinds (plugin type strings of the reference in comments). */
+typedef enum {
+    EPP_SCORER_PREFIX = 0,     /* "prefix-cache-scorer"          scorer/prefix/plugin.go:95-117               */
+    EPP_SCORER_KV_UTIL = 1,    /* "kv-cache-utilization-scorer"  scorer/kvcacheutilization/kvcache_utilization.go:76-82 */
+    EPP_SCORER_QUEUE = 2,      /* "queue-scorer"                 scorer/queuedepth/queue.go:78-108            */
+    EPP_SCORER_LOAD_AWARE = 3, /* "load-aware-scorer"            scorer/loadaware/load_aware.go:84-100; param = threshold */
+    EPP_SCORER_EXTERNAL = 4,   /* host-computed per-endpoint column (param = column index): lets the Go
+                                  side keep any other Scorer (lora-affinity, session-affinity, ...) */
+    EPP_SCORER_RUNNING = 5     /* "running-requests-size-scorer" scorer/runningrequests/runningrequest.go:78-108 */
+} epp_scorer_kind;
+
+/* Value of the llm-d.ai/role label (filter/bylabel/roles.go:25-44). */
+typedef enum {
+    EPP_ROLE_NONE = 0,         /* label absent */
+    EPP_ROLE_DECODE = 1,
+    EPP_ROLE_PREFILL = 2,
+    EPP_ROLE_PREFILL_DECODE = 3,
+    EPP_ROLE_BOTH = 4,
+    EPP_ROLE_ENCODE = 5,
+    EPP_ROLE_ENCODE_PREFILL = 6,
+    EPP_ROLE_ENCODE_PREFILL_DECODE = 7,
+    EPP_ROLE_OTHER = 8         /* label present, value not in the tables */
+} epp_role;
+
+/* Role filters (filter/bylabel/roles.go:46-70, filter.go:104-117). */
+typedef enum {
+    EPP_FILTER_NONE = 0,
+    EPP_FILTER_DECODE = 1,     /* "decode-filter": decode, prefill-decode, both, encode-prefill-decode, or no label */
+    EPP_FILTER_PREFILL = 2,    /* "prefill-filter": prefill, encode-prefill, prefill-decode, both, e-p-d; label required */
+    EPP_FILTER_ENCODE = 3      /* "encode-filter": encode, encode-prefill, e-p-d; label required */
+} epp_filter_kind;
+
+/* Profile handlers. */
+typedef enum {
+    EPP_HANDLER_SINGLE = 0,    /* profilehandler/single/single_profile_handler.go:66-99     */
+    EPP_HANDLER_DISAGG = 1     /* profilehandler/disagg/disagg_profile_handler.go:246-354 (decode -> decider -> prefill) */
+} epp_handler_kind;
+
+typedef struct {
+    int32_t kind;              /* epp_scorer_kind */
+    int32_t reserved;
+    double weight;             /* WeightedScorer.weight, scheduling/weighted_scorer.go:24-40 */
+    double param;
+} epp_scorer_cfg;
+
+/* One SchedulerProfile (scheduling/scheduler_profile.go:117-128): role filter -> scorers IN ORDER ->
+ * max-score picker (k = 1). */
+typedef struct {
+    int32_t filter;            /* epp_filter_kind */
+    int32_t n_scorers;
+    epp_scorer_cfg scorers[EPP_MAX_SCORERS];
+} epp_profile_cfg;
+
+/* Mirrors the EndpointPickerConfig fields that define this path (apix/config/v1alpha1, and
+ * approximateprefix/types.go:78-142 for the prefix producer defaults). */
+typedef struct {
+    uint32_t struct_size;          /* sizeof(epp_config), for ABI evolution                              */
+    int32_t device;                /* CUDA device ordinal                                                */
+    int32_t max_endpoints;         /* slot-id capacity                                                   */
+    int32_t block_size_tokens;     /* blockSizeTokens (default 16); block bytes = 4 * this (hashing.go:49) */
+    int32_t max_prefix_blocks;     /* maxPrefixBlocksToMatch (default 256)                               */
+    int32_t lru_capacity_per_server; /* lruCapacityPerServer (default 31250)                             */
+    int32_t handler;               /* epp_handler_kind                                                   */
+    int32_t always_disagg;         /* always-disagg-pd-decider (always_disagg_pd_decider.go:48-50)        */
+    int64_t non_cached_tokens;     /* prefix-based-pd-decider nonCachedTokens (0 disables)               */
+    int32_t n_ext_cols;            /* number of EPP_SCORER_EXTERNAL columns                              */
+    int32_t reserved0;
+    epp_profile_cfg primary;       /* the single profile, or the decode profile under EPP_HANDLER_DISAGG */
+    epp_profile_cfg prefill;       /* the prefill profile (EPP_HANDLER_DISAGG only)                      */
+    uint64_t reserved1[4];
+} epp_config;
+
+/* One routing decision (32 bytes).  status: 0 = ok, -1 = no endpoint available for the primary profile
+ * (Schedule error: scheduler_profile.go:119-121 / disagg_profile_handler.go:335-338). */
+typedef struct {
+    int32_t status;
+    uint32_t pick;             /* primary (decode) pick: lowest slot id of the arg-max set, or EPP_NO_ENDPOINT */
+    double score;              /* max weighted score (bit-exact vs the reference arithmetic)        */
+    uint32_t prefill_pick;     /* prefill pick, EPP_NO_ENDPOINT when the prefill stage did not run / found nobody */
+    uint32_t tie_count;        /* size of the primary arg-max set                                   */
+    int32_t total_blocks;      /* PrefixCacheMatchInfo.totalBlocks (= number of prefix hashes)      */
+    int32_t match_blocks;      /* PrefixCacheMatchInfo.matchBlocks of the primary pick              */
+} epp_decision;
+
+/* Optional second record per decision (16 bytes), for tests and metrics. */
+typedef struct {
+    double prefill_score;
+    uint32_t prefill_tie_count;
+    uint32_t prefill_ran;      /* the decider asked for the prefill stage                            */
+} epp_decision_detail;
+
+#define EPP_BATCH_DEVICE_PTRS 1u   /* data / offsets / model_ids and all outputs are DEVICE pointers */
+
+/* A batch of prompts.  Prompt r is data[offsets[r] .. offsets[r+1]) (bytes).  A uint32 token array viewed
+ * as little-endian bytes is a prompt with 4 bytes/token (hashing.go:49, types.go:113). */
+typedef struct {
+    int64_t n_requests;
+    const void *data;
+    const uint64_t *offsets;       /* [n_requests+1]; NULL => uniform: prompt r = data[r*uniform_len ..) */
+    uint64_t uniform_len;
+    const uint32_t *model_ids;     /* [n_requests] ids from epp_model_register; NULL => model 0       */
+    uint32_t flags;                /* EPP_BATCH_* */
+    uint32_t reserved;
+} epp_batch;
+
+typedef struct {
+    uint64_t n_batches, n_decisions;
+    uint64_t index_pairs, index_hashes, index_slots;   /* device table occupancy */
+    double last_h2d_ms, last_kernels_ms, last_d2h_ms;  /* CUDA-event times of the last batch */
+    double last_hash_ms, last_match_pick_ms;
+    uint64_t last_kernel_launches;
+    uint64_t device_bytes;
+    /* device-pointer batches only: CUDA-event time of each kernel of the last batch on the launch stream.
+     * [0] prompt lengths  [1] block digests (dominant: reads every token once)  [2] chain  [3] match+score+pick */
+    double last_kernel_ms[8];
+    /* algorithmic work of the last batch: table probes P = sum_r min(stop_r+1, B_r) and
+     * postings consumed M = sum_r sum_{i<stop_r} |servers(h_i)| */
+    uint64_t last_probes, last_postings;
+} epp_stats;
+
+/* ---- lifecycle --------------------------------------------------------------------------------- */
+EPP_API int32_t epp_abi_version(void);
+EPP_API const char *epp_last_error(void);
+/* plugin factories + EndpointPickerConfig (framework/interface/plugin/registry.go:25-30). */
+EPP_API int32_t epp_engine_create(const epp_config *cfg, epp_engine **out);
+EPP_API int32_t epp_engine_destroy(epp_engine *h);
+EPP_API void epp_config_default(epp_config *cfg);   /* types.go:136-142 + config/loader/defaults.go:47-49,78-87 */
+
+/* Pinned host staging buffers for the shim (C memory, so cgo may keep them). */
+EPP_API int32_t epp_host_alloc(size_t bytes, void **out);
+EPP_API int32_t epp_host_free(void *p);
+
+/* request.TargetModel (+ Body.CacheSalt()): registers the seed h_{-1} = XXH64(model || salt)
+ * (hashing.go:71-78), computed on the device.  Returns a small id used in epp_batch.model_ids. */
+EPP_API int32_t epp_model_register(epp_engine *h, const uint8_t *model, size_t model_len, const uint8_t *salt,
+                           size_t salt_len, uint32_t *out_model_id);
+EPP_API int32_t epp_model_seed(epp_engine *h, uint32_t model_id, uint64_t *out_seed);
+
+/* ---- pool state (fwkdl.Metrics framework/interface/datalayer/metrics.go:26-42, EndpointMetadata.Labels) --
+ * Replaces the snapshot (called by the 50 ms scrape loop).  n entries; ids[i] is the slot id of entry i;
+ * slots not listed are absent from the pool.  role: epp_role.  ext may be NULL when n_ext_cols == 0, else
+ * [n_ext_cols][n].  Also derives, ON THE DEVICE, every request-independent quantity of the scorers
+ * (queue min/max over each profile's candidates, per-scorer contributions, ordered base sums). */
+EPP_API int32_t epp_pool_set(epp_engine *h, int32_t n, const uint32_t *ids, const uint8_t *role, const double *kv_usage,
+                     const int32_t *waiting, const int32_t *running, const double *ext);
+
+/* ---- prefix index write side (approximateprefix/indexer.go:52-83, 105-115, 167-182; plugin.go:164-211) --
+ * Host mirror with the reference's per-server LRU semantics; the device table is rebuilt by
+ * epp_index_commit (also called implicitly by the next lookup when dirty). */
+EPP_API int32_t epp_index_add(epp_engine *h, uint32_t ep, int32_t n, const uint64_t *hashes, int32_t num_gpu_blocks);
+EPP_API int32_t epp_index_remove_endpoint(epp_engine *h, uint32_t ep);
+/* Bulk-replace the index with a frozen snapshot of UNIQUE-or-not (hash, endpoint) pairs (host pointers);
+ * bypasses LRU bookkeeping.  Duplicates are removed on the device. */
+EPP_API int32_t epp_index_load_snapshot(epp_engine *h, uint64_t n_pairs, const uint64_t *hashes, const uint32_t *eps);
+EPP_API int32_t epp_index_commit(epp_engine *h);
+/* indexer.Get (indexer.go:86-102), read from the DEVICE table; returns the set size in *out_n. */
+EPP_API int32_t epp_index_get(epp_engine *h, uint64_t hash, uint32_t *out_eps, int32_t cap, int32_t *out_n);
+
+/* ---- a1: hashPrompt (approximateprefix/hashing.go:35-99) -----------------------------------------
+ * out_hashes: [R][max_prefix_blocks] (row-major, unused tail undefined); out_nblocks: [R]. */
+EPP_API int32_t epp_hash_prompts(epp_engine *h, const epp_batch *batch, uint64_t *out_hashes, int32_t *out_nblocks);
+
+/* ---- a1-a4: Produce (approximateprefix/plugin.go:135-160) -- plugin-parity mode ---------------------
+ * out_match: dense [R][max_endpoints] matchBlocks (0 for unmatched); out_total: [R] totalBlocks. */
+EPP_API int32_t epp_prefix_match(epp_engine *h, const epp_batch *batch, int32_t *out_match, int32_t *out_total);
+
+/* ---- a5-a9: Scorer.Score / runScorerPlugins (scheduler_profile.go:151-174) -- plugin-parity mode ----
+ * match: [R][max_endpoints], total: [R] (as produced by epp_prefix_match or injected by a test).
+ * profile: 0 = primary, 1 = prefill.  scorer_index >= 0: raw column of that scorer (what Scorer.Score
+ * returns, 0 for non-candidates); -1: weighted, clamped, ordered sum (-1.0 for filtered-out endpoints).
+ * out_scores: [R][max_endpoints].  flags: EPP_BATCH_DEVICE_PTRS. */
+EPP_API int32_t epp_score(epp_engine *h, int64_t n_requests, const int32_t *match, const int32_t *total,
+                  int32_t profile, int32_t scorer_index, double *out_scores, uint32_t flags);
+
+/* ---- a1-a14 fused: Scheduler.Schedule for a batch (scheduling/scheduler.go:54-102) ---------------
+ * out: [R]; detail: [R] or NULL; keep_hashes != 0 keeps the batch's prefix hashes resident on the device
+ * for epp_index_add_picked (the PluginState stash of plugin.go:150-157). */
+EPP_API int32_t epp_schedule(epp_engine *h, const epp_batch *batch, epp_decision *out, epp_decision_detail *detail,
+                     int32_t keep_hashes);
+
+/* Same decision logic with PrefixCacheMatchInfo injected by the caller (how the reference's own scheduler
+ * tests drive it: disagg/scheduler_test.go:264-268): match [R][max_endpoints], total [R],
+ * input_len_bytes [R] (prompt length for the P/D decider), block_size_tokens override (0 = config). */
+EPP_API int32_t epp_schedule_with_match(epp_engine *h, int64_t n_requests, const int32_t *match, const int32_t *total,
+                                const int64_t *input_len_bytes, int32_t block_size_tokens, epp_decision *out,
+                                epp_decision_detail *detail, uint32_t flags);
+
+/* PreRequest (approximateprefix/plugin.go:164-200): index the hashes of the LAST epp_schedule batch
+ * (keep_hashes=1) for each request's primary pick and prefill pick. */
+EPP_API int32_t epp_index_add_picked(epp_engine *h);
+
+EPP_API int32_t epp_get_stats(epp_engine *h, epp_stats *out);
+
+/* ---- endpoint-sharded multi-GPU mode ----------------------------------------------
+ * Each rank holds the postings of the endpoints of its shard and the full pool state.  Phase 1 probes
+ * the local table and produces per-request block-presence masks (ceil(max_prefix_blocks/32) words per
+ * request); the caller ORs the masks of all ranks (NCCL all-gather / bitwise OR); phase 2 applies the
+ * global stop rule (plugin.go:219-223), counts local matches and returns the local best record; the caller
+ * all-gathers the records and epp_shard_merge reduces them.  All pointers are DEVICE pointers. */
+typedef struct {
+    double score;
+    uint32_t pick;
+    uint32_t tie_count;
+    int32_t match_blocks;
+    int32_t status;            /* 0 = this shard has a candidate, -1 = none */
+} epp_shard_best;              /* 24 bytes */
+EPP_API int32_t epp_shard_set(epp_engine *h, uint32_t ep_begin, uint32_t ep_end);
+EPP_API int32_t epp_shard_probe(epp_engine *h, const epp_batch *batch, uint32_t *out_masks);
+EPP_API int32_t epp_shard_pick(epp_engine *h, int64_t n_requests, const uint32_t *global_masks, epp_shard_best *out_best);
+EPP_API int32_t epp_shard_merge(epp_engine *h, int64_t n_requests, int32_t n_ranks, const epp_shard_best *all_best,
+                        epp_decision *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

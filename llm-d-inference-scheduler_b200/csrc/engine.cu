@@ -1,0 +1,946 @@
+// engine.cu -- the C ABI of libepp_engine.so (include/epp_engine.h) and the host logic above the kernels:
+// configuration, pool-state snapshot, prefix-index mirror + device table, batch staging (H2D / D2H pipelined
+// against the kernels on two streams) and the per-batch launch sequence.
+//
+// There is NO CPU compute path in this file: without a CUDA device epp_engine_create fails with
+// EPP_ERR_NO_DEVICE, and every data-path entry point only stages buffers and launches kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "index_mirror.h"
+#include "kernels.h"
+
+using namespace epp;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int32_t fail(int32_t code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(EPP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define EPP_TRY(expr)            \
+    do {                         \
+        int32_t _r = (expr);     \
+        if (_r != EPP_OK) return _r; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// device buffers
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    // Grows (never shrinks); contents are NOT preserved.
+    cudaError_t reserve(size_t bytes, size_t *accounted) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); if (accounted) *accounted -= cap; p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&p, want); }
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        if (accounted) *accounted += cap;
+        return cudaSuccess;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct ProfileState {
+    DevBuf cand, contrib, base, order, grp_size, sort_key, n_cand, qminmax;
+};
+
+struct Slot {                       // per-stream staging for host-pointer batches
+    cudaStream_t stream = nullptr;
+    DevBuf data;
+    cudaEvent_t done = nullptr;
+};
+
+struct epp_engine {
+    std::mutex mu;
+    epp_config cfg;
+    int n_profiles = 1;
+    int sm_count = 148;
+    int32_t Epad = 0;
+    size_t dev_bytes = 0;
+    size_t max_smem_optin = 0;
+
+    Slot slot[2];
+    cudaEvent_t ev[8] = {};
+    DevBuf work_counters;           // u64[2] probes, postings
+
+    // models
+    DevBuf seeds;                   // u64[kMaxModels]
+    DevBuf seed_msg;
+    int n_models = 0;
+    std::vector<uint64_t> host_seeds;
+
+    // pool state
+    bool pool_ready = false;
+    DevBuf role, kv, waiting, running, ext;
+    ProfileState prof[kMaxProfiles];
+
+    // index
+    std::unique_ptr<IndexMirror> mirror;
+    bool snapshot_mode = false;
+    DevBuf slots, postings, idx_scratch, idx_cursor, idx_special, pair_hash, pair_ep, get_out;
+    uint64_t idx_capacity = 0, idx_pairs = 0;
+    IndexSlot idx_special_host{};
+    uint32_t shard_begin = 0, shard_end = 0xFFFFFFFFu;
+
+    // batch buffers (sized for the largest batch seen)
+    DevBuf offsets, model_ids, hashes, nblocks, eff_len, in_len, decisions, details, flag;
+    DevBuf dense_match, dense_total, dense_scores;
+    DevBuf pick_scratch;            // global match counters when E is too large for shared memory
+    int pick_grid = 0;
+    bool pick_global = false;
+    size_t pick_smem = 0;
+    int64_t kept_R = 0;             // rows of `hashes` valid for epp_index_add_picked
+    std::vector<epp_decision> kept_decisions;
+
+    epp_stats stats{};
+};
+
+static constexpr int kMaxModels = 4096;
+
+static int32_t set_device(epp_engine *e) {
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    return EPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// config
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t epp_abi_version(void) { return EPP_ABI_VERSION; }
+extern "C" const char *epp_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" void epp_config_default(epp_config *cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->struct_size = sizeof(epp_config);
+    cfg->device = 0;
+    cfg->max_endpoints = 4096;
+    cfg->block_size_tokens = 16;            // types.go:92
+    cfg->max_prefix_blocks = 256;           // types.go:99
+    cfg->lru_capacity_per_server = 31250;   // types.go:110
+    cfg->handler = EPP_HANDLER_SINGLE;
+    // config/loader/defaults.go:47-49, 78-87: queue 2, kv-cache-utilization 2, prefix 3 -- in that order
+    cfg->primary.filter = EPP_FILTER_NONE;
+    cfg->primary.n_scorers = 3;
+    cfg->primary.scorers[0] = {EPP_SCORER_QUEUE, 0, 2.0, 0.0};
+    cfg->primary.scorers[1] = {EPP_SCORER_KV_UTIL, 0, 2.0, 0.0};
+    cfg->primary.scorers[2] = {EPP_SCORER_PREFIX, 0, 3.0, 0.0};
+}
+
+static int32_t validate_profile(const epp_profile_cfg &p, int n_ext, const char *name) {
+    if (p.filter < EPP_FILTER_NONE || p.filter > EPP_FILTER_ENCODE) return fail(EPP_ERR_INVALID, "%s: bad filter %d", name, p.filter);
+    if (p.n_scorers < 0 || p.n_scorers > EPP_MAX_SCORERS) return fail(EPP_ERR_INVALID, "%s: n_scorers %d out of range", name, p.n_scorers);
+    for (int s = 0; s < p.n_scorers; s++) {
+        const epp_scorer_cfg &sc = p.scorers[s];
+        if (sc.kind < EPP_SCORER_PREFIX || sc.kind > EPP_SCORER_RUNNING) return fail(EPP_ERR_INVALID, "%s: scorer %d has unknown kind %d", name, s, sc.kind);
+        if (!std::isfinite(sc.weight)) return fail(EPP_ERR_INVALID, "%s: scorer %d weight is not finite", name, s);
+        if (sc.kind == EPP_SCORER_EXTERNAL && (sc.param < 0 || sc.param >= n_ext)) return fail(EPP_ERR_INVALID, "%s: scorer %d external column %g out of range [0,%d)", name, s, sc.param, n_ext);
+    }
+    return EPP_OK;
+}
+
+static int32_t alloc_profile(epp_engine *e, ProfileState &ps) {
+    size_t E = (size_t)e->cfg.max_endpoints, Ep = (size_t)e->Epad;
+    CUDA_TRY(ps.cand.reserve(E, &e->dev_bytes));
+    CUDA_TRY(ps.contrib.reserve(sizeof(double) * EPP_MAX_SCORERS * E, &e->dev_bytes));
+    CUDA_TRY(ps.base.reserve(sizeof(double) * E, &e->dev_bytes));
+    CUDA_TRY(ps.order.reserve(sizeof(uint32_t) * Ep, &e->dev_bytes));
+    CUDA_TRY(ps.grp_size.reserve(sizeof(uint32_t) * Ep, &e->dev_bytes));
+    CUDA_TRY(ps.sort_key.reserve(sizeof(uint64_t) * Ep, &e->dev_bytes));
+    CUDA_TRY(ps.n_cand.reserve(sizeof(int32_t) * 4, &e->dev_bytes));
+    CUDA_TRY(ps.qminmax.reserve(sizeof(int64_t) * 4, &e->dev_bytes));
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
+    if (!cfg || !out) return fail(EPP_ERR_INVALID, "cfg/out is NULL");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(epp_config)) return fail(EPP_ERR_INVALID, "epp_config.struct_size %u != %zu (ABI mismatch)", cfg->struct_size, sizeof(epp_config));
+    if (cfg->max_endpoints <= 0 || cfg->max_endpoints > (1 << 24)) return fail(EPP_ERR_INVALID, "max_endpoints %d out of range", cfg->max_endpoints);
+    if (cfg->block_size_tokens <= 0 || cfg->block_size_tokens > (1 << 20)) return fail(EPP_ERR_INVALID, "block_size_tokens %d must be > 0 (plugin.go:75-77)", cfg->block_size_tokens);
+    if (cfg->max_prefix_blocks <= 0 || cfg->max_prefix_blocks > 65535) return fail(EPP_ERR_INVALID, "max_prefix_blocks %d out of range [1,65535]", cfg->max_prefix_blocks);
+    if (cfg->lru_capacity_per_server <= 0) return fail(EPP_ERR_INVALID, "lru_capacity_per_server must be > 0");
+    if (cfg->handler != EPP_HANDLER_SINGLE && cfg->handler != EPP_HANDLER_DISAGG) return fail(EPP_ERR_INVALID, "bad handler %d", cfg->handler);
+    if (cfg->n_ext_cols < 0 || cfg->n_ext_cols > 64) return fail(EPP_ERR_INVALID, "n_ext_cols %d out of range", cfg->n_ext_cols);
+    if (cfg->non_cached_tokens < 0) return fail(EPP_ERR_INVALID, "non_cached_tokens must be >= 0");
+    EPP_TRY(validate_profile(cfg->primary, cfg->n_ext_cols, "primary profile"));
+    if (cfg->handler == EPP_HANDLER_DISAGG) EPP_TRY(validate_profile(cfg->prefill, cfg->n_ext_cols, "prefill profile"));
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(EPP_ERR_NO_DEVICE, "no CUDA device available (%s); the engine has no CPU fallback", ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(EPP_ERR_INVALID, "device %d out of range [0,%d)", cfg->device, ndev);
+
+    std::unique_ptr<epp_engine> e(new epp_engine());
+    e->cfg = *cfg;
+    e->n_profiles = cfg->handler == EPP_HANDLER_DISAGG ? 2 : 1;
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    e->sm_count = prop.multiProcessorCount;
+    e->max_smem_optin = prop.sharedMemPerBlockOptin;
+    int32_t Ep = 1;
+    while (Ep < cfg->max_endpoints) Ep <<= 1;
+    e->Epad = Ep;
+    for (int i = 0; i < 2; i++) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&e->slot[i].stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&e->slot[i].done, cudaEventDisableTiming));
+    }
+    for (auto &ev : e->ev) CUDA_TRY(cudaEventCreate(&ev));
+    size_t E = (size_t)cfg->max_endpoints;
+    CUDA_TRY(e->seeds.reserve(sizeof(uint64_t) * kMaxModels, &e->dev_bytes));
+    CUDA_TRY(e->seed_msg.reserve(4096, &e->dev_bytes));
+    CUDA_TRY(e->role.reserve(E, &e->dev_bytes));
+    CUDA_TRY(e->kv.reserve(sizeof(double) * E, &e->dev_bytes));
+    CUDA_TRY(e->waiting.reserve(sizeof(int32_t) * E, &e->dev_bytes));
+    CUDA_TRY(e->running.reserve(sizeof(int32_t) * E, &e->dev_bytes));
+    if (cfg->n_ext_cols) CUDA_TRY(e->ext.reserve(sizeof(double) * E * (size_t)cfg->n_ext_cols, &e->dev_bytes));
+    for (int p = 0; p < e->n_profiles; p++) EPP_TRY(alloc_profile(e.get(), e->prof[p]));
+    CUDA_TRY(e->idx_cursor.reserve(sizeof(uint32_t) * 4, &e->dev_bytes));
+    CUDA_TRY(e->idx_special.reserve(sizeof(IndexSlot), &e->dev_bytes));
+    CUDA_TRY(e->get_out.reserve(sizeof(uint32_t) * 4096 + 16, &e->dev_bytes));
+    CUDA_TRY(e->flag.reserve(sizeof(int) * 4, &e->dev_bytes));
+    CUDA_TRY(e->work_counters.reserve(sizeof(unsigned long long) * 2, &e->dev_bytes));
+    e->idx_special_host.key = kEmptyKey;
+    e->idx_special_host.off = 0;
+    e->idx_special_host.cnt = 0;
+    e->mirror.reset(new IndexMirror(cfg->lru_capacity_per_server));
+
+    // match/pick launch geometry: counters in shared memory when they fit, else zeroed global scratch
+    size_t smem_local = match_pick_smem_bytes(cfg->max_endpoints, false);
+    e->pick_global = smem_local > std::min<size_t>(e->max_smem_optin, 200 * 1024);
+    e->pick_smem = match_pick_smem_bytes(cfg->max_endpoints, e->pick_global);
+    int ctas_per_sm = e->pick_global ? 4 : std::max<int>(1, (int)((size_t)(220 * 1024) / (e->pick_smem + 1024)));
+    ctas_per_sm = std::min(ctas_per_sm, 8);
+    e->pick_grid = e->sm_count * ctas_per_sm;
+    if (e->pick_global) {
+        size_t words = (size_t)e->pick_grid * match_pick_warps_per_cta() * (size_t)((cfg->max_endpoints + 1) / 2);
+        CUDA_TRY(e->pick_scratch.reserve(words * sizeof(uint32_t), &e->dev_bytes));
+        CUDA_TRY(cudaMemset(e->pick_scratch.p, 0, words * sizeof(uint32_t)));
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    *out = e.release();
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_engine_destroy(epp_engine *h) {
+    if (!h) return EPP_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; i++) {
+        if (h->slot[i].stream) cudaStreamDestroy(h->slot[i].stream);
+        if (h->slot[i].done) cudaEventDestroy(h->slot[i].done);
+    }
+    for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+    delete h;
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(EPP_ERR_INVALID, "out is NULL");
+    CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return EPP_OK;
+}
+extern "C" int32_t epp_host_free(void *p) {
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return EPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// models: h_{-1} = XXH64(model || salt) on the device (hashing.go:71-78)
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t epp_model_register(epp_engine *h, const uint8_t *model, size_t model_len, const uint8_t *salt,
+                                      size_t salt_len, uint32_t *out_model_id) {
+    if (!h || !out_model_id) return fail(EPP_ERR_INVALID, "NULL argument");
+    if ((model_len && !model) || (salt_len && !salt)) return fail(EPP_ERR_INVALID, "NULL model/salt with non-zero length");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    if (h->n_models >= kMaxModels) return fail(EPP_ERR_CAPACITY, "too many registered models (max %d)", kMaxModels);
+    size_t n = model_len + salt_len;
+    std::vector<uint8_t> msg(n ? n : 1);
+    if (model_len) memcpy(msg.data(), model, model_len);
+    if (salt_len) memcpy(msg.data() + model_len, salt, salt_len);
+    CUDA_TRY(h->seed_msg.reserve(n + 16, &h->dev_bytes));
+    cudaStream_t s = h->slot[0].stream;
+    if (n) CUDA_TRY(cudaMemcpyAsync(h->seed_msg.p, msg.data(), n, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(launch_hash_bytes(h->seed_msg.as<uint8_t>(), n, h->seeds.as<uint64_t>() + h->n_models, s));
+    uint64_t seed = 0;
+    CUDA_TRY(cudaMemcpyAsync(&seed, h->seeds.as<uint64_t>() + h->n_models, sizeof seed, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    h->host_seeds.push_back(seed);
+    *out_model_id = (uint32_t)h->n_models++;
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_model_seed(epp_engine *h, uint32_t model_id, uint64_t *out_seed) {
+    if (!h || !out_seed) return fail(EPP_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if ((int)model_id >= h->n_models) return fail(EPP_ERR_INVALID, "unknown model id %u", model_id);
+    *out_seed = h->host_seeds[model_id];
+    return EPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pool state
+// ------------------------------------------------------------------------------------------------
+static PoolArrays pool_arrays(epp_engine *h) {
+    PoolArrays pa;
+    pa.E = h->cfg.max_endpoints;
+    pa.n_ext_cols = h->cfg.n_ext_cols;
+    pa.role = h->role.as<uint8_t>();
+    pa.kv_usage = h->kv.as<double>();
+    pa.waiting = h->waiting.as<int32_t>();
+    pa.running = h->running.as<int32_t>();
+    pa.ext = h->ext.as<double>();
+    return pa;
+}
+
+static ProfileDev profile_dev(epp_engine *h, int p) {
+    ProfileDev pd;
+    pd.cfg = p == 0 ? h->cfg.primary : h->cfg.prefill;
+    pd.cand = h->prof[p].cand.as<uint8_t>();
+    pd.contrib = h->prof[p].contrib.as<double>();
+    pd.base = h->prof[p].base.as<double>();
+    pd.order = h->prof[p].order.as<uint32_t>();
+    pd.grp_size = h->prof[p].grp_size.as<uint32_t>();
+    pd.n_cand = h->prof[p].n_cand.as<int32_t>();
+    return pd;
+}
+
+extern "C" int32_t epp_pool_set(epp_engine *h, int32_t n, const uint32_t *ids, const uint8_t *role,
+                                const double *kv_usage, const int32_t *waiting, const int32_t *running,
+                                const double *ext) {
+    if (!h) return fail(EPP_ERR_INVALID, "NULL engine");
+    if (n < 0 || (n > 0 && (!ids || !role || !kv_usage || !waiting))) return fail(EPP_ERR_INVALID, "NULL pool arrays");
+    if (h->cfg.n_ext_cols > 0 && n > 0 && !ext) return fail(EPP_ERR_INVALID, "ext columns configured but ext is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    const int32_t E = h->cfg.max_endpoints;
+    std::vector<uint8_t> r(E, 0xFF);
+    std::vector<double> kv(E, 0.0);
+    std::vector<int32_t> w(E, 0), run(E, 0);
+    std::vector<double> ex((size_t)E * (size_t)std::max(1, h->cfg.n_ext_cols), 0.0);
+    for (int32_t i = 0; i < n; i++) {
+        uint32_t id = ids[i];
+        if (id >= (uint32_t)E) return fail(EPP_ERR_INVALID, "pool entry %d: slot id %u >= max_endpoints %d", i, id, E);
+        if (r[id] != 0xFF) return fail(EPP_ERR_INVALID, "pool entry %d: duplicate slot id %u", i, id);
+        if (role[i] > EPP_ROLE_OTHER) return fail(EPP_ERR_INVALID, "pool entry %d: bad role %u", i, role[i]);
+        if (std::isnan(kv_usage[i])) return fail(EPP_ERR_INVALID, "pool entry %d: kv_usage is NaN", i);
+        r[id] = role[i];
+        kv[id] = kv_usage[i];
+        w[id] = waiting[i];
+        run[id] = running ? running[i] : 0;
+        for (int c = 0; c < h->cfg.n_ext_cols; c++) {
+            double v = ext[(size_t)c * (size_t)n + (size_t)i];
+            if (std::isnan(v)) return fail(EPP_ERR_INVALID, "pool entry %d: ext column %d is NaN", i, c);
+            ex[(size_t)c * (size_t)E + id] = v;
+        }
+    }
+    cudaStream_t s = h->slot[0].stream;
+    CUDA_TRY(cudaMemcpyAsync(h->role.p, r.data(), E, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->kv.p, kv.data(), sizeof(double) * E, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->waiting.p, w.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->running.p, run.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
+    if (h->cfg.n_ext_cols)
+        CUDA_TRY(cudaMemcpyAsync(h->ext.p, ex.data(), sizeof(double) * E * (size_t)h->cfg.n_ext_cols, cudaMemcpyHostToDevice, s));
+    PoolArrays pa = pool_arrays(h);
+    int launches = 0;
+    for (int p = 0; p < h->n_profiles; p++) {
+        ProfileDerived d;
+        d.cand = h->prof[p].cand.as<uint8_t>();
+        d.contrib = h->prof[p].contrib.as<double>();
+        d.base = h->prof[p].base.as<double>();
+        d.order = h->prof[p].order.as<uint32_t>();
+        d.grp_size = h->prof[p].grp_size.as<uint32_t>();
+        d.sort_key = h->prof[p].sort_key.as<uint64_t>();
+        d.n_cand = h->prof[p].n_cand.as<int32_t>();
+        d.qminmax = h->prof[p].qminmax.as<int64_t>();
+        CUDA_TRY(launch_pool_prepare(pa, p == 0 ? h->cfg.primary : h->cfg.prefill, d, h->Epad, s, &launches));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    h->pool_ready = true;
+    return EPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prefix index
+// ------------------------------------------------------------------------------------------------
+static int32_t build_device_index(epp_engine *h, const uint64_t *hashes, const uint32_t *eps, uint64_t n,
+                                  uint64_t n_distinct_hint) {
+    cudaStream_t s = h->slot[0].stream;
+    uint64_t want = std::max<uint64_t>(16, 2 * std::max<uint64_t>(1, n_distinct_hint));
+    uint64_t cap = 16;
+    while (cap < want) cap <<= 1;
+    if (n >= 0xFFFFFFF0ull) return fail(EPP_ERR_CAPACITY, "index snapshot of %llu pairs exceeds the u32 posting space", (unsigned long long)n);
+    CUDA_TRY(h->slots.reserve(sizeof(IndexSlot) * cap, &h->dev_bytes));
+    CUDA_TRY(h->idx_scratch.reserve(sizeof(uint32_t) * cap, &h->dev_bytes));
+    CUDA_TRY(h->postings.reserve(sizeof(uint32_t) * std::max<uint64_t>(n, 1), &h->dev_bytes));
+    CUDA_TRY(h->pair_hash.reserve(sizeof(uint64_t) * std::max<uint64_t>(n, 1), &h->dev_bytes));
+    CUDA_TRY(h->pair_ep.reserve(sizeof(uint32_t) * std::max<uint64_t>(n, 1), &h->dev_bytes));
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(h->pair_hash.p, hashes, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(h->pair_ep.p, eps, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
+    }
+    int launches = 0;
+    CUDA_TRY(launch_index_build(h->pair_hash.as<uint64_t>(), h->pair_ep.as<uint32_t>(), n, h->slots.as<IndexSlot>(), cap,
+                                h->postings.as<uint32_t>(), h->idx_scratch.as<uint32_t>(), h->idx_cursor.as<uint32_t>(),
+                                h->idx_special.as<IndexSlot>(), (uint32_t)h->cfg.max_endpoints, s, &launches));
+    CUDA_TRY(cudaMemcpyAsync(&h->idx_special_host, h->idx_special.p, sizeof(IndexSlot), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    h->idx_capacity = cap;
+    h->idx_pairs = n;
+    h->stats.index_pairs = n;
+    h->stats.index_hashes = n_distinct_hint;
+    h->stats.index_slots = cap;
+    return EPP_OK;
+}
+
+static int32_t commit_locked(epp_engine *h) {
+    if (h->snapshot_mode || !h->mirror->dirty()) return EPP_OK;
+    std::vector<uint64_t> hs;
+    std::vector<uint32_t> es;
+    h->mirror->export_pairs(hs, es);
+    EPP_TRY(build_device_index(h, hs.data(), es.data(), hs.size(), h->mirror->n_hashes()));
+    h->mirror->mark_clean();
+    return EPP_OK;
+}
+
+static IndexView index_view(epp_engine *h) {
+    IndexView v;
+    v.slots = h->idx_capacity ? h->slots.as<IndexSlot>() : nullptr;
+    v.postings = h->postings.as<uint32_t>();
+    v.mask = h->idx_capacity ? h->idx_capacity - 1 : 0;
+    v.special = h->idx_special_host;
+    if (!h->idx_capacity) { v.special.cnt = 0; v.special.off = 0; }
+    v.ep_begin = h->shard_begin;
+    v.ep_end = h->shard_end;
+    return v;
+}
+
+extern "C" int32_t epp_index_add(epp_engine *h, uint32_t ep, int32_t n, const uint64_t *hashes, int32_t num_gpu_blocks) {
+    if (!h || n < 0 || (n > 0 && !hashes)) return fail(EPP_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->snapshot_mode) return fail(EPP_ERR_STATE, "index holds a bulk snapshot; incremental adds need an empty or mirror-built index");
+    h->mirror->add(ep, hashes, n, num_gpu_blocks);
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_index_remove_endpoint(epp_engine *h, uint32_t ep) {
+    if (!h) return fail(EPP_ERR_INVALID, "NULL engine");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->snapshot_mode) return fail(EPP_ERR_STATE, "index holds a bulk snapshot; reload it without the endpoint instead");
+    h->mirror->remove_pod(ep);
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_index_load_snapshot(epp_engine *h, uint64_t n_pairs, const uint64_t *hashes, const uint32_t *eps) {
+    if (!h || (n_pairs && (!hashes || !eps))) return fail(EPP_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    h->mirror->clear();
+    h->mirror->mark_clean();
+    EPP_TRY(build_device_index(h, hashes, eps, n_pairs, n_pairs));
+    h->snapshot_mode = n_pairs > 0;
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_index_commit(epp_engine *h) {
+    if (!h) return fail(EPP_ERR_INVALID, "NULL engine");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    return commit_locked(h);
+}
+
+extern "C" int32_t epp_index_get(epp_engine *h, uint64_t hash, uint32_t *out_eps, int32_t cap, int32_t *out_n) {
+    if (!h || !out_n || cap < 0 || (cap > 0 && !out_eps)) return fail(EPP_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    EPP_TRY(commit_locked(h));
+    cudaStream_t s = h->slot[0].stream;
+    int32_t dcap = std::min(cap, 4096);
+    uint32_t *d_eps = h->get_out.as<uint32_t>();
+    int32_t *d_n = reinterpret_cast<int32_t *>(d_eps + 4096);
+    CUDA_TRY(launch_index_get(index_view(h), hash, d_eps, dcap, d_n, s));
+    CUDA_TRY(cudaMemcpyAsync(out_n, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    int32_t ncopy = std::min(*out_n, dcap);
+    if (ncopy > 0) CUDA_TRY(cudaMemcpy(out_eps, d_eps, sizeof(uint32_t) * ncopy, cudaMemcpyDeviceToHost));
+    return EPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batches
+// ------------------------------------------------------------------------------------------------
+struct BatchView {
+    int64_t R = 0;
+    bool device = false;
+    const uint8_t *data = nullptr;
+    const uint64_t *offsets = nullptr;
+    uint64_t uniform_len = 0;
+    const uint32_t *model_ids = nullptr;
+    uint64_t total_bytes = 0;      // host batches only
+    bool aligned16 = false;
+};
+
+static int32_t check_batch(epp_engine *h, const epp_batch *b, BatchView &v) {
+    if (!b) return fail(EPP_ERR_INVALID, "batch is NULL");
+    if (b->n_requests < 0) return fail(EPP_ERR_INVALID, "n_requests < 0");
+    if (h->n_models == 0) return fail(EPP_ERR_STATE, "no model registered (epp_model_register)");
+    v.R = b->n_requests;
+    v.device = (b->flags & EPP_BATCH_DEVICE_PTRS) != 0;
+    v.data = reinterpret_cast<const uint8_t *>(b->data);
+    v.offsets = b->offsets;
+    v.uniform_len = b->uniform_len;
+    v.model_ids = b->model_ids;
+    if (v.R == 0) return EPP_OK;
+    if (!v.offsets && v.uniform_len > 0 && !v.data) return fail(EPP_ERR_INVALID, "data is NULL");
+    if (!v.device) {
+        if (v.offsets) {
+            bool al = true;
+            for (int64_t r = 0; r < v.R; r++) {
+                if (v.offsets[r + 1] < v.offsets[r]) return fail(EPP_ERR_INVALID, "offsets not monotonic at request %lld", (long long)r);
+                if (v.offsets[r] & 15) al = false;
+            }
+            v.aligned16 = al;
+            v.total_bytes = v.offsets[v.R] - v.offsets[0];
+            if (v.total_bytes && !v.data) return fail(EPP_ERR_INVALID, "data is NULL");
+        } else {
+            v.total_bytes = (uint64_t)v.R * v.uniform_len;
+        }
+        if (v.model_ids)
+            for (int64_t r = 0; r < v.R; r++)
+                if ((int)v.model_ids[r] >= h->n_models) return fail(EPP_ERR_INVALID, "request %lld: unknown model id %u", (long long)r, v.model_ids[r]);
+    }
+    return EPP_OK;
+}
+
+static int32_t reserve_batch(epp_engine *h, int64_t R) {
+    size_t B = (size_t)h->cfg.max_prefix_blocks;
+    size_t n = (size_t)std::max<int64_t>(R, 1);
+    CUDA_TRY(h->hashes.reserve(sizeof(uint64_t) * n * B, &h->dev_bytes));
+    CUDA_TRY(h->nblocks.reserve(sizeof(int32_t) * n, &h->dev_bytes));
+    CUDA_TRY(h->eff_len.reserve(sizeof(int64_t) * n, &h->dev_bytes));
+    CUDA_TRY(h->in_len.reserve(sizeof(int64_t) * n, &h->dev_bytes));
+    CUDA_TRY(h->decisions.reserve(sizeof(epp_decision) * n, &h->dev_bytes));
+    CUDA_TRY(h->details.reserve(sizeof(epp_decision_detail) * n, &h->dev_bytes));
+    CUDA_TRY(h->offsets.reserve(sizeof(uint64_t) * (n + 1), &h->dev_bytes));
+    CUDA_TRY(h->model_ids.reserve(sizeof(uint32_t) * n, &h->dev_bytes));
+    return EPP_OK;
+}
+
+// What one launch sequence works on: requests [r0, r1) whose bytes are resident at `data_base + offsets[r]`.
+struct Work {
+    int64_t r0, r1;
+    const uint8_t *data_base;
+    const uint64_t *offsets_dev;   // indexed by absolute request id, or nullptr
+    uint64_t uniform_len;
+    const uint32_t *model_ids_dev; // absolute, or nullptr
+    bool aligned16;
+    uint64_t *hashes_out;          // row r0 of the destination
+    int32_t *nblocks_out;
+};
+
+static HashParams hash_params(epp_engine *h, const Work &w) {
+    HashParams p;
+    int64_t n = w.r1 - w.r0;
+    p.data = w.data_base;
+    p.offsets = w.offsets_dev ? w.offsets_dev + w.r0 : nullptr;
+    p.uniform_len = w.uniform_len;
+    p.model_ids = w.model_ids_dev ? w.model_ids_dev + w.r0 : nullptr;
+    p.seeds = h->seeds.as<uint64_t>();
+    p.R = n;
+    p.block_bytes = h->cfg.block_size_tokens * 4;
+    p.max_blocks = h->cfg.max_prefix_blocks;
+    p.hashes = w.hashes_out;
+    p.nblocks = w.nblocks_out;
+    p.eff_len = h->eff_len.as<int64_t>() + w.r0;
+    p.in_len = h->in_len.as<int64_t>() + w.r0;
+    p.offsets_aligned16 = w.aligned16 ? 1 : 0;
+    return p;
+}
+
+static PickParams pick_params(epp_engine *h, const Work &w, epp_decision *out, epp_decision_detail *detail,
+                              int32_t *out_match) {
+    PickParams p;
+    p.R = w.r1 - w.r0;
+    p.E = h->cfg.max_endpoints;
+    p.max_blocks = h->cfg.max_prefix_blocks;
+    p.block_size_tokens = h->cfg.block_size_tokens;
+    p.n_profiles = h->n_profiles;
+    p.always_disagg = h->cfg.always_disagg;
+    p.non_cached_tokens = h->cfg.non_cached_tokens;
+    for (int i = 0; i < h->n_profiles; i++) p.prof[i] = profile_dev(h, i);
+    p.hashes = w.hashes_out;
+    p.nblocks = w.nblocks_out;
+    p.in_len = h->in_len.as<int64_t>() + w.r0;
+    p.index = index_view(h);
+    p.out = out;
+    p.detail = detail;
+    p.out_match = out_match;
+    p.work_counters = nullptr;
+    return p;
+}
+
+// Device-side offsets alignment probe for device-pointer batches.
+static int32_t device_offsets_aligned(epp_engine *h, const uint64_t *offsets_dev, int64_t n, cudaStream_t s, bool *out) {
+    int one = 1;
+    CUDA_TRY(cudaMemcpyAsync(h->flag.p, &one, sizeof one, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(launch_check_offsets_aligned(offsets_dev, n, h->flag.as<int>(), s));
+    int res = 0;
+    CUDA_TRY(cudaMemcpyAsync(&res, h->flag.p, sizeof res, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    *out = res != 0;
+    return EPP_OK;
+}
+
+enum class Mode { HashOnly, Match, Schedule };
+
+// Runs hashing (+ match/pick) for a batch.  Host batches are split into chunks whose H2D copy overlaps the
+// kernels of the previous chunk (two streams, two staging buffers); device batches run in one pass.
+static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t *out_hashes, int32_t *out_nblocks,
+                         epp_decision *out_dec, epp_decision_detail *out_detail, int32_t *out_match,
+                         int32_t *out_total) {
+    const int64_t R = v.R;
+    const size_t B = (size_t)h->cfg.max_prefix_blocks;
+    if (R == 0) return EPP_OK;
+    if (mode != Mode::HashOnly) {
+        if (!h->pool_ready) return fail(EPP_ERR_STATE, "epp_pool_set has not been called");
+        EPP_TRY(commit_locked(h));
+    }
+    EPP_TRY(reserve_batch(h, R));
+    int launches = 0;
+    cudaStream_t s0 = h->slot[0].stream;
+
+    if (v.device) {
+        bool aligned = false;
+        if (v.offsets) EPP_TRY(device_offsets_aligned(h, v.offsets, R + 1, s0, &aligned));
+        Work w{0, R, v.data, v.offsets, v.uniform_len, v.model_ids, aligned,
+               (mode == Mode::HashOnly && out_hashes) ? out_hashes : h->hashes.as<uint64_t>(),
+               (mode == Mode::HashOnly && out_nblocks) ? out_nblocks : (mode == Mode::Match && out_total ? out_total : h->nblocks.as<int32_t>())};
+        CUDA_TRY(cudaMemsetAsync(h->work_counters.p, 0, sizeof(unsigned long long) * 2, s0));
+        CUDA_TRY(launch_hash_prompts(hash_params(h, w), s0, &launches, h->ev));
+        if (mode != Mode::HashOnly) {
+            epp_decision *dec = (mode == Mode::Schedule && out_dec) ? out_dec : h->decisions.as<epp_decision>();
+            PickParams pp = pick_params(h, w, dec, mode == Mode::Schedule ? out_detail : nullptr, mode == Mode::Match ? out_match : nullptr);
+            pp.work_counters = h->work_counters.as<unsigned long long>();
+            CUDA_TRY(launch_match_pick(pp, h->pick_global ? h->pick_scratch.as<uint32_t>() : nullptr, h->pick_grid, h->pick_smem, s0, &launches));
+        }
+        CUDA_TRY(cudaEventRecord(h->ev[4], s0));
+        unsigned long long wc[2] = {0, 0};
+        CUDA_TRY(cudaMemcpyAsync(wc, h->work_counters.p, sizeof wc, cudaMemcpyDeviceToHost, s0));
+        CUDA_TRY(cudaStreamSynchronize(s0));
+        float t[4] = {0, 0, 0, 0};
+        for (int i = 0; i < 4; i++) cudaEventElapsedTime(&t[i], h->ev[i], h->ev[i + 1]);
+        for (int i = 0; i < 8; i++) h->stats.last_kernel_ms[i] = i < 4 ? t[i] : 0.0;
+        h->stats.last_hash_ms = t[0] + t[1] + t[2];
+        h->stats.last_match_pick_ms = t[3];
+        h->stats.last_kernels_ms = t[0] + t[1] + t[2] + t[3];
+        h->stats.last_h2d_ms = h->stats.last_d2h_ms = 0;
+        h->stats.last_probes = wc[0];
+        h->stats.last_postings = wc[1];
+        h->stats.last_kernel_launches = (uint64_t)launches;
+        return EPP_OK;
+    }
+
+    // ---- host batch: upload the small per-request arrays once, then pipeline the prompt bytes
+    if (v.offsets) CUDA_TRY(cudaMemcpyAsync(h->offsets.p, v.offsets, sizeof(uint64_t) * (size_t)(R + 1), cudaMemcpyHostToDevice, s0));
+    if (v.model_ids) CUDA_TRY(cudaMemcpyAsync(h->model_ids.p, v.model_ids, sizeof(uint32_t) * (size_t)R, cudaMemcpyHostToDevice, s0));
+    CUDA_TRY(cudaEventRecord(h->slot[0].done, s0));
+    CUDA_TRY(cudaStreamWaitEvent(h->slot[1].stream, h->slot[0].done, 0));
+
+    // chunk plan: at least one request per chunk, about kChunkBytes of prompt bytes
+    const uint64_t kChunkBytes = 48ull << 20;
+    struct Chunk { int64_t r0, r1; uint64_t start, bytes; };
+    std::vector<Chunk> chunks;
+    uint64_t max_bytes = 0;
+    for (int64_t r = 0; r < R;) {
+        int64_t r_end = r;
+        uint64_t start, bytes;
+        if (v.offsets) {
+            while (r_end < R && (r_end == r || (v.offsets[r_end + 1] - v.offsets[r]) <= kChunkBytes)) r_end++;
+            start = v.offsets[r];
+            bytes = v.offsets[r_end] - start;
+        } else {
+            int64_t per = v.uniform_len ? (int64_t)std::max<uint64_t>(1, kChunkBytes / v.uniform_len) : R;
+            r_end = std::min(R, r + per);
+            start = (uint64_t)r * v.uniform_len;
+            bytes = (uint64_t)(r_end - r) * v.uniform_len;
+        }
+        chunks.push_back({r, r_end, start, bytes});
+        max_bytes = std::max(max_bytes, bytes);
+        r = r_end;
+    }
+    for (int i = 0; i < 2; i++) CUDA_TRY(h->slot[i].data.reserve(max_bytes + 64, &h->dev_bytes));
+    const size_t E = (size_t)h->cfg.max_endpoints;
+    if (mode == Mode::Match) CUDA_TRY(h->dense_match.reserve(sizeof(int32_t) * (size_t)R * E, &h->dev_bytes));
+
+    CUDA_TRY(cudaEventRecord(h->ev[0], s0));
+    for (size_t k = 0; k < chunks.size(); k++) {
+        const Chunk &c = chunks[k];
+        Slot &sl = h->slot[k & 1];
+        cudaStream_t s = sl.stream;
+        const size_t nreq = (size_t)(c.r1 - c.r0);
+        // keep the staged copy aligned (mod 16) like the caller's layout
+        uint8_t *stage = sl.data.as<uint8_t>() + (c.start & 15);
+        if (c.bytes) CUDA_TRY(cudaMemcpyAsync(stage, v.data + c.start, c.bytes, cudaMemcpyHostToDevice, s));
+        Work w;
+        w.r0 = c.r0;
+        w.r1 = c.r1;
+        if (v.offsets) {
+            // the kernels address  data_base + offsets[r]  with ABSOLUTE offsets
+            w.data_base = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(stage) - (uintptr_t)c.start);
+            w.offsets_dev = h->offsets.as<uint64_t>();
+            w.aligned16 = v.aligned16;
+        } else {
+            w.data_base = stage;                    // chunk-local request index * uniform_len
+            w.offsets_dev = nullptr;
+            w.aligned16 = (v.uniform_len % 16) == 0;
+        }
+        w.uniform_len = v.uniform_len;
+        w.model_ids_dev = v.model_ids ? h->model_ids.as<uint32_t>() : nullptr;
+        w.hashes_out = h->hashes.as<uint64_t>() + (size_t)c.r0 * B;
+        w.nblocks_out = h->nblocks.as<int32_t>() + c.r0;
+        CUDA_TRY(launch_hash_prompts(hash_params(h, w), s, &launches));
+        if (mode == Mode::HashOnly) {
+            if (out_hashes) CUDA_TRY(cudaMemcpyAsync(out_hashes + (size_t)c.r0 * B, w.hashes_out, sizeof(uint64_t) * nreq * B, cudaMemcpyDeviceToHost, s));
+            if (out_nblocks) CUDA_TRY(cudaMemcpyAsync(out_nblocks + c.r0, w.nblocks_out, sizeof(int32_t) * nreq, cudaMemcpyDeviceToHost, s));
+        } else {
+            int32_t *dm = mode == Mode::Match ? h->dense_match.as<int32_t>() + (size_t)c.r0 * E : nullptr;
+            epp_decision *dec = h->decisions.as<epp_decision>() + c.r0;
+            epp_decision_detail *det = h->details.as<epp_decision_detail>() + c.r0;
+            PickParams pp = pick_params(h, w, dec, det, dm);
+            CUDA_TRY(launch_match_pick(pp, h->pick_global ? h->pick_scratch.as<uint32_t>() : nullptr, h->pick_grid, h->pick_smem, s, &launches));
+            if (mode == Mode::Schedule) {
+                if (out_dec) CUDA_TRY(cudaMemcpyAsync(out_dec + c.r0, dec, sizeof(epp_decision) * nreq, cudaMemcpyDeviceToHost, s));
+                if (out_detail) CUDA_TRY(cudaMemcpyAsync(out_detail + c.r0, det, sizeof(epp_decision_detail) * nreq, cudaMemcpyDeviceToHost, s));
+            } else {
+                if (out_match) CUDA_TRY(cudaMemcpyAsync(out_match + (size_t)c.r0 * E, dm, sizeof(int32_t) * nreq * E, cudaMemcpyDeviceToHost, s));
+                if (out_total) CUDA_TRY(cudaMemcpyAsync(out_total + c.r0, w.nblocks_out, sizeof(int32_t) * nreq, cudaMemcpyDeviceToHost, s));
+            }
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->slot[1].stream));
+    CUDA_TRY(cudaEventRecord(h->ev[1], s0));
+    CUDA_TRY(cudaStreamSynchronize(s0));
+    float t_all = 0;
+    cudaEventElapsedTime(&t_all, h->ev[0], h->ev[1]);
+    h->stats.last_kernels_ms = t_all;
+    h->stats.last_hash_ms = h->stats.last_match_pick_ms = 0;
+    h->stats.last_kernel_launches = (uint64_t)launches;
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_hash_prompts(epp_engine *h, const epp_batch *batch, uint64_t *out_hashes, int32_t *out_nblocks) {
+    if (!h) return fail(EPP_ERR_INVALID, "NULL engine");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    BatchView v;
+    EPP_TRY(check_batch(h, batch, v));
+    h->kept_R = 0;
+    return run_batch(h, v, Mode::HashOnly, out_hashes, out_nblocks, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int32_t epp_prefix_match(epp_engine *h, const epp_batch *batch, int32_t *out_match, int32_t *out_total) {
+    if (!h) return fail(EPP_ERR_INVALID, "NULL engine");
+    if (!out_match) return fail(EPP_ERR_INVALID, "out_match is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    BatchView v;
+    EPP_TRY(check_batch(h, batch, v));
+    h->kept_R = 0;
+    return run_batch(h, v, Mode::Match, nullptr, nullptr, nullptr, nullptr, out_match, out_total);
+}
+
+extern "C" int32_t epp_schedule(epp_engine *h, const epp_batch *batch, epp_decision *out, epp_decision_detail *detail,
+                                int32_t keep_hashes) {
+    if (!h) return fail(EPP_ERR_INVALID, "NULL engine");
+    if (!out) return fail(EPP_ERR_INVALID, "out is NULL");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    BatchView v;
+    EPP_TRY(check_batch(h, batch, v));
+    h->kept_R = 0;
+    EPP_TRY(run_batch(h, v, Mode::Schedule, nullptr, nullptr, out, detail, nullptr, nullptr));
+    h->stats.n_batches++;
+    h->stats.n_decisions += (uint64_t)v.R;
+    if (keep_hashes) {
+        h->kept_R = v.R;
+        h->kept_decisions.resize((size_t)v.R);
+        if (v.R) {
+            if (v.device) CUDA_TRY(cudaMemcpy(h->kept_decisions.data(), out, sizeof(epp_decision) * (size_t)v.R, cudaMemcpyDeviceToHost));
+            else memcpy(h->kept_decisions.data(), out, sizeof(epp_decision) * (size_t)v.R);
+        }
+    }
+    return EPP_OK;
+}
+
+// PreRequest: approximateprefix/plugin.go:164-200 (primary target + "prefill" profile target).
+extern "C" int32_t epp_index_add_picked(epp_engine *h) {
+    if (!h) return fail(EPP_ERR_INVALID, "NULL engine");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    if (h->kept_R == 0) return fail(EPP_ERR_STATE, "no batch kept (call epp_schedule with keep_hashes=1 first)");
+    if (h->snapshot_mode) return fail(EPP_ERR_STATE, "index holds a bulk snapshot; incremental adds need a mirror-built index");
+    const size_t B = (size_t)h->cfg.max_prefix_blocks;
+    std::vector<uint64_t> hs((size_t)h->kept_R * B);
+    std::vector<int32_t> nb((size_t)h->kept_R);
+    CUDA_TRY(cudaMemcpy(hs.data(), h->hashes.p, sizeof(uint64_t) * hs.size(), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(nb.data(), h->nblocks.p, sizeof(int32_t) * nb.size(), cudaMemcpyDeviceToHost));
+    for (int64_t r = 0; r < h->kept_R; r++) {
+        const epp_decision &d = h->kept_decisions[(size_t)r];
+        if (d.status != 0 || d.pick == EPP_NO_ENDPOINT) continue;            // plugin.go:168-170
+        h->mirror->add(d.pick, hs.data() + (size_t)r * B, nb[(size_t)r], 0);
+        if (d.prefill_pick != EPP_NO_ENDPOINT)                                // plugin.go:176-178
+            h->mirror->add(d.prefill_pick, hs.data() + (size_t)r * B, nb[(size_t)r], 0);
+    }
+    h->kept_R = 0;
+    return EPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plugin-parity entry points on injected match info
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t epp_score(epp_engine *h, int64_t n_requests, const int32_t *match, const int32_t *total,
+                             int32_t profile, int32_t scorer_index, double *out_scores, uint32_t flags) {
+    if (!h || n_requests < 0 || (n_requests && (!match || !total || !out_scores))) return fail(EPP_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    if (!h->pool_ready) return fail(EPP_ERR_STATE, "epp_pool_set has not been called");
+    if (profile < 0 || profile >= h->n_profiles) return fail(EPP_ERR_INVALID, "profile %d out of range", profile);
+    const epp_profile_cfg &pc = profile == 0 ? h->cfg.primary : h->cfg.prefill;
+    if (scorer_index < -1 || scorer_index >= pc.n_scorers) return fail(EPP_ERR_INVALID, "scorer_index %d out of range", scorer_index);
+    if (n_requests == 0) return EPP_OK;
+    const size_t E = (size_t)h->cfg.max_endpoints, n = (size_t)n_requests * E;
+    cudaStream_t s = h->slot[0].stream;
+    const bool dev = (flags & EPP_BATCH_DEVICE_PTRS) != 0;
+    const int32_t *d_match = match, *d_total = total;
+    double *d_out = out_scores;
+    if (!dev) {
+        CUDA_TRY(h->dense_match.reserve(sizeof(int32_t) * n, &h->dev_bytes));
+        CUDA_TRY(h->dense_total.reserve(sizeof(int32_t) * (size_t)n_requests, &h->dev_bytes));
+        CUDA_TRY(h->dense_scores.reserve(sizeof(double) * n, &h->dev_bytes));
+        CUDA_TRY(cudaMemcpyAsync(h->dense_match.p, match, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(h->dense_total.p, total, sizeof(int32_t) * (size_t)n_requests, cudaMemcpyHostToDevice, s));
+        d_match = h->dense_match.as<int32_t>();
+        d_total = h->dense_total.as<int32_t>();
+        d_out = h->dense_scores.as<double>();
+    }
+    int launches = 0;
+    CUDA_TRY(launch_score_dense(n_requests, h->cfg.max_endpoints, profile_dev(h, profile), pool_arrays(h),
+                                h->prof[profile].qminmax.as<int64_t>(), d_match, d_total, scorer_index, d_out, s, &launches));
+    if (!dev) CUDA_TRY(cudaMemcpyAsync(out_scores, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_schedule_with_match(epp_engine *h, int64_t n_requests, const int32_t *match, const int32_t *total,
+                                           const int64_t *input_len_bytes, int32_t block_size_tokens, epp_decision *out,
+                                           epp_decision_detail *detail, uint32_t flags) {
+    if (!h || n_requests < 0 || (n_requests && (!match || !total || !out))) return fail(EPP_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    if (!h->pool_ready) return fail(EPP_ERR_STATE, "epp_pool_set has not been called");
+    if (n_requests == 0) return EPP_OK;
+    const size_t E = (size_t)h->cfg.max_endpoints, n = (size_t)n_requests * E, R = (size_t)n_requests;
+    cudaStream_t s = h->slot[0].stream;
+    const bool dev = (flags & EPP_BATCH_DEVICE_PTRS) != 0;
+    DensePickParams p;
+    p.R = n_requests;
+    p.E = h->cfg.max_endpoints;
+    p.block_size_tokens = block_size_tokens > 0 ? block_size_tokens : h->cfg.block_size_tokens;
+    p.n_profiles = h->n_profiles;
+    p.always_disagg = h->cfg.always_disagg;
+    p.non_cached_tokens = h->cfg.non_cached_tokens;
+    for (int i = 0; i < h->n_profiles; i++) p.prof[i] = profile_dev(h, i);
+    if (dev) {
+        p.match = match; p.total = total; p.in_len = input_len_bytes; p.out = out; p.detail = detail;
+    } else {
+        EPP_TRY(reserve_batch(h, n_requests));
+        CUDA_TRY(h->dense_match.reserve(sizeof(int32_t) * n, &h->dev_bytes));
+        CUDA_TRY(h->dense_total.reserve(sizeof(int32_t) * R, &h->dev_bytes));
+        CUDA_TRY(cudaMemcpyAsync(h->dense_match.p, match, sizeof(int32_t) * n, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(h->dense_total.p, total, sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
+        if (input_len_bytes) CUDA_TRY(cudaMemcpyAsync(h->in_len.p, input_len_bytes, sizeof(int64_t) * R, cudaMemcpyHostToDevice, s));
+        else CUDA_TRY(cudaMemsetAsync(h->in_len.p, 0, sizeof(int64_t) * R, s));
+        p.match = h->dense_match.as<int32_t>();
+        p.total = h->dense_total.as<int32_t>();
+        p.in_len = h->in_len.as<int64_t>();
+        p.out = h->decisions.as<epp_decision>();
+        p.detail = h->details.as<epp_decision_detail>();
+    }
+    int launches = 0;
+    CUDA_TRY(launch_dense_pick(p, s, &launches));
+    if (!dev) {
+        CUDA_TRY(cudaMemcpyAsync(out, p.out, sizeof(epp_decision) * R, cudaMemcpyDeviceToHost, s));
+        if (detail) CUDA_TRY(cudaMemcpyAsync(detail, p.detail, sizeof(epp_decision_detail) * R, cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    h->kept_R = 0;
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_get_stats(epp_engine *h, epp_stats *out) {
+    if (!h || !out) return fail(EPP_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->stats.device_bytes = h->dev_bytes;
+    *out = h->stats;
+    return EPP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// endpoint-sharded mode (see shard_kernels.cu)
+// ------------------------------------------------------------------------------------------------
+extern "C" int32_t epp_shard_set(epp_engine *h, uint32_t ep_begin, uint32_t ep_end) {
+    if (!h || ep_begin > ep_end) return fail(EPP_ERR_INVALID, "bad shard range");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->shard_begin = ep_begin;
+    h->shard_end = ep_end;
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_shard_probe(epp_engine *h, const epp_batch *batch, uint32_t *out_masks) {
+    (void)h; (void)batch; (void)out_masks;
+    return fail(EPP_ERR_STATE, "endpoint-sharded mode is not built into this library yet");
+}
+extern "C" int32_t epp_shard_pick(epp_engine *h, int64_t n_requests, const uint32_t *global_masks, epp_shard_best *out_best) {
+    (void)h; (void)n_requests; (void)global_masks; (void)out_best;
+    return fail(EPP_ERR_STATE, "endpoint-sharded mode is not built into this library yet");
+}
+extern "C" int32_t epp_shard_merge(epp_engine *h, int64_t n_requests, int32_t n_ranks, const epp_shard_best *all_best, epp_decision *out) {
+    (void)h; (void)n_requests; (void)n_ranks; (void)all_best; (void)out;
+    return fail(EPP_ERR_STATE, "endpoint-sharded mode is not built into this library yet");
+}

@@ -1,0 +1,204 @@
+// hash_kernels.cu -- a1: batched chained XXH64 prefix-block hashing (approximateprefix/hashing.go:35-99).
+//
+// v1 layout (correctness-first; the TMA-pipelined fused kernel lives in hash_fused.cu):
+//   k_prompt_lengths : per request, truncation + block count                     (hashing.go:58-66)
+//   k_block_digests  : one thread per (request, full block), block_bytes % 32 == 0: stripe rounds + merge ->
+//                      8-byte pre-chain digest m_b stored in hashes[r][b]         (part A of xxh64.cuh)
+//   k_chain          : one thread per request walks the chain in place             (part B)
+//   k_hash_generic   : any block size / alignment, one thread per request, fully serial
+#include "kernels.h"
+#include "xxh64.cuh"
+
+namespace epp {
+
+__device__ __forceinline__ void request_span(const HashParams &p, int64_t r, uint64_t &off, uint64_t &len) {
+    if (p.offsets) {
+        off = p.offsets[r];
+        len = p.offsets[r + 1] - off;
+    } else {
+        off = (uint64_t)r * p.uniform_len;
+        len = p.uniform_len;
+    }
+}
+
+// Generic hash of one chain block: message = bytes[0..n) || LE64(prev).
+__device__ inline uint64_t hash_block_generic(const uint8_t *b, int64_t n, uint64_t prev) {
+    uint64_t v[4];
+    bool have_v = false;
+    int64_t i = 0;
+    if (n >= 32) {
+        xxh_init(v);
+        have_v = true;
+        for (; i + 32 <= n; i += 32) {
+            v[0] = xxh_round(v[0], load_le64(b + i));
+            v[1] = xxh_round(v[1], load_le64(b + i + 8));
+            v[2] = xxh_round(v[2], load_le64(b + i + 16));
+            v[3] = xxh_round(v[3], load_le64(b + i + 24));
+        }
+    }
+    uint8_t tail[40];
+    int t = 0;
+    for (; i < n; i++) tail[t++] = b[i];
+#pragma unroll
+    for (int k = 0; k < 8; k++) tail[t++] = (uint8_t)(prev >> (8 * k));
+    return xxh_finish(v, have_v, (uint64_t)n + 8, tail, t);
+}
+
+__global__ void k_hash_bytes(const uint8_t *msg, size_t len, uint64_t *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint64_t v[4];
+    bool have_v = false;
+    size_t i = 0;
+    if (len >= 32) {
+        xxh_init(v);
+        have_v = true;
+        for (; i + 32 <= len; i += 32) {
+            v[0] = xxh_round(v[0], load_le64(msg + i));
+            v[1] = xxh_round(v[1], load_le64(msg + i + 8));
+            v[2] = xxh_round(v[2], load_le64(msg + i + 16));
+            v[3] = xxh_round(v[3], load_le64(msg + i + 24));
+        }
+    }
+    uint8_t tail[32];
+    int t = 0;
+    for (; i < len; i++) tail[t++] = msg[i];
+    *out = xxh_finish(v, have_v, (uint64_t)len, tail, t);
+}
+
+cudaError_t launch_hash_bytes(const uint8_t *msg, size_t len, uint64_t *out, cudaStream_t s) {
+    k_hash_bytes<<<1, 32, 0, s>>>(msg, len, out);
+    return cudaGetLastError();
+}
+
+__global__ void k_prompt_lengths(HashParams p) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.R) return;
+    uint64_t off, len;
+    request_span(p, r, off, len);
+    if (p.in_len) p.in_len[r] = (int64_t)len;
+    int64_t bs = p.block_bytes;
+    int64_t eff = (int64_t)len;
+    int32_t nb = 0;
+    if (bs <= 0 || eff < bs) {            // hashing.go:51-61 -> nil
+        eff = 0;
+    } else {
+        int64_t cap = bs * (int64_t)p.max_blocks;
+        if (eff > cap) eff = cap;         // hashing.go:63-66
+        nb = (int32_t)(eff / bs) + ((eff % bs) ? 1 : 0);
+    }
+    p.nblocks[r] = nb;
+    p.eff_len[r] = eff;
+}
+
+// One thread per (request, full block).  Requires block_bytes % 32 == 0 and 16-byte aligned block starts.
+__global__ void __launch_bounds__(256) k_block_digests(HashParams p) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t r = idx / p.max_blocks;
+    int32_t b = (int32_t)(idx % p.max_blocks);
+    if (r >= p.R) return;
+    int64_t eff = p.eff_len[r];
+    int64_t bs = p.block_bytes;
+    if ((int64_t)(b + 1) * bs > eff) return;          // not a full block
+    uint64_t off, len;
+    request_span(p, r, off, len);
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.data + off + (uint64_t)b * (uint64_t)bs);
+    uint64_t v[4];
+    xxh_init(v);
+    int ns = (int)(bs / 32);
+    for (int s = 0; s < ns; s++) {
+        uint4 a = __ldg(src + 2 * s);
+        uint4 c = __ldg(src + 2 * s + 1);
+        v[0] = xxh_round(v[0], ((uint64_t)a.y << 32) | a.x);
+        v[1] = xxh_round(v[1], ((uint64_t)a.w << 32) | a.z);
+        v[2] = xxh_round(v[2], ((uint64_t)c.y << 32) | c.x);
+        v[3] = xxh_round(v[3], ((uint64_t)c.w << 32) | c.z);
+    }
+    p.hashes[r * (int64_t)p.max_blocks + b] = xxh_merge_all(v);
+}
+
+__global__ void __launch_bounds__(128) k_chain(HashParams p) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.R) return;
+    int32_t nb = p.nblocks[r];
+    if (nb == 0) return;
+    int64_t eff = p.eff_len[r];
+    int64_t bs = p.block_bytes;
+    int32_t nfull = (int32_t)(eff / bs);
+    uint64_t prev = p.seeds[p.model_ids ? p.model_ids[r] : 0];
+    uint64_t *row = p.hashes + r * (int64_t)p.max_blocks;
+    uint64_t lenp8 = (uint64_t)bs + 8;
+    for (int32_t b = 0; b < nfull; b++) {
+        prev = xxh_chain_step32(row[b], lenp8, prev);
+        row[b] = prev;
+    }
+    if (nfull < nb) {                                    // trailing partial block (hashing.go:90-96)
+        uint64_t off, len;
+        request_span(p, r, off, len);
+        row[nfull] = hash_block_generic(p.data + off + (uint64_t)nfull * (uint64_t)bs, eff - (int64_t)nfull * bs, prev);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_hash_generic(HashParams p) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.R) return;
+    int32_t nb = p.nblocks[r];
+    if (nb == 0) return;
+    int64_t eff = p.eff_len[r];
+    int64_t bs = p.block_bytes;
+    uint64_t off, len;
+    request_span(p, r, off, len);
+    const uint8_t *base = p.data + off;
+    uint64_t prev = p.seeds[p.model_ids ? p.model_ids[r] : 0];
+    uint64_t *row = p.hashes + r * (int64_t)p.max_blocks;
+    for (int32_t b = 0; b < nb; b++) {
+        int64_t start = (int64_t)b * bs;
+        int64_t n = eff - start < bs ? eff - start : bs;
+        prev = hash_block_generic(base + start, n, prev);
+        row[b] = prev;
+    }
+}
+
+// The vectorised path needs block_bytes % 32 == 0 and every block start 16-byte aligned.
+static bool fast_path_ok(const HashParams &p) {
+    if (p.block_bytes <= 0 || (p.block_bytes % 32) != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(p.data) & 15) != 0) return false;
+    if (p.offsets) return p.offsets_aligned16 != 0;
+    return (p.uniform_len % 16) == 0;
+}
+
+// Sets *flag = 0 when any offset is not a multiple of 16 (device-pointer batches).
+__global__ void k_offsets_aligned(const uint64_t *offsets, int64_t n, int *flag) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n && (offsets[r] & 15)) *flag = 0;
+}
+cudaError_t launch_check_offsets_aligned(const uint64_t *offsets, int64_t n, int *flag_dev, cudaStream_t s) {
+    k_offsets_aligned<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(offsets, n, flag_dev);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hash_prompts(const HashParams &p, cudaStream_t s, int *launches, cudaEvent_t *ev) {
+    if (p.R <= 0) return cudaSuccess;
+    int n = 0;
+    unsigned gR = (unsigned)((p.R + 127) / 128);
+    if (ev) cudaEventRecord(ev[0], s);
+    k_prompt_lengths<<<gR, 128, 0, s>>>(p);
+    if (ev) cudaEventRecord(ev[1], s);
+    n++;
+    if (fast_path_ok(p)) {
+        int64_t items = p.R * (int64_t)p.max_blocks;
+        k_block_digests<<<(unsigned)((items + 255) / 256), 256, 0, s>>>(p);
+        if (ev) cudaEventRecord(ev[2], s);
+        k_chain<<<gR, 128, 0, s>>>(p);
+        if (ev) cudaEventRecord(ev[3], s);
+        n += 2;
+    } else {
+        if (ev) cudaEventRecord(ev[2], s);
+        k_hash_generic<<<gR, 128, 0, s>>>(p);
+        if (ev) cudaEventRecord(ev[3], s);
+        n++;
+    }
+    if (launches) *launches += n;
+    return cudaGetLastError();
+}
+
+}  // namespace epp

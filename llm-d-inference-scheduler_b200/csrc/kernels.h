@@ -1,0 +1,153 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels (internal to libepp_engine.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/epp_engine.h"
+
+namespace epp {
+
+// ------------------------------------------------------------------------------------------------
+// hashing (a1)
+// ------------------------------------------------------------------------------------------------
+struct HashParams {
+    const uint8_t *data;        // prompt bytes (device)
+    const uint64_t *offsets;    // [R+1] device, or nullptr => uniform_len
+    uint64_t uniform_len;
+    const uint32_t *model_ids;  // [R] device or nullptr
+    const uint64_t *seeds;      // device table of h_{-1} per registered model
+    int64_t R;
+    int32_t block_bytes;        // blockSizeTokens * 4
+    int32_t max_blocks;         // row pitch of `hashes`
+    uint64_t *hashes;           // [R][max_blocks]
+    int32_t *nblocks;           // [R]
+    int64_t *eff_len;           // [R] bytes hashed after truncation (hashing.go:63-66)
+    int64_t *in_len;            // [R] untruncated prompt length in bytes (P/D decider), may be nullptr
+    int32_t offsets_aligned16;  // every offsets[r] is a multiple of 16 (enables the vectorised path)
+};
+// Generic single-message XXH64 (model || salt seeds).  msg on device.
+cudaError_t launch_hash_bytes(const uint8_t *msg, size_t len, uint64_t *out, cudaStream_t s);
+cudaError_t launch_check_offsets_aligned(const uint64_t *offsets, int64_t n, int *flag_dev, cudaStream_t s);
+// Whole hashPrompt for a batch.  Returns number of kernels launched via *launches.
+// ev (optional, 4 events): recorded before the first kernel and after each of lengths / digests / chain.
+cudaError_t launch_hash_prompts(const HashParams &p, cudaStream_t s, int *launches, cudaEvent_t *ev = nullptr);
+
+// ------------------------------------------------------------------------------------------------
+// prefix index (a2): open-addressed table  hash -> (posting offset, count)
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) IndexSlot {
+    uint64_t key;
+    uint32_t off;
+    uint32_t cnt;     // 0 == empty slot
+};
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFULL;   // build-time claim sentinel; a real key equal to it
+                                                        // lives in IndexView::special
+struct IndexView {
+    const IndexSlot *slots;
+    const uint32_t *postings;
+    uint64_t mask;            // capacity - 1 (capacity is a power of two), 0 slots => mask 0 & n_pairs 0
+    IndexSlot special;        // record for key == kEmptyKey (cnt 0 when absent)
+    uint32_t ep_begin, ep_end;  // shard range (postings outside are ignored for counting but keep the walk alive)
+};
+// Builds table + postings from n pairs (device arrays).  slots must hold `capacity` entries, postings n,
+// scratch `capacity` uint32.  *out_special receives the record of key == kEmptyKey.  Deduplicates pairs.
+cudaError_t launch_index_build(const uint64_t *pair_hash, const uint32_t *pair_ep, uint64_t n, IndexSlot *slots,
+                               uint64_t capacity, uint32_t *postings, uint32_t *scratch, uint32_t *cursor,
+                               IndexSlot *special_dev, uint32_t max_endpoints, cudaStream_t s, int *launches);
+cudaError_t launch_index_get(const IndexView &ix, uint64_t hash, uint32_t *out_eps, int32_t cap, int32_t *out_n,
+                             cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------------
+// pool state -> request-independent scorer terms (a5-a9 precompute)
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxProfiles = 2;
+struct PoolArrays {
+    int32_t E;                 // slot capacity (max_endpoints)
+    int32_t n_ext_cols;
+    const uint8_t *role;       // [E] epp_role, 0xFF = absent
+    const double *kv_usage;    // [E]
+    const int32_t *waiting;    // [E]
+    const int32_t *running;    // [E]
+    const double *ext;         // [n_ext_cols][E]
+};
+struct ProfileDerived {
+    // per profile, device arrays
+    uint8_t *cand;             // [E] 1 = passes the role filter
+    double *contrib;           // [EPP_MAX_SCORERS][E] clamp(score)*weight of every request-independent scorer
+    double *base;              // [E] ordered weighted sum with every prefix term = clamp(0)*w
+    uint32_t *order;           // [Epad] candidates sorted by (base desc, slot asc); then non-candidates
+    uint32_t *grp_size;        // [Epad] size of the equal-base group of order[k]
+    uint64_t *sort_key;        // [Epad] scratch
+    int32_t *n_cand;           // [1]
+    int64_t *qminmax;          // [4] waiting min,max, running min,max over candidates
+};
+cudaError_t launch_pool_prepare(const PoolArrays &pool, const epp_profile_cfg &prof, const ProfileDerived &d,
+                                int32_t Epad, cudaStream_t s, int *launches);
+
+// ------------------------------------------------------------------------------------------------
+// match + score + pick (a3-a14)
+// ------------------------------------------------------------------------------------------------
+struct ProfileDev {            // what the pick kernels read (device pointers + config by value)
+    epp_profile_cfg cfg;
+    const uint8_t *cand;
+    const double *contrib;
+    const double *base;
+    const uint32_t *order;
+    const uint32_t *grp_size;
+    const int32_t *n_cand;
+};
+struct PickParams {
+    int64_t R;
+    int32_t E;
+    int32_t max_blocks;
+    int32_t block_size_tokens;
+    int32_t n_profiles;        // 1 or 2 (2 => disagg: [0]=decode, [1]=prefill)
+    int32_t always_disagg;
+    int64_t non_cached_tokens;
+    ProfileDev prof[kMaxProfiles];
+    const uint64_t *hashes;    // [R][max_blocks]
+    const int32_t *nblocks;    // [R]
+    const int64_t *in_len;     // [R] prompt bytes (decider)
+    IndexView index;
+    epp_decision *out;         // [R]
+    epp_decision_detail *detail;  // [R] or nullptr
+    int32_t *out_match;        // dense [R][E] or nullptr (Produce parity mode)
+    unsigned long long *work_counters;  // [2] += (probes, postings) of this launch, or nullptr
+};
+// Fused lookup + match + score + pick, one warp per request.  Per-warp match counters live in shared memory
+// (smem = match_pick_smem_bytes(E, false)) or, when E is too large for that, in a zero-initialised global
+// scratch of grid * warps * ceil(E/2) words (smem = match_pick_smem_bytes(E, true)).
+size_t match_pick_smem_bytes(int32_t E, bool global_counts);
+int match_pick_warps_per_cta();
+cudaError_t launch_match_pick(const PickParams &p, uint32_t *gscratch, int grid, size_t smem, cudaStream_t s,
+                              int *launches);
+// Decision logic on injected dense match info (plugin parity / KAT mode).
+struct DensePickParams {
+    int64_t R;
+    int32_t E;
+    int32_t block_size_tokens;
+    int32_t n_profiles;
+    int32_t always_disagg;
+    int64_t non_cached_tokens;
+    ProfileDev prof[kMaxProfiles];
+    const int32_t *match;      // [R][E]
+    const int32_t *total;      // [R]
+    const int64_t *in_len;     // [R]
+    epp_decision *out;
+    epp_decision_detail *detail;
+};
+cudaError_t launch_dense_pick(const DensePickParams &p, cudaStream_t s, int *launches);
+// Scorer.Score parity: out[R][E].  scorer_index -1 => weighted ordered sum (-1.0 for non-candidates).
+cudaError_t launch_score_dense(int64_t R, int32_t E, const ProfileDev &prof, const PoolArrays &pool,
+                               const int64_t *qminmax, const int32_t *match, const int32_t *total,
+                               int32_t scorer_index, double *out, cudaStream_t s, int *launches);
+
+// endpoint-sharded mode
+cudaError_t launch_shard_probe(const PickParams &p, uint32_t *out_masks, int32_t mask_words, cudaStream_t s,
+                               int *launches);
+cudaError_t launch_shard_pick(const PickParams &p, const uint32_t *global_masks, int32_t mask_words,
+                              epp_shard_best *out_best, cudaStream_t s, int *launches);
+cudaError_t launch_shard_merge(int64_t R, int32_t n_ranks, const epp_shard_best *all_best, const int32_t *nblocks,
+                               epp_decision *out, cudaStream_t s, int *launches);
+
+}  // namespace epp

@@ -1,0 +1,543 @@
+// pick_kernels.cu -- a3-a14: prefix match (global-stop rule), load scorers, ordered weighted sum, arg-max pick,
+// and the decode -> decider -> prefill two-stage pick.
+//
+// Arithmetic contract: float64, IEEE round-to-nearest-even, NEVER fused -- every
+// multiply/add/divide below is an explicit __d*_rn intrinsic (the file is also compiled with -fmad=false).
+// Scorer order = profile order; accumulation starts from +0.0 (scheduler_profile.go:155-168).
+//
+// Work decomposition: all request-independent terms are derived once per pool snapshot (k_pool_*): per profile the
+// candidate mask (role filter), queue min/max over the candidates, each scorer's clamp(score)*weight column and
+// the ordered base sum every endpoint has when its prefix match is 0, plus the candidates sorted by
+// (base desc, slot asc).  Per request only the few endpoints that actually hold a prefix need arithmetic; the
+// best of all the others is the first unmatched entry of the sorted order.  This is exact, not an approximation:
+// an unmatched endpoint's weighted sum is bit-identical to its base.
+#include <math_constants.h>
+
+#include <climits>
+
+#include "kernels.h"
+
+namespace epp {
+
+// ------------------------------------------------------------------------------------------------
+// scorers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool filter_keeps(int filter, uint8_t role) {
+    if (role == 0xFF) return false;                       // slot not in the pool
+    switch (filter) {
+        case EPP_FILTER_NONE: return true;
+        case EPP_FILTER_DECODE:   // roles.go:46-48 (allowsNoLabel = true)
+            return role == EPP_ROLE_NONE || role == EPP_ROLE_DECODE || role == EPP_ROLE_PREFILL_DECODE ||
+                   role == EPP_ROLE_BOTH || role == EPP_ROLE_ENCODE_PREFILL_DECODE;
+        case EPP_FILTER_PREFILL:  // roles.go:56-58
+            return role == EPP_ROLE_PREFILL || role == EPP_ROLE_ENCODE_PREFILL || role == EPP_ROLE_PREFILL_DECODE ||
+                   role == EPP_ROLE_BOTH || role == EPP_ROLE_ENCODE_PREFILL_DECODE;
+        case EPP_FILTER_ENCODE:   // roles.go:68-70
+            return role == EPP_ROLE_ENCODE || role == EPP_ROLE_ENCODE_PREFILL ||
+                   role == EPP_ROLE_ENCODE_PREFILL_DECODE;
+        default: return false;
+    }
+}
+
+// enforceScoreRange, scheduler_profile.go:194-202 (NaN passes through, as in Go)
+__device__ __forceinline__ double clamp01(double s) {
+    if (s < 0.0) return 0.0;
+    if (s > 1.0) return 1.0;
+    return s;
+}
+
+// prefix-cache-scorer, scorer/prefix/plugin.go:100-111
+__device__ __forceinline__ double prefix_score(int32_t match, int32_t total) {
+    if (total == 0) return 0.0;
+    return __ddiv_rn((double)match, (double)total);
+}
+
+// Raw Scorer.Score value of one endpoint for the request-independent scorers.
+__device__ __forceinline__ double pool_score(const epp_scorer_cfg &sc, const PoolArrays &pool,
+                                             const int64_t *qminmax, int32_t e) {
+    switch (sc.kind) {
+        case EPP_SCORER_KV_UTIL:   // kvcache_utilization.go:79
+            return __dsub_rn(1.0, pool.kv_usage[e]);
+        case EPP_SCORER_QUEUE:     // queue.go:79-99
+        case EPP_SCORER_RUNNING: { // runningrequest.go:79-99
+            bool isq = sc.kind == EPP_SCORER_QUEUE;
+            int64_t mn = qminmax[isq ? 0 : 2], mx = qminmax[isq ? 1 : 3];
+            int64_t q = isq ? pool.waiting[e] : pool.running[e];
+            if (mx == mn) return 1.0;
+            return __ddiv_rn((double)(mx - q), (double)(mx - mn));
+        }
+        case EPP_SCORER_LOAD_AWARE: {  // load_aware.go:43-52, 87-97
+            double thr = sc.param;
+            if (!(thr > 0.0)) thr = 128.0;
+            double w = (double)pool.waiting[e];
+            if (w == 0.0) return 0.5;
+            if (w > thr) w = thr;
+            return __dmul_rn(0.5, __dsub_rn(1.0, __ddiv_rn(w, thr)));
+        }
+        case EPP_SCORER_EXTERNAL: {
+            int col = (int)sc.param;
+            if (col < 0 || col >= pool.n_ext_cols) return 0.0;
+            return pool.ext[(size_t)col * (size_t)pool.E + (size_t)e];
+        }
+        default: return 0.0;
+    }
+}
+
+// Ordered weighted sum of one endpoint (runScorerPlugins, scheduler_profile.go:151-174).
+__device__ __forceinline__ double weighted_sum(const ProfileDev &pf, int32_t E, uint32_t e, int32_t match,
+                                               int32_t total) {
+    double acc = 0.0;
+#pragma unroll 1
+    for (int s = 0; s < pf.cfg.n_scorers; s++) {
+        double term;
+        if (pf.cfg.scorers[s].kind == EPP_SCORER_PREFIX)
+            term = __dmul_rn(clamp01(prefix_score(match, total)), pf.cfg.scorers[s].weight);
+        else
+            term = pf.contrib[(size_t)s * (size_t)E + e];
+        acc = __dadd_rn(acc, term);
+    }
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pool snapshot -> derived per-profile arrays
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_pool_candidates(PoolArrays pool, int filter, uint8_t *cand,
+                                                          int32_t *n_cand, int64_t *qminmax) {
+    __shared__ long long s_mn[2][32], s_mx[2][32];
+    __shared__ int s_cnt[32];
+    long long mnw = LLONG_MAX, mxw = LLONG_MIN, mnr = LLONG_MAX, mxr = LLONG_MIN;
+    int cnt = 0;
+    for (int e = threadIdx.x; e < pool.E; e += blockDim.x) {
+        bool k = filter_keeps(filter, pool.role[e]);
+        cand[e] = k ? 1 : 0;
+        if (k) {
+            long long w = pool.waiting[e], r = pool.running[e];
+            mnw = min(mnw, w); mxw = max(mxw, w);
+            mnr = min(mnr, r); mxr = max(mxr, r);
+            cnt++;
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        mnw = min(mnw, __shfl_xor_sync(0xffffffffu, mnw, o));
+        mxw = max(mxw, __shfl_xor_sync(0xffffffffu, mxw, o));
+        mnr = min(mnr, __shfl_xor_sync(0xffffffffu, mnr, o));
+        mxr = max(mxr, __shfl_xor_sync(0xffffffffu, mxr, o));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { s_mn[0][w] = mnw; s_mx[0][w] = mxw; s_mn[1][w] = mnr; s_mx[1][w] = mxr; s_cnt[w] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int nw = blockDim.x >> 5;
+        for (int i = 1; i < nw; i++) {
+            s_mn[0][0] = min(s_mn[0][0], s_mn[0][i]); s_mx[0][0] = max(s_mx[0][0], s_mx[0][i]);
+            s_mn[1][0] = min(s_mn[1][0], s_mn[1][i]); s_mx[1][0] = max(s_mx[1][0], s_mx[1][i]);
+            s_cnt[0] += s_cnt[i];
+        }
+        qminmax[0] = s_mn[0][0]; qminmax[1] = s_mx[0][0];
+        qminmax[2] = s_mn[1][0]; qminmax[3] = s_mx[1][0];
+        *n_cand = s_cnt[0];
+    }
+}
+
+__device__ __forceinline__ uint64_t desc_key(double x) {
+    // order-preserving map double -> u64 (ascending), then inverted so that an ASCENDING sort of the key
+    // yields DESCENDING scores.
+    uint64_t b = (uint64_t)__double_as_longlong(x);
+    uint64_t asc = (b & 0x8000000000000000ULL) ? ~b : (b | 0x8000000000000000ULL);
+    return ~asc;
+}
+
+__global__ void k_pool_terms(PoolArrays pool, epp_profile_cfg cfg, const uint8_t *cand, const int64_t *qminmax,
+                             double *contrib, double *base, uint64_t *sort_key, uint32_t *order, int32_t Epad) {
+    int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Epad) return;
+    if (e >= pool.E || !cand[e]) {
+        if (e < pool.E) {
+            base[e] = 0.0;
+            for (int s = 0; s < cfg.n_scorers; s++) contrib[(size_t)s * (size_t)pool.E + e] = 0.0;
+        }
+        sort_key[e] = 0xFFFFFFFFFFFFFFFFULL;
+        order[e] = (uint32_t)e;
+        return;
+    }
+    double acc = 0.0;
+    for (int s = 0; s < cfg.n_scorers; s++) {
+        double raw = cfg.scorers[s].kind == EPP_SCORER_PREFIX ? 0.0 : pool_score(cfg.scorers[s], pool, qminmax, e);
+        double term = __dmul_rn(clamp01(raw), cfg.scorers[s].weight);
+        contrib[(size_t)s * (size_t)pool.E + e] = term;
+        acc = __dadd_rn(acc, term);
+    }
+    base[e] = acc;
+    sort_key[e] = desc_key(acc);
+    order[e] = (uint32_t)e;
+}
+
+// Single-CTA bitonic sort of (sort_key asc, slot asc) over Epad (power of two) entries in global memory.
+__global__ void __launch_bounds__(1024) k_pool_sort(uint64_t *key, uint32_t *order, int32_t Epad) {
+    for (int32_t k = 2; k <= Epad; k <<= 1) {
+        for (int32_t j = k >> 1; j > 0; j >>= 1) {
+            for (int32_t i = threadIdx.x; i < Epad; i += blockDim.x) {
+                int32_t ixj = i ^ j;
+                if (ixj > i) {
+                    uint64_t ka = key[i], kb = key[ixj];
+                    uint32_t oa = order[i], ob = order[ixj];
+                    bool a_gt_b = ka > kb || (ka == kb && oa > ob);
+                    bool up = (i & k) == 0;
+                    if (up ? a_gt_b : !a_gt_b) {
+                        key[i] = kb; key[ixj] = ka;
+                        order[i] = ob; order[ixj] = oa;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void k_pool_groups(const double *base, const uint32_t *order, const int32_t *n_cand, uint32_t *grp_size) {
+    int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    int32_t n = *n_cand;
+    if (k >= n) return;
+    double b = base[order[k]];
+    if (k > 0 && base[order[k - 1]] == b) return;        // not a group leader
+    int32_t end = k + 1;
+    while (end < n && base[order[end]] == b) end++;
+    for (int32_t i = k; i < end; i++) grp_size[i] = (uint32_t)(end - k);
+}
+
+cudaError_t launch_pool_prepare(const PoolArrays &pool, const epp_profile_cfg &prof, const ProfileDerived &d,
+                                int32_t Epad, cudaStream_t s, int *launches) {
+    k_pool_candidates<<<1, 1024, 0, s>>>(pool, prof.filter, d.cand, d.n_cand, d.qminmax);
+    k_pool_terms<<<(Epad + 255) / 256, 256, 0, s>>>(pool, prof, d.cand, d.qminmax, d.contrib, d.base, d.sort_key,
+                                                    d.order, Epad);
+    k_pool_sort<<<1, 1024, 0, s>>>(d.sort_key, d.order, Epad);
+    k_pool_groups<<<(pool.E + 255) / 256, 256, 0, s>>>(d.base, d.order, d.n_cand, d.grp_size);
+    if (launches) *launches += 4;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp helpers
+// ------------------------------------------------------------------------------------------------
+struct Best {
+    double val;
+    uint32_t pick;
+    uint32_t ties;
+};
+__device__ __forceinline__ void best_init(Best &b) { b.val = -CUDART_INF; b.pick = EPP_NO_ENDPOINT; b.ties = 0; }
+__device__ __forceinline__ void best_add(Best &b, double v, uint32_t e, uint32_t n = 1) {
+    if (v > b.val) { b.val = v; b.pick = e; b.ties = n; }
+    else if (v == b.val) { b.ties += n; if (e < b.pick) b.pick = e; }
+}
+__device__ __forceinline__ Best best_warp_reduce(Best b) {
+    double m = b.val;
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    uint32_t pk = (b.ties && b.val == m) ? b.pick : EPP_NO_ENDPOINT;
+    uint32_t tc = (b.ties && b.val == m) ? b.ties : 0;
+    for (int o = 16; o; o >>= 1) {
+        pk = min(pk, __shfl_xor_sync(0xffffffffu, pk, o));
+        tc += __shfl_xor_sync(0xffffffffu, tc, o);
+    }
+    Best r;
+    r.val = m; r.pick = pk; r.ties = tc;
+    return r;
+}
+
+// PrefixBasedPDDecider.disaggregate, prefix_based_pd_decider.go:99-149
+__device__ __forceinline__ bool pd_decide(int64_t nct, int64_t in_len_bytes, int32_t match_blocks, int32_t bst) {
+    if (nct == 0) return false;
+    int64_t tokens = in_len_bytes / 4;                    // getUserInputLenInTokens, :152-167
+    if (tokens < nct) return false;
+    int64_t hit = (int64_t)match_blocks * (int64_t)bst;
+    return (tokens - hit) >= nct;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused lookup + match + score + pick: one warp per request
+// ------------------------------------------------------------------------------------------------
+constexpr int kListCap = 128;   // matched-endpoint list per request; beyond it the warp falls back to a dense scan
+constexpr int kPickWarps = 8;
+
+__device__ __forceinline__ uint32_t cnt_get(const uint32_t *cnt32, uint32_t e) {
+    return (cnt32[e >> 1] >> ((e & 1u) * 16u)) & 0xFFFFu;
+}
+
+__device__ __forceinline__ bool probe(const IndexView &ix, uint64_t h, uint32_t &off, uint32_t &cnt) {
+    if (h == kEmptyKey) { off = ix.special.off; cnt = ix.special.cnt; return cnt != 0; }
+    if (!ix.slots) return false;
+    uint64_t i = h & ix.mask;
+    for (;;) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(ix.slots + i));
+        uint64_t key = ((uint64_t)raw.y << 32) | raw.x;
+        if (raw.w == 0) return false;                     // empty slot terminates the probe sequence
+        if (key == h) { off = raw.z; cnt = raw.w; return true; }
+        i = (i + 1) & ix.mask;
+    }
+}
+
+// Evaluate one profile for the current request.  cnt32 holds the per-endpoint match counts; list/nl the
+// distinct matched endpoints (nl > kListCap => overflow => dense scan).
+__device__ inline Best eval_profile(const ProfileDev &pf, int32_t E, const uint32_t *cnt32, const uint32_t *list,
+                                    uint32_t nl, int32_t total, int lane) {
+    Best b;
+    best_init(b);
+    int32_t ncand = *pf.n_cand;
+    if (ncand == 0) return b;
+    if (nl <= (uint32_t)kListCap) {
+        for (uint32_t j = lane; j < nl; j += 32) {       // endpoints holding part of the prefix
+            uint32_t e = list[j];
+            if (pf.cand[e]) best_add(b, weighted_sum(pf, E, e, (int32_t)cnt_get(cnt32, e), total), e);
+        }
+        b = best_warp_reduce(b);
+        // best of everyone else = first unmatched entry of the (base desc, slot asc) order
+        for (int32_t k0 = 0; k0 < ncand; k0 += 32) {
+            int32_t k = k0 + lane;
+            uint32_t e = k < ncand ? pf.order[k] : EPP_NO_ENDPOINT;
+            bool un = k < ncand && cnt_get(cnt32, e) == 0;
+            uint32_t bal = __ballot_sync(0xffffffffu, un);
+            if (bal) {
+                int first = __ffs(bal) - 1;
+                uint32_t ue = __shfl_sync(0xffffffffu, e, first);
+                double ubase = pf.base[ue];
+                uint32_t gsz = pf.grp_size[k0 + first];
+                uint32_t same = 0;                        // matched candidates sharing that base value
+                for (uint32_t j = lane; j < nl; j += 32) {
+                    uint32_t me = list[j];
+                    if (pf.cand[me] && pf.base[me] == ubase) same++;
+                }
+                for (int o = 16; o; o >>= 1) same += __shfl_xor_sync(0xffffffffu, same, o);
+                best_add(b, ubase, ue, gsz - same);
+                break;
+            }
+        }
+    } else {
+        for (uint32_t e = lane; e < (uint32_t)E; e += 32) {
+            if (!pf.cand[e]) continue;
+            uint32_t c = cnt_get(cnt32, e);
+            best_add(b, c ? weighted_sum(pf, E, e, (int32_t)c, total) : pf.base[e], e);
+        }
+        b = best_warp_reduce(b);
+    }
+    return b;
+}
+
+__global__ void __launch_bounds__(kPickWarps * 32) k_match_pick(PickParams p, int32_t cnt_words,
+                                                                uint32_t *gscratch) {
+    extern __shared__ uint32_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int64_t gwarp = (int64_t)blockIdx.x * kPickWarps + warp;
+    const int64_t nwarps = (int64_t)gridDim.x * kPickWarps;
+    uint32_t *cnt32;
+    uint32_t *list;
+    if (gscratch) {
+        cnt32 = gscratch + (size_t)gwarp * (size_t)cnt_words;   // kept all-zero between requests
+        list = smem + warp * (kListCap + 4);
+    } else {
+        uint32_t *mine = smem + (size_t)warp * (size_t)(cnt_words + kListCap + 4);
+        cnt32 = mine;
+        list = mine + cnt_words;
+        for (int i = lane; i < cnt_words; i += 32) cnt32[i] = 0;
+    }
+    uint32_t *list_n = list + kListCap;
+    unsigned long long w_probes = 0, w_postings = 0;    // algorithmic work of this warp's requests
+    __syncwarp();
+
+    for (int64_t r = gwarp; r < p.R; r += nwarps) {
+        const int32_t total = p.nblocks[r];
+        if (lane == 0) *list_n = 0;
+        __syncwarp();
+        // ---- a2/a3: probe in block order, global stop at the first block nobody holds (plugin.go:214-230)
+        const uint64_t *row = p.hashes + r * (int64_t)p.max_blocks;
+        for (int32_t c0 = 0; c0 < total; c0 += 32) {
+            int32_t i = c0 + lane;
+            bool active = i < total;
+            uint32_t off = 0, cnt = 0;
+            bool hit = false;
+            if (active) hit = probe(p.index, row[i], off, cnt);
+            uint32_t miss = __ballot_sync(0xffffffffu, active && !hit);
+            int32_t limit = miss ? c0 + (__ffs(miss) - 1) : total;
+            if (active && i < limit) {
+                w_postings += cnt;
+                for (uint32_t k = 0; k < cnt; k++) {
+                    uint32_t e = p.index.postings[off + k];
+                    if (e >= p.index.ep_begin && e < p.index.ep_end && e < (uint32_t)p.E) {
+                        uint32_t sh = (e & 1u) * 16u;
+                        uint32_t old = atomicAdd(&cnt32[e >> 1], 1u << sh);
+                        if (((old >> sh) & 0xFFFFu) == 0) {
+                            uint32_t pos = atomicAdd(list_n, 1u);
+                            if (pos < (uint32_t)kListCap) list[pos] = e;
+                        }
+                    }
+                }
+            }
+            if (lane == 0) w_probes += (unsigned long long)((miss ? limit + 1 : min(total, c0 + 32)) - c0);
+            if (miss) break;
+        }
+        __syncwarp();
+        const uint32_t nl = *list_n;
+
+        // ---- a5-a10: primary profile
+        Best b0 = eval_profile(p.prof[0], p.E, cnt32, list, nl, total, lane);
+        epp_decision d;
+        d.status = b0.ties ? 0 : -1;
+        d.pick = b0.ties ? b0.pick : EPP_NO_ENDPOINT;
+        d.score = b0.ties ? b0.val : 0.0;
+        d.prefill_pick = EPP_NO_ENDPOINT;
+        d.tie_count = b0.ties;
+        d.total_blocks = total;
+        d.match_blocks = b0.ties ? (int32_t)cnt_get(cnt32, b0.pick) : 0;
+        epp_decision_detail dd;
+        dd.prefill_score = 0.0; dd.prefill_tie_count = 0; dd.prefill_ran = 0;
+        // ---- a13: decode -> decider -> prefill (disagg_profile_handler.go:264-308)
+        if (p.n_profiles == 2 && b0.ties) {
+            bool go = p.always_disagg || pd_decide(p.non_cached_tokens, p.in_len[r], d.match_blocks, p.block_size_tokens);
+            if (go) {
+                dd.prefill_ran = 1;
+                Best b1 = eval_profile(p.prof[1], p.E, cnt32, list, nl, total, lane);
+                if (b1.ties) { d.prefill_pick = b1.pick; dd.prefill_score = b1.val; dd.prefill_tie_count = b1.ties; }
+            }
+        }
+        if (lane == 0) {
+            p.out[r] = d;
+            if (p.detail) p.detail[r] = dd;
+        }
+        // ---- a4: dense match row (Produce parity mode only)
+        if (p.out_match) {
+            int32_t *mrow = p.out_match + r * (int64_t)p.E;
+            if (nl <= (uint32_t)kListCap) {
+                for (int32_t e = lane; e < p.E; e += 32) mrow[e] = 0;
+                __syncwarp();
+                for (uint32_t j = lane; j < nl; j += 32) mrow[list[j]] = (int32_t)cnt_get(cnt32, list[j]);
+            } else {
+                for (int32_t e = lane; e < p.E; e += 32) mrow[e] = (int32_t)cnt_get(cnt32, (uint32_t)e);
+            }
+        }
+        __syncwarp();
+        // ---- reset the counters this request touched
+        if (nl <= (uint32_t)kListCap) {
+            for (uint32_t j = lane; j < nl; j += 32) cnt32[list[j] >> 1] = 0;
+        } else {
+            for (int i = lane; i < cnt_words; i += 32) cnt32[i] = 0;
+        }
+        __syncwarp();
+    }
+    if (p.work_counters) {
+        for (int o = 16; o; o >>= 1) w_postings += __shfl_xor_sync(0xffffffffu, w_postings, o);
+        if (lane == 0) {
+            atomicAdd(&p.work_counters[0], w_probes);
+            atomicAdd(&p.work_counters[1], w_postings);
+        }
+    }
+}
+
+// The engine allocates gscratch when E does not fit in shared memory; see engine.cu.
+size_t match_pick_smem_bytes(int32_t E, bool global_counts) {
+    int32_t cnt_words = (E + 1) / 2;
+    size_t per_warp = (size_t)(global_counts ? 0 : cnt_words) + kListCap + 4;
+    return per_warp * sizeof(uint32_t) * kPickWarps;
+}
+int match_pick_warps_per_cta() { return kPickWarps; }
+
+cudaError_t launch_match_pick(const PickParams &p, uint32_t *gscratch, int grid, size_t smem, cudaStream_t s,
+                                  int *launches) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_match_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    int32_t cnt_words = (p.E + 1) / 2;
+    k_match_pick<<<grid, kPickWarps * 32, smem, s>>>(p, cnt_words, gscratch);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// decision logic on injected dense match info (KAT / plugin-parity mode)
+// ------------------------------------------------------------------------------------------------
+__device__ inline Best eval_profile_dense(const ProfileDev &pf, int32_t E, const int32_t *mrow, int32_t total,
+                                          int lane) {
+    Best b;
+    best_init(b);
+    for (uint32_t e = lane; e < (uint32_t)E; e += 32) {
+        if (!pf.cand[e]) continue;
+        best_add(b, weighted_sum(pf, E, e, mrow[e], total), e);
+    }
+    return best_warp_reduce(b);
+}
+
+__global__ void __launch_bounds__(256) k_dense_pick(DensePickParams p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= p.R) return;
+    const int32_t *mrow = p.match + r * (int64_t)p.E;
+    int32_t total = p.total[r];
+    Best b0 = eval_profile_dense(p.prof[0], p.E, mrow, total, lane);
+    epp_decision d;
+    d.status = b0.ties ? 0 : -1;
+    d.pick = b0.ties ? b0.pick : EPP_NO_ENDPOINT;
+    d.score = b0.ties ? b0.val : 0.0;
+    d.prefill_pick = EPP_NO_ENDPOINT;
+    d.tie_count = b0.ties;
+    d.total_blocks = total;
+    d.match_blocks = b0.ties ? mrow[b0.pick] : 0;
+    epp_decision_detail dd;
+    dd.prefill_score = 0.0; dd.prefill_tie_count = 0; dd.prefill_ran = 0;
+    if (p.n_profiles == 2 && b0.ties) {
+        bool go = p.always_disagg || pd_decide(p.non_cached_tokens, p.in_len ? p.in_len[r] : 0, d.match_blocks,
+                                                p.block_size_tokens);
+        if (go) {
+            dd.prefill_ran = 1;
+            Best b1 = eval_profile_dense(p.prof[1], p.E, mrow, total, lane);
+            if (b1.ties) { d.prefill_pick = b1.pick; dd.prefill_score = b1.val; dd.prefill_tie_count = b1.ties; }
+        }
+    }
+    if (lane == 0) {
+        p.out[r] = d;
+        if (p.detail) p.detail[r] = dd;
+    }
+}
+
+cudaError_t launch_dense_pick(const DensePickParams &p, cudaStream_t s, int *launches) {
+    if (p.R <= 0) return cudaSuccess;
+    int64_t threads = p.R * 32;
+    k_dense_pick<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(p);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+// Scorer.Score parity (dense [R][E] output).
+__global__ void k_score_dense(int64_t R, int32_t E, ProfileDev pf, PoolArrays pool, const int64_t *qminmax,
+                              const int32_t *match, const int32_t *total, int32_t scorer_index, double *out) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= R * (int64_t)E) return;
+    int64_t r = idx / E;
+    int32_t e = (int32_t)(idx % E);
+    bool c = pf.cand[e] != 0;
+    double v;
+    if (scorer_index < 0) {
+        v = c ? weighted_sum(pf, E, (uint32_t)e, match[idx], total[r]) : -1.0;
+    } else if (!c) {
+        v = 0.0;
+    } else {
+        const epp_scorer_cfg &sc = pf.cfg.scorers[scorer_index];
+        v = sc.kind == EPP_SCORER_PREFIX ? prefix_score(match[idx], total[r]) : pool_score(sc, pool, qminmax, e);
+    }
+    out[idx] = v;
+}
+
+cudaError_t launch_score_dense(int64_t R, int32_t E, const ProfileDev &prof, const PoolArrays &pool,
+                               const int64_t *qminmax, const int32_t *match, const int32_t *total,
+                               int32_t scorer_index, double *out, cudaStream_t s, int *launches) {
+    int64_t n = R * (int64_t)E;
+    if (n <= 0) return cudaSuccess;
+    k_score_dense<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(R, E, prof, pool, qminmax, match, total, scorer_index,
+                                                             out);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace epp

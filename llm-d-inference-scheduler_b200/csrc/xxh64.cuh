@@ -1,0 +1,122 @@
+// xxh64.cuh -- device-side XXH64 primitives (seed 0 chain of approximateprefix/hashing.go:71-96).
+//
+// The message hashed for block i is  M_i = block_i_bytes || LE64(h_{i-1})  (hashing.go:82-83), so for a block of
+// n bytes the digest splits into
+//   (A) the stripe rounds over the floor(n/32) 32-byte stripes made of block bytes only -- independent of the
+//       chain, embarrassingly parallel over (request, block);
+//   (B) the serial part: [one more stripe if (n mod 32) + 8 >= 32] -> merge -> += len -> tail rounds over the
+//       remaining (< 32) bytes, which contain LE64(h_{i-1}) -> avalanche.
+// For block sizes that are a multiple of 32 bytes (every multiple of 8 tokens, incl. the default 16) part (B)
+// is: m + len, one 8-byte tail round with h_{i-1}, avalanche  (SURVEY.md App. A.1).
+#pragma once
+#include <stdint.h>
+
+namespace epp {
+
+constexpr uint64_t XP1 = 0x9E3779B185EBCA87ULL;
+constexpr uint64_t XP2 = 0xC2B2AE3D27D4EB4FULL;
+constexpr uint64_t XP3 = 0x165667B19E3779F9ULL;
+constexpr uint64_t XP4 = 0x85EBCA77C2B2AE63ULL;
+constexpr uint64_t XP5 = 0x27D4EB2F165667C5ULL;
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) {
+    // funnel shifts: 2 SHF per 64-bit rotate
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    uint32_t nlo, nhi;
+    if (r < 32) {
+        nhi = __funnelshift_l(lo, hi, r);
+        nlo = __funnelshift_l(hi, lo, r);
+    } else {
+        nhi = __funnelshift_l(hi, lo, r - 32);
+        nlo = __funnelshift_l(lo, hi, r - 32);
+    }
+    return ((uint64_t)nhi << 32) | nlo;
+}
+
+__device__ __forceinline__ uint64_t xxh_round(uint64_t acc, uint64_t x) {
+    return rotl64(acc + x * XP2, 31) * XP1;
+}
+__device__ __forceinline__ uint64_t xxh_merge(uint64_t h, uint64_t v) {
+    return (h ^ xxh_round(0, v)) * XP1 + XP4;
+}
+__device__ __forceinline__ uint64_t xxh_avalanche(uint64_t h) {
+    h ^= h >> 33;
+    h *= XP2;
+    h ^= h >> 29;
+    h *= XP3;
+    h ^= h >> 32;
+    return h;
+}
+__device__ __forceinline__ void xxh_init(uint64_t v[4]) {
+    v[0] = XP1 + XP2;
+    v[1] = XP2;
+    v[2] = 0;
+    v[3] = 0ULL - XP1;
+}
+__device__ __forceinline__ uint64_t xxh_merge_all(const uint64_t v[4]) {
+    uint64_t h = rotl64(v[0], 1) + rotl64(v[1], 7) + rotl64(v[2], 12) + rotl64(v[3], 18);
+    h = xxh_merge(h, v[0]);
+    h = xxh_merge(h, v[1]);
+    h = xxh_merge(h, v[2]);
+    h = xxh_merge(h, v[3]);
+    return h;
+}
+
+// Fast chain step for a block whose byte length n is a multiple of 32: m = merged stripe state.
+__device__ __forceinline__ uint64_t xxh_chain_step32(uint64_t m, uint64_t len_plus8, uint64_t prev) {
+    uint64_t h = m + len_plus8;
+    h ^= xxh_round(0, prev);
+    h = rotl64(h, 27) * XP1 + XP4;
+    return xxh_avalanche(h);
+}
+
+__device__ __forceinline__ uint64_t load_le64(const uint8_t *p) {
+    uint64_t x = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) x |= (uint64_t)p[k] << (8 * k);
+    return x;
+}
+__device__ __forceinline__ uint32_t load_le32(const uint8_t *p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+// Generic finish: the stripe state v (valid iff have_v) covers `consumed` bytes; `tail`/`tail_len` are the
+// remaining message bytes (tail_len < 64), total_len = consumed + tail_len.  Any layout of XXH64 is covered:
+// if total_len >= 32 and the tail still holds a full stripe it is consumed first.
+__device__ inline uint64_t xxh_finish(uint64_t v[4], bool have_v, uint64_t total_len, const uint8_t *tail,
+                                      int tail_len) {
+    uint64_t h;
+    int p = 0;
+    if (total_len >= 32) {
+        if (!have_v) xxh_init(v);
+        while (p + 32 <= tail_len) {
+            v[0] = xxh_round(v[0], load_le64(tail + p));
+            v[1] = xxh_round(v[1], load_le64(tail + p + 8));
+            v[2] = xxh_round(v[2], load_le64(tail + p + 16));
+            v[3] = xxh_round(v[3], load_le64(tail + p + 24));
+            p += 32;
+        }
+        h = xxh_merge_all(v);
+    } else {
+        h = XP5;
+    }
+    h += total_len;
+    while (p + 8 <= tail_len) {
+        h ^= xxh_round(0, load_le64(tail + p));
+        h = rotl64(h, 27) * XP1 + XP4;
+        p += 8;
+    }
+    if (p + 4 <= tail_len) {
+        h ^= (uint64_t)load_le32(tail + p) * XP1;
+        h = rotl64(h, 23) * XP2 + XP3;
+        p += 4;
+    }
+    while (p < tail_len) {
+        h ^= (uint64_t)tail[p] * XP5;
+        h = rotl64(h, 11) * XP1;
+        p++;
+    }
+    return xxh_avalanche(h);
+}
+
+}  // namespace epp

@@ -1,0 +1,286 @@
+"""Engine: a thin Python handle over the C ABI (include/epp_engine.h).  All compute happens in the CUDA kernels
+behind libepp_engine.so; this module only marshals numpy arrays (host pointers) or torch CUDA tensors (device
+pointers, EPP_BATCH_DEVICE_PTRS) into plain pointers and sizes."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _capi as capi
+
+DECISION_DTYPE = np.dtype([("status", "<i4"), ("pick", "<u4"), ("score", "<f8"), ("prefill_pick", "<u4"),
+                           ("tie_count", "<u4"), ("total_blocks", "<i4"), ("match_blocks", "<i4")])
+DETAIL_DTYPE = np.dtype([("prefill_score", "<f8"), ("prefill_tie_count", "<u4"), ("prefill_ran", "<u4")])
+SHARD_BEST_DTYPE = np.dtype([("score", "<f8"), ("pick", "<u4"), ("tie_count", "<u4"), ("match_blocks", "<i4"),
+                             ("status", "<i4")])
+assert DECISION_DTYPE.itemsize == 32 and DETAIL_DTYPE.itemsize == 16 and SHARD_BEST_DTYPE.itemsize == 24
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"epp_engine error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+@dataclass
+class ScorerSpec:
+    kind: int
+    weight: float = 1.0
+    param: float = 0.0
+
+
+@dataclass
+class ProfileSpec:
+    """One SchedulerProfile: role filter -> scorers in order -> max-score picker."""
+    filter: int = capi.FILTER_NONE
+    scorers: list = field(default_factory=list)
+
+
+def _fill_profile(dst: capi.ProfileCfg, spec: ProfileSpec):
+    if len(spec.scorers) > capi.EPP_MAX_SCORERS:
+        raise ValueError("too many scorers")
+    dst.filter = spec.filter
+    dst.n_scorers = len(spec.scorers)
+    for i, s in enumerate(spec.scorers):
+        if not isinstance(s, ScorerSpec):
+            s = ScorerSpec(*s)
+        dst.scorers[i].kind = s.kind
+        dst.scorers[i].weight = s.weight
+        dst.scorers[i].param = s.param
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if _is_torch(x):
+        return C.c_void_p(x.data_ptr())
+    return x.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    def __init__(self, max_endpoints: int, primary: ProfileSpec | None = None, prefill: ProfileSpec | None = None,
+                 *, device: int = 0, block_size_tokens: int = 16, max_prefix_blocks: int = 256,
+                 lru_capacity_per_server: int = 31250, non_cached_tokens: int = 0, always_disagg: bool = False,
+                 n_ext_cols: int = 0):
+        self._lib = capi.load()
+        cfg = capi.Config()
+        self._lib.epp_config_default(C.byref(cfg))
+        cfg.device = device
+        cfg.max_endpoints = max_endpoints
+        cfg.block_size_tokens = block_size_tokens
+        cfg.max_prefix_blocks = max_prefix_blocks
+        cfg.lru_capacity_per_server = lru_capacity_per_server
+        cfg.non_cached_tokens = non_cached_tokens
+        cfg.always_disagg = int(always_disagg)
+        cfg.n_ext_cols = n_ext_cols
+        if primary is not None:
+            _fill_profile(cfg.primary, primary)
+        if prefill is not None:
+            cfg.handler = capi.HANDLER_DISAGG
+            _fill_profile(cfg.prefill, prefill)
+        self.cfg = cfg
+        self.E = max_endpoints
+        self.B = max_prefix_blocks
+        self._h = C.c_void_p()
+        self._check(self._lib.epp_engine_create(C.byref(cfg), C.byref(self._h)))
+
+    # ---- plumbing ----
+    def _check(self, rc: int):
+        if rc != 0:
+            raise EngineError(rc, (self._lib.epp_last_error() or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.epp_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- models / pool / index ----
+    def register_model(self, model: bytes, salt: bytes = b"") -> int:
+        mid = C.c_uint32()
+        self._check(self._lib.epp_model_register(self._h, model, len(model), salt, len(salt), C.byref(mid)))
+        return mid.value
+
+    def model_seed(self, model_id: int) -> int:
+        out = C.c_uint64()
+        self._check(self._lib.epp_model_seed(self._h, model_id, C.byref(out)))
+        return out.value
+
+    def pool_set(self, ids, role, kv_usage, waiting, running=None, ext=None):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        n = ids.shape[0]
+        role = np.ascontiguousarray(role, dtype=np.uint8)
+        kv = np.ascontiguousarray(kv_usage, dtype=np.float64)
+        w = np.ascontiguousarray(waiting, dtype=np.int32)
+        run = None if running is None else np.ascontiguousarray(running, dtype=np.int32)
+        ex = None if ext is None else np.ascontiguousarray(ext, dtype=np.float64).reshape(-1, n)
+        assert role.shape[0] == n and kv.shape[0] == n and w.shape[0] == n
+        self._check(self._lib.epp_pool_set(self._h, n, _ptr(ids), _ptr(role), _ptr(kv), _ptr(w), _ptr(run), _ptr(ex)))
+
+    def index_add(self, ep: int, hashes, num_gpu_blocks: int = 0):
+        hs = np.ascontiguousarray(hashes, dtype=np.uint64)
+        self._check(self._lib.epp_index_add(self._h, ep, hs.shape[0], _ptr(hs), num_gpu_blocks))
+
+    def index_remove_endpoint(self, ep: int):
+        self._check(self._lib.epp_index_remove_endpoint(self._h, ep))
+
+    def index_load_snapshot(self, hashes, eps):
+        hs = np.ascontiguousarray(hashes, dtype=np.uint64)
+        es = np.ascontiguousarray(eps, dtype=np.uint32)
+        assert hs.shape == es.shape
+        self._check(self._lib.epp_index_load_snapshot(self._h, hs.shape[0], _ptr(hs), _ptr(es)))
+
+    def index_commit(self):
+        self._check(self._lib.epp_index_commit(self._h))
+
+    def index_get(self, h: int) -> set:
+        out = np.zeros(4096, dtype=np.uint32)
+        n = C.c_int32()
+        self._check(self._lib.epp_index_get(self._h, h, _ptr(out), out.shape[0], C.byref(n)))
+        return set(int(x) for x in out[:min(n.value, out.shape[0])])
+
+    def index_add_picked(self):
+        self._check(self._lib.epp_index_add_picked(self._h))
+
+    # ---- batches ----
+    def _batch(self, data, offsets=None, uniform_len=None, model_ids=None, n_requests=None):
+        """data: bytes-like numpy array / torch CUDA tensor (any dtype, viewed as bytes)."""
+        b = capi.Batch()
+        dev = _is_torch(data)
+        keep = [data]
+        if dev:
+            if not data.is_cuda:
+                raise ValueError("torch batches must be CUDA tensors (device-pointer mode)")
+            b.flags = capi.EPP_BATCH_DEVICE_PTRS
+            nbytes = data.numel() * data.element_size()
+        else:
+            data = np.ascontiguousarray(data)
+            keep[0] = data
+            nbytes = data.nbytes
+        b.data = _ptr(data)
+        if offsets is not None:
+            if dev:
+                assert _is_torch(offsets) and offsets.is_cuda
+                R = offsets.numel() - 1
+            else:
+                offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+                R = offsets.shape[0] - 1
+            keep.append(offsets)
+            b.offsets = _ptr(offsets)
+        else:
+            if uniform_len is None:
+                raise ValueError("offsets or uniform_len required")
+            R = n_requests if n_requests is not None else (nbytes // uniform_len if uniform_len else 0)
+            b.uniform_len = uniform_len
+        if model_ids is not None:
+            if not dev:
+                model_ids = np.ascontiguousarray(model_ids, dtype=np.uint32)
+            keep.append(model_ids)
+            b.model_ids = _ptr(model_ids)
+        b.n_requests = R
+        return b, R, dev, keep
+
+    def hash_prompts(self, data, offsets=None, uniform_len=None, model_ids=None, n_requests=None, out=None):
+        """a1 hashPrompt -> (hashes [R, max_prefix_blocks] u64, nblocks [R] i32)."""
+        b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests)
+        if dev:
+            import torch
+            hashes = torch.empty((max(R, 1), self.B), dtype=torch.int64, device=data.device) if out is None else out[0]
+            nb = torch.empty(max(R, 1), dtype=torch.int32, device=data.device) if out is None else out[1]
+        else:
+            hashes = np.zeros((R, self.B), dtype=np.uint64)
+            nb = np.zeros(R, dtype=np.int32)
+        self._check(self._lib.epp_hash_prompts(self._h, C.byref(b), _ptr(hashes), _ptr(nb)))
+        return hashes, nb
+
+    def prefix_match(self, data, offsets=None, uniform_len=None, model_ids=None, n_requests=None):
+        """a1-a4 Produce -> (match [R, E] i32, total [R] i32)."""
+        b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests)
+        if dev:
+            import torch
+            match = torch.empty((max(R, 1), self.E), dtype=torch.int32, device=data.device)
+            total = torch.empty(max(R, 1), dtype=torch.int32, device=data.device)
+        else:
+            match = np.zeros((R, self.E), dtype=np.int32)
+            total = np.zeros(R, dtype=np.int32)
+        self._check(self._lib.epp_prefix_match(self._h, C.byref(b), _ptr(match), _ptr(total)))
+        return match, total
+
+    def score(self, match, total, profile: int = 0, scorer_index: int = -1):
+        """a5-a9 Scorer.Score / weighted sum -> [R, E] f64 (host arrays)."""
+        match = np.ascontiguousarray(match, dtype=np.int32).reshape(-1, self.E)
+        total = np.ascontiguousarray(total, dtype=np.int32)
+        R = match.shape[0]
+        out = np.zeros((R, self.E), dtype=np.float64)
+        self._check(self._lib.epp_score(self._h, R, _ptr(match), _ptr(total), profile, scorer_index, _ptr(out), 0))
+        return out
+
+    def schedule(self, data, offsets=None, uniform_len=None, model_ids=None, n_requests=None, keep_hashes=False,
+                 detail=True, out=None):
+        """a1-a14 Scheduler.Schedule for a batch -> (decisions, details)."""
+        b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests)
+        if dev:
+            import torch
+            dec = out if out is not None else torch.empty((max(R, 1), 32), dtype=torch.uint8, device=data.device)
+            det = torch.empty((max(R, 1), 16), dtype=torch.uint8, device=data.device) if detail else None
+        else:
+            dec = np.zeros(R, dtype=DECISION_DTYPE) if out is None else out
+            det = np.zeros(R, dtype=DETAIL_DTYPE) if detail else None
+        self._check(self._lib.epp_schedule(self._h, C.byref(b), _ptr(dec), _ptr(det), int(keep_hashes)))
+        return dec, det
+
+    def schedule_with_match(self, match, total, input_len_bytes=None, block_size_tokens: int = 0):
+        match = np.ascontiguousarray(match, dtype=np.int32).reshape(-1, self.E)
+        total = np.ascontiguousarray(total, dtype=np.int32)
+        R = match.shape[0]
+        il = None if input_len_bytes is None else np.ascontiguousarray(input_len_bytes, dtype=np.int64)
+        dec = np.zeros(R, dtype=DECISION_DTYPE)
+        det = np.zeros(R, dtype=DETAIL_DTYPE)
+        self._check(self._lib.epp_schedule_with_match(self._h, R, _ptr(match), _ptr(total), _ptr(il),
+                                                      block_size_tokens, _ptr(dec), _ptr(det), 0))
+        return dec, det
+
+    def stats(self) -> dict:
+        s = capi.Stats()
+        self._check(self._lib.epp_get_stats(self._h, C.byref(s)))
+        d = {k: getattr(s, k) for k, _ in capi.Stats._fields_}
+        d["last_kernel_ms"] = list(s.last_kernel_ms)
+        return d
+
+    # ---- endpoint-sharded mode (device pointers only) ----
+    def shard_set(self, ep_begin: int, ep_end: int):
+        self._check(self._lib.epp_shard_set(self._h, ep_begin, ep_end))
+
+    def shard_probe(self, data, out_masks, offsets=None, uniform_len=None, model_ids=None, n_requests=None):
+        b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests)
+        self._check(self._lib.epp_shard_probe(self._h, C.byref(b), _ptr(out_masks)))
+        return R
+
+    def shard_pick(self, n_requests, global_masks, out_best):
+        self._check(self._lib.epp_shard_pick(self._h, n_requests, _ptr(global_masks), _ptr(out_best)))
+
+    def shard_merge(self, n_requests, n_ranks, all_best, out_decisions):
+        self._check(self._lib.epp_shard_merge(self._h, n_requests, n_ranks, _ptr(all_best), _ptr(out_decisions)))
+
+
+def decisions_from_torch(t) -> np.ndarray:
+    """View a [R, 32] uint8 CUDA tensor of epp_decision records as a host structured array."""
+    return t.cpu().numpy().view(DECISION_DTYPE).reshape(-1)

@@ -1,0 +1,465 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) vs the CPU oracle on the same seeded inputs, vs the
+committed golden vectors, and through the reference-interface mirror (KATs of the reference's own tests).
+Bar: bit-exact for hashes / counts / picks, bit-exact fp64 score bits.  Run on the B200 box: pytest -m gpu."""
+import json
+import os
+import random
+import struct
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "xxh64_vectors.json")
+
+
+@pytest.fixture(scope="module")
+def epp():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import epp_b200
+    epp_b200.build.build()
+    return epp_b200
+
+
+@pytest.fixture(scope="module")
+def tg():
+    from tools import tracegen
+    tracegen.build()
+    return tracegen
+
+
+def _pack(prompts):
+    offs = np.zeros(len(prompts) + 1, dtype=np.uint64)
+    np.cumsum([len(p) for p in prompts], out=offs[1:])
+    blob = b"".join(prompts)
+    data = np.frombuffer(blob, dtype=np.uint8).copy() if blob else np.zeros(16, np.uint8)
+    return data, offs
+
+
+def _pack_aligned(prompts, align=16):
+    offs = np.zeros(len(prompts) + 1, dtype=np.uint64)
+    chunks, pos = [], 0
+    starts = []
+    for p in prompts:
+        pad = (-pos) % align
+        chunks.append(b"\0" * pad)
+        pos += pad
+        starts.append(pos)
+        chunks.append(p)
+        pos += len(p)
+    return np.frombuffer(b"".join(chunks) + b"\0" * 16, dtype=np.uint8).copy(), starts
+
+
+# ------------------------------------------------------------------------------------------------
+# a1 hashing
+# ------------------------------------------------------------------------------------------------
+def test_model_seed(epp, orc):
+    with epp.Engine(8) as eng:
+        for m, s in ((b"test-model1", b""), (b"synthetic-model", b""), (b"test-model1", b"s1"), (b"", b""),
+                     (b"x" * 100, b"y" * 33)):
+            mid = eng.register_model(m, s)
+            assert eng.model_seed(mid) == orc.xxh64(m + s)
+        assert eng.model_seed(0) == 0x55B9CE9184DD8509
+
+
+def test_hash_golden_vectors(epp):
+    """Every prompt vector of tests/golden/xxh64_vectors.json (python-xxhash), each with its own engine config."""
+    with open(GOLD) as f:
+        gold = json.load(f)
+    for v in gold["prompts"]:
+        data = bytes.fromhex(v["data_hex"])
+        want = [int(h, 16) for h in v["hashes"]]
+        with epp.Engine(8, block_size_tokens=v["block_size_tokens"], max_prefix_blocks=v["max_blocks"]) as eng:
+            mid = eng.register_model(v["model"].encode(), v["salt"].encode())
+            d, offs = _pack([data])
+            hs, nb = eng.hash_prompts(d, offsets=offs, model_ids=np.array([mid], np.uint32))
+            assert nb[0] == len(want), v["name"]
+            assert [int(x) for x in hs[0, : nb[0]]] == want, v["name"]
+
+
+@pytest.mark.parametrize("bst", [1, 2, 3, 6, 7, 8, 16, 24, 32])
+def test_hash_ragged_vs_oracle(epp, orc, bst):
+    """Ragged batch (empty, shorter than a block, partial tail, truncated) for block sizes hitting every XXH64 tail
+    class: bs%32==0 (vector path), bs%32 in {24,28} (mixed stripe), tiny blocks (<32 bytes, no stripe)."""
+    rng = random.Random(bst)
+    maxb = 12
+    prompts = [b"", b"a", bytes(rng.getrandbits(8) for _ in range(bst * 4 - 1)), bytes(rng.getrandbits(8) for _ in range(bst * 4))]
+    for _ in range(60):
+        n = rng.randint(0, bst * 4 * (maxb + 3))
+        prompts.append(bytes(rng.getrandbits(8) for _ in range(n)))
+    with epp.Engine(8, block_size_tokens=bst, max_prefix_blocks=maxb) as eng:
+        mid = eng.register_model(b"mdl")
+        # (a) tightly packed (unaligned offsets -> generic path)
+        d, offs = _pack(prompts)
+        hs, nb = eng.hash_prompts(d, offsets=offs)
+        for i, p in enumerate(prompts):
+            want = orc.hash_prompt(p, b"mdl", bst, maxb)
+            assert nb[i] == len(want), (i, len(p))
+            assert [int(x) for x in hs[i, : nb[i]]] == want, (i, len(p))
+        # (b) 16-byte aligned prompt starts with explicit offsets (vector path when bs % 32 == 0)
+        d2, starts = _pack_aligned(prompts)
+        offs2 = np.array(starts + [starts[-1] + len(prompts[-1])], dtype=np.uint64)
+        # offsets[r+1]-offsets[r] must equal the prompt length: use per-request spans via a gather copy
+        for i in (0, 1, 2, 3, 10, 33):
+            di = np.zeros(((len(prompts[i]) + 31) // 16) * 16 + 16, np.uint8)
+            di[: len(prompts[i])] = np.frombuffer(prompts[i], np.uint8)
+            h1, n1 = eng.hash_prompts(di, offsets=np.array([0, len(prompts[i])], np.uint64))
+            assert [int(x) for x in h1[0, : n1[0]]] == orc.hash_prompt(prompts[i], b"mdl", bst, maxb)
+        assert mid == 0
+
+
+def test_hash_uniform_tokens_vs_oracle(epp, orc):
+    """uint32 token arrays (4 bytes/token), T = 4096 -> 256 blocks of 64 bytes (BASELINE config 3 shape), host and
+    device-pointer batches."""
+    import torch
+    rng = np.random.default_rng(3)
+    R, T = 96, 4096
+    toks = rng.integers(0, 128000, size=(R, T), dtype=np.uint32)
+    with epp.Engine(8) as eng:
+        eng.register_model(b"synthetic-model")
+        hs, nb = eng.hash_prompts(toks, uniform_len=T * 4)
+        assert (nb == 256).all()
+        for r in (0, 1, 50, R - 1):
+            want = orc.hash_prompt(toks[r].tobytes(), b"synthetic-model", 16, 256)
+            assert [int(x) for x in hs[r]] == want
+        dt = torch.from_numpy(toks.view(np.int32)).cuda()
+        hd, nd = eng.hash_prompts(dt, uniform_len=T * 4)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(hd.cpu().numpy().view(np.uint64), hs)
+        np.testing.assert_array_equal(nd.cpu().numpy(), nb)
+        # prefix property (size-independent): changing token t only changes hashes of blocks >= t // 16
+        t2 = toks.copy()
+        t2[:, 1000] ^= 1
+        h2, _ = eng.hash_prompts(t2, uniform_len=T * 4)
+        blk = 1000 // 16
+        assert (h2[:, :blk] == hs[:, :blk]).all() and (h2[:, blk:] != hs[:, blk:]).all()
+
+
+def test_hash_truncation_and_short(epp, orc):
+    toks = np.arange(40, dtype=np.uint32)
+    with epp.Engine(8, max_prefix_blocks=2) as eng:
+        eng.register_model(b"synthetic-model")
+        hs, nb = eng.hash_prompts(toks, uniform_len=160)
+        assert nb[0] == 2 and [int(x) for x in hs[0, :2]] == [0x8A787856B0C98B2D, 0xC57021EFCC0A8595]
+    with epp.Engine(8) as eng:
+        eng.register_model(b"synthetic-model")
+        hs, nb = eng.hash_prompts(toks, uniform_len=160)
+        assert [int(x) for x in hs[0, :3]] == [0x8A787856B0C98B2D, 0xC57021EFCC0A8595, 0xA8A7E535C242C990]
+        hs, nb = eng.hash_prompts(toks[:15], uniform_len=60)         # shorter than one block -> nil
+        assert nb[0] == 0
+        hs, nb = eng.hash_prompts(np.zeros(16, np.uint8), offsets=np.zeros(1, np.uint64))   # empty batch
+        assert hs.shape[0] == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# a2 index (write side mirror + device table)
+# ------------------------------------------------------------------------------------------------
+def test_index_mirror_vs_oracle_indexer(epp, orc):
+    rng = random.Random(5)
+    with epp.Engine(16, lru_capacity_per_server=5) as eng:
+        ix = orc.Indexer(5)
+        for step in range(1500):
+            op = rng.random()
+            srv = rng.randrange(8)
+            if op < 0.85:
+                hs = [rng.randrange(60) for _ in range(rng.randint(1, 8))]
+                cap = rng.choice([0, 3, 7])
+                eng.index_add(srv, hs, cap)
+                ix.add(hs, srv, cap)
+            elif op < 0.92:
+                eng.index_remove_endpoint(srv)
+                ix.remove_pod(srv)
+            if step % 100 == 99:
+                for h in range(60):
+                    assert eng.index_get(h) == ix.get(h), (step, h)
+
+
+def test_index_kats(epp):
+    """indexer_test.go:27-113 re-encoded against the engine."""
+    with epp.Engine(8, lru_capacity_per_server=3) as eng:
+        eng.index_add(7, [1], 2)
+        assert eng.index_get(1) == {7}
+        eng.index_add(7, [2], 2)
+        eng.index_add(7, [3], 2)
+        assert eng.index_get(4) == set() and eng.index_get(1) == set()
+        assert eng.index_get(2) == {7} and eng.index_get(3) == {7}
+    with epp.Engine(8, lru_capacity_per_server=10) as eng:
+        for j in range(10):
+            eng.index_add(1, [j])
+            eng.index_add(2, [j])
+        eng.index_add(1, [10])
+        assert eng.index_get(0) == {2}
+        eng.index_remove_endpoint(2)
+        assert eng.index_get(0) == set()
+        for j in range(1, 11):
+            assert eng.index_get(j) == {1}
+    with epp.Engine(8) as eng:                       # the all-ones key uses the side record
+        eng.index_load_snapshot([0xFFFFFFFFFFFFFFFF, 0xFFFFFFFFFFFFFFFF, 5, 5, 5], [1, 2, 3, 3, 4])
+        assert eng.index_get(0xFFFFFFFFFFFFFFFF) == {1, 2}
+        assert eng.index_get(5) == {3, 4}            # duplicate pair removed
+        assert eng.index_get(6) == set()
+
+
+# ------------------------------------------------------------------------------------------------
+# a3/a4 match, a5-a9 scores, a10-a14 decisions on scaled BASELINE configs
+# ------------------------------------------------------------------------------------------------
+def _scaled(tg, name):
+    c = tg.baseline_configs()
+    return {
+        "config1": c["config1"].scaled(R=512),
+        "config2": c["config2"].scaled(E=256, R=384, T=512),
+        "config3": c["config3"].scaled(E=512, R=512, T=1024),
+        "config4": c["config4"].scaled(E=320, R=512, T=1024),
+    }[name]
+
+
+@pytest.mark.parametrize("name", ["config1", "config2", "config3", "config4"])
+def test_schedule_vs_oracle(epp, orc, tg, name):
+    import helpers
+    w = _scaled(tg, name)
+    trace = tg.Trace(w)
+    tokens, fam_of, shared = trace.requests()
+    pool, ix, primary, prefill, (ohs, oes) = helpers.setup_oracle(orc, w, trace)
+    odec, ototal = helpers.oracle_decisions(orc, w, pool, ix, primary, prefill, tokens)
+    with helpers.make_engine(w) as eng:
+        _, (hs, es) = helpers.setup_engine(eng, w, trace)
+        np.testing.assert_array_equal(np.sort(hs), np.sort(ohs))       # same index snapshot on both sides
+        dec, det = eng.schedule(tokens, uniform_len=w.prompt_bytes)
+        helpers.assert_decisions_equal(dec, det, odec, ototal, where=name)
+        # the workload must actually exercise the interesting paths
+        assert (dec["match_blocks"] > 0).sum() > w.R // 10
+        assert (dec["tie_count"] > 1).any() or name != "config3"
+        if name == "config4":
+            assert (det["prefill_ran"] == 1).any() and (det["prefill_ran"] == 0).any()
+        # Produce parity (dense match rows) vs the oracle's matchLongestPrefix
+        match, total = eng.prefix_match(tokens[:64], uniform_len=w.prompt_bytes)
+        for r in range(64):
+            oh = orc.hash_prompt(tokens[r].tobytes(), tg.MODEL, w.block_size_tokens, w.max_prefix_blocks)
+            want, _ = ix.match_longest_prefix(oh, w.E)
+            np.testing.assert_array_equal(match[r], want)
+            assert total[r] == len(oh)
+        # device-pointer batch gives the same records
+        import torch
+        dt = torch.from_numpy(tokens.view(np.int32)).cuda()
+        ddec, _ = eng.schedule(dt, uniform_len=w.prompt_bytes)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(epp.decisions_from_torch(ddec), dec)
+
+
+def test_global_stop_rule_and_holes(epp, orc):
+    """Non-prefix-closed index states: the walk stops at the first block NOBODY holds; endpoints missing earlier
+    blocks still count later ones; endpoints outside the slot range keep the walk alive (App. C.5)."""
+    with epp.Engine(4, epp.ProfileSpec(0, [epp.ScorerSpec(0, 1.0)]), block_size_tokens=1, max_prefix_blocks=8) as eng:
+        eng.register_model(b"m")
+        eng.pool_set([0, 1, 2, 3], [1, 1, 1, 1], [0, 0, 0, 0], [0, 0, 0, 0])
+        prompt = b"aaaabbbbccccddddeeee"
+        h = orc.hash_prompt(prompt, b"m", 1, 8)
+        # ep0: blocks 0,1,2 ; ep1: blocks 1,2,4 ; ep 9 (outside the pool): block 3
+        eng.index_load_snapshot([h[0], h[1], h[2], h[1], h[2], h[4]], [0, 0, 0, 1, 1, 1])
+        d, offs = _pack([prompt])
+        m, t = eng.prefix_match(d, offsets=offs)
+        assert list(m[0]) == [3, 2, 0, 0] and t[0] == 5
+        eng.index_load_snapshot([h[0], h[1], h[2], h[1], h[2], h[4], h[3]], [0, 0, 0, 1, 1, 1, 9])
+        m, t = eng.prefix_match(d, offsets=offs)
+        assert list(m[0]) == [3, 3, 0, 0]
+        dec, _ = eng.schedule(d, offsets=offs)
+        assert dec["pick"][0] == 0 and dec["tie_count"][0] == 2 and dec["score"][0] == 3 / 5
+
+
+def test_many_matched_endpoints_dense_fallback(epp, orc):
+    """More than 128 distinct matched endpoints per request -> the warp's dense-scan path; must agree with the oracle."""
+    import helpers
+    E = 600
+    rng = np.random.default_rng(9)
+    with epp.Engine(E, epp.ProfileSpec(1, [epp.ScorerSpec(2, 2.0), epp.ScorerSpec(1, 2.0), epp.ScorerSpec(0, 3.0)]),
+                    block_size_tokens=2, max_prefix_blocks=32) as eng:
+        eng.register_model(b"m")
+        kv = rng.integers(0, 1001, E) / 1000.0
+        waiting = rng.integers(0, 5, E).astype(np.int32)
+        eng.pool_set(np.arange(E), np.ones(E, np.uint8), kv, waiting)
+        prompts = [bytes(rng.integers(0, 256, 8 * 20, dtype=np.uint8)) for _ in range(8)]
+        ix = orc.Indexer()
+        pairs_h, pairs_e = [], []
+        for p in prompts[:4]:
+            h = orc.hash_prompt(p, b"m", 2, 32)
+            for e in range(0, E, 2):                       # 300 endpoints hold a random-depth prefix
+                depth = int(rng.integers(1, len(h) + 1))
+                pairs_h += h[:depth]
+                pairs_e += [e] * depth
+        ix.load_pairs(pairs_h, pairs_e)
+        eng.index_load_snapshot(pairs_h, pairs_e)
+        d, offs = _pack(prompts)
+        dec, det = eng.schedule(d, offsets=offs)
+        pool = orc.PoolState(np.ones(E, np.uint8), kv, waiting)
+        prof = orc.make_profile(1, [(2, 2.0, 0), (1, 2.0, 0), (0, 3.0, 0)])
+        odec, ototal = orc.cycle_batch(b"m", 2, 32, 0, False, ix, prof, None, pool, d, offs, 1)
+        helpers.assert_decisions_equal(dec, det, odec, ototal, where="dense-fallback")
+        m, t = eng.prefix_match(d, offsets=offs)
+        for r in range(8):
+            want, _ = ix.match_longest_prefix(orc.hash_prompt(prompts[r], b"m", 2, 32), E)
+            np.testing.assert_array_equal(m[r], want)
+
+
+def test_large_pool_global_counters(epp, orc, tg):
+    """E too large for per-warp shared-memory counters -> zeroed global scratch path (config-5-sized pool on 1 GPU)."""
+    import helpers
+    w = tg.baseline_configs()["config5"].scaled(R=256, T=512, name="config5-smallR")
+    trace = tg.Trace(w)
+    tokens, _, _ = trace.requests()
+    pool, ix, primary, prefill, _ = helpers.setup_oracle(orc, w, trace)
+    odec, ototal = helpers.oracle_decisions(orc, w, pool, ix, primary, prefill, tokens)
+    with helpers.make_engine(w) as eng:
+        helpers.setup_engine(eng, w, trace)
+        for _ in range(2):                                  # twice: counters must come back to zero
+            dec, det = eng.schedule(tokens, uniform_len=w.prompt_bytes)
+            helpers.assert_decisions_equal(dec, det, odec, ototal, where="config5")
+
+
+def test_score_columns_vs_oracle(epp, orc):
+    """Scorer.Score parity (dense [R][E] rows): every scorer kind, clamp, filters, ordered weighted sum."""
+    rng = np.random.default_rng(21)
+    E, R = 97, 9
+    roles = rng.choice([0, 1, 2, 3, 4, 5, 8], E).astype(np.uint8)
+    kv = np.where(rng.random(E) < 0.2, rng.choice([0.0, 1.0, 1.5, -0.25], E), rng.random(E))
+    waiting = np.where(rng.random(E) < 0.6, 0, rng.integers(1, 300, E)).astype(np.int32)
+    running = rng.integers(0, 50, E).astype(np.int32)
+    ext = rng.random((2, E)) * 1.4 - 0.2
+    scorers = [(0, 3.0, 0), (1, 2.0, 0), (2, 2.0, 0), (3, 1.0, 10), (4, 0.37, 1), (5, 1.5, 0), (4, 50.0, 0)]
+    total = rng.choice([0, 1, 7, 256], R).astype(np.int32)
+    match = (rng.random((R, E)) * (total[:, None] + 1)).astype(np.int32)
+    match = np.minimum(match, total[:, None])
+    for filt in (0, 1, 2):
+        with epp.Engine(E, epp.ProfileSpec(filt, [epp.ScorerSpec(*s) for s in scorers]), n_ext_cols=2) as eng:
+            eng.pool_set(np.arange(E), roles, kv, waiting, running, ext)
+            pool = orc.PoolState(roles, kv, waiting, running, ext)
+            prof = orc.make_profile(filt, scorers)
+            cand = np.array([orc.lib().orc_role_filter_keeps(filt, int(r)) for r in roles], np.uint8)
+            got = eng.score(match, total, 0, -1)
+            for r in range(R):
+                want, _, _, _ = orc.profile_run(prof, pool, match[r], int(total[r]))
+                if cand.any():
+                    np.testing.assert_array_equal(got[r].view(np.uint64), want.view(np.uint64))
+            for si, s in enumerate(scorers):
+                col = eng.score(match, total, 0, si)
+                for r in range(R):
+                    want = orc.score_column(s, pool, cand, match[r], int(total[r]))
+                    np.testing.assert_array_equal(col[r].view(np.uint64), want.view(np.uint64))
+            dec, det = eng.schedule_with_match(match, total)
+            for r in range(R):
+                d = orc.schedule(prof, None, pool, match[r], int(total[r]), 16, 0, 0)
+                assert dec["status"][r] == d.status
+                if d.status == 0:
+                    assert dec["pick"][r] == d.pick and dec["tie_count"][r] == d.tie_count
+                    assert dec["score"][r : r + 1].view(np.uint64)[0] == np.float64(d.score).view(np.uint64)
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's own scheduler tests through the interface mirror
+# ------------------------------------------------------------------------------------------------
+def test_reference_TestSchedule(epp):
+    """pkg/epp/scheduling/scheduler_test.go:40-157 (default 4-scorer profile -> pod2, score 2.8)."""
+    P = epp.plugins
+    prof = P.NewSchedulerProfile().WithScorers(
+        P.NewWeightedScorer(P.KVCacheUtilizationScorer(), 1), P.NewWeightedScorer(P.QueueScorer(), 1),
+        P.NewWeightedScorer(P.PrefixCacheScorer(), 1), P.NewWeightedScorer(P.ExternalScorer(0), 1),
+    ).WithPicker(P.NewMaxScorePicker(1))
+    sched = P.Scheduler(P.SingleProfileHandler(), {"default": prof}, ext_columns=1)
+    with pytest.raises(P.SchedulingError):
+        sched.Schedule(P.InferenceRequest(TargetModel="any-model"), [])
+    pods = [P.NewEndpoint(P.EndpointMetadata("pod1"), P.Metrics(0, 0.2)),
+            P.NewEndpoint(P.EndpointMetadata("pod2"), P.Metrics(0, 0.2)),
+            P.NewEndpoint(P.EndpointMetadata("pod3"), P.Metrics(10, 0.8))]
+    lora = [[0.0, 1.0, 0.8]]        # lora_affinity.go:76-100 tiers for TargetModel "critical"
+    res = sched.Schedule(P.InferenceRequest(TargetModel="critical"), pods, ext=lora)
+    tgt = res.ProfileResults["default"]
+    assert tgt.TargetEndpoints[0].GetMetadata().Name == "pod2" and tgt.Score == 2.8
+    assert res.PrimaryProfileName == "default"
+
+
+def test_reference_TestPDSchedule(epp):
+    """profilehandler/disagg/scheduler_test.go:34-297."""
+    P = epp.plugins
+    ep1 = P.NewEndpoint(P.EndpointMetadata("endpoint1", {P.RoleLabel: P.RolePrefill}, "1.2.3.4"), P.Metrics(0))
+    ep2 = P.NewEndpoint(P.EndpointMetadata("endpoint2", {P.RoleLabel: P.RoleDecode}, "5.6.7.8"), P.Metrics(0))
+    norole = P.NewEndpoint(P.EndpointMetadata("noRoleEndpoint1", {}, "1.1.1.1"), P.Metrics(2))
+
+    def mk():
+        prefill = P.NewSchedulerProfile().WithFilters(P.NewPrefillRole()).WithPicker(P.NewMaxScorePicker(1))
+        prefill.AddPlugins(P.NewWeightedScorer(P.PrefixCacheScorer(), 50))
+        decode = P.NewSchedulerProfile().WithFilters(P.NewDecodeRole()).WithScorers(
+            P.NewWeightedScorer(P.NewLoadAware(128), 1)).WithPicker(P.NewMaxScorePicker(1))
+        decode.AddPlugins(P.NewWeightedScorer(P.PrefixCacheScorer(), 0))
+        handler = P.DisaggProfileHandler("decode", "prefill", P.PrefixBasedPDDecider(2))
+        return P.Scheduler(handler, {"prefill": prefill, "decode": decode})
+
+    def run(prompt, pods, cached):
+        tokens = len(prompt) // 4
+        for p in pods:
+            p.Put(P.PrefixCacheMatchInfoKey, P.NewPrefixCacheMatchInfo(tokens if cached else 0, tokens, 1))
+        return mk().Schedule(P.InferenceRequest(TargetModel="critical", Prompt=prompt), pods)
+
+    def names(res):
+        return {k: v.TargetEndpoints[0].GetMetadata().Name for k, v in res.ProfileResults.items()}
+
+    with pytest.raises(P.SchedulingError):
+        mk().Schedule(P.InferenceRequest(Prompt=b"12345678901"), [])
+    assert names(run(b"12345678901", [ep2], False)) == {"decode": "endpoint2"}
+    with pytest.raises(P.SchedulingError):
+        run(b"12345678901", [ep1], False)
+    assert names(run(b"12345678906", [ep1, ep2], False)) == {"decode": "endpoint2", "prefill": "endpoint1"}
+    assert names(run(b"12345678906", [ep1, ep2], True)) == {"decode": "endpoint2"}
+    assert names(run(b"12345", [ep1, ep2], False)) == {"decode": "endpoint2"}
+    assert names(run(b"12345", [ep1, ep2], True)) == {"decode": "endpoint2"}
+    assert names(run(b"12345678901", [ep1, norole], False)) == {"decode": "noRoleEndpoint1", "prefill": "endpoint1"}
+    long = b"1234567890123456789012345678901234567890"
+    r = run(long, [ep1, ep2, norole], False)
+    assert names(r) == {"decode": "endpoint2", "prefill": "endpoint1"} and r.ProfileResults["decode"].Score == 0.5
+    assert names(run(long, [ep1, ep2, norole], True)) == {"decode": "endpoint2"}
+
+
+def test_reference_prefix_plugin_flow(epp):
+    """approximateprefix/plugin_test.go:37-82 and :174-226 through Produce / PreRequest on the engine."""
+    P = epp.plugins
+    with epp.Engine(3, epp.ProfileSpec(0, [epp.ScorerSpec(0, 1.0)]), block_size_tokens=1) as eng:
+        eng.pool_set([0, 1, 2], [0, 0, 0], [0, 0, 0], [0, 0, 0])
+        prod = P.ApproxPrefixCacheProducer(eng, b"test-model1")
+        pods = [P.NewEndpoint(P.EndpointMetadata(f"pod{i+1}")) for i in range(3)]
+        m, t = prod.Produce([b"aaaabbbb"], pods)                     # empty index
+        assert list(m[0]) == [0, 0, 0] and t[0] == 2
+        info, ok = pods[0].Get(P.PrefixCacheMatchInfoKey)
+        assert ok and (info.MatchBlocks(), info.TotalBlocks()) == (0, 2)
+        m, t = prod.Produce([b"aaaaaa"], pods)
+        assert t[0] == 2                                             # 1 full + 1 partial block
+        prod.PreRequest(0, [0, 2])                                   # pod1 primary, pod3 prefill
+        m, t = prod.Produce([b"aaaabbbb"], pods)
+        assert list(m[0]) == [1, 0, 1] and t[0] == 2
+        # keep_hashes + epp_index_add_picked == PreRequest for the picked endpoint
+        d, offs = _pack([b"ccccdddd"])
+        dec, _ = eng.schedule(d, offsets=offs, keep_hashes=True)
+        eng.index_add_picked()
+        m, t = eng.prefix_match(d, offsets=offs)
+        assert m[0, int(dec["pick"][0])] == 2
+
+
+def test_errors(epp):
+    with pytest.raises(epp.EngineError):
+        epp.Engine(0)
+    with pytest.raises(epp.EngineError):
+        epp.Engine(8, epp.ProfileSpec(0, [epp.ScorerSpec(99, 1.0)]))
+    with epp.Engine(8) as eng:
+        toks = np.zeros(64, np.uint32)
+        with pytest.raises(epp.EngineError):                        # no model registered
+            eng.hash_prompts(toks, uniform_len=256)
+        eng.register_model(b"m")
+        with pytest.raises(epp.EngineError):                        # schedule before pool_set
+            eng.schedule(toks, uniform_len=256)
+        with pytest.raises(epp.EngineError):
+            eng.pool_set([9], [0], [0.0], [0])                      # slot id out of range
+        with pytest.raises(epp.EngineError):
+            eng.pool_set([1], [0], [float("nan")], [0])
+        eng.pool_set([], [], [], [])                                # empty pool -> every decision is an error
+        dec, _ = eng.schedule(toks, uniform_len=256)
+        assert dec["status"][0] == -1 and dec["pick"][0] == 0xFFFFFFFF
