@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- routing decisions/s of the EPP scheduling cycle on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config3] [--impl reference]
+
+One "step" = one pass of the whole hot path (prefix-block hashing -> index lookup / global-stop match -> load scoring
+-> weighted sum -> arg-max pick [-> decider -> prefill pick]) over one batch of synthetic requests.
+  value     decisions/s with the batch already resident in HBM (device-pointer batch through the C ABI)
+  e2e       the same metric through the C ABI with HOST (pinned) buffers: the H2D copy of every prompt byte and the
+            D2H copy of every decision record are inside the timed region
+  roofline  dominant kernel: algorithmic bytes per launch / CUDA-event launch time vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the oracle (C restatement of the reference Go loops, kind "port") on the host cores, bounded sample
+--impl reference: times the reference's CPU algorithm (the oracle port; Go is not installable here) on all host cores.
+Multi-GPU (--gpus N under torchrun): N independent replicas, each with the full index and its own batch (weak
+scaling, no data-path collective); time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "routing decisions/sec at 4K-token prompts x 4,096 endpoints"
+UNIT = "decisions/s"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 8:
+                self.rows.append(f)
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for f in self.rows:
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def _pinned(nbytes: int, lib):
+    p = C.c_void_p()
+    rc = lib.epp_host_alloc(nbytes, C.byref(p))
+    if rc != 0:
+        raise RuntimeError("epp_host_alloc failed")
+    return p, np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,))
+
+
+def _workload(name: str, R: int | None):
+    from tools import tracegen as tg
+    w = tg.baseline_configs()[name]
+    if R:
+        w = w.scaled(R=R, name=w.name)
+    return w
+
+
+def _config_json(w, n_gpus, extra=None):
+    scor = ",".join(f"{ {0: 'prefix', 1: 'kv-util', 2: 'queue', 3: 'load-aware'}[k]}*{wt:g}" for k, wt, _ in w.primary_scorers)
+    c = {"workload": f"{w.name}: {w.E} endpoints, {w.T}-token prompts ({w.prompt_bytes} B, {w.blocks} blocks of "
+                     f"{w.block_size_tokens * 4} B), batch {w.R} requests per GPU, scorers {scor}"
+                     + (f", P/D two-stage pick ({w.n_prefill} prefill endpoints, nonCachedTokens {w.non_cached_tokens})"
+                        if w.prefill_scorers else ""),
+         "endpoints": w.E, "prompt_tokens": w.T, "batch_requests_per_gpu": w.R, "block_size_tokens": w.block_size_tokens,
+         "max_prefix_blocks": w.max_prefix_blocks,
+         "l2": f"inputs are {w.R * w.prompt_bytes / 2**20:.0f} MiB per step per GPU, larger than the 126 MB L2 (no flush needed)",
+         "parallelism": f"{n_gpus} independent replicas (index replicated, requests sharded; no data-path collective)",
+         "trace_seed": hex(w.seed)}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def cpu_baseline(w, trace, n_threads: int, target_s: float = 12.0, tokens: np.ndarray | None = None):
+    """Oracle (port of the reference Go loops) on the host cores over a bounded sample of the same workload."""
+    import helpers
+    from oracle import pyoracle as orc
+    pool, ix, primary, prefill, _ = helpers.setup_oracle(orc, w, trace)
+    probe_n = min(w.R, max(4 * n_threads, 64))
+    tk = tokens[:probe_n] if tokens is not None and tokens.shape[0] >= probe_n else trace.requests(0, probe_n)[0]
+    helpers.oracle_decisions(orc, w, pool, ix, primary, prefill, tk, n_threads)          # warm caches / page in
+    n = int(min(w.R, tokens.shape[0] if tokens is not None else w.R))
+    tk = tokens[:n] if tokens is not None else trace.requests(0, n)[0]
+    passes, dt = 0, 0.0
+    while dt < target_s and passes < 1000:      # repeat the batch until ~target_s of CPU work has been timed
+        t0 = time.perf_counter()
+        helpers.oracle_decisions(orc, w, pool, ix, primary, prefill, tk, n_threads)
+        dt += time.perf_counter() - t0
+        passes += 1
+    n_total = n * passes
+    return {"value": n_total / dt, "unit": UNIT, "cores": n_threads, "kind": "port",
+            "sample": f"{passes} passes over the first {n} requests of the step's batch ({n_total} decisions), "
+                      f"{n_threads} host threads, {dt:.2f} s; C restatement of the reference Go loops "
+                      "(oracle/epp_oracle.c) -- the Go toolchain is not installable here"}, (n_total, dt)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from tools import tracegen as tg
+    w = _workload(args.workload, args.requests)
+    trace = tg.Trace(w)
+    n_threads = os.cpu_count() or 1
+    import helpers
+    from oracle import pyoracle as orc
+    orc.build()
+    pool, ix, primary, prefill, _ = helpers.setup_oracle(orc, w, trace)
+    # size one step so that (warmup + steps) steps take about 60 s in total
+    probe = trace.requests(0, max(2 * n_threads, 16))[0]
+    t0 = time.perf_counter()
+    helpers.oracle_decisions(orc, w, pool, ix, primary, prefill, probe, n_threads)
+    per_req = max(time.perf_counter() - t0, 1e-4) / probe.shape[0]
+    n = int(min(w.R, max(n_threads, 60.0 / max(1, args.steps + args.warmup) / per_req)))
+    n = max(n_threads, (n // n_threads) * n_threads)
+    tokens = trace.requests(0, n)[0]
+    for _ in range(args.warmup):
+        helpers.oracle_decisions(orc, w, pool, ix, primary, prefill, tokens, n_threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        helpers.oracle_decisions(orc, w, pool, ix, primary, prefill, tokens, n_threads)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt
+    sample = (f"each step = first {n} requests of the workload's batch on {n_threads} host threads; C restatement of the "
+              "reference Go loops (oracle/epp_oracle.c), Go toolchain unavailable")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 (XXH64) + f64 (scores)", "data": "synthetic",
+        "config": _config_json(w, args.gpus, {"reference_step_requests": n}),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": n_threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import epp_b200 as epp
+    import helpers
+    from tools import tracegen as tg
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    epp.build.build()
+    tg.build()
+    w = _workload(args.workload, args.requests)
+    trace = tg.Trace(w)
+    lib = epp.capi.load()
+    R, nbytes = w.R, w.R * w.prompt_bytes
+
+    # this rank's batch: requests [rank*R, (rank+1)*R) of the seeded trace, generated straight into pinned memory
+    pin_ptr, pin = _pinned(nbytes, lib)
+    host_tokens = pin.view(np.uint32).reshape(R, w.T)
+    trace.requests(rank * R, R, out=host_tokens)
+    dev_tokens = torch.empty((R, w.T), dtype=torch.int32, device="cuda")
+    dev_tokens.copy_(torch.from_numpy(host_tokens.view(np.int32)))
+    dec_ptr, dec_pin = _pinned(R * 32, lib)
+    host_dec = dec_pin.view(epp.DECISION_DTYPE)
+    dev_dec = torch.empty((R, 32), dtype=torch.uint8, device="cuda")
+
+    eng = helpers.make_engine(w, device=local_rank)
+    helpers.setup_engine(eng, w, trace)
+    st0 = eng.stats()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: inputs resident in HBM
+    for _ in range(args.warmup):
+        eng.schedule(dev_tokens, uniform_len=w.prompt_bytes, detail=False, out=dev_dec)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    kms = np.zeros(8)
+    dev_ms = 0.0
+    launches = 0
+    probes = postings = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.schedule(dev_tokens, uniform_len=w.prompt_bytes, detail=False, out=dev_dec)
+        st = eng.stats()
+        kms += np.array(st["last_kernel_ms"])
+        dev_ms += st["last_kernels_ms"]
+        launches += st["last_kernel_launches"]
+        probes, postings = st["last_probes"], st["last_postings"]
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    barrier()
+    wall = max_over_ranks(wall)
+    dev_ms = max_over_ranks(dev_ms)
+    value = world * R * args.steps / wall
+
+    # ---- e2e: host buffers through the C ABI (H2D of the prompts + D2H of the decisions inside the timed region)
+    for _ in range(max(1, min(args.warmup, 3))):
+        eng.schedule(host_tokens, uniform_len=w.prompt_bytes, detail=False, out=host_dec)
+    e2e_steps = max(1, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.schedule(host_tokens, uniform_len=w.prompt_bytes, detail=False, out=host_dec)
+    torch.cuda.synchronize()
+    e2e_wall = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * R * e2e_steps / e2e_wall
+    # sanity: device-pointer and host-pointer paths agree
+    np.testing.assert_array_equal(epp.decisions_from_torch(dev_dec), host_dec)
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        kms /= args.steps
+        # dominant kernel = k_block_digests (reads every prompt byte once).  Its share of the algorithmic bytes
+        # A(r) = 4*T_eff + 16*P(r) + 4*M(r) + 16 + 16*E/R is the token term 4*T_eff.
+        t_eff = min(w.T, w.block_size_tokens * w.max_prefix_blocks)
+        token_bytes = R * 4 * t_eff
+        algo_total = token_bytes + 16 * probes + 4 * postings + 16 * R + 16 * w.E
+        dom_ms = kms[1]
+        achieved = token_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        ncu_traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                ncu_traffic = json.load(open(tpath)).get(f"{w.name}:k_block_digests")
+            except Exception:
+                pass
+        n_threads = os.cpu_count() or 1
+        cpu, _ = cpu_baseline(w, trace, n_threads, tokens=host_tokens) if not args.no_cpu else ({"value": None}, None)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 (XXH64) + f64 (scores)", "data": "synthetic",
+            "config": _config_json(w, world),
+            "device_ms_per_step": dev_ms / args.steps,
+            "kernel_ms_per_step": {"k_prompt_lengths": kms[0], "k_block_digests": kms[1], "k_chain": kms[2], "k_match_pick": kms[3]},
+            "algorithmic_bytes_per_step": int(algo_total),
+            "algorithmic_gbs_whole_step": algo_total / (dev_ms / args.steps * 1e-3) / 1e9,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(R * 32),
+                    "steps": e2e_steps, "ms_per_step": e2e_wall / e2e_steps * 1e3},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_block_digests", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": ncu_traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(token_bytes),
+                         "launch_ms": dom_ms},
+            "cpu_baseline": cpu,
+            "index": {"pairs": st0["index_pairs"], "slots": st0["index_slots"], "probes_per_step": int(probes),
+                      "postings_per_step": int(postings)},
+        }
+        print(json.dumps(out), flush=True)
+    eng.close()
+    lib.epp_host_free(pin_ptr)
+    lib.epp_host_free(dec_ptr)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config3", choices=["config1", "config2", "config3", "config4", "config5"])
+    ap.add_argument("--requests", type=int, default=0, help="override the batch size R (0 = the config's)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -120,10 +121,12 @@ struct epp_engine {
     DevBuf offsets, model_ids, hashes, nblocks, eff_len, in_len, decisions, details, flag;
     DevBuf dense_match, dense_total, dense_scores;
     DevBuf pick_scratch;            // global match counters when E is too large for shared memory
+    int force_v1 = 0;               // EPP_HASH_V1=1: unfused v1 hash kernels (A/B)
     int pick_grid = 0;
     bool pick_global = false;
     size_t pick_smem = 0;
     int64_t kept_R = 0;             // rows of `hashes` valid for epp_index_add_picked
+    int64_t shard_R = 0;            // rows of `hashes` valid for epp_shard_pick / epp_shard_merge
     std::vector<epp_decision> kept_decisions;
 
     epp_stats stats{};
@@ -239,6 +242,7 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
     e->idx_special_host.off = 0;
     e->idx_special_host.cnt = 0;
     e->mirror.reset(new IndexMirror(cfg->lru_capacity_per_server));
+    { const char *v1 = getenv("EPP_HASH_V1"); e->force_v1 = (v1 && v1[0] == '1') ? 1 : 0; }
 
     // match/pick launch geometry: counters in shared memory when they fit, else zeroed global scratch
     size_t smem_local = match_pick_smem_bytes(cfg->max_endpoints, false);
@@ -389,7 +393,7 @@ extern "C" int32_t epp_pool_set(epp_engine *h, int32_t n, const uint32_t *ids, c
         d.sort_key = h->prof[p].sort_key.as<uint64_t>();
         d.n_cand = h->prof[p].n_cand.as<int32_t>();
         d.qminmax = h->prof[p].qminmax.as<int64_t>();
-        CUDA_TRY(launch_pool_prepare(pa, p == 0 ? h->cfg.primary : h->cfg.prefill, d, h->Epad, s, &launches));
+        CUDA_TRY(launch_pool_prepare(pa, p == 0 ? h->cfg.primary : h->cfg.prefill, d, h->Epad, h->shard_begin, h->shard_end, s, &launches));
     }
     CUDA_TRY(cudaStreamSynchronize(s));
     h->pool_ready = true;
@@ -513,7 +517,7 @@ struct BatchView {
     uint64_t uniform_len = 0;
     const uint32_t *model_ids = nullptr;
     uint64_t total_bytes = 0;      // host batches only
-    bool aligned16 = false;
+    uint64_t offsets_or_bits = 0;
 };
 
 static int32_t check_batch(epp_engine *h, const epp_batch *b, BatchView &v) {
@@ -530,12 +534,12 @@ static int32_t check_batch(epp_engine *h, const epp_batch *b, BatchView &v) {
     if (!v.offsets && v.uniform_len > 0 && !v.data) return fail(EPP_ERR_INVALID, "data is NULL");
     if (!v.device) {
         if (v.offsets) {
-            bool al = true;
+            uint64_t bits = 0;
             for (int64_t r = 0; r < v.R; r++) {
                 if (v.offsets[r + 1] < v.offsets[r]) return fail(EPP_ERR_INVALID, "offsets not monotonic at request %lld", (long long)r);
-                if (v.offsets[r] & 15) al = false;
+                bits |= v.offsets[r];
             }
-            v.aligned16 = al;
+            v.offsets_or_bits = bits;
             v.total_bytes = v.offsets[v.R] - v.offsets[0];
             if (v.total_bytes && !v.data) return fail(EPP_ERR_INVALID, "data is NULL");
         } else {
@@ -569,7 +573,7 @@ struct Work {
     const uint64_t *offsets_dev;   // indexed by absolute request id, or nullptr
     uint64_t uniform_len;
     const uint32_t *model_ids_dev; // absolute, or nullptr
-    bool aligned16;
+    uint64_t offsets_or_bits;      // OR of all offsets (alignment of the batch layout)
     uint64_t *hashes_out;          // row r0 of the destination
     int32_t *nblocks_out;
 };
@@ -589,7 +593,9 @@ static HashParams hash_params(epp_engine *h, const Work &w) {
     p.nblocks = w.nblocks_out;
     p.eff_len = h->eff_len.as<int64_t>() + w.r0;
     p.in_len = h->in_len.as<int64_t>() + w.r0;
-    p.offsets_aligned16 = w.aligned16 ? 1 : 0;
+    p.offsets_or_bits = w.offsets_or_bits;
+    p.sm_count = h->sm_count;
+    p.force_v1 = h->force_v1;
     return p;
 }
 
@@ -612,18 +618,20 @@ static PickParams pick_params(epp_engine *h, const Work &w, epp_decision *out, e
     p.detail = detail;
     p.out_match = out_match;
     p.work_counters = nullptr;
+    p.global_masks = nullptr;
+    p.mask_words = 0;
+    p.shard_out = nullptr;
     return p;
 }
 
 // Device-side offsets alignment probe for device-pointer batches.
-static int32_t device_offsets_aligned(epp_engine *h, const uint64_t *offsets_dev, int64_t n, cudaStream_t s, bool *out) {
-    int one = 1;
-    CUDA_TRY(cudaMemcpyAsync(h->flag.p, &one, sizeof one, cudaMemcpyHostToDevice, s));
+static int32_t device_offsets_or_bits(epp_engine *h, const uint64_t *offsets_dev, int64_t n, cudaStream_t s, uint64_t *out) {
+    CUDA_TRY(cudaMemsetAsync(h->flag.p, 0, sizeof(int), s));
     CUDA_TRY(launch_check_offsets_aligned(offsets_dev, n, h->flag.as<int>(), s));
     int res = 0;
     CUDA_TRY(cudaMemcpyAsync(&res, h->flag.p, sizeof res, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    *out = res != 0;
+    *out = (uint64_t)res;
     return EPP_OK;
 }
 
@@ -646,9 +654,9 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
     cudaStream_t s0 = h->slot[0].stream;
 
     if (v.device) {
-        bool aligned = false;
-        if (v.offsets) EPP_TRY(device_offsets_aligned(h, v.offsets, R + 1, s0, &aligned));
-        Work w{0, R, v.data, v.offsets, v.uniform_len, v.model_ids, aligned,
+        uint64_t or_bits = 0;
+        if (v.offsets) EPP_TRY(device_offsets_or_bits(h, v.offsets, R, s0, &or_bits));
+        Work w{0, R, v.data, v.offsets, v.uniform_len, v.model_ids, or_bits,
                (mode == Mode::HashOnly && out_hashes) ? out_hashes : h->hashes.as<uint64_t>(),
                (mode == Mode::HashOnly && out_nblocks) ? out_nblocks : (mode == Mode::Match && out_total ? out_total : h->nblocks.as<int32_t>())};
         CUDA_TRY(cudaMemsetAsync(h->work_counters.p, 0, sizeof(unsigned long long) * 2, s0));
@@ -714,8 +722,8 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
         Slot &sl = h->slot[k & 1];
         cudaStream_t s = sl.stream;
         const size_t nreq = (size_t)(c.r1 - c.r0);
-        // keep the staged copy aligned (mod 16) like the caller's layout
-        uint8_t *stage = sl.data.as<uint8_t>() + (c.start & 15);
+        // keep the staged copy aligned (mod 32) like the caller's layout
+        uint8_t *stage = sl.data.as<uint8_t>() + (c.start & 31);
         if (c.bytes) CUDA_TRY(cudaMemcpyAsync(stage, v.data + c.start, c.bytes, cudaMemcpyHostToDevice, s));
         Work w;
         w.r0 = c.r0;
@@ -724,11 +732,11 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
             // the kernels address  data_base + offsets[r]  with ABSOLUTE offsets
             w.data_base = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(stage) - (uintptr_t)c.start);
             w.offsets_dev = h->offsets.as<uint64_t>();
-            w.aligned16 = v.aligned16;
+            w.offsets_or_bits = v.offsets_or_bits;
         } else {
             w.data_base = stage;                    // chunk-local request index * uniform_len
             w.offsets_dev = nullptr;
-            w.aligned16 = (v.uniform_len % 16) == 0;
+            w.offsets_or_bits = 0;
         }
         w.uniform_len = v.uniform_len;
         w.model_ids_dev = v.model_ids ? h->model_ids.as<uint32_t>() : nullptr;
@@ -927,20 +935,62 @@ extern "C" int32_t epp_get_stats(epp_engine *h, epp_stats *out) {
 extern "C" int32_t epp_shard_set(epp_engine *h, uint32_t ep_begin, uint32_t ep_end) {
     if (!h || ep_begin > ep_end) return fail(EPP_ERR_INVALID, "bad shard range");
     std::lock_guard<std::mutex> lk(h->mu);
+    if (h->cfg.handler != EPP_HANDLER_SINGLE) return fail(EPP_ERR_INVALID, "endpoint-sharded mode supports the single-profile handler only");
     h->shard_begin = ep_begin;
     h->shard_end = ep_end;
+    h->pool_ready = false;          // candidates are derived per shard: epp_pool_set must follow
     return EPP_OK;
 }
 
+static int32_t mask_words_of(const epp_engine *h) { return (h->cfg.max_prefix_blocks + 31) / 32; }
+
 extern "C" int32_t epp_shard_probe(epp_engine *h, const epp_batch *batch, uint32_t *out_masks) {
-    (void)h; (void)batch; (void)out_masks;
-    return fail(EPP_ERR_STATE, "endpoint-sharded mode is not built into this library yet");
+    if (!h || !out_masks) return fail(EPP_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    BatchView v;
+    EPP_TRY(check_batch(h, batch, v));
+    if (!v.device) return fail(EPP_ERR_INVALID, "epp_shard_probe takes device-pointer batches (EPP_BATCH_DEVICE_PTRS)");
+    h->kept_R = 0;
+    h->shard_R = 0;
+    EPP_TRY(commit_locked(h));
+    EPP_TRY(run_batch(h, v, Mode::HashOnly, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+    int launches = 0;
+    cudaStream_t s = h->slot[0].stream;
+    CUDA_TRY(launch_shard_probe(v.R, h->cfg.max_prefix_blocks, h->hashes.as<uint64_t>(), h->nblocks.as<int32_t>(),
+                                index_view(h), out_masks, mask_words_of(h), s, &launches));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    h->shard_R = v.R;
+    return EPP_OK;
 }
+
 extern "C" int32_t epp_shard_pick(epp_engine *h, int64_t n_requests, const uint32_t *global_masks, epp_shard_best *out_best) {
-    (void)h; (void)n_requests; (void)global_masks; (void)out_best;
-    return fail(EPP_ERR_STATE, "endpoint-sharded mode is not built into this library yet");
+    if (!h || !global_masks || !out_best) return fail(EPP_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    if (!h->pool_ready) return fail(EPP_ERR_STATE, "epp_pool_set has not been called (after epp_shard_set)");
+    if (n_requests != h->shard_R) return fail(EPP_ERR_STATE, "epp_shard_pick: n_requests %lld does not match the probed batch (%lld)", (long long)n_requests, (long long)h->shard_R);
+    if (n_requests == 0) return EPP_OK;
+    Work w{0, n_requests, nullptr, nullptr, 0, nullptr, 0, h->hashes.as<uint64_t>(), h->nblocks.as<int32_t>()};
+    PickParams pp = pick_params(h, w, h->decisions.as<epp_decision>(), nullptr, nullptr);
+    pp.global_masks = global_masks;
+    pp.mask_words = mask_words_of(h);
+    pp.shard_out = out_best;
+    int launches = 0;
+    cudaStream_t s = h->slot[0].stream;
+    CUDA_TRY(launch_match_pick(pp, h->pick_global ? h->pick_scratch.as<uint32_t>() : nullptr, h->pick_grid, h->pick_smem, s, &launches));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return EPP_OK;
 }
+
 extern "C" int32_t epp_shard_merge(epp_engine *h, int64_t n_requests, int32_t n_ranks, const epp_shard_best *all_best, epp_decision *out) {
-    (void)h; (void)n_requests; (void)n_ranks; (void)all_best; (void)out;
-    return fail(EPP_ERR_STATE, "endpoint-sharded mode is not built into this library yet");
+    if (!h || !all_best || !out || n_ranks <= 0) return fail(EPP_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    if (n_requests != h->shard_R) return fail(EPP_ERR_STATE, "epp_shard_merge: n_requests does not match the probed batch");
+    int launches = 0;
+    cudaStream_t s = h->slot[0].stream;
+    CUDA_TRY(launch_shard_merge(n_requests, n_ranks, all_best, h->nblocks.as<int32_t>(), out, s, &launches));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return EPP_OK;
 }

@@ -21,29 +21,6 @@ __device__ __forceinline__ void request_span(const HashParams &p, int64_t r, uin
     }
 }
 
-// Generic hash of one chain block: message = bytes[0..n) || LE64(prev).
-__device__ inline uint64_t hash_block_generic(const uint8_t *b, int64_t n, uint64_t prev) {
-    uint64_t v[4];
-    bool have_v = false;
-    int64_t i = 0;
-    if (n >= 32) {
-        xxh_init(v);
-        have_v = true;
-        for (; i + 32 <= n; i += 32) {
-            v[0] = xxh_round(v[0], load_le64(b + i));
-            v[1] = xxh_round(v[1], load_le64(b + i + 8));
-            v[2] = xxh_round(v[2], load_le64(b + i + 16));
-            v[3] = xxh_round(v[3], load_le64(b + i + 24));
-        }
-    }
-    uint8_t tail[40];
-    int t = 0;
-    for (; i < n; i++) tail[t++] = b[i];
-#pragma unroll
-    for (int k = 0; k < 8; k++) tail[t++] = (uint8_t)(prev >> (8 * k));
-    return xxh_finish(v, have_v, (uint64_t)n + 8, tail, t);
-}
-
 __global__ void k_hash_bytes(const uint8_t *msg, size_t len, uint64_t *out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     uint64_t v[4];
@@ -158,27 +135,40 @@ __global__ void __launch_bounds__(128) k_hash_generic(HashParams p) {
     }
 }
 
-// The vectorised path needs block_bytes % 32 == 0 and every block start 16-byte aligned.
-static bool fast_path_ok(const HashParams &p) {
-    if (p.block_bytes <= 0 || (p.block_bytes % 32) != 0) return false;
-    if ((reinterpret_cast<uintptr_t>(p.data) & 15) != 0) return false;
-    if (p.offsets) return p.offsets_aligned16 != 0;
-    return (p.uniform_len % 16) == 0;
+// Common alignment (0, 16 or 32 bytes) of every block start of the batch; the vectorised paths need
+// block_bytes % 32 == 0 and alignment >= 16 (128-bit loads) or 32 (256-bit loads, one per XXH64 stripe).
+int hash_batch_alignment(const HashParams &p) {
+    if (p.block_bytes <= 0 || (p.block_bytes % 32) != 0) return 0;
+    uint64_t bits = reinterpret_cast<uintptr_t>(p.data);
+    bits |= p.offsets ? p.offsets_or_bits : p.uniform_len;
+    if ((bits & 31) == 0) return 32;
+    if ((bits & 15) == 0) return 16;
+    return 0;
 }
+static bool fast_path_ok(const HashParams &p) { return hash_batch_alignment(p) >= 16; }
 
-// Sets *flag = 0 when any offset is not a multiple of 16 (device-pointer batches).
+// *flag |= low bits of every offset (device-pointer batches).
 __global__ void k_offsets_aligned(const uint64_t *offsets, int64_t n, int *flag) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n && (offsets[r] & 15)) *flag = 0;
+    if (r < n && (offsets[r] & 31)) atomicOr(flag, (int)(offsets[r] & 31));
 }
 cudaError_t launch_check_offsets_aligned(const uint64_t *offsets, int64_t n, int *flag_dev, cudaStream_t s) {
     k_offsets_aligned<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(offsets, n, flag_dev);
     return cudaGetLastError();
 }
 
+cudaError_t launch_hash_fused(const HashParams &p, int align, int sm_count, cudaStream_t s, int *launches);
+
 cudaError_t launch_hash_prompts(const HashParams &p, cudaStream_t s, int *launches, cudaEvent_t *ev) {
     if (p.R <= 0) return cudaSuccess;
     int n = 0;
+    int align = hash_batch_alignment(p);
+    if (align >= 16 && !p.force_v1) {          // one fused kernel: lengths + digests + chain
+        if (ev) { cudaEventRecord(ev[0], s); cudaEventRecord(ev[1], s); }
+        cudaError_t e = launch_hash_fused(p, align, p.sm_count, s, launches);
+        if (ev) { cudaEventRecord(ev[2], s); cudaEventRecord(ev[3], s); }
+        return e;
+    }
     unsigned gR = (unsigned)((p.R + 127) / 128);
     if (ev) cudaEventRecord(ev[0], s);
     k_prompt_lengths<<<gR, 128, 0, s>>>(p);

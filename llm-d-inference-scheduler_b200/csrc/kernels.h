@@ -23,7 +23,9 @@ struct HashParams {
     int32_t *nblocks;           // [R]
     int64_t *eff_len;           // [R] bytes hashed after truncation (hashing.go:63-66)
     int64_t *in_len;            // [R] untruncated prompt length in bytes (P/D decider), may be nullptr
-    int32_t offsets_aligned16;  // every offsets[r] is a multiple of 16 (enables the vectorised path)
+    uint64_t offsets_or_bits;   // OR of every offsets[r] (low bits decide the common alignment)
+    int32_t sm_count;
+    int32_t force_v1;           // use the unfused v1 kernels (A/B testing)
 };
 // Generic single-message XXH64 (model || salt seeds).  msg on device.
 cudaError_t launch_hash_bytes(const uint8_t *msg, size_t len, uint64_t *out, cudaStream_t s);
@@ -81,8 +83,9 @@ struct ProfileDerived {
     int32_t *n_cand;           // [1]
     int64_t *qminmax;          // [4] waiting min,max, running min,max over candidates
 };
+// [shard_begin, shard_end): only these slots become candidates (queue min/max still span the whole pool).
 cudaError_t launch_pool_prepare(const PoolArrays &pool, const epp_profile_cfg &prof, const ProfileDerived &d,
-                                int32_t Epad, cudaStream_t s, int *launches);
+                                int32_t Epad, uint32_t shard_begin, uint32_t shard_end, cudaStream_t s, int *launches);
 
 // ------------------------------------------------------------------------------------------------
 // match + score + pick (a3-a14)
@@ -113,6 +116,10 @@ struct PickParams {
     epp_decision_detail *detail;  // [R] or nullptr
     int32_t *out_match;        // dense [R][E] or nullptr (Produce parity mode)
     unsigned long long *work_counters;  // [2] += (probes, postings) of this launch, or nullptr
+    // endpoint-sharded mode (nullptr otherwise): the stop rule comes from the OR of all ranks' presence masks
+    const uint32_t *global_masks;       // [R][mask_words]
+    int32_t mask_words;
+    epp_shard_best *shard_out;          // [R] local best record instead of `out`
 };
 // Fused lookup + match + score + pick, one warp per request.  Per-warp match counters live in shared memory
 // (smem = match_pick_smem_bytes(E, false)) or, when E is too large for that, in a zero-initialised global
@@ -142,11 +149,11 @@ cudaError_t launch_score_dense(int64_t R, int32_t E, const ProfileDev &prof, con
                                const int64_t *qminmax, const int32_t *match, const int32_t *total,
                                int32_t scorer_index, double *out, cudaStream_t s, int *launches);
 
-// endpoint-sharded mode
-cudaError_t launch_shard_probe(const PickParams &p, uint32_t *out_masks, int32_t mask_words, cudaStream_t s,
+// endpoint-sharded mode: per-request block-presence masks of the LOCAL table (bit i of word i/32 = block i held
+// by some endpoint of this shard), and the cross-rank reduction of the per-shard best records.
+cudaError_t launch_shard_probe(int64_t R, int32_t max_blocks, const uint64_t *hashes, const int32_t *nblocks,
+                               const IndexView &index, uint32_t *out_masks, int32_t mask_words, cudaStream_t s,
                                int *launches);
-cudaError_t launch_shard_pick(const PickParams &p, const uint32_t *global_masks, int32_t mask_words,
-                              epp_shard_best *out_best, cudaStream_t s, int *launches);
 cudaError_t launch_shard_merge(int64_t R, int32_t n_ranks, const epp_shard_best *all_best, const int32_t *nblocks,
                                epp_decision *out, cudaStream_t s, int *launches);
 

@@ -102,21 +102,23 @@ __device__ __forceinline__ double weighted_sum(const ProfileDev &pf, int32_t E, 
 // ------------------------------------------------------------------------------------------------
 // pool snapshot -> derived per-profile arrays
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_pool_candidates(PoolArrays pool, int filter, uint8_t *cand,
-                                                          int32_t *n_cand, int64_t *qminmax) {
+__global__ void __launch_bounds__(1024) k_pool_candidates(PoolArrays pool, int filter, uint32_t shard_begin,
+                                                          uint32_t shard_end, uint8_t *cand, int32_t *n_cand,
+                                                          int64_t *qminmax) {
     __shared__ long long s_mn[2][32], s_mx[2][32];
     __shared__ int s_cnt[32];
     long long mnw = LLONG_MAX, mxw = LLONG_MIN, mnr = LLONG_MAX, mxr = LLONG_MIN;
     int cnt = 0;
     for (int e = threadIdx.x; e < pool.E; e += blockDim.x) {
         bool k = filter_keeps(filter, pool.role[e]);
-        cand[e] = k ? 1 : 0;
-        if (k) {
+        bool local = k && (uint32_t)e >= shard_begin && (uint32_t)e < shard_end;
+        cand[e] = local ? 1 : 0;
+        if (k) {      // queue min/max span every candidate of the pool, not only this shard's (queue.go:79-91)
             long long w = pool.waiting[e], r = pool.running[e];
             mnw = min(mnw, w); mxw = max(mxw, w);
             mnr = min(mnr, r); mxr = max(mxr, r);
-            cnt++;
         }
+        if (local) cnt++;
     }
     for (int o = 16; o; o >>= 1) {
         mnw = min(mnw, __shfl_xor_sync(0xffffffffu, mnw, o));
@@ -208,8 +210,8 @@ __global__ void k_pool_groups(const double *base, const uint32_t *order, const i
 }
 
 cudaError_t launch_pool_prepare(const PoolArrays &pool, const epp_profile_cfg &prof, const ProfileDerived &d,
-                                int32_t Epad, cudaStream_t s, int *launches) {
-    k_pool_candidates<<<1, 1024, 0, s>>>(pool, prof.filter, d.cand, d.n_cand, d.qminmax);
+                                int32_t Epad, uint32_t shard_begin, uint32_t shard_end, cudaStream_t s, int *launches) {
+    k_pool_candidates<<<1, 1024, 0, s>>>(pool, prof.filter, shard_begin, shard_end, d.cand, d.n_cand, d.qminmax);
     k_pool_terms<<<(Epad + 255) / 256, 256, 0, s>>>(pool, prof, d.cand, d.qminmax, d.contrib, d.base, d.sort_key,
                                                     d.order, Epad);
     k_pool_sort<<<1, 1024, 0, s>>>(d.sort_key, d.order, Epad);
@@ -357,7 +359,15 @@ __global__ void __launch_bounds__(kPickWarps * 32) k_match_pick(PickParams p, in
             uint32_t off = 0, cnt = 0;
             bool hit = false;
             if (active) hit = probe(p.index, row[i], off, cnt);
-            uint32_t miss = __ballot_sync(0xffffffffu, active && !hit);
+            uint32_t miss;
+            if (p.global_masks) {   // sharded: a block is missing only if NO rank holds it
+                uint32_t word = p.global_masks[r * (int64_t)p.mask_words + (c0 >> 5)];
+                uint32_t valid = (total - c0) >= 32 ? 0xffffffffu : ((1u << (total - c0)) - 1u);
+                miss = ~word & valid;
+                if (!hit) cnt = 0;
+            } else {
+                miss = __ballot_sync(0xffffffffu, active && !hit);
+            }
             int32_t limit = miss ? c0 + (__ffs(miss) - 1) : total;
             if (active && i < limit) {
                 w_postings += cnt;
@@ -401,8 +411,15 @@ __global__ void __launch_bounds__(kPickWarps * 32) k_match_pick(PickParams p, in
             }
         }
         if (lane == 0) {
-            p.out[r] = d;
-            if (p.detail) p.detail[r] = dd;
+            if (p.shard_out) {
+                epp_shard_best sb;
+                sb.score = d.score; sb.pick = d.pick; sb.tie_count = d.tie_count;
+                sb.match_blocks = d.match_blocks; sb.status = d.status;
+                p.shard_out[r] = sb;
+            } else {
+                p.out[r] = d;
+                if (p.detail) p.detail[r] = dd;
+            }
         }
         // ---- a4: dense match row (Produce parity mode only)
         if (p.out_match) {
@@ -536,6 +553,74 @@ cudaError_t launch_score_dense(int64_t R, int32_t E, const ProfileDev &prof, con
     if (n <= 0) return cudaSuccess;
     k_score_dense<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(R, E, prof, pool, qminmax, match, total, scorer_index,
                                                              out);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// endpoint-sharded mode: presence masks + merge of the per-shard best records
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_shard_probe(int64_t R, int32_t max_blocks, const uint64_t *hashes,
+                                                     const int32_t *nblocks, IndexView index, uint32_t *out_masks,
+                                                     int32_t mask_words) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= R) return;
+    const int32_t total = nblocks[r];
+    const uint64_t *row = hashes + r * (int64_t)max_blocks;
+    for (int32_t w = 0; w < mask_words; w++) {
+        int32_t i = w * 32 + lane;
+        bool hit = false;
+        if (i < total) {
+            uint32_t off, cnt;
+            hit = probe(index, row[i], off, cnt);
+        }
+        uint32_t word = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) out_masks[r * (int64_t)mask_words + w] = word;
+    }
+}
+
+cudaError_t launch_shard_probe(int64_t R, int32_t max_blocks, const uint64_t *hashes, const int32_t *nblocks,
+                               const IndexView &index, uint32_t *out_masks, int32_t mask_words, cudaStream_t s,
+                               int *launches) {
+    if (R <= 0) return cudaSuccess;
+    int64_t threads = R * 32;
+    k_shard_probe<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(R, max_blocks, hashes, nblocks, index, out_masks,
+                                                                   mask_words);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+// all_best is [n_ranks][R]; the winner is the max score, lowest slot id among equals, ties summed.
+__global__ void k_shard_merge(int64_t R, int32_t n_ranks, const epp_shard_best *all_best, const int32_t *nblocks,
+                              epp_decision *out) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    Best b;
+    best_init(b);
+    int32_t mb = 0;
+    for (int32_t k = 0; k < n_ranks; k++) {
+        epp_shard_best sb = all_best[(int64_t)k * R + r];
+        if (sb.status != 0) continue;
+        uint32_t before = b.pick;
+        best_add(b, sb.score, sb.pick, sb.tie_count);
+        if (b.pick != before) mb = sb.match_blocks;
+    }
+    epp_decision d;
+    d.status = b.ties ? 0 : -1;
+    d.pick = b.ties ? b.pick : EPP_NO_ENDPOINT;
+    d.score = b.ties ? b.val : 0.0;
+    d.prefill_pick = EPP_NO_ENDPOINT;
+    d.tie_count = b.ties;
+    d.total_blocks = nblocks[r];
+    d.match_blocks = b.ties ? mb : 0;
+    out[r] = d;
+}
+
+cudaError_t launch_shard_merge(int64_t R, int32_t n_ranks, const epp_shard_best *all_best, const int32_t *nblocks,
+                               epp_decision *out, cudaStream_t s, int *launches) {
+    if (R <= 0) return cudaSuccess;
+    k_shard_merge<<<(unsigned)((R + 255) / 256), 256, 0, s>>>(R, n_ranks, all_best, nblocks, out);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

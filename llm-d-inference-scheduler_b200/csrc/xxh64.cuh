@@ -119,4 +119,28 @@ __device__ inline uint64_t xxh_finish(uint64_t v[4], bool have_v, uint64_t total
     return xxh_avalanche(h);
 }
 
+// Generic hash of one chain block: message = bytes[0..n) || LE64(prev)  (hashing.go:82-83), any n >= 0, any
+// alignment (byte loads).
+__device__ inline uint64_t hash_block_generic(const uint8_t *b, int64_t n, uint64_t prev) {
+    uint64_t v[4];
+    bool have_v = false;
+    int64_t i = 0;
+    if (n >= 32) {
+        xxh_init(v);
+        have_v = true;
+        for (; i + 32 <= n; i += 32) {
+            v[0] = xxh_round(v[0], load_le64(b + i));
+            v[1] = xxh_round(v[1], load_le64(b + i + 8));
+            v[2] = xxh_round(v[2], load_le64(b + i + 16));
+            v[3] = xxh_round(v[3], load_le64(b + i + 24));
+        }
+    }
+    uint8_t tail[40];
+    int t = 0;
+    for (; i < n; i++) tail[t++] = b[i];
+#pragma unroll
+    for (int k = 0; k < 8; k++) tail[t++] = (uint8_t)(prev >> (8 * k));
+    return xxh_finish(v, have_v, (uint64_t)n + 8, tail, t);
+}
+
 }  // namespace epp

@@ -1,6 +1,7 @@
 """GPU parity tests: the CUDA engine (through the C ABI) vs the CPU oracle on the same seeded inputs, vs the
 committed golden vectors, and through the reference-interface mirror (KATs of the reference's own tests).
 Bar: bit-exact for hashes / counts / picks, bit-exact fp64 score bits.  Run on the B200 box: pytest -m gpu."""
+import dataclasses
 import json
 import os
 import random
@@ -212,7 +213,8 @@ def _scaled(tg, name):
         "config1": c["config1"].scaled(R=512),
         "config2": c["config2"].scaled(E=256, R=384, T=512),
         "config3": c["config3"].scaled(E=512, R=512, T=1024),
-        "config4": c["config4"].scaled(E=320, R=512, T=1024),
+        # nonCachedTokens raised from 16 so that BOTH decider outcomes occur on 1K-token prompts
+        "config4": dataclasses.replace(c["config4"].scaled(E=320, R=512, T=1024), non_cached_tokens=512),
     }[name]
 
 
@@ -231,7 +233,8 @@ def test_schedule_vs_oracle(epp, orc, tg, name):
         helpers.assert_decisions_equal(dec, det, odec, ototal, where=name)
         # the workload must actually exercise the interesting paths
         assert (dec["match_blocks"] > 0).sum() > w.R // 10
-        assert (dec["tie_count"] > 1).any() or name != "config3"
+        if name == "config1":
+            assert (dec["tie_count"] > 1).any()       # ties are real in this workload: the tie rule is exercised
         if name == "config4":
             assert (det["prefill_ran"] == 1).any() and (det["prefill_ran"] == 0).any()
         # Produce parity (dense match rows) vs the oracle's matchLongestPrefix
