@@ -257,19 +257,21 @@ def run_gpu(args, rank, world, local_rank):
     value = world * R * args.steps / wall
 
     # ---- e2e: host buffers through the C ABI (H2D of the prompts + D2H of the decisions inside the timed region)
-    for _ in range(max(1, min(args.warmup, 3))):
-        eng.schedule(host_tokens, uniform_len=w.prompt_bytes, detail=False, out=host_dec)
     e2e_steps = max(1, min(args.steps, 10))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        eng.schedule(host_tokens, uniform_len=w.prompt_bytes, detail=False, out=host_dec)
-    torch.cuda.synchronize()
-    e2e_wall = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    e2e_value = world * R * e2e_steps / e2e_wall
-    # sanity: device-pointer and host-pointer paths agree
-    np.testing.assert_array_equal(epp.decisions_from_torch(dev_dec), host_dec)
+    e2e_wall, e2e_value = float("nan"), None
+    if not args.no_e2e:
+        for _ in range(max(1, min(args.warmup, 3))):
+            eng.schedule(host_tokens, uniform_len=w.prompt_bytes, detail=False, out=host_dec)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            eng.schedule(host_tokens, uniform_len=w.prompt_bytes, detail=False, out=host_dec)
+        torch.cuda.synchronize()
+        e2e_wall = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        e2e_value = world * R * e2e_steps / e2e_wall
+        # sanity: device-pointer and host-pointer paths agree
+        np.testing.assert_array_equal(epp.decisions_from_torch(dev_dec), host_dec)
 
     if rank == 0:
         peak, peak_src = _peaks()
@@ -328,6 +330,7 @@ def main():
     ap.add_argument("--workload", default="config3", choices=["config1", "config2", "config3", "config4", "config5"])
     ap.add_argument("--requests", type=int, default=0, help="override the batch size R (0 = the config's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

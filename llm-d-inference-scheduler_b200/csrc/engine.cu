@@ -82,6 +82,7 @@ struct ProfileState {
 struct Slot {                       // per-stream staging for host-pointer batches
     cudaStream_t stream = nullptr;
     DevBuf data;
+    DevBuf overflow_list, overflow_n;   // requests handed from a sparse pass to the dense-counter pass (per stream)
     cudaEvent_t done = nullptr;
 };
 
@@ -112,7 +113,7 @@ struct epp_engine {
     // index
     std::unique_ptr<IndexMirror> mirror;
     bool snapshot_mode = false;
-    DevBuf slots, postings, idx_scratch, idx_cursor, idx_special, pair_hash, pair_ep, get_out;
+    DevBuf slots, postings, idx_scratch, idx_cursor, idx_special, pair_hash, pair_ep, get_out, intern_keys, intern_vals;
     uint64_t idx_capacity = 0, idx_pairs = 0;
     IndexSlot idx_special_host{};
     uint32_t shard_begin = 0, shard_end = 0xFFFFFFFFu;
@@ -122,6 +123,8 @@ struct epp_engine {
     DevBuf dense_match, dense_total, dense_scores;
     DevBuf pick_scratch;            // global match counters when E is too large for shared memory
     int force_v1 = 0;               // EPP_HASH_V1=1: unfused v1 hash kernels (A/B)
+    int force_match_v1 = 0;         // EPP_MATCH_V1=1: dense-counter match kernel only (A/B)
+    int no_fuse = 1;                // EPP_FUSE_MATCH=1 runs a2-a14 inside the hash kernel (experimental, slower today)
     int pick_grid = 0;
     bool pick_global = false;
     size_t pick_smem = 0;
@@ -238,11 +241,13 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
     CUDA_TRY(e->get_out.reserve(sizeof(uint32_t) * 4096 + 16, &e->dev_bytes));
     CUDA_TRY(e->flag.reserve(sizeof(int) * 4, &e->dev_bytes));
     CUDA_TRY(e->work_counters.reserve(sizeof(unsigned long long) * 2, &e->dev_bytes));
+    memset(&e->idx_special_host, 0, sizeof(IndexSlot));
     e->idx_special_host.key = kEmptyKey;
-    e->idx_special_host.off = 0;
-    e->idx_special_host.cnt = 0;
     e->mirror.reset(new IndexMirror(cfg->lru_capacity_per_server));
     { const char *v1 = getenv("EPP_HASH_V1"); e->force_v1 = (v1 && v1[0] == '1') ? 1 : 0; }
+    { const char *v1 = getenv("EPP_MATCH_V1"); e->force_match_v1 = (v1 && v1[0] == '1') ? 1 : 0; }
+    { const char *v1 = getenv("EPP_FUSE_MATCH"); e->no_fuse = (v1 && v1[0] == '1') ? 0 : 1; }
+    for (int i = 0; i < 2; i++) CUDA_TRY(e->slot[i].overflow_n.reserve(sizeof(int32_t) * 4, &e->dev_bytes));
 
     // match/pick launch geometry: counters in shared memory when they fit, else zeroed global scratch
     size_t smem_local = match_pick_smem_bytes(cfg->max_endpoints, false);
@@ -406,12 +411,7 @@ extern "C" int32_t epp_pool_set(epp_engine *h, int32_t n, const uint32_t *ids, c
 static int32_t build_device_index(epp_engine *h, const uint64_t *hashes, const uint32_t *eps, uint64_t n,
                                   uint64_t n_distinct_hint) {
     cudaStream_t s = h->slot[0].stream;
-    uint64_t want = std::max<uint64_t>(16, 2 * std::max<uint64_t>(1, n_distinct_hint));
-    uint64_t cap = 16;
-    while (cap < want) cap <<= 1;
     if (n >= 0xFFFFFFF0ull) return fail(EPP_ERR_CAPACITY, "index snapshot of %llu pairs exceeds the u32 posting space", (unsigned long long)n);
-    CUDA_TRY(h->slots.reserve(sizeof(IndexSlot) * cap, &h->dev_bytes));
-    CUDA_TRY(h->idx_scratch.reserve(sizeof(uint32_t) * cap, &h->dev_bytes));
     CUDA_TRY(h->postings.reserve(sizeof(uint32_t) * std::max<uint64_t>(n, 1), &h->dev_bytes));
     CUDA_TRY(h->pair_hash.reserve(sizeof(uint64_t) * std::max<uint64_t>(n, 1), &h->dev_bytes));
     CUDA_TRY(h->pair_ep.reserve(sizeof(uint32_t) * std::max<uint64_t>(n, 1), &h->dev_bytes));
@@ -419,16 +419,35 @@ static int32_t build_device_index(epp_engine *h, const uint64_t *hashes, const u
         CUDA_TRY(cudaMemcpyAsync(h->pair_hash.p, hashes, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemcpyAsync(h->pair_ep.p, eps, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
     }
-    int launches = 0;
-    CUDA_TRY(launch_index_build(h->pair_hash.as<uint64_t>(), h->pair_ep.as<uint32_t>(), n, h->slots.as<IndexSlot>(), cap,
-                                h->postings.as<uint32_t>(), h->idx_scratch.as<uint32_t>(), h->idx_cursor.as<uint32_t>(),
-                                h->idx_special.as<IndexSlot>(), (uint32_t)h->cfg.max_endpoints, s, &launches));
-    CUDA_TRY(cudaMemcpyAsync(&h->idx_special_host, h->idx_special.p, sizeof(IndexSlot), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    uint64_t distinct = std::max<uint64_t>(1, n_distinct_hint);
+    uint32_t cursor[4] = {0, 0, 0, 0};
+    uint64_t cap = 16;
+    for (int pass = 0; pass < 2; pass++) {
+        // load factor <= 0.5 over the distinct hashes; the first pass only knows an upper bound (the pair count)
+        uint64_t want = std::max<uint64_t>(16, 2 * distinct);
+        cap = 16;
+        while (cap < want) cap <<= 1;
+        CUDA_TRY(h->slots.reserve(sizeof(IndexSlot) * cap, &h->dev_bytes));
+        CUDA_TRY(h->idx_scratch.reserve(sizeof(uint32_t) * cap, &h->dev_bytes));
+        CUDA_TRY(h->intern_keys.reserve(sizeof(uint64_t) * cap, &h->dev_bytes));
+        CUDA_TRY(h->intern_vals.reserve(sizeof(uint32_t) * cap, &h->dev_bytes));
+        int launches = 0;
+        CUDA_TRY(launch_index_build(h->pair_hash.as<uint64_t>(), h->pair_ep.as<uint32_t>(), n, h->slots.as<IndexSlot>(), cap,
+                                    h->postings.as<uint32_t>(), h->idx_scratch.as<uint32_t>(), h->idx_cursor.as<uint32_t>(),
+                                    h->idx_special.as<IndexSlot>(), h->intern_keys.as<uint64_t>(), h->intern_vals.as<uint32_t>(), s, &launches));
+        CUDA_TRY(cudaMemcpyAsync(&h->idx_special_host, h->idx_special.p, sizeof(IndexSlot), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(cursor, h->idx_cursor.p, sizeof cursor, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        uint64_t true_distinct = std::max<uint64_t>(1, cursor[2]);
+        uint64_t tight = 16;
+        while (tight < 2 * true_distinct) tight <<= 1;
+        if (tight >= cap) break;            // already as small as the load factor allows
+        distinct = true_distinct;           // rebuild once into a table a quarter (or less) of the size
+    }
     h->idx_capacity = cap;
     h->idx_pairs = n;
     h->stats.index_pairs = n;
-    h->stats.index_hashes = n_distinct_hint;
+    h->stats.index_hashes = cursor[2];
     h->stats.index_slots = cap;
     return EPP_OK;
 }
@@ -449,7 +468,7 @@ static IndexView index_view(epp_engine *h) {
     v.postings = h->postings.as<uint32_t>();
     v.mask = h->idx_capacity ? h->idx_capacity - 1 : 0;
     v.special = h->idx_special_host;
-    if (!h->idx_capacity) { v.special.cnt = 0; v.special.off = 0; }
+    if (!h->idx_capacity) v.special.cnt = 0;
     v.ep_begin = h->shard_begin;
     v.ep_end = h->shard_end;
     return v;
@@ -563,6 +582,7 @@ static int32_t reserve_batch(epp_engine *h, int64_t R) {
     CUDA_TRY(h->details.reserve(sizeof(epp_decision_detail) * n, &h->dev_bytes));
     CUDA_TRY(h->offsets.reserve(sizeof(uint64_t) * (n + 1), &h->dev_bytes));
     CUDA_TRY(h->model_ids.reserve(sizeof(uint32_t) * n, &h->dev_bytes));
+    for (int i = 0; i < 2; i++) CUDA_TRY(h->slot[i].overflow_list.reserve(sizeof(int32_t) * n, &h->dev_bytes));
     return EPP_OK;
 }
 
@@ -596,6 +616,7 @@ static HashParams hash_params(epp_engine *h, const Work &w) {
     p.offsets_or_bits = w.offsets_or_bits;
     p.sm_count = h->sm_count;
     p.force_v1 = h->force_v1;
+    p.fused_pick = nullptr;
     return p;
 }
 
@@ -621,6 +642,10 @@ static PickParams pick_params(epp_engine *h, const Work &w, epp_decision *out, e
     p.global_masks = nullptr;
     p.mask_words = 0;
     p.shard_out = nullptr;
+    p.req_list = nullptr;
+    p.req_list_n = nullptr;
+    p.overflow_list = nullptr;
+    p.overflow_n = nullptr;
     return p;
 }
 
@@ -636,6 +661,54 @@ static int32_t device_offsets_or_bits(epp_engine *h, const uint64_t *offsets_dev
 }
 
 enum class Mode { HashOnly, Match, Schedule };
+
+// Dense-counter kernel over the requests a sparse kernel could not finish (their matched-endpoint set overflowed its
+// per-request map).  No host round trip: the kernel reads the list length on the device.
+static int32_t launch_overflow_pass(epp_engine *h, Slot &sl, PickParams pp, int *launches) {
+    cudaStream_t s = sl.stream;
+    pp.req_list = sl.overflow_list.as<int32_t>();
+    pp.req_list_n = sl.overflow_n.as<int32_t>();
+    pp.overflow_list = nullptr;
+    pp.overflow_n = nullptr;
+    pp.work_counters = nullptr;            // already counted by the sparse pass
+    CUDA_TRY(launch_match_pick(pp, h->pick_global ? h->pick_scratch.as<uint32_t>() : nullptr, h->pick_grid, h->pick_smem, s, launches));
+    return EPP_OK;
+}
+
+// Standalone match/pick over hashes already in HBM: warp-per-request sparse kernel + overflow pass (or the dense
+// kernel alone for Produce-parity rows / A-B runs).
+static int32_t launch_match(epp_engine *h, Slot &sl, PickParams pp, int *launches) {
+    cudaStream_t s = sl.stream;
+    uint32_t *gs = h->pick_global ? h->pick_scratch.as<uint32_t>() : nullptr;
+    if (pp.out_match || h->force_match_v1) {
+        CUDA_TRY(launch_match_pick(pp, gs, h->pick_grid, h->pick_smem, s, launches));
+        return EPP_OK;
+    }
+    CUDA_TRY(cudaMemsetAsync(sl.overflow_n.p, 0, sizeof(int32_t), s));
+    pp.overflow_list = sl.overflow_list.as<int32_t>();
+    pp.overflow_n = sl.overflow_n.as<int32_t>();
+    CUDA_TRY(launch_match_pick_sparse(pp, h->sm_count, s, launches));
+    return launch_overflow_pass(h, sl, pp, launches);
+}
+
+// The whole cycle for one Work item.  Fast path (aligned prompts, block_bytes % 32 == 0): ONE fused kernel hashes,
+// probes, scores and picks; otherwise hash kernels + standalone match.
+static int32_t launch_cycle(epp_engine *h, Slot &sl, const HashParams &hp_in, PickParams pp, int *launches,
+                            cudaEvent_t *ev) {
+    cudaStream_t s = sl.stream;
+    HashParams hp = hp_in;
+    const bool fuse = !pp.out_match && !h->force_match_v1 && !h->force_v1 && !h->no_fuse && hash_batch_alignment(hp) >= 16;
+    if (fuse) {
+        CUDA_TRY(cudaMemsetAsync(sl.overflow_n.p, 0, sizeof(int32_t), s));
+        pp.overflow_list = sl.overflow_list.as<int32_t>();
+        pp.overflow_n = sl.overflow_n.as<int32_t>();
+        hp.fused_pick = &pp;
+        CUDA_TRY(launch_hash_prompts(hp, s, launches, ev));
+        return launch_overflow_pass(h, sl, pp, launches);
+    }
+    CUDA_TRY(launch_hash_prompts(hp, s, launches, ev));
+    return launch_match(h, sl, pp, launches);
+}
 
 // Runs hashing (+ match/pick) for a batch.  Host batches are split into chunks whose H2D copy overlaps the
 // kernels of the previous chunk (two streams, two staging buffers); device batches run in one pass.
@@ -660,12 +733,13 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
                (mode == Mode::HashOnly && out_hashes) ? out_hashes : h->hashes.as<uint64_t>(),
                (mode == Mode::HashOnly && out_nblocks) ? out_nblocks : (mode == Mode::Match && out_total ? out_total : h->nblocks.as<int32_t>())};
         CUDA_TRY(cudaMemsetAsync(h->work_counters.p, 0, sizeof(unsigned long long) * 2, s0));
-        CUDA_TRY(launch_hash_prompts(hash_params(h, w), s0, &launches, h->ev));
-        if (mode != Mode::HashOnly) {
+        if (mode == Mode::HashOnly) {
+            CUDA_TRY(launch_hash_prompts(hash_params(h, w), s0, &launches, h->ev));
+        } else {
             epp_decision *dec = (mode == Mode::Schedule && out_dec) ? out_dec : h->decisions.as<epp_decision>();
             PickParams pp = pick_params(h, w, dec, mode == Mode::Schedule ? out_detail : nullptr, mode == Mode::Match ? out_match : nullptr);
             pp.work_counters = h->work_counters.as<unsigned long long>();
-            CUDA_TRY(launch_match_pick(pp, h->pick_global ? h->pick_scratch.as<uint32_t>() : nullptr, h->pick_grid, h->pick_smem, s0, &launches));
+            EPP_TRY(launch_cycle(h, h->slot[0], hash_params(h, w), pp, &launches, h->ev));
         }
         CUDA_TRY(cudaEventRecord(h->ev[4], s0));
         unsigned long long wc[2] = {0, 0};
@@ -742,8 +816,8 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
         w.model_ids_dev = v.model_ids ? h->model_ids.as<uint32_t>() : nullptr;
         w.hashes_out = h->hashes.as<uint64_t>() + (size_t)c.r0 * B;
         w.nblocks_out = h->nblocks.as<int32_t>() + c.r0;
-        CUDA_TRY(launch_hash_prompts(hash_params(h, w), s, &launches));
         if (mode == Mode::HashOnly) {
+            CUDA_TRY(launch_hash_prompts(hash_params(h, w), s, &launches));
             if (out_hashes) CUDA_TRY(cudaMemcpyAsync(out_hashes + (size_t)c.r0 * B, w.hashes_out, sizeof(uint64_t) * nreq * B, cudaMemcpyDeviceToHost, s));
             if (out_nblocks) CUDA_TRY(cudaMemcpyAsync(out_nblocks + c.r0, w.nblocks_out, sizeof(int32_t) * nreq, cudaMemcpyDeviceToHost, s));
         } else {
@@ -751,7 +825,7 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
             epp_decision *dec = h->decisions.as<epp_decision>() + c.r0;
             epp_decision_detail *det = h->details.as<epp_decision_detail>() + c.r0;
             PickParams pp = pick_params(h, w, dec, det, dm);
-            CUDA_TRY(launch_match_pick(pp, h->pick_global ? h->pick_scratch.as<uint32_t>() : nullptr, h->pick_grid, h->pick_smem, s, &launches));
+            EPP_TRY(launch_cycle(h, sl, hash_params(h, w), pp, &launches, nullptr));
             if (mode == Mode::Schedule) {
                 if (out_dec) CUDA_TRY(cudaMemcpyAsync(out_dec + c.r0, dec, sizeof(epp_decision) * nreq, cudaMemcpyDeviceToHost, s));
                 if (out_detail) CUDA_TRY(cudaMemcpyAsync(out_detail + c.r0, det, sizeof(epp_decision_detail) * nreq, cudaMemcpyDeviceToHost, s));
@@ -978,7 +1052,8 @@ extern "C" int32_t epp_shard_pick(epp_engine *h, int64_t n_requests, const uint3
     pp.shard_out = out_best;
     int launches = 0;
     cudaStream_t s = h->slot[0].stream;
-    CUDA_TRY(launch_match_pick(pp, h->pick_global ? h->pick_scratch.as<uint32_t>() : nullptr, h->pick_grid, h->pick_smem, s, &launches));
+    EPP_TRY(reserve_batch(h, n_requests));
+    EPP_TRY(launch_match(h, h->slot[0], pp, &launches));
     CUDA_TRY(cudaStreamSynchronize(s));
     return EPP_OK;
 }

@@ -157,7 +157,8 @@ cudaError_t launch_check_offsets_aligned(const uint64_t *offsets, int64_t n, int
     return cudaGetLastError();
 }
 
-cudaError_t launch_hash_fused(const HashParams &p, int align, int sm_count, cudaStream_t s, int *launches);
+cudaError_t launch_hash_fused(const HashParams &p, const PickParams *pick, int align, int sm_count, cudaStream_t s,
+                              int *launches);
 
 cudaError_t launch_hash_prompts(const HashParams &p, cudaStream_t s, int *launches, cudaEvent_t *ev) {
     if (p.R <= 0) return cudaSuccess;
@@ -165,7 +166,7 @@ cudaError_t launch_hash_prompts(const HashParams &p, cudaStream_t s, int *launch
     int align = hash_batch_alignment(p);
     if (align >= 16 && !p.force_v1) {          // one fused kernel: lengths + digests + chain
         if (ev) { cudaEventRecord(ev[0], s); cudaEventRecord(ev[1], s); }
-        cudaError_t e = launch_hash_fused(p, align, p.sm_count, s, launches);
+        cudaError_t e = launch_hash_fused(p, p.fused_pick, align, p.sm_count, s, launches);
         if (ev) { cudaEventRecord(ev[2], s); cudaEventRecord(ev[3], s); }
         return e;
     }

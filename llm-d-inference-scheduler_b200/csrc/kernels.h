@@ -26,7 +26,10 @@ struct HashParams {
     uint64_t offsets_or_bits;   // OR of every offsets[r] (low bits decide the common alignment)
     int32_t sm_count;
     int32_t force_v1;           // use the unfused v1 kernels (A/B testing)
+    const struct PickParams *fused_pick;  // non-null: run a2-a14 inside the fused kernel's chain warp (fast path only)
 };
+// Common alignment (0, 16, 32) of every block start; >= 16 (and block_bytes % 32 == 0) enables the fused kernel.
+int hash_batch_alignment(const HashParams &p);
 // Generic single-message XXH64 (model || salt seeds).  msg on device.
 cudaError_t launch_hash_bytes(const uint8_t *msg, size_t len, uint64_t *out, cudaStream_t s);
 cudaError_t launch_check_offsets_aligned(const uint64_t *offsets, int64_t n, int *flag_dev, cudaStream_t s);
@@ -37,25 +40,32 @@ cudaError_t launch_hash_prompts(const HashParams &p, cudaStream_t s, int *launch
 // ------------------------------------------------------------------------------------------------
 // prefix index (a2): open-addressed table  hash -> (posting offset, count)
 // ------------------------------------------------------------------------------------------------
-struct __align__(16) IndexSlot {
+constexpr int kInlineIds = 5;
+// One 32-byte slot = one DRAM/L2 sector, fetched by a single 256-bit load.  Posting lists of up to kInlineIds
+// endpoints live IN the slot (no dependent load); longer lists live in `postings` at offset ids[0].  Lists are
+// sorted by endpoint id and duplicate-free.
+struct __align__(32) IndexSlot {
     uint64_t key;
-    uint32_t off;
-    uint32_t cnt;     // 0 == empty slot
+    uint32_t cnt;                 // 0 == empty slot
+    uint32_t ids[kInlineIds];     // cnt <= kInlineIds: the endpoints; else ids[0] = offset into postings
 };
 constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFULL;   // build-time claim sentinel; a real key equal to it
                                                         // lives in IndexView::special
 struct IndexView {
     const IndexSlot *slots;
     const uint32_t *postings;
-    uint64_t mask;            // capacity - 1 (capacity is a power of two), 0 slots => mask 0 & n_pairs 0
+    uint64_t mask;            // capacity - 1 (capacity is a power of two); slots == nullptr => empty index
     IndexSlot special;        // record for key == kEmptyKey (cnt 0 when absent)
     uint32_t ep_begin, ep_end;  // shard range (postings outside are ignored for counting but keep the walk alive)
 };
 // Builds table + postings from n pairs (device arrays).  slots must hold `capacity` entries, postings n,
-// scratch `capacity` uint32.  *out_special receives the record of key == kEmptyKey.  Deduplicates pairs.
+// scratch `capacity` uint32, cursor 4 uint32 (cursor[2] returns the number of distinct hashes).  *special_dev
+// receives the record of key == kEmptyKey.  Deduplicates pairs, sorts every posting list and interns equal spilled
+// lists (intern_keys / intern_vals: `capacity` entries each).
 cudaError_t launch_index_build(const uint64_t *pair_hash, const uint32_t *pair_ep, uint64_t n, IndexSlot *slots,
                                uint64_t capacity, uint32_t *postings, uint32_t *scratch, uint32_t *cursor,
-                               IndexSlot *special_dev, uint32_t max_endpoints, cudaStream_t s, int *launches);
+                               IndexSlot *special_dev, uint64_t *intern_keys, uint32_t *intern_vals,
+                               cudaStream_t s, int *launches);
 cudaError_t launch_index_get(const IndexView &ix, uint64_t hash, uint32_t *out_eps, int32_t cap, int32_t *out_n,
                              cudaStream_t s);
 
@@ -120,6 +130,12 @@ struct PickParams {
     const uint32_t *global_masks;       // [R][mask_words]
     int32_t mask_words;
     epp_shard_best *shard_out;          // [R] local best record instead of `out`
+    // v1 kernel only: process the requests listed in req_list[0 .. *req_list_n) (the sparse kernel's overflows)
+    const int32_t *req_list;
+    const int32_t *req_list_n;
+    // v2 (sparse) kernel only: requests whose matched-endpoint set overflowed the per-warp map are appended here
+    int32_t *overflow_list;
+    int32_t *overflow_n;
 };
 // Fused lookup + match + score + pick, one warp per request.  Per-warp match counters live in shared memory
 // (smem = match_pick_smem_bytes(E, false)) or, when E is too large for that, in a zero-initialised global
@@ -128,6 +144,9 @@ size_t match_pick_smem_bytes(int32_t E, bool global_counts);
 int match_pick_warps_per_cta();
 cudaError_t launch_match_pick(const PickParams &p, uint32_t *gscratch, int grid, size_t smem, cudaStream_t s,
                               int *launches);
+// v2: the same decision per request with a per-warp sparse endpoint map (48 matched endpoints max; requests that
+// overflow are appended to p.overflow_list for the v1 kernel).  16 warps per CTA, high occupancy.
+cudaError_t launch_match_pick_sparse(const PickParams &p, int sm_count, cudaStream_t s, int *launches);
 // Decision logic on injected dense match info (plugin parity / KAT mode).
 struct DensePickParams {
     int64_t R;

@@ -15,89 +15,10 @@
 
 #include <climits>
 
-#include "kernels.h"
+#include "index.cuh"
+#include "score.cuh"
 
 namespace epp {
-
-// ------------------------------------------------------------------------------------------------
-// scorers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool filter_keeps(int filter, uint8_t role) {
-    if (role == 0xFF) return false;                       // slot not in the pool
-    switch (filter) {
-        case EPP_FILTER_NONE: return true;
-        case EPP_FILTER_DECODE:   // roles.go:46-48 (allowsNoLabel = true)
-            return role == EPP_ROLE_NONE || role == EPP_ROLE_DECODE || role == EPP_ROLE_PREFILL_DECODE ||
-                   role == EPP_ROLE_BOTH || role == EPP_ROLE_ENCODE_PREFILL_DECODE;
-        case EPP_FILTER_PREFILL:  // roles.go:56-58
-            return role == EPP_ROLE_PREFILL || role == EPP_ROLE_ENCODE_PREFILL || role == EPP_ROLE_PREFILL_DECODE ||
-                   role == EPP_ROLE_BOTH || role == EPP_ROLE_ENCODE_PREFILL_DECODE;
-        case EPP_FILTER_ENCODE:   // roles.go:68-70
-            return role == EPP_ROLE_ENCODE || role == EPP_ROLE_ENCODE_PREFILL ||
-                   role == EPP_ROLE_ENCODE_PREFILL_DECODE;
-        default: return false;
-    }
-}
-
-// enforceScoreRange, scheduler_profile.go:194-202 (NaN passes through, as in Go)
-__device__ __forceinline__ double clamp01(double s) {
-    if (s < 0.0) return 0.0;
-    if (s > 1.0) return 1.0;
-    return s;
-}
-
-// prefix-cache-scorer, scorer/prefix/plugin.go:100-111
-__device__ __forceinline__ double prefix_score(int32_t match, int32_t total) {
-    if (total == 0) return 0.0;
-    return __ddiv_rn((double)match, (double)total);
-}
-
-// Raw Scorer.Score value of one endpoint for the request-independent scorers.
-__device__ __forceinline__ double pool_score(const epp_scorer_cfg &sc, const PoolArrays &pool,
-                                             const int64_t *qminmax, int32_t e) {
-    switch (sc.kind) {
-        case EPP_SCORER_KV_UTIL:   // kvcache_utilization.go:79
-            return __dsub_rn(1.0, pool.kv_usage[e]);
-        case EPP_SCORER_QUEUE:     // queue.go:79-99
-        case EPP_SCORER_RUNNING: { // runningrequest.go:79-99
-            bool isq = sc.kind == EPP_SCORER_QUEUE;
-            int64_t mn = qminmax[isq ? 0 : 2], mx = qminmax[isq ? 1 : 3];
-            int64_t q = isq ? pool.waiting[e] : pool.running[e];
-            if (mx == mn) return 1.0;
-            return __ddiv_rn((double)(mx - q), (double)(mx - mn));
-        }
-        case EPP_SCORER_LOAD_AWARE: {  // load_aware.go:43-52, 87-97
-            double thr = sc.param;
-            if (!(thr > 0.0)) thr = 128.0;
-            double w = (double)pool.waiting[e];
-            if (w == 0.0) return 0.5;
-            if (w > thr) w = thr;
-            return __dmul_rn(0.5, __dsub_rn(1.0, __ddiv_rn(w, thr)));
-        }
-        case EPP_SCORER_EXTERNAL: {
-            int col = (int)sc.param;
-            if (col < 0 || col >= pool.n_ext_cols) return 0.0;
-            return pool.ext[(size_t)col * (size_t)pool.E + (size_t)e];
-        }
-        default: return 0.0;
-    }
-}
-
-// Ordered weighted sum of one endpoint (runScorerPlugins, scheduler_profile.go:151-174).
-__device__ __forceinline__ double weighted_sum(const ProfileDev &pf, int32_t E, uint32_t e, int32_t match,
-                                               int32_t total) {
-    double acc = 0.0;
-#pragma unroll 1
-    for (int s = 0; s < pf.cfg.n_scorers; s++) {
-        double term;
-        if (pf.cfg.scorers[s].kind == EPP_SCORER_PREFIX)
-            term = __dmul_rn(clamp01(prefix_score(match, total)), pf.cfg.scorers[s].weight);
-        else
-            term = pf.contrib[(size_t)s * (size_t)E + e];
-        acc = __dadd_rn(acc, term);
-    }
-    return acc;
-}
 
 // ------------------------------------------------------------------------------------------------
 // pool snapshot -> derived per-profile arrays
@@ -221,42 +142,6 @@ cudaError_t launch_pool_prepare(const PoolArrays &pool, const epp_profile_cfg &p
 }
 
 // ------------------------------------------------------------------------------------------------
-// warp helpers
-// ------------------------------------------------------------------------------------------------
-struct Best {
-    double val;
-    uint32_t pick;
-    uint32_t ties;
-};
-__device__ __forceinline__ void best_init(Best &b) { b.val = -CUDART_INF; b.pick = EPP_NO_ENDPOINT; b.ties = 0; }
-__device__ __forceinline__ void best_add(Best &b, double v, uint32_t e, uint32_t n = 1) {
-    if (v > b.val) { b.val = v; b.pick = e; b.ties = n; }
-    else if (v == b.val) { b.ties += n; if (e < b.pick) b.pick = e; }
-}
-__device__ __forceinline__ Best best_warp_reduce(Best b) {
-    double m = b.val;
-    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    uint32_t pk = (b.ties && b.val == m) ? b.pick : EPP_NO_ENDPOINT;
-    uint32_t tc = (b.ties && b.val == m) ? b.ties : 0;
-    for (int o = 16; o; o >>= 1) {
-        pk = min(pk, __shfl_xor_sync(0xffffffffu, pk, o));
-        tc += __shfl_xor_sync(0xffffffffu, tc, o);
-    }
-    Best r;
-    r.val = m; r.pick = pk; r.ties = tc;
-    return r;
-}
-
-// PrefixBasedPDDecider.disaggregate, prefix_based_pd_decider.go:99-149
-__device__ __forceinline__ bool pd_decide(int64_t nct, int64_t in_len_bytes, int32_t match_blocks, int32_t bst) {
-    if (nct == 0) return false;
-    int64_t tokens = in_len_bytes / 4;                    // getUserInputLenInTokens, :152-167
-    if (tokens < nct) return false;
-    int64_t hit = (int64_t)match_blocks * (int64_t)bst;
-    return (tokens - hit) >= nct;
-}
-
-// ------------------------------------------------------------------------------------------------
 // fused lookup + match + score + pick: one warp per request
 // ------------------------------------------------------------------------------------------------
 constexpr int kListCap = 128;   // matched-endpoint list per request; beyond it the warp falls back to a dense scan
@@ -264,19 +149,6 @@ constexpr int kPickWarps = 8;
 
 __device__ __forceinline__ uint32_t cnt_get(const uint32_t *cnt32, uint32_t e) {
     return (cnt32[e >> 1] >> ((e & 1u) * 16u)) & 0xFFFFu;
-}
-
-__device__ __forceinline__ bool probe(const IndexView &ix, uint64_t h, uint32_t &off, uint32_t &cnt) {
-    if (h == kEmptyKey) { off = ix.special.off; cnt = ix.special.cnt; return cnt != 0; }
-    if (!ix.slots) return false;
-    uint64_t i = h & ix.mask;
-    for (;;) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(ix.slots + i));
-        uint64_t key = ((uint64_t)raw.y << 32) | raw.x;
-        if (raw.w == 0) return false;                     // empty slot terminates the probe sequence
-        if (key == h) { off = raw.z; cnt = raw.w; return true; }
-        i = (i + 1) & ix.mask;
-    }
 }
 
 // Evaluate one profile for the current request.  cnt32 holds the per-endpoint match counts; list/nl the
@@ -347,7 +219,9 @@ __global__ void __launch_bounds__(kPickWarps * 32) k_match_pick(PickParams p, in
     unsigned long long w_probes = 0, w_postings = 0;    // algorithmic work of this warp's requests
     __syncwarp();
 
-    for (int64_t r = gwarp; r < p.R; r += nwarps) {
+    const int64_t n_work = p.req_list ? (int64_t)*p.req_list_n : p.R;
+    for (int64_t wi = gwarp; wi < n_work; wi += nwarps) {
+        const int64_t r = p.req_list ? (int64_t)p.req_list[wi] : wi;
         const int32_t total = p.nblocks[r];
         if (lane == 0) *list_n = 0;
         __syncwarp();
@@ -356,23 +230,25 @@ __global__ void __launch_bounds__(kPickWarps * 32) k_match_pick(PickParams p, in
         for (int32_t c0 = 0; c0 < total; c0 += 32) {
             int32_t i = c0 + lane;
             bool active = i < total;
-            uint32_t off = 0, cnt = 0;
-            bool hit = false;
-            if (active) hit = probe(p.index, row[i], off, cnt);
+            Hit hit;
+            hit.cnt = 0;
+            bool found = false;
+            if (active) found = probe(p.index, row[i], hit);
+            if (!found) hit.cnt = 0;
+            const uint32_t cnt = hit.cnt;
             uint32_t miss;
             if (p.global_masks) {   // sharded: a block is missing only if NO rank holds it
                 uint32_t word = p.global_masks[r * (int64_t)p.mask_words + (c0 >> 5)];
                 uint32_t valid = (total - c0) >= 32 ? 0xffffffffu : ((1u << (total - c0)) - 1u);
                 miss = ~word & valid;
-                if (!hit) cnt = 0;
             } else {
-                miss = __ballot_sync(0xffffffffu, active && !hit);
+                miss = __ballot_sync(0xffffffffu, active && !found);
             }
             int32_t limit = miss ? c0 + (__ffs(miss) - 1) : total;
             if (active && i < limit) {
                 w_postings += cnt;
                 for (uint32_t k = 0; k < cnt; k++) {
-                    uint32_t e = p.index.postings[off + k];
+                    uint32_t e = posting(p.index, hit, k);
                     if (e >= p.index.ep_begin && e < p.index.ep_end && e < (uint32_t)p.E) {
                         uint32_t sh = (e & 1u) * 16u;
                         uint32_t old = atomicAdd(&cnt32[e >> 1], 1u << sh);
@@ -572,8 +448,8 @@ __global__ void __launch_bounds__(256) k_shard_probe(int64_t R, int32_t max_bloc
         int32_t i = w * 32 + lane;
         bool hit = false;
         if (i < total) {
-            uint32_t off, cnt;
-            hit = probe(index, row[i], off, cnt);
+            Hit h;
+            hit = probe(index, row[i], h);
         }
         uint32_t word = __ballot_sync(0xffffffffu, hit);
         if (lane == 0) out_masks[r * (int64_t)mask_words + w] = word;

@@ -1,0 +1,129 @@
+// score.cuh -- device-side scoring arithmetic shared by the pick kernels (a5-a10, a13).
+//
+// Arithmetic contract: float64, IEEE round-to-nearest-even, NEVER fused -- every
+// multiply/add/divide is an explicit __d*_rn intrinsic (the files are also compiled with -fmad=false).
+// Scorer order = profile order; accumulation starts from +0.0 (scheduler_profile.go:155-168).
+#pragma once
+#include <math_constants.h>
+
+#include "kernels.h"
+
+namespace epp {
+
+// ------------------------------------------------------------------------------------------------
+// scorers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool filter_keeps(int filter, uint8_t role) {
+    if (role == 0xFF) return false;                       // slot not in the pool
+    switch (filter) {
+        case EPP_FILTER_NONE: return true;
+        case EPP_FILTER_DECODE:   // roles.go:46-48 (allowsNoLabel = true)
+            return role == EPP_ROLE_NONE || role == EPP_ROLE_DECODE || role == EPP_ROLE_PREFILL_DECODE ||
+                   role == EPP_ROLE_BOTH || role == EPP_ROLE_ENCODE_PREFILL_DECODE;
+        case EPP_FILTER_PREFILL:  // roles.go:56-58
+            return role == EPP_ROLE_PREFILL || role == EPP_ROLE_ENCODE_PREFILL || role == EPP_ROLE_PREFILL_DECODE ||
+                   role == EPP_ROLE_BOTH || role == EPP_ROLE_ENCODE_PREFILL_DECODE;
+        case EPP_FILTER_ENCODE:   // roles.go:68-70
+            return role == EPP_ROLE_ENCODE || role == EPP_ROLE_ENCODE_PREFILL ||
+                   role == EPP_ROLE_ENCODE_PREFILL_DECODE;
+        default: return false;
+    }
+}
+
+// enforceScoreRange, scheduler_profile.go:194-202 (NaN passes through, as in Go)
+__device__ __forceinline__ double clamp01(double s) {
+    if (s < 0.0) return 0.0;
+    if (s > 1.0) return 1.0;
+    return s;
+}
+
+// prefix-cache-scorer, scorer/prefix/plugin.go:100-111
+__device__ __forceinline__ double prefix_score(int32_t match, int32_t total) {
+    if (total == 0) return 0.0;
+    return __ddiv_rn((double)match, (double)total);
+}
+
+// Raw Scorer.Score value of one endpoint for the request-independent scorers.
+__device__ __forceinline__ double pool_score(const epp_scorer_cfg &sc, const PoolArrays &pool,
+                                             const int64_t *qminmax, int32_t e) {
+    switch (sc.kind) {
+        case EPP_SCORER_KV_UTIL:   // kvcache_utilization.go:79
+            return __dsub_rn(1.0, pool.kv_usage[e]);
+        case EPP_SCORER_QUEUE:     // queue.go:79-99
+        case EPP_SCORER_RUNNING: { // runningrequest.go:79-99
+            bool isq = sc.kind == EPP_SCORER_QUEUE;
+            int64_t mn = qminmax[isq ? 0 : 2], mx = qminmax[isq ? 1 : 3];
+            int64_t q = isq ? pool.waiting[e] : pool.running[e];
+            if (mx == mn) return 1.0;
+            return __ddiv_rn((double)(mx - q), (double)(mx - mn));
+        }
+        case EPP_SCORER_LOAD_AWARE: {  // load_aware.go:43-52, 87-97
+            double thr = sc.param;
+            if (!(thr > 0.0)) thr = 128.0;
+            double w = (double)pool.waiting[e];
+            if (w == 0.0) return 0.5;
+            if (w > thr) w = thr;
+            return __dmul_rn(0.5, __dsub_rn(1.0, __ddiv_rn(w, thr)));
+        }
+        case EPP_SCORER_EXTERNAL: {
+            int col = (int)sc.param;
+            if (col < 0 || col >= pool.n_ext_cols) return 0.0;
+            return pool.ext[(size_t)col * (size_t)pool.E + (size_t)e];
+        }
+        default: return 0.0;
+    }
+}
+
+// Ordered weighted sum of one endpoint (runScorerPlugins, scheduler_profile.go:151-174).
+__device__ __forceinline__ double weighted_sum(const ProfileDev &pf, int32_t E, uint32_t e, int32_t match,
+                                               int32_t total) {
+    double acc = 0.0;
+#pragma unroll 1
+    for (int s = 0; s < pf.cfg.n_scorers; s++) {
+        double term;
+        if (pf.cfg.scorers[s].kind == EPP_SCORER_PREFIX)
+            term = __dmul_rn(clamp01(prefix_score(match, total)), pf.cfg.scorers[s].weight);
+        else
+            term = pf.contrib[(size_t)s * (size_t)E + e];
+        acc = __dadd_rn(acc, term);
+    }
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp helpers
+// ------------------------------------------------------------------------------------------------
+struct Best {
+    double val;
+    uint32_t pick;
+    uint32_t ties;
+};
+__device__ __forceinline__ void best_init(Best &b) { b.val = -CUDART_INF; b.pick = EPP_NO_ENDPOINT; b.ties = 0; }
+__device__ __forceinline__ void best_add(Best &b, double v, uint32_t e, uint32_t n = 1) {
+    if (v > b.val) { b.val = v; b.pick = e; b.ties = n; }
+    else if (v == b.val) { b.ties += n; if (e < b.pick) b.pick = e; }
+}
+__device__ __forceinline__ Best best_warp_reduce(Best b) {
+    double m = b.val;
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    uint32_t pk = (b.ties && b.val == m) ? b.pick : EPP_NO_ENDPOINT;
+    uint32_t tc = (b.ties && b.val == m) ? b.ties : 0;
+    for (int o = 16; o; o >>= 1) {
+        pk = min(pk, __shfl_xor_sync(0xffffffffu, pk, o));
+        tc += __shfl_xor_sync(0xffffffffu, tc, o);
+    }
+    Best r;
+    r.val = m; r.pick = pk; r.ties = tc;
+    return r;
+}
+
+// PrefixBasedPDDecider.disaggregate, prefix_based_pd_decider.go:99-149
+__device__ __forceinline__ bool pd_decide(int64_t nct, int64_t in_len_bytes, int32_t match_blocks, int32_t bst) {
+    if (nct == 0) return false;
+    int64_t tokens = in_len_bytes / 4;                    // getUserInputLenInTokens, :152-167
+    if (tokens < nct) return false;
+    int64_t hit = (int64_t)match_blocks * (int64_t)bst;
+    return (tokens - hit) >= nct;
+}
+
+}  // namespace epp
