@@ -1,0 +1,216 @@
+// Package eppcuda is the cgo shim between the llm-d EPP (pkg/epp) and libepp_engine.so.
+//
+// It is shipped as SOURCE ONLY: the build environment of this repository has no Go toolchain, so this file has not
+// been compiled.  It binds exactly the symbols declared in include/epp_engine.h and keeps the reference's plugin
+// interfaces unchanged:
+//
+//	Scheduler.Schedule        pkg/epp/scheduling/scheduler.go:54        -> epp_schedule (micro-batched)
+//	DataProducer.Produce      framework/interface/requestcontrol/plugins.go:69-72 -> epp_prefix_match
+//	Scorer.Score              framework/interface/scheduling/plugins.go:68-72      -> epp_score
+//	PreRequest.PreRequest     framework/interface/requestcontrol/plugins.go:36-39  -> epp_index_add
+//
+// Build (once Go is available):  CGO_ENABLED=1 CGO_CFLAGS=-I${REPO}/include CGO_LDFLAGS="-L${REPO}/llm-d-inference-scheduler_b200 -lepp_engine" go build ./...
+package eppcuda
+
+/*
+#cgo LDFLAGS: -lepp_engine
+#include <stdlib.h>
+#include "epp_engine.h"
+*/
+import "C"
+
+import (
+	"context"
+	"errors"
+	"fmt"
+	"sync"
+	"time"
+	"unsafe"
+)
+
+// Engine wraps one epp_engine handle (one GPU).
+type Engine struct {
+	h     *C.epp_engine
+	mu    sync.Mutex        // guards slots
+	slots map[string]uint32 // NamespacedName -> dense slot id
+	free  []uint32
+	cfg   C.epp_config
+	batch *batcher
+}
+
+func lastErr(code C.int32_t) error {
+	return fmt.Errorf("epp_engine error %d: %s", int(code), C.GoString(C.epp_last_error()))
+}
+
+// ScorerSpec mirrors one `pluginRef` + weight of a SchedulingProfile (configloader.go:229-247).
+type ScorerSpec struct {
+	Kind   int     // C.EPP_SCORER_*
+	Weight float64 // default 1.0 (loader/defaults.go:42)
+	Param  float64
+}
+
+type ProfileSpec struct {
+	Filter  int // C.EPP_FILTER_*
+	Scorers []ScorerSpec
+}
+
+type Config struct {
+	Device               int
+	MaxEndpoints         int
+	BlockSizeTokens      int // approximateprefix config.BlockSizeTokens
+	MaxPrefixBlocks      int // config.MaxPrefixBlocksToMatch
+	LRUCapacityPerServer int
+	Primary              ProfileSpec  // the single profile, or "decode"
+	Prefill              *ProfileSpec // non-nil => disagg-profile-handler
+	NonCachedTokens      int64        // prefix-based-pd-decider
+	MaxBatch             int          // micro-batcher: flush at this many requests ...
+	MaxDelay             time.Duration // ... or after this long (e.g. 200us)
+}
+
+func fillProfile(dst *C.epp_profile_cfg, p ProfileSpec) {
+	dst.filter = C.int32_t(p.Filter)
+	dst.n_scorers = C.int32_t(len(p.Scorers))
+	for i, s := range p.Scorers {
+		dst.scorers[i].kind = C.int32_t(s.Kind)
+		dst.scorers[i].weight = C.double(s.Weight)
+		dst.scorers[i].param = C.double(s.Param)
+	}
+}
+
+// New creates the engine (plugin factory; registry.go:25-30).
+func New(c Config) (*Engine, error) {
+	e := &Engine{slots: map[string]uint32{}}
+	C.epp_config_default(&e.cfg)
+	e.cfg.device = C.int32_t(c.Device)
+	e.cfg.max_endpoints = C.int32_t(c.MaxEndpoints)
+	e.cfg.block_size_tokens = C.int32_t(c.BlockSizeTokens)
+	e.cfg.max_prefix_blocks = C.int32_t(c.MaxPrefixBlocks)
+	e.cfg.lru_capacity_per_server = C.int32_t(c.LRUCapacityPerServer)
+	fillProfile(&e.cfg.primary, c.Primary)
+	if c.Prefill != nil {
+		e.cfg.handler = C.EPP_HANDLER_DISAGG
+		e.cfg.non_cached_tokens = C.int64_t(c.NonCachedTokens)
+		fillProfile(&e.cfg.prefill, *c.Prefill)
+	}
+	if rc := C.epp_engine_create(&e.cfg, &e.h); rc != 0 {
+		return nil, lastErr(rc) // EPP_ERR_NO_DEVICE: keep the stock Go scorers registered instead
+	}
+	e.batch = newBatcher(e, c.MaxBatch, c.MaxDelay)
+	return e, nil
+}
+
+func (e *Engine) Close() { C.epp_engine_destroy(e.h) }
+
+// RegisterModel registers request.TargetModel (+ cache salt); returns the id used in batches.
+func (e *Engine) RegisterModel(model, salt string) (uint32, error) {
+	var id C.uint32_t
+	m, s := []byte(model), []byte(salt)
+	var mp, sp *C.uint8_t
+	if len(m) > 0 {
+		mp = (*C.uint8_t)(unsafe.Pointer(&m[0]))
+	}
+	if len(s) > 0 {
+		sp = (*C.uint8_t)(unsafe.Pointer(&s[0]))
+	}
+	if rc := C.epp_model_register(e.h, mp, C.size_t(len(m)), sp, C.size_t(len(s)), &id); rc != 0 {
+		return 0, lastErr(rc)
+	}
+	return uint32(id), nil
+}
+
+// PoolEntry is what the 50 ms scrape loop knows about one endpoint (fwkdl.Metrics + role label).
+type PoolEntry struct {
+	Name        string // NamespacedName
+	Role        uint8  // C.EPP_ROLE_*
+	KVUsage     float64
+	Waiting     int32
+	Running     int32
+}
+
+// SetPool replaces the snapshot (Datastore.PodList + metrics; director.go:222-230).
+func (e *Engine) SetPool(entries []PoolEntry) error {
+	n := len(entries)
+	ids := make([]C.uint32_t, n)
+	role := make([]C.uint8_t, n)
+	kv := make([]C.double, n)
+	wq := make([]C.int32_t, n)
+	rq := make([]C.int32_t, n)
+	e.mu.Lock()
+	for i, p := range entries {
+		ids[i] = C.uint32_t(e.slotOf(p.Name))
+		role[i], kv[i], wq[i], rq[i] = C.uint8_t(p.Role), C.double(p.KVUsage), C.int32_t(p.Waiting), C.int32_t(p.Running)
+	}
+	e.mu.Unlock()
+	if n == 0 {
+		return errors.New("empty pool")
+	}
+	if rc := C.epp_pool_set(e.h, C.int32_t(n), &ids[0], &role[0], &kv[0], &wq[0], &rq[0], nil); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+func (e *Engine) slotOf(name string) uint32 {
+	if s, ok := e.slots[name]; ok {
+		return s
+	}
+	var s uint32
+	if n := len(e.free); n > 0 {
+		s, e.free = e.free[n-1], e.free[:n-1]
+	} else {
+		s = uint32(len(e.slots))
+	}
+	e.slots[name] = s
+	return s
+}
+
+// RemoveEndpoint mirrors indexer.RemovePod (indexer.go:167-182) / CleanUpInactivePods (plugin.go:99-122).
+func (e *Engine) RemoveEndpoint(name string) {
+	e.mu.Lock()
+	s, ok := e.slots[name]
+	if ok {
+		delete(e.slots, name)
+		e.free = append(e.free, s)
+	}
+	e.mu.Unlock()
+	if ok {
+		C.epp_index_remove_endpoint(e.h, C.uint32_t(s))
+	}
+}
+
+// Decision is one epp_decision translated back to endpoint names.
+type Decision struct {
+	Err         error
+	Pick        uint32
+	Score       float64
+	PrefillPick uint32 // EPP_NO_ENDPOINT when absent
+	TotalBlocks int
+	MatchBlocks int
+}
+
+// Schedule is what a Scheduler implementation (director.go:69-71) calls per request; requests from concurrent
+// ext-proc goroutines (handlers/server.go:168) are coalesced by the micro-batcher into one epp_schedule call.
+func (e *Engine) Schedule(ctx context.Context, modelID uint32, prompt []byte) (Decision, error) {
+	return e.batch.submit(ctx, modelID, prompt)
+}
+
+// scheduleBatch is the single cgo crossing per batch.  Prompts are copied into a pinned C staging buffer
+// (epp_host_alloc) so that no Go pointer is retained by C and the H2D copy is asynchronous.
+func (e *Engine) scheduleBatch(stage unsafe.Pointer, offsets, lengths []C.uint64_t, modelIDs []C.uint32_t, out []C.epp_decision) error {
+	var b C.epp_batch
+	b.n_requests = C.int64_t(len(modelIDs))
+	b.data = stage
+	b.offsets = &offsets[0]
+	b.lengths = &lengths[0]
+	b.model_ids = &modelIDs[0]
+	if rc := C.epp_schedule(e.h, &b, &out[0], nil, 1 /* keep_hashes: PreRequest follows */); rc != 0 {
+		return lastErr(rc)
+	}
+	// PreRequest (approximateprefix/plugin.go:164-200): index the batch's hashes for the picked endpoints.
+	if rc := C.epp_index_add_picked(e.h); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+var errNoEndpoints = errors.New("no endpoints available for the given request") // scheduler_profile.go:119-121

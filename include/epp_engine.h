@@ -153,8 +153,10 @@ typedef struct {
 
 #define EPP_BATCH_DEVICE_PTRS 1u   /* data / offsets / model_ids and all outputs are DEVICE pointers */
 
-/* A batch of prompts.  Prompt r is data[offsets[r] .. offsets[r+1]) (bytes).  A uint32 token array viewed
- * as little-endian bytes is a prompt with 4 bytes/token (hashing.go:49, types.go:113). */
+/* A batch of prompts.  Prompt r is data[offsets[r] .. offsets[r+1]) (bytes), or data[offsets[r] .. offsets[r] +
+ * lengths[r]) when `lengths` is given (lets ragged prompts START on 32-byte boundaries, which selects the 256-bit-load
+ * kernel; offsets[r] + lengths[r] <= offsets[r+1] must hold).  A uint32 token array viewed as little-endian bytes is
+ * a prompt with 4 bytes/token (hashing.go:49, types.go:113). */
 typedef struct {
     int64_t n_requests;
     const void *data;
@@ -163,6 +165,7 @@ typedef struct {
     const uint32_t *model_ids;     /* [n_requests] ids from epp_model_register; NULL => model 0       */
     uint32_t flags;                /* EPP_BATCH_* */
     uint32_t reserved;
+    const uint64_t *lengths;       /* [n_requests] or NULL */
 } epp_batch;
 
 typedef struct {

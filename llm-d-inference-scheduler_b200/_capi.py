@@ -50,7 +50,7 @@ class DecisionDetail(C.Structure):
 class Batch(C.Structure):
     _fields_ = [("n_requests", C.c_int64), ("data", C.c_void_p), ("offsets", C.c_void_p),
                 ("uniform_len", C.c_uint64), ("model_ids", C.c_void_p), ("flags", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("reserved", C.c_uint32), ("lengths", C.c_void_p)]
 
 
 class Stats(C.Structure):

@@ -119,7 +119,7 @@ struct epp_engine {
     uint32_t shard_begin = 0, shard_end = 0xFFFFFFFFu;
 
     // batch buffers (sized for the largest batch seen)
-    DevBuf offsets, model_ids, hashes, nblocks, eff_len, in_len, decisions, details, flag;
+    DevBuf offsets, lengths, model_ids, hashes, nblocks, eff_len, in_len, decisions, details, flag;
     DevBuf dense_match, dense_total, dense_scores;
     DevBuf pick_scratch;            // global match counters when E is too large for shared memory
     int force_v1 = 0;               // EPP_HASH_V1=1: unfused v1 hash kernels (A/B)
@@ -533,6 +533,7 @@ struct BatchView {
     bool device = false;
     const uint8_t *data = nullptr;
     const uint64_t *offsets = nullptr;
+    const uint64_t *lengths = nullptr;
     uint64_t uniform_len = 0;
     const uint32_t *model_ids = nullptr;
     uint64_t total_bytes = 0;      // host batches only
@@ -547,6 +548,8 @@ static int32_t check_batch(epp_engine *h, const epp_batch *b, BatchView &v) {
     v.device = (b->flags & EPP_BATCH_DEVICE_PTRS) != 0;
     v.data = reinterpret_cast<const uint8_t *>(b->data);
     v.offsets = b->offsets;
+    v.lengths = b->lengths;
+    if (v.lengths && !v.offsets) return fail(EPP_ERR_INVALID, "lengths needs offsets");
     v.uniform_len = b->uniform_len;
     v.model_ids = b->model_ids;
     if (v.R == 0) return EPP_OK;
@@ -556,6 +559,7 @@ static int32_t check_batch(epp_engine *h, const epp_batch *b, BatchView &v) {
             uint64_t bits = 0;
             for (int64_t r = 0; r < v.R; r++) {
                 if (v.offsets[r + 1] < v.offsets[r]) return fail(EPP_ERR_INVALID, "offsets not monotonic at request %lld", (long long)r);
+                if (v.lengths && v.offsets[r] + v.lengths[r] > v.offsets[r + 1]) return fail(EPP_ERR_INVALID, "request %lld: offsets[r] + lengths[r] exceeds offsets[r+1]", (long long)r);
                 bits |= v.offsets[r];
             }
             v.offsets_or_bits = bits;
@@ -581,6 +585,7 @@ static int32_t reserve_batch(epp_engine *h, int64_t R) {
     CUDA_TRY(h->decisions.reserve(sizeof(epp_decision) * n, &h->dev_bytes));
     CUDA_TRY(h->details.reserve(sizeof(epp_decision_detail) * n, &h->dev_bytes));
     CUDA_TRY(h->offsets.reserve(sizeof(uint64_t) * (n + 1), &h->dev_bytes));
+    CUDA_TRY(h->lengths.reserve(sizeof(uint64_t) * n, &h->dev_bytes));
     CUDA_TRY(h->model_ids.reserve(sizeof(uint32_t) * n, &h->dev_bytes));
     for (int i = 0; i < 2; i++) CUDA_TRY(h->slot[i].overflow_list.reserve(sizeof(int32_t) * n, &h->dev_bytes));
     return EPP_OK;
@@ -591,6 +596,7 @@ struct Work {
     int64_t r0, r1;
     const uint8_t *data_base;
     const uint64_t *offsets_dev;   // indexed by absolute request id, or nullptr
+    const uint64_t *lengths_dev;   // absolute, or nullptr
     uint64_t uniform_len;
     const uint32_t *model_ids_dev; // absolute, or nullptr
     uint64_t offsets_or_bits;      // OR of all offsets (alignment of the batch layout)
@@ -603,6 +609,7 @@ static HashParams hash_params(epp_engine *h, const Work &w) {
     int64_t n = w.r1 - w.r0;
     p.data = w.data_base;
     p.offsets = w.offsets_dev ? w.offsets_dev + w.r0 : nullptr;
+    p.lengths = w.lengths_dev ? w.lengths_dev + w.r0 : nullptr;
     p.uniform_len = w.uniform_len;
     p.model_ids = w.model_ids_dev ? w.model_ids_dev + w.r0 : nullptr;
     p.seeds = h->seeds.as<uint64_t>();
@@ -729,7 +736,7 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
     if (v.device) {
         uint64_t or_bits = 0;
         if (v.offsets) EPP_TRY(device_offsets_or_bits(h, v.offsets, R, s0, &or_bits));
-        Work w{0, R, v.data, v.offsets, v.uniform_len, v.model_ids, or_bits,
+        Work w{0, R, v.data, v.offsets, v.lengths, v.uniform_len, v.model_ids, or_bits,
                (mode == Mode::HashOnly && out_hashes) ? out_hashes : h->hashes.as<uint64_t>(),
                (mode == Mode::HashOnly && out_nblocks) ? out_nblocks : (mode == Mode::Match && out_total ? out_total : h->nblocks.as<int32_t>())};
         CUDA_TRY(cudaMemsetAsync(h->work_counters.p, 0, sizeof(unsigned long long) * 2, s0));
@@ -760,6 +767,7 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
 
     // ---- host batch: upload the small per-request arrays once, then pipeline the prompt bytes
     if (v.offsets) CUDA_TRY(cudaMemcpyAsync(h->offsets.p, v.offsets, sizeof(uint64_t) * (size_t)(R + 1), cudaMemcpyHostToDevice, s0));
+    if (v.lengths) CUDA_TRY(cudaMemcpyAsync(h->lengths.p, v.lengths, sizeof(uint64_t) * (size_t)R, cudaMemcpyHostToDevice, s0));
     if (v.model_ids) CUDA_TRY(cudaMemcpyAsync(h->model_ids.p, v.model_ids, sizeof(uint32_t) * (size_t)R, cudaMemcpyHostToDevice, s0));
     CUDA_TRY(cudaEventRecord(h->slot[0].done, s0));
     CUDA_TRY(cudaStreamWaitEvent(h->slot[1].stream, h->slot[0].done, 0));
@@ -806,10 +814,12 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
             // the kernels address  data_base + offsets[r]  with ABSOLUTE offsets
             w.data_base = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(stage) - (uintptr_t)c.start);
             w.offsets_dev = h->offsets.as<uint64_t>();
+            w.lengths_dev = v.lengths ? h->lengths.as<uint64_t>() : nullptr;
             w.offsets_or_bits = v.offsets_or_bits;
         } else {
             w.data_base = stage;                    // chunk-local request index * uniform_len
             w.offsets_dev = nullptr;
+            w.lengths_dev = nullptr;
             w.offsets_or_bits = 0;
         }
         w.uniform_len = v.uniform_len;
@@ -1045,7 +1055,7 @@ extern "C" int32_t epp_shard_pick(epp_engine *h, int64_t n_requests, const uint3
     if (!h->pool_ready) return fail(EPP_ERR_STATE, "epp_pool_set has not been called (after epp_shard_set)");
     if (n_requests != h->shard_R) return fail(EPP_ERR_STATE, "epp_shard_pick: n_requests %lld does not match the probed batch (%lld)", (long long)n_requests, (long long)h->shard_R);
     if (n_requests == 0) return EPP_OK;
-    Work w{0, n_requests, nullptr, nullptr, 0, nullptr, 0, h->hashes.as<uint64_t>(), h->nblocks.as<int32_t>()};
+    Work w{0, n_requests, nullptr, nullptr, nullptr, 0, nullptr, 0, h->hashes.as<uint64_t>(), h->nblocks.as<int32_t>()};
     PickParams pp = pick_params(h, w, h->decisions.as<epp_decision>(), nullptr, nullptr);
     pp.global_masks = global_masks;
     pp.mask_words = mask_words_of(h);

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(Cta<kMatch>::kThreads) k_hash_fused(HashParams
             int32_t nfull = 0;
             if (r < p.R) {
                 uint64_t len;
-                if (p.offsets) { off = p.offsets[r]; len = p.offsets[r + 1] - off; }
+                if (p.offsets) { off = p.offsets[r]; len = p.lengths ? p.lengths[r] : p.offsets[r + 1] - off; }
                 else { off = (uint64_t)r * p.uniform_len; len = p.uniform_len; }
                 if (p.in_len) p.in_len[r] = (int64_t)len;
                 eff = (int64_t)len;

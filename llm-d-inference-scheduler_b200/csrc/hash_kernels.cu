@@ -14,7 +14,7 @@ namespace epp {
 __device__ __forceinline__ void request_span(const HashParams &p, int64_t r, uint64_t &off, uint64_t &len) {
     if (p.offsets) {
         off = p.offsets[r];
-        len = p.offsets[r + 1] - off;
+        len = p.lengths ? p.lengths[r] : p.offsets[r + 1] - off;
     } else {
         off = (uint64_t)r * p.uniform_len;
         len = p.uniform_len;

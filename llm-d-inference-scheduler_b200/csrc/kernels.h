@@ -13,6 +13,7 @@ namespace epp {
 struct HashParams {
     const uint8_t *data;        // prompt bytes (device)
     const uint64_t *offsets;    // [R+1] device, or nullptr => uniform_len
+    const uint64_t *lengths;    // [R] device or nullptr => offsets[r+1] - offsets[r]
     uint64_t uniform_len;
     const uint32_t *model_ids;  // [R] device or nullptr
     const uint64_t *seeds;      // device table of h_{-1} per registered model

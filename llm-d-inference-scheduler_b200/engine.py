@@ -161,7 +161,7 @@ class Engine:
         self._check(self._lib.epp_index_add_picked(self._h))
 
     # ---- batches ----
-    def _batch(self, data, offsets=None, uniform_len=None, model_ids=None, n_requests=None):
+    def _batch(self, data, offsets=None, uniform_len=None, model_ids=None, n_requests=None, lengths=None):
         """data: bytes-like numpy array / torch CUDA tensor (any dtype, viewed as bytes)."""
         b = capi.Batch()
         dev = _is_torch(data)
@@ -195,12 +195,17 @@ class Engine:
                 model_ids = np.ascontiguousarray(model_ids, dtype=np.uint32)
             keep.append(model_ids)
             b.model_ids = _ptr(model_ids)
+        if lengths is not None:
+            if not dev:
+                lengths = np.ascontiguousarray(lengths, dtype=np.uint64)
+            keep.append(lengths)
+            b.lengths = _ptr(lengths)
         b.n_requests = R
         return b, R, dev, keep
 
-    def hash_prompts(self, data, offsets=None, uniform_len=None, model_ids=None, n_requests=None, out=None):
+    def hash_prompts(self, data, offsets=None, uniform_len=None, model_ids=None, n_requests=None, lengths=None, out=None):
         """a1 hashPrompt -> (hashes [R, max_prefix_blocks] u64, nblocks [R] i32)."""
-        b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests)
+        b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests, lengths)
         if dev:
             import torch
             hashes = torch.empty((max(R, 1), self.B), dtype=torch.int64, device=data.device) if out is None else out[0]
@@ -211,9 +216,9 @@ class Engine:
         self._check(self._lib.epp_hash_prompts(self._h, C.byref(b), _ptr(hashes), _ptr(nb)))
         return hashes, nb
 
-    def prefix_match(self, data, offsets=None, uniform_len=None, model_ids=None, n_requests=None):
+    def prefix_match(self, data, offsets=None, uniform_len=None, model_ids=None, n_requests=None, lengths=None):
         """a1-a4 Produce -> (match [R, E] i32, total [R] i32)."""
-        b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests)
+        b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests, lengths)
         if dev:
             import torch
             match = torch.empty((max(R, 1), self.E), dtype=torch.int32, device=data.device)
@@ -234,9 +239,9 @@ class Engine:
         return out
 
     def schedule(self, data, offsets=None, uniform_len=None, model_ids=None, n_requests=None, keep_hashes=False,
-                 detail=True, out=None):
+                 detail=True, out=None, lengths=None):
         """a1-a14 Scheduler.Schedule for a batch -> (decisions, details)."""
-        b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests)
+        b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests, lengths)
         if dev:
             import torch
             dec = out if out is not None else torch.empty((max(R, 1), 32), dtype=torch.uint8, device=data.device)
@@ -270,7 +275,7 @@ class Engine:
         self._check(self._lib.epp_shard_set(self._h, ep_begin, ep_end))
 
     def shard_probe(self, data, out_masks, offsets=None, uniform_len=None, model_ids=None, n_requests=None):
-        b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests)
+        b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests, lengths)
         self._check(self._lib.epp_shard_probe(self._h, C.byref(b), _ptr(out_masks)))
         return R
 

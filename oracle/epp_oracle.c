@@ -543,11 +543,26 @@ static inline double enforce_score_range(double s) {
 /* =====================================================================================
  * A.5 SchedulerProfile.Run -- scheduling/scheduler_profile.go:117-192 + maxscore picker
  * ===================================================================================== */
+static int profile_run_scratch(const orc_profile *p, const orc_pool *pool, const int32_t *match, int32_t total,
+                               double *out_scores, double *out_max, int32_t *out_pick, int32_t *argmax_set,
+                               uint8_t *cand, double *col);
+
 int orc_profile_run(const orc_profile *p, const orc_pool *pool, const int32_t *match, int32_t total,
                     double *out_scores, double *out_max, int32_t *out_pick, int32_t *argmax_set) {
     int n = pool->n;
     uint8_t *cand = (uint8_t *)malloc((size_t)n + 1);
     double *col = (double *)malloc(sizeof(double) * ((size_t)n + 1));
+    int r = profile_run_scratch(p, pool, match, total, out_scores, out_max, out_pick, argmax_set, cand, col);
+    free(cand); free(col);
+    return r;
+}
+
+/* The Go code allocates fresh maps per call; the timed CPU baseline reuses per-thread scratch instead, which only
+ * makes the baseline FASTER than the reference. */
+static int profile_run_scratch(const orc_profile *p, const orc_pool *pool, const int32_t *match, int32_t total,
+                               double *out_scores, double *out_max, int32_t *out_pick, int32_t *argmax_set,
+                               uint8_t *cand, double *col) {
+    int n = pool->n;
     int n_cand = 0;
     for (int e = 0; e < n; e++) {                       /* runFilterPlugins, :130-149 */
         cand[e] = (uint8_t)orc_role_filter_keeps(p->filter, pool->role[e]);
@@ -555,7 +570,6 @@ int orc_profile_run(const orc_profile *p, const orc_pool *pool, const int32_t *m
     }
     if (n_cand == 0) {                                  /* :119-121 */
         for (int e = 0; e < n; e++) out_scores[e] = -1.0;
-        free(cand); free(col);
         if (out_max) *out_max = 0;
         if (out_pick) *out_pick = -1;
         return 0;
@@ -588,7 +602,6 @@ int orc_profile_run(const orc_profile *p, const orc_pool *pool, const int32_t *m
     }
     if (out_max) *out_max = mx;
     if (out_pick) *out_pick = first;
-    free(cand); free(col);
     return cnt;
 }
 
@@ -605,14 +618,30 @@ int orc_pd_decide(int64_t non_cached_tokens, int64_t input_len_bytes, int32_t ma
 }
 
 /* Scheduler.Schedule + single / disagg profile handlers */
+static void schedule_scratch(const orc_profile *primary, const orc_profile *prefill, const orc_pool *pool,
+                             const int32_t *match, int32_t total, int32_t block_size_tokens, int64_t input_len_bytes,
+                             int64_t non_cached_tokens, int always_disagg, double *scratch_scores, orc_decision *out,
+                             uint8_t *cand, double *col);
+
 void orc_schedule(const orc_profile *primary, const orc_profile *prefill, const orc_pool *pool,
                   const int32_t *match, int32_t total, int32_t block_size_tokens,
                   int64_t input_len_bytes, int64_t non_cached_tokens, int always_disagg,
                   double *scratch_scores, orc_decision *out) {
+    uint8_t *cand = (uint8_t *)malloc((size_t)pool->n + 1);
+    double *col = (double *)malloc(sizeof(double) * ((size_t)pool->n + 1));
+    schedule_scratch(primary, prefill, pool, match, total, block_size_tokens, input_len_bytes, non_cached_tokens,
+                     always_disagg, scratch_scores, out, cand, col);
+    free(cand); free(col);
+}
+
+static void schedule_scratch(const orc_profile *primary, const orc_profile *prefill, const orc_pool *pool,
+                             const int32_t *match, int32_t total, int32_t block_size_tokens, int64_t input_len_bytes,
+                             int64_t non_cached_tokens, int always_disagg, double *scratch_scores, orc_decision *out,
+                             uint8_t *cand, double *col) {
     memset(out, 0, sizeof *out);
     out->pick = -1; out->prefill_pick = -1;
     double mx; int32_t pick;
-    int ties = orc_profile_run(primary, pool, match, total, scratch_scores, &mx, &pick, NULL);
+    int ties = profile_run_scratch(primary, pool, match, total, scratch_scores, &mx, &pick, NULL, cand, col);
     if (ties == 0) {            /* disagg ProcessResults :335-338 / single ProcessResults: error */
         out->status = -1;
         return;
@@ -624,10 +653,24 @@ void orc_schedule(const orc_profile *primary, const orc_profile *prefill, const 
         out->prefill_ran = go;
         if (go) {
             double pmx; int32_t ppick;
-            int pt = orc_profile_run(prefill, pool, match, total, scratch_scores, &pmx, &ppick, NULL);
+            int pt = profile_run_scratch(prefill, pool, match, total, scratch_scores, &pmx, &ppick, NULL, cand, col);
             if (pt > 0) { out->prefill_pick = ppick; out->prefill_tie_count = pt; out->prefill_score = pmx; }
         }
     }
+}
+
+static void cycle_scratch(const orc_cycle_cfg *cfg, const orc_indexer *ix, const orc_profile *primary,
+                          const orc_profile *prefill, const orc_pool *pool, const uint8_t *prompt, size_t prompt_len,
+                          uint64_t *scratch_hashes, int32_t *scratch_match, double *scratch_scores, orc_decision *out,
+                          int32_t *out_total, uint8_t *cand, double *col) {
+    int cap = cfg->max_prefix_blocks + 1;
+    int total = orc_hash_prompt(prompt, prompt_len, cfg->model, cfg->model_len, NULL, 0,
+                                cfg->block_size_tokens, cfg->max_prefix_blocks, scratch_hashes, cap);
+    memset(scratch_match, 0, sizeof(int32_t) * (size_t)pool->n);
+    orc_match_longest_prefix(ix, scratch_hashes, total, scratch_match, pool->n);
+    schedule_scratch(primary, prefill, pool, scratch_match, total, cfg->block_size_tokens, (int64_t)prompt_len,
+                     cfg->non_cached_tokens, cfg->always_disagg, scratch_scores, out, cand, col);
+    if (out_total) *out_total = total;
 }
 
 void orc_cycle(const orc_cycle_cfg *cfg, const orc_indexer *ix, const orc_profile *primary,
@@ -656,12 +699,14 @@ static void *batch_worker(void *arg) {
     uint64_t *hashes = (uint64_t *)malloc(sizeof(uint64_t) * ((size_t)j->cfg->max_prefix_blocks + 2));
     int32_t *match = (int32_t *)malloc(sizeof(int32_t) * ((size_t)n + 1));
     double *scores = (double *)malloc(sizeof(double) * ((size_t)n + 1));
+    uint8_t *cand = (uint8_t *)malloc((size_t)n + 1);
+    double *col = (double *)malloc(sizeof(double) * ((size_t)n + 1));
     for (int64_t r = j->lo; r < j->hi; r++) {
-        orc_cycle(j->cfg, j->ix, j->primary, j->prefill, j->pool, j->data + j->offsets[r],
-                  (size_t)(j->offsets[r + 1] - j->offsets[r]), hashes, match, scores, &j->out[r],
-                  j->out_total ? &j->out_total[r] : NULL);
+        cycle_scratch(j->cfg, j->ix, j->primary, j->prefill, j->pool, j->data + j->offsets[r],
+                      (size_t)(j->offsets[r + 1] - j->offsets[r]), hashes, match, scores, &j->out[r],
+                      j->out_total ? &j->out_total[r] : NULL, cand, col);
     }
-    free(hashes); free(match); free(scores);
+    free(hashes); free(match); free(scores); free(cand); free(col);
     return NULL;
 }
 
