@@ -37,8 +37,8 @@ constexpr int kBarFull = 1;               // named barrier ids 1..4
 constexpr int kBarEmpty = 1 + kStages;    // 5..8
 constexpr int kBarHashed = 1 + 2 * kStages;   // 9..12
 constexpr int kBarTail = 1 + 3 * kStages;     // 13
+constexpr int kLag = 3;                   // digest warps match window k-kLag while hashing window k (kLag < kStages)
 constexpr int kMaxRuns = 24;              // run records per request before the dense-counter fallback takes over
-template <bool kMatch> struct Cta { static constexpr int kThreads = kDigestThreads + 32 + (kMatch ? 32 : 0); };
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -63,33 +63,99 @@ __device__ __forceinline__ void load_stripe(const uint8_t *p, uint64_t x[4]) {
     }
 }
 
-struct MatchSmem {                        // match warp state (kMatch only); every array is [..][lane]
-    uint4 slot[kWin][2][32];              // the window's table slots: [block in window][half of the 32 bytes][lane]
-    uint32_t run[kMaxRuns][7][32];        // run queue: (length, count, w0..w4)
-    uint64_t tail_hash[32];
-    uint32_t has_tail[32];
-};
+// Per-request lengths (hashing.go:58-66) for one tile; called by threads t < kTileR (one warp).
+__device__ __forceinline__ void tile_lengths(const HashParams &p, int64_t r0, int t, uint64_t *s_off, int64_t *s_eff,
+                                             int32_t *s_nfull, int32_t *s_maxfull) {
+    const int64_t bs = p.block_bytes;
+    int64_t r = r0 + t;
+    uint64_t off = 0;
+    int64_t eff = 0;
+    int32_t nfull = 0;
+    if (r < p.R) {
+        uint64_t len;
+        if (p.offsets) { off = p.offsets[r]; len = p.lengths ? p.lengths[r] : p.offsets[r + 1] - off; }
+        else { off = (uint64_t)r * p.uniform_len; len = p.uniform_len; }
+        if (p.in_len) p.in_len[r] = (int64_t)len;
+        eff = (int64_t)len;
+        int32_t nb = 0;
+        if (eff < bs) {
+            eff = 0;
+        } else {
+            int64_t cap = bs * (int64_t)p.max_blocks;
+            if (eff > cap) eff = cap;
+            nfull = (int32_t)(eff / bs);
+            nb = nfull + ((eff % bs) ? 1 : 0);
+        }
+        p.nblocks[r] = nb;
+        p.eff_len[r] = eff;
+    }
+    s_off[t] = off;
+    s_eff[t] = eff;
+    s_nfull[t] = nfull;
+    int mx = nfull;
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (t == 0) *s_maxfull = mx;
+}
 
-__device__ __forceinline__ lane::Slot8 ring_read(const MatchSmem &ms, int q, int lane) {
-    uint4 a = ms.slot[q][0][lane], b = ms.slot[q][1][lane];
-    lane::Slot8 s;
-    s.key = ((uint64_t)a.y << 32) | a.x;
-    s.cnt = a.z; s.w0 = a.w;
-    s.w1 = b.x; s.w2 = b.y; s.w3 = b.z; s.w4 = b.w;
-    return s;
+// Stripe rounds + merge of one full block (part A of xxh64.cuh).
+template <bool kAlign32>
+__device__ __forceinline__ uint64_t block_digest(const uint8_t *src, int n_stripes) {
+    uint64_t v[4];
+    xxh_init(v);
+    if (n_stripes == 2) {               // the default 64-byte block: both stripes in flight at once
+        uint64_t x0[4], x1[4];
+        load_stripe<kAlign32>(src, x0);
+        load_stripe<kAlign32>(src + 32, x1);
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[q] = xxh_round(v[q], x0[q]);
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[q] = xxh_round(v[q], x1[q]);
+    } else {
+        for (int st = 0; st < n_stripes; st++) {
+            uint64_t x[4];
+            load_stripe<kAlign32>(src + 32 * st, x);
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[q] = xxh_round(v[q], x[q]);
+        }
+    }
+    return xxh_merge_all(v);
+}
+
+// Chain warp, one window: the serial part of the digest for 32 requests at once, in place, then the 8 hashes of
+// each request written as one 64-byte segment.
+__device__ __forceinline__ uint64_t chain_window(uint64_t (*sm)[kPitch], const int32_t *s_nfull, const HashParams &p,
+                                                 int64_t r0, int k, int lane, int32_t nfull, uint64_t lenp8,
+                                                 uint64_t prev) {
+#pragma unroll
+    for (int j = 0; j < kWin; j++) {
+        if (k * kWin + j < nfull) {
+            prev = xxh_chain_step32(sm[lane][j], lenp8, prev);
+            sm[lane][j] = prev;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < kTileR / 4; it++) {
+        int rr = it * 4 + (lane >> 3), jj = lane & 7;
+        int b = k * kWin + jj;
+        if (b < s_nfull[rr]) p.hashes[(r0 + rr) * (int64_t)p.max_blocks + b] = sm[rr][jj];
+    }
+    __syncwarp();
+    return prev;
 }
 }  // namespace
 
-template <bool kAlign32, bool kMatch>
-__global__ void __launch_bounds__(Cta<kMatch>::kThreads) k_hash_fused(HashParams p, PickParams pk, int n_tiles) {
-    constexpr int kProducers = kDigestThreads + 32;       // threads on the full/empty barriers
+// =====================================================================================================
+// k_hash_fused: a1 only (epp_hash_prompts, Produce-parity and sharded modes, A/B runs)
+// =====================================================================================================
+template <bool kAlign32>
+__global__ void __launch_bounds__(kDigestThreads + 32) k_hash_fused(HashParams p, int n_tiles) {
+    constexpr int kProducers = kDigestThreads + 32;
     __shared__ uint64_t s_m[kStages][kTileR][kPitch];
     __shared__ uint64_t s_off[kTileR];
     __shared__ int64_t s_eff[kTileR];
     __shared__ int32_t s_nfull[kTileR];
     __shared__ int32_t s_maxfull;
-    __shared__ __align__(16) unsigned char s_match_raw[kMatch ? sizeof(MatchSmem) : 16];
-    MatchSmem &ms = *reinterpret_cast<MatchSmem *>(s_match_raw);
 
     const int t = threadIdx.x;
     const int warp = t >> 5, lane = t & 31;
@@ -99,80 +165,25 @@ __global__ void __launch_bounds__(Cta<kMatch>::kThreads) k_hash_fused(HashParams
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t r0 = (int64_t)tile * kTileR;
-        // ---- per-request lengths (hashing.go:58-66) by the first warp
-        if (t < kTileR) {
-            int64_t r = r0 + t;
-            uint64_t off = 0;
-            int64_t eff = 0;
-            int32_t nfull = 0;
-            if (r < p.R) {
-                uint64_t len;
-                if (p.offsets) { off = p.offsets[r]; len = p.lengths ? p.lengths[r] : p.offsets[r + 1] - off; }
-                else { off = (uint64_t)r * p.uniform_len; len = p.uniform_len; }
-                if (p.in_len) p.in_len[r] = (int64_t)len;
-                eff = (int64_t)len;
-                int32_t nb = 0;
-                if (eff < bs) {
-                    eff = 0;
-                } else {
-                    int64_t cap = bs * (int64_t)p.max_blocks;
-                    if (eff > cap) eff = cap;
-                    nfull = (int32_t)(eff / bs);
-                    nb = nfull + ((eff % bs) ? 1 : 0);
-                }
-                p.nblocks[r] = nb;
-                p.eff_len[r] = eff;
-            }
-            s_off[t] = off;
-            s_eff[t] = eff;
-            s_nfull[t] = nfull;
-            int mx = nfull;
-            for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            if (t == 0) s_maxfull = mx;
-        }
+        if (t < kTileR) tile_lengths(p, r0, t, s_off, s_eff, s_nfull, &s_maxfull);
         __syncthreads();
         const int n_win = (s_maxfull + kWin - 1) / kWin;
 
         if (warp < kDigestWarps) {
-            // ================= digest warps =================
             const int r = t / kWin, j = t % kWin;
             const int32_t nfull = s_nfull[r];
             const uint8_t *base = p.data + s_off[r] + (uint64_t)j * (uint64_t)bs;
             for (int k = 0; k < n_win; k++) {
                 const int s = k % kStages;
                 if (k >= kStages) bar_sync(kBarEmpty + s, kProducers);
-                const int b = k * kWin + j;
-                if (b < nfull) {
-                    const uint8_t *src = base + (uint64_t)k * (uint64_t)(kWin * bs);
-                    uint64_t v[4];
-                    xxh_init(v);
-                    if (n_stripes == 2) {               // the default 64-byte block: both stripes in flight at once
-                        uint64_t x0[4], x1[4];
-                        load_stripe<kAlign32>(src, x0);
-                        load_stripe<kAlign32>(src + 32, x1);
-#pragma unroll
-                        for (int q = 0; q < 4; q++) v[q] = xxh_round(v[q], x0[q]);
-#pragma unroll
-                        for (int q = 0; q < 4; q++) v[q] = xxh_round(v[q], x1[q]);
-                    } else {
-                        for (int st = 0; st < n_stripes; st++) {
-                            uint64_t x[4];
-                            load_stripe<kAlign32>(src + 32 * st, x);
-#pragma unroll
-                            for (int q = 0; q < 4; q++) v[q] = xxh_round(v[q], x[q]);
-                        }
-                    }
-                    s_m[s][r][j] = xxh_merge_all(v);
-                }
+                if (k * kWin + j < nfull)
+                    s_m[s][r][j] = block_digest<kAlign32>(base + (uint64_t)k * (uint64_t)(kWin * bs), n_stripes);
                 __threadfence_block();
                 bar_arrive(kBarFull + s, kProducers);
             }
-            // drain: the empty-barrier arrivals of the last min(n_win, kStages) windows must be consumed before
-            // the ring is reused by the next tile
             int first = n_win > kStages ? n_win - kStages : 0;
             for (int k = first; k < n_win; k++) bar_sync(kBarEmpty + (k % kStages), kProducers);
-        } else if (warp == kDigestWarps) {
-            // ================= chain warp: lane = request =================
+        } else {
             const int64_t r = r0 + lane;
             const int32_t nfull = s_nfull[lane];
             uint64_t prev = 0;
@@ -180,169 +191,252 @@ __global__ void __launch_bounds__(Cta<kMatch>::kThreads) k_hash_fused(HashParams
             for (int k = 0; k < n_win; k++) {
                 const int s = k % kStages;
                 bar_sync(kBarFull + s, kProducers);
-#pragma unroll
-                for (int j = 0; j < kWin; j++) {
-                    if (k * kWin + j < nfull) {
-                        prev = xxh_chain_step32(s_m[s][lane][j], lenp8, prev);
-                        s_m[s][lane][j] = prev;
-                    }
-                }
-                __syncwarp();
-                // write-out: 8 lanes cover one request's 8 hashes = one 64-byte segment
-#pragma unroll
-                for (int it = 0; it < kTileR / 4; it++) {
-                    int rr = it * 4 + (lane >> 3), jj = lane & 7;
-                    int b = k * kWin + jj;
-                    if (b < s_nfull[rr]) p.hashes[(r0 + rr) * (int64_t)p.max_blocks + b] = s_m[s][rr][jj];
-                }
-                __syncwarp();
-                if (kMatch) {
-                    __threadfence_block();
-                    bar_arrive(kBarHashed + s, 64);                 // the match warp releases the stage
-                } else {
-                    bar_arrive(kBarEmpty + s, kProducers);
-                }
+                prev = chain_window(s_m[s], s_nfull, p, r0, k, lane, nfull, lenp8, prev);
+                bar_arrive(kBarEmpty + s, kProducers);
             }
-            // trailing partial block (hashing.go:90-96): generic tail, rare
-            uint64_t tail_hash = 0;
-            uint32_t has_tail = 0;
-            if (r < p.R) {
+            if (r < p.R) {                           // trailing partial block (hashing.go:90-96): generic tail, rare
                 int64_t eff = s_eff[lane];
-                if ((int64_t)nfull * bs < eff) {
-                    tail_hash = hash_block_generic(p.data + s_off[lane] + (uint64_t)nfull * (uint64_t)bs,
-                                                   eff - (int64_t)nfull * bs, prev);
-                    p.hashes[r * (int64_t)p.max_blocks + nfull] = tail_hash;
-                    has_tail = 1;
-                }
-            }
-            if (kMatch) {
-                ms.tail_hash[lane] = tail_hash;
-                ms.has_tail[lane] = has_tail;
-                __threadfence_block();
-                bar_arrive(kBarTail, 64);
-            }
-        } else if (kMatch) {
-            // ================= match warp: lane = request =================
-            const int64_t r = r0 + lane;
-            const int32_t nfull = s_nfull[lane];
-            const IndexSlot *slots = pk.index.slots;
-            const uint64_t mask = pk.index.mask;
-            lane::Walk w;
-            w.init();
-            uint32_t nruns = 0;
-            bool run_overflow = false;
-            auto push_run = [&]() {
-                if (w.rl == 0 || w.rc == 0) return;
-                if (nruns < (uint32_t)kMaxRuns) {
-                    ms.run[nruns][0][lane] = w.rl; ms.run[nruns][1][lane] = w.rc;
-                    ms.run[nruns][2][lane] = w.r0; ms.run[nruns][3][lane] = w.r1;
-                    ms.run[nruns][4][lane] = w.r2; ms.run[nruns][5][lane] = w.r3;
-                    ms.run[nruns][6][lane] = w.r4;
-                    nruns++;
-                } else {
-                    run_overflow = true;
-                }
-            };
-            // Walks one block: stop test + run-length encoding of the posting set (plugin.go:214-230).
-            auto step = [&](lane::Slot8 sl, uint64_t h) {
-                if (h == kEmptyKey) {                                    // the all-ones key lives in a side record
-                    sl.key = h; sl.cnt = pk.index.special.cnt;
-                    sl.w0 = pk.index.special.ids[0]; sl.w1 = pk.index.special.ids[1]; sl.w2 = pk.index.special.ids[2];
-                    sl.w3 = pk.index.special.ids[3]; sl.w4 = pk.index.special.ids[4];
-                } else if (slots) {
-                    uint64_t i = h & mask;
-                    while (sl.cnt != 0 && sl.key != h) {                 // linear probing past colliding keys (rare)
-                        i = (i + 1) & mask;
-                        sl = lane::ld_slot(slots + i);
-                    }
-                } else {
-                    sl.cnt = 0;
-                }
-                w.n_probes++;
-                if (sl.cnt == 0) { w.stopped = true; return; }            // nobody holds it: stop (plugin.go:221-223)
-                w.n_postings += sl.cnt;
-                if (sl.cnt == w.rc && sl.w0 == w.r0 && sl.w1 == w.r1 && sl.w2 == w.r2 && sl.w3 == w.r3 && sl.w4 == w.r4) {
-                    w.rl++;
-                } else {
-                    push_run();
-                    w.rl = 1; w.rc = sl.cnt; w.r0 = sl.w0; w.r1 = sl.w1; w.r2 = sl.w2; w.r3 = sl.w3; w.r4 = sl.w4;
-                }
-            };
-            for (int k = 0; k < n_win; k++) {
-                const int s = k % kStages;
-                bar_sync(kBarHashed + s, 64);
-                const bool any = __any_sync(0xffffffffu, !w.stopped && k * kWin < nfull);
-                if (any) {
-                    uint64_t hh[kWin];
-#pragma unroll
-                    for (int j = 0; j < kWin; j++) {
-                        hh[j] = s_m[s][lane][j];
-                        if (k * kWin + j < nfull && !w.stopped && slots) {
-                            const IndexSlot *home = slots + (hh[j] & mask);
-                            cp_async16(&ms.slot[j][0][lane], home);
-                            cp_async16(&ms.slot[j][1][lane], reinterpret_cast<const unsigned char *>(home) + 16);
-                        }
-                    }
-                    cp_async_commit();
-                    bar_arrive(kBarEmpty + s, kProducers);          // hashes are in registers: release the stage early
-                    cp_async_wait<0>();
-#pragma unroll
-                    for (int j = 0; j < kWin; j++)
-                        if (k * kWin + j < nfull && !w.stopped) step(ring_read(ms, j, lane), hh[j]);
-                } else {
-                    bar_arrive(kBarEmpty + s, kProducers);
-                }
-            }
-            bar_sync(kBarTail, 64);
-            if (ms.has_tail[lane] && !w.stopped) {
-                const uint64_t th = ms.tail_hash[lane];
-                lane::Slot8 sl;
-                sl.key = 0; sl.cnt = 0; sl.w0 = sl.w1 = sl.w2 = sl.w3 = sl.w4 = 0;
-                if (slots) sl = lane::ld_slot(slots + (th & mask));
-                step(sl, th);
-            }
-            push_run();
-            __syncwarp();
-            // ---- epilogue, all 32 lanes together: runs -> per-endpoint counts -> score -> pick (a4-a14)
-            if (r < p.R) {
-                const int32_t total = nfull + (int32_t)ms.has_tail[lane];
-                const uint32_t lo = pk.index.ep_begin, hi = min(pk.index.ep_end, (uint32_t)pk.E);
-                lane::Matched m;
-                m.n = 0;
-                m.overflow = run_overflow;
-                for (uint32_t i = 0; i < nruns && !m.overflow; i++)
-                    lane::flush_run(m, pk.index, ms.run[i][0][lane], ms.run[i][1][lane], ms.run[i][2][lane],
-                                    ms.run[i][3][lane], ms.run[i][4][lane], ms.run[i][5][lane], ms.run[i][6][lane], lo, hi);
-                lane::decide(pk, r, m, total);
-            }
-            if (pk.work_counters) {
-                unsigned long long pr = w.n_probes, po = w.n_postings;
-                for (int o = 16; o; o >>= 1) {
-                    pr += __shfl_xor_sync(0xffffffffu, pr, o);
-                    po += __shfl_xor_sync(0xffffffffu, po, o);
-                }
-                if (lane == 0) {
-                    atomicAdd(&pk.work_counters[0], pr);
-                    atomicAdd(&pk.work_counters[1], po);
-                }
+                if ((int64_t)nfull * bs < eff)
+                    p.hashes[r * (int64_t)p.max_blocks + nfull] = hash_block_generic(
+                        p.data + s_off[lane] + (uint64_t)nfull * (uint64_t)bs, eff - (int64_t)nfull * bs, prev);
             }
         }
         __syncthreads();
     }
 }
 
-template <bool kAlign32, bool kMatch>
-static cudaError_t launch_fused_t(const HashParams &p, const PickParams &pk, int sm_count, cudaStream_t s) {
-    constexpr int kThreads = Cta<kMatch>::kThreads;
-    int n_tiles = (int)((p.R + kTileR - 1) / kTileR);
-    static int occ = 0;
-    if (!occ) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_hash_fused<kAlign32, kMatch>, kThreads, 0);
-        if (occ < 1) occ = 1;
+// =====================================================================================================
+// k_cycle_fused: a1-a14 in one kernel.  Same hashing pipeline; the index probes of window k-2 are spread over the
+// 8 digest warps (thread (r, j) probes block j of that window for request r while it hashes window k), so the
+// lookup costs no serial warp time.  Per-request walk state lives in shared memory and is touched only by the
+// request's own 8 lanes; run records are closed and scored by the chain warp once per tile.
+// =====================================================================================================
+struct CycleSmem {
+    uint4 slot[2][kDigestThreads];            // each digest thread's in-flight table slot (cp.async target)
+    int32_t stopped[kTileR];                  // walk reached a block nobody holds
+    int32_t stop_b[kTileR];                   // ... at this block index
+    int32_t nrec[kTileR];
+    int32_t overflow[kTileR];
+    uint32_t carry[6][kTileR];                // posting-set signature (cnt, w0..w4) of the last valid block
+    uint32_t rec[kMaxRuns][7][kTileR];        // run records: (start block, cnt, w0..w4)
+};
+
+template <bool kAlign32>
+__global__ void __launch_bounds__(kDigestThreads + 32) k_cycle_fused(HashParams p, PickParams pk, int n_tiles) {
+    constexpr int kAll = kDigestThreads + 32;
+    __shared__ uint64_t s_m[kStages][kTileR][kPitch];
+    __shared__ uint64_t s_off[kTileR];
+    __shared__ int64_t s_eff[kTileR];
+    __shared__ int32_t s_nfull[kTileR];
+    __shared__ int32_t s_maxfull;
+    __shared__ __align__(16) CycleSmem cs;
+
+    const int t = threadIdx.x;
+    const int warp = t >> 5, lane = t & 31;
+    const int64_t bs = p.block_bytes;
+    const int n_stripes = (int)(bs >> 5);
+    const uint64_t lenp8 = (uint64_t)bs + 8;
+    const IndexSlot *slots = pk.index.slots;
+    const uint64_t mask = pk.index.mask;
+    unsigned long long n_probes = 0, n_postings = 0;      // per-thread work counters
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t r0 = (int64_t)tile * kTileR;
+        if (t < kTileR) {
+            tile_lengths(p, r0, t, s_off, s_eff, s_nfull, &s_maxfull);
+            cs.stopped[t] = 0; cs.stop_b[t] = 0; cs.nrec[t] = 0; cs.overflow[t] = 0;
+#pragma unroll
+            for (int q = 0; q < 6; q++) cs.carry[q][t] = 0;
+        }
+        __syncthreads();
+        const int n_win = (s_maxfull + kWin - 1) / kWin;
+
+        if (warp < kDigestWarps) {
+            // ================= digest warps: hash window k, match window k-2 =================
+            const int r = t / kWin, j = t % kWin;
+            const int g8 = (lane >> 3) * 8;                       // first lane of this request's 8-lane group
+            const int32_t nfull = s_nfull[r];
+            const uint8_t *base = p.data + s_off[r] + (uint64_t)j * (uint64_t)bs;
+            for (int k = 0; k < n_win + kLag; k++) {
+                // ---- issue the probe of window kk = k-kLag (its hashes are final once the chain warp arrived)
+                const int kk = k - kLag;
+                bool active = false, any_active = false;
+                uint64_t h = 0;
+                if (kk >= 0) {
+                    const int s2 = kk % kStages;
+                    bar_sync(kBarHashed + s2, kAll);
+                    active = (kk * kWin + j < nfull) && !cs.stopped[r];
+                    any_active = __any_sync(0xffffffffu, active);   // most late windows: all 4 requests already stopped
+                    if (active) {
+                        h = s_m[s2][r][j];
+                        if (slots) {
+                            const unsigned char *home = reinterpret_cast<const unsigned char *>(slots + (h & mask));
+                            cp_async16(&cs.slot[0][t], home);
+                            cp_async16(&cs.slot[1][t], home + 16);
+                        }
+                    }
+                    if (any_active) cp_async_commit();
+                }
+                // ---- hash window k (the stage was released when every digest thread passed hashed[k-4] two
+                //      iterations ago; its cells are private to this thread until bar_arrive(full))
+                if (k < n_win) {
+                    const int s = k % kStages;
+                    if (k * kWin + j < nfull)
+                        s_m[s][r][j] = block_digest<kAlign32>(base + (uint64_t)k * (uint64_t)(kWin * bs), n_stripes);
+                    __threadfence_block();
+                    bar_arrive(kBarFull + s, kAll);
+                }
+                // ---- consume the probe: stop test + run-length encoding within the 8-lane group
+                if (any_active) {
+                    cp_async_wait<0>();
+                    lane::Slot8 sl;
+                    sl.key = 0; sl.cnt = 0; sl.w0 = sl.w1 = sl.w2 = sl.w3 = sl.w4 = 0;
+                    if (active) {
+                        if (h == kEmptyKey) {                      // the all-ones key lives in a side record
+                            sl.key = h; sl.cnt = pk.index.special.cnt;
+                            sl.w0 = pk.index.special.ids[0]; sl.w1 = pk.index.special.ids[1]; sl.w2 = pk.index.special.ids[2];
+                            sl.w3 = pk.index.special.ids[3]; sl.w4 = pk.index.special.ids[4];
+                        } else if (slots) {
+                            uint4 a = cs.slot[0][t], b4 = cs.slot[1][t];
+                            sl.key = ((uint64_t)a.y << 32) | a.x;
+                            sl.cnt = a.z; sl.w0 = a.w; sl.w1 = b4.x; sl.w2 = b4.y; sl.w3 = b4.z; sl.w4 = b4.w;
+                            uint64_t i = h & mask;
+                            while (sl.cnt != 0 && sl.key != h) {   // linear probing past colliding keys (rare)
+                                i = (i + 1) & mask;
+                                sl = lane::ld_slot(slots + i);
+                            }
+                        }
+                    }
+                    const bool present = active && sl.cnt != 0;
+                    const uint32_t amask = (__ballot_sync(0xffffffffu, active) >> g8) & 0xFFu;
+                    const uint32_t pmask = (__ballot_sync(0xffffffffu, present) >> g8) & 0xFFu;
+                    const uint32_t miss = amask & ~pmask;           // active blocks nobody holds
+                    const int limit = miss ? __ffs(miss) - 1 : 8;  // blocks j < limit are walked (plugin.go:214-230)
+                    const bool valid = active && j < limit;
+                    if (active && j <= limit) n_probes++;
+                    // signature of this block's posting set; unused words are zero by construction of the table
+                    const uint32_t c = valid ? sl.cnt : 0, w0 = valid ? sl.w0 : 0, w1 = valid ? sl.w1 : 0,
+                                   w2 = valid ? sl.w2 : 0, w3 = valid ? sl.w3 : 0, w4 = valid ? sl.w4 : 0;
+                    n_postings += c;
+                    uint32_t pc = __shfl_up_sync(0xffffffffu, c, 1), p0 = __shfl_up_sync(0xffffffffu, w0, 1),
+                             p1 = __shfl_up_sync(0xffffffffu, w1, 1), p2 = __shfl_up_sync(0xffffffffu, w2, 1),
+                             p3 = __shfl_up_sync(0xffffffffu, w3, 1), p4 = __shfl_up_sync(0xffffffffu, w4, 1);
+                    if (j == 0) {                                  // previous block = last valid block of the previous window
+                        pc = cs.carry[0][r]; p0 = cs.carry[1][r]; p1 = cs.carry[2][r];
+                        p2 = cs.carry[3][r]; p3 = cs.carry[4][r]; p4 = cs.carry[5][r];
+                    }
+                    const bool boundary = valid && (c != pc || w0 != p0 || w1 != p1 || w2 != p2 || w3 != p3 || w4 != p4);
+                    const uint32_t ball = __ballot_sync(0xffffffffu, boundary);
+                    const uint32_t bmask = (ball >> g8) & 0xFFu;
+                    if (boundary) {
+                        const int idx = cs.nrec[r] + __popc(bmask & ((1u << j) - 1u));
+                        if (idx < kMaxRuns) {
+                            cs.rec[idx][0][r] = (uint32_t)(kk * kWin + j);
+                            cs.rec[idx][1][r] = c;  cs.rec[idx][2][r] = w0; cs.rec[idx][3][r] = w1;
+                            cs.rec[idx][4][r] = w2; cs.rec[idx][5][r] = w3; cs.rec[idx][6][r] = w4;
+                        } else {
+                            cs.overflow[r] = 1;
+                        }
+                    }
+                    if (valid && j == limit - 1) {                 // last walked block of the window: carry its signature
+                        cs.carry[0][r] = c;  cs.carry[1][r] = w0; cs.carry[2][r] = w1;
+                        cs.carry[3][r] = w2; cs.carry[4][r] = w3; cs.carry[5][r] = w4;
+                    }
+                    __syncwarp();
+                    if (j == 0 && amask) {
+                        cs.nrec[r] += __popc(bmask);
+                        if (miss) { cs.stopped[r] = 1; cs.stop_b[r] = kk * kWin + limit; }
+                    }
+                    __syncwarp();
+                }
+            }
+            __threadfence_block();
+            bar_arrive(kBarTail, kAll);                            // every window of this tile has been walked
+        } else {
+            // ================= chain warp: lane = request =================
+            const int64_t r = r0 + lane;
+            const int32_t nfull = s_nfull[lane];
+            uint64_t prev = 0;
+            if (r < p.R) prev = p.seeds[p.model_ids ? p.model_ids[r] : 0];
+            for (int k = 0; k < n_win; k++) {
+                const int s = k % kStages;
+                bar_sync(kBarFull + s, kAll);
+                prev = chain_window(s_m[s], s_nfull, p, r0, k, lane, nfull, lenp8, prev);
+                __threadfence_block();
+                bar_arrive(kBarHashed + s, kAll);
+            }
+            // trailing partial block (hashing.go:90-96): generic tail, rare
+            uint64_t tail_hash = 0;
+            bool has_tail = false;
+            if (r < p.R) {
+                int64_t eff = s_eff[lane];
+                if ((int64_t)nfull * bs < eff) {
+                    tail_hash = hash_block_generic(p.data + s_off[lane] + (uint64_t)nfull * (uint64_t)bs,
+                                                   eff - (int64_t)nfull * bs, prev);
+                    p.hashes[r * (int64_t)p.max_blocks + nfull] = tail_hash;
+                    has_tail = true;
+                }
+            }
+            bar_sync(kBarTail, kAll);
+            // ---- epilogue, all 32 lanes together: close the runs, count, score, pick (a3-a14)
+            if (r < p.R) {
+                const uint32_t lo = pk.index.ep_begin, hi = min(pk.index.ep_end, (uint32_t)pk.E);
+                lane::Matched m;
+                m.n = 0;
+                m.overflow = cs.overflow[lane] != 0;
+                int32_t nrec = min(cs.nrec[lane], kMaxRuns);
+                int32_t end = cs.stopped[lane] ? cs.stop_b[lane] : nfull;     // blocks [0, end) were walked
+                int32_t total = nfull;
+                // the partial tail block continues the walk when nothing stopped it
+                uint32_t tc = 0, t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+                bool tail_valid = false;
+                if (has_tail) {
+                    total = nfull + 1;
+                    if (!cs.stopped[lane]) {
+                        n_probes++;
+                        Hit th;
+                        if (probe(pk.index, tail_hash, th)) {
+                            tail_valid = true;
+                            tc = th.cnt; t0 = th.w[0];
+                            if (tc <= (uint32_t)kInlineIds) { t1 = th.w[1]; t2 = th.w[2]; t3 = th.w[3]; t4 = th.w[4]; }
+                            n_postings += tc;
+                        }
+                    }
+                }
+                for (int32_t i = 0; i < nrec && !m.overflow; i++) {
+                    int32_t start = (int32_t)cs.rec[i][0][lane];
+                    int32_t next = i + 1 < nrec ? (int32_t)cs.rec[i + 1][0][lane] : end;
+                    lane::flush_run(m, pk.index, (uint32_t)(next - start), cs.rec[i][1][lane], cs.rec[i][2][lane],
+                                    cs.rec[i][3][lane], cs.rec[i][4][lane], cs.rec[i][5][lane], cs.rec[i][6][lane], lo, hi);
+                }
+                if (tail_valid && !m.overflow) lane::flush_run(m, pk.index, 1, tc, t0, t1, t2, t3, t4, lo, hi);
+                lane::decide(pk, r, m, total);
+            }
+        }
+        __syncthreads();
+    }
+    if (pk.work_counters) {
+        for (int o = 16; o; o >>= 1) {
+            n_probes += __shfl_xor_sync(0xffffffffu, n_probes, o);
+            n_postings += __shfl_xor_sync(0xffffffffu, n_postings, o);
+        }
+        if (lane == 0 && (n_probes | n_postings)) {
+            atomicAdd(&pk.work_counters[0], n_probes);
+            atomicAdd(&pk.work_counters[1], n_postings);
+        }
+    }
+}
+
+template <typename K, typename... Args>
+static cudaError_t launch_persistent(K kernel, int64_t R, int sm_count, cudaStream_t s, int *occ_cache, Args... args) {
+    int n_tiles = (int)((R + kTileR - 1) / kTileR);
+    if (!*occ_cache) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_cache, kernel, kDigestThreads + 32, 0);
+        if (*occ_cache < 1) *occ_cache = 1;
     }
     if (sm_count <= 0) sm_count = 148;
-    int grid = n_tiles < sm_count * occ ? n_tiles : sm_count * occ;
-    k_hash_fused<kAlign32, kMatch><<<grid, kThreads, 0, s>>>(p, pk, n_tiles);
+    int grid = n_tiles < sm_count * *occ_cache ? n_tiles : sm_count * *occ_cache;
+    kernel<<<grid, kDigestThreads + 32, 0, s>>>(args..., n_tiles);
     return cudaGetLastError();
 }
 
@@ -351,12 +445,14 @@ static cudaError_t launch_fused_t(const HashParams &p, const PickParams &pk, int
 cudaError_t launch_hash_fused(const HashParams &p, const PickParams *pick, int align, int sm_count, cudaStream_t s,
                               int *launches) {
     if (p.R <= 0) return cudaSuccess;
+    static int occ[4] = {0, 0, 0, 0};
     cudaError_t e;
     if (pick) {
-        e = align >= 32 ? launch_fused_t<true, true>(p, *pick, sm_count, s) : launch_fused_t<false, true>(p, *pick, sm_count, s);
+        e = align >= 32 ? launch_persistent(k_cycle_fused<true>, p.R, sm_count, s, &occ[0], p, *pick)
+                        : launch_persistent(k_cycle_fused<false>, p.R, sm_count, s, &occ[1], p, *pick);
     } else {
-        PickParams none{};
-        e = align >= 32 ? launch_fused_t<true, false>(p, none, sm_count, s) : launch_fused_t<false, false>(p, none, sm_count, s);
+        e = align >= 32 ? launch_persistent(k_hash_fused<true>, p.R, sm_count, s, &occ[2], p)
+                        : launch_persistent(k_hash_fused<false>, p.R, sm_count, s, &occ[3], p);
     }
     if (launches) *launches += 1;
     return e;

@@ -70,7 +70,8 @@ __device__ inline Best eval_profile_lanes(const ProfileDev &pf, int32_t E, const
     for (int32_t k0 = 0; k0 < ncand; k0 += 32) {
         int32_t k = k0 + lane;
         uint32_t e = k < ncand ? pf.order[k] : kNoKey;
-        bool un = k < ncand && !map_contains_any(m, e);
+        const bool matched = map_contains_any(m, e);   // shuffles inside: EVERY lane must call it (no short-circuit)
+        bool un = k < ncand && !matched;
         uint32_t bal = __ballot_sync(kFull, un);
         if (bal) {
             int first = __ffs(bal) - 1;

@@ -274,7 +274,8 @@ class Engine:
     def shard_set(self, ep_begin: int, ep_end: int):
         self._check(self._lib.epp_shard_set(self._h, ep_begin, ep_end))
 
-    def shard_probe(self, data, out_masks, offsets=None, uniform_len=None, model_ids=None, n_requests=None):
+    def shard_probe(self, data, out_masks, offsets=None, uniform_len=None, model_ids=None, n_requests=None,
+                    lengths=None):
         b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests, lengths)
         self._check(self._lib.epp_shard_probe(self._h, C.byref(b), _ptr(out_masks)))
         return R

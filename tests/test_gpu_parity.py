@@ -112,6 +112,54 @@ def test_hash_ragged_vs_oracle(epp, orc, bst):
         assert mid == 0
 
 
+def test_hash_ragged_aligned_starts_with_lengths(epp, orc):
+    """Ragged prompts whose STARTS sit on 32-byte boundaries (epp_batch.lengths): the fused 256-bit-load kernel with
+    per-request block counts, partial tail blocks, prompts shorter than a block and truncation, hashes AND decisions."""
+    rng = random.Random(77)
+    maxb = 20
+    lens = [0, 5, 63, 64, 65, 127, 128, 64 * maxb, 64 * maxb + 9, 64 * (maxb + 3)] + [rng.randint(0, 64 * (maxb + 4)) for _ in range(90)]
+    prompts = [bytes(rng.getrandbits(8) for _ in range(n)) for n in lens]
+    starts, pos = [], 0
+    for p in prompts:
+        starts.append(pos)
+        pos += (len(p) + 31) // 32 * 32
+    blob = np.zeros(pos + 64, np.uint8)
+    for st, p in zip(starts, prompts):
+        blob[st:st + len(p)] = np.frombuffer(p, np.uint8)
+    offs = np.array(starts + [pos], dtype=np.uint64)
+    lengths = np.array(lens, dtype=np.uint64)
+    E = 12
+    with epp.Engine(E, epp.ProfileSpec(0, [epp.ScorerSpec(2, 2.0), epp.ScorerSpec(1, 2.0), epp.ScorerSpec(0, 3.0)]),
+                    max_prefix_blocks=maxb) as eng:
+        eng.register_model(b"mdl")
+        hs, nb = eng.hash_prompts(blob, offsets=offs, lengths=lengths)
+        for i, p in enumerate(prompts):
+            want = orc.hash_prompt(p, b"mdl", 16, maxb)
+            assert nb[i] == len(want), (i, len(p))
+            assert [int(x) for x in hs[i, : nb[i]]] == want, (i, len(p))
+        # decisions on a small pool whose endpoints cache prefixes of some of these prompts
+        kv = np.linspace(0, 0.9, E)
+        waiting = np.arange(E, dtype=np.int32) % 3
+        eng.pool_set(np.arange(E), np.zeros(E, np.uint8), kv, waiting)
+        ix = orc.Indexer()
+        ph, pe = [], []
+        for e in range(E):
+            h = orc.hash_prompt(prompts[10 + e], b"mdl", 16, maxb)
+            ph += h[: max(1, len(h) // 2)]
+            pe += [e] * max(1, len(h) // 2)
+        ix.load_pairs(ph, pe)
+        eng.index_load_snapshot(ph, pe)
+        dec, det = eng.schedule(blob, offsets=offs, lengths=lengths)
+        pool = orc.PoolState(np.zeros(E, np.uint8), kv, waiting)
+        prof = orc.make_profile(0, [(2, 2.0, 0), (1, 2.0, 0), (0, 3.0, 0)])
+        for i, p in enumerate(prompts):
+            h = orc.hash_prompt(p, b"mdl", 16, maxb)
+            m, _ = ix.match_longest_prefix(h, E)
+            d = orc.schedule(prof, None, pool, m, len(h), 16, len(p), 0)
+            assert (dec["status"][i], dec["pick"][i], dec["tie_count"][i], dec["total_blocks"][i]) == (d.status, d.pick, d.tie_count, len(h)), i
+            assert dec["score"][i] == d.score and dec["match_blocks"][i] == m[d.pick]
+
+
 def test_hash_uniform_tokens_vs_oracle(epp, orc):
     """uint32 token arrays (4 bytes/token), T = 4096 -> 256 blocks of 64 bytes (BASELINE config 3 shape), host and
     device-pointer batches."""

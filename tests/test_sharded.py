@@ -59,10 +59,6 @@ def _oracle_rank_pick(orc, sh, w, pool, ix, primary, hashes, gmasks, lo, hi):
     """Phase 2 restated: global stop from the OR-ed masks, local counts, best among this shard's endpoints."""
     R = len(hashes)
     best = np.zeros(R, dtype=sh.SHARD_BEST_DTYPE)
-    role = pool.role.copy()
-    role[:lo] = orc.ROLE_ABSENT                      # candidates = this shard only ...
-    role[hi:] = orc.ROLE_ABSENT
-    shard_pool = orc.PoolState(role, pool.kv_usage, pool.waiting, pool.running)
     for r in range(R):
         h = hashes[r]
         stop = len(h)
@@ -83,8 +79,6 @@ def _oracle_rank_pick(orc, sh, w, pool, ix, primary, hashes, gmasks, lo, hi):
             best[r] = (mx, idx[0], len(idx), counts[idx[0]], 0)
         else:
             best[r] = (0.0, sh.NO_ENDPOINT, 0, 0, -1)
-        del shard_pool
-        shard_pool = None
     return best
 
 
