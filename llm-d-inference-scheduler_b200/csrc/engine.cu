@@ -124,6 +124,9 @@ struct epp_engine {
     DevBuf pick_scratch;            // global match counters when E is too large for shared memory
     int force_v1 = 0;               // EPP_HASH_V1=1: unfused v1 hash kernels (A/B)
     int force_match_v1 = 0;         // EPP_MATCH_V1=1: dense-counter match kernel only (A/B)
+    int prefetch = 0;               // EPP_PREFETCH=1
+    int wide = 0;                   // EPP_WIDE=1: 32-block windows in the hash kernel (A/B; measured slower)
+    int tile_r = 32;                // EPP_TILE=16: 16-request tiles in the fused kernels (A/B; measured slower)
     int no_fuse = 1;                // EPP_FUSE_MATCH=1 runs a2-a14 inside the hash kernel (experimental, slower today)
     int pick_grid = 0;
     bool pick_global = false;
@@ -246,6 +249,9 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
     e->mirror.reset(new IndexMirror(cfg->lru_capacity_per_server));
     { const char *v1 = getenv("EPP_HASH_V1"); e->force_v1 = (v1 && v1[0] == '1') ? 1 : 0; }
     { const char *v1 = getenv("EPP_MATCH_V1"); e->force_match_v1 = (v1 && v1[0] == '1') ? 1 : 0; }
+    { const char *v1 = getenv("EPP_WIDE"); e->wide = (v1 && v1[0] == '1') ? 1 : 0; }
+    { const char *v1 = getenv("EPP_PREFETCH"); e->prefetch = (v1 && v1[0] == '1') ? 1 : 0; }
+    { const char *v1 = getenv("EPP_TILE"); e->tile_r = (v1 && atoi(v1) == 16) ? 16 : 32; }
     { const char *v1 = getenv("EPP_FUSE_MATCH"); e->no_fuse = (v1 && v1[0] == '1') ? 0 : 1; }
     for (int i = 0; i < 2; i++) CUDA_TRY(e->slot[i].overflow_n.reserve(sizeof(int32_t) * 4, &e->dev_bytes));
 
@@ -623,6 +629,9 @@ static HashParams hash_params(epp_engine *h, const Work &w) {
     p.offsets_or_bits = w.offsets_or_bits;
     p.sm_count = h->sm_count;
     p.force_v1 = h->force_v1;
+    p.tile_r = h->tile_r;
+    p.prefetch = h->prefetch;
+    p.wide = h->wide;
     p.fused_pick = nullptr;
     return p;
 }

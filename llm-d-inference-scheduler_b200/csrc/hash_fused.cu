@@ -27,10 +27,8 @@
 namespace epp {
 
 namespace {
-constexpr int kTileR = 32;
+constexpr int kMaxTileR = 32;             // tile = TR requests (16 or 32): chain-warp lanes = requests
 constexpr int kWin = 8;
-constexpr int kDigestWarps = 8;
-constexpr int kDigestThreads = kDigestWarps * 32;
 constexpr int kStages = 4;
 constexpr int kPitch = kWin + 1;          // u64 cells per request row (odd pitch: conflict-free lane = request reads)
 constexpr int kBarFull = 1;               // named barrier ids 1..4
@@ -63,15 +61,15 @@ __device__ __forceinline__ void load_stripe(const uint8_t *p, uint64_t x[4]) {
     }
 }
 
-// Per-request lengths (hashing.go:58-66) for one tile; called by threads t < kTileR (one warp).
-__device__ __forceinline__ void tile_lengths(const HashParams &p, int64_t r0, int t, uint64_t *s_off, int64_t *s_eff,
-                                             int32_t *s_nfull, int32_t *s_maxfull) {
+// Per-request lengths (hashing.go:58-66) for one tile; called by the first warp (threads t < 32; t >= TR idle).
+__device__ __forceinline__ void tile_lengths(const HashParams &p, int64_t r0, int t, int tr, uint64_t *s_off,
+                                             int64_t *s_eff, int32_t *s_nfull, int32_t *s_maxfull) {
     const int64_t bs = p.block_bytes;
     int64_t r = r0 + t;
     uint64_t off = 0;
     int64_t eff = 0;
     int32_t nfull = 0;
-    if (r < p.R) {
+    if (t < tr && r < p.R) {
         uint64_t len;
         if (p.offsets) { off = p.offsets[r]; len = p.lengths ? p.lengths[r] : p.offsets[r + 1] - off; }
         else { off = (uint64_t)r * p.uniform_len; len = p.uniform_len; }
@@ -89,9 +87,11 @@ __device__ __forceinline__ void tile_lengths(const HashParams &p, int64_t r0, in
         p.nblocks[r] = nb;
         p.eff_len[r] = eff;
     }
-    s_off[t] = off;
-    s_eff[t] = eff;
-    s_nfull[t] = nfull;
+    if (t < tr) {
+        s_off[t] = off;
+        s_eff[t] = eff;
+        s_nfull[t] = nfull;
+    }
     int mx = nfull;
     for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if (t == 0) *s_maxfull = mx;
@@ -121,21 +121,35 @@ __device__ __forceinline__ uint64_t block_digest(const uint8_t *src, int n_strip
     return xxh_merge_all(v);
 }
 
+// Same, for the default 64-byte block with the two stripes already in registers (software prefetch).
+__device__ __forceinline__ uint64_t block_digest64(const uint64_t x0[4], const uint64_t x1[4]) {
+    uint64_t v[4];
+    xxh_init(v);
+#pragma unroll
+    for (int q = 0; q < 4; q++) v[q] = xxh_round(v[q], x0[q]);
+#pragma unroll
+    for (int q = 0; q < 4; q++) v[q] = xxh_round(v[q], x1[q]);
+    return xxh_merge_all(v);
+}
+
 // Chain warp, one window: the serial part of the digest for 32 requests at once, in place, then the 8 hashes of
 // each request written as one 64-byte segment.
+template <int TR>
 __device__ __forceinline__ uint64_t chain_window(uint64_t (*sm)[kPitch], const int32_t *s_nfull, const HashParams &p,
                                                  int64_t r0, int k, int lane, int32_t nfull, uint64_t lenp8,
                                                  uint64_t prev) {
+    if (lane < TR) {
 #pragma unroll
-    for (int j = 0; j < kWin; j++) {
-        if (k * kWin + j < nfull) {
-            prev = xxh_chain_step32(sm[lane][j], lenp8, prev);
-            sm[lane][j] = prev;
+        for (int j = 0; j < kWin; j++) {
+            if (k * kWin + j < nfull) {
+                prev = xxh_chain_step32(sm[lane][j], lenp8, prev);
+                sm[lane][j] = prev;
+            }
         }
     }
     __syncwarp();
 #pragma unroll
-    for (int it = 0; it < kTileR / 4; it++) {
+    for (int it = 0; it < TR / 4; it++) {
         int rr = it * 4 + (lane >> 3), jj = lane & 7;
         int b = k * kWin + jj;
         if (b < s_nfull[rr]) p.hashes[(r0 + rr) * (int64_t)p.max_blocks + b] = sm[rr][jj];
@@ -148,8 +162,10 @@ __device__ __forceinline__ uint64_t chain_window(uint64_t (*sm)[kPitch], const i
 // =====================================================================================================
 // k_hash_fused: a1 only (epp_hash_prompts, Produce-parity and sharded modes, A/B runs)
 // =====================================================================================================
-template <bool kAlign32>
-__global__ void __launch_bounds__(kDigestThreads + 32) k_hash_fused(HashParams p, int n_tiles) {
+template <bool kAlign32, int TR>
+__global__ void __launch_bounds__(TR * kWin + 32) k_hash_fused(HashParams p, int n_tiles) {
+    constexpr int kTileR = TR;
+    constexpr int kDigestThreads = TR * kWin, kDigestWarps = kDigestThreads / 32;
     constexpr int kProducers = kDigestThreads + 32;
     __shared__ uint64_t s_m[kStages][kTileR][kPitch];
     __shared__ uint64_t s_off[kTileR];
@@ -165,7 +181,7 @@ __global__ void __launch_bounds__(kDigestThreads + 32) k_hash_fused(HashParams p
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t r0 = (int64_t)tile * kTileR;
-        if (t < kTileR) tile_lengths(p, r0, t, s_off, s_eff, s_nfull, &s_maxfull);
+        if (t < 32) tile_lengths(p, r0, t, TR, s_off, s_eff, s_nfull, &s_maxfull);
         __syncthreads();
         const int n_win = (s_maxfull + kWin - 1) / kWin;
 
@@ -173,17 +189,112 @@ __global__ void __launch_bounds__(kDigestThreads + 32) k_hash_fused(HashParams p
             const int r = t / kWin, j = t % kWin;
             const int32_t nfull = s_nfull[r];
             const uint8_t *base = p.data + s_off[r] + (uint64_t)j * (uint64_t)bs;
+            if (n_stripes == 2 && p.prefetch) {
+                // default 64-byte blocks: the loads of window k+1 are issued before window k is hashed, so every
+                // digest thread always has 64 bytes in flight
+                uint64_t xa[4] = {0, 0, 0, 0}, xb[4] = {0, 0, 0, 0};
+                if (j < nfull) { load_stripe<kAlign32>(base, xa); load_stripe<kAlign32>(base + 32, xb); }
+                for (int k = 0; k < n_win; k++) {
+                    const int s = k % kStages;
+                    uint64_t x0[4], x1[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) { x0[q] = xa[q]; x1[q] = xb[q]; }
+                    if ((k + 1) * kWin + j < nfull) {
+                        const uint8_t *nx = base + (uint64_t)(k + 1) * (uint64_t)(kWin * bs);
+                        load_stripe<kAlign32>(nx, xa);
+                        load_stripe<kAlign32>(nx + 32, xb);
+                    }
+                    if (k >= kStages) bar_sync(kBarEmpty + s, kProducers);
+                    if (k * kWin + j < nfull) s_m[s][r][j] = block_digest64(x0, x1);
+                    __threadfence_block();
+                    bar_arrive(kBarFull + s, kProducers);
+                }
+            } else {
+                for (int k = 0; k < n_win; k++) {
+                    const int s = k % kStages;
+                    if (k >= kStages) bar_sync(kBarEmpty + s, kProducers);
+                    if (k * kWin + j < nfull)
+                        s_m[s][r][j] = block_digest<kAlign32>(base + (uint64_t)k * (uint64_t)(kWin * bs), n_stripes);
+                    __threadfence_block();
+                    bar_arrive(kBarFull + s, kProducers);
+                }
+            }
+            int first = n_win > kStages ? n_win - kStages : 0;
+            for (int k = first; k < n_win; k++) bar_sync(kBarEmpty + (k % kStages), kProducers);
+        } else {
+            const bool mine = lane < TR;
+            const int64_t r = r0 + lane;
+            const int32_t nfull = mine ? s_nfull[lane] : 0;
+            uint64_t prev = 0;
+            if (mine && r < p.R) prev = p.seeds[p.model_ids ? p.model_ids[r] : 0];
+            for (int k = 0; k < n_win; k++) {
+                const int s = k % kStages;
+                bar_sync(kBarFull + s, kProducers);
+                prev = chain_window<TR>(s_m[s], s_nfull, p, r0, k, lane, nfull, lenp8, prev);
+                bar_arrive(kBarEmpty + s, kProducers);
+            }
+            if (mine && r < p.R) {                   // trailing partial block (hashing.go:90-96): generic tail, rare
+                int64_t eff = s_eff[lane];
+                if ((int64_t)nfull * bs < eff)
+                    p.hashes[r * (int64_t)p.max_blocks + nfull] = hash_block_generic(
+                        p.data + s_off[lane] + (uint64_t)nfull * (uint64_t)bs, eff - (int64_t)nfull * bs, prev);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// =====================================================================================================
+// k_hash_wide: a1 with 32-block windows.  Same pipeline as k_hash_fused, but a digest warp reads 32 consecutive
+// blocks (2 KiB contiguous) of ONE request per load instruction instead of 8 blocks of four requests -- DRAM sees
+// 2-KiB bursts, which is what the streaming v1 kernel had (5.85 TB/s there vs 4.85 TB/s with 512-byte bursts).
+// Each digest warp owns four requests of the tile and hashes their windows one after the other.
+// =====================================================================================================
+template <bool kAlign32>
+__global__ void __launch_bounds__(288) k_hash_wide(HashParams p, int n_tiles) {
+    constexpr int TR = 32, W = 32, PW = W + 1, kDigestWarps = 8, kProducers = kDigestWarps * 32 + 32;
+    __shared__ uint64_t s_m[kStages][TR][PW];
+    __shared__ uint64_t s_off[TR];
+    __shared__ int64_t s_eff[TR];
+    __shared__ int32_t s_nfull[TR];
+    __shared__ int32_t s_maxfull;
+
+    const int t = threadIdx.x;
+    const int warp = t >> 5, lane = t & 31;
+    const int64_t bs = p.block_bytes;
+    const int n_stripes = (int)(bs >> 5);
+    const uint64_t lenp8 = (uint64_t)bs + 8;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t r0 = (int64_t)tile * TR;
+        if (t < 32) tile_lengths(p, r0, t, TR, s_off, s_eff, s_nfull, &s_maxfull);
+        __syncthreads();
+        const int n_win = (s_maxfull + W - 1) / W;
+
+        if (warp < kDigestWarps) {
+            // ================= digest warps: warp w owns requests 4w .. 4w+3, lane = block in window =================
+            const uint8_t *base[4];
+            int32_t nf[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                base[q] = p.data + s_off[warp * 4 + q] + (uint64_t)lane * (uint64_t)bs;
+                nf[q] = s_nfull[warp * 4 + q];
+            }
             for (int k = 0; k < n_win; k++) {
                 const int s = k % kStages;
                 if (k >= kStages) bar_sync(kBarEmpty + s, kProducers);
-                if (k * kWin + j < nfull)
-                    s_m[s][r][j] = block_digest<kAlign32>(base + (uint64_t)k * (uint64_t)(kWin * bs), n_stripes);
+                const int b = k * W + lane;
+                const uint64_t woff = (uint64_t)k * (uint64_t)(W * bs);
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (b < nf[q]) s_m[s][warp * 4 + q][lane] = block_digest<kAlign32>(base[q] + woff, n_stripes);
                 __threadfence_block();
                 bar_arrive(kBarFull + s, kProducers);
             }
             int first = n_win > kStages ? n_win - kStages : 0;
             for (int k = first; k < n_win; k++) bar_sync(kBarEmpty + (k % kStages), kProducers);
         } else {
+            // ================= chain warp: lane = request =================
             const int64_t r = r0 + lane;
             const int32_t nfull = s_nfull[lane];
             uint64_t prev = 0;
@@ -191,7 +302,20 @@ __global__ void __launch_bounds__(kDigestThreads + 32) k_hash_fused(HashParams p
             for (int k = 0; k < n_win; k++) {
                 const int s = k % kStages;
                 bar_sync(kBarFull + s, kProducers);
-                prev = chain_window(s_m[s], s_nfull, p, r0, k, lane, nfull, lenp8, prev);
+#pragma unroll 8
+                for (int j = 0; j < W; j++) {
+                    if (k * W + j < nfull) {
+                        prev = xxh_chain_step32(s_m[s][lane][j], lenp8, prev);
+                        s_m[s][lane][j] = prev;
+                    }
+                }
+                __syncwarp();
+                // write-out: the 32 hashes of each request's window = one 256-byte segment
+                const int b = k * W + lane;
+#pragma unroll 4
+                for (int rr = 0; rr < TR; rr++)
+                    if (b < s_nfull[rr]) p.hashes[(r0 + rr) * (int64_t)p.max_blocks + b] = s_m[s][rr][lane];
+                __syncwarp();
                 bar_arrive(kBarEmpty + s, kProducers);
             }
             if (r < p.R) {                           // trailing partial block (hashing.go:90-96): generic tail, rare
@@ -211,25 +335,28 @@ __global__ void __launch_bounds__(kDigestThreads + 32) k_hash_fused(HashParams p
 // lookup costs no serial warp time.  Per-request walk state lives in shared memory and is touched only by the
 // request's own 8 lanes; run records are closed and scored by the chain warp once per tile.
 // =====================================================================================================
+template <int TR>
 struct CycleSmem {
-    uint4 slot[2][kDigestThreads];            // each digest thread's in-flight table slot (cp.async target)
-    int32_t stopped[kTileR];                  // walk reached a block nobody holds
-    int32_t stop_b[kTileR];                   // ... at this block index
-    int32_t nrec[kTileR];
-    int32_t overflow[kTileR];
-    uint32_t carry[6][kTileR];                // posting-set signature (cnt, w0..w4) of the last valid block
-    uint32_t rec[kMaxRuns][7][kTileR];        // run records: (start block, cnt, w0..w4)
+    uint4 slot[2][TR * kWin];                 // each digest thread's in-flight table slot (cp.async target)
+    int32_t stopped[TR];                      // walk reached a block nobody holds
+    int32_t stop_b[TR];                       // ... at this block index
+    int32_t nrec[TR];
+    int32_t overflow[TR];
+    uint32_t carry[6][TR];                    // posting-set signature (cnt, w0..w4) of the last valid block
+    uint32_t rec[kMaxRuns][7][TR];            // run records: (start block, cnt, w0..w4)
 };
 
-template <bool kAlign32>
-__global__ void __launch_bounds__(kDigestThreads + 32) k_cycle_fused(HashParams p, PickParams pk, int n_tiles) {
+template <bool kAlign32, int TR>
+__global__ void __launch_bounds__(TR * kWin + 32) k_cycle_fused(HashParams p, PickParams pk, int n_tiles) {
+    constexpr int kTileR = TR;
+    constexpr int kDigestThreads = TR * kWin, kDigestWarps = kDigestThreads / 32;
     constexpr int kAll = kDigestThreads + 32;
     __shared__ uint64_t s_m[kStages][kTileR][kPitch];
     __shared__ uint64_t s_off[kTileR];
     __shared__ int64_t s_eff[kTileR];
     __shared__ int32_t s_nfull[kTileR];
     __shared__ int32_t s_maxfull;
-    __shared__ __align__(16) CycleSmem cs;
+    __shared__ __align__(16) CycleSmem<TR> cs;
 
     const int t = threadIdx.x;
     const int warp = t >> 5, lane = t & 31;
@@ -242,11 +369,13 @@ __global__ void __launch_bounds__(kDigestThreads + 32) k_cycle_fused(HashParams 
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t r0 = (int64_t)tile * kTileR;
-        if (t < kTileR) {
-            tile_lengths(p, r0, t, s_off, s_eff, s_nfull, &s_maxfull);
-            cs.stopped[t] = 0; cs.stop_b[t] = 0; cs.nrec[t] = 0; cs.overflow[t] = 0;
+        if (t < 32) {
+            tile_lengths(p, r0, t, TR, s_off, s_eff, s_nfull, &s_maxfull);
+            if (t < TR) {
+                cs.stopped[t] = 0; cs.stop_b[t] = 0; cs.nrec[t] = 0; cs.overflow[t] = 0;
 #pragma unroll
-            for (int q = 0; q < 6; q++) cs.carry[q][t] = 0;
+                for (int q = 0; q < 6; q++) cs.carry[q][t] = 0;
+            }
         }
         __syncthreads();
         const int n_win = (s_maxfull + kWin - 1) / kWin;
@@ -354,21 +483,22 @@ __global__ void __launch_bounds__(kDigestThreads + 32) k_cycle_fused(HashParams 
             bar_arrive(kBarTail, kAll);                            // every window of this tile has been walked
         } else {
             // ================= chain warp: lane = request =================
+            const bool mine = lane < TR;
             const int64_t r = r0 + lane;
-            const int32_t nfull = s_nfull[lane];
+            const int32_t nfull = mine ? s_nfull[lane] : 0;
             uint64_t prev = 0;
-            if (r < p.R) prev = p.seeds[p.model_ids ? p.model_ids[r] : 0];
+            if (mine && r < p.R) prev = p.seeds[p.model_ids ? p.model_ids[r] : 0];
             for (int k = 0; k < n_win; k++) {
                 const int s = k % kStages;
                 bar_sync(kBarFull + s, kAll);
-                prev = chain_window(s_m[s], s_nfull, p, r0, k, lane, nfull, lenp8, prev);
+                prev = chain_window<TR>(s_m[s], s_nfull, p, r0, k, lane, nfull, lenp8, prev);
                 __threadfence_block();
                 bar_arrive(kBarHashed + s, kAll);
             }
             // trailing partial block (hashing.go:90-96): generic tail, rare
             uint64_t tail_hash = 0;
             bool has_tail = false;
-            if (r < p.R) {
+            if (mine && r < p.R) {
                 int64_t eff = s_eff[lane];
                 if ((int64_t)nfull * bs < eff) {
                     tail_hash = hash_block_generic(p.data + s_off[lane] + (uint64_t)nfull * (uint64_t)bs,
@@ -378,8 +508,8 @@ __global__ void __launch_bounds__(kDigestThreads + 32) k_cycle_fused(HashParams 
                 }
             }
             bar_sync(kBarTail, kAll);
-            // ---- epilogue, all 32 lanes together: close the runs, count, score, pick (a3-a14)
-            if (r < p.R) {
+            // ---- epilogue, all lanes together: close the runs, count, score, pick (a3-a14)
+            if (mine && r < p.R) {
                 const uint32_t lo = pk.index.ep_begin, hi = min(pk.index.ep_end, (uint32_t)pk.E);
                 lane::Matched m;
                 m.n = 0;
@@ -428,31 +558,49 @@ __global__ void __launch_bounds__(kDigestThreads + 32) k_cycle_fused(HashParams 
 }
 
 template <typename K, typename... Args>
-static cudaError_t launch_persistent(K kernel, int64_t R, int sm_count, cudaStream_t s, int *occ_cache, Args... args) {
-    int n_tiles = (int)((R + kTileR - 1) / kTileR);
+static cudaError_t launch_persistent(K kernel, int tile_r, int64_t R, int sm_count, cudaStream_t s, int *occ_cache,
+                                     Args... args) {
+    const int threads = tile_r * kWin + 32;
+    int n_tiles = (int)((R + tile_r - 1) / tile_r);
     if (!*occ_cache) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_cache, kernel, kDigestThreads + 32, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_cache, kernel, threads, 0);
         if (*occ_cache < 1) *occ_cache = 1;
     }
     if (sm_count <= 0) sm_count = 148;
     int grid = n_tiles < sm_count * *occ_cache ? n_tiles : sm_count * *occ_cache;
-    kernel<<<grid, kDigestThreads + 32, 0, s>>>(args..., n_tiles);
+    kernel<<<grid, threads, 0, s>>>(args..., n_tiles);
     return cudaGetLastError();
 }
 
 // pick == nullptr: hashing only.  Otherwise the whole cycle; decisions go to pick->out, overflowing requests to
-// pick->overflow_list (dense-counter kernel).
+// pick->overflow_list (dense-counter kernel).  tile_r: 32 (default) or 16 requests per CTA tile.  16-request tiles
+// give a finer-grained last wave (2 048 tiles of 32 over 592 CTA slots quantise to 4 rounds for 3.46 rounds of
+// work) but double the chain-warp overhead per digest thread; measured 0.323 ms vs 0.251 ms on config 3.
 cudaError_t launch_hash_fused(const HashParams &p, const PickParams *pick, int align, int sm_count, cudaStream_t s,
                               int *launches) {
     if (p.R <= 0) return cudaSuccess;
-    static int occ[4] = {0, 0, 0, 0};
+    static int occ[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int tile_r = p.tile_r == 16 ? 16 : 32;
+    const bool a32 = align >= 32;
     cudaError_t e;
     if (pick) {
-        e = align >= 32 ? launch_persistent(k_cycle_fused<true>, p.R, sm_count, s, &occ[0], p, *pick)
-                        : launch_persistent(k_cycle_fused<false>, p.R, sm_count, s, &occ[1], p, *pick);
+        if (tile_r == 32)
+            e = a32 ? launch_persistent(k_cycle_fused<true, 32>, 32, p.R, sm_count, s, &occ[0], p, *pick)
+                    : launch_persistent(k_cycle_fused<false, 32>, 32, p.R, sm_count, s, &occ[1], p, *pick);
+        else
+            e = a32 ? launch_persistent(k_cycle_fused<true, 16>, 16, p.R, sm_count, s, &occ[2], p, *pick)
+                    : launch_persistent(k_cycle_fused<false, 16>, 16, p.R, sm_count, s, &occ[3], p, *pick);
     } else {
-        e = align >= 32 ? launch_persistent(k_hash_fused<true>, p.R, sm_count, s, &occ[2], p)
-                        : launch_persistent(k_hash_fused<false>, p.R, sm_count, s, &occ[3], p);
+        static int occw[2] = {0, 0};
+        if (tile_r == 32 && p.wide)
+            e = a32 ? launch_persistent(k_hash_wide<true>, 32, p.R, sm_count, s, &occw[0], p)
+                    : launch_persistent(k_hash_wide<false>, 32, p.R, sm_count, s, &occw[1], p);
+        else if (tile_r == 32)
+            e = a32 ? launch_persistent(k_hash_fused<true, 32>, 32, p.R, sm_count, s, &occ[4], p)
+                    : launch_persistent(k_hash_fused<false, 32>, 32, p.R, sm_count, s, &occ[5], p);
+        else
+            e = a32 ? launch_persistent(k_hash_fused<true, 16>, 16, p.R, sm_count, s, &occ[6], p)
+                    : launch_persistent(k_hash_fused<false, 16>, 16, p.R, sm_count, s, &occ[7], p);
     }
     if (launches) *launches += 1;
     return e;

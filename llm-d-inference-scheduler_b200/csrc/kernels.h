@@ -27,6 +27,9 @@ struct HashParams {
     uint64_t offsets_or_bits;   // OR of every offsets[r] (low bits decide the common alignment)
     int32_t sm_count;
     int32_t force_v1;           // use the unfused v1 kernels (A/B testing)
+    int32_t tile_r;             // fused kernels: requests per CTA tile (32 default, 16)
+    int32_t prefetch;           // hash kernel: register software prefetch of the next window (A/B)
+    int32_t wide;               // hash kernel: 32-block windows (2-KiB DRAM bursts per warp load)
     const struct PickParams *fused_pick;  // non-null: run a2-a14 inside the fused kernel's chain warp (fast path only)
 };
 // Common alignment (0, 16, 32) of every block start; >= 16 (and block_bytes % 32 == 0) enables the fused kernel.

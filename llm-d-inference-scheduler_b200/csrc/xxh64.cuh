@@ -33,17 +33,33 @@ __device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) {
     return ((uint64_t)nhi << 32) | nlo;
 }
 
+// a + x * C (mod 2^64) for a compile-time constant C, in exactly three integer multiply-adds: one IMAD.WIDE.U32
+// carrying the 64-bit addend and two IMADs folded into the high word.  (The compiler's own expansion of the 64-bit
+// multiply spends a fourth instruction on a separate add; XXH64 is ~2 such multiplies per 8 input bytes and the
+// hash kernel is issue-bound, so the count matters.)
+template <uint64_t C>
+__device__ __forceinline__ uint64_t mad64c(uint64_t x, uint64_t a) {
+    constexpr uint32_t cl = (uint32_t)C, ch = (uint32_t)(C >> 32);
+    const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32);
+    uint64_t t;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(t) : "r"(xl), "n"(cl), "l"(a));
+    uint32_t tl = (uint32_t)t, th = (uint32_t)(t >> 32);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(th) : "r"(xl), "n"(ch));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(th) : "r"(xh), "n"(cl));
+    return ((uint64_t)th << 32) | tl;
+}
+
 __device__ __forceinline__ uint64_t xxh_round(uint64_t acc, uint64_t x) {
-    return rotl64(acc + x * XP2, 31) * XP1;
+    return mad64c<XP1>(rotl64(mad64c<XP2>(x, acc), 31), 0);
 }
 __device__ __forceinline__ uint64_t xxh_merge(uint64_t h, uint64_t v) {
-    return (h ^ xxh_round(0, v)) * XP1 + XP4;
+    return mad64c<XP1>(h ^ xxh_round(0, v), XP4);
 }
 __device__ __forceinline__ uint64_t xxh_avalanche(uint64_t h) {
     h ^= h >> 33;
-    h *= XP2;
+    h = mad64c<XP2>(h, 0);
     h ^= h >> 29;
-    h *= XP3;
+    h = mad64c<XP3>(h, 0);
     h ^= h >> 32;
     return h;
 }
@@ -66,7 +82,7 @@ __device__ __forceinline__ uint64_t xxh_merge_all(const uint64_t v[4]) {
 __device__ __forceinline__ uint64_t xxh_chain_step32(uint64_t m, uint64_t len_plus8, uint64_t prev) {
     uint64_t h = m + len_plus8;
     h ^= xxh_round(0, prev);
-    h = rotl64(h, 27) * XP1 + XP4;
+    h = mad64c<XP1>(rotl64(h, 27), XP4);
     return xxh_avalanche(h);
 }
 
