@@ -35,6 +35,10 @@ constexpr int kBarFull = 1;               // named barrier ids 1..4
 constexpr int kBarEmpty = 1 + kStages;    // 5..8
 constexpr int kBarHashed = 1 + 2 * kStages;   // 9..12
 constexpr int kBarTail = 1 + 3 * kStages;     // 13
+#ifndef EPP_HASH_MIN_CTAS
+#define EPP_HASH_MIN_CTAS 4
+#endif
+constexpr int kHashMinCtas = EPP_HASH_MIN_CTAS;
 constexpr int kLag = 3;                   // digest warps match window k-kLag while hashing window k (kLag < kStages)
 constexpr int kMaxRuns = 24;              // run records per request before the dense-counter fallback takes over
 
@@ -163,7 +167,7 @@ __device__ __forceinline__ uint64_t chain_window(uint64_t (*sm)[kPitch], const i
 // k_hash_fused: a1 only (epp_hash_prompts, Produce-parity and sharded modes, A/B runs)
 // =====================================================================================================
 template <bool kAlign32, int TR>
-__global__ void __launch_bounds__(TR * kWin + 32) k_hash_fused(HashParams p, int n_tiles) {
+__global__ void __launch_bounds__(TR * kWin + 32, kHashMinCtas) k_hash_fused(HashParams p, int n_tiles) {
     constexpr int kTileR = TR;
     constexpr int kDigestThreads = TR * kWin, kDigestWarps = kDigestThreads / 32;
     constexpr int kProducers = kDigestThreads + 32;
