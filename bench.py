@@ -27,6 +27,10 @@ import time
 
 import numpy as np
 
+# stdout carries exactly ONE JSON line: keep NCCL's version banner (printed on stdout at NCCL_DEBUG=VERSION/INFO) out
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -405,6 +409,20 @@ def run_gpu_sharded(args, rank, world, local_rank):
         t = torch.tensor([wall], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         wall = float(t.item())
+    parity = None
+    if rank == 0:
+        # the sharded decisions must equal what ONE engine holding the whole index decides
+        n_chk = min(R, 4096)
+        full = helpers.make_engine(w, device=local_rank)
+        full.register_model(tg.MODEL)
+        full.pool_set(np.arange(w.E, dtype=np.uint32), role, kv, waiting, running)
+        full.index_load_snapshot(hs, es)
+        ref_dec, _ = full.schedule(host[:n_chk], uniform_len=w.prompt_bytes, detail=False)
+        got = epp.decisions_from_torch(dec)[:n_chk]
+        parity = bool((got["status"] == ref_dec["status"]).all() and (got["pick"] == ref_dec["pick"]).all()
+                      and (got["score"].view(np.uint64) == ref_dec["score"].view(np.uint64)).all()
+                      and (got["tie_count"] == ref_dec["tie_count"]).all())
+        full.close()
     if rank == 0:
         W = (w.max_prefix_blocks + 31) // 32
         print(json.dumps({
@@ -416,6 +434,7 @@ def run_gpu_sharded(args, rank, world, local_rank):
                                f"batch; per batch: all-gather+OR of {R * W * 4} B of presence masks per rank, all-gather of "
                                f"{R * 24} B of best records per rank (NCCL)"}),
             "decisions_ok": int((epp.decisions_from_torch(dec)["status"] == 0).sum()),
+            "parity_vs_unsharded_engine": parity,
         }), flush=True)
     eng.close()
     if world > 1:

@@ -17,6 +17,10 @@
  * memory.  Every entry point is thread-safe (calls on one engine are serialised internally; goroutines
  * should batch requests before calling).  Handles are opaque.
  *
+ * Streams: the engine launches on its own CUDA streams.  With EPP_BATCH_DEVICE_PTRS (and in the epp_shard_* calls)
+ * every device buffer passed IN must be complete before the call (the engine does not wait on the caller's
+ * streams); every output is complete when the call returns.
+ *
  * Endpoint identity: the reference keys servers by NamespacedName strings.  The shim maps each endpoint
  * to a dense SLOT id in [0, max_endpoints); all arrays below are indexed by slot id.
  *

@@ -85,8 +85,12 @@ def schedule_sharded(engine, tokens_dev, uniform_len: int, dist=None):
     engine.shard_probe(tokens_dev, masks, uniform_len=uniform_len)
     gmasks = or_allgather(masks, dist)
     best = torch.empty((R, 24), dtype=torch.uint8, device=dev)
+    # The engine runs on its own streams and only guarantees that ITS outputs are complete on return; tensors produced
+    # by torch / NCCL on the caller's stream must be complete before they are handed over (epp_engine.h, "streams").
+    torch.cuda.current_stream(dev).synchronize()
     engine.shard_pick(R, gmasks, best)
     allb = allgather_records(best, dist)
     dec = torch.empty((R, 32), dtype=torch.uint8, device=dev)
+    torch.cuda.current_stream(dev).synchronize()
     engine.shard_merge(R, allb.shape[0], allb, dec)
     return dec

@@ -188,6 +188,7 @@ def _gpu_sharded_decisions(epp, w, trace, tokens, world, dist=None, rank=None, d
         gm = masks[0].clone()
         for g in ranks[1:]:
             gm |= masks[g]
+    torch.cuda.synchronize()           # torch-produced masks must be complete before the engine reads them
     bests = {}
     for g in ranks:
         b = torch.empty((tokens.shape[0], 24), dtype=torch.uint8, device=dt.device)
@@ -195,6 +196,7 @@ def _gpu_sharded_decisions(epp, w, trace, tokens, world, dist=None, rank=None, d
         bests[g] = b
     allb = sh.allgather_records(bests[rank], dist) if dist is not None else torch.stack([bests[g] for g in ranks])
     dec = torch.empty((tokens.shape[0], 32), dtype=torch.uint8, device=dt.device)
+    torch.cuda.synchronize()
     engines[ranks[0]].shard_merge(tokens.shape[0], allb.shape[0], allb, dec)
     torch.cuda.synchronize()
     out = epp.decisions_from_torch(dec)
