@@ -262,9 +262,19 @@ def run_gpu(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sched_kw = dict(uniform_len=w.prompt_bytes)
+    if args.pitch_pad:
+        pitch = w.prompt_bytes + args.pitch_pad
+        padded = torch.zeros((R, pitch), dtype=torch.uint8, device="cuda")
+        padded[:, : w.prompt_bytes] = dev_tokens.view(torch.uint8).view(R, w.prompt_bytes)
+        dev_tokens = padded
+        offs = (torch.arange(R + 1, dtype=torch.int64, device="cuda") * pitch)
+        lens = torch.full((R,), w.prompt_bytes, dtype=torch.int64, device="cuda")
+        sched_kw = dict(offsets=offs, lengths=lens)
+        torch.cuda.synchronize()
     # ---- value: inputs resident in HBM
     for _ in range(args.warmup):
-        eng.schedule(dev_tokens, uniform_len=w.prompt_bytes, detail=False, out=dev_dec)
+        eng.schedule(dev_tokens, detail=False, out=dev_dec, **sched_kw)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -274,7 +284,7 @@ def run_gpu(args, rank, world, local_rank):
     probes = postings = 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        eng.schedule(dev_tokens, uniform_len=w.prompt_bytes, detail=False, out=dev_dec)
+        eng.schedule(dev_tokens, detail=False, out=dev_dec, **sched_kw)
         st = eng.stats()
         kms += np.array(st["last_kernel_ms"])
         dev_ms += st["last_kernels_ms"]
@@ -451,6 +461,8 @@ def main():
     ap.add_argument("--requests", type=int, default=0, help="override the batch size R (0 = the config's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs only)")
+    ap.add_argument("--pitch-pad", type=int, default=0,
+                    help="experiment: lay the device-resident prompts out with this many pad bytes between requests")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
