@@ -35,6 +35,9 @@ constexpr int kBarFull = 1;               // named barrier ids 1..4
 constexpr int kBarEmpty = 1 + kStages;    // 5..8
 constexpr int kBarHashed = 1 + 2 * kStages;   // 9..12
 constexpr int kBarTail = 1 + 3 * kStages;     // 13
+#ifndef EPP_STRIPE_AT_A_TIME
+#define EPP_STRIPE_AT_A_TIME 0
+#endif
 #ifndef EPP_HASH_MIN_CTAS
 #define EPP_HASH_MIN_CTAS 4
 #endif
@@ -106,7 +109,7 @@ template <bool kAlign32>
 __device__ __forceinline__ uint64_t block_digest(const uint8_t *src, int n_stripes) {
     uint64_t v[4];
     xxh_init(v);
-    if (n_stripes == 2) {               // the default 64-byte block: both stripes in flight at once
+    if (n_stripes == 2 && !EPP_STRIPE_AT_A_TIME) {   // the default 64-byte block: both stripes in flight at once
         uint64_t x0[4], x1[4];
         load_stripe<kAlign32>(src, x0);
         load_stripe<kAlign32>(src + 32, x1);

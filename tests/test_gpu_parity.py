@@ -300,6 +300,37 @@ def test_schedule_vs_oracle(epp, orc, tg, name):
         np.testing.assert_array_equal(epp.decisions_from_torch(ddec), dec)
 
 
+@pytest.mark.parametrize("name,R", [("config3", 65536), ("config4", 16384), ("config2", 8192)])
+def test_full_size_baseline_configs_vs_oracle(epp, orc, tg, name, R):
+    """BASELINE.json's FULL sizes (config 3: 4 096 endpoints x 4 096-token prompts x 65 536 requests): every decision
+    of the batch against the multi-threaded oracle -- status, pick, tie count, fp64 score bits, prefill pick -- plus
+    the size-independent properties: device-pointer == host-pointer results, and a second run is bit-identical."""
+    import torch
+    import helpers
+    w = tg.baseline_configs()[name].scaled(R=R, name=name)
+    trace = tg.Trace(w)
+    tokens, fam_of, shared = trace.requests()
+    pool, ix, primary, prefill, _ = helpers.setup_oracle(orc, w, trace)
+    odec, ototal = helpers.oracle_decisions(orc, w, pool, ix, primary, prefill, tokens, n_threads=min(64, os.cpu_count() or 1))
+    with helpers.make_engine(w) as eng:
+        helpers.setup_engine(eng, w, trace)
+        dt = torch.from_numpy(tokens.view(np.int32)).cuda()
+        ddec, ddet = eng.schedule(dt, uniform_len=w.prompt_bytes)
+        torch.cuda.synchronize()
+        dec = epp.decisions_from_torch(ddec)
+        det = ddet.cpu().numpy().view(epp.DETAIL_DTYPE).reshape(-1)
+        helpers.assert_decisions_equal(dec, det, odec, ototal, where=name + " full size")
+        ddec2, _ = eng.schedule(dt, uniform_len=w.prompt_bytes)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(epp.decisions_from_torch(ddec2), dec)            # idempotent / deterministic
+        hdec, _ = eng.schedule(tokens[: R // 4], uniform_len=w.prompt_bytes)            # host path, chunked + pipelined
+        np.testing.assert_array_equal(hdec, dec[: R // 4])
+        st = eng.stats()
+        assert st["index_pairs"] > 0
+        # the trace exercises what it claims: hot prefixes, cold prompts, ties, early stops
+        assert 0.2 < (dec["match_blocks"] > 0).mean() < 0.9 and (dec["tie_count"] > 1).any()
+
+
 def test_global_stop_rule_and_holes(epp, orc):
     """Non-prefix-closed index states: the walk stops at the first block NOBODY holds; endpoints missing earlier
     blocks still count later ones; endpoints outside the slot range keep the walk alive (App. C.5)."""
