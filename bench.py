@@ -96,6 +96,30 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _bind_to_gpu_numa_node(local_rank: int):
+    """Run this rank (and first-touch its pinned staging buffers) on the NUMA node its GPU hangs off, so 8 ranks do not
+    pull their H2D traffic across the socket interconnect.  Returns (node, all_cpus) or (None, all_cpus)."""
+    all_cpus = os.sched_getaffinity(0)
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None, all_cpus
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= all_cpus
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node, all_cpus
+    except Exception:
+        pass
+    return None, all_cpus
+
+
 def _pinned(nbytes: int, lib):
     p = C.c_void_p()
     rc = lib.epp_host_alloc(nbytes, C.byref(p))
@@ -226,6 +250,7 @@ def run_gpu(args, rank, world, local_rank):
     from tools import tracegen as tg
 
     torch.cuda.set_device(local_rank)
+    numa_node, all_cpus = _bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     epp.build.build()
@@ -272,31 +297,47 @@ def run_gpu(args, rank, world, local_rank):
         lens = torch.full((R,), w.prompt_bytes, dtype=torch.int64, device="cuda")
         sched_kw = dict(offsets=offs, lengths=lens)
         torch.cuda.synchronize()
-    # ---- value: inputs resident in HBM
+    # ---- value: inputs resident in HBM.  K batches are enqueued back to back (EPP_BATCH_ASYNC) and timed on the
+    # device with CUDA events recorded on the engine's launch stream; the wall clock around the same region is kept
+    # as a cross-check.  The clock sampler runs from the warm-up to the end of the per-kernel pass below.
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         eng.schedule(dev_tokens, detail=False, out=dev_dec, **sched_kw)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    t0 = time.perf_counter()
+    eng.event_record(0)
+    for _ in range(args.steps):
+        eng.schedule(dev_tokens, detail=False, out=dev_dec, asynchronous=True, **sched_kw)
+    eng.event_record(1)
+    eng.synchronize()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    timed_ms = eng.event_elapsed_ms()
+    barrier()
+    wall = max_over_ranks(wall)
+    timed_ms = max_over_ranks(timed_ms)
+    value = world * R * args.steps / (timed_ms * 1e-3)
+    # ---- per-kernel pass: the same K steps again, one at a time, each kernel bracketed by CUDA events on the launch
+    # stream (roofline.launch_ms); repeated until the clock sampler has seen the GPU under this load
     kms = np.zeros(8)
     dev_ms = 0.0
     launches = 0
     probes = postings = 0
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    t_k = time.perf_counter()
+    n_k = 0
+    while n_k < args.steps or (len(sampler.rows) < 5 and time.perf_counter() - t_k < 3.0):
         eng.schedule(dev_tokens, detail=False, out=dev_dec, **sched_kw)
         st = eng.stats()
         kms += np.array(st["last_kernel_ms"])
         dev_ms += st["last_kernels_ms"]
-        launches += st["last_kernel_launches"]
+        launches = st["last_kernel_launches"] * args.steps
         probes, postings = st["last_probes"], st["last_postings"]
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    clocks = sampler.stop()
-    barrier()
-    wall = max_over_ranks(wall)
+        n_k += 1
+    kms *= args.steps / n_k
+    dev_ms *= args.steps / n_k
     dev_ms = max_over_ranks(dev_ms)
-    value = world * R * args.steps / wall
+    clocks = sampler.stop()
 
     # ---- e2e: host buffers through the C ABI (H2D of the prompts + D2H of the decisions inside the timed region)
     e2e_steps = max(1, min(args.steps, 10))
@@ -333,12 +374,15 @@ def run_gpu(args, rank, world, local_rank):
             except Exception:
                 pass
         n_threads = os.cpu_count() or 1
+        os.sched_setaffinity(0, all_cpus)            # the CPU leg gets every host core again
         cpu, _ = cpu_baseline(w, trace, n_threads, tokens=host_tokens) if not args.no_cpu else ({"value": None}, None)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": timed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 (XXH64) + f64 (scores)", "data": "synthetic",
-            "config": _config_json(w, world),
+            "config": _config_json(w, world, {"numa_node_of_rank0": numa_node}),
+            "timing": "CUDA events on the engine launch stream around K back-to-back (EPP_BATCH_ASYNC) batches, max over ranks",
+            "wall_ms_per_step": wall / args.steps * 1e3,
             "device_ms_per_step": dev_ms / args.steps,
             "kernel_ms_per_step": {"k_hash_fused (lengths+digests+chain)": kms[1] + kms[0] + kms[2], "match+score+pick (k_match_pick_sparse + overflow pass)": kms[3]},
             "algorithmic_bytes_per_step": int(algo_total),

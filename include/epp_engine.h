@@ -19,7 +19,7 @@
  *
  * Streams: the engine launches on its own CUDA streams.  With EPP_BATCH_DEVICE_PTRS (and in the epp_shard_* calls)
  * every device buffer passed IN must be complete before the call (the engine does not wait on the caller's
- * streams); every output is complete when the call returns.
+ * streams); every output is complete when the call returns (EPP_BATCH_ASYNC: when epp_synchronize returns).
  *
  * Endpoint identity: the reference keys servers by NamespacedName strings.  The shim maps each endpoint
  * to a dense SLOT id in [0, max_endpoints); all arrays below are indexed by slot id.
@@ -156,6 +156,8 @@ typedef struct {
 } epp_decision_detail;
 
 #define EPP_BATCH_DEVICE_PTRS 1u   /* data / offsets / model_ids and all outputs are DEVICE pointers */
+#define EPP_BATCH_ASYNC 2u         /* epp_schedule + DEVICE_PTRS: enqueue and return; outputs (and epp_stats.last_*)
+                                    * are complete after epp_synchronize().  Batches enqueue in call order.       */
 
 /* A batch of prompts.  Prompt r is data[offsets[r] .. offsets[r+1]) (bytes), or data[offsets[r] .. offsets[r] +
  * lengths[r]) when `lengths` is given (lets ragged prompts START on 32-byte boundaries, which selects the 256-bit-load
@@ -259,6 +261,13 @@ EPP_API int32_t epp_schedule_with_match(epp_engine *h, int64_t n_requests, const
 EPP_API int32_t epp_index_add_picked(epp_engine *h);
 
 EPP_API int32_t epp_get_stats(epp_engine *h, epp_stats *out);
+
+/* Waits for everything the engine has enqueued (EPP_BATCH_ASYNC batches). */
+EPP_API int32_t epp_synchronize(epp_engine *h);
+/* CUDA events on the engine's launch stream: record event `which` (0 = start, 1 = stop) after the work enqueued so
+ * far; epp_event_elapsed_ms waits for the stop event and returns stop - start in milliseconds (device time). */
+EPP_API int32_t epp_event_record(epp_engine *h, int32_t which);
+EPP_API int32_t epp_event_elapsed_ms(epp_engine *h, double *out_ms);
 
 /* ---- endpoint-sharded multi-GPU mode ----------------------------------------------
  * Each rank holds the postings of the endpoints of its shard and the full pool state.  Phase 1 probes

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "libepp_engine.so")
 EPP_MAX_SCORERS = 8
 EPP_NO_ENDPOINT = 0xFFFFFFFF
 EPP_BATCH_DEVICE_PTRS = 1
+EPP_BATCH_ASYNC = 2
 
 EPP_OK, EPP_ERR_INVALID, EPP_ERR_CUDA, EPP_ERR_NO_DEVICE, EPP_ERR_CAPACITY, EPP_ERR_STATE, EPP_ERR_NCCL = \
     0, -1, -2, -3, -4, -5, -6
@@ -97,6 +98,9 @@ SIGNATURES = {
                                             C.c_void_p, C.c_void_p, C.c_uint32]),
     "epp_index_add_picked": (C.c_int32, [C.c_void_p]),
     "epp_get_stats": (C.c_int32, [C.c_void_p, C.POINTER(Stats)]),
+    "epp_synchronize": (C.c_int32, [C.c_void_p]),
+    "epp_event_record": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "epp_event_elapsed_ms": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
     "epp_shard_set": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "epp_shard_probe": (C.c_int32, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     "epp_shard_pick": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -97,6 +97,10 @@ struct epp_engine {
 
     Slot slot[2];
     cudaEvent_t ev[8] = {};
+    cudaEvent_t user_ev[2] = {};    // epp_event_record / epp_event_elapsed_ms
+    unsigned long long *wc_host = nullptr;   // pinned: work counters of an async batch
+    bool async_pending = false;     // an EPP_BATCH_ASYNC batch whose stats have not been read back yet
+    int async_launches = 0;
     DevBuf work_counters;           // u64[2] probes, postings
 
     // models
@@ -230,6 +234,8 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
         CUDA_TRY(cudaEventCreateWithFlags(&e->slot[i].done, cudaEventDisableTiming));
     }
     for (auto &ev : e->ev) CUDA_TRY(cudaEventCreate(&ev));
+    for (auto &ev : e->user_ev) CUDA_TRY(cudaEventCreate(&ev));
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->wc_host), sizeof(unsigned long long) * 2, cudaHostAllocDefault));
     size_t E = (size_t)cfg->max_endpoints;
     CUDA_TRY(e->seeds.reserve(sizeof(uint64_t) * kMaxModels, &e->dev_bytes));
     CUDA_TRY(e->seed_msg.reserve(4096, &e->dev_bytes));
@@ -281,6 +287,8 @@ extern "C" int32_t epp_engine_destroy(epp_engine *h) {
         if (h->slot[i].done) cudaEventDestroy(h->slot[i].done);
     }
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : h->user_ev) if (ev) cudaEventDestroy(ev);
+    if (h->wc_host) cudaFreeHost(h->wc_host);
     delete h;
     return EPP_OK;
 }
@@ -537,6 +545,7 @@ extern "C" int32_t epp_index_get(epp_engine *h, uint64_t hash, uint32_t *out_eps
 struct BatchView {
     int64_t R = 0;
     bool device = false;
+    bool async = false;            // EPP_BATCH_ASYNC (device batches, epp_schedule only)
     const uint8_t *data = nullptr;
     const uint64_t *offsets = nullptr;
     const uint64_t *lengths = nullptr;
@@ -552,6 +561,8 @@ static int32_t check_batch(epp_engine *h, const epp_batch *b, BatchView &v) {
     if (h->n_models == 0) return fail(EPP_ERR_STATE, "no model registered (epp_model_register)");
     v.R = b->n_requests;
     v.device = (b->flags & EPP_BATCH_DEVICE_PTRS) != 0;
+    v.async = (b->flags & EPP_BATCH_ASYNC) != 0;
+    if (v.async && !v.device) return fail(EPP_ERR_INVALID, "EPP_BATCH_ASYNC needs EPP_BATCH_DEVICE_PTRS");
     v.data = reinterpret_cast<const uint8_t *>(b->data);
     v.offsets = b->offsets;
     v.lengths = b->lengths;
@@ -726,6 +737,24 @@ static int32_t launch_cycle(epp_engine *h, Slot &sl, const HashParams &hp_in, Pi
     return launch_match(h, sl, pp, launches);
 }
 
+// Completes the device batch in flight on stream 0 and reads its per-kernel CUDA-event times and work counters.
+static int32_t finish_async(epp_engine *h) {
+    CUDA_TRY(cudaStreamSynchronize(h->slot[0].stream));
+    if (!h->async_pending) return EPP_OK;
+    h->async_pending = false;
+    float t[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) cudaEventElapsedTime(&t[i], h->ev[i], h->ev[i + 1]);
+    for (int i = 0; i < 8; i++) h->stats.last_kernel_ms[i] = i < 4 ? t[i] : 0.0;
+    h->stats.last_hash_ms = t[0] + t[1] + t[2];
+    h->stats.last_match_pick_ms = t[3];
+    h->stats.last_kernels_ms = t[0] + t[1] + t[2] + t[3];
+    h->stats.last_h2d_ms = h->stats.last_d2h_ms = 0;
+    h->stats.last_probes = h->wc_host[0];
+    h->stats.last_postings = h->wc_host[1];
+    h->stats.last_kernel_launches = (uint64_t)h->async_launches;
+    return EPP_OK;
+}
+
 // Runs hashing (+ match/pick) for a batch.  Host batches are split into chunks whose H2D copy overlaps the
 // kernels of the previous chunk (two streams, two staging buffers); device batches run in one pass.
 static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t *out_hashes, int32_t *out_nblocks,
@@ -738,6 +767,7 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
         if (!h->pool_ready) return fail(EPP_ERR_STATE, "epp_pool_set has not been called");
         EPP_TRY(commit_locked(h));
     }
+    if (h->async_pending && !(v.device && v.async)) EPP_TRY(finish_async(h));
     EPP_TRY(reserve_batch(h, R));
     int launches = 0;
     cudaStream_t s0 = h->slot[0].stream;
@@ -758,20 +788,11 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
             EPP_TRY(launch_cycle(h, h->slot[0], hash_params(h, w), pp, &launches, h->ev));
         }
         CUDA_TRY(cudaEventRecord(h->ev[4], s0));
-        unsigned long long wc[2] = {0, 0};
-        CUDA_TRY(cudaMemcpyAsync(wc, h->work_counters.p, sizeof wc, cudaMemcpyDeviceToHost, s0));
-        CUDA_TRY(cudaStreamSynchronize(s0));
-        float t[4] = {0, 0, 0, 0};
-        for (int i = 0; i < 4; i++) cudaEventElapsedTime(&t[i], h->ev[i], h->ev[i + 1]);
-        for (int i = 0; i < 8; i++) h->stats.last_kernel_ms[i] = i < 4 ? t[i] : 0.0;
-        h->stats.last_hash_ms = t[0] + t[1] + t[2];
-        h->stats.last_match_pick_ms = t[3];
-        h->stats.last_kernels_ms = t[0] + t[1] + t[2] + t[3];
-        h->stats.last_h2d_ms = h->stats.last_d2h_ms = 0;
-        h->stats.last_probes = wc[0];
-        h->stats.last_postings = wc[1];
-        h->stats.last_kernel_launches = (uint64_t)launches;
-        return EPP_OK;
+        CUDA_TRY(cudaMemcpyAsync(h->wc_host, h->work_counters.p, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, s0));
+        h->async_pending = true;
+        h->async_launches = launches;
+        if (v.async && mode == Mode::Schedule) return EPP_OK;      // epp_synchronize() completes it
+        return finish_async(h);
     }
 
     // ---- host batch: upload the small per-request arrays once, then pipeline the prompt bytes
@@ -899,6 +920,7 @@ extern "C" int32_t epp_schedule(epp_engine *h, const epp_batch *batch, epp_decis
     h->stats.n_batches++;
     h->stats.n_decisions += (uint64_t)v.R;
     if (keep_hashes) {
+        EPP_TRY(finish_async(h));
         h->kept_R = v.R;
         h->kept_decisions.resize((size_t)v.R);
         if (v.R) {
@@ -1017,8 +1039,37 @@ extern "C" int32_t epp_schedule_with_match(epp_engine *h, int64_t n_requests, co
 extern "C" int32_t epp_get_stats(epp_engine *h, epp_stats *out) {
     if (!h || !out) return fail(EPP_ERR_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lk(h->mu);
+    if (h->async_pending) { EPP_TRY(set_device(h)); EPP_TRY(finish_async(h)); }
     h->stats.device_bytes = h->dev_bytes;
     *out = h->stats;
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_synchronize(epp_engine *h) {
+    if (!h) return fail(EPP_ERR_INVALID, "NULL engine");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    EPP_TRY(finish_async(h));
+    CUDA_TRY(cudaStreamSynchronize(h->slot[1].stream));
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_event_record(epp_engine *h, int32_t which) {
+    if (!h || which < 0 || which > 1) return fail(EPP_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    CUDA_TRY(cudaEventRecord(h->user_ev[which], h->slot[0].stream));
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_event_elapsed_ms(epp_engine *h, double *out_ms) {
+    if (!h || !out_ms) return fail(EPP_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    CUDA_TRY(cudaEventSynchronize(h->user_ev[1]));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->user_ev[0], h->user_ev[1]));
+    *out_ms = ms;
     return EPP_OK;
 }
 

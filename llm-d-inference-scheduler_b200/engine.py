@@ -239,9 +239,12 @@ class Engine:
         return out
 
     def schedule(self, data, offsets=None, uniform_len=None, model_ids=None, n_requests=None, keep_hashes=False,
-                 detail=True, out=None, lengths=None):
-        """a1-a14 Scheduler.Schedule for a batch -> (decisions, details)."""
+                 detail=True, out=None, lengths=None, asynchronous=False):
+        """a1-a14 Scheduler.Schedule for a batch -> (decisions, details).  asynchronous=True (CUDA tensors only)
+        enqueues the batch and returns; the outputs are complete after synchronize()."""
         b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests, lengths)
+        if asynchronous:
+            b.flags |= capi.EPP_BATCH_ASYNC
         if dev:
             import torch
             dec = out if out is not None else torch.empty((max(R, 1), 32), dtype=torch.uint8, device=data.device)
@@ -262,6 +265,18 @@ class Engine:
         self._check(self._lib.epp_schedule_with_match(self._h, R, _ptr(match), _ptr(total), _ptr(il),
                                                       block_size_tokens, _ptr(dec), _ptr(det), 0))
         return dec, det
+
+    def synchronize(self):
+        self._check(self._lib.epp_synchronize(self._h))
+
+    def event_record(self, which: int):
+        """CUDA event on the engine's launch stream (0 = start, 1 = stop)."""
+        self._check(self._lib.epp_event_record(self._h, which))
+
+    def event_elapsed_ms(self) -> float:
+        ms = C.c_double(0.0)
+        self._check(self._lib.epp_event_elapsed_ms(self._h, C.byref(ms)))
+        return ms.value
 
     def stats(self) -> dict:
         s = capi.Stats()

@@ -331,6 +331,34 @@ def test_full_size_baseline_configs_vs_oracle(epp, orc, tg, name, R):
         assert 0.2 < (dec["match_blocks"] > 0).mean() < 0.9 and (dec["tie_count"] > 1).any()
 
 
+def test_async_device_batches_match_synchronous_ones(epp, orc, tg):
+    """EPP_BATCH_ASYNC: several device batches enqueued back to back; after epp_synchronize every output equals the
+    synchronous call's, the stats describe the last batch, and the engine's stream events bracket the work."""
+    import torch
+    import helpers
+    w = tg.baseline_configs()["config3"].scaled(E=256, R=768, name="config3")
+    trace = tg.Trace(w)
+    tokens, _, _ = trace.requests()
+    with helpers.make_engine(w) as eng:
+        helpers.setup_engine(eng, w, trace)
+        parts = [torch.from_numpy(tokens[i * 256:(i + 1) * 256].view(np.int32)).cuda() for i in range(3)]
+        want = [epp.decisions_from_torch(eng.schedule(p, uniform_len=w.prompt_bytes, detail=False)[0]) for p in parts]
+        outs = [torch.zeros((256, 32), dtype=torch.uint8, device="cuda") for _ in parts]
+        torch.cuda.synchronize()
+        eng.event_record(0)
+        for p, o in zip(parts, outs):
+            eng.schedule(p, uniform_len=w.prompt_bytes, detail=False, out=o, asynchronous=True)
+        eng.event_record(1)
+        eng.synchronize()
+        assert eng.event_elapsed_ms() > 0.0
+        for o, wnt in zip(outs, want):
+            np.testing.assert_array_equal(epp.decisions_from_torch(o), wnt)
+        st = eng.stats()
+        assert st["last_kernels_ms"] > 0 and st["last_probes"] > 0
+        with pytest.raises(epp.EngineError):
+            eng.schedule(tokens[:8], uniform_len=w.prompt_bytes, asynchronous=True)      # host buffers cannot be async
+
+
 def test_global_stop_rule_and_holes(epp, orc):
     """Non-prefix-closed index states: the walk stops at the first block NOBODY holds; endpoints missing earlier
     blocks still count later ones; endpoints outside the slot range keep the walk alive (App. C.5)."""
