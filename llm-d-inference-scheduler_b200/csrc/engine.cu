@@ -1,5 +1,5 @@
 // engine.cu -- the C ABI of libepp_engine.so (include/epp_engine.h) and the host logic above the kernels:
-// configuration, pool-state snapshot, prefix-index mirror + device table, batch staging (H2D / D2H pipelined
+// configuration, pool-state snapshot, prefix-index store + device table, batch staging (H2D / D2H pipelined
 // against the kernels on two streams) and the per-batch launch sequence.
 //
 // There is NO CPU compute path in this file: without a CUDA device epp_engine_create fails with
@@ -17,7 +17,8 @@
 #include <string>
 #include <vector>
 
-#include "index_mirror.h"
+#include "devbuf.h"
+#include "index_store.h"
 #include "kernels.h"
 
 using namespace epp;
@@ -49,31 +50,6 @@ static int32_t fail(int32_t code, const char *fmt, ...) {
         int32_t _r = (expr);     \
         if (_r != EPP_OK) return _r; \
     } while (0)
-
-// ------------------------------------------------------------------------------------------------
-// device buffers
-// ------------------------------------------------------------------------------------------------
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
-    DevBuf() = default;
-    DevBuf(const DevBuf &) = delete;
-    DevBuf &operator=(const DevBuf &) = delete;
-    // Grows (never shrinks); contents are NOT preserved.
-    cudaError_t reserve(size_t bytes, size_t *accounted) {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) { cudaFree(p); if (accounted) *accounted -= cap; p = nullptr; cap = 0; }
-        size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&p, want); }
-        if (e != cudaSuccess) { p = nullptr; return e; }
-        cap = want;
-        if (accounted) *accounted += cap;
-        return cudaSuccess;
-    }
-    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
-};
 
 struct ProfileState {
     DevBuf cand, contrib, base, order, grp_size, sort_key, n_cand, qminmax;
@@ -115,7 +91,12 @@ struct epp_engine {
     ProfileState prof[kMaxProfiles];
 
     // index
-    std::unique_ptr<IndexMirror> mirror;
+    std::unique_ptr<IndexStore> store;          // write side: LRU bookkeeping in HBM (index_store.cu)
+    // indexer.Add calls queued by epp_index_add until the next commit / read (applied as ONE device batch)
+    std::vector<uint32_t> q_ep, q_n;
+    std::vector<int32_t> q_nb;
+    std::vector<uint64_t> q_src, q_hashes;
+    DevBuf q_ep_dev, q_n_dev, q_nb_dev, q_src_dev, q_hashes_dev, kept_dec;
     bool snapshot_mode = false;
     DevBuf slots, postings, idx_scratch, idx_cursor, idx_special, pair_hash, pair_ep, get_out, intern_keys, intern_vals;
     uint64_t idx_capacity = 0, idx_pairs = 0;
@@ -137,7 +118,6 @@ struct epp_engine {
     size_t pick_smem = 0;
     int64_t kept_R = 0;             // rows of `hashes` valid for epp_index_add_picked
     int64_t shard_R = 0;            // rows of `hashes` valid for epp_shard_pick / epp_shard_merge
-    std::vector<epp_decision> kept_decisions;
 
     epp_stats stats{};
 };
@@ -252,7 +232,7 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
     CUDA_TRY(e->work_counters.reserve(sizeof(unsigned long long) * 2, &e->dev_bytes));
     memset(&e->idx_special_host, 0, sizeof(IndexSlot));
     e->idx_special_host.key = kEmptyKey;
-    e->mirror.reset(new IndexMirror(cfg->lru_capacity_per_server));
+    e->store.reset(new IndexStore((uint32_t)cfg->max_endpoints, cfg->lru_capacity_per_server));
     { const char *v1 = getenv("EPP_HASH_V1"); e->force_v1 = (v1 && v1[0] == '1') ? 1 : 0; }
     { const char *v1 = getenv("EPP_MATCH_V1"); e->force_match_v1 = (v1 && v1[0] == '1') ? 1 : 0; }
     { const char *v1 = getenv("EPP_WIDE"); e->wide = (v1 && v1[0] == '1') ? 1 : 0; }
@@ -422,17 +402,11 @@ extern "C" int32_t epp_pool_set(epp_engine *h, int32_t n, const uint32_t *ids, c
 // ------------------------------------------------------------------------------------------------
 // prefix index
 // ------------------------------------------------------------------------------------------------
-static int32_t build_device_index(epp_engine *h, const uint64_t *hashes, const uint32_t *eps, uint64_t n,
-                                  uint64_t n_distinct_hint) {
+// Bulk build of the read table from n (hash, endpoint) pairs already in h->pair_hash / h->pair_ep.
+static int32_t build_index_from_device_pairs(epp_engine *h, uint64_t n, uint64_t n_distinct_hint) {
     cudaStream_t s = h->slot[0].stream;
     if (n >= 0xFFFFFFF0ull) return fail(EPP_ERR_CAPACITY, "index snapshot of %llu pairs exceeds the u32 posting space", (unsigned long long)n);
     CUDA_TRY(h->postings.reserve(sizeof(uint32_t) * std::max<uint64_t>(n, 1), &h->dev_bytes));
-    CUDA_TRY(h->pair_hash.reserve(sizeof(uint64_t) * std::max<uint64_t>(n, 1), &h->dev_bytes));
-    CUDA_TRY(h->pair_ep.reserve(sizeof(uint32_t) * std::max<uint64_t>(n, 1), &h->dev_bytes));
-    if (n) {
-        CUDA_TRY(cudaMemcpyAsync(h->pair_hash.p, hashes, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(h->pair_ep.p, eps, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
-    }
     uint64_t distinct = std::max<uint64_t>(1, n_distinct_hint);
     uint32_t cursor[4] = {0, 0, 0, 0};
     uint64_t cap = 16;
@@ -466,13 +440,61 @@ static int32_t build_device_index(epp_engine *h, const uint64_t *hashes, const u
     return EPP_OK;
 }
 
+static int32_t build_device_index(epp_engine *h, const uint64_t *hashes, const uint32_t *eps, uint64_t n,
+                                  uint64_t n_distinct_hint) {
+    cudaStream_t s = h->slot[0].stream;
+    CUDA_TRY(h->pair_hash.reserve(sizeof(uint64_t) * std::max<uint64_t>(n, 1), &h->dev_bytes));
+    CUDA_TRY(h->pair_ep.reserve(sizeof(uint32_t) * std::max<uint64_t>(n, 1), &h->dev_bytes));
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(h->pair_hash.p, hashes, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(h->pair_ep.p, eps, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, s));
+    }
+    return build_index_from_device_pairs(h, n, n_distinct_hint);
+}
+
+// Applies the queued epp_index_add calls to the device store as one batch (sub-batches bound the ordering scratch).
+static int32_t flush_add_queue(epp_engine *h) {
+    const size_t M = h->q_ep.size();
+    if (M == 0) return EPP_OK;
+    cudaStream_t s = h->slot[0].stream;
+    CUDA_TRY(h->q_ep_dev.reserve(sizeof(uint32_t) * M, &h->dev_bytes));
+    CUDA_TRY(h->q_n_dev.reserve(sizeof(uint32_t) * M, &h->dev_bytes));
+    CUDA_TRY(h->q_nb_dev.reserve(sizeof(int32_t) * M, &h->dev_bytes));
+    CUDA_TRY(h->q_src_dev.reserve(sizeof(uint64_t) * M, &h->dev_bytes));
+    CUDA_TRY(h->q_hashes_dev.reserve(sizeof(uint64_t) * std::max<size_t>(1, h->q_hashes.size()), &h->dev_bytes));
+    CUDA_TRY(cudaMemcpyAsync(h->q_ep_dev.p, h->q_ep.data(), sizeof(uint32_t) * M, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->q_n_dev.p, h->q_n.data(), sizeof(uint32_t) * M, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->q_nb_dev.p, h->q_nb.data(), sizeof(int32_t) * M, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->q_src_dev.p, h->q_src.data(), sizeof(uint64_t) * M, cudaMemcpyHostToDevice, s));
+    if (!h->q_hashes.empty())
+        CUDA_TRY(cudaMemcpyAsync(h->q_hashes_dev.p, h->q_hashes.data(), sizeof(uint64_t) * h->q_hashes.size(), cudaMemcpyHostToDevice, s));
+    const size_t kSub = 1u << 18;
+    for (size_t c0 = 0; c0 < M; c0 += kSub) {
+        StoreCalls c;
+        c.M = (uint32_t)std::min(kSub, M - c0);
+        c.ep = h->q_ep_dev.as<uint32_t>() + c0;
+        c.n = h->q_n_dev.as<uint32_t>() + c0;
+        c.nb = h->q_nb_dev.as<int32_t>() + c0;
+        c.src = h->q_src_dev.as<uint64_t>() + c0;
+        c.hashes = h->q_hashes_dev.as<uint64_t>();
+        CUDA_TRY(h->store->apply(c, s));
+    }
+    h->q_ep.clear();
+    h->q_n.clear();
+    h->q_nb.clear();
+    h->q_src.clear();
+    h->q_hashes.clear();
+    return EPP_OK;
+}
+
 static int32_t commit_locked(epp_engine *h) {
-    if (h->snapshot_mode || !h->mirror->dirty()) return EPP_OK;
-    std::vector<uint64_t> hs;
-    std::vector<uint32_t> es;
-    h->mirror->export_pairs(hs, es);
-    EPP_TRY(build_device_index(h, hs.data(), es.data(), hs.size(), h->mirror->n_hashes()));
-    h->mirror->mark_clean();
+    if (h->snapshot_mode) return EPP_OK;
+    EPP_TRY(flush_add_queue(h));
+    if (!h->store->dirty()) return EPP_OK;
+    uint64_t n = 0;
+    CUDA_TRY(h->store->export_pairs(h->pair_hash, h->pair_ep, &n, &h->dev_bytes, h->slot[0].stream));
+    EPP_TRY(build_index_from_device_pairs(h, n, n));
+    h->store->mark_clean();
     return EPP_OK;
 }
 
@@ -491,8 +513,17 @@ static IndexView index_view(epp_engine *h) {
 extern "C" int32_t epp_index_add(epp_engine *h, uint32_t ep, int32_t n, const uint64_t *hashes, int32_t num_gpu_blocks) {
     if (!h || n < 0 || (n > 0 && !hashes)) return fail(EPP_ERR_INVALID, "bad arguments");
     std::lock_guard<std::mutex> lk(h->mu);
-    if (h->snapshot_mode) return fail(EPP_ERR_STATE, "index holds a bulk snapshot; incremental adds need an empty or mirror-built index");
-    h->mirror->add(ep, hashes, n, num_gpu_blocks);
+    if (h->snapshot_mode) return fail(EPP_ERR_STATE, "index holds a bulk snapshot; incremental adds need an empty or incrementally built index");
+    if (ep >= (uint32_t)h->cfg.max_endpoints) return fail(EPP_ERR_INVALID, "endpoint slot %u out of range [0,%d)", ep, h->cfg.max_endpoints);
+    h->q_ep.push_back(ep);
+    h->q_n.push_back((uint32_t)n);
+    h->q_nb.push_back(num_gpu_blocks);
+    h->q_src.push_back((uint64_t)h->q_hashes.size());
+    h->q_hashes.insert(h->q_hashes.end(), hashes, hashes + n);
+    if (h->q_hashes.size() >= (1u << 26) || h->q_ep.size() >= (1u << 22)) {      // bound the host queue
+        EPP_TRY(set_device(h));
+        EPP_TRY(flush_add_queue(h));
+    }
     return EPP_OK;
 }
 
@@ -500,7 +531,9 @@ extern "C" int32_t epp_index_remove_endpoint(epp_engine *h, uint32_t ep) {
     if (!h) return fail(EPP_ERR_INVALID, "NULL engine");
     std::lock_guard<std::mutex> lk(h->mu);
     if (h->snapshot_mode) return fail(EPP_ERR_STATE, "index holds a bulk snapshot; reload it without the endpoint instead");
-    h->mirror->remove_pod(ep);
+    EPP_TRY(set_device(h));
+    EPP_TRY(flush_add_queue(h));                    // calls apply in the order they were made
+    CUDA_TRY(h->store->remove_endpoint(ep, h->slot[0].stream));
     return EPP_OK;
 }
 
@@ -508,8 +541,9 @@ extern "C" int32_t epp_index_load_snapshot(epp_engine *h, uint64_t n_pairs, cons
     if (!h || (n_pairs && (!hashes || !eps))) return fail(EPP_ERR_INVALID, "bad arguments");
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
-    h->mirror->clear();
-    h->mirror->mark_clean();
+    h->q_ep.clear(); h->q_n.clear(); h->q_nb.clear(); h->q_src.clear(); h->q_hashes.clear();
+    CUDA_TRY(h->store->clear(h->slot[0].stream));
+    h->store->mark_clean();
     EPP_TRY(build_device_index(h, hashes, eps, n_pairs, n_pairs));
     h->snapshot_mode = n_pairs > 0;
     return EPP_OK;
@@ -919,14 +953,14 @@ extern "C" int32_t epp_schedule(epp_engine *h, const epp_batch *batch, epp_decis
     EPP_TRY(run_batch(h, v, Mode::Schedule, nullptr, nullptr, out, detail, nullptr, nullptr));
     h->stats.n_batches++;
     h->stats.n_decisions += (uint64_t)v.R;
-    if (keep_hashes) {
-        EPP_TRY(finish_async(h));
+    if (keep_hashes && v.R) {
+        // the decisions stay on the device next to the hashes; host batches already have them in h->decisions
+        cudaStream_t s0 = h->slot[0].stream;
+        CUDA_TRY(h->kept_dec.reserve(sizeof(epp_decision) * (size_t)v.R, &h->dev_bytes));
+        const void *src = v.device ? (const void *)out : (const void *)h->decisions.p;
+        CUDA_TRY(cudaMemcpyAsync(h->kept_dec.p, src, sizeof(epp_decision) * (size_t)v.R, cudaMemcpyDeviceToDevice, s0));
+        if (!v.async) CUDA_TRY(cudaStreamSynchronize(s0));
         h->kept_R = v.R;
-        h->kept_decisions.resize((size_t)v.R);
-        if (v.R) {
-            if (v.device) CUDA_TRY(cudaMemcpy(h->kept_decisions.data(), out, sizeof(epp_decision) * (size_t)v.R, cudaMemcpyDeviceToHost));
-            else memcpy(h->kept_decisions.data(), out, sizeof(epp_decision) * (size_t)v.R);
-        }
     }
     return EPP_OK;
 }
@@ -937,19 +971,10 @@ extern "C" int32_t epp_index_add_picked(epp_engine *h) {
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
     if (h->kept_R == 0) return fail(EPP_ERR_STATE, "no batch kept (call epp_schedule with keep_hashes=1 first)");
-    if (h->snapshot_mode) return fail(EPP_ERR_STATE, "index holds a bulk snapshot; incremental adds need a mirror-built index");
-    const size_t B = (size_t)h->cfg.max_prefix_blocks;
-    std::vector<uint64_t> hs((size_t)h->kept_R * B);
-    std::vector<int32_t> nb((size_t)h->kept_R);
-    CUDA_TRY(cudaMemcpy(hs.data(), h->hashes.p, sizeof(uint64_t) * hs.size(), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(nb.data(), h->nblocks.p, sizeof(int32_t) * nb.size(), cudaMemcpyDeviceToHost));
-    for (int64_t r = 0; r < h->kept_R; r++) {
-        const epp_decision &d = h->kept_decisions[(size_t)r];
-        if (d.status != 0 || d.pick == EPP_NO_ENDPOINT) continue;            // plugin.go:168-170
-        h->mirror->add(d.pick, hs.data() + (size_t)r * B, nb[(size_t)r], 0);
-        if (d.prefill_pick != EPP_NO_ENDPOINT)                                // plugin.go:176-178
-            h->mirror->add(d.prefill_pick, hs.data() + (size_t)r * B, nb[(size_t)r], 0);
-    }
+    if (h->snapshot_mode) return fail(EPP_ERR_STATE, "index holds a bulk snapshot; incremental adds need an incrementally built index");
+    EPP_TRY(flush_add_queue(h));
+    CUDA_TRY(h->store->apply_picks(h->kept_dec.as<epp_decision>(), h->hashes.as<uint64_t>(), h->nblocks.as<int32_t>(), h->kept_R,
+                                   h->cfg.max_prefix_blocks, h->slot[0].stream));
     h->kept_R = 0;
     return EPP_OK;
 }
@@ -1040,7 +1065,7 @@ extern "C" int32_t epp_get_stats(epp_engine *h, epp_stats *out) {
     if (!h || !out) return fail(EPP_ERR_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lk(h->mu);
     if (h->async_pending) { EPP_TRY(set_device(h)); EPP_TRY(finish_async(h)); }
-    h->stats.device_bytes = h->dev_bytes;
+    h->stats.device_bytes = h->dev_bytes + h->store->device_bytes();
     *out = h->stats;
     return EPP_OK;
 }

@@ -1,0 +1,670 @@
+// index_store.cu -- kernels and host logic of the HBM-resident write side of the prefix index (see index_store.h).
+#include "index_store.h"
+
+#include <algorithm>
+
+namespace epp {
+
+namespace {
+
+constexpr unsigned long long kLeakBit = 1ull << 63;   // log entry: evicting it leaves the pair in the inverted map
+constexpr unsigned long long kTmpBit = 1ull << 62;    // scratch of k_store_leak
+constexpr unsigned long long kSeqMask = ~(kLeakBit | kTmpBit);
+constexpr int kCallChunk = 1024;                      // calls per ordering chunk (= threads of k_store_offsets)
+enum { kCtrPtUsed = 0, kCtrTotalItems, kCtrNeedRepack, kCtrInMap, kCtrCursor, kCtrAlive, kCtrN = 8 };
+
+// One (hash, endpoint) pair of the write side: 32 bytes = one sector.
+struct __align__(32) StoreEntry {
+    unsigned long long hash;   // kEmptyKey = free slot
+    unsigned long long seq;    // 0 = not in the endpoint's LRU, else sequence number of the latest Add of the pair
+    uint32_t ep;               // kNoEp between the claim of `hash` and the publication of the endpoint
+    uint32_t in_map;           // 1 = endpoint is in hashToPods[hash]
+    unsigned long long pad;
+};
+
+}  // namespace
+
+struct IndexStore::View {
+    StoreEntry *pt;
+    uint64_t pt_mask;
+    unsigned long long *log_hash;
+    unsigned long long *log_seq;
+    uint32_t E;
+    int32_t default_cap;
+    uint32_t *cap, *live, *firstcall, *sp_in_map;
+    unsigned long long *seg_off, *seg_cap, *head, *tail, *inc, *next_seq, *sp_seq;
+    unsigned long long *ctr;
+};
+
+namespace {
+using View = IndexStore::View;
+
+struct EntryRef {
+    unsigned long long *seq;
+    uint32_t *in_map;
+};
+
+__device__ __forceinline__ uint64_t pt_home(uint64_t h, uint32_t e, uint64_t mask) {
+    // XXH64 output is uniformly mixed; the endpoint term keeps the many endpoints of one hot hash off one probe chain
+    return (h + (uint64_t)e * 0x9E3779B97F4A7C15ULL) & mask;
+}
+
+// Finds or creates the entry of (h, e).  Lock-free: a slot is claimed by CAS on its hash word; its endpoint word is
+// then published by CAS as well, by the claimer or by any thread inserting the same hash (whoever wins owns the
+// slot, the loser keeps probing) -- no thread ever waits for another.
+__device__ __forceinline__ StoreEntry *pt_find_or_claim(const View &v, uint64_t h, uint32_t e) {
+    uint64_t i = pt_home(h, e, v.pt_mask);
+    for (;;) {
+        StoreEntry *s = v.pt + i;
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&s->hash);
+        if (cur == kEmptyKey) {
+            unsigned long long old = atomicCAS(&s->hash, (unsigned long long)kEmptyKey, (unsigned long long)h);
+            if (old == kEmptyKey) {
+                atomicAdd(&v.ctr[kCtrPtUsed], 1ull);
+                cur = h;
+            } else {
+                cur = old;
+            }
+        }
+        if (cur == h) {
+            uint32_t ce = *reinterpret_cast<volatile uint32_t *>(&s->ep);
+            if (ce == kNoEp) {
+                uint32_t old = atomicCAS(&s->ep, kNoEp, e);
+                ce = old == kNoEp ? e : old;
+            }
+            if (ce == e) return s;
+        }
+        i = (i + 1) & v.pt_mask;
+    }
+}
+
+__device__ __forceinline__ StoreEntry *pt_find(const View &v, uint64_t h, uint32_t e) {
+    uint64_t i = pt_home(h, e, v.pt_mask);
+    for (;;) {
+        StoreEntry *s = v.pt + i;
+        unsigned long long cur = s->hash;
+        if (cur == kEmptyKey) return nullptr;
+        if (cur == h && s->ep == e) return s;
+        i = (i + 1) & v.pt_mask;
+    }
+}
+
+__device__ __forceinline__ EntryRef ref_claim(const View &v, uint64_t h, uint32_t e) {
+    if (h == kEmptyKey) return {&v.sp_seq[e], &v.sp_in_map[e]};    // the one hash equal to the free-slot sentinel
+    StoreEntry *s = pt_find_or_claim(v, h, e);
+    return {&s->seq, &s->in_map};
+}
+
+__device__ __forceinline__ bool ref_find(const View &v, uint64_t h, uint32_t e, EntryRef &r) {
+    if (h == kEmptyKey) {
+        r = {&v.sp_seq[e], &v.sp_in_map[e]};
+        return true;
+    }
+    StoreEntry *s = pt_find(v, h, e);
+    if (!s) return false;
+    r = {&s->seq, &s->in_map};
+    return true;
+}
+
+// ---- table / state initialisation ---------------------------------------------------------------------------------
+__global__ void k_store_pt_clear(StoreEntry *pt, uint64_t capacity) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= capacity) return;
+    StoreEntry z;
+    z.hash = kEmptyKey;
+    z.seq = 0;
+    z.ep = kNoEp;
+    z.in_map = 0;
+    z.pad = 0;
+    pt[i] = z;
+}
+
+__global__ void k_store_state_clear(View v) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < v.E) {
+        v.cap[e] = 0;
+        v.live[e] = 0;
+        v.firstcall[e] = kNoEp;
+        v.sp_in_map[e] = 0;
+        v.seg_off[e] = 0;
+        v.seg_cap[e] = 0;
+        v.head[e] = 0;
+        v.tail[e] = 0;
+        v.inc[e] = 0;
+        v.next_seq[e] = 1;
+        v.sp_seq[e] = 0;
+    }
+    if (e < kCtrN) v.ctr[e] = 0;
+}
+
+// ---- picks -> calls (plugin.go:164-200) -------------------------------------------------------------------------------
+__global__ void k_store_calls_from_picks(const epp_decision *dec, const int32_t *nblocks, int64_t R, int32_t max_blocks,
+                                         uint32_t E, uint32_t *call_ep, uint32_t *call_n, int32_t *call_nb,
+                                         unsigned long long *call_src) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    epp_decision d = dec[r];
+    const bool ok = d.status == 0 && d.pick != EPP_NO_ENDPOINT && d.pick < E;      // plugin.go:168-170
+    const uint32_t n = ok ? (uint32_t)max(0, nblocks[r]) : 0u;
+    call_ep[2 * r] = ok ? d.pick : kNoEp;
+    call_n[2 * r] = n;
+    call_nb[2 * r] = 0;
+    call_src[2 * r] = (unsigned long long)r * (unsigned long long)max_blocks;
+    const bool pf = ok && d.prefill_pick != EPP_NO_ENDPOINT && d.prefill_pick < E;   // plugin.go:176-178
+    call_ep[2 * r + 1] = pf ? d.prefill_pick : kNoEp;
+    call_n[2 * r + 1] = pf ? n : 0u;
+    call_nb[2 * r + 1] = 0;
+    call_src[2 * r + 1] = (unsigned long long)r * (unsigned long long)max_blocks;
+}
+
+// ---- sequencing: where in its endpoint's Add order does each call start? ---------------------------------------------
+__global__ void k_store_batch_clear(View v, uint32_t *hist, uint64_t hist_n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < hist_n) hist[i] = 0;
+    if (i < v.E) v.firstcall[i] = kNoEp;
+    if (i == 0) {
+        v.ctr[kCtrTotalItems] = 0;
+        v.ctr[kCtrNeedRepack] = 0;
+    }
+}
+
+__global__ void k_store_hist(View v, uint32_t M, const uint32_t *call_ep, const uint32_t *call_n, uint32_t *hist) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= M) return;
+    uint32_t e = call_ep[c];
+    if (e >= v.E) return;
+    if (call_n[c]) atomicAdd(&hist[(uint64_t)(c / kCallChunk) * v.E + e], call_n[c]);
+    atomicMin(&v.firstcall[e], c);
+}
+
+// Per endpoint: exclusive scan of its per-chunk item counts (hist becomes the chunk's starting offset), creation of
+// the LRU by the endpoint's first call of the batch (indexer.go:57-69), room check of the log segment.
+__global__ void k_store_plan(View v, uint32_t n_chunks, uint32_t *hist, const int32_t *call_nb) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= v.E) return;
+    unsigned long long run = 0;
+    for (uint32_t ch = 0; ch < n_chunks; ch++) {
+        uint32_t t = hist[(uint64_t)ch * v.E + e];
+        hist[(uint64_t)ch * v.E + e] = (uint32_t)run;
+        run += t;
+    }
+    v.inc[e] = run;
+    uint32_t fc = v.firstcall[e];
+    if (fc != kNoEp && v.cap[e] == 0) {
+        int32_t nb = call_nb[fc];
+        int32_t c = nb > 0 ? nb : v.default_cap;
+        v.cap[e] = c > 0 ? (uint32_t)c : 1u;
+    }
+    if (run) {
+        atomicAdd(&v.ctr[kCtrTotalItems], run);
+        if (v.head[e] + run > v.seg_cap[e]) atomicOr(&v.ctr[kCtrNeedRepack], 1ull);
+    }
+}
+
+__global__ void __launch_bounds__(kCallChunk) k_store_offsets(View v, uint32_t M, const uint32_t *call_ep,
+                                                               const uint32_t *call_n, const uint32_t *hist,
+                                                               unsigned long long *call_off) {
+    __shared__ uint32_t s_ep[kCallChunk];
+    __shared__ uint32_t s_n[kCallChunk];
+    const uint32_t t = threadIdx.x, c = blockIdx.x * kCallChunk + t;
+    const uint32_t e = c < M ? call_ep[c] : kNoEp;
+    s_ep[t] = e;
+    s_n[t] = c < M ? call_n[c] : 0u;
+    __syncthreads();
+    if (e >= v.E) return;
+    unsigned long long before = 0;
+    for (uint32_t u = 0; u < t; u++) before += s_ep[u] == e ? s_n[u] : 0u;
+    call_off[c] = hist[(uint64_t)blockIdx.x * v.E + e] + before;
+}
+
+// ---- Add: append to the endpoint's log, upsert the pair table (first loop + second loop of indexer.Add) ---------------
+__global__ void k_store_upsert(View v, uint32_t M, const uint32_t *call_ep, const uint32_t *call_n,
+                               const unsigned long long *call_src, const unsigned long long *call_off,
+                               const unsigned long long *hashes) {
+    const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t in_map_new = 0;
+    for (uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < M; c += warps) {
+        const uint32_t e = call_ep[c], n = call_n[c];
+        if (e >= v.E || n == 0) continue;
+        const unsigned long long off = call_off[c];
+        const unsigned long long seq0 = v.next_seq[e] + off;
+        const unsigned long long pos0 = v.seg_off[e] + v.head[e] + off;
+        const unsigned long long *src = hashes + call_src[c];
+        for (uint32_t i = lane; i < n; i += 32) {
+            const unsigned long long hsh = src[i], seq = seq0 + i;
+            v.log_hash[pos0 + i] = hsh;
+            v.log_seq[pos0 + i] = seq;
+            EntryRef r = ref_claim(v, hsh, e);
+            if (atomicMax(r.seq, seq) == 0) atomicAdd(&v.live[e], 1u);       // lru.Add of an absent key
+            if (*reinterpret_cast<volatile uint32_t *>(r.in_map) == 0 && atomicExch(r.in_map, 1u) == 0) in_map_new++;
+        }
+    }
+    for (int o = 16; o; o >>= 1) in_map_new += __shfl_xor_sync(0xFFFFFFFFu, in_map_new, o);
+    if (lane == 0 && in_map_new) atomicAdd(&v.ctr[kCtrInMap], (unsigned long long)in_map_new);
+}
+
+// Calls longer than their endpoint's LRU: hash i of the call is evicted BY THE SAME CALL iff at least `cap` distinct
+// hashes follow its last occurrence; indexer.go:76-83 then re-inserts it into the inverted map only (leak bit).
+__global__ void k_store_leak(View v, uint32_t M, const uint32_t *call_ep, const uint32_t *call_n,
+                             const unsigned long long *call_off) {
+    for (uint32_t c = blockIdx.x; c < M; c += gridDim.x) {
+        const uint32_t e = call_ep[c], n = call_n[c];
+        if (e >= v.E || n <= v.cap[e]) continue;                    // uniform across the CTA
+        const uint32_t cap = v.cap[e];
+        const unsigned long long pos0 = v.seg_off[e] + v.head[e] + call_off[c];
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned long long hsh = v.log_hash[pos0 + i];
+            bool last = true;
+            for (uint32_t j = i + 1; j < n && last; j++) last = v.log_hash[pos0 + j] != hsh;
+            if (last) v.log_seq[pos0 + i] |= kTmpBit;
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            if (!(v.log_seq[pos0 + i] & kTmpBit)) continue;
+            uint32_t after = 0;
+            for (uint32_t j = i + 1; j < n && after < cap; j++) after += (v.log_seq[pos0 + j] & kTmpBit) ? 1u : 0u;
+            if (after >= cap) v.log_seq[pos0 + i] |= kLeakBit;
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) v.log_seq[pos0 + i] &= ~kTmpBit;
+        __syncthreads();
+    }
+}
+
+// ---- eviction: per endpoint, drop the oldest live log entries until live <= cap (lru.Add overflow + callback) ----------
+__global__ void k_store_evict(View v) {
+    const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long removed = 0;
+    for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < v.E; e += warps) {
+        const unsigned long long inc = v.inc[e];
+        const unsigned long long head = v.head[e] + inc;
+        const uint32_t cap = v.cap[e], live = v.live[e];
+        __syncwarp();
+        if (lane == 0 && inc) {
+            v.head[e] = head;
+            v.next_seq[e] += inc;
+            v.inc[e] = 0;
+        }
+        if (cap == 0 || live <= cap) continue;
+        uint32_t k = live - cap;
+        const unsigned long long seg = v.seg_off[e];
+        unsigned long long pos = v.tail[e];
+        while (k > 0 && pos < head) {
+            const unsigned long long idx = pos + lane;
+            bool is_live = false, leak = false;
+            EntryRef r{nullptr, nullptr};
+            if (idx < head) {
+                const unsigned long long hsh = v.log_hash[seg + idx], sq = v.log_seq[seg + idx];
+                leak = (sq & kLeakBit) != 0;
+                if (ref_find(v, hsh, e, r)) is_live = *r.seq == (sq & kSeqMask);
+            }
+            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, is_live);
+            const uint32_t rank = __popc(ballot & ((1u << lane) - 1u));
+            const uint32_t n_live = __popc(ballot);
+            if (is_live && rank < k) {
+                *r.seq = 0;                                  // out of the LRU ...
+                if (!leak) {                                 // ... and, through the eviction callback, out of the map
+                    *r.in_map = 0;
+                    removed++;
+                }
+            }
+            if (n_live >= k) {
+                // position right after the k-th live entry of this window
+                uint32_t b = ballot;
+                for (uint32_t q = 1; q < k; q++) b &= b - 1;
+                pos += (uint32_t)__ffs(b);
+                k = 0;
+            } else {
+                k -= n_live;
+                pos += 32;
+            }
+        }
+        if (lane == 0) {
+            v.tail[e] = pos < head ? pos : head;
+            v.live[e] = cap;
+        }
+    }
+    for (int o = 16; o; o >>= 1) removed += __shfl_xor_sync(0xFFFFFFFFu, removed, o);
+    if (lane == 0 && removed) atomicAdd(&v.ctr[kCtrInMap], (unsigned long long)(0ull - removed));
+}
+
+// RemovePod (indexer.go:167-182): every key of the endpoint's LRU goes through the eviction callback, the LRU is
+// deleted (the next Add of the endpoint creates a new one, possibly with another size).
+__global__ void k_store_remove_endpoint(View v, uint32_t e) {
+    const uint32_t lane = threadIdx.x & 31;
+    const unsigned long long head = v.head[e], seg = v.seg_off[e];
+    unsigned long long removed = 0;
+    for (unsigned long long idx = v.tail[e] + lane; idx < head; idx += 32) {
+        EntryRef r;
+        const unsigned long long hsh = v.log_hash[seg + idx], sq = v.log_seq[seg + idx];
+        if (ref_find(v, hsh, e, r) && *r.seq == (sq & kSeqMask) && *r.seq != 0) {
+            *r.seq = 0;
+            *r.in_map = 0;
+            removed++;
+        }
+    }
+    for (int o = 16; o; o >>= 1) removed += __shfl_xor_sync(0xFFFFFFFFu, removed, o);
+    __syncwarp();
+    if (lane == 0) {
+        v.head[e] = 0;
+        v.tail[e] = 0;
+        v.live[e] = 0;
+        v.cap[e] = 0;
+        if (removed) atomicAdd(&v.ctr[kCtrInMap], (unsigned long long)(0ull - removed));
+    }
+}
+
+// ---- housekeeping: log compaction into fresh segments, pair-table rehash ------------------------------------------------
+__global__ void k_store_repack(View v, const unsigned long long *new_off, const unsigned long long *new_cap,
+                               unsigned long long *new_hash, unsigned long long *new_seq) {
+    const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < v.E; e += warps) {
+        const unsigned long long head = v.head[e], seg = v.seg_off[e], dst = new_off[e];
+        unsigned long long w = 0;
+        for (unsigned long long pos = v.tail[e]; pos < head; pos += 32) {
+            const unsigned long long idx = pos + lane;
+            bool is_live = false;
+            unsigned long long hsh = 0, sq = 0;
+            if (idx < head) {
+                hsh = v.log_hash[seg + idx];
+                sq = v.log_seq[seg + idx];
+                EntryRef r;
+                if (ref_find(v, hsh, e, r)) is_live = *r.seq == (sq & kSeqMask) && *r.seq != 0;
+            }
+            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, is_live);
+            if (is_live) {
+                const unsigned long long at = dst + w + __popc(ballot & ((1u << lane) - 1u));
+                new_hash[at] = hsh;
+                new_seq[at] = sq;
+            }
+            w += __popc(ballot);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            v.seg_off[e] = dst;
+            v.seg_cap[e] = new_cap[e];
+            v.head[e] = w;
+            v.tail[e] = 0;
+        }
+    }
+}
+
+__global__ void k_store_count_alive(const StoreEntry *pt, uint64_t capacity, unsigned long long *ctr) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool alive = i < capacity && pt[i].hash != kEmptyKey && (pt[i].seq != 0 || pt[i].in_map != 0);
+    uint32_t b = __ballot_sync(0xFFFFFFFFu, alive);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&ctr[kCtrAlive], (unsigned long long)__popc(b));
+}
+
+__global__ void k_store_rehash(const StoreEntry *old_pt, uint64_t old_capacity, View v) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= old_capacity) return;
+    StoreEntry o = old_pt[i];
+    if (o.hash == kEmptyKey || (o.seq == 0 && o.in_map == 0)) return;       // free slot or tombstone
+    StoreEntry *s = pt_find_or_claim(v, o.hash, o.ep);
+    s->seq = o.seq;
+    s->in_map = o.in_map;
+}
+
+__global__ void k_store_export(View v, uint64_t capacity, unsigned long long *out_hash, uint32_t *out_ep) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    bool take = false;
+    unsigned long long hsh = 0;
+    uint32_t ep = 0;
+    if (i < capacity) {
+        StoreEntry s = v.pt[i];
+        take = s.hash != kEmptyKey && s.in_map != 0;
+        hsh = s.hash;
+        ep = s.ep;
+    } else if (i - capacity < v.E) {                                         // tail threads: the sentinel-hash records
+        ep = (uint32_t)(i - capacity);
+        take = v.sp_in_map[ep] != 0;
+        hsh = kEmptyKey;
+    }
+    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, take);
+    unsigned long long base = 0;
+    if (lane == 0 && ballot) base = atomicAdd(&v.ctr[kCtrCursor], (unsigned long long)__popc(ballot));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (take) {
+        const unsigned long long at = base + __popc(ballot & ((1u << lane) - 1u));
+        out_hash[at] = hsh;
+        out_ep[at] = ep;
+    }
+}
+
+inline unsigned blocks_for(uint64_t n, unsigned per) { return (unsigned)std::max<uint64_t>(1, (n + per - 1) / per); }
+
+}  // namespace
+
+#define ST_TRY(expr)                         \
+    do {                                     \
+        cudaError_t _e = (expr);             \
+        if (_e != cudaSuccess) return _e;    \
+    } while (0)
+
+void IndexStore::fill_view(View &v) const {
+    v.pt = pt_.as<StoreEntry>();
+    v.pt_mask = pt_cap_ ? pt_cap_ - 1 : 0;
+    v.log_hash = log_hash_.as<unsigned long long>();
+    v.log_seq = log_seq_.as<unsigned long long>();
+    v.E = E_;
+    v.default_cap = default_cap_;
+    v.cap = cap_.as<uint32_t>();
+    v.live = live_.as<uint32_t>();
+    v.firstcall = firstcall_.as<uint32_t>();
+    v.sp_in_map = sp_in_map_.as<uint32_t>();
+    v.seg_off = seg_off_.as<unsigned long long>();
+    v.seg_cap = seg_cap_.as<unsigned long long>();
+    v.head = head_.as<unsigned long long>();
+    v.tail = tail_.as<unsigned long long>();
+    v.inc = inc_.as<unsigned long long>();
+    v.next_seq = next_seq_.as<unsigned long long>();
+    v.sp_seq = sp_seq_.as<unsigned long long>();
+    v.ctr = ctr_.as<unsigned long long>();
+}
+
+cudaError_t IndexStore::ensure_init(cudaStream_t s) {
+    if (init_) return cudaSuccess;
+    const size_t E = std::max<uint32_t>(E_, kCtrN);
+    for (DevBuf *b : {&cap_, &live_, &firstcall_, &sp_in_map_}) ST_TRY(b->reserve(sizeof(uint32_t) * E, &bytes_));
+    for (DevBuf *b : {&seg_off_, &seg_cap_, &head_, &tail_, &inc_, &next_seq_, &sp_seq_, &new_off_, &new_cap_})
+        ST_TRY(b->reserve(sizeof(unsigned long long) * E, &bytes_));
+    ST_TRY(ctr_.reserve(sizeof(unsigned long long) * kCtrN, &bytes_));
+    if (!ctr_host_) ST_TRY(cudaHostAlloc(reinterpret_cast<void **>(&ctr_host_), sizeof(unsigned long long) * kCtrN, cudaHostAllocDefault));
+    pt_cap_ = 1024;
+    ST_TRY(pt_.reserve(sizeof(StoreEntry) * pt_cap_, &bytes_));
+    ST_TRY(log_hash_.reserve(sizeof(unsigned long long) * 64, &bytes_));
+    ST_TRY(log_seq_.reserve(sizeof(unsigned long long) * 64, &bytes_));
+    log_cap_ = 0;
+    View v;
+    fill_view(v);
+    k_store_pt_clear<<<blocks_for(pt_cap_, 256), 256, 0, s>>>(v.pt, pt_cap_);
+    k_store_state_clear<<<blocks_for(E, 256), 256, 0, s>>>(v);
+    ST_TRY(cudaGetLastError());
+    init_ = true;
+    in_map_ = 0;
+    pt_used_ = 0;
+    return cudaSuccess;
+}
+
+cudaError_t IndexStore::clear(cudaStream_t s) {
+    if (!init_) return cudaSuccess;
+    ST_TRY(cudaStreamSynchronize(s));
+    init_ = false;
+    used_ = false;
+    dirty_ = true;
+    return ensure_init(s);
+}
+
+// Rebuilds the pair table (dropping tombstones) so that `incoming` more pairs keep the load factor under one half.
+cudaError_t IndexStore::grow_pair_table(uint64_t incoming, cudaStream_t s) {
+    View v;
+    fill_view(v);
+    ST_TRY(cudaMemsetAsync(&v.ctr[kCtrAlive], 0, sizeof(unsigned long long), s));
+    k_store_count_alive<<<blocks_for(pt_cap_, 256), 256, 0, s>>>(v.pt, pt_cap_, v.ctr);
+    ST_TRY(cudaMemcpyAsync(ctr_host_, v.ctr, sizeof(unsigned long long) * kCtrN, cudaMemcpyDeviceToHost, s));
+    ST_TRY(cudaStreamSynchronize(s));
+    const uint64_t alive = ctr_host_[kCtrAlive];
+    uint64_t want = 1024;
+    while (want < (alive + incoming) * 5 / 2) want <<= 1;
+    DevBuf fresh;
+    size_t fresh_bytes = 0;
+    ST_TRY(fresh.reserve(sizeof(StoreEntry) * want, &fresh_bytes));
+    k_store_pt_clear<<<blocks_for(want, 256), 256, 0, s>>>(fresh.as<StoreEntry>(), want);
+    ST_TRY(cudaMemsetAsync(&v.ctr[kCtrPtUsed], 0, sizeof(unsigned long long), s));
+    View nv = v;
+    nv.pt = fresh.as<StoreEntry>();
+    nv.pt_mask = want - 1;
+    k_store_rehash<<<blocks_for(pt_cap_, 256), 256, 0, s>>>(v.pt, pt_cap_, nv);
+    ST_TRY(cudaGetLastError());
+    ST_TRY(cudaStreamSynchronize(s));
+    bytes_ -= pt_.cap;
+    std::swap(pt_.p, fresh.p);
+    std::swap(pt_.cap, fresh.cap);
+    bytes_ += pt_.cap;
+    pt_cap_ = want;
+    pt_used_ = alive;
+    last_launches += 3;
+    last_rehashed = true;
+    return cudaSuccess;
+}
+
+// Moves every endpoint's live log entries, in order, into a fresh segment sized for twice (live + incoming).
+cudaError_t IndexStore::repack_logs(cudaStream_t s) {
+    View v;
+    fill_view(v);
+    std::vector<uint32_t> live(E_), cap(E_);
+    h_inc_.resize(E_);
+    ST_TRY(cudaMemcpyAsync(live.data(), v.live, sizeof(uint32_t) * E_, cudaMemcpyDeviceToHost, s));
+    ST_TRY(cudaMemcpyAsync(cap.data(), v.cap, sizeof(uint32_t) * E_, cudaMemcpyDeviceToHost, s));
+    ST_TRY(cudaMemcpyAsync(h_inc_.data(), v.inc, sizeof(unsigned long long) * E_, cudaMemcpyDeviceToHost, s));
+    ST_TRY(cudaStreamSynchronize(s));
+    h_off_.resize(E_);
+    h_cap_.resize(E_);
+    uint64_t total = 0;
+    for (uint32_t e = 0; e < E_; e++) {
+        uint64_t need = (uint64_t)live[e] + h_inc_[e];
+        uint64_t c = need ? ((2 * need + 64 + 63) & ~63ull) : 0;
+        h_off_[e] = total;
+        h_cap_[e] = c;
+        total += c;
+    }
+    ST_TRY(cudaMemcpyAsync(new_off_.p, h_off_.data(), sizeof(unsigned long long) * E_, cudaMemcpyHostToDevice, s));
+    ST_TRY(cudaMemcpyAsync(new_cap_.p, h_cap_.data(), sizeof(unsigned long long) * E_, cudaMemcpyHostToDevice, s));
+    DevBuf nh, ns;
+    size_t nb = 0;
+    ST_TRY(nh.reserve(sizeof(unsigned long long) * std::max<uint64_t>(total, 64), &nb));
+    ST_TRY(ns.reserve(sizeof(unsigned long long) * std::max<uint64_t>(total, 64), &nb));
+    k_store_repack<<<blocks_for((uint64_t)E_ * 32, 256), 256, 0, s>>>(v, new_off_.as<unsigned long long>(), new_cap_.as<unsigned long long>(),
+                                                                     nh.as<unsigned long long>(), ns.as<unsigned long long>());
+    ST_TRY(cudaGetLastError());
+    ST_TRY(cudaStreamSynchronize(s));
+    bytes_ -= log_hash_.cap + log_seq_.cap;
+    std::swap(log_hash_.p, nh.p);
+    std::swap(log_hash_.cap, nh.cap);
+    std::swap(log_seq_.p, ns.p);
+    std::swap(log_seq_.cap, ns.cap);
+    bytes_ += log_hash_.cap + log_seq_.cap;
+    log_cap_ = total;
+    last_launches += 1;
+    last_repacked = true;
+    return cudaSuccess;
+}
+
+cudaError_t IndexStore::apply(const StoreCalls &calls, cudaStream_t s) {
+    last_launches = 0;
+    last_items = 0;
+    last_repacked = last_rehashed = false;
+    if (calls.M == 0) return cudaSuccess;
+    ST_TRY(ensure_init(s));
+    used_ = true;
+    const uint32_t M = calls.M, n_chunks = (M + kCallChunk - 1) / kCallChunk;
+    const uint64_t hist_n = (uint64_t)n_chunks * E_;
+    ST_TRY(hist_.reserve(sizeof(uint32_t) * hist_n, &bytes_));
+    ST_TRY(off_.reserve(sizeof(unsigned long long) * M, &bytes_));
+    View v;
+    fill_view(v);
+    uint32_t *hist = hist_.as<uint32_t>();
+    unsigned long long *off = off_.as<unsigned long long>();
+    k_store_batch_clear<<<blocks_for(std::max<uint64_t>(hist_n, E_), 256), 256, 0, s>>>(v, hist, hist_n);
+    k_store_hist<<<blocks_for(M, 256), 256, 0, s>>>(v, M, calls.ep, calls.n, hist);
+    k_store_plan<<<blocks_for(E_, 128), 128, 0, s>>>(v, n_chunks, hist, calls.nb);
+    ST_TRY(cudaMemcpyAsync(ctr_host_, v.ctr, sizeof(unsigned long long) * kCtrN, cudaMemcpyDeviceToHost, s));
+    ST_TRY(cudaStreamSynchronize(s));
+    last_launches += 3;
+    const uint64_t total = ctr_host_[kCtrTotalItems];
+    last_items = total;
+    pt_used_ = ctr_host_[kCtrPtUsed];
+    if ((pt_used_ + total) * 2 > pt_cap_) ST_TRY(grow_pair_table(total, s));
+    if (ctr_host_[kCtrNeedRepack]) ST_TRY(repack_logs(s));
+    fill_view(v);
+    if (total) {
+        k_store_offsets<<<n_chunks, kCallChunk, 0, s>>>(v, M, calls.ep, calls.n, hist, off);
+        k_store_upsert<<<blocks_for((uint64_t)M * 32, 256), 256, 0, s>>>(v, M, calls.ep, calls.n,
+                                                                         reinterpret_cast<const unsigned long long *>(calls.src), off,
+                                                                         reinterpret_cast<const unsigned long long *>(calls.hashes));
+        k_store_leak<<<std::min<uint32_t>(M, 592), 256, 0, s>>>(v, M, calls.ep, calls.n, off);
+        k_store_evict<<<blocks_for((uint64_t)E_ * 32, 256), 256, 0, s>>>(v);
+        last_launches += 4;
+    }
+    ST_TRY(cudaMemcpyAsync(ctr_host_, v.ctr, sizeof(unsigned long long) * kCtrN, cudaMemcpyDeviceToHost, s));
+    ST_TRY(cudaStreamSynchronize(s));
+    in_map_ = ctr_host_[kCtrInMap];
+    pt_used_ = ctr_host_[kCtrPtUsed];
+    dirty_ = true;
+    return cudaGetLastError();
+}
+
+cudaError_t IndexStore::apply_picks(const epp_decision *decisions, const uint64_t *hashes, const int32_t *nblocks,
+                                    int64_t R, int32_t max_blocks, cudaStream_t s) {
+    if (R <= 0) return cudaSuccess;
+    const uint32_t M = (uint32_t)(2 * R);
+    ST_TRY(call_ep_.reserve(sizeof(uint32_t) * M, &bytes_));
+    ST_TRY(call_n_.reserve(sizeof(uint32_t) * M, &bytes_));
+    ST_TRY(call_nb_.reserve(sizeof(int32_t) * M, &bytes_));
+    ST_TRY(call_src_.reserve(sizeof(unsigned long long) * M, &bytes_));
+    k_store_calls_from_picks<<<blocks_for((uint64_t)R, 256), 256, 0, s>>>(decisions, nblocks, R, max_blocks, E_, call_ep_.as<uint32_t>(),
+                                                                          call_n_.as<uint32_t>(), call_nb_.as<int32_t>(),
+                                                                          call_src_.as<unsigned long long>());
+    StoreCalls c;
+    c.M = M;
+    c.ep = call_ep_.as<uint32_t>();
+    c.n = call_n_.as<uint32_t>();
+    c.nb = call_nb_.as<int32_t>();
+    c.src = call_src_.as<uint64_t>();
+    c.hashes = hashes;
+    cudaError_t e = apply(c, s);
+    last_launches += 1;
+    return e;
+}
+
+cudaError_t IndexStore::remove_endpoint(uint32_t ep, cudaStream_t s) {
+    if (ep >= E_ || !init_) return cudaSuccess;
+    View v;
+    fill_view(v);
+    k_store_remove_endpoint<<<1, 32, 0, s>>>(v, ep);
+    ST_TRY(cudaMemcpyAsync(ctr_host_, v.ctr, sizeof(unsigned long long) * kCtrN, cudaMemcpyDeviceToHost, s));
+    ST_TRY(cudaStreamSynchronize(s));
+    in_map_ = ctr_host_[kCtrInMap];
+    dirty_ = true;
+    return cudaGetLastError();
+}
+
+cudaError_t IndexStore::export_pairs(DevBuf &pair_hash, DevBuf &pair_ep, uint64_t *n_pairs, size_t *accounted,
+                                     cudaStream_t s) {
+    *n_pairs = 0;
+    if (!init_) return cudaSuccess;
+    View v;
+    fill_view(v);
+    ST_TRY(pair_hash.reserve(sizeof(uint64_t) * std::max<uint64_t>(in_map_, 1), accounted));
+    ST_TRY(pair_ep.reserve(sizeof(uint32_t) * std::max<uint64_t>(in_map_, 1), accounted));
+    ST_TRY(cudaMemsetAsync(&v.ctr[kCtrCursor], 0, sizeof(unsigned long long), s));
+    k_store_export<<<blocks_for(pt_cap_ + E_, 256), 256, 0, s>>>(v, pt_cap_, pair_hash.as<unsigned long long>(), pair_ep.as<uint32_t>());
+    ST_TRY(cudaMemcpyAsync(ctr_host_, v.ctr, sizeof(unsigned long long) * kCtrN, cudaMemcpyDeviceToHost, s));
+    ST_TRY(cudaStreamSynchronize(s));
+    *n_pairs = ctr_host_[kCtrCursor];
+    return cudaGetLastError();
+}
+
+}  // namespace epp

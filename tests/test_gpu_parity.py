@@ -204,9 +204,9 @@ def test_hash_truncation_and_short(epp, orc):
 
 
 # ------------------------------------------------------------------------------------------------
-# a2 index (write side mirror + device table)
+# a2 index (write side: HBM-resident LRU store; read side: device table)
 # ------------------------------------------------------------------------------------------------
-def test_index_mirror_vs_oracle_indexer(epp, orc):
+def test_index_store_vs_oracle_indexer(epp, orc):
     rng = random.Random(5)
     with epp.Engine(16, lru_capacity_per_server=5) as eng:
         ix = orc.Indexer(5)
@@ -224,6 +224,81 @@ def test_index_mirror_vs_oracle_indexer(epp, orc):
             if step % 100 == 99:
                 for h in range(60):
                     assert eng.index_get(h) == ix.get(h), (step, h)
+
+
+@pytest.mark.parametrize("seed,n_srv,universe,default_cap", [(11, 6, 90, 5), (12, 40, 4000, 64), (13, 3, 40, 1)])
+def test_index_store_batched_adds_vs_oracle(epp, orc, seed, n_srv, universe, default_cap):
+    """indexer.Add / RemovePod applied to the device store in LARGE batches (thousands of queued calls, several calls per
+    endpoint and chunk, duplicates inside and across calls, calls longer than the LRU, the all-ones hash) must leave
+    exactly the inverted map the reference leaves after running the same calls one by one."""
+    rng = random.Random(seed)
+    ALL1 = 0xFFFFFFFFFFFFFFFF
+
+    def hash_of(k):
+        return ALL1 if k == 0 else (k * 0x9E3779B97F4A7C15) & ALL1
+
+    with epp.Engine(64, lru_capacity_per_server=default_cap) as eng:
+        ix = orc.Indexer(default_cap)
+        for rnd in range(6):
+            for _ in range(rng.choice([1, 700, 2600])):
+                srv = rng.randrange(n_srv)
+                n = rng.choice([0, 1, 2, 5, 9, 17, 70]) if default_cap <= 5 else rng.randint(0, 96)
+                base = rng.randrange(universe)
+                hs = [hash_of((base + (j if rng.random() < 0.8 else rng.randrange(universe))) % universe) for j in range(n)]
+                cap = rng.choice([0, 0, 3, 7, 33])
+                eng.index_add(srv, hs, cap)
+                ix.add(hs, srv, cap)
+                if rng.random() < 0.002:
+                    eng.index_remove_endpoint(srv)
+                    ix.remove_pod(srv)
+            for k in range(universe):
+                assert eng.index_get(hash_of(k)) == ix.get(hash_of(k)), (rnd, k)
+            assert eng.stats()["index_pairs"] == len(ix.export()[0])
+
+
+def test_index_add_picked_many_batches_vs_oracle(epp, orc, tg):
+    """PreRequest at batch rate: after every scheduled batch the picks (and prefill picks) are indexed ON THE DEVICE;
+    the next batch's decisions must equal the oracle's, whose indexer ran the same Adds one request at a time.  LRU
+    capacity is far below the working set, so every batch evicts."""
+    import torch
+    import helpers
+    w = tg.baseline_configs()["config4"].scaled(E=48, R=640, T=1024, name="config4")
+    w.non_cached_tokens = 128
+    trace = tg.Trace(w)
+    role, kv, waiting, running = trace.pool()
+    lru = 150
+    pool = orc.PoolState(role, kv, waiting, running)
+    ix = orc.Indexer(lru)
+    primary = orc.make_profile(w.primary_filter, list(w.primary_scorers))
+    prefill = orc.make_profile(tg.FILTER_PREFILL, list(w.prefill_scorers))
+    with helpers.make_engine(w, lru_capacity_per_server=lru) as eng:
+        eng.register_model(tg.MODEL)
+        eng.pool_set(np.arange(w.E, dtype=np.uint32), role, kv, waiting, running)
+        seen_prefill = 0
+        for b in range(5):
+            tokens, _, _ = trace.requests(b * w.R, w.R)
+            odec, ototal = helpers.oracle_decisions(orc, w, pool, ix, primary, prefill, tokens)
+            if b % 2 == 0:
+                dt = torch.from_numpy(tokens.view(np.int32)).cuda()
+                ddec, ddet = eng.schedule(dt, uniform_len=w.prompt_bytes, keep_hashes=True)
+                dec = epp.decisions_from_torch(ddec)
+                det = ddet.cpu().numpy().view(epp.DETAIL_DTYPE).reshape(-1)
+            else:
+                dec, det = eng.schedule(tokens, uniform_len=w.prompt_bytes, keep_hashes=True)
+            helpers.assert_decisions_equal(dec, det, odec, ototal, where=f"batch {b}")
+            eng.index_add_picked()
+            for r in range(w.R):                                       # plugin.go:164-200, one request at a time
+                if odec["status"][r] != 0:
+                    continue
+                hs = orc.hash_prompt(tokens[r].tobytes(), tg.MODEL, w.block_size_tokens, w.max_prefix_blocks)
+                ix.add(hs, int(odec["pick"][r]))
+                if odec["prefill_pick"][r] >= 0:
+                    ix.add(hs, int(odec["prefill_pick"][r]))
+                    seen_prefill += 1
+            assert (dec["match_blocks"] > 0).any() or b == 0
+        assert seen_prefill > 0
+        eng.index_commit()
+        assert eng.stats()["index_pairs"] == len(ix.export()[0])
 
 
 def test_index_kats(epp):
