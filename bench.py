@@ -241,6 +241,67 @@ def run_reference(args, rank, world):
     }), flush=True)
 
 
+def index_write_leg(args, w, trace, dev_tokens, dev_dec, local_rank, epp, helpers, orc_mod):
+    """SURVEY 8(f).1 -- PreRequest at batch rate: schedule a batch, index its picks ON THE DEVICE (indexer.Add + LRU
+    eviction for 65 536 x 256 hashes), rebuild the read table.  The engine's index is seeded through indexer.Add (not a
+    snapshot), LRU capacity is the reference default (31 250 per endpoint).  The CPU number beside it is the oracle's
+    indexer (one mutex, like indexer.go) applying a bounded sample of the same Adds."""
+    import torch
+    from tools import tracegen as tg
+    eng = helpers.make_engine(w, device=local_rank)
+    eng.register_model(tg.MODEL)
+    role, kv, waiting, running = trace.pool()
+    eng.pool_set(np.arange(w.E, dtype=np.uint32), role, kv, waiting, running)
+    fh, _ = eng.hash_prompts(trace.family_tokens(), uniform_len=w.prompt_bytes)
+    hs, es = trace.index_pairs(fh)
+    order = np.argsort(es, kind="stable")
+    hs, es = hs[order], es[order]
+    cuts = np.flatnonzero(np.diff(es)) + 1
+    for seg_h, seg_e in zip(np.split(hs, cuts), np.split(es, cuts)):
+        if len(seg_e):
+            eng.index_add(int(seg_e[0]), seg_h)
+    eng.index_commit()
+    cycles = []
+    R = w.R
+    for k in range(3):
+        eng.schedule(dev_tokens, uniform_len=w.prompt_bytes, detail=False, out=dev_dec, keep_hashes=True)
+        t0 = time.perf_counter()
+        eng.index_add_picked()
+        eng.index_commit()
+        wall = time.perf_counter() - t0
+        st = eng.stats()
+        cycles.append({"apply_ms": st["last_index_apply_ms"], "build_ms": st["last_index_build_ms"], "wall_ms": wall * 1e3,
+                       "hashes_added": int(st["last_index_items"]), "pairs_after": int(st["index_pairs"])})
+    last = cycles[-1]
+    out = {"what": "epp_index_add_picked + epp_index_commit after a config-3 batch (65 536 picks x up to 256 block hashes)",
+           "cycles": cycles, "adds_per_s": last["hashes_added"] / (last["apply_ms"] * 1e-3),
+           "adds_per_s_incl_read_table_build": last["hashes_added"] / (last["wall_ms"] * 1e-3),
+           "kernels_per_apply": int(eng.stats()["last_index_launches"]),
+           "store_device_bytes": int(eng.stats()["device_bytes"])}
+    # CPU: the oracle's indexer applying the Adds of the first requests of the same batch to the same seeded index
+    if orc_mod is not None:
+        ix = orc_mod.Indexer()
+        for seg_h, seg_e in zip(np.split(hs, cuts), np.split(es, cuts)):
+            if len(seg_e):
+                ix.add(seg_h, int(seg_e[0]))
+        dec = epp.decisions_from_torch(dev_dec)
+        n_s = min(R, 8192)
+        hh, nb = eng.hash_prompts(dev_tokens[:n_s], uniform_len=w.prompt_bytes)
+        hh = hh.cpu().numpy().view(np.uint64) if hasattr(hh, "cpu") else hh
+        nb = nb.cpu().numpy() if hasattr(nb, "cpu") else nb
+        t0 = time.perf_counter()
+        tot = 0
+        for r in range(n_s):
+            if dec["status"][r] == 0:
+                ix.add(hh[r, : nb[r]], int(dec["pick"][r]))
+                tot += int(nb[r])
+        dt = time.perf_counter() - t0
+        out["cpu_adds_per_s"] = tot / dt
+        out["cpu_sample"] = f"oracle indexer (C port of indexer.go Add + golang-lru), 1 thread, Adds of the first {n_s} requests"
+    eng.close()
+    return out
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -376,6 +437,14 @@ def run_gpu(args, rank, world, local_rank):
         n_threads = os.cpu_count() or 1
         os.sched_setaffinity(0, all_cpus)            # the CPU leg gets every host core again
         cpu, _ = cpu_baseline(w, trace, n_threads, tokens=host_tokens) if not args.no_cpu else ({"value": None}, None)
+        index_write = None
+        if world == 1 and not args.no_index_write:
+            try:
+                from oracle import pyoracle as _orc
+                _orc.build()
+            except Exception:
+                _orc = None
+            index_write = index_write_leg(args, w, trace, dev_tokens, dev_dec, local_rank, epp, helpers, None if args.no_cpu else _orc)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": timed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -396,6 +465,7 @@ def run_gpu(args, rank, world, local_rank):
                          "algorithmic_bytes_per_launch": int(token_bytes),
                          "launch_ms": dom_ms},
             "cpu_baseline": cpu,
+            "index_write": index_write,
             "index": {"pairs": st0["index_pairs"], "slots": st0["index_slots"], "probes_per_step": int(probes),
                       "postings_per_step": int(postings)},
         }
@@ -504,6 +574,7 @@ def main():
     ap.add_argument("--workload", default="config3", choices=["config1", "config2", "config3", "config4", "config5"])
     ap.add_argument("--requests", type=int, default=0, help="override the batch size R (0 = the config's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-index-write", action="store_true", help="skip the index write-side leg (SURVEY 8(f).1)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs only)")
     ap.add_argument("--pitch-pad", type=int, default=0,
                     help="experiment: lay the device-resident prompts out with this many pad bytes between requests")

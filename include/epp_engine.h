@@ -187,6 +187,11 @@ typedef struct {
     /* algorithmic work of the last batch: table probes P = sum_r min(stop_r+1, B_r) and
      * postings consumed M = sum_r sum_{i<stop_r} |servers(h_i)| */
     uint64_t last_probes, last_postings;
+    /* write side (index_store.cu): the last epp_index_add_picked / queued-Add flush and the last read-table build */
+    double last_index_apply_ms;        /* Add + eviction kernels incl. their two small read-backs (host clock)   */
+    double last_index_build_ms;        /* export of the inverted map + bulk build of the read table (host clock) */
+    uint64_t last_index_items;         /* hashes added by the last applied batch                               */
+    uint64_t last_index_launches;      /* kernels launched by it                                               */
 } epp_stats;
 
 /* ---- lifecycle --------------------------------------------------------------------------------- */

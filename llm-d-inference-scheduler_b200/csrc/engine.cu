@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -487,14 +488,20 @@ static int32_t flush_add_queue(epp_engine *h) {
     return EPP_OK;
 }
 
+static double ms_since(std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
 static int32_t commit_locked(epp_engine *h) {
     if (h->snapshot_mode) return EPP_OK;
     EPP_TRY(flush_add_queue(h));
     if (!h->store->dirty()) return EPP_OK;
+    auto t0 = std::chrono::steady_clock::now();
     uint64_t n = 0;
     CUDA_TRY(h->store->export_pairs(h->pair_hash, h->pair_ep, &n, &h->dev_bytes, h->slot[0].stream));
     EPP_TRY(build_index_from_device_pairs(h, n, n));
     h->store->mark_clean();
+    h->stats.last_index_build_ms = ms_since(t0);
     return EPP_OK;
 }
 
@@ -973,8 +980,12 @@ extern "C" int32_t epp_index_add_picked(epp_engine *h) {
     if (h->kept_R == 0) return fail(EPP_ERR_STATE, "no batch kept (call epp_schedule with keep_hashes=1 first)");
     if (h->snapshot_mode) return fail(EPP_ERR_STATE, "index holds a bulk snapshot; incremental adds need an incrementally built index");
     EPP_TRY(flush_add_queue(h));
+    auto t0 = std::chrono::steady_clock::now();
     CUDA_TRY(h->store->apply_picks(h->kept_dec.as<epp_decision>(), h->hashes.as<uint64_t>(), h->nblocks.as<int32_t>(), h->kept_R,
                                    h->cfg.max_prefix_blocks, h->slot[0].stream));
+    h->stats.last_index_apply_ms = ms_since(t0);
+    h->stats.last_index_items = h->store->last_items;
+    h->stats.last_index_launches = (uint64_t)h->store->last_launches;
     h->kept_R = 0;
     return EPP_OK;
 }

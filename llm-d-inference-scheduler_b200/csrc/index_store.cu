@@ -2,6 +2,9 @@
 #include "index_store.h"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <utility>
 
 namespace epp {
 
@@ -32,7 +35,7 @@ struct IndexStore::View {
     uint32_t E;
     int32_t default_cap;
     uint32_t *cap, *live, *firstcall, *sp_in_map;
-    unsigned long long *seg_off, *seg_cap, *head, *tail, *inc, *next_seq, *sp_seq;
+    unsigned long long *seg_off, *seg_cap, *head, *tail, *inc, *next_seq, *sp_seq, *cut;
     unsigned long long *ctr;
 };
 
@@ -133,6 +136,7 @@ __global__ void k_store_state_clear(View v) {
         v.inc[e] = 0;
         v.next_seq[e] = 1;
         v.sp_seq[e] = 0;
+        v.cut[e] = 0;
     }
     if (e < kCtrN) v.ctr[e] = 0;
 }
@@ -195,10 +199,7 @@ __global__ void k_store_plan(View v, uint32_t n_chunks, uint32_t *hist, const in
         int32_t c = nb > 0 ? nb : v.default_cap;
         v.cap[e] = c > 0 ? (uint32_t)c : 1u;
     }
-    if (run) {
-        atomicAdd(&v.ctr[kCtrTotalItems], run);
-        if (v.head[e] + run > v.seg_cap[e]) atomicOr(&v.ctr[kCtrNeedRepack], 1ull);
-    }
+    if (run) atomicAdd(&v.ctr[kCtrTotalItems], run);
 }
 
 __global__ void __launch_bounds__(kCallChunk) k_store_offsets(View v, uint32_t M, const uint32_t *call_ep,
@@ -226,6 +227,7 @@ __global__ void k_store_upsert(View v, uint32_t M, const uint32_t *call_ep, cons
     for (uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < M; c += warps) {
         const uint32_t e = call_ep[c], n = call_n[c];
         if (e >= v.E || n == 0) continue;
+        uint32_t live_new = 0;
         const unsigned long long off = call_off[c];
         const unsigned long long seq0 = v.next_seq[e] + off;
         const unsigned long long pos0 = v.seg_off[e] + v.head[e] + off;
@@ -235,9 +237,11 @@ __global__ void k_store_upsert(View v, uint32_t M, const uint32_t *call_ep, cons
             v.log_hash[pos0 + i] = hsh;
             v.log_seq[pos0 + i] = seq;
             EntryRef r = ref_claim(v, hsh, e);
-            if (atomicMax(r.seq, seq) == 0) atomicAdd(&v.live[e], 1u);       // lru.Add of an absent key
+            if (atomicMax(r.seq, seq) == 0) live_new++;                      // lru.Add of an absent key
             if (*reinterpret_cast<volatile uint32_t *>(r.in_map) == 0 && atomicExch(r.in_map, 1u) == 0) in_map_new++;
         }
+        for (int o = 16; o; o >>= 1) live_new += __shfl_xor_sync(0xFFFFFFFFu, live_new, o);
+        if (lane == 0 && live_new) atomicAdd(&v.live[e], live_new);
     }
     for (int o = 16; o; o >>= 1) in_map_new += __shfl_xor_sync(0xFFFFFFFFu, in_map_new, o);
     if (lane == 0 && in_map_new) atomicAdd(&v.ctr[kCtrInMap], (unsigned long long)in_map_new);
@@ -272,60 +276,173 @@ __global__ void k_store_leak(View v, uint32_t M, const uint32_t *call_ep, const 
 }
 
 // ---- eviction: per endpoint, drop the oldest live log entries until live <= cap (lru.Add overflow + callback) ----------
-__global__ void k_store_evict(View v) {
+// A skewed batch can append millions of entries to ONE endpoint, so the walk from the tail is spread over CTAs:
+//   k_evict_count  live entries per 256-entry block of every over-full endpoint's log window
+//   k_evict_cut    per endpoint: the position right after the k-th oldest live entry (k = live - cap)
+//   k_evict_apply  every live entry before the cut leaves the LRU (and the inverted map, unless it leaked)
+//   k_evict_finish tail / live bookkeeping
+constexpr int kEvictBlock = 256;
+
+__device__ __forceinline__ bool log_entry_live(const View &v, uint32_t e, unsigned long long at, EntryRef &r, bool &leak) {
+    const unsigned long long hsh = v.log_hash[at], sq = v.log_seq[at];
+    leak = (sq & kLeakBit) != 0;
+    return ref_find(v, hsh, e, r) && *r.seq == (sq & kSeqMask) && *r.seq != 0;
+}
+
+// Folds the batch into the endpoint's counters (head, next_seq) -- runs once per batch before the eviction kernels.
+__global__ void k_store_advance(View v) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= v.E) return;
+    const unsigned long long inc = v.inc[e];
+    if (inc) {
+        v.head[e] += inc;
+        v.next_seq[e] += inc;
+        v.inc[e] = 0;
+    }
+    v.cut[e] = v.tail[e];
+}
+
+__global__ void __launch_bounds__(kEvictBlock) k_evict_count(View v, uint32_t *blockcnt) {
+    for (uint32_t e = blockIdx.y; e < v.E; e += gridDim.y) {
+    const uint32_t cap = v.cap[e], live = v.live[e];
+    if (cap == 0 || live <= cap) continue;
+    const unsigned long long seg = v.seg_off[e], tail = v.tail[e], head = v.head[e];
+    const unsigned long long b0 = tail / kEvictBlock, b1 = (head + kEvictBlock - 1) / kEvictBlock;
+    for (unsigned long long b = b0 + blockIdx.x; b < b1; b += gridDim.x) {
+        const unsigned long long idx = b * kEvictBlock + threadIdx.x;
+        bool is_live = false, leak;
+        EntryRef r;
+        if (idx >= tail && idx < head) is_live = log_entry_live(v, e, seg + idx, r, leak);
+        const int n = __syncthreads_count(is_live);
+        if (threadIdx.x == 0) blockcnt[seg / kEvictBlock + b] = (uint32_t)n;
+    }
+    }
+}
+
+__global__ void k_evict_cut(View v, const uint32_t *blockcnt) {
     const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
-    unsigned long long removed = 0;
     for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < v.E; e += warps) {
-        const unsigned long long inc = v.inc[e];
-        const unsigned long long head = v.head[e] + inc;
         const uint32_t cap = v.cap[e], live = v.live[e];
-        __syncwarp();
-        if (lane == 0 && inc) {
-            v.head[e] = head;
-            v.next_seq[e] += inc;
-            v.inc[e] = 0;
-        }
         if (cap == 0 || live <= cap) continue;
-        uint32_t k = live - cap;
-        const unsigned long long seg = v.seg_off[e];
-        unsigned long long pos = v.tail[e];
-        while (k > 0 && pos < head) {
-            const unsigned long long idx = pos + lane;
-            bool is_live = false, leak = false;
-            EntryRef r{nullptr, nullptr};
-            if (idx < head) {
-                const unsigned long long hsh = v.log_hash[seg + idx], sq = v.log_seq[seg + idx];
-                leak = (sq & kLeakBit) != 0;
-                if (ref_find(v, hsh, e, r)) is_live = *r.seq == (sq & kSeqMask);
+        unsigned long long k = live - cap;
+        const unsigned long long seg = v.seg_off[e], tail = v.tail[e], head = v.head[e];
+        const unsigned long long b0 = tail / kEvictBlock, b1 = (head + kEvictBlock - 1) / kEvictBlock;
+        // 1. the block holding the k-th oldest live entry
+        unsigned long long b = b0;
+        bool found = false;
+        while (b < b1 && !found) {
+            const unsigned long long mine = b + lane;
+            const uint32_t c = mine < b1 ? blockcnt[seg / kEvictBlock + mine] : 0u;
+            uint32_t incl = c;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= (uint32_t)o) incl += t;
             }
-            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, is_live);
-            const uint32_t rank = __popc(ballot & ((1u << lane) - 1u));
-            const uint32_t n_live = __popc(ballot);
-            if (is_live && rank < k) {
-                *r.seq = 0;                                  // out of the LRU ...
-                if (!leak) {                                 // ... and, through the eviction callback, out of the map
-                    *r.in_map = 0;
-                    removed++;
+            const uint32_t hit = __ballot_sync(0xFFFFFFFFu, incl >= k);
+            if (hit) {
+                const int l = __ffs(hit) - 1;
+                const uint32_t before = __shfl_sync(0xFFFFFFFFu, incl - c, l);
+                k -= before;
+                b += l;
+                found = true;
+            } else {
+                k -= __shfl_sync(0xFFFFFFFFu, incl, 31);
+                b += 32;
+            }
+        }
+        unsigned long long pos = head;
+        if (found) {
+            // 2. inside that block: right after its k-th live entry
+            pos = b * kEvictBlock;
+            for (int w = 0; w < kEvictBlock / 32 && k > 0; w++) {
+                const unsigned long long idx = pos + lane;
+                bool is_live = false, leak;
+                EntryRef r;
+                if (idx >= tail && idx < head) is_live = log_entry_live(v, e, seg + idx, r, leak);
+                const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, is_live);
+                const uint32_t n_live = __popc(ballot);
+                if (n_live >= k) {
+                    uint32_t bb = ballot;
+                    for (uint32_t q = 1; q < k; q++) bb &= bb - 1;
+                    pos += (uint32_t)__ffs(bb);
+                    k = 0;
+                } else {
+                    k -= n_live;
+                    pos += 32;
                 }
             }
-            if (n_live >= k) {
-                // position right after the k-th live entry of this window
-                uint32_t b = ballot;
-                for (uint32_t q = 1; q < k; q++) b &= b - 1;
-                pos += (uint32_t)__ffs(b);
-                k = 0;
-            } else {
-                k -= n_live;
-                pos += 32;
+        }
+        if (lane == 0) v.cut[e] = pos < head ? pos : head;
+    }
+}
+
+__global__ void __launch_bounds__(kEvictBlock) k_evict_apply(View v) {
+    unsigned long long removed = 0;
+    for (uint32_t e = blockIdx.y; e < v.E; e += gridDim.y) {
+    const unsigned long long tail = v.tail[e], cut = v.cut[e];
+    if (cut <= tail) continue;
+    const unsigned long long seg = v.seg_off[e];
+    for (unsigned long long idx = tail + (unsigned long long)blockIdx.x * kEvictBlock + threadIdx.x; idx < cut;
+         idx += (unsigned long long)gridDim.x * kEvictBlock) {
+        bool leak;
+        EntryRef r;
+        if (log_entry_live(v, e, seg + idx, r, leak)) {
+            *r.seq = 0;                                  // out of the LRU ...
+            if (!leak) {                                 // ... and, through the eviction callback, out of the map
+                *r.in_map = 0;
+                removed++;
             }
         }
-        if (lane == 0) {
-            v.tail[e] = pos < head ? pos : head;
-            v.live[e] = cap;
-        }
+    }
     }
     for (int o = 16; o; o >>= 1) removed += __shfl_xor_sync(0xFFFFFFFFu, removed, o);
-    if (lane == 0 && removed) atomicAdd(&v.ctr[kCtrInMap], (unsigned long long)(0ull - removed));
+    if ((threadIdx.x & 31) == 0 && removed) atomicAdd(&v.ctr[kCtrInMap], (unsigned long long)(0ull - removed));
+}
+
+__global__ void k_evict_finish(View v) {
+    uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= v.E) return;
+    if (v.cut[e] > v.tail[e]) {
+        v.tail[e] = v.cut[e];
+        v.live[e] = v.cap[e];
+    }
+}
+
+// In-place compaction of one endpoint's log window to the start of its segment (keeps order; writes trail reads).
+// Runs for the endpoints whose segment cannot take the batch's appends; if that is still not enough the host
+// re-allocates every segment (k_store_repack).
+__global__ void k_store_compact(View v) {
+    const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < v.E; e += warps) {
+        const unsigned long long inc = v.inc[e], head = v.head[e], cap = v.seg_cap[e], seg = v.seg_off[e];
+        if (inc == 0 || head + inc <= cap) continue;
+        unsigned long long w = 0;
+        for (unsigned long long pos = v.tail[e]; pos < head; pos += 32) {
+            const unsigned long long idx = pos + lane;
+            bool is_live = false, leak;
+            unsigned long long hsh = 0, sq = 0;
+            if (idx < head) {
+                hsh = v.log_hash[seg + idx];
+                sq = v.log_seq[seg + idx];
+                EntryRef r;
+                is_live = log_entry_live(v, e, seg + idx, r, leak);
+            }
+            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, is_live);
+            __syncwarp();
+            if (is_live) {
+                const unsigned long long at = seg + w + __popc(ballot & ((1u << lane) - 1u));
+                v.log_hash[at] = hsh;
+                v.log_seq[at] = sq;
+            }
+            __syncwarp();
+            w += __popc(ballot);
+        }
+        if (lane == 0) {
+            v.head[e] = w;
+            v.tail[e] = 0;
+            if (w + inc > cap) atomicOr(&v.ctr[kCtrNeedRepack], 1ull);
+        }
+    }
 }
 
 // RemovePod (indexer.go:167-182): every key of the endpoint's LRU goes through the eviction callback, the LRU is
@@ -461,6 +578,7 @@ void IndexStore::fill_view(View &v) const {
     v.inc = inc_.as<unsigned long long>();
     v.next_seq = next_seq_.as<unsigned long long>();
     v.sp_seq = sp_seq_.as<unsigned long long>();
+    v.cut = cut_.as<unsigned long long>();
     v.ctr = ctr_.as<unsigned long long>();
 }
 
@@ -468,7 +586,7 @@ cudaError_t IndexStore::ensure_init(cudaStream_t s) {
     if (init_) return cudaSuccess;
     const size_t E = std::max<uint32_t>(E_, kCtrN);
     for (DevBuf *b : {&cap_, &live_, &firstcall_, &sp_in_map_}) ST_TRY(b->reserve(sizeof(uint32_t) * E, &bytes_));
-    for (DevBuf *b : {&seg_off_, &seg_cap_, &head_, &tail_, &inc_, &next_seq_, &sp_seq_, &new_off_, &new_cap_})
+    for (DevBuf *b : {&seg_off_, &seg_cap_, &head_, &tail_, &inc_, &next_seq_, &sp_seq_, &new_off_, &new_cap_, &cut_})
         ST_TRY(b->reserve(sizeof(unsigned long long) * E, &bytes_));
     ST_TRY(ctr_.reserve(sizeof(unsigned long long) * kCtrN, &bytes_));
     if (!ctr_host_) ST_TRY(cudaHostAlloc(reinterpret_cast<void **>(&ctr_host_), sizeof(unsigned long long) * kCtrN, cudaHostAllocDefault));
@@ -545,7 +663,7 @@ cudaError_t IndexStore::repack_logs(cudaStream_t s) {
     uint64_t total = 0;
     for (uint32_t e = 0; e < E_; e++) {
         uint64_t need = (uint64_t)live[e] + h_inc_[e];
-        uint64_t c = need ? ((2 * need + 64 + 63) & ~63ull) : 0;
+        uint64_t c = need ? ((2 * need + 256 + 255) & ~255ull) : 0;      // whole eviction blocks
         h_off_[e] = total;
         h_cap_[e] = c;
         total += c;
@@ -572,7 +690,35 @@ cudaError_t IndexStore::repack_logs(cudaStream_t s) {
     return cudaSuccess;
 }
 
+namespace {
+// EPP_STORE_TIMING=1: per-kernel CUDA-event times of every apply() on stderr (profiling aid).
+struct StoreTimer {
+    bool on;
+    cudaStream_t s;
+    std::vector<std::pair<const char *, cudaEvent_t>> marks;
+    explicit StoreTimer(cudaStream_t st) : on(getenv("EPP_STORE_TIMING") != nullptr), s(st) { mark("start"); }
+    void mark(const char *name) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        marks.emplace_back(name, e);
+    }
+    ~StoreTimer() {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        for (size_t i = 1; i < marks.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            fprintf(stderr, "[store] %-10s %8.3f ms\n", marks[i].first, ms);
+        }
+        for (auto &m : marks) cudaEventDestroy(m.second);
+    }
+};
+}  // namespace
+
 cudaError_t IndexStore::apply(const StoreCalls &calls, cudaStream_t s) {
+    StoreTimer tm(s);
     last_launches = 0;
     last_items = 0;
     last_repacked = last_rehashed = false;
@@ -590,23 +736,39 @@ cudaError_t IndexStore::apply(const StoreCalls &calls, cudaStream_t s) {
     k_store_batch_clear<<<blocks_for(std::max<uint64_t>(hist_n, E_), 256), 256, 0, s>>>(v, hist, hist_n);
     k_store_hist<<<blocks_for(M, 256), 256, 0, s>>>(v, M, calls.ep, calls.n, hist);
     k_store_plan<<<blocks_for(E_, 128), 128, 0, s>>>(v, n_chunks, hist, calls.nb);
+    tm.mark("plan");
+    k_store_compact<<<blocks_for((uint64_t)E_ * 32, 256), 256, 0, s>>>(v);
+    tm.mark("compact");
     ST_TRY(cudaMemcpyAsync(ctr_host_, v.ctr, sizeof(unsigned long long) * kCtrN, cudaMemcpyDeviceToHost, s));
     ST_TRY(cudaStreamSynchronize(s));
-    last_launches += 3;
+    last_launches += 4;
     const uint64_t total = ctr_host_[kCtrTotalItems];
     last_items = total;
     pt_used_ = ctr_host_[kCtrPtUsed];
     if ((pt_used_ + total) * 2 > pt_cap_) ST_TRY(grow_pair_table(total, s));
     if (ctr_host_[kCtrNeedRepack]) ST_TRY(repack_logs(s));
     fill_view(v);
+    tm.mark("grow");
     if (total) {
         k_store_offsets<<<n_chunks, kCallChunk, 0, s>>>(v, M, calls.ep, calls.n, hist, off);
+        tm.mark("offsets");
         k_store_upsert<<<blocks_for((uint64_t)M * 32, 256), 256, 0, s>>>(v, M, calls.ep, calls.n,
                                                                          reinterpret_cast<const unsigned long long *>(calls.src), off,
                                                                          reinterpret_cast<const unsigned long long *>(calls.hashes));
+        tm.mark("upsert");
         k_store_leak<<<std::min<uint32_t>(M, 592), 256, 0, s>>>(v, M, calls.ep, calls.n, off);
-        k_store_evict<<<blocks_for((uint64_t)E_ * 32, 256), 256, 0, s>>>(v);
-        last_launches += 4;
+        ST_TRY(blockcnt_.reserve(sizeof(uint32_t) * (log_cap_ / kEvictBlock + 1), &bytes_));
+        tm.mark("leak");
+        k_store_advance<<<blocks_for(E_, 256), 256, 0, s>>>(v);
+        const dim3 eg(64, std::min<uint32_t>(E_, 65535u));
+        k_evict_count<<<eg, kEvictBlock, 0, s>>>(v, blockcnt_.as<uint32_t>());
+        tm.mark("ev_count");
+        k_evict_cut<<<blocks_for((uint64_t)E_ * 32, 256), 256, 0, s>>>(v, blockcnt_.as<uint32_t>());
+        tm.mark("ev_cut");
+        k_evict_apply<<<eg, kEvictBlock, 0, s>>>(v);
+        k_evict_finish<<<blocks_for(E_, 256), 256, 0, s>>>(v);
+        tm.mark("ev_apply");
+        last_launches += 8;
     }
     ST_TRY(cudaMemcpyAsync(ctr_host_, v.ctr, sizeof(unsigned long long) * kCtrN, cudaMemcpyDeviceToHost, s));
     ST_TRY(cudaStreamSynchronize(s));

@@ -81,7 +81,7 @@ class IndexStore {
     uint64_t pt_cap_ = 0, log_cap_ = 0, in_map_ = 0, pt_used_ = 0;
     DevBuf pt_, log_hash_, log_seq_;
     DevBuf cap_, live_, firstcall_, seg_off_, seg_cap_, head_, tail_, inc_, next_seq_, sp_seq_, sp_in_map_, ctr_;
-    DevBuf hist_, off_, new_off_, new_cap_;
+    DevBuf hist_, off_, new_off_, new_cap_, cut_, blockcnt_;
     DevBuf call_ep_, call_n_, call_nb_, call_src_;
     std::vector<uint64_t> h_live_, h_inc_, h_off_, h_cap_;
     unsigned long long *ctr_host_ = nullptr;   // pinned
