@@ -221,10 +221,13 @@ EPP_API int32_t epp_pool_set(epp_engine *h, int32_t n, const uint32_t *ids, cons
                      const int32_t *waiting, const int32_t *running, const double *ext);
 
 /* ---- prefix index write side (approximateprefix/indexer.go:52-83, 105-115, 167-182; plugin.go:164-211) --
- * Host mirror with the reference's per-server LRU semantics; the device table is rebuilt by
- * epp_index_commit (also called implicitly by the next lookup when dirty). */
+ * The LRU bookkeeping lives in HBM (index_store.cu): epp_index_add calls are queued and applied as ONE device batch,
+ * in call order, by the next commit / lookup / remove; epp_index_add_picked never leaves the device.  The read table
+ * is rebuilt on the device by epp_index_commit (also called implicitly by the next lookup when dirty). */
 EPP_API int32_t epp_index_add(epp_engine *h, uint32_t ep, int32_t n, const uint64_t *hashes, int32_t num_gpu_blocks);
 EPP_API int32_t epp_index_remove_endpoint(epp_engine *h, uint32_t ep);
+/* CleanUpInactivePods (approximateprefix/plugin.go:99-122): RemovePod for every indexed endpoint NOT in active_ids. */
+EPP_API int32_t epp_index_retain_endpoints(epp_engine *h, int32_t n, const uint32_t *active_ids);
 /* Bulk-replace the index with a frozen snapshot of UNIQUE-or-not (hash, endpoint) pairs (host pointers);
  * bypasses LRU bookkeeping.  Duplicates are removed on the device. */
 EPP_API int32_t epp_index_load_snapshot(epp_engine *h, uint64_t n_pairs, const uint64_t *hashes, const uint32_t *eps);

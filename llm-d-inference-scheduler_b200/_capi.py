@@ -87,6 +87,7 @@ SIGNATURES = {
                                  C.c_void_p]),
     "epp_index_add": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_int32]),
     "epp_index_remove_endpoint": (C.c_int32, [C.c_void_p, C.c_uint32]),
+    "epp_index_retain_endpoints": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p]),
     "epp_index_load_snapshot": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "epp_index_commit": (C.c_int32, [C.c_void_p]),
     "epp_index_get": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),

@@ -544,6 +544,26 @@ extern "C" int32_t epp_index_remove_endpoint(epp_engine *h, uint32_t ep) {
     return EPP_OK;
 }
 
+// CleanUpInactivePods (approximateprefix/plugin.go:99-122).
+extern "C" int32_t epp_index_retain_endpoints(epp_engine *h, int32_t n, const uint32_t *active_ids) {
+    if (!h || n < 0 || (n > 0 && !active_ids)) return fail(EPP_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->snapshot_mode) return fail(EPP_ERR_STATE, "index holds a bulk snapshot; reload it without the endpoints instead");
+    EPP_TRY(set_device(h));
+    EPP_TRY(flush_add_queue(h));
+    const size_t E = (size_t)h->cfg.max_endpoints;
+    std::vector<uint8_t> active(E, 0);
+    for (int32_t i = 0; i < n; i++) {
+        if (active_ids[i] >= E) return fail(EPP_ERR_INVALID, "endpoint slot %u out of range [0,%zu)", active_ids[i], E);
+        active[active_ids[i]] = 1;
+    }
+    cudaStream_t s = h->slot[0].stream;
+    CUDA_TRY(h->q_ep_dev.reserve(E, &h->dev_bytes));
+    CUDA_TRY(cudaMemcpyAsync(h->q_ep_dev.p, active.data(), E, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h->store->retain_endpoints(h->q_ep_dev.as<uint8_t>(), s));
+    return EPP_OK;
+}
+
 extern "C" int32_t epp_index_load_snapshot(epp_engine *h, uint64_t n_pairs, const uint64_t *hashes, const uint32_t *eps) {
     if (!h || (n_pairs && (!hashes || !eps))) return fail(EPP_ERR_INVALID, "bad arguments");
     std::lock_guard<std::mutex> lk(h->mu);

@@ -14,7 +14,7 @@ constexpr unsigned long long kLeakBit = 1ull << 63;   // log entry: evicting it 
 constexpr unsigned long long kTmpBit = 1ull << 62;    // scratch of k_store_leak
 constexpr unsigned long long kSeqMask = ~(kLeakBit | kTmpBit);
 constexpr int kCallChunk = 1024;                      // calls per ordering chunk (= threads of k_store_offsets)
-enum { kCtrPtUsed = 0, kCtrTotalItems, kCtrNeedRepack, kCtrInMap, kCtrCursor, kCtrAlive, kCtrN = 8 };
+enum { kCtrPtUsed = 0, kCtrTotalItems, kCtrNeedRepack, kCtrInMap, kCtrCursor, kCtrAlive, kCtrEvict, kCtrN = 8 };
 
 // One (hash, endpoint) pair of the write side: 32 bytes = one sector.
 struct __align__(32) StoreEntry {
@@ -55,7 +55,7 @@ __device__ __forceinline__ uint64_t pt_home(uint64_t h, uint32_t e, uint64_t mas
 // Finds or creates the entry of (h, e).  Lock-free: a slot is claimed by CAS on its hash word; its endpoint word is
 // then published by CAS as well, by the claimer or by any thread inserting the same hash (whoever wins owns the
 // slot, the loser keeps probing) -- no thread ever waits for another.
-__device__ __forceinline__ StoreEntry *pt_find_or_claim(const View &v, uint64_t h, uint32_t e) {
+__device__ __forceinline__ StoreEntry *pt_find_or_claim(const View &v, uint64_t h, uint32_t e, uint32_t &claimed) {
     uint64_t i = pt_home(h, e, v.pt_mask);
     for (;;) {
         StoreEntry *s = v.pt + i;
@@ -63,7 +63,7 @@ __device__ __forceinline__ StoreEntry *pt_find_or_claim(const View &v, uint64_t 
         if (cur == kEmptyKey) {
             unsigned long long old = atomicCAS(&s->hash, (unsigned long long)kEmptyKey, (unsigned long long)h);
             if (old == kEmptyKey) {
-                atomicAdd(&v.ctr[kCtrPtUsed], 1ull);
+                claimed++;                      // the caller adds its total to ctr[kCtrPtUsed] once
                 cur = h;
             } else {
                 cur = old;
@@ -92,9 +92,9 @@ __device__ __forceinline__ StoreEntry *pt_find(const View &v, uint64_t h, uint32
     }
 }
 
-__device__ __forceinline__ EntryRef ref_claim(const View &v, uint64_t h, uint32_t e) {
+__device__ __forceinline__ EntryRef ref_claim(const View &v, uint64_t h, uint32_t e, uint32_t &claimed) {
     if (h == kEmptyKey) return {&v.sp_seq[e], &v.sp_in_map[e]};    // the one hash equal to the free-slot sentinel
-    StoreEntry *s = pt_find_or_claim(v, h, e);
+    StoreEntry *s = pt_find_or_claim(v, h, e, claimed);
     return {&s->seq, &s->in_map};
 }
 
@@ -223,7 +223,7 @@ __global__ void k_store_upsert(View v, uint32_t M, const uint32_t *call_ep, cons
                                const unsigned long long *call_src, const unsigned long long *call_off,
                                const unsigned long long *hashes) {
     const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
-    uint32_t in_map_new = 0;
+    uint32_t in_map_new = 0, claimed = 0;
     for (uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < M; c += warps) {
         const uint32_t e = call_ep[c], n = call_n[c];
         if (e >= v.E || n == 0) continue;
@@ -236,15 +236,19 @@ __global__ void k_store_upsert(View v, uint32_t M, const uint32_t *call_ep, cons
             const unsigned long long hsh = src[i], seq = seq0 + i;
             v.log_hash[pos0 + i] = hsh;
             v.log_seq[pos0 + i] = seq;
-            EntryRef r = ref_claim(v, hsh, e);
+            EntryRef r = ref_claim(v, hsh, e, claimed);
             if (atomicMax(r.seq, seq) == 0) live_new++;                      // lru.Add of an absent key
             if (*reinterpret_cast<volatile uint32_t *>(r.in_map) == 0 && atomicExch(r.in_map, 1u) == 0) in_map_new++;
         }
         for (int o = 16; o; o >>= 1) live_new += __shfl_xor_sync(0xFFFFFFFFu, live_new, o);
         if (lane == 0 && live_new) atomicAdd(&v.live[e], live_new);
     }
-    for (int o = 16; o; o >>= 1) in_map_new += __shfl_xor_sync(0xFFFFFFFFu, in_map_new, o);
+    for (int o = 16; o; o >>= 1) {
+        in_map_new += __shfl_xor_sync(0xFFFFFFFFu, in_map_new, o);
+        claimed += __shfl_xor_sync(0xFFFFFFFFu, claimed, o);
+    }
     if (lane == 0 && in_map_new) atomicAdd(&v.ctr[kCtrInMap], (unsigned long long)in_map_new);
+    if (lane == 0 && claimed) atomicAdd(&v.ctr[kCtrPtUsed], (unsigned long long)claimed);
 }
 
 // Calls longer than their endpoint's LRU: hash i of the call is evicted BY THE SAME CALL iff at least `cap` distinct
@@ -289,8 +293,11 @@ __device__ __forceinline__ bool log_entry_live(const View &v, uint32_t e, unsign
     return ref_find(v, hsh, e, r) && *r.seq == (sq & kSeqMask) && *r.seq != 0;
 }
 
-// Folds the batch into the endpoint's counters (head, next_seq) -- runs once per batch before the eviction kernels.
-__global__ void k_store_advance(View v) {
+// Folds the batch into the endpoint's counters (head, next_seq) and lists the over-full endpoints with the range of
+// 256-entry log blocks each contributes to ONE flat block index space (so a single endpoint that received millions of
+// entries is spread over the whole grid).  One packed atomic orders (list position, first block) together.
+constexpr int kEvictPackShift = 40;
+__global__ void k_store_advance(View v, uint32_t *list_e, unsigned long long *list_start) {
     uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= v.E) return;
     const unsigned long long inc = v.inc[e];
@@ -299,23 +306,44 @@ __global__ void k_store_advance(View v) {
         v.next_seq[e] += inc;
         v.inc[e] = 0;
     }
-    v.cut[e] = v.tail[e];
+    const unsigned long long tail = v.tail[e], head = v.head[e];
+    v.cut[e] = tail;
+    const uint32_t cap = v.cap[e];
+    if (cap == 0 || v.live[e] <= cap) return;
+    const unsigned long long nb = (head + kEvictBlock - 1) / kEvictBlock - tail / kEvictBlock;
+    const unsigned long long old = atomicAdd(&v.ctr[kCtrEvict], (1ull << kEvictPackShift) | nb);
+    list_e[old >> kEvictPackShift] = e;
+    list_start[old >> kEvictPackShift] = old & ((1ull << kEvictPackShift) - 1);
 }
 
-__global__ void __launch_bounds__(kEvictBlock) k_evict_count(View v, uint32_t *blockcnt) {
-    for (uint32_t e = blockIdx.y; e < v.E; e += gridDim.y) {
-    const uint32_t cap = v.cap[e], live = v.live[e];
-    if (cap == 0 || live <= cap) continue;
-    const unsigned long long seg = v.seg_off[e], tail = v.tail[e], head = v.head[e];
-    const unsigned long long b0 = tail / kEvictBlock, b1 = (head + kEvictBlock - 1) / kEvictBlock;
-    for (unsigned long long b = b0 + blockIdx.x; b < b1; b += gridDim.x) {
+// Flat block g -> (endpoint, block of its log).  list_start is increasing; n > 0.
+__device__ __forceinline__ void evict_locate(const View &v, const uint32_t *list_e, const unsigned long long *list_start,
+                                             uint32_t n, unsigned long long g, uint32_t &e, unsigned long long &b) {
+    uint32_t lo = 0, hi = n;                      // last j with list_start[j] <= g
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (list_start[mid] <= g) lo = mid; else hi = mid;
+    }
+    e = list_e[lo];
+    b = v.tail[e] / kEvictBlock + (g - list_start[lo]);
+}
+
+__global__ void __launch_bounds__(kEvictBlock) k_evict_count(View v, const uint32_t *list_e,
+                                                              const unsigned long long *list_start, uint32_t *blockcnt) {
+    const unsigned long long packed = v.ctr[kCtrEvict];
+    const uint32_t n = (uint32_t)(packed >> kEvictPackShift);
+    const unsigned long long total = packed & ((1ull << kEvictPackShift) - 1);
+    for (unsigned long long g = blockIdx.x; g < total; g += gridDim.x) {
+        uint32_t e;
+        unsigned long long b;
+        evict_locate(v, list_e, list_start, n, g, e, b);
+        const unsigned long long seg = v.seg_off[e], tail = v.tail[e], head = v.head[e];
         const unsigned long long idx = b * kEvictBlock + threadIdx.x;
         bool is_live = false, leak;
         EntryRef r;
         if (idx >= tail && idx < head) is_live = log_entry_live(v, e, seg + idx, r, leak);
-        const int n = __syncthreads_count(is_live);
-        if (threadIdx.x == 0) blockcnt[seg / kEvictBlock + b] = (uint32_t)n;
-    }
+        const int cnt = __syncthreads_count(is_live);
+        if (threadIdx.x == 0) blockcnt[seg / kEvictBlock + b] = (uint32_t)cnt;
     }
 }
 
@@ -327,13 +355,20 @@ __global__ void k_evict_cut(View v, const uint32_t *blockcnt) {
         unsigned long long k = live - cap;
         const unsigned long long seg = v.seg_off[e], tail = v.tail[e], head = v.head[e];
         const unsigned long long b0 = tail / kEvictBlock, b1 = (head + kEvictBlock - 1) / kEvictBlock;
-        // 1. the block holding the k-th oldest live entry
+        // 1. the block holding the k-th oldest live entry (each lane sums kPer consecutive block counts per step)
+        constexpr int kPer = 8;
+        const uint32_t *bc = blockcnt + seg / kEvictBlock;
         unsigned long long b = b0;
         bool found = false;
         while (b < b1 && !found) {
-            const unsigned long long mine = b + lane;
-            const uint32_t c = mine < b1 ? blockcnt[seg / kEvictBlock + mine] : 0u;
-            uint32_t incl = c;
+            const unsigned long long mine = b + (unsigned long long)lane * kPer;
+            uint32_t c[kPer], sum = 0;
+#pragma unroll
+            for (int q = 0; q < kPer; q++) {
+                c[q] = mine + q < b1 ? bc[mine + q] : 0u;
+                sum += c[q];
+            }
+            uint32_t incl = sum;
             for (int o = 1; o < 32; o <<= 1) {
                 uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
                 if (lane >= (uint32_t)o) incl += t;
@@ -341,13 +376,24 @@ __global__ void k_evict_cut(View v, const uint32_t *blockcnt) {
             const uint32_t hit = __ballot_sync(0xFFFFFFFFu, incl >= k);
             if (hit) {
                 const int l = __ffs(hit) - 1;
-                const uint32_t before = __shfl_sync(0xFFFFFFFFu, incl - c, l);
+                // inside lane l's strip
+                unsigned long long before = incl - sum, bb = mine;
+                if ((int)lane == l) {
+#pragma unroll
+                    for (int q = 0; q < kPer; q++) {
+                        if (before + c[q] >= k) break;
+                        before += c[q];
+                        bb++;
+                    }
+                }
+                before = __shfl_sync(0xFFFFFFFFu, before, l);
+                bb = __shfl_sync(0xFFFFFFFFu, bb, l);
                 k -= before;
-                b += l;
+                b = bb;
                 found = true;
             } else {
                 k -= __shfl_sync(0xFFFFFFFFu, incl, 31);
-                b += 32;
+                b += 32 * kPer;
             }
         }
         unsigned long long pos = head;
@@ -376,24 +422,27 @@ __global__ void k_evict_cut(View v, const uint32_t *blockcnt) {
     }
 }
 
-__global__ void __launch_bounds__(kEvictBlock) k_evict_apply(View v) {
+__global__ void __launch_bounds__(kEvictBlock) k_evict_apply(View v, const uint32_t *list_e,
+                                                              const unsigned long long *list_start) {
+    const unsigned long long packed = v.ctr[kCtrEvict];
+    const uint32_t n = (uint32_t)(packed >> kEvictPackShift);
+    const unsigned long long total = packed & ((1ull << kEvictPackShift) - 1);
     unsigned long long removed = 0;
-    for (uint32_t e = blockIdx.y; e < v.E; e += gridDim.y) {
-    const unsigned long long tail = v.tail[e], cut = v.cut[e];
-    if (cut <= tail) continue;
-    const unsigned long long seg = v.seg_off[e];
-    for (unsigned long long idx = tail + (unsigned long long)blockIdx.x * kEvictBlock + threadIdx.x; idx < cut;
-         idx += (unsigned long long)gridDim.x * kEvictBlock) {
+    for (unsigned long long g = blockIdx.x; g < total; g += gridDim.x) {
+        uint32_t e;
+        unsigned long long b;
+        evict_locate(v, list_e, list_start, n, g, e, b);
+        const unsigned long long idx = b * kEvictBlock + threadIdx.x;
+        if (idx < v.tail[e] || idx >= v.cut[e]) continue;
         bool leak;
         EntryRef r;
-        if (log_entry_live(v, e, seg + idx, r, leak)) {
+        if (log_entry_live(v, e, v.seg_off[e] + idx, r, leak)) {
             *r.seq = 0;                                  // out of the LRU ...
             if (!leak) {                                 // ... and, through the eviction callback, out of the map
                 *r.in_map = 0;
                 removed++;
             }
         }
-    }
     }
     for (int o = 16; o; o >>= 1) removed += __shfl_xor_sync(0xFFFFFFFFu, removed, o);
     if ((threadIdx.x & 31) == 0 && removed) atomicAdd(&v.ctr[kCtrInMap], (unsigned long long)(0ull - removed));
@@ -447,14 +496,13 @@ __global__ void k_store_compact(View v) {
 
 // RemovePod (indexer.go:167-182): every key of the endpoint's LRU goes through the eviction callback, the LRU is
 // deleted (the next Add of the endpoint creates a new one, possibly with another size).
-__global__ void k_store_remove_endpoint(View v, uint32_t e) {
-    const uint32_t lane = threadIdx.x & 31;
+__device__ __forceinline__ void remove_endpoint_warp(const View &v, uint32_t e, uint32_t lane) {
     const unsigned long long head = v.head[e], seg = v.seg_off[e];
     unsigned long long removed = 0;
     for (unsigned long long idx = v.tail[e] + lane; idx < head; idx += 32) {
         EntryRef r;
-        const unsigned long long hsh = v.log_hash[seg + idx], sq = v.log_seq[seg + idx];
-        if (ref_find(v, hsh, e, r) && *r.seq == (sq & kSeqMask) && *r.seq != 0) {
+        bool leak;
+        if (log_entry_live(v, e, seg + idx, r, leak)) {
             *r.seq = 0;
             *r.in_map = 0;
             removed++;
@@ -469,6 +517,15 @@ __global__ void k_store_remove_endpoint(View v, uint32_t e) {
         v.cap[e] = 0;
         if (removed) atomicAdd(&v.ctr[kCtrInMap], (unsigned long long)(0ull - removed));
     }
+}
+
+__global__ void k_store_remove_endpoint(View v, uint32_t e) { remove_endpoint_warp(v, e, threadIdx.x & 31); }
+
+// CleanUpInactivePods (plugin.go:99-122): RemovePod for every endpoint that has an LRU and is not in the active set.
+__global__ void k_store_retain(View v, const uint8_t *active) {
+    const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < v.E; e += warps)
+        if (v.cap[e] != 0 && !active[e]) remove_endpoint_warp(v, e, lane);
 }
 
 // ---- housekeeping: log compaction into fresh segments, pair-table rehash ------------------------------------------------
@@ -518,9 +575,11 @@ __global__ void k_store_rehash(const StoreEntry *old_pt, uint64_t old_capacity, 
     if (i >= old_capacity) return;
     StoreEntry o = old_pt[i];
     if (o.hash == kEmptyKey || (o.seq == 0 && o.in_map == 0)) return;       // free slot or tombstone
-    StoreEntry *s = pt_find_or_claim(v, o.hash, o.ep);
+    uint32_t claimed = 0;
+    StoreEntry *s = pt_find_or_claim(v, o.hash, o.ep, claimed);
     s->seq = o.seq;
     s->in_map = o.in_map;
+    if (claimed) atomicAdd(&v.ctr[kCtrPtUsed], (unsigned long long)claimed);
 }
 
 __global__ void k_store_export(View v, uint64_t capacity, unsigned long long *out_hash, uint32_t *out_ep) {
@@ -759,13 +818,16 @@ cudaError_t IndexStore::apply(const StoreCalls &calls, cudaStream_t s) {
         k_store_leak<<<std::min<uint32_t>(M, 592), 256, 0, s>>>(v, M, calls.ep, calls.n, off);
         ST_TRY(blockcnt_.reserve(sizeof(uint32_t) * (log_cap_ / kEvictBlock + 1), &bytes_));
         tm.mark("leak");
-        k_store_advance<<<blocks_for(E_, 256), 256, 0, s>>>(v);
-        const dim3 eg(64, std::min<uint32_t>(E_, 65535u));
-        k_evict_count<<<eg, kEvictBlock, 0, s>>>(v, blockcnt_.as<uint32_t>());
+        ST_TRY(list_e_.reserve(sizeof(uint32_t) * E_, &bytes_));
+        ST_TRY(list_start_.reserve(sizeof(unsigned long long) * E_, &bytes_));
+        ST_TRY(cudaMemsetAsync(&v.ctr[kCtrEvict], 0, sizeof(unsigned long long), s));
+        k_store_advance<<<blocks_for(E_, 256), 256, 0, s>>>(v, list_e_.as<uint32_t>(), list_start_.as<unsigned long long>());
+        const unsigned eg = 148 * 8;                     // persistent: CTAs stride over the flat block space
+        k_evict_count<<<eg, kEvictBlock, 0, s>>>(v, list_e_.as<uint32_t>(), list_start_.as<unsigned long long>(), blockcnt_.as<uint32_t>());
         tm.mark("ev_count");
         k_evict_cut<<<blocks_for((uint64_t)E_ * 32, 256), 256, 0, s>>>(v, blockcnt_.as<uint32_t>());
         tm.mark("ev_cut");
-        k_evict_apply<<<eg, kEvictBlock, 0, s>>>(v);
+        k_evict_apply<<<eg, kEvictBlock, 0, s>>>(v, list_e_.as<uint32_t>(), list_start_.as<unsigned long long>());
         k_evict_finish<<<blocks_for(E_, 256), 256, 0, s>>>(v);
         tm.mark("ev_apply");
         last_launches += 8;
@@ -806,6 +868,18 @@ cudaError_t IndexStore::remove_endpoint(uint32_t ep, cudaStream_t s) {
     View v;
     fill_view(v);
     k_store_remove_endpoint<<<1, 32, 0, s>>>(v, ep);
+    ST_TRY(cudaMemcpyAsync(ctr_host_, v.ctr, sizeof(unsigned long long) * kCtrN, cudaMemcpyDeviceToHost, s));
+    ST_TRY(cudaStreamSynchronize(s));
+    in_map_ = ctr_host_[kCtrInMap];
+    dirty_ = true;
+    return cudaGetLastError();
+}
+
+cudaError_t IndexStore::retain_endpoints(const uint8_t *active_dev, cudaStream_t s) {
+    if (!init_) return cudaSuccess;
+    View v;
+    fill_view(v);
+    k_store_retain<<<blocks_for((uint64_t)E_ * 32, 256), 256, 0, s>>>(v, active_dev);
     ST_TRY(cudaMemcpyAsync(ctr_host_, v.ctr, sizeof(unsigned long long) * kCtrN, cudaMemcpyDeviceToHost, s));
     ST_TRY(cudaStreamSynchronize(s));
     in_map_ = ctr_host_[kCtrInMap];

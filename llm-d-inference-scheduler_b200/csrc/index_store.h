@@ -53,6 +53,8 @@ class IndexStore {
     cudaError_t apply_picks(const epp_decision *decisions, const uint64_t *hashes, const int32_t *nblocks, int64_t R,
                             int32_t max_blocks, cudaStream_t s);
     cudaError_t remove_endpoint(uint32_t ep, cudaStream_t s);
+    // CleanUpInactivePods: active_dev[e] != 0 keeps endpoint e (device array of max_endpoints bytes).
+    cudaError_t retain_endpoints(const uint8_t *active_dev, cudaStream_t s);
     cudaError_t clear(cudaStream_t s);
     // Every (hash, endpoint) pair of the inverted map, for the bulk build of the read table.
     cudaError_t export_pairs(DevBuf &pair_hash, DevBuf &pair_ep, uint64_t *n_pairs, size_t *accounted, cudaStream_t s);
@@ -81,7 +83,7 @@ class IndexStore {
     uint64_t pt_cap_ = 0, log_cap_ = 0, in_map_ = 0, pt_used_ = 0;
     DevBuf pt_, log_hash_, log_seq_;
     DevBuf cap_, live_, firstcall_, seg_off_, seg_cap_, head_, tail_, inc_, next_seq_, sp_seq_, sp_in_map_, ctr_;
-    DevBuf hist_, off_, new_off_, new_cap_, cut_, blockcnt_;
+    DevBuf hist_, off_, new_off_, new_cap_, cut_, blockcnt_, list_e_, list_start_;
     DevBuf call_ep_, call_n_, call_nb_, call_src_;
     std::vector<uint64_t> h_live_, h_inc_, h_off_, h_cap_;
     unsigned long long *ctr_host_ = nullptr;   // pinned

@@ -148,6 +148,11 @@ class Engine:
         assert hs.shape == es.shape
         self._check(self._lib.epp_index_load_snapshot(self._h, hs.shape[0], _ptr(hs), _ptr(es)))
 
+    def index_retain_endpoints(self, active_ids):
+        """CleanUpInactivePods (plugin.go:99-122): drop every indexed endpoint that is not in active_ids."""
+        a = np.ascontiguousarray(active_ids, dtype=np.uint32)
+        self._check(self._lib.epp_index_retain_endpoints(self._h, a.shape[0], _ptr(a)))
+
     def index_commit(self):
         self._check(self._lib.epp_index_commit(self._h))
 

@@ -251,6 +251,12 @@ def test_index_store_batched_adds_vs_oracle(epp, orc, seed, n_srv, universe, def
                 if rng.random() < 0.002:
                     eng.index_remove_endpoint(srv)
                     ix.remove_pod(srv)
+            if rnd == 3:                                               # CleanUpInactivePods (plugin.go:99-122)
+                active = [p for p in range(n_srv) if p % 3 != 1]
+                eng.index_retain_endpoints(active)
+                for p in ix.pods():
+                    if p not in active:
+                        ix.remove_pod(p)
             for k in range(universe):
                 assert eng.index_get(hash_of(k)) == ix.get(hash_of(k)), (rnd, k)
             assert eng.stats()["index_pairs"] == len(ix.export()[0])
