@@ -47,6 +47,8 @@ type ScorerSpec struct {
 	Kind   int     // C.EPP_SCORER_*
 	Weight float64 // default 1.0 (loader/defaults.go:42)
 	Param  float64
+	Column int     // ext column read by EPP_SCORER_TOKEN_LOAD / EPP_SCORER_ACTIVE_REQUEST
+	Param2 float64 // active-request: idleThreshold
 }
 
 type ProfileSpec struct {
@@ -74,6 +76,8 @@ func fillProfile(dst *C.epp_profile_cfg, p ProfileSpec) {
 		dst.scorers[i].kind = C.int32_t(s.Kind)
 		dst.scorers[i].weight = C.double(s.Weight)
 		dst.scorers[i].param = C.double(s.Param)
+		dst.scorers[i].column = C.int32_t(s.Column)
+		dst.scorers[i].param2 = C.double(s.Param2)
 	}
 }
 

@@ -48,7 +48,7 @@ extern "C" {
 #define EPP_API
 #endif
 
-#define EPP_ABI_VERSION 1
+#define EPP_ABI_VERSION 2
 #define EPP_MAX_SCORERS 8
 #define EPP_NO_ENDPOINT 0xFFFFFFFFu
 
@@ -72,7 +72,12 @@ typedef enum {
     EPP_SCORER_LOAD_AWARE = 3, /* "load-aware-scorer"            scorer/loadaware/load_aware.go:84-100; param = threshold */
     EPP_SCORER_EXTERNAL = 4,   /* host-computed per-endpoint column (param = column index): lets the Go
                                   side keep any other Scorer (lora-affinity, session-affinity, ...) */
-    EPP_SCORER_RUNNING = 5     /* "running-requests-size-scorer" scorer/runningrequests/runningrequest.go:78-108 */
+    EPP_SCORER_RUNNING = 5,    /* "running-requests-size-scorer" scorer/runningrequests/runningrequest.go:78-108 */
+    EPP_SCORER_TOKEN_LOAD = 6, /* "token-load-scorer"            scorer/tokenload/token_load.go:84-112; column = ext column
+                                  holding InFlightLoad.Tokens, param = queueThresholdTokens (<= 0: 4194304)       */
+    EPP_SCORER_ACTIVE_REQUEST = 7 /* "active-request-scorer"     scorer/activerequest/active_request.go:140-173; column = ext
+                                  column holding InFlightLoad.Requests, param = maxBusyScore (outside [0,1]: 1.0),
+                                  param2 = idleThreshold (< 0: 0)                                                 */
 } epp_scorer_kind;
 
 /* Value of the llm-d.ai/role label (filter/bylabel/roles.go:25-44). */
@@ -104,9 +109,10 @@ typedef enum {
 
 typedef struct {
     int32_t kind;              /* epp_scorer_kind */
-    int32_t reserved;
+    int32_t column;            /* ext column read by TOKEN_LOAD / ACTIVE_REQUEST (raw attribute values, not scores) */
     double weight;             /* WeightedScorer.weight, scheduling/weighted_scorer.go:24-40 */
     double param;
+    double param2;
 } epp_scorer_cfg;
 
 /* One SchedulerProfile (scheduling/scheduler_profile.go:117-128): role filter -> scorers IN ORDER ->

@@ -16,7 +16,8 @@ EPP_BATCH_ASYNC = 2
 
 EPP_OK, EPP_ERR_INVALID, EPP_ERR_CUDA, EPP_ERR_NO_DEVICE, EPP_ERR_CAPACITY, EPP_ERR_STATE, EPP_ERR_NCCL = \
     0, -1, -2, -3, -4, -5, -6
-(SCORER_PREFIX, SCORER_KV_UTIL, SCORER_QUEUE, SCORER_LOAD_AWARE, SCORER_EXTERNAL, SCORER_RUNNING) = range(6)
+(SCORER_PREFIX, SCORER_KV_UTIL, SCORER_QUEUE, SCORER_LOAD_AWARE, SCORER_EXTERNAL, SCORER_RUNNING, SCORER_TOKEN_LOAD,
+ SCORER_ACTIVE_REQUEST) = range(8)
 (ROLE_NONE, ROLE_DECODE, ROLE_PREFILL, ROLE_PREFILL_DECODE, ROLE_BOTH, ROLE_ENCODE, ROLE_ENCODE_PREFILL,
  ROLE_ENCODE_PREFILL_DECODE, ROLE_OTHER) = range(9)
 FILTER_NONE, FILTER_DECODE, FILTER_PREFILL, FILTER_ENCODE = range(4)
@@ -24,7 +25,8 @@ HANDLER_SINGLE, HANDLER_DISAGG = 0, 1
 
 
 class ScorerCfg(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("weight", C.c_double), ("param", C.c_double)]
+    _fields_ = [("kind", C.c_int32), ("column", C.c_int32), ("weight", C.c_double), ("param", C.c_double),
+                ("param2", C.c_double)]
 
 
 class ProfileCfg(C.Structure):

@@ -149,9 +149,9 @@ extern "C" void epp_config_default(epp_config *cfg) {
     // config/loader/defaults.go:47-49, 78-87: queue 2, kv-cache-utilization 2, prefix 3 -- in that order
     cfg->primary.filter = EPP_FILTER_NONE;
     cfg->primary.n_scorers = 3;
-    cfg->primary.scorers[0] = {EPP_SCORER_QUEUE, 0, 2.0, 0.0};
-    cfg->primary.scorers[1] = {EPP_SCORER_KV_UTIL, 0, 2.0, 0.0};
-    cfg->primary.scorers[2] = {EPP_SCORER_PREFIX, 0, 3.0, 0.0};
+    cfg->primary.scorers[0] = {EPP_SCORER_QUEUE, 0, 2.0, 0.0, 0.0};
+    cfg->primary.scorers[1] = {EPP_SCORER_KV_UTIL, 0, 2.0, 0.0, 0.0};
+    cfg->primary.scorers[2] = {EPP_SCORER_PREFIX, 0, 3.0, 0.0, 0.0};
 }
 
 static int32_t validate_profile(const epp_profile_cfg &p, int n_ext, const char *name) {
@@ -159,8 +159,10 @@ static int32_t validate_profile(const epp_profile_cfg &p, int n_ext, const char 
     if (p.n_scorers < 0 || p.n_scorers > EPP_MAX_SCORERS) return fail(EPP_ERR_INVALID, "%s: n_scorers %d out of range", name, p.n_scorers);
     for (int s = 0; s < p.n_scorers; s++) {
         const epp_scorer_cfg &sc = p.scorers[s];
-        if (sc.kind < EPP_SCORER_PREFIX || sc.kind > EPP_SCORER_RUNNING) return fail(EPP_ERR_INVALID, "%s: scorer %d has unknown kind %d", name, s, sc.kind);
+        if (sc.kind < EPP_SCORER_PREFIX || sc.kind > EPP_SCORER_ACTIVE_REQUEST) return fail(EPP_ERR_INVALID, "%s: scorer %d has unknown kind %d", name, s, sc.kind);
         if (!std::isfinite(sc.weight)) return fail(EPP_ERR_INVALID, "%s: scorer %d weight is not finite", name, s);
+        if ((sc.kind == EPP_SCORER_TOKEN_LOAD || sc.kind == EPP_SCORER_ACTIVE_REQUEST) && (sc.column < 0 || sc.column >= n_ext))
+            return fail(EPP_ERR_INVALID, "%s: scorer %d reads ext column %d, out of range [0,%d)", name, s, sc.column, n_ext);
         if (sc.kind == EPP_SCORER_EXTERNAL && (sc.param < 0 || sc.param >= n_ext)) return fail(EPP_ERR_INVALID, "%s: scorer %d external column %g out of range [0,%d)", name, s, sc.param, n_ext);
     }
     return EPP_OK;
@@ -175,7 +177,7 @@ static int32_t alloc_profile(epp_engine *e, ProfileState &ps) {
     CUDA_TRY(ps.grp_size.reserve(sizeof(uint32_t) * Ep, &e->dev_bytes));
     CUDA_TRY(ps.sort_key.reserve(sizeof(uint64_t) * Ep, &e->dev_bytes));
     CUDA_TRY(ps.n_cand.reserve(sizeof(int32_t) * 4, &e->dev_bytes));
-    CUDA_TRY(ps.qminmax.reserve(sizeof(int64_t) * 4, &e->dev_bytes));
+    CUDA_TRY(ps.qminmax.reserve(sizeof(int64_t) * (4 + EPP_MAX_SCORERS), &e->dev_bytes));
     return EPP_OK;
 }
 

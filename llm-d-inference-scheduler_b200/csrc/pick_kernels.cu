@@ -64,6 +64,28 @@ __global__ void __launch_bounds__(1024) k_pool_candidates(PoolArrays pool, int f
     }
 }
 
+// active-request scorers: max in-flight request count over the profile's candidates (whole pool, like the queue
+// min/max), starting from 0 (active_request.go:144-155) -> qminmax[4 + s].
+__global__ void __launch_bounds__(1024) k_pool_aux(PoolArrays pool, epp_profile_cfg cfg, int filter, int64_t *qminmax) {
+    __shared__ long long s_mx[32];
+    for (int s = 0; s < cfg.n_scorers; s++) {
+        if (cfg.scorers[s].kind != EPP_SCORER_ACTIVE_REQUEST) continue;
+        const int col = cfg.scorers[s].column;
+        long long mx = 0;
+        if (col >= 0 && col < pool.n_ext_cols)
+            for (int e = threadIdx.x; e < pool.E; e += blockDim.x)
+                if (filter_keeps(filter, pool.role[e])) mx = max(mx, (long long)pool.ext[(size_t)col * (size_t)pool.E + (size_t)e]);
+        for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0) s_mx[threadIdx.x >> 5] = mx;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int i = 1; i < (int)(blockDim.x >> 5); i++) s_mx[0] = max(s_mx[0], s_mx[i]);
+            qminmax[4 + s] = s_mx[0];
+        }
+        __syncthreads();
+    }
+}
+
 __device__ __forceinline__ uint64_t desc_key(double x) {
     // order-preserving map double -> u64 (ascending), then inverted so that an ASCENDING sort of the key
     // yields DESCENDING scores.
@@ -87,7 +109,7 @@ __global__ void k_pool_terms(PoolArrays pool, epp_profile_cfg cfg, const uint8_t
     }
     double acc = 0.0;
     for (int s = 0; s < cfg.n_scorers; s++) {
-        double raw = cfg.scorers[s].kind == EPP_SCORER_PREFIX ? 0.0 : pool_score(cfg.scorers[s], pool, qminmax, e);
+        double raw = cfg.scorers[s].kind == EPP_SCORER_PREFIX ? 0.0 : pool_score(cfg.scorers[s], s, pool, qminmax, e);
         double term = __dmul_rn(clamp01(raw), cfg.scorers[s].weight);
         contrib[(size_t)s * (size_t)pool.E + e] = term;
         acc = __dadd_rn(acc, term);
@@ -133,6 +155,12 @@ __global__ void k_pool_groups(const double *base, const uint32_t *order, const i
 cudaError_t launch_pool_prepare(const PoolArrays &pool, const epp_profile_cfg &prof, const ProfileDerived &d,
                                 int32_t Epad, uint32_t shard_begin, uint32_t shard_end, cudaStream_t s, int *launches) {
     k_pool_candidates<<<1, 1024, 0, s>>>(pool, prof.filter, shard_begin, shard_end, d.cand, d.n_cand, d.qminmax);
+    for (int i = 0; i < prof.n_scorers; i++)
+        if (prof.scorers[i].kind == EPP_SCORER_ACTIVE_REQUEST) {
+            k_pool_aux<<<1, 1024, 0, s>>>(pool, prof, prof.filter, d.qminmax);
+            if (launches) *launches += 1;
+            break;
+        }
     k_pool_terms<<<(Epad + 255) / 256, 256, 0, s>>>(pool, prof, d.cand, d.qminmax, d.contrib, d.base, d.sort_key,
                                                     d.order, Epad);
     k_pool_sort<<<1, 1024, 0, s>>>(d.sort_key, d.order, Epad);
@@ -417,7 +445,7 @@ __global__ void k_score_dense(int64_t R, int32_t E, ProfileDev pf, PoolArrays po
         v = 0.0;
     } else {
         const epp_scorer_cfg &sc = pf.cfg.scorers[scorer_index];
-        v = sc.kind == EPP_SCORER_PREFIX ? prefix_score(match[idx], total[r]) : pool_score(sc, pool, qminmax, e);
+        v = sc.kind == EPP_SCORER_PREFIX ? prefix_score(match[idx], total[r]) : pool_score(sc, scorer_index, pool, qminmax, e);
     }
     out[idx] = v;
 }

@@ -44,7 +44,9 @@ __device__ __forceinline__ double prefix_score(int32_t match, int32_t total) {
 }
 
 // Raw Scorer.Score value of one endpoint for the request-independent scorers.
-__device__ __forceinline__ double pool_score(const epp_scorer_cfg &sc, const PoolArrays &pool,
+// qminmax: [0..3] waiting / running min,max over the profile's candidates, [4 + s] max in-flight request count of
+// active-request scorer s.
+__device__ __forceinline__ double pool_score(const epp_scorer_cfg &sc, int s_index, const PoolArrays &pool,
                                              const int64_t *qminmax, int32_t e) {
     switch (sc.kind) {
         case EPP_SCORER_KV_UTIL:   // kvcache_utilization.go:79
@@ -69,6 +71,24 @@ __device__ __forceinline__ double pool_score(const epp_scorer_cfg &sc, const Poo
             int col = (int)sc.param;
             if (col < 0 || col >= pool.n_ext_cols) return 0.0;
             return pool.ext[(size_t)col * (size_t)pool.E + (size_t)e];
+        }
+        case EPP_SCORER_TOKEN_LOAD: {   // token_load.go:84-112
+            double thr = sc.param;
+            if (!(thr > 0.0)) thr = 4194304.0;
+            const int col = sc.column;
+            double load = (col >= 0 && col < pool.n_ext_cols) ? pool.ext[(size_t)col * (size_t)pool.E + (size_t)e] : 0.0;
+            if (load <= 0.0) return 1.0;
+            if (load > thr) load = thr;
+            return __dsub_rn(1.0, __ddiv_rn(load, thr));
+        }
+        case EPP_SCORER_ACTIVE_REQUEST: {   // active_request.go:140-173, NewActiveRequest :83-93
+            const int col = sc.column;
+            const int64_t idle = sc.param2 >= 0.0 ? (int64_t)sc.param2 : 0;
+            const double max_busy = (sc.param >= 0.0 && sc.param <= 1.0) ? sc.param : 1.0;
+            const int64_t c = (col >= 0 && col < pool.n_ext_cols) ? (int64_t)pool.ext[(size_t)col * (size_t)pool.E + (size_t)e] : 0;
+            if (c <= idle) return 1.0;
+            const int64_t mx = qminmax[4 + s_index];
+            return __dmul_rn(__ddiv_rn((double)(mx - c), (double)mx), max_busy);
         }
         default: return 0.0;
     }

@@ -30,6 +30,8 @@ class ScorerSpec:
     kind: int
     weight: float = 1.0
     param: float = 0.0
+    column: int = 0          # ext column read by token-load / active-request
+    param2: float = 0.0
 
 
 @dataclass
@@ -50,6 +52,8 @@ def _fill_profile(dst: capi.ProfileCfg, spec: ProfileSpec):
         dst.scorers[i].kind = s.kind
         dst.scorers[i].weight = s.weight
         dst.scorers[i].param = s.param
+        dst.scorers[i].column = s.column
+        dst.scorers[i].param2 = s.param2
 
 
 def _is_torch(x) -> bool:

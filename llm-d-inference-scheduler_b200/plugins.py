@@ -108,6 +108,8 @@ class _Scorer:
     kind: int
     param: float = 0.0
     type_name: str = ""
+    column: int = 0
+    param2: float = 0.0
 
 
 def PrefixCacheScorer():                         # scorer/prefix "prefix-cache-scorer"
@@ -128,6 +130,17 @@ def RunningRequestsScorer():                     # "running-requests-size-scorer
 
 def NewLoadAware(queueThreshold: int = 128):     # loadaware.NewLoadAware, load_aware.go:43-52
     return _Scorer(capi.SCORER_LOAD_AWARE, float(queueThreshold), "load-aware-scorer")
+
+
+def TokenLoadScorer(column: int, queueThresholdTokens: int = 4194304):
+    """ "token-load-scorer" (scorer/tokenload/token_load.go:84-112); `column` = ext column holding InFlightLoad.Tokens."""
+    return _Scorer(capi.SCORER_TOKEN_LOAD, float(queueThresholdTokens), "token-load-scorer", column)
+
+
+def NewActiveRequest(column: int, idleThreshold: int = 0, maxBusyScore: float = 1.0):
+    """ "active-request-scorer" (scorer/activerequest/active_request.go:72-101, 140-173); `column` = ext column holding
+    InFlightLoad.Requests."""
+    return _Scorer(capi.SCORER_ACTIVE_REQUEST, float(maxBusyScore), "active-request-scorer", column, float(idleThreshold))
 
 
 def ExternalScorer(column: int):                 # host-computed column (e.g. lora-affinity)
@@ -199,7 +212,8 @@ class SchedulerProfile:
 
     def spec(self) -> ProfileSpec:
         return ProfileSpec(self.filters[0].kind if self.filters else capi.FILTER_NONE,
-                           [ScorerSpec(ws.scorer.kind, ws.weight, ws.scorer.param) for ws in self.scorers])
+                           [ScorerSpec(ws.scorer.kind, ws.weight, ws.scorer.param, ws.scorer.column, ws.scorer.param2)
+                            for ws in self.scorers])
 
 
 def NewSchedulerProfile():

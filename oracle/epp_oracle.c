@@ -528,6 +528,39 @@ void orc_score_column(const orc_scorer *s, const orc_pool *pool, const uint8_t *
             out[e] = (cand[e] && col >= 0 && col < pool->n_ext_cols) ? pool->ext[(size_t)col * (size_t)n + (size_t)e] : 0.0;
         break;
     }
+    case ORC_SCORER_TOKEN_LOAD: {  /* token_load.go:84-112 */
+        double thr = s->param;
+        if (!(thr > 0)) thr = 4194304.0;            /* TokenLoadScorerFactory: <= 0 -> tokenQueueThresholdDefault */
+        int col = s->column;
+        for (int e = 0; e < n; e++) {
+            if (!cand[e]) { out[e] = 0.0; continue; }
+            double load = (col >= 0 && col < pool->n_ext_cols) ? pool->ext[(size_t)col * (size_t)n + (size_t)e] : 0.0;
+            if (load <= 0) out[e] = 1.0;
+            else {
+                if (load > thr) load = thr;
+                out[e] = 1.0 - (load / thr);
+            }
+        }
+        break;
+    }
+    case ORC_SCORER_ACTIVE_REQUEST: {  /* active_request.go:140-173; NewActiveRequest :83-93 */
+        int64_t idle = s->param2 >= 0 ? (int64_t)s->param2 : 0;
+        double max_busy = (s->param >= 0 && s->param <= 1.0) ? s->param : 1.0;
+        int col = s->column;
+        int64_t max_count = 0;
+        for (int e = 0; e < n; e++) {
+            if (!cand[e]) continue;
+            int64_t c = (col >= 0 && col < pool->n_ext_cols) ? (int64_t)pool->ext[(size_t)col * (size_t)n + (size_t)e] : 0;
+            if (c > max_count) max_count = c;
+        }
+        for (int e = 0; e < n; e++) {
+            if (!cand[e]) { out[e] = 0.0; continue; }
+            int64_t c = (col >= 0 && col < pool->n_ext_cols) ? (int64_t)pool->ext[(size_t)col * (size_t)n + (size_t)e] : 0;
+            if (c <= idle) out[e] = 1.0;
+            else out[e] = (double)(max_count - c) / (double)max_count * max_busy;
+        }
+        break;
+    }
     default:
         for (int e = 0; e < n; e++) out[e] = 0.0;
     }

@@ -70,7 +70,11 @@ enum {
     ORC_SCORER_LOAD_AWARE = 3,   /* scorer/loadaware/load_aware.go:84-100 (param = threshold) */
     ORC_SCORER_EXTERNAL = 4,     /* host-computed column (param = column index); used for the
                                     lora-affinity column of scheduler_test.go:77-141      */
-    ORC_SCORER_RUNNING = 5       /* scorer/runningrequests/runningrequest.go:78-108      */
+    ORC_SCORER_RUNNING = 5,      /* scorer/runningrequests/runningrequest.go:78-108      */
+    ORC_SCORER_TOKEN_LOAD = 6,   /* scorer/tokenload/token_load.go:84-112: column = ext column of InFlightLoad.Tokens,
+                                    param = queueThresholdTokens (<= 0: 4194304, :27-28, :60-62) */
+    ORC_SCORER_ACTIVE_REQUEST = 7 /* scorer/activerequest/active_request.go:140-173: column = ext column of
+                                    InFlightLoad.Requests, param = maxBusyScore, param2 = idleThreshold (:83-93) */
 };
 
 /* Role filters: filter/bylabel/roles.go:46-70, filter.go:104-117. */
@@ -90,9 +94,10 @@ int orc_role_filter_keeps(int filter, int role);
 
 typedef struct {
     int32_t kind;
-    int32_t _pad;
+    int32_t column;              /* ext column read by TOKEN_LOAD / ACTIVE_REQUEST */
     double weight;               /* WeightedScorer.weight, weighted_scorer.go:24-40 */
     double param;
+    double param2;
 } orc_scorer;
 
 #define ORC_MAX_SCORERS 8

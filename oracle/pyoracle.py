@@ -15,7 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libepp_oracle.so")
 
 MAX_SCORERS = 8
-SCORER_PREFIX, SCORER_KV_UTIL, SCORER_QUEUE, SCORER_LOAD_AWARE, SCORER_EXTERNAL, SCORER_RUNNING = range(6)
+(SCORER_PREFIX, SCORER_KV_UTIL, SCORER_QUEUE, SCORER_LOAD_AWARE, SCORER_EXTERNAL, SCORER_RUNNING, SCORER_TOKEN_LOAD,
+ SCORER_ACTIVE_REQUEST) = range(8)
 ROLE_NONE, ROLE_DECODE, ROLE_PREFILL, ROLE_PREFILL_DECODE, ROLE_BOTH, ROLE_ENCODE, ROLE_ENCODE_PREFILL, \
     ROLE_ENCODE_PREFILL_DECODE, ROLE_OTHER = range(9)
 ROLE_ABSENT = 0xFF
@@ -23,7 +24,8 @@ FILTER_NONE, FILTER_DECODE, FILTER_PREFILL, FILTER_ENCODE = range(4)
 
 
 class Scorer(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("weight", C.c_double), ("param", C.c_double)]
+    _fields_ = [("kind", C.c_int32), ("column", C.c_int32), ("weight", C.c_double), ("param", C.c_double),
+                ("param2", C.c_double)]
 
 
 class Profile(C.Structure):
@@ -131,14 +133,17 @@ def hash_prompt(data: bytes, model: bytes, block_size_tokens: int, max_prefix_bl
     return [int(x) for x in out[:n]]
 
 
-def make_profile(filter_kind: int, scorers: list[tuple[int, float, float]]) -> Profile:
+def make_profile(filter_kind: int, scorers: list[tuple]) -> Profile:
     p = Profile()
     p.filter = filter_kind
     p.n_scorers = len(scorers)
-    for i, (kind, weight, param) in enumerate(scorers):
+    for i, sc in enumerate(scorers):              # (kind, weight, param[, column[, param2]])
+        kind, weight, param = sc[:3]
         p.scorers[i].kind = kind
         p.scorers[i].weight = weight
         p.scorers[i].param = param
+        p.scorers[i].column = int(sc[3]) if len(sc) > 3 else 0
+        p.scorers[i].param2 = float(sc[4]) if len(sc) > 4 else 0.0
     return p
 
 
@@ -230,9 +235,11 @@ def profile_run(profile: Profile, pool: PoolState, match, total: int):
     return scores, mx.value, pick.value, [int(x) for x in amax[:cnt]]
 
 
-def score_column(scorer: tuple[int, float, float], pool: PoolState, cand, match, total: int):
+def score_column(scorer: tuple, pool: PoolState, cand, match, total: int):
     s = Scorer()
-    s.kind, s.weight, s.param = scorer
+    s.kind, s.weight, s.param = scorer[:3]
+    s.column = int(scorer[3]) if len(scorer) > 3 else 0
+    s.param2 = float(scorer[4]) if len(scorer) > 4 else 0.0
     c = np.ascontiguousarray(cand, dtype=np.uint8)
     m = np.ascontiguousarray(match, dtype=np.int32)
     out = np.zeros(pool.n, dtype=np.float64)

@@ -517,13 +517,16 @@ def test_score_columns_vs_oracle(epp, orc):
     kv = np.where(rng.random(E) < 0.2, rng.choice([0.0, 1.0, 1.5, -0.25], E), rng.random(E))
     waiting = np.where(rng.random(E) < 0.6, 0, rng.integers(1, 300, E)).astype(np.int32)
     running = rng.integers(0, 50, E).astype(np.int32)
-    ext = rng.random((2, E)) * 1.4 - 0.2
-    scorers = [(0, 3.0, 0), (1, 2.0, 0), (2, 2.0, 0), (3, 1.0, 10), (4, 0.37, 1), (5, 1.5, 0), (4, 50.0, 0)]
+    ext = rng.random((4, E)) * 1.4 - 0.2
+    ext[2] = np.where(rng.random(E) < 0.3, 0, rng.integers(0, 9000, E))        # InFlightLoad.Tokens
+    ext[3] = np.where(rng.random(E) < 0.3, 0, rng.integers(0, 40, E))          # InFlightLoad.Requests
+    scorers = [(0, 3.0, 0), (1, 2.0, 0), (2, 2.0, 0), (3, 1.0, 10), (4, 0.37, 1), (5, 1.5, 0), (6, 1.25, 5000.0, 2),
+               (7, 0.8, 0.5, 3, 2.0)]
     total = rng.choice([0, 1, 7, 256], R).astype(np.int32)
     match = (rng.random((R, E)) * (total[:, None] + 1)).astype(np.int32)
     match = np.minimum(match, total[:, None])
     for filt in (0, 1, 2):
-        with epp.Engine(E, epp.ProfileSpec(filt, [epp.ScorerSpec(*s) for s in scorers]), n_ext_cols=2) as eng:
+        with epp.Engine(E, epp.ProfileSpec(filt, [epp.ScorerSpec(*s) for s in scorers]), n_ext_cols=4) as eng:
             eng.pool_set(np.arange(E), roles, kv, waiting, running, ext)
             pool = orc.PoolState(roles, kv, waiting, running, ext)
             prof = orc.make_profile(filt, scorers)
@@ -545,6 +548,30 @@ def test_score_columns_vs_oracle(epp, orc):
                 if d.status == 0:
                     assert dec["pick"][r] == d.pick and dec["tie_count"][r] == d.tie_count
                     assert dec["score"][r : r + 1].view(np.uint64)[0] == np.float64(d.score).view(np.uint64)
+
+
+def test_token_load_and_active_request_kats(epp):
+    """token_load_test.go:32-61 and active_request_test.go:36-92, 172-216 re-encoded against the engine."""
+    P = epp.plugins
+
+    def scores(scorer, column_values):
+        n = len(column_values)
+        prof = epp.ProfileSpec(0, [epp.ScorerSpec(scorer.kind, 1.0, scorer.param, scorer.column, scorer.param2)])
+        with epp.Engine(n, prof, n_ext_cols=1) as eng:
+            eng.pool_set(np.arange(n), np.zeros(n, np.uint8), np.zeros(n), np.zeros(n, np.int32), np.zeros(n, np.int32),
+                         np.asarray(column_values, dtype=np.float64).reshape(1, n))
+            return list(eng.score(np.zeros((1, n), np.int32), np.zeros(1, np.int32), 0, 0)[0])
+
+    assert scores(P.TokenLoadScorer(0, 1000), [0, 500, 1000]) == [1.0, 0.5, 0.0]
+    assert scores(P.TokenLoadScorer(0, 1000), [-5, 2500, 250]) == [1.0, 0.0, 0.75]
+    assert scores(P.TokenLoadScorer(0, 0), [4194304 // 2]) == [0.5]                  # <= 0 -> default threshold
+    assert scores(P.NewActiveRequest(0), [0, 0, 0]) == [1.0, 1.0, 1.0]               # no load attribute set
+    assert scores(P.NewActiveRequest(0), [3, 0, 6]) == [0.5, 1.0, 0.0]
+    assert scores(P.NewActiveRequest(0), [4, 0, 1]) == [0.0, 1.0, 0.75]
+    assert scores(P.NewActiveRequest(0, 0, 0.0), [0, 0]) == [1.0, 1.0]               # binary mode
+    assert scores(P.NewActiveRequest(0, 0, 0.0), [1, 0]) == [0.0, 1.0]
+    assert scores(P.NewActiveRequest(0, 1, 0.5), [1, 2, 0]) == [1.0, 0.0, 1.0]       # hybrid mode
+    assert scores(P.NewActiveRequest(0, -3, 7.0), [2, 4]) == [0.5, 0.0]              # invalid params -> defaults
 
 
 # ------------------------------------------------------------------------------------------------

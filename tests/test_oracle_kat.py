@@ -114,6 +114,35 @@ def test_load_aware_scorer(orc):
     assert list(out) == [0.5 * (1.0 - 2 / 128.0), 0.5, 0.5 * (1.0 - 15 / 128.0)]
 
 
+def test_token_load_scorer(orc):
+    # tokenload/token_load_test.go:32-61 (threshold 1000; 0 / 500 / 1000 in-flight tokens)
+    pool = _pool(orc, n=3, kv=[0.0] * 3, ext=[[0, 500, 1000]])
+    out = orc.score_column((orc.SCORER_TOKEN_LOAD, 1.0, 1000.0, 0), pool, [1, 1, 1], [0] * 3, 0)
+    assert list(out) == [1.0, 0.5, 0.0]
+    out = orc.score_column((orc.SCORER_TOKEN_LOAD, 1.0, 0.0, 0), pool, [1, 1, 1], [0] * 3, 0)   # <= 0 -> 4194304
+    assert list(out) == [1.0, 1.0 - 500 / 4194304.0, 1.0 - 1000 / 4194304.0]
+
+
+def test_active_request_scorer(orc):
+    AR = orc.SCORER_ACTIVE_REQUEST
+
+    def run(counts, max_busy=1.0, idle=0.0, cand=None):
+        pool = _pool(orc, n=len(counts), kv=[0.0] * len(counts), ext=[counts])
+        return list(orc.score_column((AR, 1.0, max_busy, 0, idle), pool, cand or [1] * len(counts), [0] * len(counts), 0))
+
+    # activerequest/active_request_test.go:36-92
+    assert run([0, 0, 0]) == [1.0, 1.0, 1.0]
+    assert run([3, 0, 6]) == [0.5, 1.0, 0.0]
+    assert run([4, 0, 1]) == [0.0, 1.0, 0.75]
+    # :172-216 idleThreshold / maxBusyScore
+    assert run([0, 0], 0.0, 0) == [1.0, 1.0]
+    assert run([1, 0], 0.0, 0) == [0.0, 1.0]
+    assert run([1, 2, 0], 0.5, 1) == [1.0, 0.0, 1.0]
+    # NewActiveRequest :83-93: out-of-range parameters fall back to the defaults; max is over the candidates only
+    assert run([2, 4], 7.0, -3) == [0.5, 0.0]
+    assert run([2, 4, 8], cand=[1, 1, 0]) == [0.5, 0.0, 0.0]
+
+
 # ---- B.1 #12: picker/maxscore/picker_test.go:43-110 -- ties are a SET ----------------------------------
 def test_max_score_picker_tie_set(orc):
     pool = _pool(orc, n=4, ext=[[0.5, 0.9, 0.9, 0.1]])
