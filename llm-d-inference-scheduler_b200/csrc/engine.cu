@@ -111,6 +111,8 @@ struct epp_engine {
     int force_v1 = 0;               // EPP_HASH_V1=1: unfused v1 hash kernels (A/B)
     int force_match_v1 = 0;         // EPP_MATCH_V1=1: dense-counter match kernel only (A/B)
     int prefetch = 0;               // EPP_PREFETCH=1
+    int win = 8;                    // EPP_HASH_WIN=4: 4-block windows in k_hash_fused
+    int bulk = 0;                   // EPP_HASH_BULK=2|3|4|5: bulk-copy fed hash kernel (hash_bulk.cu), data stages per CTA
     int wide = 0;                   // EPP_WIDE=1: 32-block windows in the hash kernel (A/B; measured slower)
     int tile_r = 32;                // EPP_TILE=16: 16-request tiles in the fused kernels (A/B; measured slower)
     int no_fuse = 1;                // EPP_FUSE_MATCH=1 runs a2-a14 inside the hash kernel (experimental, slower today)
@@ -239,6 +241,8 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
     { const char *v1 = getenv("EPP_HASH_V1"); e->force_v1 = (v1 && v1[0] == '1') ? 1 : 0; }
     { const char *v1 = getenv("EPP_MATCH_V1"); e->force_match_v1 = (v1 && v1[0] == '1') ? 1 : 0; }
     { const char *v1 = getenv("EPP_WIDE"); e->wide = (v1 && v1[0] == '1') ? 1 : 0; }
+    { const char *v1 = getenv("EPP_HASH_BULK"); e->bulk = v1 ? atoi(v1) : 0; }
+    { const char *v1 = getenv("EPP_HASH_WIN"); e->win = v1 ? atoi(v1) : 8; }
     { const char *v1 = getenv("EPP_PREFETCH"); e->prefetch = (v1 && v1[0] == '1') ? 1 : 0; }
     { const char *v1 = getenv("EPP_TILE"); e->tile_r = (v1 && atoi(v1) == 16) ? 16 : 32; }
     { const char *v1 = getenv("EPP_FUSE_MATCH"); e->no_fuse = (v1 && v1[0] == '1') ? 0 : 1; }
@@ -706,6 +710,8 @@ static HashParams hash_params(epp_engine *h, const Work &w) {
     p.tile_r = h->tile_r;
     p.prefetch = h->prefetch;
     p.wide = h->wide;
+    p.bulk = h->bulk;
+    p.win = h->win;
     p.fused_pick = nullptr;
     return p;
 }

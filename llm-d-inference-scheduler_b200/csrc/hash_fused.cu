@@ -141,14 +141,14 @@ __device__ __forceinline__ uint64_t block_digest64(const uint64_t x0[4], const u
 
 // Chain warp, one window: the serial part of the digest for 32 requests at once, in place, then the 8 hashes of
 // each request written as one 64-byte segment.
-template <int TR>
-__device__ __forceinline__ uint64_t chain_window(uint64_t (*sm)[kPitch], const int32_t *s_nfull, const HashParams &p,
+template <int TR, int W = kWin>
+__device__ __forceinline__ uint64_t chain_window(uint64_t (*sm)[W + 1], const int32_t *s_nfull, const HashParams &p,
                                                  int64_t r0, int k, int lane, int32_t nfull, uint64_t lenp8,
                                                  uint64_t prev) {
     if (lane < TR) {
 #pragma unroll
-        for (int j = 0; j < kWin; j++) {
-            if (k * kWin + j < nfull) {
+        for (int j = 0; j < W; j++) {
+            if (k * W + j < nfull) {
                 prev = xxh_chain_step32(sm[lane][j], lenp8, prev);
                 sm[lane][j] = prev;
             }
@@ -156,9 +156,10 @@ __device__ __forceinline__ uint64_t chain_window(uint64_t (*sm)[kPitch], const i
     }
     __syncwarp();
 #pragma unroll
-    for (int it = 0; it < TR / 4; it++) {
-        int rr = it * 4 + (lane >> 3), jj = lane & 7;
-        int b = k * kWin + jj;
+    constexpr int kRows = 32 / W;                 // request rows written per warp instruction
+    for (int it = 0; it < TR / kRows; it++) {
+        int rr = it * kRows + lane / W, jj = lane % W;
+        int b = k * W + jj;
         if (b < s_nfull[rr]) p.hashes[(r0 + rr) * (int64_t)p.max_blocks + b] = sm[rr][jj];
     }
     __syncwarp();
@@ -169,12 +170,12 @@ __device__ __forceinline__ uint64_t chain_window(uint64_t (*sm)[kPitch], const i
 // =====================================================================================================
 // k_hash_fused: a1 only (epp_hash_prompts, Produce-parity and sharded modes, A/B runs)
 // =====================================================================================================
-template <bool kAlign32, int TR>
-__global__ void __launch_bounds__(TR * kWin + 32, kHashMinCtas) k_hash_fused(HashParams p, int n_tiles) {
+template <bool kAlign32, int TR, int W = kWin, int MINCTA = kHashMinCtas>
+__global__ void __launch_bounds__(TR * W + 32, MINCTA) k_hash_fused(HashParams p, int n_tiles) {
     constexpr int kTileR = TR;
-    constexpr int kDigestThreads = TR * kWin, kDigestWarps = kDigestThreads / 32;
+    constexpr int kDigestThreads = TR * W, kDigestWarps = kDigestThreads / 32;
     constexpr int kProducers = kDigestThreads + 32;
-    __shared__ uint64_t s_m[kStages][kTileR][kPitch];
+    __shared__ uint64_t s_m[kStages][kTileR][(W + 1)];
     __shared__ uint64_t s_off[kTileR];
     __shared__ int64_t s_eff[kTileR];
     __shared__ int32_t s_nfull[kTileR];
@@ -190,10 +191,10 @@ __global__ void __launch_bounds__(TR * kWin + 32, kHashMinCtas) k_hash_fused(Has
         const int64_t r0 = (int64_t)tile * kTileR;
         if (t < 32) tile_lengths(p, r0, t, TR, s_off, s_eff, s_nfull, &s_maxfull);
         __syncthreads();
-        const int n_win = (s_maxfull + kWin - 1) / kWin;
+        const int n_win = (s_maxfull + W - 1) / W;
 
         if (warp < kDigestWarps) {
-            const int r = t / kWin, j = t % kWin;
+            const int r = t / W, j = t % W;
             const int32_t nfull = s_nfull[r];
             const uint8_t *base = p.data + s_off[r] + (uint64_t)j * (uint64_t)bs;
             if (n_stripes == 2 && p.prefetch) {
@@ -206,13 +207,13 @@ __global__ void __launch_bounds__(TR * kWin + 32, kHashMinCtas) k_hash_fused(Has
                     uint64_t x0[4], x1[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) { x0[q] = xa[q]; x1[q] = xb[q]; }
-                    if ((k + 1) * kWin + j < nfull) {
-                        const uint8_t *nx = base + (uint64_t)(k + 1) * (uint64_t)(kWin * bs);
+                    if ((k + 1) * W + j < nfull) {
+                        const uint8_t *nx = base + (uint64_t)(k + 1) * (uint64_t)(W * bs);
                         load_stripe<kAlign32>(nx, xa);
                         load_stripe<kAlign32>(nx + 32, xb);
                     }
                     if (k >= kStages) bar_sync(kBarEmpty + s, kProducers);
-                    if (k * kWin + j < nfull) s_m[s][r][j] = block_digest64(x0, x1);
+                    if (k * W + j < nfull) s_m[s][r][j] = block_digest64(x0, x1);
                     __threadfence_block();
                     bar_arrive(kBarFull + s, kProducers);
                 }
@@ -220,8 +221,8 @@ __global__ void __launch_bounds__(TR * kWin + 32, kHashMinCtas) k_hash_fused(Has
                 for (int k = 0; k < n_win; k++) {
                     const int s = k % kStages;
                     if (k >= kStages) bar_sync(kBarEmpty + s, kProducers);
-                    if (k * kWin + j < nfull)
-                        s_m[s][r][j] = block_digest<kAlign32>(base + (uint64_t)k * (uint64_t)(kWin * bs), n_stripes);
+                    if (k * W + j < nfull)
+                        s_m[s][r][j] = block_digest<kAlign32>(base + (uint64_t)k * (uint64_t)(W * bs), n_stripes);
                     __threadfence_block();
                     bar_arrive(kBarFull + s, kProducers);
                 }
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(TR * kWin + 32, kHashMinCtas) k_hash_fused(Has
             for (int k = 0; k < n_win; k++) {
                 const int s = k % kStages;
                 bar_sync(kBarFull + s, kProducers);
-                prev = chain_window<TR>(s_m[s], s_nfull, p, r0, k, lane, nfull, lenp8, prev);
+                prev = chain_window<TR, W>(s_m[s], s_nfull, p, r0, k, lane, nfull, lenp8, prev);
                 bar_arrive(kBarEmpty + s, kProducers);
             }
             if (mine && r < p.R) {                   // trailing partial block (hashing.go:90-96): generic tail, rare
@@ -565,9 +566,18 @@ __global__ void __launch_bounds__(TR * kWin + 32) k_cycle_fused(HashParams p, Pi
 }
 
 template <typename K, typename... Args>
+static cudaError_t launch_persistent_w(K kernel, int tile_r, int threads, int64_t R, int sm_count, cudaStream_t s,
+                                       int *occ_cache, Args... args);
+
+template <typename K, typename... Args>
 static cudaError_t launch_persistent(K kernel, int tile_r, int64_t R, int sm_count, cudaStream_t s, int *occ_cache,
                                      Args... args) {
-    const int threads = tile_r * kWin + 32;
+    return launch_persistent_w(kernel, tile_r, tile_r * kWin + 32, R, sm_count, s, occ_cache, args...);
+}
+
+template <typename K, typename... Args>
+static cudaError_t launch_persistent_w(K kernel, int tile_r, int threads, int64_t R, int sm_count, cudaStream_t s,
+                                       int *occ_cache, Args... args) {
     int n_tiles = (int)((R + tile_r - 1) / tile_r);
     if (!*occ_cache) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_cache, kernel, threads, 0);
@@ -602,7 +612,11 @@ cudaError_t launch_hash_fused(const HashParams &p, const PickParams *pick, int a
         if (tile_r == 32 && p.wide)
             e = a32 ? launch_persistent(k_hash_wide<true>, 32, p.R, sm_count, s, &occw[0], p)
                     : launch_persistent(k_hash_wide<false>, 32, p.R, sm_count, s, &occw[1], p);
-        else if (tile_r == 32)
+        else if (tile_r == 32 && p.win == 4) {
+            static int occ4[2] = {0, 0};
+            e = a32 ? launch_persistent_w(k_hash_fused<true, 32, 4, 8>, 32, 160, p.R, sm_count, s, &occ4[0], p)
+                    : launch_persistent_w(k_hash_fused<false, 32, 4, 8>, 32, 160, p.R, sm_count, s, &occ4[1], p);
+        } else if (tile_r == 32)
             e = a32 ? launch_persistent(k_hash_fused<true, 32>, 32, p.R, sm_count, s, &occ[4], p)
                     : launch_persistent(k_hash_fused<false, 32>, 32, p.R, sm_count, s, &occ[5], p);
         else

@@ -166,7 +166,9 @@ cudaError_t launch_hash_prompts(const HashParams &p, cudaStream_t s, int *launch
     int align = hash_batch_alignment(p);
     if (align >= 16 && !p.force_v1) {          // one fused kernel: lengths + digests + chain
         if (ev) { cudaEventRecord(ev[0], s); cudaEventRecord(ev[1], s); }
-        cudaError_t e = launch_hash_fused(p, p.fused_pick, align, p.sm_count, s, launches);
+        cudaError_t e = (p.bulk && !p.fused_pick && hash_bulk_supported(p))
+                            ? launch_hash_bulk(p, p.sm_count, s, launches)
+                            : launch_hash_fused(p, p.fused_pick, align, p.sm_count, s, launches);
         if (ev) { cudaEventRecord(ev[2], s); cudaEventRecord(ev[3], s); }
         return e;
     }

@@ -30,6 +30,8 @@ struct HashParams {
     int32_t tile_r;             // fused kernels: requests per CTA tile (32 default, 16)
     int32_t prefetch;           // hash kernel: register software prefetch of the next window (A/B)
     int32_t wide;               // hash kernel: 32-block windows (2-KiB DRAM bursts per warp load)
+    int32_t win;                // fused hash kernel: blocks per window (8 default; 4 = smaller CTAs, twice the chains in flight)
+    int32_t bulk;               // hash kernel fed by cp.async.bulk into shared memory: 0 off, else data stages (2/3/4; 5 = 2 stages, 5 CTAs)
     const struct PickParams *fused_pick;  // non-null: run a2-a14 inside the fused kernel's chain warp (fast path only)
 };
 // Common alignment (0, 16, 32) of every block start; >= 16 (and block_bytes % 32 == 0) enables the fused kernel.
@@ -40,6 +42,9 @@ cudaError_t launch_check_offsets_aligned(const uint64_t *offsets, int64_t n, int
 // Whole hashPrompt for a batch.  Returns number of kernels launched via *launches.
 // ev (optional, 4 events): recorded before the first kernel and after each of lengths / digests / chain.
 cudaError_t launch_hash_prompts(const HashParams &p, cudaStream_t s, int *launches, cudaEvent_t *ev = nullptr);
+// hash_bulk.cu: a1 with bulk-copy (TMA engine) staging of the prompt bytes; same contract as the fused kernel.
+bool hash_bulk_supported(const HashParams &p);
+cudaError_t launch_hash_bulk(const HashParams &p, int sm_count, cudaStream_t s, int *launches);
 
 // ------------------------------------------------------------------------------------------------
 // prefix index (a2): open-addressed table  hash -> (posting offset, count)
