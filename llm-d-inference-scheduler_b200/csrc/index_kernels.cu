@@ -63,8 +63,20 @@ __global__ void k_index_insert(const uint64_t *pair_hash, uint64_t n, IndexSlot 
 }
 
 __global__ void k_index_alloc(IndexSlot *slots, uint64_t capacity, uint32_t *cursor, IndexSlot *special) {
+    // one atomic per warp: the lanes' list lengths are prefix-summed with shuffles
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < capacity && slots[i].cnt) slots[i].ids[0] = atomicAdd(&cursor[0], slots[i].cnt);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t cnt = i < capacity ? slots[i].cnt : 0u;
+    uint32_t incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t base = 0;
+    if (lane == 31 && total) base = atomicAdd(&cursor[0], total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (cnt) slots[i].ids[0] = base + incl - cnt;
     if (i == 0 && special->cnt) special->ids[0] = atomicAdd(&cursor[0], special->cnt);
 }
 
