@@ -111,6 +111,7 @@ struct epp_engine {
     int force_v1 = 0;               // EPP_HASH_V1=1: unfused v1 hash kernels (A/B)
     int force_match_v1 = 0;         // EPP_MATCH_V1=1: dense-counter match kernel only (A/B)
     int prefetch = 0;               // EPP_PREFETCH=1
+    int chain_spread = 0;           // EPP_CHAIN_SPREAD=1
     int win = 8;                    // EPP_HASH_WIN=4: 4-block windows in k_hash_fused
     int bulk = 0;                   // EPP_HASH_BULK=2|3|4|5: bulk-copy fed hash kernel (hash_bulk.cu), data stages per CTA
     int wide = 0;                   // EPP_WIDE=1: 32-block windows in the hash kernel (A/B; measured slower)
@@ -242,6 +243,7 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
     { const char *v1 = getenv("EPP_MATCH_V1"); e->force_match_v1 = (v1 && v1[0] == '1') ? 1 : 0; }
     { const char *v1 = getenv("EPP_WIDE"); e->wide = (v1 && v1[0] == '1') ? 1 : 0; }
     { const char *v1 = getenv("EPP_HASH_BULK"); e->bulk = v1 ? atoi(v1) : 0; }
+    { const char *v1 = getenv("EPP_CHAIN_SPREAD"); e->chain_spread = v1 ? atoi(v1) : 0; }
     { const char *v1 = getenv("EPP_HASH_WIN"); e->win = v1 ? atoi(v1) : 8; }
     { const char *v1 = getenv("EPP_PREFETCH"); e->prefetch = (v1 && v1[0] == '1') ? 1 : 0; }
     { const char *v1 = getenv("EPP_TILE"); e->tile_r = (v1 && atoi(v1) == 16) ? 16 : 32; }
@@ -712,6 +714,7 @@ static HashParams hash_params(epp_engine *h, const Work &w) {
     p.wide = h->wide;
     p.bulk = h->bulk;
     p.win = h->win;
+    p.chain_spread = h->chain_spread;
     p.fused_pick = nullptr;
     return p;
 }

@@ -78,7 +78,11 @@ __global__ void __launch_bounds__(kThreads, MINCTA) k_hash_bulk(HashParams p, in
     __shared__ int32_t s_nfull[kTR];
     __shared__ int32_t s_maxfull;
 
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int lane = threadIdx.x & 31, hw_warp = threadIdx.x >> 5;
+    // see k_hash_fused: chain warp rotated over the SM sub-partitions per resident CTA (roles: 0-7 digest, 8 chain, 9 producer)
+    const int chain_at = p.chain_spread ? (int)((blockIdx.x / (unsigned)max(p.sm_count, 1)) & 3u) : kWin;
+    const int warp = hw_warp == kWin + 1 ? kWin + 1 : (hw_warp == chain_at ? kWin : (hw_warp > chain_at ? hw_warp - 1 : hw_warp));
+    const int t = threadIdx.x;
     const int64_t bs = p.block_bytes;
     const int n_stripes = (int)(bs >> 5);
     const uint64_t lenp8 = (uint64_t)bs + 8;

@@ -181,8 +181,14 @@ __global__ void __launch_bounds__(TR * W + 32, MINCTA) k_hash_fused(HashParams p
     __shared__ int32_t s_nfull[kTileR];
     __shared__ int32_t s_maxfull;
 
-    const int t = threadIdx.x;
-    const int warp = t >> 5, lane = t & 31;
+    // Role placement: the chain warp is the serial critical path and warps are bound to the four SM sub-partitions by
+    // warp index mod 4; with the chain always on the last warp every co-resident CTA puts it on the SAME scheduler.
+    // p.chain_spread rotates it by the CTA's residency slot (blockIdx / SM count) so the chains sit on different ones.
+    const int lane = threadIdx.x & 31;
+    const int hw_warp = threadIdx.x >> 5;
+    const int chain_at = p.chain_spread ? (int)((blockIdx.x / (unsigned)max(p.sm_count, 1)) & 3u) : kDigestWarps;
+    const int warp = hw_warp == chain_at ? kDigestWarps : (hw_warp > chain_at ? hw_warp - 1 : hw_warp);
+    const int t = warp * 32 + lane;
     const int64_t bs = p.block_bytes;
     const int n_stripes = (int)(bs >> 5);
     const uint64_t lenp8 = (uint64_t)bs + 8;
