@@ -111,6 +111,10 @@ struct epp_engine {
     int force_v1 = 0;               // EPP_HASH_V1=1: unfused v1 hash kernels (A/B)
     int force_match_v1 = 0;         // EPP_MATCH_V1=1: dense-counter match kernel only (A/B)
     int prefetch = 0;               // EPP_PREFETCH=1
+    int tile_rows = 32;             // EPP_TILE_ROWS=n: requests per hash tile (0 = balance the waves of the persistent grid; measured: no gain)
+    int dev_ordered = 0;            // EPP_DEV_ORDERED=1: chunk c's hash kernel waits for chunk c-1's
+    cudaEvent_t hash_done[8] = {};
+    int dev_chunks = 2;             // EPP_DEV_CHUNKS=N: async device batches run as N chunks over both streams (1 = off)
     int chain_spread = 0;           // EPP_CHAIN_SPREAD=1
     int win = 8;                    // EPP_HASH_WIN=4: 4-block windows in k_hash_fused
     int bulk = 0;                   // EPP_HASH_BULK=2|3|4|5: bulk-copy fed hash kernel (hash_bulk.cu), data stages per CTA
@@ -243,6 +247,10 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
     { const char *v1 = getenv("EPP_MATCH_V1"); e->force_match_v1 = (v1 && v1[0] == '1') ? 1 : 0; }
     { const char *v1 = getenv("EPP_WIDE"); e->wide = (v1 && v1[0] == '1') ? 1 : 0; }
     { const char *v1 = getenv("EPP_HASH_BULK"); e->bulk = v1 ? atoi(v1) : 0; }
+    { const char *v1 = getenv("EPP_TILE_ROWS"); e->tile_rows = v1 ? atoi(v1) : 32; }
+    { const char *v1 = getenv("EPP_DEV_ORDERED"); e->dev_ordered = v1 ? atoi(v1) : 0; }
+    for (auto &ev : e->hash_done) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    { const char *v1 = getenv("EPP_DEV_CHUNKS"); e->dev_chunks = v1 ? std::max(1, atoi(v1)) : 2; }
     { const char *v1 = getenv("EPP_CHAIN_SPREAD"); e->chain_spread = v1 ? atoi(v1) : 0; }
     { const char *v1 = getenv("EPP_HASH_WIN"); e->win = v1 ? atoi(v1) : 8; }
     { const char *v1 = getenv("EPP_PREFETCH"); e->prefetch = (v1 && v1[0] == '1') ? 1 : 0; }
@@ -277,6 +285,7 @@ extern "C" int32_t epp_engine_destroy(epp_engine *h) {
     }
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->user_ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : h->hash_done) if (ev) cudaEventDestroy(ev);
     if (h->wc_host) cudaFreeHost(h->wc_host);
     delete h;
     return EPP_OK;
@@ -715,6 +724,7 @@ static HashParams hash_params(epp_engine *h, const Work &w) {
     p.bulk = h->bulk;
     p.win = h->win;
     p.chain_spread = h->chain_spread;
+    p.tile_rows = h->tile_rows;
     p.fused_pick = nullptr;
     return p;
 }
@@ -851,7 +861,39 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
                (mode == Mode::HashOnly && out_hashes) ? out_hashes : h->hashes.as<uint64_t>(),
                (mode == Mode::HashOnly && out_nblocks) ? out_nblocks : (mode == Mode::Match && out_total ? out_total : h->nblocks.as<int32_t>())};
         CUDA_TRY(cudaMemsetAsync(h->work_counters.p, 0, sizeof(unsigned long long) * 2, s0));
-        if (mode == Mode::HashOnly) {
+        const int64_t min_chunk = 4096;
+        if (v.async && mode == Mode::Schedule && h->dev_chunks > 1 && R >= 2 * min_chunk && !h->pick_global) {
+            // Throughput mode: the batch runs as C chunks alternating between the engine's two streams, so the hash
+            // kernel of chunk c+1 (HBM / integer bound) shares the SMs with the match kernel of chunk c (latency bound).
+            const int64_t C = std::min<int64_t>(h->dev_chunks, R / min_chunk);
+            const int64_t per = ((R + C - 1) / C + 31) & ~(int64_t)31;
+            cudaStream_t s1 = h->slot[1].stream;
+            for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventRecord(h->ev[i], s0));
+            CUDA_TRY(cudaEventRecord(h->slot[0].done, s0));
+            CUDA_TRY(cudaStreamWaitEvent(s1, h->slot[0].done, 0));
+            epp_decision *dec_base = out_dec ? out_dec : h->decisions.as<epp_decision>();
+            int k = 0;
+            for (int64_t r0 = 0; r0 < R; r0 += per, k++) {
+                const int64_t r1 = std::min(R, r0 + per);
+                Work w{r0, r1, v.offsets ? v.data : v.data + (uint64_t)r0 * v.uniform_len, v.offsets, v.lengths, v.uniform_len,
+                       v.model_ids, or_bits, h->hashes.as<uint64_t>() + (size_t)r0 * B, h->nblocks.as<int32_t>() + r0};
+                PickParams pp = pick_params(h, w, dec_base + r0, out_detail ? out_detail + r0 : nullptr, nullptr);
+                pp.work_counters = h->work_counters.as<unsigned long long>();
+                Slot &sl = h->slot[k & 1];
+                if (h->dev_ordered && !h->force_v1 && !h->force_match_v1 && h->no_fuse) {
+                    // ordered pipeline: hash(c) starts when hash(c-1) is done, so it runs beside match(c-1) rather
+                    // than beside the previous hash kernel
+                    if (k > 0) CUDA_TRY(cudaStreamWaitEvent(sl.stream, h->hash_done[(k - 1) & 7], 0));
+                    CUDA_TRY(launch_hash_prompts(hash_params(h, w), sl.stream, &launches, nullptr));
+                    CUDA_TRY(cudaEventRecord(h->hash_done[k & 7], sl.stream));
+                    EPP_TRY(launch_match(h, sl, pp, &launches));
+                } else {
+                    EPP_TRY(launch_cycle(h, sl, hash_params(h, w), pp, &launches, nullptr));
+                }
+            }
+            CUDA_TRY(cudaEventRecord(h->slot[1].done, s1));
+            CUDA_TRY(cudaStreamWaitEvent(s0, h->slot[1].done, 0));
+        } else if (mode == Mode::HashOnly) {
             CUDA_TRY(launch_hash_prompts(hash_params(h, w), s0, &launches, h->ev));
         } else {
             epp_decision *dec = (mode == Mode::Schedule && out_dec) ? out_dec : h->decisions.as<epp_decision>();

@@ -70,7 +70,7 @@ __device__ __forceinline__ void load_stripe(const uint8_t *p, uint64_t x[4]) {
 
 // Per-request lengths (hashing.go:58-66) for one tile; called by the first warp (threads t < 32; t >= TR idle).
 __device__ __forceinline__ void tile_lengths(const HashParams &p, int64_t r0, int t, int tr, uint64_t *s_off,
-                                             int64_t *s_eff, int32_t *s_nfull, int32_t *s_maxfull) {
+                                             int64_t *s_eff, int32_t *s_nfull, int32_t *s_maxfull, int rows_alloc = 0) {
     const int64_t bs = p.block_bytes;
     int64_t r = r0 + t;
     uint64_t off = 0;
@@ -98,6 +98,10 @@ __device__ __forceinline__ void tile_lengths(const HashParams &p, int64_t r0, in
         s_off[t] = off;
         s_eff[t] = eff;
         s_nfull[t] = nfull;
+    } else if (t < rows_alloc) {          // rows of the CTA that this (smaller) tile does not use
+        s_off[t] = 0;
+        s_eff[t] = 0;
+        s_nfull[t] = 0;
     }
     int mx = nfull;
     for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -193,9 +197,11 @@ __global__ void __launch_bounds__(TR * W + 32, MINCTA) k_hash_fused(HashParams p
     const int n_stripes = (int)(bs >> 5);
     const uint64_t lenp8 = (uint64_t)bs + 8;
 
+    // rows per tile: TR, or fewer when the launcher balances the waves of the persistent grid (p.tile_rows)
+    const int tr = (p.tile_rows > 0 && p.tile_rows < TR) ? p.tile_rows : TR;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t r0 = (int64_t)tile * kTileR;
-        if (t < 32) tile_lengths(p, r0, t, TR, s_off, s_eff, s_nfull, &s_maxfull);
+        const int64_t r0 = (int64_t)tile * tr;
+        if (t < 32) tile_lengths(p, r0, t, tr, s_off, s_eff, s_nfull, &s_maxfull, TR);
         __syncthreads();
         const int n_win = (s_maxfull + W - 1) / W;
 
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(TR * W + 32, MINCTA) k_hash_fused(HashParams p
             int first = n_win > kStages ? n_win - kStages : 0;
             for (int k = first; k < n_win; k++) bar_sync(kBarEmpty + (k % kStages), kProducers);
         } else {
-            const bool mine = lane < TR;
+            const bool mine = lane < tr;
             const int64_t r = r0 + lane;
             const int32_t nfull = mine ? s_nfull[lane] : 0;
             uint64_t prev = 0;
@@ -622,9 +628,33 @@ cudaError_t launch_hash_fused(const HashParams &p, const PickParams *pick, int a
             static int occ4[2] = {0, 0};
             e = a32 ? launch_persistent_w(k_hash_fused<true, 32, 4, 8>, 32, 160, p.R, sm_count, s, &occ4[0], p)
                     : launch_persistent_w(k_hash_fused<false, 32, 4, 8>, 32, 160, p.R, sm_count, s, &occ4[1], p);
-        } else if (tile_r == 32)
-            e = a32 ? launch_persistent(k_hash_fused<true, 32>, 32, p.R, sm_count, s, &occ[4], p)
-                    : launch_persistent(k_hash_fused<false, 32>, 32, p.R, sm_count, s, &occ[5], p);
+        } else if (tile_r == 32) {
+            // Wave balancing: 2 048 tiles of 32 requests over 592 resident CTAs is 3.46 waves -- the last one 46 % full
+            // but as long as the others.  Shrinking the tile to `rows` requests (rows of the CTA left idle) makes the
+            // tile count a near multiple of the CTA slots: cost ~ waves x (rows + fixed per-tile overhead).
+            HashParams q = p;
+            int &oc = occ[a32 ? 4 : 5];
+            if (!oc) {
+                if (a32) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, k_hash_fused<true, 32>, 288, 0);
+                else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, k_hash_fused<false, 32>, 288, 0);
+                if (oc < 1) oc = 1;
+            }
+            int rows = 32;
+            if (p.tile_rows > 0) {
+                rows = p.tile_rows < 32 ? p.tile_rows : 32;
+            } else if (p.tile_rows == 0) {
+                const int64_t slots = (int64_t)(sm_count > 0 ? sm_count : 148) * oc;
+                double best = 1e30;
+                for (int tr = 32; tr >= 8; tr--) {
+                    const int64_t tiles = (p.R + tr - 1) / tr, waves = (tiles + slots - 1) / slots;
+                    const double cost = (double)waves * (tr + 4.0);
+                    if (cost < best * 0.97) { best = cost; rows = tr; }     // prefer full tiles unless clearly better
+                }
+            }
+            q.tile_rows = rows;
+            e = a32 ? launch_persistent_w(k_hash_fused<true, 32>, rows, 288, p.R, sm_count, s, &oc, q)
+                    : launch_persistent_w(k_hash_fused<false, 32>, rows, 288, p.R, sm_count, s, &oc, q);
+        }
         else
             e = a32 ? launch_persistent(k_hash_fused<true, 16>, 16, p.R, sm_count, s, &occ[6], p)
                     : launch_persistent(k_hash_fused<false, 16>, 16, p.R, sm_count, s, &occ[7], p);

@@ -30,6 +30,7 @@ struct HashParams {
     int32_t tile_r;             // fused kernels: requests per CTA tile (32 default, 16)
     int32_t prefetch;           // hash kernel: register software prefetch of the next window (A/B)
     int32_t wide;               // hash kernel: 32-block windows (2-KiB DRAM bursts per warp load)
+    int32_t tile_rows;          // k_hash_fused: requests per tile actually used (0 = launcher balances the waves, -1/32 = all 32)
     int32_t chain_spread;       // fused hash kernels: rotate the chain warp over the SM sub-partitions per resident CTA
     int32_t win;                // fused hash kernel: blocks per window (8 default; 4 = smaller CTAs, twice the chains in flight)
     int32_t bulk;               // hash kernel fed by cp.async.bulk into shared memory: 0 off, else data stages (2/3/4; 5 = 2 stages, 5 CTAs)

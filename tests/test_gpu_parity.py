@@ -440,6 +440,37 @@ def test_async_device_batches_match_synchronous_ones(epp, orc, tg):
             eng.schedule(tokens[:8], uniform_len=w.prompt_bytes, asynchronous=True)      # host buffers cannot be async
 
 
+def test_async_chunk_pipelined_batches(epp, orc, tg, monkeypatch):
+    """EPP_DEV_CHUNKS: an async device batch split into chunks that alternate between the engine's two streams (hash of
+    chunk c+1 overlapping match of chunk c) must produce exactly the synchronous single-pass decisions, ragged tail
+    chunk included, and leave the hashes in place for epp_index_add_picked."""
+    import torch
+    import helpers
+    monkeypatch.setenv("EPP_DEV_CHUNKS", "4")
+    w = tg.baseline_configs()["config4"].scaled(E=192, R=20000 + 37, T=512, name="config4")
+    w.non_cached_tokens = 64
+    trace = tg.Trace(w)
+    tokens, _, _ = trace.requests()
+    with helpers.make_engine(w) as eng:
+        helpers.setup_engine(eng, w, trace)
+        dt = torch.from_numpy(tokens.view(np.int32)).cuda()
+        want, want_det = eng.schedule(dt, uniform_len=w.prompt_bytes)
+        want = epp.decisions_from_torch(want)
+        out = torch.zeros((w.R, 32), dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        for _ in range(3):
+            eng.schedule(dt, uniform_len=w.prompt_bytes, detail=False, out=out, asynchronous=True)
+        eng.synchronize()
+        np.testing.assert_array_equal(epp.decisions_from_torch(out), want)
+        assert (want["prefill_pick"] != 0xFFFFFFFF).any() and eng.stats()["last_kernel_launches"] >= 8
+        # ragged offsets through the same path
+        offs = torch.arange(w.R + 1, dtype=torch.int64, device="cuda") * w.prompt_bytes
+        out.zero_()
+        eng.schedule(dt, offsets=offs, detail=False, out=out, asynchronous=True)
+        eng.synchronize()
+        np.testing.assert_array_equal(epp.decisions_from_torch(out), want)
+
+
 def test_global_stop_rule_and_holes(epp, orc):
     """Non-prefix-closed index states: the walk stops at the first block NOBODY holds; endpoints missing earlier
     blocks still count later ones; endpoints outside the slot range keep the walk alive (App. C.5)."""
