@@ -77,6 +77,8 @@ struct epp_engine {
     cudaEvent_t user_ev[2] = {};    // epp_event_record / epp_event_elapsed_ms
     unsigned long long *wc_host = nullptr;   // pinned: work counters of an async batch
     bool async_pending = false;     // an EPP_BATCH_ASYNC batch whose stats have not been read back yet
+    bool s1_unjoined = false;       // chunk-pipelined async batches left work on stream 1 that stream 0 has not waited for
+    int64_t pipe_R = 0, pipe_per = 0;   // chunk layout of the pipelined batches in flight (row ranges are per stream)
     int async_launches = 0;
     DevBuf work_counters;           // u64[2] probes, postings
 
@@ -134,6 +136,16 @@ static constexpr int kMaxModels = 4096;
 
 static int32_t set_device(epp_engine *e) {
     CUDA_TRY(cudaSetDevice(e->cfg.device));
+    return EPP_OK;
+}
+
+// Orders stream 0 after whatever chunk-pipelined async batches left on stream 1 (no host synchronisation).  Every entry
+// point that enqueues on stream 0 calls it first, so everything outside the pipelined path stays in call order.
+static int32_t join_streams(epp_engine *e) {
+    if (!e->s1_unjoined) return EPP_OK;
+    CUDA_TRY(cudaEventRecord(e->slot[1].done, e->slot[1].stream));
+    CUDA_TRY(cudaStreamWaitEvent(e->slot[0].stream, e->slot[1].done, 0));
+    e->s1_unjoined = false;
     return EPP_OK;
 }
 
@@ -310,6 +322,7 @@ extern "C" int32_t epp_model_register(epp_engine *h, const uint8_t *model, size_
     if ((model_len && !model) || (salt_len && !salt)) return fail(EPP_ERR_INVALID, "NULL model/salt with non-zero length");
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
     if (h->n_models >= kMaxModels) return fail(EPP_ERR_CAPACITY, "too many registered models (max %d)", kMaxModels);
     size_t n = model_len + salt_len;
     std::vector<uint8_t> msg(n ? n : 1);
@@ -370,6 +383,7 @@ extern "C" int32_t epp_pool_set(epp_engine *h, int32_t n, const uint32_t *ids, c
     if (h->cfg.n_ext_cols > 0 && n > 0 && !ext) return fail(EPP_ERR_INVALID, "ext columns configured but ext is NULL");
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
     const int32_t E = h->cfg.max_endpoints;
     std::vector<uint8_t> r(E, 0xFF);
     std::vector<double> kv(E, 0.0);
@@ -511,6 +525,7 @@ static double ms_since(std::chrono::steady_clock::time_point t0) {
 
 static int32_t commit_locked(epp_engine *h) {
     if (h->snapshot_mode) return EPP_OK;
+    if (!h->q_ep.empty() || h->store->dirty()) EPP_TRY(join_streams(h));     // the table is about to change under stream 1
     EPP_TRY(flush_add_queue(h));
     if (!h->store->dirty()) return EPP_OK;
     auto t0 = std::chrono::steady_clock::now();
@@ -546,6 +561,7 @@ extern "C" int32_t epp_index_add(epp_engine *h, uint32_t ep, int32_t n, const ui
     h->q_hashes.insert(h->q_hashes.end(), hashes, hashes + n);
     if (h->q_hashes.size() >= (1u << 26) || h->q_ep.size() >= (1u << 22)) {      // bound the host queue
         EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
         EPP_TRY(flush_add_queue(h));
     }
     return EPP_OK;
@@ -556,6 +572,7 @@ extern "C" int32_t epp_index_remove_endpoint(epp_engine *h, uint32_t ep) {
     std::lock_guard<std::mutex> lk(h->mu);
     if (h->snapshot_mode) return fail(EPP_ERR_STATE, "index holds a bulk snapshot; reload it without the endpoint instead");
     EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
     EPP_TRY(flush_add_queue(h));                    // calls apply in the order they were made
     CUDA_TRY(h->store->remove_endpoint(ep, h->slot[0].stream));
     return EPP_OK;
@@ -567,6 +584,7 @@ extern "C" int32_t epp_index_retain_endpoints(epp_engine *h, int32_t n, const ui
     std::lock_guard<std::mutex> lk(h->mu);
     if (h->snapshot_mode) return fail(EPP_ERR_STATE, "index holds a bulk snapshot; reload it without the endpoints instead");
     EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
     EPP_TRY(flush_add_queue(h));
     const size_t E = (size_t)h->cfg.max_endpoints;
     std::vector<uint8_t> active(E, 0);
@@ -585,6 +603,7 @@ extern "C" int32_t epp_index_load_snapshot(epp_engine *h, uint64_t n_pairs, cons
     if (!h || (n_pairs && (!hashes || !eps))) return fail(EPP_ERR_INVALID, "bad arguments");
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
     h->q_ep.clear(); h->q_n.clear(); h->q_nb.clear(); h->q_src.clear(); h->q_hashes.clear();
     CUDA_TRY(h->store->clear(h->slot[0].stream));
     h->store->mark_clean();
@@ -597,6 +616,7 @@ extern "C" int32_t epp_index_commit(epp_engine *h) {
     if (!h) return fail(EPP_ERR_INVALID, "NULL engine");
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
     return commit_locked(h);
 }
 
@@ -604,6 +624,7 @@ extern "C" int32_t epp_index_get(epp_engine *h, uint64_t hash, uint32_t *out_eps
     if (!h || !out_n || cap < 0 || (cap > 0 && !out_eps)) return fail(EPP_ERR_INVALID, "bad arguments");
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
     EPP_TRY(commit_locked(h));
     cudaStream_t s = h->slot[0].stream;
     int32_t dcap = std::min(cap, 4096);
@@ -821,6 +842,7 @@ static int32_t launch_cycle(epp_engine *h, Slot &sl, const HashParams &hp_in, Pi
 
 // Completes the device batch in flight on stream 0 and reads its per-kernel CUDA-event times and work counters.
 static int32_t finish_async(epp_engine *h) {
+    EPP_TRY(join_streams(h));
     CUDA_TRY(cudaStreamSynchronize(h->slot[0].stream));
     if (!h->async_pending) return EPP_OK;
     h->async_pending = false;
@@ -850,6 +872,8 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
         EPP_TRY(commit_locked(h));
     }
     if (h->async_pending && !(v.device && v.async)) EPP_TRY(finish_async(h));
+    const bool pipelined = v.device && v.async && mode == Mode::Schedule && h->dev_chunks > 1 && R >= 2 * 4096 && !h->pick_global;
+    if (!pipelined) EPP_TRY(join_streams(h));
     EPP_TRY(reserve_batch(h, R));
     int launches = 0;
     cudaStream_t s0 = h->slot[0].stream;
@@ -862,15 +886,20 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
                (mode == Mode::HashOnly && out_nblocks) ? out_nblocks : (mode == Mode::Match && out_total ? out_total : h->nblocks.as<int32_t>())};
         CUDA_TRY(cudaMemsetAsync(h->work_counters.p, 0, sizeof(unsigned long long) * 2, s0));
         const int64_t min_chunk = 4096;
-        if (v.async && mode == Mode::Schedule && h->dev_chunks > 1 && R >= 2 * min_chunk && !h->pick_global) {
+        if (pipelined) {
             // Throughput mode: the batch runs as C chunks alternating between the engine's two streams, so the hash
-            // kernel of chunk c+1 (HBM / integer bound) shares the SMs with the match kernel of chunk c (latency bound).
+            // kernel of one chunk (HBM / integer bound) shares the SMs with the match kernel of another (latency bound).
+            // Consecutive pipelined batches of the same shape are not joined: every row range of the engine's buffers is
+            // only ever touched by one stream, and the next entry point of any other kind joins the streams first.
             const int64_t C = std::min<int64_t>(h->dev_chunks, R / min_chunk);
             const int64_t per = ((R + C - 1) / C + 31) & ~(int64_t)31;
             cudaStream_t s1 = h->slot[1].stream;
+            if (h->s1_unjoined && (h->pipe_R != R || h->pipe_per != per)) EPP_TRY(join_streams(h));
             for (int i = 0; i < 4; i++) CUDA_TRY(cudaEventRecord(h->ev[i], s0));
-            CUDA_TRY(cudaEventRecord(h->slot[0].done, s0));
-            CUDA_TRY(cudaStreamWaitEvent(s1, h->slot[0].done, 0));
+            if (!h->s1_unjoined) {
+                CUDA_TRY(cudaEventRecord(h->slot[0].done, s0));
+                CUDA_TRY(cudaStreamWaitEvent(s1, h->slot[0].done, 0));
+            }
             epp_decision *dec_base = out_dec ? out_dec : h->decisions.as<epp_decision>();
             int k = 0;
             for (int64_t r0 = 0; r0 < R; r0 += per, k++) {
@@ -878,11 +907,9 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
                 Work w{r0, r1, v.offsets ? v.data : v.data + (uint64_t)r0 * v.uniform_len, v.offsets, v.lengths, v.uniform_len,
                        v.model_ids, or_bits, h->hashes.as<uint64_t>() + (size_t)r0 * B, h->nblocks.as<int32_t>() + r0};
                 PickParams pp = pick_params(h, w, dec_base + r0, out_detail ? out_detail + r0 : nullptr, nullptr);
-                pp.work_counters = h->work_counters.as<unsigned long long>();
                 Slot &sl = h->slot[k & 1];
                 if (h->dev_ordered && !h->force_v1 && !h->force_match_v1 && h->no_fuse) {
-                    // ordered pipeline: hash(c) starts when hash(c-1) is done, so it runs beside match(c-1) rather
-                    // than beside the previous hash kernel
+                    // ordered pipeline (A/B): hash(c) starts when hash(c-1) is done
                     if (k > 0) CUDA_TRY(cudaStreamWaitEvent(sl.stream, h->hash_done[(k - 1) & 7], 0));
                     CUDA_TRY(launch_hash_prompts(hash_params(h, w), sl.stream, &launches, nullptr));
                     CUDA_TRY(cudaEventRecord(h->hash_done[k & 7], sl.stream));
@@ -891,8 +918,9 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
                     EPP_TRY(launch_cycle(h, sl, hash_params(h, w), pp, &launches, nullptr));
                 }
             }
-            CUDA_TRY(cudaEventRecord(h->slot[1].done, s1));
-            CUDA_TRY(cudaStreamWaitEvent(s0, h->slot[1].done, 0));
+            h->s1_unjoined = true;
+            h->pipe_R = R;
+            h->pipe_per = per;
         } else if (mode == Mode::HashOnly) {
             CUDA_TRY(launch_hash_prompts(hash_params(h, w), s0, &launches, h->ev));
         } else {
@@ -1036,6 +1064,7 @@ extern "C" int32_t epp_schedule(epp_engine *h, const epp_batch *batch, epp_decis
     if (keep_hashes && v.R) {
         // the decisions stay on the device next to the hashes; host batches already have them in h->decisions
         cudaStream_t s0 = h->slot[0].stream;
+        EPP_TRY(join_streams(h));
         CUDA_TRY(h->kept_dec.reserve(sizeof(epp_decision) * (size_t)v.R, &h->dev_bytes));
         const void *src = v.device ? (const void *)out : (const void *)h->decisions.p;
         CUDA_TRY(cudaMemcpyAsync(h->kept_dec.p, src, sizeof(epp_decision) * (size_t)v.R, cudaMemcpyDeviceToDevice, s0));
@@ -1050,6 +1079,7 @@ extern "C" int32_t epp_index_add_picked(epp_engine *h) {
     if (!h) return fail(EPP_ERR_INVALID, "NULL engine");
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
     if (h->kept_R == 0) return fail(EPP_ERR_STATE, "no batch kept (call epp_schedule with keep_hashes=1 first)");
     if (h->snapshot_mode) return fail(EPP_ERR_STATE, "index holds a bulk snapshot; incremental adds need an incrementally built index");
     EPP_TRY(flush_add_queue(h));
@@ -1071,6 +1101,7 @@ extern "C" int32_t epp_score(epp_engine *h, int64_t n_requests, const int32_t *m
     if (!h || n_requests < 0 || (n_requests && (!match || !total || !out_scores))) return fail(EPP_ERR_INVALID, "bad arguments");
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
     if (!h->pool_ready) return fail(EPP_ERR_STATE, "epp_pool_set has not been called");
     if (profile < 0 || profile >= h->n_profiles) return fail(EPP_ERR_INVALID, "profile %d out of range", profile);
     const epp_profile_cfg &pc = profile == 0 ? h->cfg.primary : h->cfg.prefill;
@@ -1105,6 +1136,7 @@ extern "C" int32_t epp_schedule_with_match(epp_engine *h, int64_t n_requests, co
     if (!h || n_requests < 0 || (n_requests && (!match || !total || !out))) return fail(EPP_ERR_INVALID, "bad arguments");
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
     if (!h->pool_ready) return fail(EPP_ERR_STATE, "epp_pool_set has not been called");
     if (n_requests == 0) return EPP_OK;
     const size_t E = (size_t)h->cfg.max_endpoints, n = (size_t)n_requests * E, R = (size_t)n_requests;
@@ -1158,6 +1190,7 @@ extern "C" int32_t epp_synchronize(epp_engine *h) {
     if (!h) return fail(EPP_ERR_INVALID, "NULL engine");
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
     EPP_TRY(finish_async(h));
     CUDA_TRY(cudaStreamSynchronize(h->slot[1].stream));
     return EPP_OK;
@@ -1167,6 +1200,7 @@ extern "C" int32_t epp_event_record(epp_engine *h, int32_t which) {
     if (!h || which < 0 || which > 1) return fail(EPP_ERR_INVALID, "bad arguments");
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
     CUDA_TRY(cudaEventRecord(h->user_ev[which], h->slot[0].stream));
     return EPP_OK;
 }
@@ -1175,6 +1209,7 @@ extern "C" int32_t epp_event_elapsed_ms(epp_engine *h, double *out_ms) {
     if (!h || !out_ms) return fail(EPP_ERR_INVALID, "bad arguments");
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
     CUDA_TRY(cudaEventSynchronize(h->user_ev[1]));
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, h->user_ev[0], h->user_ev[1]));
@@ -1201,6 +1236,7 @@ extern "C" int32_t epp_shard_probe(epp_engine *h, const epp_batch *batch, uint32
     if (!h || !out_masks) return fail(EPP_ERR_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
     BatchView v;
     EPP_TRY(check_batch(h, batch, v));
     if (!v.device) return fail(EPP_ERR_INVALID, "epp_shard_probe takes device-pointer batches (EPP_BATCH_DEVICE_PTRS)");
@@ -1221,6 +1257,7 @@ extern "C" int32_t epp_shard_pick(epp_engine *h, int64_t n_requests, const uint3
     if (!h || !global_masks || !out_best) return fail(EPP_ERR_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
     if (!h->pool_ready) return fail(EPP_ERR_STATE, "epp_pool_set has not been called (after epp_shard_set)");
     if (n_requests != h->shard_R) return fail(EPP_ERR_STATE, "epp_shard_pick: n_requests %lld does not match the probed batch (%lld)", (long long)n_requests, (long long)h->shard_R);
     if (n_requests == 0) return EPP_OK;
@@ -1241,6 +1278,7 @@ extern "C" int32_t epp_shard_merge(epp_engine *h, int64_t n_requests, int32_t n_
     if (!h || !all_best || !out || n_ranks <= 0) return fail(EPP_ERR_INVALID, "bad arguments");
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
     if (n_requests != h->shard_R) return fail(EPP_ERR_STATE, "epp_shard_merge: n_requests does not match the probed batch");
     int launches = 0;
     cudaStream_t s = h->slot[0].stream;
