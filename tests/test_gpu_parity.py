@@ -307,6 +307,51 @@ def test_index_add_picked_many_batches_vs_oracle(epp, orc, tg):
         assert eng.stats()["index_pairs"] == len(ix.export()[0])
 
 
+def test_full_size_write_side_vs_oracle(epp, orc, tg):
+    """BASELINE config 3 at FULL size through the write side: schedule 65 536 requests, index all their picks on the
+    device (16.8 M indexer.Add hashes, LRU capacity 31 250 -> the hot endpoints evict millions of entries), then
+    schedule the NEXT 65 536 requests: every decision must equal the oracle's, whose indexer ran the same Adds one
+    request at a time.  Also: the inverted maps have the same number of pairs."""
+    import torch
+    import helpers
+    w = tg.baseline_configs()["config3"]
+    trace = tg.Trace(w)
+    role, kv, waiting, running = trace.pool()
+    pool = orc.PoolState(role, kv, waiting, running)
+    primary = orc.make_profile(w.primary_filter, list(w.primary_scorers))
+    ix = orc.Indexer()
+    nthr = min(64, os.cpu_count() or 1)
+    with helpers.make_engine(w) as eng:
+        eng.register_model(tg.MODEL)
+        eng.pool_set(np.arange(w.E, dtype=np.uint32), role, kv, waiting, running)
+        fh, _ = eng.hash_prompts(trace.family_tokens(), uniform_len=w.prompt_bytes)
+        hs, es = trace.index_pairs(fh)
+        order = np.argsort(es, kind="stable")
+        hs, es = hs[order], es[order]
+        cuts = np.flatnonzero(np.diff(es)) + 1
+        for seg_h, seg_e in zip(np.split(hs, cuts), np.split(es, cuts)):     # seed through indexer.Add, not a snapshot
+            eng.index_add(int(seg_e[0]), seg_h)
+            ix.add(seg_h, int(seg_e[0]))
+        for b in range(2):
+            tokens, _, _ = trace.requests(b * w.R, w.R)
+            odec, ototal = helpers.oracle_decisions(orc, w, pool, ix, primary, None, tokens, n_threads=nthr)
+            dt = torch.from_numpy(tokens.view(np.int32)).cuda()
+            ddec, _ = eng.schedule(dt, uniform_len=w.prompt_bytes, detail=False, keep_hashes=True)
+            dec = epp.decisions_from_torch(ddec)
+            helpers.assert_decisions_equal(dec, None, odec, ototal, where=f"full-size batch {b}")
+            if b == 0:
+                eng.index_add_picked()
+                hh, nb = eng.hash_prompts(dt, uniform_len=w.prompt_bytes)
+                hh = hh.cpu().numpy().view(np.uint64)
+                nb = nb.cpu().numpy()
+                for r in range(w.R):                                          # plugin.go:164-200, sequentially
+                    if odec["status"][r] == 0:
+                        ix.add(hh[r, : nb[r]], int(odec["pick"][r]))
+                eng.index_commit()
+                assert eng.stats()["index_pairs"] == len(ix.export()[0])
+                assert eng.stats()["last_index_items"] == int(nb[odec["status"] == 0].sum())
+
+
 def test_index_kats(epp):
     """indexer_test.go:27-113 re-encoded against the engine."""
     with epp.Engine(8, lru_capacity_per_server=3) as eng:
