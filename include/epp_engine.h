@@ -48,7 +48,7 @@ extern "C" {
 #define EPP_API
 #endif
 
-#define EPP_ABI_VERSION 2
+#define EPP_ABI_VERSION 3
 #define EPP_MAX_SCORERS 8
 #define EPP_NO_ENDPOINT 0xFFFFFFFFu
 
@@ -75,9 +75,11 @@ typedef enum {
     EPP_SCORER_RUNNING = 5,    /* "running-requests-size-scorer" scorer/runningrequests/runningrequest.go:78-108 */
     EPP_SCORER_TOKEN_LOAD = 6, /* "token-load-scorer"            scorer/tokenload/token_load.go:84-112; column = ext column
                                   holding InFlightLoad.Tokens, param = queueThresholdTokens (<= 0: 4194304)       */
-    EPP_SCORER_ACTIVE_REQUEST = 7 /* "active-request-scorer"     scorer/activerequest/active_request.go:140-173; column = ext
+    EPP_SCORER_ACTIVE_REQUEST = 7, /* "active-request-scorer"    scorer/activerequest/active_request.go:140-173; column = ext
                                   column holding InFlightLoad.Requests, param = maxBusyScore (outside [0,1]: 1.0),
                                   param2 = idleThreshold (< 0: 0)                                                 */
+    EPP_SCORER_LORA_AFFINITY = 8  /* "lora-affinity-scorer"      scorer/loraaffinity/lora_affinity.go:76-100; the adapter is the
+                                  request's model id; residency comes from epp_pool_set_lora                     */
 } epp_scorer_kind;
 
 /* Value of the llm-d.ai/role label (filter/bylabel/roles.go:25-44). */
@@ -226,6 +228,15 @@ EPP_API int32_t epp_model_seed(epp_engine *h, uint32_t model_id, uint64_t *out_s
 EPP_API int32_t epp_pool_set(epp_engine *h, int32_t n, const uint32_t *ids, const uint8_t *role, const double *kv_usage,
                      const int32_t *waiting, const int32_t *running, const double *ext);
 
+/* LoRA adapter residency for EPP_SCORER_LORA_AFFINITY (fwkdl.Metrics.ActiveModels / WaitingModels / MaxActiveModels,
+ * scorer/loraaffinity/lora_affinity.go:76-100).  n entries by slot id: MaxActiveModels and len(ActiveModels) +
+ * len(WaitingModels); n_members triples (endpoint slot, model id from epp_model_register, state 1 = active /
+ * 2 = waiting) list where each adapter is resident.  Replaces the previous LoRA state and re-derives the scorer terms;
+ * call it after epp_pool_set of the same scrape (slots absent here have capacity 0 and nothing resident). */
+EPP_API int32_t epp_pool_set_lora(epp_engine *h, int32_t n, const uint32_t *ids, const int32_t *max_active_models,
+                          const int32_t *n_models_loaded, int64_t n_members, const uint32_t *member_ep,
+                          const uint32_t *member_model, const uint8_t *member_state);
+
 /* ---- prefix index write side (approximateprefix/indexer.go:52-83, 105-115, 167-182; plugin.go:164-211) --
  * The LRU bookkeeping lives in HBM (index_store.cu): epp_index_add calls are queued and applied as ONE device batch,
  * in call order, by the next commit / lookup / remove; epp_index_add_picked never leaves the device.  The read table
@@ -253,9 +264,10 @@ EPP_API int32_t epp_prefix_match(epp_engine *h, const epp_batch *batch, int32_t 
  * match: [R][max_endpoints], total: [R] (as produced by epp_prefix_match or injected by a test).
  * profile: 0 = primary, 1 = prefill.  scorer_index >= 0: raw column of that scorer (what Scorer.Score
  * returns, 0 for non-candidates); -1: weighted, clamped, ordered sum (-1.0 for filtered-out endpoints).
- * out_scores: [R][max_endpoints].  flags: EPP_BATCH_DEVICE_PTRS. */
+ * out_scores: [R][max_endpoints].  flags: EPP_BATCH_DEVICE_PTRS.
+ * model_ids: [R] model (= LoRA adapter) of each request, NULL = model 0 (only lora-affinity reads it). */
 EPP_API int32_t epp_score(epp_engine *h, int64_t n_requests, const int32_t *match, const int32_t *total,
-                  int32_t profile, int32_t scorer_index, double *out_scores, uint32_t flags);
+                  const uint32_t *model_ids, int32_t profile, int32_t scorer_index, double *out_scores, uint32_t flags);
 
 /* ---- a1-a14 fused: Scheduler.Schedule for a batch (scheduling/scheduler.go:54-102) ---------------
  * out: [R]; detail: [R] or NULL; keep_hashes != 0 keeps the batch's prefix hashes resident on the device
@@ -265,9 +277,10 @@ EPP_API int32_t epp_schedule(epp_engine *h, const epp_batch *batch, epp_decision
 
 /* Same decision logic with PrefixCacheMatchInfo injected by the caller (how the reference's own scheduler
  * tests drive it: disagg/scheduler_test.go:264-268): match [R][max_endpoints], total [R],
- * input_len_bytes [R] (prompt length for the P/D decider), block_size_tokens override (0 = config). */
+ * model_ids [R] or NULL, input_len_bytes [R] (prompt length for the P/D decider), block_size_tokens override
+ * (0 = config). */
 EPP_API int32_t epp_schedule_with_match(epp_engine *h, int64_t n_requests, const int32_t *match, const int32_t *total,
-                                const int64_t *input_len_bytes, int32_t block_size_tokens, epp_decision *out,
+                                const uint32_t *model_ids, const int64_t *input_len_bytes, int32_t block_size_tokens, epp_decision *out,
                                 epp_decision_detail *detail, uint32_t flags);
 
 /* PreRequest (approximateprefix/plugin.go:164-200): index the hashes of the LAST epp_schedule batch

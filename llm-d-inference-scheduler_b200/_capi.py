@@ -17,7 +17,7 @@ EPP_BATCH_ASYNC = 2
 EPP_OK, EPP_ERR_INVALID, EPP_ERR_CUDA, EPP_ERR_NO_DEVICE, EPP_ERR_CAPACITY, EPP_ERR_STATE, EPP_ERR_NCCL = \
     0, -1, -2, -3, -4, -5, -6
 (SCORER_PREFIX, SCORER_KV_UTIL, SCORER_QUEUE, SCORER_LOAD_AWARE, SCORER_EXTERNAL, SCORER_RUNNING, SCORER_TOKEN_LOAD,
- SCORER_ACTIVE_REQUEST) = range(8)
+ SCORER_ACTIVE_REQUEST, SCORER_LORA_AFFINITY) = range(9)
 (ROLE_NONE, ROLE_DECODE, ROLE_PREFILL, ROLE_PREFILL_DECODE, ROLE_BOTH, ROLE_ENCODE, ROLE_ENCODE_PREFILL,
  ROLE_ENCODE_PREFILL_DECODE, ROLE_OTHER) = range(9)
 FILTER_NONE, FILTER_DECODE, FILTER_PREFILL, FILTER_ENCODE = range(4)
@@ -95,10 +95,12 @@ SIGNATURES = {
     "epp_index_get": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "epp_hash_prompts": (C.c_int32, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p]),
     "epp_prefix_match": (C.c_int32, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p]),
-    "epp_score": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+    "epp_pool_set_lora": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "epp_score": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                               C.c_uint32]),
     "epp_schedule": (C.c_int32, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_int32]),
-    "epp_schedule_with_match": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+    "epp_schedule_with_match": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                             C.c_void_p, C.c_void_p, C.c_uint32]),
     "epp_index_add_picked": (C.c_int32, [C.c_void_p]),
     "epp_get_stats": (C.c_int32, [C.c_void_p, C.POINTER(Stats)]),

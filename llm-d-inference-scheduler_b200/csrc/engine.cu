@@ -91,6 +91,9 @@ struct epp_engine {
     // pool state
     bool pool_ready = false;
     DevBuf role, kv, waiting, running, ext;
+    DevBuf lora_max, lora_cnt, lora_ptr, lora_ep, lora_state, score_models;   // LoRA residency (epp_pool_set_lora)
+    bool lora_set = false, lora_enabled = false;
+    int32_t lora_models = 0;
     ProfileState prof[kMaxProfiles];
 
     // index
@@ -178,7 +181,7 @@ static int32_t validate_profile(const epp_profile_cfg &p, int n_ext, const char 
     if (p.n_scorers < 0 || p.n_scorers > EPP_MAX_SCORERS) return fail(EPP_ERR_INVALID, "%s: n_scorers %d out of range", name, p.n_scorers);
     for (int s = 0; s < p.n_scorers; s++) {
         const epp_scorer_cfg &sc = p.scorers[s];
-        if (sc.kind < EPP_SCORER_PREFIX || sc.kind > EPP_SCORER_ACTIVE_REQUEST) return fail(EPP_ERR_INVALID, "%s: scorer %d has unknown kind %d", name, s, sc.kind);
+        if (sc.kind < EPP_SCORER_PREFIX || sc.kind > EPP_SCORER_LORA_AFFINITY) return fail(EPP_ERR_INVALID, "%s: scorer %d has unknown kind %d", name, s, sc.kind);
         if (!std::isfinite(sc.weight)) return fail(EPP_ERR_INVALID, "%s: scorer %d weight is not finite", name, s);
         if ((sc.kind == EPP_SCORER_TOKEN_LOAD || sc.kind == EPP_SCORER_ACTIVE_REQUEST) && (sc.column < 0 || sc.column >= n_ext))
             return fail(EPP_ERR_INVALID, "%s: scorer %d reads ext column %d, out of range [0,%d)", name, s, sc.column, n_ext);
@@ -254,6 +257,10 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
     CUDA_TRY(e->work_counters.reserve(sizeof(unsigned long long) * 2, &e->dev_bytes));
     memset(&e->idx_special_host, 0, sizeof(IndexSlot));
     e->idx_special_host.key = kEmptyKey;
+    for (int pi = 0; pi < (cfg->handler == EPP_HANDLER_DISAGG ? 2 : 1); pi++) {
+        const epp_profile_cfg &pc = pi == 0 ? cfg->primary : cfg->prefill;
+        for (int si = 0; si < pc.n_scorers; si++) if (pc.scorers[si].kind == EPP_SCORER_LORA_AFFINITY) e->lora_enabled = true;
+    }
     e->store.reset(new IndexStore((uint32_t)cfg->max_endpoints, cfg->lru_capacity_per_server));
     { const char *v1 = getenv("EPP_HASH_V1"); e->force_v1 = (v1 && v1[0] == '1') ? 1 : 0; }
     { const char *v1 = getenv("EPP_MATCH_V1"); e->force_match_v1 = (v1 && v1[0] == '1') ? 1 : 0; }
@@ -351,6 +358,20 @@ extern "C" int32_t epp_model_seed(epp_engine *h, uint32_t model_id, uint64_t *ou
 // ------------------------------------------------------------------------------------------------
 // pool state
 // ------------------------------------------------------------------------------------------------
+static LoraDev lora_dev(epp_engine *h) {
+    LoraDev L{};
+    L.enabled = h->lora_enabled ? 1 : 0;
+    if (h->lora_set) {
+        L.max_active = h->lora_max.as<int32_t>();
+        L.n_loaded = h->lora_cnt.as<int32_t>();
+        L.ptr = h->lora_ptr.as<uint32_t>();
+        L.ep = h->lora_ep.as<uint32_t>();
+        L.state = h->lora_state.as<uint8_t>();
+        L.n_models = h->lora_models;
+    }
+    return L;
+}
+
 static PoolArrays pool_arrays(epp_engine *h) {
     PoolArrays pa;
     pa.E = h->cfg.max_endpoints;
@@ -360,6 +381,7 @@ static PoolArrays pool_arrays(epp_engine *h) {
     pa.waiting = h->waiting.as<int32_t>();
     pa.running = h->running.as<int32_t>();
     pa.ext = h->ext.as<double>();
+    pa.lora = lora_dev(h);
     return pa;
 }
 
@@ -373,6 +395,26 @@ static ProfileDev profile_dev(epp_engine *h, int p) {
     pd.grp_size = h->prof[p].grp_size.as<uint32_t>();
     pd.n_cand = h->prof[p].n_cand.as<int32_t>();
     return pd;
+}
+
+// Request-independent scorer terms of every profile from the current pool (+ LoRA) snapshot, on the device.
+static int32_t derive_pool(epp_engine *h) {
+    cudaStream_t s = h->slot[0].stream;
+    PoolArrays pa = pool_arrays(h);
+    int launches = 0;
+    for (int p = 0; p < h->n_profiles; p++) {
+        ProfileDerived d;
+        d.cand = h->prof[p].cand.as<uint8_t>();
+        d.contrib = h->prof[p].contrib.as<double>();
+        d.base = h->prof[p].base.as<double>();
+        d.order = h->prof[p].order.as<uint32_t>();
+        d.grp_size = h->prof[p].grp_size.as<uint32_t>();
+        d.sort_key = h->prof[p].sort_key.as<uint64_t>();
+        d.n_cand = h->prof[p].n_cand.as<int32_t>();
+        d.qminmax = h->prof[p].qminmax.as<int64_t>();
+        CUDA_TRY(launch_pool_prepare(pa, p == 0 ? h->cfg.primary : h->cfg.prefill, d, h->Epad, h->shard_begin, h->shard_end, s, &launches));
+    }
+    return EPP_OK;
 }
 
 extern "C" int32_t epp_pool_set(epp_engine *h, int32_t n, const uint32_t *ids, const uint8_t *role,
@@ -412,22 +454,69 @@ extern "C" int32_t epp_pool_set(epp_engine *h, int32_t n, const uint32_t *ids, c
     CUDA_TRY(cudaMemcpyAsync(h->running.p, run.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
     if (h->cfg.n_ext_cols)
         CUDA_TRY(cudaMemcpyAsync(h->ext.p, ex.data(), sizeof(double) * E * (size_t)h->cfg.n_ext_cols, cudaMemcpyHostToDevice, s));
-    PoolArrays pa = pool_arrays(h);
-    int launches = 0;
-    for (int p = 0; p < h->n_profiles; p++) {
-        ProfileDerived d;
-        d.cand = h->prof[p].cand.as<uint8_t>();
-        d.contrib = h->prof[p].contrib.as<double>();
-        d.base = h->prof[p].base.as<double>();
-        d.order = h->prof[p].order.as<uint32_t>();
-        d.grp_size = h->prof[p].grp_size.as<uint32_t>();
-        d.sort_key = h->prof[p].sort_key.as<uint64_t>();
-        d.n_cand = h->prof[p].n_cand.as<int32_t>();
-        d.qminmax = h->prof[p].qminmax.as<int64_t>();
-        CUDA_TRY(launch_pool_prepare(pa, p == 0 ? h->cfg.primary : h->cfg.prefill, d, h->Epad, h->shard_begin, h->shard_end, s, &launches));
-    }
+    EPP_TRY(derive_pool(h));
     CUDA_TRY(cudaStreamSynchronize(s));
     h->pool_ready = true;
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_pool_set_lora(epp_engine *h, int32_t n, const uint32_t *ids, const int32_t *max_active_models,
+                                     const int32_t *n_models_loaded, int64_t n_members, const uint32_t *member_ep,
+                                     const uint32_t *member_model, const uint8_t *member_state) {
+    if (!h || n < 0 || n_members < 0) return fail(EPP_ERR_INVALID, "bad arguments");
+    if (n > 0 && (!ids || !max_active_models || !n_models_loaded)) return fail(EPP_ERR_INVALID, "NULL LoRA arrays");
+    if (n_members > 0 && (!member_ep || !member_model || !member_state)) return fail(EPP_ERR_INVALID, "NULL LoRA member arrays");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
+    const uint32_t E = (uint32_t)h->cfg.max_endpoints;
+    std::vector<int32_t> mx(E, 0), cnt(E, 0);
+    for (int32_t i = 0; i < n; i++) {
+        if (ids[i] >= E) return fail(EPP_ERR_INVALID, "LoRA entry %d: slot id %u >= max_endpoints %u", i, ids[i], E);
+        mx[ids[i]] = max_active_models[i];
+        cnt[ids[i]] = n_models_loaded[i];
+    }
+    const int32_t n_models = std::max(1, h->n_models);
+    struct Mem { uint32_t model, ep; uint8_t st; };
+    std::vector<Mem> mem;
+    mem.reserve((size_t)n_members);
+    for (int64_t i = 0; i < n_members; i++) {
+        if (member_ep[i] >= E) return fail(EPP_ERR_INVALID, "LoRA member %lld: slot id %u >= max_endpoints %u", (long long)i, member_ep[i], E);
+        if (member_model[i] >= (uint32_t)n_models) return fail(EPP_ERR_INVALID, "LoRA member %lld: model id %u is not registered", (long long)i, member_model[i]);
+        if (member_state[i] != 1 && member_state[i] != 2) return fail(EPP_ERR_INVALID, "LoRA member %lld: state %u (1 = active, 2 = waiting)", (long long)i, member_state[i]);
+        mem.push_back({member_model[i], member_ep[i], member_state[i]});
+    }
+    // CSR by adapter, endpoints ascending; an adapter both active and waiting on an endpoint counts as active
+    // (the `case active` branch comes first, lora_affinity.go:85-87)
+    std::sort(mem.begin(), mem.end(), [](const Mem &a, const Mem &b) {
+        return a.model != b.model ? a.model < b.model : (a.ep != b.ep ? a.ep < b.ep : a.st < b.st);
+    });
+    std::vector<uint32_t> ptr((size_t)n_models + 1, 0), eps;
+    std::vector<uint8_t> sts;
+    for (size_t i = 0; i < mem.size(); i++) {
+        if (i && mem[i].model == mem[i - 1].model && mem[i].ep == mem[i - 1].ep) continue;
+        eps.push_back(mem[i].ep);
+        sts.push_back(mem[i].st);
+        ptr[mem[i].model + 1]++;
+    }
+    for (int32_t a = 0; a < n_models; a++) ptr[a + 1] += ptr[a];
+    cudaStream_t s = h->slot[0].stream;
+    CUDA_TRY(h->lora_max.reserve(sizeof(int32_t) * E, &h->dev_bytes));
+    CUDA_TRY(h->lora_cnt.reserve(sizeof(int32_t) * E, &h->dev_bytes));
+    CUDA_TRY(h->lora_ptr.reserve(sizeof(uint32_t) * ptr.size(), &h->dev_bytes));
+    CUDA_TRY(h->lora_ep.reserve(sizeof(uint32_t) * std::max<size_t>(1, eps.size()), &h->dev_bytes));
+    CUDA_TRY(h->lora_state.reserve(std::max<size_t>(1, sts.size()), &h->dev_bytes));
+    CUDA_TRY(cudaMemcpyAsync(h->lora_max.p, mx.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->lora_cnt.p, cnt.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->lora_ptr.p, ptr.data(), sizeof(uint32_t) * ptr.size(), cudaMemcpyHostToDevice, s));
+    if (!eps.empty()) {
+        CUDA_TRY(cudaMemcpyAsync(h->lora_ep.p, eps.data(), sizeof(uint32_t) * eps.size(), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(h->lora_state.p, sts.data(), sts.size(), cudaMemcpyHostToDevice, s));
+    }
+    h->lora_models = n_models;
+    h->lora_set = true;
+    if (h->pool_ready) EPP_TRY(derive_pool(h));
+    CUDA_TRY(cudaStreamSynchronize(s));
     return EPP_OK;
 }
 
@@ -764,6 +853,8 @@ static PickParams pick_params(epp_engine *h, const Work &w, epp_decision *out, e
     p.hashes = w.hashes_out;
     p.nblocks = w.nblocks_out;
     p.in_len = h->in_len.as<int64_t>() + w.r0;
+    p.model_ids = w.model_ids_dev ? w.model_ids_dev + w.r0 : nullptr;
+    p.lora = lora_dev(h);
     p.index = index_view(h);
     p.out = out;
     p.detail = detail;
@@ -827,7 +918,7 @@ static int32_t launch_cycle(epp_engine *h, Slot &sl, const HashParams &hp_in, Pi
                             cudaEvent_t *ev) {
     cudaStream_t s = sl.stream;
     HashParams hp = hp_in;
-    const bool fuse = !pp.out_match && !h->force_match_v1 && !h->force_v1 && !h->no_fuse && hash_batch_alignment(hp) >= 16;
+    const bool fuse = !pp.out_match && !h->force_match_v1 && !h->force_v1 && !h->no_fuse && !h->lora_enabled && hash_batch_alignment(hp) >= 16;
     if (fuse) {
         CUDA_TRY(cudaMemsetAsync(sl.overflow_n.p, 0, sizeof(int32_t), s));
         pp.overflow_list = sl.overflow_list.as<int32_t>();
@@ -1097,7 +1188,8 @@ extern "C" int32_t epp_index_add_picked(epp_engine *h) {
 // plugin-parity entry points on injected match info
 // ------------------------------------------------------------------------------------------------
 extern "C" int32_t epp_score(epp_engine *h, int64_t n_requests, const int32_t *match, const int32_t *total,
-                             int32_t profile, int32_t scorer_index, double *out_scores, uint32_t flags) {
+                             const uint32_t *model_ids, int32_t profile, int32_t scorer_index, double *out_scores,
+                             uint32_t flags) {
     if (!h || n_requests < 0 || (n_requests && (!match || !total || !out_scores))) return fail(EPP_ERR_INVALID, "bad arguments");
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
@@ -1122,16 +1214,22 @@ extern "C" int32_t epp_score(epp_engine *h, int64_t n_requests, const int32_t *m
         d_total = h->dense_total.as<int32_t>();
         d_out = h->dense_scores.as<double>();
     }
+    const uint32_t *d_models = model_ids;
+    if (!dev && model_ids) {
+        CUDA_TRY(h->score_models.reserve(sizeof(uint32_t) * (size_t)n_requests, &h->dev_bytes));
+        CUDA_TRY(cudaMemcpyAsync(h->score_models.p, model_ids, sizeof(uint32_t) * (size_t)n_requests, cudaMemcpyHostToDevice, s));
+        d_models = h->score_models.as<uint32_t>();
+    }
     int launches = 0;
     CUDA_TRY(launch_score_dense(n_requests, h->cfg.max_endpoints, profile_dev(h, profile), pool_arrays(h),
-                                h->prof[profile].qminmax.as<int64_t>(), d_match, d_total, scorer_index, d_out, s, &launches));
+                                h->prof[profile].qminmax.as<int64_t>(), d_match, d_total, d_models, scorer_index, d_out, s, &launches));
     if (!dev) CUDA_TRY(cudaMemcpyAsync(out_scores, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return EPP_OK;
 }
 
 extern "C" int32_t epp_schedule_with_match(epp_engine *h, int64_t n_requests, const int32_t *match, const int32_t *total,
-                                           const int64_t *input_len_bytes, int32_t block_size_tokens, epp_decision *out,
+                                           const uint32_t *model_ids, const int64_t *input_len_bytes, int32_t block_size_tokens, epp_decision *out,
                                            epp_decision_detail *detail, uint32_t flags) {
     if (!h || n_requests < 0 || (n_requests && (!match || !total || !out))) return fail(EPP_ERR_INVALID, "bad arguments");
     std::lock_guard<std::mutex> lk(h->mu);
@@ -1150,9 +1248,16 @@ extern "C" int32_t epp_schedule_with_match(epp_engine *h, int64_t n_requests, co
     p.always_disagg = h->cfg.always_disagg;
     p.non_cached_tokens = h->cfg.non_cached_tokens;
     for (int i = 0; i < h->n_profiles; i++) p.prof[i] = profile_dev(h, i);
+    p.lora = lora_dev(h);
+    p.model_ids = model_ids;
     if (dev) {
         p.match = match; p.total = total; p.in_len = input_len_bytes; p.out = out; p.detail = detail;
     } else {
+        if (model_ids) {
+            CUDA_TRY(h->score_models.reserve(sizeof(uint32_t) * R, &h->dev_bytes));
+            CUDA_TRY(cudaMemcpyAsync(h->score_models.p, model_ids, sizeof(uint32_t) * R, cudaMemcpyHostToDevice, s));
+            p.model_ids = h->score_models.as<uint32_t>();
+        }
         EPP_TRY(reserve_batch(h, n_requests));
         CUDA_TRY(h->dense_match.reserve(sizeof(int32_t) * n, &h->dev_bytes));
         CUDA_TRY(h->dense_total.reserve(sizeof(int32_t) * R, &h->dev_bytes));

@@ -84,6 +84,18 @@ cudaError_t launch_index_get(const IndexView &ix, uint64_t hash, uint32_t *out_e
 // pool state -> request-independent scorer terms (a5-a9 precompute)
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxProfiles = 2;
+// LoRA adapter residency (fwkdl.Metrics.ActiveModels / WaitingModels / MaxActiveModels) for lora-affinity-scorer:
+// per endpoint the adapter capacity, per adapter (= registered model id) the endpoints where it is active (1) or
+// waiting (2), sorted by endpoint.  ptr == nullptr: no LoRA state (every endpoint scores 0.0 / its capacity tier).
+struct LoraDev {
+    const int32_t *max_active;   // [E] MaxActiveModels
+    const int32_t *n_loaded;     // [E] len(ActiveModels) + len(WaitingModels)
+    const uint32_t *ptr;         // [n_models + 1]
+    const uint32_t *ep;          // [ptr[n_models]] endpoint slot ids, ascending within an adapter
+    const uint8_t *state;        // 1 = active, 2 = waiting
+    int32_t n_models;
+    int32_t enabled;             // some profile has a lora-affinity scorer
+};
 struct PoolArrays {
     int32_t E;                 // slot capacity (max_endpoints)
     int32_t n_ext_cols;
@@ -92,6 +104,7 @@ struct PoolArrays {
     const int32_t *waiting;    // [E]
     const int32_t *running;    // [E]
     const double *ext;         // [n_ext_cols][E]
+    LoraDev lora;
 };
 struct ProfileDerived {
     // per profile, device arrays
@@ -132,6 +145,8 @@ struct PickParams {
     const uint64_t *hashes;    // [R][max_blocks]
     const int32_t *nblocks;    // [R]
     const int64_t *in_len;     // [R] prompt bytes (decider)
+    const uint32_t *model_ids; // [R] registered model (= LoRA adapter) of each request, or nullptr => model 0
+    LoraDev lora;
     IndexView index;
     epp_decision *out;         // [R]
     epp_decision_detail *detail;  // [R] or nullptr
@@ -170,6 +185,8 @@ struct DensePickParams {
     const int32_t *match;      // [R][E]
     const int32_t *total;      // [R]
     const int64_t *in_len;     // [R]
+    const uint32_t *model_ids; // [R] or nullptr
+    LoraDev lora;
     epp_decision *out;
     epp_decision_detail *detail;
 };
@@ -177,7 +194,8 @@ cudaError_t launch_dense_pick(const DensePickParams &p, cudaStream_t s, int *lau
 // Scorer.Score parity: out[R][E].  scorer_index -1 => weighted ordered sum (-1.0 for non-candidates).
 cudaError_t launch_score_dense(int64_t R, int32_t E, const ProfileDev &prof, const PoolArrays &pool,
                                const int64_t *qminmax, const int32_t *match, const int32_t *total,
-                               int32_t scorer_index, double *out, cudaStream_t s, int *launches);
+                               const uint32_t *model_ids, int32_t scorer_index, double *out, cudaStream_t s,
+                               int *launches);
 
 // endpoint-sharded mode: per-request block-presence masks of the LOCAL table (bit i of word i/32 = block i held
 // by some endpoint of this shard), and the cross-rank reduction of the per-shard best records.

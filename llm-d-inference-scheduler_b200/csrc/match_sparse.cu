@@ -64,13 +64,14 @@ __device__ __forceinline__ bool map_contains_any(const LaneMap &m, uint32_t e) {
 
 // One profile for the current request (SchedulerProfile.Run): matched candidates from the lane map, everyone else
 // from the (base desc, slot asc) order.
-__device__ inline Best eval_profile_lanes(const ProfileDev &pf, int32_t E, const LaneMap &m, int32_t total, int lane) {
+__device__ inline Best eval_profile_lanes(const ProfileDev &pf, int32_t E, const LaneMap &m, int32_t total, int lane,
+                                         const LoraDev &lora, int lora_st) {
     Best b;
     best_init(b);
     const int32_t ncand = *pf.n_cand;
     if (ncand == 0) return b;
     const bool mine = (uint32_t)lane < m.n && pf.cand[m.e];
-    if (mine) best_add(b, weighted_sum(pf, E, m.e, (int32_t)m.c, total), m.e);
+    if (mine) best_add(b, weighted_sum(pf, E, m.e, (int32_t)m.c, total, lora, lora_st), m.e);
     if (m.n) b = best_warp_reduce(b);
     for (int32_t k0 = 0; k0 < ncand; k0 += 32) {
         int32_t k = k0 + lane;
@@ -178,13 +179,31 @@ __global__ void __launch_bounds__(kWarps * 32, kMinCtas) k_match_pick_sparse(Pic
             if (limit > cq) count_chunk(m, p.index, hit, cnt, shard_lo, shard_hi, lane);
             if (miss) stopped = true;
         }
+        // ---- lora-affinity: the endpoints where the request's adapter is active or waiting get a request-dependent
+        //      score, so they join the map (count 0) and are evaluated one by one like the prefix holders
+        int lora_st = 0;
+        if (p.lora.enabled && p.lora.ptr && !m.overflow) {
+            const uint32_t a = p.model_ids ? p.model_ids[r] : 0u;
+            if (a < (uint32_t)p.lora.n_models) {
+                const uint32_t lo = p.lora.ptr[a], hi = p.lora.ptr[a + 1];
+                for (uint32_t k0 = lo; k0 < hi && !m.overflow; k0 += 32) {
+                    const uint32_t mine_e = (k0 + lane < hi) ? p.lora.ep[k0 + lane] : kNoKey;
+                    const uint32_t nk = min(32u, hi - k0);
+                    for (uint32_t k = 0; k < nk && !m.overflow; k++) {
+                        const uint32_t e = __shfl_sync(kFull, mine_e, (int)k);
+                        if (e >= shard_lo && e < shard_hi) map_add(m, e, 0, lane);
+                    }
+                }
+                if ((uint32_t)lane < m.n) lora_st = lora_lookup(p.lora, a, m.e);
+            }
+        }
         if (m.overflow) {
             // hand the request to the dense-counter kernel
             if (lane == 0 && p.overflow_list) p.overflow_list[atomicAdd(p.overflow_n, 1)] = (int32_t)r;
             continue;
         }
         // ---- a5-a10: primary profile
-        Best b0 = eval_profile_lanes(p.prof[0], p.E, m, total, lane);
+        Best b0 = eval_profile_lanes(p.prof[0], p.E, m, total, lane, p.lora, lora_st);
         epp_decision d;
         d.status = b0.ties ? 0 : -1;
         d.pick = b0.ties ? b0.pick : EPP_NO_ENDPOINT;
@@ -200,7 +219,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinCtas) k_match_pick_sparse(Pic
             bool go = p.always_disagg || pd_decide(p.non_cached_tokens, p.in_len[r], d.match_blocks, p.block_size_tokens);
             if (go) {
                 dd.prefill_ran = 1;
-                Best b1 = eval_profile_lanes(p.prof[1], p.E, m, total, lane);
+                Best b1 = eval_profile_lanes(p.prof[1], p.E, m, total, lane, p.lora, lora_st);
                 if (b1.ties) { d.prefill_pick = b1.pick; dd.prefill_score = b1.val; dd.prefill_tie_count = b1.ties; }
             }
         }

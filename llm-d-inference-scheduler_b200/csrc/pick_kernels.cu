@@ -182,11 +182,19 @@ __device__ __forceinline__ uint32_t cnt_get(const uint32_t *cnt32, uint32_t e) {
 // Evaluate one profile for the current request.  cnt32 holds the per-endpoint match counts; list/nl the
 // distinct matched endpoints (nl > kListCap => overflow => dense scan).
 __device__ inline Best eval_profile(const ProfileDev &pf, int32_t E, const uint32_t *cnt32, const uint32_t *list,
-                                    uint32_t nl, int32_t total, int lane) {
+                                    uint32_t nl, int32_t total, int lane, const LoraDev &lora, uint32_t adapter) {
     Best b;
     best_init(b);
     int32_t ncand = *pf.n_cand;
     if (ncand == 0) return b;
+    if (lora.enabled && lora.ptr) {
+        // lora-affinity makes the score of some unmatched endpoints request-dependent: plain scan of every candidate
+        for (uint32_t e = lane; e < (uint32_t)E; e += 32) {
+            if (!pf.cand[e]) continue;
+            best_add(b, weighted_sum(pf, E, e, (int32_t)cnt_get(cnt32, e), total, lora, lora_lookup(lora, adapter, e)), e);
+        }
+        return best_warp_reduce(b);
+    }
     if (nl <= (uint32_t)kListCap) {
         for (uint32_t j = lane; j < nl; j += 32) {       // endpoints holding part of the prefix
             uint32_t e = list[j];
@@ -294,7 +302,8 @@ __global__ void __launch_bounds__(kPickWarps * 32) k_match_pick(PickParams p, in
         const uint32_t nl = *list_n;
 
         // ---- a5-a10: primary profile
-        Best b0 = eval_profile(p.prof[0], p.E, cnt32, list, nl, total, lane);
+        const uint32_t adapter = p.model_ids ? p.model_ids[r] : 0u;
+        Best b0 = eval_profile(p.prof[0], p.E, cnt32, list, nl, total, lane, p.lora, adapter);
         epp_decision d;
         d.status = b0.ties ? 0 : -1;
         d.pick = b0.ties ? b0.pick : EPP_NO_ENDPOINT;
@@ -310,7 +319,7 @@ __global__ void __launch_bounds__(kPickWarps * 32) k_match_pick(PickParams p, in
             bool go = p.always_disagg || pd_decide(p.non_cached_tokens, p.in_len[r], d.match_blocks, p.block_size_tokens);
             if (go) {
                 dd.prefill_ran = 1;
-                Best b1 = eval_profile(p.prof[1], p.E, cnt32, list, nl, total, lane);
+                Best b1 = eval_profile(p.prof[1], p.E, cnt32, list, nl, total, lane, p.lora, adapter);
                 if (b1.ties) { d.prefill_pick = b1.pick; dd.prefill_score = b1.val; dd.prefill_tie_count = b1.ties; }
             }
         }
@@ -380,12 +389,13 @@ cudaError_t launch_match_pick(const PickParams &p, uint32_t *gscratch, int grid,
 // decision logic on injected dense match info (KAT / plugin-parity mode)
 // ------------------------------------------------------------------------------------------------
 __device__ inline Best eval_profile_dense(const ProfileDev &pf, int32_t E, const int32_t *mrow, int32_t total,
-                                          int lane) {
+                                          int lane, const LoraDev &lora, uint32_t adapter) {
     Best b;
     best_init(b);
+    const bool use_lora = lora.enabled && lora.ptr;
     for (uint32_t e = lane; e < (uint32_t)E; e += 32) {
         if (!pf.cand[e]) continue;
-        best_add(b, weighted_sum(pf, E, e, mrow[e], total), e);
+        best_add(b, weighted_sum(pf, E, e, mrow[e], total, lora, use_lora ? lora_lookup(lora, adapter, e) : 0), e);
     }
     return best_warp_reduce(b);
 }
@@ -396,7 +406,8 @@ __global__ void __launch_bounds__(256) k_dense_pick(DensePickParams p) {
     if (r >= p.R) return;
     const int32_t *mrow = p.match + r * (int64_t)p.E;
     int32_t total = p.total[r];
-    Best b0 = eval_profile_dense(p.prof[0], p.E, mrow, total, lane);
+    const uint32_t adapter = p.model_ids ? p.model_ids[r] : 0u;
+    Best b0 = eval_profile_dense(p.prof[0], p.E, mrow, total, lane, p.lora, adapter);
     epp_decision d;
     d.status = b0.ties ? 0 : -1;
     d.pick = b0.ties ? b0.pick : EPP_NO_ENDPOINT;
@@ -412,7 +423,7 @@ __global__ void __launch_bounds__(256) k_dense_pick(DensePickParams p) {
                                                 p.block_size_tokens);
         if (go) {
             dd.prefill_ran = 1;
-            Best b1 = eval_profile_dense(p.prof[1], p.E, mrow, total, lane);
+            Best b1 = eval_profile_dense(p.prof[1], p.E, mrow, total, lane, p.lora, adapter);
             if (b1.ties) { d.prefill_pick = b1.pick; dd.prefill_score = b1.val; dd.prefill_tie_count = b1.ties; }
         }
     }
@@ -432,31 +443,36 @@ cudaError_t launch_dense_pick(const DensePickParams &p, cudaStream_t s, int *lau
 
 // Scorer.Score parity (dense [R][E] output).
 __global__ void k_score_dense(int64_t R, int32_t E, ProfileDev pf, PoolArrays pool, const int64_t *qminmax,
-                              const int32_t *match, const int32_t *total, int32_t scorer_index, double *out) {
+                              const int32_t *match, const int32_t *total, const uint32_t *model_ids,
+                              int32_t scorer_index, double *out) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= R * (int64_t)E) return;
     int64_t r = idx / E;
     int32_t e = (int32_t)(idx % E);
     bool c = pf.cand[e] != 0;
+    const int lora_st = (pool.lora.enabled && pool.lora.ptr) ? lora_lookup(pool.lora, model_ids ? model_ids[r] : 0u, (uint32_t)e) : 0;
     double v;
     if (scorer_index < 0) {
-        v = c ? weighted_sum(pf, E, (uint32_t)e, match[idx], total[r]) : -1.0;
+        v = c ? weighted_sum(pf, E, (uint32_t)e, match[idx], total[r], pool.lora, lora_st) : -1.0;
     } else if (!c) {
         v = 0.0;
     } else {
         const epp_scorer_cfg &sc = pf.cfg.scorers[scorer_index];
-        v = sc.kind == EPP_SCORER_PREFIX ? prefix_score(match[idx], total[r]) : pool_score(sc, scorer_index, pool, qminmax, e);
+        v = sc.kind == EPP_SCORER_PREFIX ? prefix_score(match[idx], total[r])
+            : (sc.kind == EPP_SCORER_LORA_AFFINITY ? lora_score(pool.lora, (uint32_t)e, lora_st)
+                                                   : pool_score(sc, scorer_index, pool, qminmax, e));
     }
     out[idx] = v;
 }
 
 cudaError_t launch_score_dense(int64_t R, int32_t E, const ProfileDev &prof, const PoolArrays &pool,
                                const int64_t *qminmax, const int32_t *match, const int32_t *total,
-                               int32_t scorer_index, double *out, cudaStream_t s, int *launches) {
+                               const uint32_t *model_ids, int32_t scorer_index, double *out, cudaStream_t s,
+                               int *launches) {
     int64_t n = R * (int64_t)E;
     if (n <= 0) return cudaSuccess;
-    k_score_dense<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(R, E, prof, pool, qminmax, match, total, scorer_index,
-                                                             out);
+    k_score_dense<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(R, E, prof, pool, qminmax, match, total, model_ids,
+                                                             scorer_index, out);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -43,6 +43,28 @@ __device__ __forceinline__ double prefix_score(int32_t match, int32_t total) {
     return __ddiv_rn((double)match, (double)total);
 }
 
+// lora-affinity-scorer (scorer/loraaffinity/lora_affinity.go:76-100).  st: 0 = the request's adapter is neither active
+// nor waiting on the endpoint, 1 = active, 2 = waiting.
+__device__ __forceinline__ double lora_score(const LoraDev &L, uint32_t e, int st) {
+    if (st == 1) return 1.0;
+    const bool room = L.max_active && L.n_loaded[e] < L.max_active[e];
+    if (room) return 0.8;
+    return st == 2 ? 0.6 : 0.0;
+}
+
+// Residency state of adapter a on endpoint e (binary search in the adapter's endpoint list).
+__device__ __forceinline__ int lora_lookup(const LoraDev &L, uint32_t a, uint32_t e) {
+    if (!L.ptr || a >= (uint32_t)L.n_models) return 0;
+    uint32_t lo = L.ptr[a];
+    const uint32_t end = L.ptr[a + 1];
+    uint32_t hi = end;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (L.ep[mid] < e) lo = mid + 1; else hi = mid;
+    }
+    return (lo < end && L.ep[lo] == e) ? (int)L.state[lo] : 0;
+}
+
 // Raw Scorer.Score value of one endpoint for the request-independent scorers.
 // qminmax: [0..3] waiting / running min,max over the profile's candidates, [4 + s] max in-flight request count of
 // active-request scorer s.
@@ -90,19 +112,24 @@ __device__ __forceinline__ double pool_score(const epp_scorer_cfg &sc, int s_ind
             const int64_t mx = qminmax[4 + s_index];
             return __dmul_rn(__ddiv_rn((double)(mx - c), (double)mx), max_busy);
         }
+        case EPP_SCORER_LORA_AFFINITY:      // request-independent part: the adapter is not resident on the endpoint
+            return lora_score(pool.lora, (uint32_t)e, 0);
         default: return 0.0;
     }
 }
 
 // Ordered weighted sum of one endpoint (runScorerPlugins, scheduler_profile.go:151-174).
+// lora_st: residency of the request's adapter on e (0 => the precomputed contribution already holds).
 __device__ __forceinline__ double weighted_sum(const ProfileDev &pf, int32_t E, uint32_t e, int32_t match,
-                                               int32_t total) {
+                                               int32_t total, const LoraDev &L = LoraDev{}, int lora_st = 0) {
     double acc = 0.0;
 #pragma unroll 1
     for (int s = 0; s < pf.cfg.n_scorers; s++) {
         double term;
         if (pf.cfg.scorers[s].kind == EPP_SCORER_PREFIX)
             term = __dmul_rn(clamp01(prefix_score(match, total)), pf.cfg.scorers[s].weight);
+        else if (lora_st && pf.cfg.scorers[s].kind == EPP_SCORER_LORA_AFFINITY)
+            term = __dmul_rn(clamp01(lora_score(L, e, lora_st)), pf.cfg.scorers[s].weight);
         else
             term = pf.contrib[(size_t)s * (size_t)E + e];
         acc = __dadd_rn(acc, term);

@@ -238,14 +238,28 @@ class Engine:
         self._check(self._lib.epp_prefix_match(self._h, C.byref(b), _ptr(match), _ptr(total)))
         return match, total
 
-    def score(self, match, total, profile: int = 0, scorer_index: int = -1):
+    def score(self, match, total, profile: int = 0, scorer_index: int = -1, model_ids=None):
         """a5-a9 Scorer.Score / weighted sum -> [R, E] f64 (host arrays)."""
         match = np.ascontiguousarray(match, dtype=np.int32).reshape(-1, self.E)
         total = np.ascontiguousarray(total, dtype=np.int32)
         R = match.shape[0]
+        mids = None if model_ids is None else np.ascontiguousarray(model_ids, dtype=np.uint32)
         out = np.zeros((R, self.E), dtype=np.float64)
-        self._check(self._lib.epp_score(self._h, R, _ptr(match), _ptr(total), profile, scorer_index, _ptr(out), 0))
+        self._check(self._lib.epp_score(self._h, R, _ptr(match), _ptr(total), _ptr(mids), profile, scorer_index, _ptr(out), 0))
         return out
+
+    def pool_set_lora(self, ids, max_active_models, n_models_loaded, members=()):
+        """LoRA residency for the lora-affinity scorer; members = iterable of (endpoint slot, model id, state) with
+        state 1 = active, 2 = waiting (fwkdl.Metrics.ActiveModels / WaitingModels / MaxActiveModels)."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        mx = np.ascontiguousarray(max_active_models, dtype=np.int32)
+        nl = np.ascontiguousarray(n_models_loaded, dtype=np.int32)
+        mem = np.asarray(list(members), dtype=np.int64).reshape(-1, 3)
+        mep = np.ascontiguousarray(mem[:, 0], dtype=np.uint32)
+        mmo = np.ascontiguousarray(mem[:, 1], dtype=np.uint32)
+        mst = np.ascontiguousarray(mem[:, 2], dtype=np.uint8)
+        self._check(self._lib.epp_pool_set_lora(self._h, ids.shape[0], _ptr(ids), _ptr(mx), _ptr(nl), mem.shape[0],
+                                                _ptr(mep), _ptr(mmo), _ptr(mst)))
 
     def schedule(self, data, offsets=None, uniform_len=None, model_ids=None, n_requests=None, keep_hashes=False,
                  detail=True, out=None, lengths=None, asynchronous=False):
@@ -264,14 +278,15 @@ class Engine:
         self._check(self._lib.epp_schedule(self._h, C.byref(b), _ptr(dec), _ptr(det), int(keep_hashes)))
         return dec, det
 
-    def schedule_with_match(self, match, total, input_len_bytes=None, block_size_tokens: int = 0):
+    def schedule_with_match(self, match, total, input_len_bytes=None, block_size_tokens: int = 0, model_ids=None):
         match = np.ascontiguousarray(match, dtype=np.int32).reshape(-1, self.E)
         total = np.ascontiguousarray(total, dtype=np.int32)
         R = match.shape[0]
         il = None if input_len_bytes is None else np.ascontiguousarray(input_len_bytes, dtype=np.int64)
         dec = np.zeros(R, dtype=DECISION_DTYPE)
         det = np.zeros(R, dtype=DETAIL_DTYPE)
-        self._check(self._lib.epp_schedule_with_match(self._h, R, _ptr(match), _ptr(total), _ptr(il),
+        mids = None if model_ids is None else np.ascontiguousarray(model_ids, dtype=np.uint32)
+        self._check(self._lib.epp_schedule_with_match(self._h, R, _ptr(match), _ptr(total), _ptr(mids), _ptr(il),
                                                       block_size_tokens, _ptr(dec), _ptr(det), 0))
         return dec, det
 

@@ -143,6 +143,11 @@ def NewActiveRequest(column: int, idleThreshold: int = 0, maxBusyScore: float = 
     return _Scorer(capi.SCORER_ACTIVE_REQUEST, float(maxBusyScore), "active-request-scorer", column, float(idleThreshold))
 
 
+def LoraAffinityScorer():
+    """ "lora-affinity-scorer" (scorer/loraaffinity/lora_affinity.go:76-100); residency via Engine.pool_set_lora."""
+    return _Scorer(capi.SCORER_LORA_AFFINITY, 0.0, "lora-affinity-scorer")
+
+
 def ExternalScorer(column: int):                 # host-computed column (e.g. lora-affinity)
     return _Scorer(capi.SCORER_EXTERNAL, float(column), "external")
 

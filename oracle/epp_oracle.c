@@ -561,6 +561,17 @@ void orc_score_column(const orc_scorer *s, const orc_pool *pool, const uint8_t *
         }
         break;
     }
+    case ORC_SCORER_LORA_AFFINITY:  /* lora_affinity.go:76-100: the switch, in its order */
+        for (int e = 0; e < n; e++) {
+            if (!cand[e]) { out[e] = 0.0; continue; }
+            int st = pool->lora_state ? pool->lora_state[e] : 0;
+            int room = pool->lora_max && pool->lora_loaded && pool->lora_loaded[e] < pool->lora_max[e];
+            if (st == 1) out[e] = 1.0;            /* active */
+            else if (room) out[e] = 0.8;          /* capacity for one more adapter */
+            else if (st == 2) out[e] = 0.6;       /* waiting */
+            else out[e] = 0.0;
+        }
+        break;
     default:
         for (int e = 0; e < n; e++) out[e] = 0.0;
     }

@@ -73,8 +73,10 @@ enum {
     ORC_SCORER_RUNNING = 5,      /* scorer/runningrequests/runningrequest.go:78-108      */
     ORC_SCORER_TOKEN_LOAD = 6,   /* scorer/tokenload/token_load.go:84-112: column = ext column of InFlightLoad.Tokens,
                                     param = queueThresholdTokens (<= 0: 4194304, :27-28, :60-62) */
-    ORC_SCORER_ACTIVE_REQUEST = 7 /* scorer/activerequest/active_request.go:140-173: column = ext column of
+    ORC_SCORER_ACTIVE_REQUEST = 7, /* scorer/activerequest/active_request.go:140-173: column = ext column of
                                     InFlightLoad.Requests, param = maxBusyScore, param2 = idleThreshold (:83-93) */
+    ORC_SCORER_LORA_AFFINITY = 8  /* scorer/loraaffinity/lora_affinity.go:76-100; reads orc_pool.lora_* (the pool as
+                                    seen by a request whose TargetModel is the adapter lora_state describes) */
 };
 
 /* Role filters: filter/bylabel/roles.go:46-70, filter.go:104-117. */
@@ -116,6 +118,10 @@ typedef struct {
     const int32_t *waiting;      /* WaitingQueueSize                                        */
     const int32_t *running;      /* RunningRequestsSize                                     */
     const double *ext;           /* [n_ext_cols][n] host-computed score columns             */
+    /* LoRA residency for the request's TargetModel (NULL = no adapter information):        */
+    const uint8_t *lora_state;   /* [n] 0 = not resident, 1 = in ActiveModels, 2 = in WaitingModels */
+    const int32_t *lora_max;     /* [n] MaxActiveModels                                     */
+    const int32_t *lora_loaded;  /* [n] len(ActiveModels) + len(WaitingModels)              */
 } orc_pool;
 
 /* SchedulerProfile.Run: scheduling/scheduler_profile.go:117-128 (filters -> scorers -> picker).

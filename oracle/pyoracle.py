@@ -16,7 +16,7 @@ _SO = os.path.join(_HERE, "_build", "libepp_oracle.so")
 
 MAX_SCORERS = 8
 (SCORER_PREFIX, SCORER_KV_UTIL, SCORER_QUEUE, SCORER_LOAD_AWARE, SCORER_EXTERNAL, SCORER_RUNNING, SCORER_TOKEN_LOAD,
- SCORER_ACTIVE_REQUEST) = range(8)
+ SCORER_ACTIVE_REQUEST, SCORER_LORA_AFFINITY) = range(9)
 ROLE_NONE, ROLE_DECODE, ROLE_PREFILL, ROLE_PREFILL_DECODE, ROLE_BOTH, ROLE_ENCODE, ROLE_ENCODE_PREFILL, \
     ROLE_ENCODE_PREFILL_DECODE, ROLE_OTHER = range(9)
 ROLE_ABSENT = 0xFF
@@ -34,7 +34,8 @@ class Profile(C.Structure):
 
 class Pool(C.Structure):
     _fields_ = [("n", C.c_int32), ("n_ext_cols", C.c_int32), ("role", C.c_void_p), ("kv_usage", C.c_void_p),
-                ("waiting", C.c_void_p), ("running", C.c_void_p), ("ext", C.c_void_p)]
+                ("waiting", C.c_void_p), ("running", C.c_void_p), ("ext", C.c_void_p), ("lora_state", C.c_void_p),
+                ("lora_max", C.c_void_p), ("lora_loaded", C.c_void_p)]
 
 
 class Decision(C.Structure):
@@ -166,6 +167,18 @@ class PoolState:
         self.c.waiting = self.waiting.ctypes.data
         self.c.running = self.running.ctypes.data
         self.c.ext = 0 if self.ext is None else self.ext.ctypes.data
+        self.c.lora_state = self.c.lora_max = self.c.lora_loaded = 0
+
+    def set_lora(self, state, max_active, loaded):
+        """LoRA residency as seen by a request for ONE adapter: state[e] in {0, 1 active, 2 waiting}."""
+        self.lora_state = np.ascontiguousarray(state, dtype=np.uint8)
+        self.lora_max = np.ascontiguousarray(max_active, dtype=np.int32)
+        self.lora_loaded = np.ascontiguousarray(loaded, dtype=np.int32)
+        assert self.lora_state.shape[0] == self.lora_max.shape[0] == self.lora_loaded.shape[0] == self.n
+        self.c.lora_state = self.lora_state.ctypes.data
+        self.c.lora_max = self.lora_max.ctypes.data
+        self.c.lora_loaded = self.lora_loaded.ctypes.data
+        return self
 
 
 class Indexer:

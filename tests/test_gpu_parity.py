@@ -650,6 +650,74 @@ def test_token_load_and_active_request_kats(epp):
     assert scores(P.NewActiveRequest(0, -3, 7.0), [2, 4]) == [0.5, 0.0]              # invalid params -> defaults
 
 
+def test_lora_affinity_kats_and_parity(epp, orc, tg):
+    """lora-affinity-scorer: the reference's table (lora_affinity_test.go:30-141) through the engine, then the whole
+    cycle (prefix matches from the index + queue + lora-affinity, three adapters, sparse kernel AND its dense-counter
+    fallback) against the oracle evaluated per adapter."""
+    import torch
+    import helpers
+    P = epp.plugins
+    LA = P.LoraAffinityScorer()
+    prof = epp.ProfileSpec(0, [epp.ScorerSpec(LA.kind, 1.0)])
+    with epp.Engine(5, prof) as eng:
+        m1 = eng.register_model(b"active-model-1")
+        m2 = eng.register_model(b"active-model-2")
+        eng.pool_set(np.arange(5), np.zeros(5, np.uint8), np.zeros(5), np.zeros(5, np.int32), np.zeros(5, np.int32))
+        # pod1..pod5 of "Multiple endpoints with mixed active and waiting models"
+        eng.pool_set_lora(np.arange(5), [5, 5, 2, 2, 2], [1, 2, 1, 2, 2],
+                          [(0, m1, 1), (1, m2, 1), (1, m1, 2), (2, m2, 1), (3, m1, 2)])
+        z = np.zeros((1, 5), np.int32)
+        assert list(eng.score(z, [0], 0, 0, model_ids=[m1])[0]) == [1.0, 0.8, 0.8, 0.6, 0.0]
+        assert list(eng.score(z, [0], 0, 0, model_ids=[m2])[0]) == [0.8, 1.0, 1.0, 0.0, 0.0]
+        dec, _ = eng.schedule_with_match(z, [0], model_ids=[m1])
+        assert dec["pick"][0] == 0 and dec["score"][0] == 1.0 and dec["tie_count"][0] == 1
+
+    # ---- whole cycle, several adapters
+    w = tg.baseline_configs()["config3"].scaled(E=96, R=1536, T=512, name="config3")
+    trace = tg.Trace(w)
+    role, kv, waiting, running = trace.pool()
+    tokens, _, _ = trace.requests()
+    rng = np.random.default_rng(5)
+    A = 3
+    names = [tg.MODEL] + [tg.MODEL + b"-lora%d" % a for a in range(1, A)]
+    mx = rng.integers(0, 5, w.E).astype(np.int32)
+    state = np.zeros((A, w.E), np.uint8)
+    for a in range(A):
+        k = [6, 40, 70][a]                                     # adapter 2 is resident on more endpoints than the lane map holds
+        idx = rng.choice(w.E, k, replace=False)
+        state[a, idx] = rng.choice([1, 2], k)
+    loaded = (state != 0).sum(axis=0).astype(np.int32) + rng.integers(0, 2, w.E).astype(np.int32)
+    scorers = [(0, 2.0, 0.0), (2, 1.0, 0.0), (8, 1.5, 0.0)]    # prefix, queue, lora-affinity
+    model_of = rng.integers(0, A, w.R).astype(np.uint32)
+    with epp.Engine(w.E, epp.ProfileSpec(0, [epp.ScorerSpec(*s) for s in scorers]), block_size_tokens=w.block_size_tokens,
+                    max_prefix_blocks=w.max_prefix_blocks) as eng:
+        mids = [eng.register_model(n) for n in names]
+        eng.pool_set(np.arange(w.E, dtype=np.uint32), role, kv, waiting, running)
+        members = [(e, mids[a], int(state[a, e])) for a in range(A) for e in range(w.E) if state[a, e]]
+        eng.pool_set_lora(np.arange(w.E), mx, loaded, members)
+        # index: every adapter has its own hash chain (the seed is XXH64(model)), families cached per adapter 0 only
+        fh, _ = eng.hash_prompts(trace.family_tokens(), uniform_len=w.prompt_bytes)
+        hs, es = trace.index_pairs(fh)
+        eng.index_load_snapshot(hs, es)
+        ix = orc.Indexer()
+        ix.load_pairs(hs, es)
+        dt = torch.from_numpy(tokens.view(np.int32)).cuda()
+        ddec, _ = eng.schedule(dt, uniform_len=w.prompt_bytes, model_ids=torch.from_numpy(np.array(mids, np.uint32)[model_of].view(np.int32)).cuda())
+        dec = epp.decisions_from_torch(ddec)
+        hdec, _ = eng.schedule(tokens, uniform_len=w.prompt_bytes, model_ids=np.array(mids, np.uint32)[model_of])
+        np.testing.assert_array_equal(hdec, dec)
+        prof_o = orc.make_profile(0, scorers)
+        st = eng.stats()
+        for a in range(A):
+            pool = orc.PoolState(role, kv, waiting, running).set_lora(state[a], mx, loaded)
+            sel = np.flatnonzero(model_of == a)
+            offs = np.arange(len(sel) + 1, dtype=np.uint64) * np.uint64(w.prompt_bytes)
+            odec, ototal = orc.cycle_batch(names[a], w.block_size_tokens, w.max_prefix_blocks, 0, False, ix, prof_o, None,
+                                           pool, np.ascontiguousarray(tokens[sel]), offs, 4)
+            helpers.assert_decisions_equal(dec[sel], None, odec, ototal, where=f"adapter {a}")
+        assert (dec["match_blocks"] > 0).any()
+
+
 # ------------------------------------------------------------------------------------------------
 # the reference's own scheduler tests through the interface mirror
 # ------------------------------------------------------------------------------------------------

@@ -143,6 +143,25 @@ def test_active_request_scorer(orc):
     assert run([2, 4, 8], cand=[1, 1, 0]) == [0.5, 0.0, 0.0]
 
 
+def test_lora_affinity_scorer(orc):
+    # loraaffinity/lora_affinity_test.go:30-141, TargetModel "active-model-1"; per pod (state, MaxActiveModels, loaded)
+    LA = (orc.SCORER_LORA_AFFINITY, 1.0, 0.0)
+
+    def run(pods):
+        st, mx, ld = zip(*pods)
+        pool = _pool(orc, n=len(pods), kv=[0.0] * len(pods)).set_lora(st, mx, ld)
+        return list(orc.score_column(LA, pool, [1] * len(pods), [0] * len(pods), 0))
+
+    assert run([(1, 5, 1)]) == [1.0]                       # "Target model is active"
+    assert run([(2, 2, 2)]) == [0.6]                       # "Target model is waiting" (active-model-2 + waiting = 2 of 2)
+    assert run([(0, 2, 2), (0, 0, 0)]) == [0.0, 0.0]       # "Endpoints have no space for new model"
+    # "Multiple endpoints with mixed active and waiting models"
+    assert run([(1, 5, 1), (2, 5, 2), (0, 2, 1), (2, 2, 2), (0, 2, 2)]) == [1.0, 0.8, 0.8, 0.6, 0.0]
+    # no adapter information at all: nothing is resident, nobody has room
+    pool = _pool(orc, n=2, kv=[0.0, 0.0])
+    assert list(orc.score_column(LA, pool, [1, 1], [0, 0], 0)) == [0.0, 0.0]
+
+
 # ---- B.1 #12: picker/maxscore/picker_test.go:43-110 -- ties are a SET ----------------------------------
 def test_max_score_picker_tie_set(orc):
     pool = _pool(orc, n=4, ext=[[0.5, 0.9, 0.9, 0.1]])
