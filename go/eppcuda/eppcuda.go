@@ -182,6 +182,70 @@ func (e *Engine) RemoveEndpoint(name string) {
 	}
 }
 
+// RetainEndpoints mirrors CleanUpInactivePods (approximateprefix/plugin.go:99-122): every indexed endpoint that is not
+// in `active` loses its LRU and its postings (RemovePod), on the device, in one call.
+func (e *Engine) RetainEndpoints(active []string) error {
+	e.mu.Lock()
+	ids := make([]C.uint32_t, 0, len(active))
+	for _, name := range active {
+		if s, ok := e.slots[name]; ok {
+			ids = append(ids, C.uint32_t(s))
+		}
+	}
+	e.mu.Unlock()
+	var p *C.uint32_t
+	if len(ids) > 0 {
+		p = &ids[0]
+	}
+	if rc := C.epp_index_retain_endpoints(e.h, C.int32_t(len(ids)), p); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// LoraState is fwkdl.Metrics.{ActiveModels, WaitingModels, MaxActiveModels} of one endpoint (metrics.go:26-42) with the
+// adapter names already translated to model ids (epp_model_register).
+type LoraState struct {
+	Endpoint        string
+	MaxActiveModels int
+	Active, Waiting []uint32
+}
+
+// SetLora feeds the lora-affinity scorer (scorer/loraaffinity/lora_affinity.go:76-100); call it after SetPool of the
+// same scrape.
+func (e *Engine) SetLora(states []LoraState) error {
+	n := len(states)
+	if n == 0 {
+		return nil
+	}
+	ids := make([]C.uint32_t, n)
+	mx := make([]C.int32_t, n)
+	cnt := make([]C.int32_t, n)
+	var mep, mmo []C.uint32_t
+	var mst []C.uint8_t
+	e.mu.Lock()
+	for i, st := range states {
+		s := e.slotOf(st.Endpoint)
+		ids[i], mx[i], cnt[i] = C.uint32_t(s), C.int32_t(st.MaxActiveModels), C.int32_t(len(st.Active)+len(st.Waiting))
+		for _, m := range st.Active {
+			mep, mmo, mst = append(mep, C.uint32_t(s)), append(mmo, C.uint32_t(m)), append(mst, 1)
+		}
+		for _, m := range st.Waiting {
+			mep, mmo, mst = append(mep, C.uint32_t(s)), append(mmo, C.uint32_t(m)), append(mst, 2)
+		}
+	}
+	e.mu.Unlock()
+	var pe, pm *C.uint32_t
+	var ps *C.uint8_t
+	if len(mep) > 0 {
+		pe, pm, ps = &mep[0], &mmo[0], &mst[0]
+	}
+	if rc := C.epp_pool_set_lora(e.h, C.int32_t(n), &ids[0], &mx[0], &cnt[0], C.int64_t(len(mep)), pe, pm, ps); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
 // Decision is one epp_decision translated back to endpoint names.
 type Decision struct {
 	Err         error
