@@ -116,6 +116,7 @@ struct epp_engine {
     int force_v1 = 0;               // EPP_HASH_V1=1: unfused v1 hash kernels (A/B)
     int force_match_v1 = 0;         // EPP_MATCH_V1=1: dense-counter match kernel only (A/B)
     int prefetch = 0;               // EPP_PREFETCH=1
+    int index_load = 2;             // EPP_INDEX_LOAD=n: read-table slots per distinct hash (2 = load factor <= 0.5, 4 = <= 0.25)
     int tile_rows = 32;             // EPP_TILE_ROWS=n: requests per hash tile (0 = balance the waves of the persistent grid; measured: no gain)
     int dev_ordered = 0;            // EPP_DEV_ORDERED=1: chunk c's hash kernel waits for chunk c-1's
     cudaEvent_t hash_done[8] = {};
@@ -266,6 +267,7 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
     { const char *v1 = getenv("EPP_MATCH_V1"); e->force_match_v1 = (v1 && v1[0] == '1') ? 1 : 0; }
     { const char *v1 = getenv("EPP_WIDE"); e->wide = (v1 && v1[0] == '1') ? 1 : 0; }
     { const char *v1 = getenv("EPP_HASH_BULK"); e->bulk = v1 ? atoi(v1) : 0; }
+    { const char *v1 = getenv("EPP_INDEX_LOAD"); e->index_load = v1 ? std::max(2, atoi(v1)) : 2; }
     { const char *v1 = getenv("EPP_TILE_ROWS"); e->tile_rows = v1 ? atoi(v1) : 32; }
     { const char *v1 = getenv("EPP_DEV_ORDERED"); e->dev_ordered = v1 ? atoi(v1) : 0; }
     for (auto &ev : e->hash_done) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -533,7 +535,7 @@ static int32_t build_index_from_device_pairs(epp_engine *h, uint64_t n, uint64_t
     uint64_t cap = 16;
     for (int pass = 0; pass < 2; pass++) {
         // load factor <= 0.5 over the distinct hashes; the first pass only knows an upper bound (the pair count)
-        uint64_t want = std::max<uint64_t>(16, 2 * distinct);
+        uint64_t want = std::max<uint64_t>(16, (uint64_t)h->index_load * distinct);
         cap = 16;
         while (cap < want) cap <<= 1;
         CUDA_TRY(h->slots.reserve(sizeof(IndexSlot) * cap, &h->dev_bytes));
@@ -549,7 +551,7 @@ static int32_t build_index_from_device_pairs(epp_engine *h, uint64_t n, uint64_t
         CUDA_TRY(cudaStreamSynchronize(s));
         uint64_t true_distinct = std::max<uint64_t>(1, cursor[2]);
         uint64_t tight = 16;
-        while (tight < 2 * true_distinct) tight <<= 1;
+        while (tight < (uint64_t)h->index_load * true_distinct) tight <<= 1;
         if (tight >= cap) break;            // already as small as the load factor allows
         distinct = true_distinct;           // rebuild once into a table a quarter (or less) of the size
     }

@@ -137,6 +137,19 @@ __device__ __forceinline__ void count_chunk(LaneMap &m, const IndexView &ix, con
         }
     }
 }
+// indexer.Get for the hot loop: 32-bit slot arithmetic (the table never exceeds 2^32 slots), no per-call checks.  A
+// hash equal to the free-slot sentinel ends at the first free slot like any absent hash; its side record is consulted
+// by the caller on that (rare) miss.
+__device__ __forceinline__ bool probe_fast(const IndexSlot *slots, uint32_t mask, uint64_t hash, Hit &h) {
+    uint32_t i = (uint32_t)hash & mask;
+    for (;;) {
+        uint64_t key;
+        load_slot(slots + i, key, h);
+        if (h.cnt == 0) return false;
+        if (key == hash) return true;
+        i = (i + 1) & mask;
+    }
+}
 }  // namespace
 
 __global__ void __launch_bounds__(kWarps * 32, kMinCtas) k_match_pick_sparse(PickParams p) {
@@ -146,6 +159,9 @@ __global__ void __launch_bounds__(kWarps * 32, kMinCtas) k_match_pick_sparse(Pic
     const int64_t nwarps = (int64_t)gridDim.x * kWarps;
     unsigned long long w_probes = 0, w_postings = 0;
     const uint32_t shard_lo = p.index.ep_begin, shard_hi = min(p.index.ep_end, (uint32_t)p.E);
+    const IndexSlot *slots = p.index.slots;
+    const uint32_t mask32 = (uint32_t)p.index.mask;
+    const bool counting = p.work_counters != nullptr;
 
     for (int64_t r = gwarp; r < p.R; r += nwarps) {
         const int32_t total = p.nblocks[r];
@@ -163,7 +179,14 @@ __global__ void __launch_bounds__(kWarps * 32, kMinCtas) k_match_pick_sparse(Pic
             if (i + 32 < total) hnext = row[i + 32];                  // next chunk's hashes in flight during this one
             Hit hit;
             hit.cnt = 0;
-            if (i < total && !probe(p.index, hcur, hit)) hit.cnt = 0;
+            if (i < total && slots) {
+                if (!probe_fast(slots, mask32, hcur, hit)) {
+                    hit.cnt = 0;
+                    if (hcur == kEmptyKey && !probe(p.index, hcur, hit)) hit.cnt = 0;     // the sentinel hash's side record
+                }
+            } else if (i < total && hcur == kEmptyKey) {
+                if (!probe(p.index, hcur, hit)) hit.cnt = 0;
+            }
             uint32_t miss;
             if (p.global_masks) {   // sharded: a block is missing only if NO rank holds it
                 uint32_t word = p.global_masks[r * (int64_t)p.mask_words + (cq >> 5)];
@@ -174,8 +197,10 @@ __global__ void __launch_bounds__(kWarps * 32, kMinCtas) k_match_pick_sparse(Pic
             }
             const int32_t limit = miss ? cq + (__ffs(miss) - 1) : total;
             const uint32_t cnt = (i < limit) ? hit.cnt : 0;
-            if (lane == 0) w_probes += (unsigned long long)((miss ? limit + 1 : min(total, cq + 32)) - cq);
-            w_postings += cnt;
+            if (counting) {
+                if (lane == 0) w_probes += (unsigned long long)((miss ? limit + 1 : min(total, cq + 32)) - cq);
+                w_postings += cnt;
+            }
             if (limit > cq) count_chunk(m, p.index, hit, cnt, shard_lo, shard_hi, lane);
             if (miss) stopped = true;
         }
