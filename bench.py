@@ -332,7 +332,7 @@ def run_gpu(args, rank, world, local_rank):
     dev_dec = torch.empty((R, 32), dtype=torch.uint8, device="cuda")
 
     eng = helpers.make_engine(w, device=local_rank)
-    helpers.setup_engine(eng, w, trace)
+    helpers.setup_engine(eng, w, trace, filler_per_endpoint=args.index_fill)
     st0 = eng.stats()
 
     def barrier():
@@ -468,7 +468,8 @@ def run_gpu(args, rank, world, local_rank):
                          "launch_ms": dom_ms},
             "cpu_baseline": cpu,
             "index_write": index_write,
-            "index": {"pairs": st0["index_pairs"], "slots": st0["index_slots"], "probes_per_step": int(probes),
+            "index": {"pairs": st0["index_pairs"], "slots": st0["index_slots"], "filler_per_endpoint": args.index_fill,
+                      "device_bytes": st0["device_bytes"], "probes_per_step": int(probes),
                       "postings_per_step": int(postings)},
         }
         print(json.dumps(out), flush=True)
@@ -578,6 +579,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-index-write", action="store_true", help="skip the index write-side leg (SURVEY 8(f).1)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs only)")
+    ap.add_argument("--index-fill", type=int, default=0,
+                    help="extra never-matching index entries per endpoint (31250 = every endpoint's LRU full: 1.28e8 pairs, "
+                         "a table far larger than L2); decisions are unchanged")
     ap.add_argument("--pitch-pad", type=int, default=0,
                     help="experiment: lay the device-resident prompts out with this many pad bytes between requests")
     args = ap.parse_args()

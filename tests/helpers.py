@@ -16,7 +16,18 @@ def make_engine(w: tg.Workload, **kw) -> epp.Engine:
                       max_prefix_blocks=w.max_prefix_blocks, non_cached_tokens=w.non_cached_tokens, **kw)
 
 
-def setup_engine(eng: epp.Engine, w: tg.Workload, trace: tg.Trace):
+def filler_pairs(E: int, per_endpoint: int, seed: int = 0x0F111E5):
+    """`per_endpoint` extra (hash, endpoint) pairs per endpoint whose hashes no prompt of the trace produces: they fill
+    the index to its production size (31 250 blocks per endpoint = the reference's default LRU capacity) without
+    changing a single decision."""
+    rng = np.random.default_rng(seed)
+    n = E * per_endpoint
+    hs = rng.integers(1, 2**63, size=n, dtype=np.int64).view(np.uint64) | np.uint64(1 << 63)
+    es = np.repeat(np.arange(E, dtype=np.uint32), per_endpoint)
+    return hs, es
+
+
+def setup_engine(eng: epp.Engine, w: tg.Workload, trace: tg.Trace, filler_per_endpoint: int = 0):
     """model + pool snapshot + index snapshot (family hashes come from the ENGINE's own hash kernel)."""
     mid = eng.register_model(tg.MODEL)
     role, kv, waiting, running = trace.pool()
@@ -24,6 +35,9 @@ def setup_engine(eng: epp.Engine, w: tg.Workload, trace: tg.Trace):
     fam = trace.family_tokens()
     fh, nb = eng.hash_prompts(fam, uniform_len=w.prompt_bytes)
     hs, es = trace.index_pairs(fh)
+    if filler_per_endpoint > 0:
+        fhs, fes = filler_pairs(w.E, filler_per_endpoint)
+        hs, es = np.concatenate([hs, fhs]), np.concatenate([es, fes])
     eng.index_load_snapshot(hs, es)
     return mid, (hs, es)
 
