@@ -200,6 +200,7 @@ typedef struct {
     double last_index_build_ms;        /* export of the inverted map + bulk build of the read table (host clock) */
     uint64_t last_index_items;         /* hashes added by the last applied batch                               */
     uint64_t last_index_launches;      /* kernels launched by it                                               */
+    uint64_t last_index_patched;       /* 1: the last commit patched the read table from the change log; 0: bulk build */
 } epp_stats;
 
 /* ---- lifecycle --------------------------------------------------------------------------------- */

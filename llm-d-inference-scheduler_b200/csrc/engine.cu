@@ -106,6 +106,11 @@ struct epp_engine {
     bool snapshot_mode = false;
     DevBuf slots, postings, idx_scratch, idx_cursor, idx_special, pair_hash, pair_ep, get_out, intern_keys, intern_vals;
     uint64_t idx_capacity = 0, idx_pairs = 0;
+    // incremental maintenance of the read table (IndexStore::patch_read_table)
+    bool rt_from_store = false;     // the table mirrors the store's inverted map (bulk-built from its export)
+    uint64_t post_cap = 0, post_used = 0, rt_slots_used = 0;
+    int patches_since_build = 0;
+    int patch_enabled = 1;          // EPP_INDEX_PATCH=0: always rebuild
     IndexSlot idx_special_host{};
     uint32_t shard_begin = 0, shard_end = 0xFFFFFFFFu;
 
@@ -267,6 +272,7 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
     { const char *v1 = getenv("EPP_MATCH_V1"); e->force_match_v1 = (v1 && v1[0] == '1') ? 1 : 0; }
     { const char *v1 = getenv("EPP_WIDE"); e->wide = (v1 && v1[0] == '1') ? 1 : 0; }
     { const char *v1 = getenv("EPP_HASH_BULK"); e->bulk = v1 ? atoi(v1) : 0; }
+    { const char *v1 = getenv("EPP_INDEX_PATCH"); e->patch_enabled = v1 ? atoi(v1) : 1; }
     { const char *v1 = getenv("EPP_INDEX_LOAD"); e->index_load = v1 ? std::max(2, atoi(v1)) : 2; }
     { const char *v1 = getenv("EPP_TILE_ROWS"); e->tile_rows = v1 ? atoi(v1) : 32; }
     { const char *v1 = getenv("EPP_DEV_ORDERED"); e->dev_ordered = v1 ? atoi(v1) : 0; }
@@ -526,10 +532,13 @@ extern "C" int32_t epp_pool_set_lora(epp_engine *h, int32_t n, const uint32_t *i
 // prefix index
 // ------------------------------------------------------------------------------------------------
 // Bulk build of the read table from n (hash, endpoint) pairs already in h->pair_hash / h->pair_ep.
-static int32_t build_index_from_device_pairs(epp_engine *h, uint64_t n, uint64_t n_distinct_hint) {
+static int32_t build_index_from_device_pairs(epp_engine *h, uint64_t n, uint64_t n_distinct_hint, bool from_store = false) {
     cudaStream_t s = h->slot[0].stream;
     if (n >= 0xFFFFFFF0ull) return fail(EPP_ERR_CAPACITY, "index snapshot of %llu pairs exceeds the u32 posting space", (unsigned long long)n);
-    CUDA_TRY(h->postings.reserve(sizeof(uint32_t) * std::max<uint64_t>(n, 1), &h->dev_bytes));
+    // posting space: the lists of this build + room for the copy-on-write lists of later patches
+    uint64_t post_entries = std::max<uint64_t>(n, 1);
+    if (from_store) post_entries = std::min<uint64_t>(0xFFFFFFF0ull, n + std::max<uint64_t>(n / 2, 1ull << 20));
+    CUDA_TRY(h->postings.reserve(sizeof(uint32_t) * post_entries, &h->dev_bytes));
     uint64_t distinct = std::max<uint64_t>(1, n_distinct_hint);
     uint32_t cursor[4] = {0, 0, 0, 0};
     uint64_t cap = 16;
@@ -560,6 +569,13 @@ static int32_t build_index_from_device_pairs(epp_engine *h, uint64_t n, uint64_t
     h->stats.index_pairs = n;
     h->stats.index_hashes = cursor[2];
     h->stats.index_slots = cap;
+    // patch bookkeeping: pending-list heads idle, posting cursor, used slots
+    CUDA_TRY(cudaMemsetAsync(h->idx_scratch.p, 0xFF, sizeof(uint32_t) * cap, s));
+    h->post_cap = h->postings.cap / sizeof(uint32_t);
+    h->post_used = cursor[0];
+    h->rt_slots_used = cursor[2];
+    h->rt_from_store = from_store;
+    h->patches_since_build = 0;
     return EPP_OK;
 }
 
@@ -620,9 +636,38 @@ static int32_t commit_locked(epp_engine *h) {
     EPP_TRY(flush_add_queue(h));
     if (!h->store->dirty()) return EPP_OK;
     auto t0 = std::chrono::steady_clock::now();
-    uint64_t n = 0;
-    CUDA_TRY(h->store->export_pairs(h->pair_hash, h->pair_ep, &n, &h->dev_bytes, h->slot[0].stream));
-    EPP_TRY(build_index_from_device_pairs(h, n, n));
+    cudaStream_t s = h->slot[0].stream;
+    bool patched = false;
+    if (h->patch_enabled && h->rt_from_store && h->idx_capacity && h->patches_since_build < 256) {
+        ReadTableRef rt;
+        rt.slots = h->slots.as<IndexSlot>();
+        rt.capacity = h->idx_capacity;
+        rt.slots_used = h->rt_slots_used;
+        rt.postings = h->postings.as<uint32_t>();
+        rt.post_cap = h->post_cap;
+        rt.post_used = h->post_used;
+        rt.head = h->idx_scratch.as<uint32_t>();
+        rt.intern_keys = h->intern_keys.as<uint64_t>();
+        rt.intern_vals = h->intern_vals.as<uint32_t>();
+        uint64_t np = 0, nu = 0, npost = 0;
+        CUDA_TRY(h->store->patch_read_table(rt, h->idx_pairs, s, &patched, &np, &nu, &npost));
+        if (patched) {
+            h->idx_pairs = np;
+            h->rt_slots_used = nu;
+            h->post_used = npost;
+            h->stats.index_pairs = np;
+            h->stats.index_hashes = nu;
+            h->patches_since_build++;
+            h->stats.last_index_patched = 1;
+        }
+    }
+    if (!patched) {
+        uint64_t n = 0;
+        CUDA_TRY(h->store->export_pairs(h->pair_hash, h->pair_ep, &n, &h->dev_bytes, s));
+        EPP_TRY(build_index_from_device_pairs(h, n, n, true));
+        h->stats.last_index_patched = 0;
+    }
+    CUDA_TRY(h->store->touch_reset(s));
     h->store->mark_clean();
     h->stats.last_index_build_ms = ms_since(t0);
     return EPP_OK;

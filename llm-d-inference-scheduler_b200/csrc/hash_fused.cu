@@ -450,10 +450,11 @@ __global__ void __launch_bounds__(TR * kWin + 32) k_cycle_fused(HashParams p, Pi
                             sl.key = ((uint64_t)a.y << 32) | a.x;
                             sl.cnt = a.z; sl.w0 = a.w; sl.w1 = b4.x; sl.w2 = b4.y; sl.w3 = b4.z; sl.w4 = b4.w;
                             uint64_t i = h & mask;
-                            while (sl.cnt != 0 && sl.key != h) {   // linear probing past colliding keys (rare)
+                            while (sl.key != h && sl.key != kEmptyKey) {   // linear probing past colliding keys (rare)
                                 i = (i + 1) & mask;
                                 sl = lane::ld_slot(slots + i);
                             }
+                            if (sl.key != h) sl.cnt = 0;
                         }
                     }
                     const bool present = active && sl.cnt != 0;

@@ -36,8 +36,11 @@ __device__ __forceinline__ bool probe(const IndexView &ix, uint64_t hash, Hit &h
     for (;;) {
         uint64_t key;
         load_slot(ix.slots + i, key, h);
-        if (h.cnt == 0) return false;                     // empty slot terminates the probe sequence
-        if (key == hash) return true;
+        if (key == hash) return h.cnt != 0;               // cnt == 0: every holder was evicted (incremental patching)
+        if (key == kEmptyKey) {                           // a never-used slot terminates the probe sequence
+            h.cnt = 0;
+            return false;
+        }
         i = (i + 1) & ix.mask;
     }
 }

@@ -14,7 +14,8 @@ constexpr unsigned long long kLeakBit = 1ull << 63;   // log entry: evicting it 
 constexpr unsigned long long kTmpBit = 1ull << 62;    // scratch of k_store_leak
 constexpr unsigned long long kSeqMask = ~(kLeakBit | kTmpBit);
 constexpr int kCallChunk = 1024;                      // calls per ordering chunk (= threads of k_store_offsets)
-enum { kCtrPtUsed = 0, kCtrTotalItems, kCtrNeedRepack, kCtrInMap, kCtrCursor, kCtrAlive, kCtrEvict, kCtrN = 8 };
+enum { kCtrPtUsed = 0, kCtrTotalItems, kCtrNeedRepack, kCtrInMap, kCtrCursor, kCtrAlive, kCtrEvict, kCtrTouch,
+       kCtrTouchLost, kCtrPatchFlag, kCtrPatchDirty, kCtrPatchClaims, kCtrPatchAdd, kCtrPatchDel, kCtrPatchPost, kCtrN = 16 };
 
 // One (hash, endpoint) pair of the write side: 32 bytes = one sector.
 struct __align__(32) StoreEntry {
@@ -37,6 +38,11 @@ struct IndexStore::View {
     uint32_t *cap, *live, *firstcall, *sp_in_map;
     unsigned long long *seg_off, *seg_cap, *head, *tail, *inc, *next_seq, *sp_seq, *cut;
     unsigned long long *ctr;
+    // touch log: every (hash, endpoint) whose membership in the inverted map changed since the read table was last
+    // brought up to date (consumed by patch_read_table)
+    unsigned long long *touch_hash;
+    uint32_t *touch_ep;
+    unsigned long long touch_cap;
 };
 
 namespace {
@@ -107,6 +113,25 @@ __device__ __forceinline__ bool ref_find(const View &v, uint64_t h, uint32_t e, 
     if (!s) return false;
     r = {&s->seq, &s->in_map};
     return true;
+}
+
+// Appends this lane's (hash, endpoint) to the touch log; warp-aggregated, every lane of the warp must call it.
+__device__ __forceinline__ void touch_append(const View &v, bool take, unsigned long long hsh, uint32_t ep) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, take);
+    if (!ballot) return;
+    unsigned long long base = 0;
+    if (lane == (uint32_t)(__ffs(ballot) - 1)) base = atomicAdd(&v.ctr[kCtrTouch], (unsigned long long)__popc(ballot));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(ballot) - 1);
+    if (take) {
+        const unsigned long long at = base + __popc(ballot & ((1u << lane) - 1u));
+        if (at < v.touch_cap) {
+            v.touch_hash[at] = hsh;
+            v.touch_ep[at] = ep;
+        } else {
+            v.ctr[kCtrTouchLost] = 1;          // the log is incomplete: the next commit rebuilds the table instead
+        }
+    }
 }
 
 // ---- table / state initialisation ---------------------------------------------------------------------------------
@@ -232,13 +257,21 @@ __global__ void k_store_upsert(View v, uint32_t M, const uint32_t *call_ep, cons
         const unsigned long long seq0 = v.next_seq[e] + off;
         const unsigned long long pos0 = v.seg_off[e] + v.head[e] + off;
         const unsigned long long *src = hashes + call_src[c];
-        for (uint32_t i = lane; i < n; i += 32) {
-            const unsigned long long hsh = src[i], seq = seq0 + i;
-            v.log_hash[pos0 + i] = hsh;
-            v.log_seq[pos0 + i] = seq;
-            EntryRef r = ref_claim(v, hsh, e, claimed);
-            if (atomicMax(r.seq, seq) == 0) live_new++;                      // lru.Add of an absent key
-            if (*reinterpret_cast<volatile uint32_t *>(r.in_map) == 0 && atomicExch(r.in_map, 1u) == 0) in_map_new++;
+        for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            bool added = false;
+            unsigned long long hsh = 0;
+            if (i < n) {
+                hsh = src[i];
+                const unsigned long long seq = seq0 + i;
+                v.log_hash[pos0 + i] = hsh;
+                v.log_seq[pos0 + i] = seq;
+                EntryRef r = ref_claim(v, hsh, e, claimed);
+                if (atomicMax(r.seq, seq) == 0) live_new++;                  // lru.Add of an absent key
+                added = *reinterpret_cast<volatile uint32_t *>(r.in_map) == 0 && atomicExch(r.in_map, 1u) == 0;
+                if (added) in_map_new++;
+            }
+            touch_append(v, added, hsh, e);
         }
         for (int o = 16; o; o >>= 1) live_new += __shfl_xor_sync(0xFFFFFFFFu, live_new, o);
         if (lane == 0 && live_new) atomicAdd(&v.live[e], live_new);
@@ -433,16 +466,22 @@ __global__ void __launch_bounds__(kEvictBlock) k_evict_apply(View v, const uint3
         unsigned long long b;
         evict_locate(v, list_e, list_start, n, g, e, b);
         const unsigned long long idx = b * kEvictBlock + threadIdx.x;
-        if (idx < v.tail[e] || idx >= v.cut[e]) continue;
-        bool leak;
-        EntryRef r;
-        if (log_entry_live(v, e, v.seg_off[e] + idx, r, leak)) {
-            *r.seq = 0;                                  // out of the LRU ...
-            if (!leak) {                                 // ... and, through the eviction callback, out of the map
-                *r.in_map = 0;
-                removed++;
+        bool gone = false;
+        unsigned long long hsh = 0;
+        if (idx >= v.tail[e] && idx < v.cut[e]) {
+            bool leak;
+            EntryRef r;
+            hsh = v.log_hash[v.seg_off[e] + idx];
+            if (log_entry_live(v, e, v.seg_off[e] + idx, r, leak)) {
+                *r.seq = 0;                              // out of the LRU ...
+                if (!leak) {                             // ... and, through the eviction callback, out of the map
+                    *r.in_map = 0;
+                    removed++;
+                    gone = true;
+                }
             }
         }
+        touch_append(v, gone, hsh, e);
     }
     for (int o = 16; o; o >>= 1) removed += __shfl_xor_sync(0xFFFFFFFFu, removed, o);
     if ((threadIdx.x & 31) == 0 && removed) atomicAdd(&v.ctr[kCtrInMap], (unsigned long long)(0ull - removed));
@@ -499,14 +538,22 @@ __global__ void k_store_compact(View v) {
 __device__ __forceinline__ void remove_endpoint_warp(const View &v, uint32_t e, uint32_t lane) {
     const unsigned long long head = v.head[e], seg = v.seg_off[e];
     unsigned long long removed = 0;
-    for (unsigned long long idx = v.tail[e] + lane; idx < head; idx += 32) {
-        EntryRef r;
-        bool leak;
-        if (log_entry_live(v, e, seg + idx, r, leak)) {
-            *r.seq = 0;
-            *r.in_map = 0;
-            removed++;
+    for (unsigned long long pos = v.tail[e]; pos < head; pos += 32) {
+        const unsigned long long idx = pos + lane;
+        bool gone = false;
+        unsigned long long hsh = 0;
+        if (idx < head) {
+            EntryRef r;
+            bool leak;
+            hsh = v.log_hash[seg + idx];
+            if (log_entry_live(v, e, seg + idx, r, leak)) {
+                *r.seq = 0;
+                *r.in_map = 0;
+                removed++;
+                gone = true;
+            }
         }
+        touch_append(v, gone, hsh, e);
     }
     for (int o = 16; o; o >>= 1) removed += __shfl_xor_sync(0xFFFFFFFFu, removed, o);
     __syncwarp();
@@ -609,6 +656,167 @@ __global__ void k_store_export(View v, uint64_t capacity, unsigned long long *ou
     }
 }
 
+
+// ---- incremental maintenance of the READ table (index_kernels.cu layout) from the touch log ---------------------------
+// The log names every (hash, endpoint) whose membership changed; the pair table holds the FINAL membership, so applying
+// the log is idempotent and order-free:  for every touched hash, new list = (old list U touched endpoints that are
+// in the map) \ (touched endpoints that are not).  Lists never change in place when spilled: the new list is written to
+// fresh posting space (other slots may share the old one through interning), the old space becomes garbage until the
+// next bulk build.  A hash whose last endpoint leaves keeps its slot with cnt = 0 (a tombstone: probes continue past
+// it, and finding it means "nobody holds the block").
+constexpr uint32_t kNil = 0xFFFFFFFFu;
+constexpr int kPatchLocal = 16;
+
+struct PatchView {
+    IndexSlot *slots;
+    uint64_t mask;
+    uint32_t *postings;
+    unsigned long long post_cap;
+    unsigned long long *post_cursor;   // posting entries used (64-bit: failed allocations must not wrap)
+    uint32_t *head;              // [capacity] pending-list head per slot (kNil when idle)
+    uint32_t *next;              // [n_touch]
+    uint32_t *dirty;             // [n_touch] slots with pending entries
+    uint64_t *intern_keys;       // interning table of the last bulk build (capacity entries)
+    uint32_t *intern_vals;
+};
+
+__device__ __forceinline__ uint64_t rt_find_or_claim(const PatchView &pv, uint64_t key, uint32_t &claimed) {
+    uint64_t i = key & pv.mask;
+    for (;;) {
+        unsigned long long *kp = reinterpret_cast<unsigned long long *>(&pv.slots[i].key);
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(kp);
+        if (cur == key) return i;
+        if (cur == kEmptyKey) {
+            unsigned long long old = atomicCAS(kp, (unsigned long long)kEmptyKey, (unsigned long long)key);
+            if (old == kEmptyKey) { claimed++; return i; }
+            if (old == key) return i;
+        }
+        i = (i + 1) & pv.mask;
+    }
+}
+
+// Same list hash as index_kernels.cu (interning).
+__device__ __forceinline__ uint64_t patch_list_hash(const uint32_t *list, uint32_t cnt) {
+    uint64_t h = 0x9E3779B185EBCA87ULL ^ cnt;
+    for (uint32_t k = 0; k < cnt; k++) {
+        h ^= list[k];
+        h *= 0xC2B2AE3D27D4EB4FULL;
+        h ^= h >> 29;
+    }
+    return h == kEmptyKey ? 0 : h;
+}
+
+__global__ void k_patch_group(View v, PatchView pv, unsigned long long n_touch) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_touch) return;
+    const unsigned long long hsh = v.touch_hash[t];
+    if (hsh == kEmptyKey) {                       // the sentinel hash lives in the side record: bulk build handles it
+        v.ctr[kCtrPatchFlag] = 1;
+        return;
+    }
+    uint32_t claimed = 0;
+    const uint64_t slot = rt_find_or_claim(pv, hsh, claimed);
+    if (claimed) atomicAdd(&v.ctr[kCtrPatchClaims], 1ull);
+    const uint32_t old = atomicExch(&pv.head[slot], (uint32_t)t);
+    pv.next[t] = old;
+    if (old == kNil) pv.dirty[atomicAdd(&v.ctr[kCtrPatchDirty], 1ull)] = (uint32_t)slot;
+}
+
+// Sorted-list helpers on a small array / a posting range.
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *a, uint32_t n, uint32_t x) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ uint32_t list_apply(uint32_t *a, uint32_t n, uint32_t ep, bool member) {
+    const uint32_t p = lower_bound_u32(a, n, ep);
+    const bool present = p < n && a[p] == ep;
+    if (member && !present) {
+        for (uint32_t k = n; k > p; k--) a[k] = a[k - 1];
+        a[p] = ep;
+        return n + 1;
+    }
+    if (!member && present) {
+        for (uint32_t k = p; k + 1 < n; k++) a[k] = a[k + 1];
+        return n - 1;
+    }
+    return n;
+}
+
+__global__ void k_patch_apply(View v, PatchView pv, unsigned long long n_dirty) {
+    const unsigned long long d = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_dirty) return;
+    const uint32_t si = pv.dirty[d];
+    IndexSlot *sl = &pv.slots[si];
+    const uint64_t hsh = sl->key;
+    const uint32_t cnt = sl->cnt;
+    uint32_t k = 0;
+    for (uint32_t t = pv.head[si]; t != kNil; t = pv.next[t]) k++;
+    const bool was_spilled = cnt > (uint32_t)kInlineIds;
+    const uint32_t old_off = sl->ids[0];
+    uint32_t n_new;
+    if (!was_spilled && cnt + k <= (uint32_t)kPatchLocal) {
+        // ---- short list: registers / local memory, no posting space unless it outgrows the slot
+        uint32_t a[kPatchLocal];
+        for (uint32_t q = 0; q < cnt; q++) a[q] = sl->ids[q];
+        n_new = cnt;
+        for (uint32_t t = pv.head[si]; t != kNil; t = pv.next[t]) {
+            const uint32_t ep = v.touch_ep[t];
+            const StoreEntry *pe = pt_find(v, hsh, ep);
+            n_new = list_apply(a, n_new, ep, pe && pe->in_map != 0);
+        }
+        if (n_new <= (uint32_t)kInlineIds) {
+            for (uint32_t q = 0; q < (uint32_t)kInlineIds; q++) sl->ids[q] = q < n_new ? a[q] : 0u;
+        } else {
+            const unsigned long long off = atomicAdd(pv.post_cursor, (unsigned long long)n_new);
+            if (off + n_new > pv.post_cap) { v.ctr[kCtrPatchFlag] = 1; pv.head[si] = kNil; return; }
+            for (uint32_t q = 0; q < n_new; q++) pv.postings[off + q] = a[q];
+            sl->ids[0] = (uint32_t)off;
+            for (uint32_t q = 1; q < (uint32_t)kInlineIds; q++) sl->ids[q] = 0u;
+        }
+    } else {
+        // ---- long list: copy-on-write into fresh posting space sized for the worst case
+        const unsigned long long need = (unsigned long long)cnt + k;
+        const unsigned long long off = atomicAdd(pv.post_cursor, need);
+        if (off + need > pv.post_cap) { v.ctr[kCtrPatchFlag] = 1; pv.head[si] = kNil; return; }
+        uint32_t *a = pv.postings + off;
+        if (was_spilled) {
+            // if this slot is the interning canonical of its old list, retire it so that a later equal list can register
+            const uint64_t j0 = patch_list_hash(pv.postings + old_off, cnt) & pv.mask;
+            for (uint64_t j = j0;; j = (j + 1) & pv.mask) {
+                const uint64_t key = pv.intern_keys[j];
+                if (key == kEmptyKey) break;
+                if (pv.intern_vals[j] == si) { pv.intern_vals[j] = kNil; break; }
+                if (((j + 1) & pv.mask) == j0) break;
+            }
+            for (uint32_t q = 0; q < cnt; q++) a[q] = pv.postings[old_off + q];
+        } else {
+            for (uint32_t q = 0; q < cnt; q++) a[q] = sl->ids[q];
+        }
+        n_new = cnt;
+        for (uint32_t t = pv.head[si]; t != kNil; t = pv.next[t]) {
+            const uint32_t ep = v.touch_ep[t];
+            const StoreEntry *pe = pt_find(v, hsh, ep);
+            n_new = list_apply(a, n_new, ep, pe && pe->in_map != 0);
+        }
+        if (n_new <= (uint32_t)kInlineIds) {
+            uint32_t tmp[kInlineIds];
+            for (uint32_t q = 0; q < (uint32_t)kInlineIds; q++) tmp[q] = q < n_new ? a[q] : 0u;
+            for (uint32_t q = 0; q < (uint32_t)kInlineIds; q++) sl->ids[q] = tmp[q];
+        } else {
+            sl->ids[0] = (uint32_t)off;
+            for (uint32_t q = 1; q < (uint32_t)kInlineIds; q++) sl->ids[q] = 0u;
+        }
+    }
+    sl->cnt = n_new;
+    pv.head[si] = kNil;
+    if (n_new > cnt) atomicAdd(&v.ctr[kCtrPatchAdd], (unsigned long long)(n_new - cnt));
+    if (n_new < cnt) atomicAdd(&v.ctr[kCtrPatchDel], (unsigned long long)(cnt - n_new));
+}
+
 inline unsigned blocks_for(uint64_t n, unsigned per) { return (unsigned)std::max<uint64_t>(1, (n + per - 1) / per); }
 
 }  // namespace
@@ -639,6 +847,9 @@ void IndexStore::fill_view(View &v) const {
     v.sp_seq = sp_seq_.as<unsigned long long>();
     v.cut = cut_.as<unsigned long long>();
     v.ctr = ctr_.as<unsigned long long>();
+    v.touch_hash = touch_hash_.as<unsigned long long>();
+    v.touch_ep = touch_ep_.as<uint32_t>();
+    v.touch_cap = touch_disabled_ ? 0 : touch_cap_;
 }
 
 cudaError_t IndexStore::ensure_init(cudaStream_t s) {
@@ -806,6 +1017,7 @@ cudaError_t IndexStore::apply(const StoreCalls &calls, cudaStream_t s) {
     pt_used_ = ctr_host_[kCtrPtUsed];
     if ((pt_used_ + total) * 2 > pt_cap_) ST_TRY(grow_pair_table(total, s));
     if (ctr_host_[kCtrNeedRepack]) ST_TRY(repack_logs(s));
+    ST_TRY(reserve_touch(2 * total, s));
     fill_view(v);
     tm.mark("grow");
     if (total) {
@@ -840,6 +1052,99 @@ cudaError_t IndexStore::apply(const StoreCalls &calls, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// Room in the touch log for `more` entries (adds that enter the map + evictions that leave it).  Beyond kTouchMax the
+// log is abandoned for this cycle and the next commit falls back to the bulk build.
+cudaError_t IndexStore::reserve_touch(uint64_t more, cudaStream_t s) {
+    constexpr uint64_t kTouchMax = 1ull << 27;            // 134 M entries = 1.6 GB
+    if (touch_disabled_) return cudaSuccess;
+    touch_upper_ += more;
+    if (touch_upper_ > kTouchMax) {
+        touch_disabled_ = true;
+        return cudaSuccess;
+    }
+    if (touch_upper_ <= touch_cap_) return cudaSuccess;
+    uint64_t want = std::max<uint64_t>(1 << 16, touch_cap_ * 2);
+    while (want < touch_upper_) want *= 2;
+    DevBuf nh, ne;
+    size_t acc = 0;
+    ST_TRY(nh.reserve(sizeof(unsigned long long) * want, &acc));
+    ST_TRY(ne.reserve(sizeof(uint32_t) * want, &acc));
+    if (touch_cap_) {
+        ST_TRY(cudaMemcpyAsync(nh.p, touch_hash_.p, sizeof(unsigned long long) * touch_cap_, cudaMemcpyDeviceToDevice, s));
+        ST_TRY(cudaMemcpyAsync(ne.p, touch_ep_.p, sizeof(uint32_t) * touch_cap_, cudaMemcpyDeviceToDevice, s));
+        ST_TRY(cudaStreamSynchronize(s));
+    }
+    bytes_ -= touch_hash_.cap + touch_ep_.cap;
+    std::swap(touch_hash_.p, nh.p);
+    std::swap(touch_hash_.cap, nh.cap);
+    std::swap(touch_ep_.p, ne.p);
+    std::swap(touch_ep_.cap, ne.cap);
+    bytes_ += touch_hash_.cap + touch_ep_.cap;
+    touch_cap_ = want;
+    return cudaSuccess;
+}
+
+// The read table now reflects the inverted map (bulk build or patch): start a new touch log.
+cudaError_t IndexStore::touch_reset(cudaStream_t s) {
+    touch_upper_ = 0;
+    touch_disabled_ = false;
+    if (!init_) return cudaSuccess;
+    return cudaMemsetAsync(&ctr_.as<unsigned long long>()[kCtrTouch], 0, sizeof(unsigned long long) * 2, s);   // kCtrTouch, kCtrTouchLost
+}
+
+// Brings a bulk-built read table up to date from the touch log.  *patched = false: nothing was done (log unusable, the
+// table lacks room, the sentinel hash is involved, or the change set is too large to be worth it) -> bulk build.
+cudaError_t IndexStore::patch_read_table(const ReadTableRef &rt, uint64_t table_pairs, cudaStream_t s, bool *patched,
+                                         uint64_t *new_pairs, uint64_t *new_slots_used, uint64_t *new_post_used) {
+    *patched = false;
+    if (!init_ || touch_disabled_) return cudaSuccess;
+    View v;
+    fill_view(v);
+    ST_TRY(cudaMemcpyAsync(ctr_host_, v.ctr, sizeof(unsigned long long) * kCtrN, cudaMemcpyDeviceToHost, s));
+    ST_TRY(cudaStreamSynchronize(s));
+    const uint64_t n_touch = ctr_host_[kCtrTouch];
+    if (ctr_host_[kCtrTouchLost] || n_touch > touch_cap_) return cudaSuccess;
+    if (n_touch == 0) { *patched = true; *new_pairs = table_pairs; *new_slots_used = rt.slots_used; *new_post_used = rt.post_used; return cudaSuccess; }
+    // worth it only when the change set is small next to the table; and the table must keep its load factor
+    if (n_touch > std::max<uint64_t>(1 << 16, table_pairs / 2)) return cudaSuccess;
+    if ((rt.slots_used + n_touch) * 10 > rt.capacity * 6) return cudaSuccess;
+    if (n_touch >= 0xFFFFFFF0ull) return cudaSuccess;
+    ST_TRY(patch_next_.reserve(sizeof(uint32_t) * n_touch, &bytes_));
+    ST_TRY(patch_dirty_.reserve(sizeof(uint32_t) * n_touch, &bytes_));
+    PatchView pv;
+    pv.slots = rt.slots;
+    pv.mask = rt.capacity - 1;
+    pv.postings = rt.postings;
+    pv.post_cap = rt.post_cap;
+    pv.post_cursor = &v.ctr[kCtrPatchPost];
+    pv.head = rt.head;
+    pv.next = patch_next_.as<uint32_t>();
+    pv.dirty = patch_dirty_.as<uint32_t>();
+    pv.intern_keys = rt.intern_keys;
+    pv.intern_vals = rt.intern_vals;
+    ST_TRY(cudaMemsetAsync(&v.ctr[kCtrPatchFlag], 0, sizeof(unsigned long long) * 5, s));     // flag, dirty, claims, add, del
+    ctr_host_[kCtrPatchPost] = rt.post_used;
+    ST_TRY(cudaMemcpyAsync(&v.ctr[kCtrPatchPost], &ctr_host_[kCtrPatchPost], sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+    ST_TRY(cudaStreamSynchronize(s));
+    k_patch_group<<<blocks_for(n_touch, 256), 256, 0, s>>>(v, pv, n_touch);
+    ST_TRY(cudaMemcpyAsync(ctr_host_, v.ctr, sizeof(unsigned long long) * kCtrN, cudaMemcpyDeviceToHost, s));
+    ST_TRY(cudaStreamSynchronize(s));
+    const uint64_t n_dirty = ctr_host_[kCtrPatchDirty];
+    if (ctr_host_[kCtrPatchFlag]) return cudaSuccess;                    // sentinel hash touched: bulk build
+    k_patch_apply<<<blocks_for(n_dirty, 128), 128, 0, s>>>(v, pv, n_dirty);
+    ST_TRY(cudaMemcpyAsync(ctr_host_, v.ctr, sizeof(unsigned long long) * kCtrN, cudaMemcpyDeviceToHost, s));
+    ST_TRY(cudaStreamSynchronize(s));
+    ST_TRY(cudaGetLastError());
+    if (ctr_host_[kCtrPatchFlag]) return cudaSuccess;                    // out of posting space mid-way: bulk build
+    *new_pairs = table_pairs + ctr_host_[kCtrPatchAdd] - ctr_host_[kCtrPatchDel];
+    *new_slots_used = rt.slots_used + ctr_host_[kCtrPatchClaims];
+    *new_post_used = ctr_host_[kCtrPatchPost];
+    last_patch_touches = n_touch;
+    last_patch_dirty = n_dirty;
+    *patched = true;
+    return cudaSuccess;
+}
+
 cudaError_t IndexStore::apply_picks(const epp_decision *decisions, const uint64_t *hashes, const int32_t *nblocks,
                                     int64_t R, int32_t max_blocks, cudaStream_t s) {
     if (R <= 0) return cudaSuccess;
@@ -865,6 +1170,7 @@ cudaError_t IndexStore::apply_picks(const epp_decision *decisions, const uint64_
 
 cudaError_t IndexStore::remove_endpoint(uint32_t ep, cudaStream_t s) {
     if (ep >= E_ || !init_) return cudaSuccess;
+    ST_TRY(reserve_touch(in_map_, s));            // at most every pair of the map leaves it
     View v;
     fill_view(v);
     k_store_remove_endpoint<<<1, 32, 0, s>>>(v, ep);
@@ -877,6 +1183,7 @@ cudaError_t IndexStore::remove_endpoint(uint32_t ep, cudaStream_t s) {
 
 cudaError_t IndexStore::retain_endpoints(const uint8_t *active_dev, cudaStream_t s) {
     if (!init_) return cudaSuccess;
+    ST_TRY(reserve_touch(in_map_, s));
     View v;
     fill_view(v);
     k_store_retain<<<blocks_for((uint64_t)E_ * 32, 256), 256, 0, s>>>(v, active_dev);

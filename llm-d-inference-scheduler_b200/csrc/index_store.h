@@ -43,6 +43,19 @@ struct StoreCalls {
     const uint64_t *hashes = nullptr;
 };
 
+// What patch_read_table needs to know about the read table (index_kernels.cu layout, owned by the engine).
+struct ReadTableRef {
+    IndexSlot *slots = nullptr;
+    uint64_t capacity = 0;        // power of two
+    uint64_t slots_used = 0;      // claimed keys incl. tombstones
+    uint32_t *postings = nullptr;
+    uint64_t post_cap = 0;        // allocated posting entries
+    uint64_t post_used = 0;       // posting entries handed out so far
+    uint32_t *head = nullptr;     // device: [capacity], all 0xFFFFFFFF between patches
+    uint64_t *intern_keys = nullptr;
+    uint32_t *intern_vals = nullptr;
+};
+
 class IndexStore {
   public:
     IndexStore(uint32_t max_endpoints, int32_t default_lru_size) : E_(max_endpoints), default_cap_(default_lru_size) {}
@@ -57,6 +70,11 @@ class IndexStore {
     cudaError_t retain_endpoints(const uint8_t *active_dev, cudaStream_t s);
     cudaError_t clear(cudaStream_t s);
     // Every (hash, endpoint) pair of the inverted map, for the bulk build of the read table.
+    // Incremental read-table maintenance from the log of changed (hash, endpoint) pairs (see index_store.cu).
+    cudaError_t patch_read_table(const ReadTableRef &rt, uint64_t table_pairs, cudaStream_t s, bool *patched,
+                                 uint64_t *new_pairs, uint64_t *new_slots_used, uint64_t *new_post_used);
+    cudaError_t touch_reset(cudaStream_t s);
+    uint64_t last_patch_touches = 0, last_patch_dirty = 0;
     cudaError_t export_pairs(DevBuf &pair_hash, DevBuf &pair_ep, uint64_t *n_pairs, size_t *accounted, cudaStream_t s);
 
     bool dirty() const { return dirty_; }
@@ -74,6 +92,7 @@ class IndexStore {
     cudaError_t ensure_init(cudaStream_t s);
     cudaError_t grow_pair_table(uint64_t incoming, cudaStream_t s);
     cudaError_t repack_logs(cudaStream_t s);
+    cudaError_t reserve_touch(uint64_t more, cudaStream_t s);
     void fill_view(View &v) const;
 
     uint32_t E_;
@@ -84,6 +103,10 @@ class IndexStore {
     DevBuf pt_, log_hash_, log_seq_;
     DevBuf cap_, live_, firstcall_, seg_off_, seg_cap_, head_, tail_, inc_, next_seq_, sp_seq_, sp_in_map_, ctr_;
     DevBuf hist_, off_, new_off_, new_cap_, cut_, blockcnt_, list_e_, list_start_;
+    // touch log + scratch of patch_read_table
+    DevBuf touch_hash_, touch_ep_, patch_next_, patch_dirty_;
+    uint64_t touch_cap_ = 0, touch_upper_ = 0;      // allocated entries; host upper bound of the entries logged so far
+    bool touch_disabled_ = false;                   // too many changes to log: the next commit rebuilds
     DevBuf call_ep_, call_n_, call_nb_, call_src_;
     std::vector<uint64_t> h_live_, h_inc_, h_off_, h_cap_;
     unsigned long long *ctr_host_ = nullptr;   // pinned

@@ -113,10 +113,11 @@ struct Walk {
             s.w3 = ix.special.ids[3]; s.w4 = ix.special.ids[4];
         } else if (ix.slots) {
             uint64_t i = h & ix.mask;
-            while (s.cnt != 0 && s.key != h) {                   // linear probing past colliding keys (rare)
+            while (s.key != h && s.key != kEmptyKey) {           // linear probing past colliding keys (rare)
                 i = (i + 1) & ix.mask;
                 s = ld_slot(ix.slots + i);
             }
+            if (s.key != h) s.cnt = 0;
         } else {
             s.cnt = 0;
         }

@@ -145,8 +145,8 @@ __device__ __forceinline__ bool probe_fast(const IndexSlot *slots, uint32_t mask
     for (;;) {
         uint64_t key;
         load_slot(slots + i, key, h);
-        if (h.cnt == 0) return false;
-        if (key == hash) return true;
+        if (key == hash) return h.cnt != 0;
+        if (key == kEmptyKey) { h.cnt = 0; return false; }
         i = (i + 1) & mask;
     }
 }
