@@ -260,6 +260,10 @@ def index_write_leg(args, w, trace, dev_tokens, dev_dec, local_rank, epp, helper
     for seg_h, seg_e in zip(np.split(hs, cuts), np.split(es, cuts)):
         if len(seg_e):
             eng.index_add(int(seg_e[0]), seg_h)
+    if args.index_fill > 0:                      # production-size index: every endpoint's LRU (nearly) full
+        fhs, _ = helpers.filler_pairs(w.E, args.index_fill)
+        for e in range(w.E):
+            eng.index_add(e, fhs[e * args.index_fill:(e + 1) * args.index_fill])
     eng.index_commit()
     cycles = []
     R = w.R
@@ -271,7 +275,8 @@ def index_write_leg(args, w, trace, dev_tokens, dev_dec, local_rank, epp, helper
         wall = time.perf_counter() - t0
         st = eng.stats()
         cycles.append({"apply_ms": st["last_index_apply_ms"], "build_ms": st["last_index_build_ms"], "wall_ms": wall * 1e3,
-                       "hashes_added": int(st["last_index_items"]), "pairs_after": int(st["index_pairs"])})
+                       "hashes_added": int(st["last_index_items"]), "pairs_after": int(st["index_pairs"]),
+                       "read_table": "patched from the change log" if st["last_index_patched"] else "bulk rebuild"})
     last = cycles[-1]
     out = {"what": "epp_index_add_picked + epp_index_commit after a config-3 batch (65 536 picks x up to 256 block hashes)",
            "cycles": cycles, "adds_per_s": last["hashes_added"] / (last["apply_ms"] * 1e-3),
