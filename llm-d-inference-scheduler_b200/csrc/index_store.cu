@@ -817,6 +817,50 @@ __global__ void k_patch_apply(View v, PatchView pv, unsigned long long n_dirty) 
     if (n_new < cnt) atomicAdd(&v.ctr[kCtrPatchDel], (unsigned long long)(cnt - n_new));
 }
 
+// ---- interning of the lists a patch wrote (same table and rule as the bulk build: the lowest slot index among equal
+// lists is canonical, everyone else points at its copy; equality is verified on the contents, the hash is a hint)
+__device__ __forceinline__ uint64_t patch_intern_slot(const PatchView &pv, uint64_t key, bool claim) {
+    uint64_t i = key & pv.mask;
+    for (;;) {
+        unsigned long long *kp = reinterpret_cast<unsigned long long *>(&pv.intern_keys[i]);
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(kp);
+        if (cur == key) return i;
+        if (cur == kEmptyKey) {
+            if (!claim) return i;
+            unsigned long long old = atomicCAS(kp, (unsigned long long)kEmptyKey, (unsigned long long)key);
+            if (old == kEmptyKey || old == key) return i;
+        }
+        i = (i + 1) & pv.mask;
+    }
+}
+
+__global__ void k_patch_intern_claim(PatchView pv, unsigned long long n_dirty) {
+    const unsigned long long d = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_dirty) return;
+    const uint32_t si = pv.dirty[d];
+    const IndexSlot &sl = pv.slots[si];
+    if (sl.cnt <= (uint32_t)kInlineIds) return;
+    const uint64_t j = patch_intern_slot(pv, patch_list_hash(pv.postings + sl.ids[0], sl.cnt), true);
+    atomicMin(&pv.intern_vals[j], si);
+}
+
+__global__ void k_patch_intern_apply(PatchView pv, unsigned long long n_dirty) {
+    const unsigned long long d = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_dirty) return;
+    const uint32_t si = pv.dirty[d];
+    IndexSlot &sl = pv.slots[si];
+    const uint32_t cnt = sl.cnt, off = sl.ids[0];
+    if (cnt <= (uint32_t)kInlineIds) return;
+    const uint64_t j = patch_intern_slot(pv, patch_list_hash(pv.postings + off, cnt), false);
+    const uint32_t c = pv.intern_vals[j];
+    if (c == si || c == kNil) return;                         // canonical slots are never rewritten
+    if (pv.slots[c].cnt != cnt) return;
+    const uint32_t canon = pv.slots[c].ids[0];
+    for (uint32_t k = 0; k < cnt; k++)
+        if (pv.postings[canon + k] != pv.postings[off + k]) return;
+    sl.ids[0] = canon;
+}
+
 inline unsigned blocks_for(uint64_t n, unsigned per) { return (unsigned)std::max<uint64_t>(1, (n + per - 1) / per); }
 
 }  // namespace
@@ -1136,6 +1180,9 @@ cudaError_t IndexStore::patch_read_table(const ReadTableRef &rt, uint64_t table_
     ST_TRY(cudaStreamSynchronize(s));
     ST_TRY(cudaGetLastError());
     if (ctr_host_[kCtrPatchFlag]) return cudaSuccess;                    // out of posting space mid-way: bulk build
+    k_patch_intern_claim<<<blocks_for(n_dirty, 128), 128, 0, s>>>(pv, n_dirty);
+    k_patch_intern_apply<<<blocks_for(n_dirty, 128), 128, 0, s>>>(pv, n_dirty);
+    ST_TRY(cudaGetLastError());
     *new_pairs = table_pairs + ctr_host_[kCtrPatchAdd] - ctr_host_[kCtrPatchDel];
     *new_slots_used = rt.slots_used + ctr_host_[kCtrPatchClaims];
     *new_post_used = ctr_host_[kCtrPatchPost];
