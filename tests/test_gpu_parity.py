@@ -286,6 +286,7 @@ def test_index_add_picked_many_batches_vs_oracle(epp, orc, tg):
         eng.register_model(tg.MODEL)
         eng.pool_set(np.arange(w.E, dtype=np.uint32), role, kv, waiting, running)
         seen_prefill = 0
+        patched = 0
         for b in range(5):
             tokens, _, _ = trace.requests(b * w.R, w.R)
             odec, ototal = helpers.oracle_decisions(orc, w, pool, ix, primary, prefill, tokens)
@@ -297,6 +298,7 @@ def test_index_add_picked_many_batches_vs_oracle(epp, orc, tg):
             else:
                 dec, det = eng.schedule(tokens, uniform_len=w.prompt_bytes, keep_hashes=True)
             helpers.assert_decisions_equal(dec, det, odec, ototal, where=f"batch {b}")
+            patched += int(eng.stats()["last_index_patched"])          # how the read table caught up with the previous picks
             eng.index_add_picked()
             for r in range(w.R):                                       # plugin.go:164-200, one request at a time
                 if odec["status"][r] != 0:
@@ -307,7 +309,7 @@ def test_index_add_picked_many_batches_vs_oracle(epp, orc, tg):
                     ix.add(hs, int(odec["prefill_pick"][r]))
                     seen_prefill += 1
             assert (dec["match_blocks"] > 0).any() or b == 0
-        assert seen_prefill > 0
+        assert seen_prefill > 0 and patched >= 0       # (tiny tables rebuild: the change set exceeds their free slots)
         eng.index_commit()
         assert eng.stats()["index_pairs"] == len(ix.export()[0])
 
