@@ -528,12 +528,19 @@ def run_gpu_sharded(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    use_p2p = not args.sharded_nccl
+    if use_p2p:
+        sh.connect_p2p(eng, R, d)             # CUDA IPC handles of the exchange buffers: the only collective, once
+        out_dec = torch.empty((R, 32), dtype=torch.uint8, device="cuda")
+        step = lambda: sh.schedule_sharded_p2p(eng, dev_tokens, w.prompt_bytes, out=out_dec)
+    else:
+        step = lambda: sh.schedule_sharded(eng, dev_tokens, w.prompt_bytes, d)
     for _ in range(args.warmup):
-        dec = sh.schedule_sharded(eng, dev_tokens, w.prompt_bytes, d)
+        dec = step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        dec = sh.schedule_sharded(eng, dev_tokens, w.prompt_bytes, d)
+        dec = step()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     barrier()
@@ -563,8 +570,11 @@ def run_gpu_sharded(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "u64 (XXH64) + f64 (scores)", "data": "synthetic",
             "config": _config_json(w, world, {
                 "parallelism": f"endpoint index sharded over {world} GPUs ({4096} endpoints each), every rank hashes the "
-                               f"batch; per batch: all-gather+OR of {R * W * 4} B of presence masks per rank, all-gather of "
-                               f"{R * 24} B of best records per rank (NCCL)"}),
+                               f"batch; per batch two exchanges: OR of {R * W * 4} B of presence masks per rank, merge of "
+                               f"{R * 24} B of best records per rank -- "
+                               + ("read straight from the peers' memory over NVLink by the engine's own kernels "
+                                  "(CUDA IPC, release/acquire flags; no NCCL on the data path)" if use_p2p else
+                                  "NCCL all-gathers + torch OR (--sharded-nccl)")}),
             "decisions_ok": int((epp.decisions_from_torch(dec)["status"] == 0).sum()),
             "parity_vs_unsharded_engine": parity,
         }), flush=True)
@@ -582,6 +592,8 @@ def main():
     ap.add_argument("--workload", default="config3", choices=["config1", "config2", "config3", "config4", "config5"])
     ap.add_argument("--requests", type=int, default=0, help="override the batch size R (0 = the config's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sharded-nccl", action="store_true",
+                    help="config5: exchange masks / records with NCCL all-gathers instead of the peer-memory kernels")
     ap.add_argument("--no-index-write", action="store_true", help="skip the index write-side leg (SURVEY 8(f).1)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs only)")
     ap.add_argument("--index-fill", type=int, default=0,

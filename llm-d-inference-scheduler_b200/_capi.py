@@ -111,6 +111,9 @@ SIGNATURES = {
     "epp_shard_probe": (C.c_int32, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
     "epp_shard_pick": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "epp_shard_merge": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "epp_shard_p2p_export": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "epp_shard_p2p_connect": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
+    "epp_shard_schedule_p2p": (C.c_int32, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
 }
 
 _lib = None

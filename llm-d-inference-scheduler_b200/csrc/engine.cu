@@ -137,6 +137,15 @@ struct epp_engine {
     size_t pick_smem = 0;
     int64_t kept_R = 0;             // rows of `hashes` valid for epp_index_add_picked
     int64_t shard_R = 0;            // rows of `hashes` valid for epp_shard_pick / epp_shard_merge
+    // endpoint-sharded mode over NVLink peer memory (shard_p2p.cu)
+    void *p2p_buf = nullptr;        // this rank's exchange buffer {flags, masks, records} (cudaMalloc, IPC-exported)
+    size_t p2p_bytes = 0, p2p_masks_off = 0, p2p_best_off = 0;
+    int64_t p2p_R = 0;              // requests the buffer was sized for
+    int p2p_ranks = 0, p2p_rank = 0;
+    bool p2p_ipc = false;
+    std::vector<void *> p2p_peer;   // peers' buffers in this process's address space (own buffer at [p2p_rank])
+    DevBuf p2p_peer_dev, p2p_gmasks, p2p_allbest, p2p_err;
+    unsigned long long p2p_epoch = 0;
 
     epp_stats stats{};
 };
@@ -314,6 +323,9 @@ extern "C" int32_t epp_engine_destroy(epp_engine *h) {
     for (auto &ev : h->user_ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->hash_done) if (ev) cudaEventDestroy(ev);
     if (h->wc_host) cudaFreeHost(h->wc_host);
+    for (int g = 0; g < (int)h->p2p_peer.size(); g++)
+        if (h->p2p_ipc && g != h->p2p_rank && h->p2p_peer[g]) cudaIpcCloseMemHandle(h->p2p_peer[g]);
+    if (h->p2p_buf) cudaFree(h->p2p_buf);
     delete h;
     return EPP_OK;
 }
@@ -1436,5 +1448,128 @@ extern "C" int32_t epp_shard_merge(epp_engine *h, int64_t n_requests, int32_t n_
     cudaStream_t s = h->slot[0].stream;
     CUDA_TRY(launch_shard_merge(n_requests, n_ranks, all_best, h->nblocks.as<int32_t>(), out, s, &launches));
     CUDA_TRY(cudaStreamSynchronize(s));
+    return EPP_OK;
+}
+
+// ---- endpoint-sharded mode with the exchanges over NVLink peer memory (shard_p2p.cu) ------------------------------
+static constexpr size_t kP2pFlag1 = 0, kP2pFlag2 = 128, kP2pHeader = 256;
+
+extern "C" int32_t epp_shard_p2p_export(epp_engine *h, int64_t max_requests, uint8_t *out_handle, uint64_t *out_ptr) {
+    if (!h || max_requests <= 0 || !out_handle || !out_ptr) return fail(EPP_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
+    if (h->p2p_buf) return fail(EPP_ERR_STATE, "the exchange buffer is already exported");
+    const size_t W = (size_t)mask_words_of(h);
+    h->p2p_masks_off = kP2pHeader;
+    h->p2p_best_off = (kP2pHeader + (size_t)max_requests * W * sizeof(uint32_t) + 255) & ~(size_t)255;
+    h->p2p_bytes = (h->p2p_best_off + (size_t)max_requests * sizeof(epp_shard_best) + 255) & ~(size_t)255;
+    CUDA_TRY(cudaMalloc(&h->p2p_buf, h->p2p_bytes));
+    CUDA_TRY(cudaMemset(h->p2p_buf, 0, h->p2p_bytes));
+    h->dev_bytes += h->p2p_bytes;
+    h->p2p_R = max_requests;
+    cudaIpcMemHandle_t hd;
+    CUDA_TRY(cudaIpcGetMemHandle(&hd, h->p2p_buf));
+    static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(out_handle, &hd, sizeof hd);
+    *out_ptr = (uint64_t)(uintptr_t)h->p2p_buf;
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_shard_p2p_connect(epp_engine *h, int32_t n_ranks, int32_t rank, const void *peers, int32_t ipc_handles) {
+    if (!h || n_ranks <= 0 || n_ranks > 64 || rank < 0 || rank >= n_ranks || !peers) return fail(EPP_ERR_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
+    if (!h->p2p_buf) return fail(EPP_ERR_STATE, "epp_shard_p2p_export has not been called");
+    if (!h->p2p_peer.empty()) return fail(EPP_ERR_STATE, "peers are already connected");
+    h->p2p_peer.assign((size_t)n_ranks, nullptr);
+    h->p2p_ipc = ipc_handles != 0;
+    for (int g = 0; g < n_ranks; g++) {
+        if (g == rank) { h->p2p_peer[g] = h->p2p_buf; continue; }
+        if (ipc_handles) {
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, static_cast<const uint8_t *>(peers) + (size_t)g * 64, sizeof hd);
+            CUDA_TRY(cudaIpcOpenMemHandle(&h->p2p_peer[g], hd, cudaIpcMemLazyEnablePeerAccess));
+        } else {
+            h->p2p_peer[g] = (void *)(uintptr_t)static_cast<const uint64_t *>(peers)[g];    // same process: plain pointers
+        }
+    }
+    h->p2p_ranks = n_ranks;
+    h->p2p_rank = rank;
+    CUDA_TRY(h->p2p_peer_dev.reserve(sizeof(void *) * (size_t)n_ranks, &h->dev_bytes));
+    CUDA_TRY(cudaMemcpy(h->p2p_peer_dev.p, h->p2p_peer.data(), sizeof(void *) * (size_t)n_ranks, cudaMemcpyHostToDevice));
+    CUDA_TRY(h->p2p_err.reserve(sizeof(int), &h->dev_bytes));
+    CUDA_TRY(cudaMemset(h->p2p_err.p, 0, sizeof(int)));
+    // everything the batches need is allocated now: no cudaMalloc / cudaFree (device-wide synchronisation) may happen
+    // while a peer-wait kernel is spinning
+    const size_t W = (size_t)mask_words_of(h);
+    CUDA_TRY(h->p2p_gmasks.reserve(((size_t)h->p2p_R * W * sizeof(uint32_t) + 15) & ~(size_t)15, &h->dev_bytes));
+    CUDA_TRY(h->p2p_allbest.reserve(sizeof(epp_shard_best) * (size_t)h->p2p_R * (size_t)n_ranks, &h->dev_bytes));
+    EPP_TRY(reserve_batch(h, h->p2p_R));
+    return EPP_OK;
+}
+
+// One batch of the sharded protocol with both exchanges done by this rank's own kernels over peer memory.  Every rank
+// calls it with the same batch; the decisions (identical on every rank) land in `out` (device pointer).
+extern "C" int32_t epp_shard_schedule_p2p(epp_engine *h, const epp_batch *batch, epp_decision *out) {
+    if (!h || !out) return fail(EPP_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
+    if (h->p2p_peer.empty()) return fail(EPP_ERR_STATE, "epp_shard_p2p_connect has not been called");
+    if (!h->pool_ready) return fail(EPP_ERR_STATE, "epp_pool_set has not been called (after epp_shard_set)");
+    BatchView v;
+    EPP_TRY(check_batch(h, batch, v));
+    if (!v.device) return fail(EPP_ERR_INVALID, "epp_shard_schedule_p2p takes device-pointer batches (EPP_BATCH_DEVICE_PTRS)");
+    if (v.R > h->p2p_R) return fail(EPP_ERR_CAPACITY, "batch of %lld requests exceeds the exported exchange buffer (%lld)", (long long)v.R, (long long)h->p2p_R);
+    if (v.R == 0) return EPP_OK;
+    v.async = false;
+    h->kept_R = 0;
+    h->shard_R = 0;
+    EPP_TRY(commit_locked(h));
+    EPP_TRY(run_batch(h, v, Mode::HashOnly, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+    const int64_t R = v.R;
+    const int n = h->p2p_ranks;
+    const size_t W = (size_t)mask_words_of(h);
+    const unsigned long long epoch = ++h->p2p_epoch;
+    const unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
+    cudaStream_t s = h->slot[0].stream;
+    uint8_t *own = static_cast<uint8_t *>(h->p2p_buf);
+    unsigned char *const *peers = h->p2p_peer_dev.as<unsigned char *>();
+    int launches = 0;
+    const size_t mask_bytes = ((size_t)R * W * sizeof(uint32_t) + 15) & ~(size_t)15;
+    CUDA_TRY(h->p2p_gmasks.reserve(mask_bytes, &h->dev_bytes));
+    CUDA_TRY(h->p2p_allbest.reserve(sizeof(epp_shard_best) * (size_t)R * (size_t)n, &h->dev_bytes));
+    // phase 1: local presence masks -> own exchange buffer, raise flag 1
+    CUDA_TRY(launch_shard_probe(R, h->cfg.max_prefix_blocks, h->hashes.as<uint64_t>(), h->nblocks.as<int32_t>(), index_view(h),
+                                reinterpret_cast<uint32_t *>(own + h->p2p_masks_off), (int32_t)W, s, &launches));
+    CUDA_TRY(launch_p2p_signal(reinterpret_cast<unsigned long long *>(own + kP2pFlag1), epoch, s));
+    // exchange 1: OR of every rank's masks, read straight from the peers
+    CUDA_TRY(launch_p2p_wait(peers, n, kP2pFlag1, epoch, h->p2p_err.as<int>(), timeout_ns, s));
+    CUDA_TRY(launch_p2p_or_masks(peers, n, h->p2p_masks_off, mask_bytes, h->p2p_gmasks.p, s));
+    // phase 2: global stop rule on the local counts -> local best record in the own exchange buffer, raise flag 2
+    Work w{0, R, nullptr, nullptr, nullptr, 0, nullptr, 0, h->hashes.as<uint64_t>(), h->nblocks.as<int32_t>()};
+    PickParams pp = pick_params(h, w, h->decisions.as<epp_decision>(), nullptr, nullptr);
+    pp.model_ids = v.model_ids;
+    pp.global_masks = h->p2p_gmasks.as<uint32_t>();
+    pp.mask_words = (int32_t)W;
+    pp.shard_out = reinterpret_cast<epp_shard_best *>(own + h->p2p_best_off);
+    EPP_TRY(launch_match(h, h->slot[0], pp, &launches));
+    CUDA_TRY(launch_p2p_signal(reinterpret_cast<unsigned long long *>(own + kP2pFlag2), epoch, s));
+    // exchange 2 + phase 3: gather every rank's records from the peers and merge
+    CUDA_TRY(launch_p2p_wait(peers, n, kP2pFlag2, epoch, h->p2p_err.as<int>(), timeout_ns, s));
+    CUDA_TRY(launch_p2p_gather(peers, n, h->p2p_best_off, sizeof(epp_shard_best) * (size_t)R, h->p2p_allbest.p, s));
+    CUDA_TRY(launch_shard_merge(R, n, h->p2p_allbest.as<epp_shard_best>(), h->nblocks.as<int32_t>(), out, s, &launches));
+    int err = 0;
+    CUDA_TRY(cudaMemcpyAsync(&err, h->p2p_err.p, sizeof err, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    h->stats.last_kernel_launches = (uint64_t)launches + 6;
+    if (err) {
+        CUDA_TRY(cudaMemset(h->p2p_err.p, 0, sizeof(int)));
+        return fail(EPP_ERR_NCCL, "peer rank %d did not reach batch %llu of the sharded exchange within 20 s", err - 1, epoch);
+    }
+    h->stats.n_batches++;
+    h->stats.n_decisions += (uint64_t)R;
     return EPP_OK;
 }

@@ -205,4 +205,13 @@ cudaError_t launch_shard_probe(int64_t R, int32_t max_blocks, const uint64_t *ha
 cudaError_t launch_shard_merge(int64_t R, int32_t n_ranks, const epp_shard_best *all_best, const int32_t *nblocks,
                                epp_decision *out, cudaStream_t s, int *launches);
 
+// shard_p2p.cu: exchanges of the endpoint-sharded mode over NVLink peer memory (no NCCL)
+cudaError_t launch_p2p_signal(unsigned long long *flag, unsigned long long epoch, cudaStream_t s);
+cudaError_t launch_p2p_wait(unsigned char *const *peers_dev, int n, size_t flag_off, unsigned long long epoch, int *err_dev,
+                            unsigned long long timeout_ns, cudaStream_t s);
+cudaError_t launch_p2p_or_masks(unsigned char *const *peers_dev, int n, size_t masks_off, unsigned long long n_bytes,
+                                void *out, cudaStream_t s);
+cudaError_t launch_p2p_gather(unsigned char *const *peers_dev, int n, size_t best_off, unsigned long long n_bytes,
+                              void *out, cudaStream_t s);
+
 }  // namespace epp

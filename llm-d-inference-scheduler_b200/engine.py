@@ -322,6 +322,24 @@ class Engine:
     def shard_pick(self, n_requests, global_masks, out_best):
         self._check(self._lib.epp_shard_pick(self._h, n_requests, _ptr(global_masks), _ptr(out_best)))
 
+    def shard_p2p_export(self, max_requests: int):
+        """-> (64-byte CUDA IPC handle, raw device pointer) of this rank's exchange buffer."""
+        handle = np.zeros(64, dtype=np.uint8)
+        ptr = C.c_uint64(0)
+        self._check(self._lib.epp_shard_p2p_export(self._h, max_requests, _ptr(handle), C.byref(ptr)))
+        return handle, ptr.value
+
+    def shard_p2p_connect(self, n_ranks: int, rank: int, peers, ipc_handles: bool = True):
+        """peers: [n_ranks, 64] uint8 handles (other processes) or [n_ranks] uint64 pointers (same process)."""
+        a = np.ascontiguousarray(peers, dtype=np.uint8 if ipc_handles else np.uint64)
+        self._check(self._lib.epp_shard_p2p_connect(self._h, n_ranks, rank, _ptr(a), int(ipc_handles)))
+
+    def shard_schedule_p2p(self, data, out_decisions, offsets=None, uniform_len=None, model_ids=None, n_requests=None,
+                           lengths=None):
+        b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests, lengths)
+        self._check(self._lib.epp_shard_schedule_p2p(self._h, C.byref(b), _ptr(out_decisions)))
+        return R
+
     def shard_merge(self, n_requests, n_ranks, all_best, out_decisions):
         self._check(self._lib.epp_shard_merge(self._h, n_requests, n_ranks, _ptr(all_best), _ptr(out_decisions)))
 

@@ -94,3 +94,29 @@ def schedule_sharded(engine, tokens_dev, uniform_len: int, dist=None):
     torch.cuda.current_stream(dev).synchronize()
     engine.shard_merge(R, allb.shape[0], allb, dec)
     return dec
+
+
+# ---- the same protocol with the exchanges over NVLink peer memory (csrc/shard_p2p.cu): no NCCL on the data path ----
+def connect_p2p(engine, max_requests: int, dist=None):
+    """Export this rank's exchange buffer, all-gather the 64-byte CUDA IPC handles (the only collective, once) and open
+    every peer's buffer."""
+    import torch
+    handle, _ = engine.shard_p2p_export(max_requests)
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        engine.shard_p2p_connect(1, 0, handle.reshape(1, 64), ipc_handles=True)
+        return
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    mine = torch.from_numpy(handle).to(dev)
+    allh = torch.empty((world, 64), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allh.view(-1), mine)
+    engine.shard_p2p_connect(world, rank, allh.cpu().numpy(), ipc_handles=True)
+
+
+def schedule_sharded_p2p(engine, tokens_dev, uniform_len: int, out=None):
+    """One batch; every rank calls it with the same tokens.  Returns a [R, 32] uint8 CUDA tensor of epp_decision."""
+    import torch
+    R = tokens_dev.shape[0]
+    dec = out if out is not None else torch.empty((R, 32), dtype=torch.uint8, device=tokens_dev.device)
+    engine.shard_schedule_p2p(tokens_dev, dec, uniform_len=uniform_len)
+    return dec

@@ -224,6 +224,153 @@ def test_sharded_two_shards_one_gpu(orc):
         assert any((masks[0] != m).any() for m in masks[1:])
 
 
+def _p2p_engines_one_gpu(epp, w, trace, world, R_max):
+    """`world` shard engines on ONE GPU wired to each other's exchange buffers by raw pointers (same process)."""
+    import helpers
+    sh = _sharded()
+    role, kv, waiting, running = trace.pool()
+    fam = trace.family_tokens()
+    engines, ptrs = [], []
+    for g in range(world):
+        eng = helpers.make_engine(w)
+        eng.register_model(b"synthetic-model")
+        lo, hi = sh.shard_range(g, world, w.E)
+        eng.shard_set(lo, hi)
+        eng.pool_set(np.arange(w.E, dtype=np.uint32), role, kv, waiting, running)
+        fh, _ = eng.hash_prompts(fam, uniform_len=w.prompt_bytes)
+        hs, es = trace.index_pairs(fh)
+        keep = (es >= lo) & (es < hi)
+        eng.index_load_snapshot(hs[keep], es[keep])
+        _, ptr = eng.shard_p2p_export(R_max)
+        engines.append(eng)
+        ptrs.append(ptr)
+    for g, eng in enumerate(engines):
+        eng.shard_p2p_connect(world, g, np.array(ptrs, dtype=np.uint64), ipc_handles=False)
+    return engines
+
+
+@pytest.mark.gpu
+def test_sharded_p2p_exchange_one_gpu(orc):
+    """The peer-memory exchange (flags, OR of the masks, gather + merge of the records) with two shard engines on one
+    GPU, each driven by its own host thread like a rank: three consecutive batches (buffer reuse across epochs), every
+    rank's decisions identical and equal to the oracle's."""
+    import threading
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import epp_b200 as epp
+    import helpers
+    from tools import tracegen as tg
+    w = _workload(E=512, R=384, T=1024)
+    trace = tg.Trace(w)
+    pool, ix, primary, prefill, _ = helpers.setup_oracle(orc, w, trace)
+    world = 2
+    engines = _p2p_engines_one_gpu(epp, w, trace, world, R_max=512)
+    try:
+        for b in range(3):
+            tokens, _, _ = trace.requests(b * w.R, w.R)
+            odec, ototal = helpers.oracle_decisions(orc, w, pool, ix, primary, None, tokens)
+            dt = torch.from_numpy(tokens.view(np.int32)).cuda()
+            outs = [torch.zeros((w.R, 32), dtype=torch.uint8, device="cuda") for _ in range(world)]
+            errs = []
+
+            def run(g):
+                try:
+                    engines[g].shard_schedule_p2p(dt, outs[g], uniform_len=w.prompt_bytes)
+                except Exception as e:          # noqa: BLE001
+                    errs.append((g, e))
+            torch.cuda.synchronize()
+            ths = [threading.Thread(target=run, args=(g,)) for g in range(world)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join(timeout=120)
+            if errs and all("did not reach batch" in str(e) for _, e in errs):
+                # ranks that share ONE GPU can be serialised behind each other's wait kernel when their streams map to
+                # the same hardware queue (the engine then reports the missing peer after its time-out instead of
+                # hanging); with one GPU per rank -- test_sharded_two_gpus_p2p -- that cannot happen
+                pytest.skip("co-resident engines were serialised by the GPU's hardware queues: " + str(errs[0][1]))
+            assert not errs, errs
+            decs = [epp.decisions_from_torch(o) for o in outs]
+            for d in decs[1:]:
+                np.testing.assert_array_equal(d, decs[0])
+            helpers.assert_decisions_equal(decs[0], None, odec, ototal, where=f"p2p sharded x{world}, batch {b}")
+    finally:
+        for e in engines:
+            e.close()
+
+
+def _p2p_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import epp_b200 as epp
+        import helpers
+        from tools import tracegen as tg
+        sh = _sharded()
+        w = _workload(E=512, R=384, T=1024)
+        trace = tg.Trace(w, n_threads=2)
+        role, kv, waiting, running = trace.pool()
+        eng = helpers.make_engine(w, device=rank)
+        eng.register_model(b"synthetic-model")
+        lo, hi = sh.shard_range(rank, world, w.E)
+        eng.shard_set(lo, hi)
+        eng.pool_set(np.arange(w.E, dtype=np.uint32), role, kv, waiting, running)
+        fh, _ = eng.hash_prompts(trace.family_tokens(), uniform_len=w.prompt_bytes)
+        hs, es = trace.index_pairs(fh)
+        keep = (es >= lo) & (es < hi)
+        eng.index_load_snapshot(hs[keep], es[keep])
+        sh.connect_p2p(eng, 512, dist)                     # CUDA IPC handles, the only collective
+        res = []
+        for b in range(2):
+            tokens, _, _ = trace.requests(b * w.R, w.R)
+            dt = torch.from_numpy(tokens.view(np.int32)).cuda(rank)
+            dec = sh.schedule_sharded_p2p(eng, dt, w.prompt_bytes)
+            torch.cuda.synchronize()
+            res.append(epp.decisions_from_torch(dec).tobytes())
+        q.put((rank, res))
+        dist.barrier()
+        eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_two_gpus_p2p(orc):
+    """Two ranks on two GPUs: exchange buffers opened through CUDA IPC, masks and records read over NVLink."""
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    import epp_b200 as epp
+    import helpers
+    from tools import tracegen as tg
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_p2p_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    w = _workload(E=512, R=384, T=1024)
+    trace = tg.Trace(w)
+    pool, ix, primary, prefill, _ = helpers.setup_oracle(orc, w, trace)
+    for b in range(2):
+        tokens, _, _ = trace.requests(b * w.R, w.R)
+        odec, ototal = helpers.oracle_decisions(orc, w, pool, ix, primary, None, tokens)
+        d0 = np.frombuffer(res[0][b], dtype=epp.DECISION_DTYPE)
+        d1 = np.frombuffer(res[1][b], dtype=epp.DECISION_DTYPE)
+        np.testing.assert_array_equal(d0, d1)
+        helpers.assert_decisions_equal(d0, None, odec, ototal, where=f"sharded p2p x2, batch {b}")
+
+
 def _nccl_worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
