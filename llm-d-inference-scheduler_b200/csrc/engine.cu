@@ -1533,7 +1533,8 @@ extern "C" int32_t epp_shard_schedule_p2p(epp_engine *h, const epp_batch *batch,
     const int n = h->p2p_ranks;
     const size_t W = (size_t)mask_words_of(h);
     const unsigned long long epoch = ++h->p2p_epoch;
-    const unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
+    unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
+    if (const char *tv = getenv("EPP_P2P_TIMEOUT_MS")) timeout_ns = (unsigned long long)std::max(1, atoi(tv)) * 1000ull * 1000ull;
     cudaStream_t s = h->slot[0].stream;
     uint8_t *own = static_cast<uint8_t *>(h->p2p_buf);
     unsigned char *const *peers = h->p2p_peer_dev.as<unsigned char *>();
@@ -1567,7 +1568,7 @@ extern "C" int32_t epp_shard_schedule_p2p(epp_engine *h, const epp_batch *batch,
     h->stats.last_kernel_launches = (uint64_t)launches + 6;
     if (err) {
         CUDA_TRY(cudaMemset(h->p2p_err.p, 0, sizeof(int)));
-        return fail(EPP_ERR_NCCL, "peer rank %d did not reach batch %llu of the sharded exchange within 20 s", err - 1, epoch);
+        return fail(EPP_ERR_NCCL, "peer rank %d did not reach batch %llu of the sharded exchange within %llu ms", err - 1, epoch, timeout_ns / 1000000ull);
     }
     h->stats.n_batches++;
     h->stats.n_decisions += (uint64_t)R;
