@@ -629,33 +629,50 @@ __global__ void k_store_rehash(const StoreEntry *old_pt, uint64_t old_capacity, 
     if (claimed) atomicAdd(&v.ctr[kCtrPtUsed], (unsigned long long)claimed);
 }
 
+// Scan of the pair table: kExportPer slots per thread, all loads issued before any is used (the scan is pure
+// streaming; with one 32-byte load per thread it ran at 1.1 TB/s).
+constexpr int kExportPer = 4;
 __global__ void k_store_export(View v, uint64_t capacity, unsigned long long *out_hash, uint32_t *out_ep) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
-    bool take = false;
-    unsigned long long hsh = 0;
-    uint32_t ep = 0;
-    if (i < capacity) {
-        StoreEntry s = v.pt[i];
-        take = s.hash != kEmptyKey && s.in_map != 0;
-        hsh = s.hash;
-        ep = s.ep;
-    } else if (i - capacity < v.E) {                                         // tail threads: the sentinel-hash records
-        ep = (uint32_t)(i - capacity);
-        take = v.sp_in_map[ep] != 0;
-        hsh = kEmptyKey;
+    const uint64_t base = (uint64_t)blockIdx.x * (blockDim.x * kExportPer) + threadIdx.x;
+    ulonglong2 lo[kExportPer];
+    uint2 mid[kExportPer];
+#pragma unroll
+    for (int k = 0; k < kExportPer; k++) {
+        const uint64_t i = base + (uint64_t)k * blockDim.x;
+        lo[k] = make_ulonglong2(kEmptyKey, 0);
+        mid[k] = make_uint2(0, 0);
+        if (i < capacity) {
+            const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(v.pt + i);      // {hash, seq}
+            lo[k] = __ldcs(p);
+            mid[k] = __ldcs(reinterpret_cast<const uint2 *>(p + 1));                    // {ep, in_map}
+        }
     }
-    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, take);
-    unsigned long long base = 0;
-    if (lane == 0 && ballot) base = atomicAdd(&v.ctr[kCtrCursor], (unsigned long long)__popc(ballot));
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (take) {
-        const unsigned long long at = base + __popc(ballot & ((1u << lane) - 1u));
-        out_hash[at] = hsh;
-        out_ep[at] = ep;
+#pragma unroll
+    for (int k = 0; k < kExportPer; k++) {
+        const uint64_t i = base + (uint64_t)k * blockDim.x;
+        bool take = false;
+        unsigned long long hsh = lo[k].x;
+        uint32_t ep = mid[k].x;
+        if (i < capacity) {
+            take = hsh != kEmptyKey && mid[k].y != 0;
+        } else if (i - capacity < v.E) {                                     // tail threads: the sentinel-hash records
+            ep = (uint32_t)(i - capacity);
+            take = v.sp_in_map[ep] != 0;
+            hsh = kEmptyKey;
+        }
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, take);
+        if (!ballot) continue;
+        unsigned long long at0 = 0;
+        if (lane == 0) at0 = atomicAdd(&v.ctr[kCtrCursor], (unsigned long long)__popc(ballot));
+        at0 = __shfl_sync(0xFFFFFFFFu, at0, 0);
+        if (take) {
+            const unsigned long long at = at0 + __popc(ballot & ((1u << lane) - 1u));
+            out_hash[at] = hsh;
+            out_ep[at] = ep;
+        }
     }
 }
-
 
 // ---- incremental maintenance of the READ table (index_kernels.cu layout) from the touch log ---------------------------
 // The log names every (hash, endpoint) whose membership changed; the pair table holds the FINAL membership, so applying
@@ -1250,7 +1267,7 @@ cudaError_t IndexStore::export_pairs(DevBuf &pair_hash, DevBuf &pair_ep, uint64_
     ST_TRY(pair_hash.reserve(sizeof(uint64_t) * std::max<uint64_t>(in_map_, 1), accounted));
     ST_TRY(pair_ep.reserve(sizeof(uint32_t) * std::max<uint64_t>(in_map_, 1), accounted));
     ST_TRY(cudaMemsetAsync(&v.ctr[kCtrCursor], 0, sizeof(unsigned long long), s));
-    k_store_export<<<blocks_for(pt_cap_ + E_, 256), 256, 0, s>>>(v, pt_cap_, pair_hash.as<unsigned long long>(), pair_ep.as<uint32_t>());
+    k_store_export<<<blocks_for(pt_cap_ + E_, 256 * kExportPer), 256, 0, s>>>(v, pt_cap_, pair_hash.as<unsigned long long>(), pair_ep.as<uint32_t>());
     ST_TRY(cudaMemcpyAsync(ctr_host_, v.ctr, sizeof(unsigned long long) * kCtrN, cudaMemcpyDeviceToHost, s));
     ST_TRY(cudaStreamSynchronize(s));
     *n_pairs = ctr_host_[kCtrCursor];
