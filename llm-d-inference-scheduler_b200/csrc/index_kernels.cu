@@ -8,7 +8,12 @@
 //
 // Build (bulk, on the device, from a snapshot of (hash, endpoint) pairs):
 //   k_index_clear -> k_index_insert (atomicCAS claim + count) -> k_index_alloc (posting ranges by atomic cursor)
-//   -> k_index_fill (scatter endpoint ids) -> k_index_finalize (sort + dedupe, move short lists into the slot).
+//   -> k_index_fill (scatter endpoint ids) -> k_index_finalize (sort + dedupe, move short lists into the slot)
+//   -> k_intern_* (equal spilled lists share one copy).
+// Between bulk builds the table is kept up to date in place from the write side's change log (index_store.cu:
+// k_patch_group / k_patch_apply): new keys claim free slots, lists are rewritten copy-on-write, a hash that loses its
+// last endpoint keeps its slot with count 0 -- probe chains therefore end at FREE slots (key == sentinel), not at
+// count == 0.
 #include "index.cuh"
 
 namespace epp {

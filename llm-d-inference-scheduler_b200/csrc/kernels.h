@@ -57,10 +57,11 @@ constexpr int kInlineIds = 5;
 // sorted by endpoint id and duplicate-free.
 struct __align__(32) IndexSlot {
     uint64_t key;
-    uint32_t cnt;                 // 0 == empty slot
+    uint32_t cnt;                 // endpoints holding the block; 0 with a real key = every holder was evicted
+                                  // (tombstone left by the incremental patch); a FREE slot has key == kEmptyKey
     uint32_t ids[kInlineIds];     // cnt <= kInlineIds: the endpoints; else ids[0] = offset into postings
 };
-constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFULL;   // build-time claim sentinel; a real key equal to it
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFULL;   // free-slot sentinel (ends probe chains); a real key equal to it
                                                         // lives in IndexView::special
 struct IndexView {
     const IndexSlot *slots;
