@@ -282,3 +282,50 @@ func (e *Engine) scheduleBatch(stage unsafe.Pointer, offsets, lengths []C.uint64
 }
 
 var errNoEndpoints = errors.New("no endpoints available for the given request") // scheduler_profile.go:119-121
+
+// ---- endpoint-sharded pools (index larger than one GPU): exchanges over NVLink peer memory, include/epp_engine.h ----
+
+// ShardSet restricts this replica's engine to the endpoint slots [begin, end); SetPool must follow.
+func (e *Engine) ShardSet(begin, end uint32) error {
+	if rc := C.epp_shard_set(e.h, C.uint32_t(begin), C.uint32_t(end)); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// ShardP2PExport allocates this rank's exchange buffer and returns its 64-byte CUDA IPC handle; the replicas exchange
+// the handles once over their control channel (any transport: they are plain bytes).
+func (e *Engine) ShardP2PExport(maxRequests int) ([64]byte, error) {
+	var h [64]byte
+	var ptr C.uint64_t
+	if rc := C.epp_shard_p2p_export(e.h, C.int64_t(maxRequests), (*C.uint8_t)(unsafe.Pointer(&h[0])), &ptr); rc != 0 {
+		return h, lastErr(rc)
+	}
+	return h, nil
+}
+
+// ShardP2PConnect opens every peer's exchange buffer (handles[rank] is this rank's own and is ignored).
+func (e *Engine) ShardP2PConnect(rank int, handles [][64]byte) error {
+	flat := make([]byte, 0, 64*len(handles))
+	for _, h := range handles {
+		flat = append(flat, h[:]...)
+	}
+	if rc := C.epp_shard_p2p_connect(e.h, C.int32_t(len(handles)), C.int32_t(rank), unsafe.Pointer(&flat[0]), 1); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
+
+// ShardScheduleP2P runs one batch of the sharded protocol; every replica calls it with the same device-resident batch
+// (devPrompts / devOut are device pointers owned by the caller, e.g. filled by the tokenizer stage on the same GPU).
+func (e *Engine) ShardScheduleP2P(devPrompts unsafe.Pointer, nRequests int, uniformLen uint64, devOut unsafe.Pointer) error {
+	var b C.epp_batch
+	b.n_requests = C.int64_t(nRequests)
+	b.data = devPrompts
+	b.uniform_len = C.uint64_t(uniformLen)
+	b.flags = C.EPP_BATCH_DEVICE_PTRS
+	if rc := C.epp_shard_schedule_p2p(e.h, &b, (*C.epp_decision)(devOut)); rc != 0 {
+		return lastErr(rc)
+	}
+	return nil
+}
