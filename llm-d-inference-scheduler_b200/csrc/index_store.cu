@@ -943,6 +943,8 @@ cudaError_t IndexStore::clear(cudaStream_t s) {
     init_ = false;
     used_ = false;
     dirty_ = true;
+    touch_upper_ = 0;
+    touch_disabled_ = false;
     return ensure_init(s);
 }
 
