@@ -138,3 +138,18 @@ def test_oracle_cycle_batch_matches_stepwise(orc):
             assert (d.status, d.pick, d.tie_count, d.prefill_pick, d.prefill_ran) == tuple(
                 int(d1[k][r]) for k in ("status", "pick", "tie_count", "prefill_pick", "prefill_ran"))
             assert d.score == d1["score"][r] and t1[r] == len(h)
+
+
+def test_every_switch_in_the_code_is_documented():
+    """DESIGN.md section 12 lists every environment variable the library reads (and nothing else)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "llm-d-inference-scheduler_b200", "csrc")
+    in_code = set()
+    for f in os.listdir(csrc):
+        if f.endswith((".cu", ".cuh", ".h")):
+            in_code |= set(re.findall(r'getenv\("([A-Z0-9_]+)"\)', open(os.path.join(csrc, f)).read()))
+    design = open(os.path.join(root, "DESIGN.md")).read()
+    section = design[design.index("## 12. A/B switches"):]
+    documented = set(re.findall(r"`(EPP_[A-Z0-9_]+)`", section))
+    assert in_code == documented, (sorted(in_code - documented), sorted(documented - in_code))
