@@ -193,6 +193,34 @@ def score(kind, param, endpoints, match, total):
         return out
     if kind == "ext":
         return [e["ext"][int(param)] for e in endpoints]
+    if kind == "token_load":                                     # scorer/tokenload/token_load.go:84-112
+        thr = float(param) if param > 0 else 4194304.0           # :27-28, :60-62
+        out = []
+        for e in endpoints:
+            load = float(e.get("tokens", 0))
+            out.append(1.0 if load <= 0 else 1.0 - (min(load, thr) / thr))
+        return out
+    if kind == "active_request":                                 # scorer/activerequest/active_request.go:140-173
+        max_busy, idle = param                                   # NewActiveRequest :83-93
+        idle = int(idle) if idle >= 0 else 0
+        max_busy = max_busy if 0 <= max_busy <= 1.0 else 1.0
+        counts = [int(e.get("requests", 0)) for e in endpoints]
+        mx = max([0] + counts)
+        return [1.0 if c <= idle else float(mx - c) / float(mx) * max_busy for c in counts]
+    if kind == "lora":                                           # scorer/loraaffinity/lora_affinity.go:76-100
+        target = param
+        out = []
+        for e in endpoints:
+            active, waiting_m, cap = e.get("active", set()), e.get("waiting_models", set()), e.get("max_active", 0)
+            if target in active:
+                out.append(1.0)
+            elif len(active) + len(waiting_m) < cap:
+                out.append(0.8)
+            elif target in waiting_m:
+                out.append(0.6)
+            else:
+                out.append(0.0)
+        return out
     raise ValueError(kind)
 
 

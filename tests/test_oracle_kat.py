@@ -391,3 +391,51 @@ def test_profile_run_random_vs_python_restatement(orc):
         assert mx == wmx and aset == wset and pick == wset[0]
         for i in range(n):
             assert scores[i] == (acc[i] if i in acc else -1.0)
+
+
+def test_new_scorers_random_vs_python_restatement(orc):
+    """token-load, active-request and lora-affinity of the C oracle against the independent Python restatement (dicts
+    and sets, straight from the Go switch statements), inside whole profiles with the other scorers."""
+    import random
+    rng = random.Random(23)
+    labels = {orc.ROLE_NONE: None, orc.ROLE_DECODE: "decode", orc.ROLE_PREFILL: "prefill", orc.ROLE_BOTH: "both"}
+    fnames = {orc.FILTER_NONE: "none", orc.FILTER_DECODE: "decode", orc.FILTER_PREFILL: "prefill"}
+    adapters = ["a", "b", "c", "d"]
+    for _ in range(200):
+        n = rng.randint(1, 30)
+        roles = [rng.choice(list(labels)) for _ in range(n)]
+        kv = [rng.randrange(1001) / 1000.0 for _ in range(n)]
+        waiting = [rng.choice([0, 0, rng.randint(1, 200)]) for _ in range(n)]
+        tokens = [rng.choice([0, 0, rng.randint(1, 9000), 5000000]) for _ in range(n)]
+        requests = [rng.choice([0, 0, 1, rng.randint(2, 40)]) for _ in range(n)]
+        active = [set(rng.sample(adapters, rng.randint(0, 3))) for _ in range(n)]
+        waiting_m = [set(rng.sample(adapters, rng.randint(0, 2))) - active[i] for i in range(n)]
+        max_active = [rng.randint(0, 5) for _ in range(n)]
+        target = rng.choice(adapters)
+        total = rng.choice([0, 4, 64])
+        match = [rng.randint(0, total) for _ in range(n)]
+        thr = rng.choice([0.0, 1000.0, 5000.0])
+        max_busy, idle = rng.choice([1.0, 0.5, 0.0, 7.0]), rng.choice([0.0, 1.0, 3.0, -2.0])
+        pool = _pool(orc, role=roles, kv=kv, waiting=waiting, ext=[tokens, requests])
+        state = [1 if target in active[i] else (2 if target in waiting_m[i] else 0) for i in range(n)]
+        pool.set_lora(state, max_active, [len(active[i]) + len(waiting_m[i]) for i in range(n)])
+        c_sc = [(orc.SCORER_TOKEN_LOAD, 1.5, thr, 0), (orc.SCORER_ACTIVE_REQUEST, 0.7, max_busy, 1, idle),
+                (orc.SCORER_LORA_AFFINITY, 2.0, 0.0), (orc.SCORER_PREFIX, 1.0, 0.0), (orc.SCORER_QUEUE, 1.0, 0.0)]
+        p_sc = [("token_load", 1.5, thr), ("active_request", 0.7, (max_busy, idle)), ("lora", 2.0, target),
+                ("prefix", 1.0, 0), ("queue", 1.0, 0)]
+        order = list(range(len(c_sc)))
+        rng.shuffle(order)
+        k = rng.randint(1, len(order))
+        c_sc, p_sc = [c_sc[i] for i in order[:k]], [p_sc[i] for i in order[:k]]
+        fk = rng.choice(list(fnames))
+        scores, mx, pick, aset = orc.profile_run(orc.make_profile(fk, c_sc), pool, match, total)
+        eps = [{"role": labels[r], "kv": kv[i], "waiting": waiting[i], "tokens": tokens[i], "requests": requests[i],
+                "active": active[i], "waiting_models": waiting_m[i], "max_active": max_active[i]} for i, r in enumerate(roles)]
+        want = pr.profile_run(fnames[fk], p_sc, eps, match, total)
+        if want is None:
+            assert aset == []
+            continue
+        acc, wmx, wset = want
+        assert mx == wmx and aset == wset and pick == wset[0]
+        for i in range(n):
+            assert scores[i] == (acc[i] if i in acc else -1.0)
