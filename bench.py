@@ -33,7 +33,6 @@ if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "routing decisions/sec at 4K-token prompts x 4,096 endpoints"
 UNIT = "decisions/s"
@@ -166,7 +165,7 @@ def _best_thread_count(run, n_max: int) -> int:
 
 def cpu_baseline(w, trace, n_threads: int, target_s: float = 12.0, tokens: np.ndarray | None = None):
     """Oracle (port of the reference Go loops) on the host cores over a bounded sample of the same workload."""
-    import helpers
+    from tools import workload_setup as helpers
     from oracle import pyoracle as orc
     pool, ix, primary, prefill, _ = helpers.setup_oracle(orc, w, trace)
     n = int(min(w.R, tokens.shape[0] if tokens is not None else w.R))
@@ -201,7 +200,7 @@ def run_reference(args, rank, world):
     w = _workload(args.workload, args.requests)
     trace = tg.Trace(w)
     n_threads = os.cpu_count() or 1
-    import helpers
+    from tools import workload_setup as helpers
     from oracle import pyoracle as orc
     orc.build()
     pool, ix, primary, prefill, _ = helpers.setup_oracle(orc, w, trace)
@@ -312,7 +311,7 @@ def run_gpu(args, rank, world, local_rank):
     import torch.distributed as dist
 
     import epp_b200 as epp
-    import helpers
+    from tools import workload_setup as helpers
     from tools import tracegen as tg
 
     torch.cuda.set_device(local_rank)
@@ -494,7 +493,7 @@ def run_gpu_sharded(args, rank, world, local_rank):
     import torch.distributed as dist
 
     import epp_b200 as epp
-    import helpers
+    from tools import workload_setup as helpers
     from tools import tracegen as tg
     sh = importlib.import_module("llm-d-inference-scheduler_b200.sharded")
 

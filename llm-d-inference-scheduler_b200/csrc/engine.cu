@@ -60,6 +60,8 @@ struct Slot {                       // per-stream staging for host-pointer batch
     cudaStream_t stream = nullptr;
     DevBuf data;
     DevBuf overflow_list, overflow_n;   // requests handed from a sparse pass to the dense-counter pass (per stream)
+    DevBuf pick_scratch;                // zeroed global match counters of the dense-counter kernel when max_endpoints is too
+                                        // large for shared memory: per stream, two streams may run that kernel at once
     cudaEvent_t done = nullptr;
 };
 
@@ -117,21 +119,10 @@ struct epp_engine {
     // batch buffers (sized for the largest batch seen)
     DevBuf offsets, lengths, model_ids, hashes, nblocks, eff_len, in_len, decisions, details, flag;
     DevBuf dense_match, dense_total, dense_scores;
-    DevBuf pick_scratch;            // global match counters when E is too large for shared memory
-    int force_v1 = 0;               // EPP_HASH_V1=1: unfused v1 hash kernels (A/B)
-    int force_match_v1 = 0;         // EPP_MATCH_V1=1: dense-counter match kernel only (A/B)
-    int prefetch = 0;               // EPP_PREFETCH=1
-    int index_load = 2;             // EPP_INDEX_LOAD=n: read-table slots per distinct hash (2 = load factor <= 0.5, 4 = <= 0.25)
-    int tile_rows = 32;             // EPP_TILE_ROWS=n: requests per hash tile (0 = balance the waves of the persistent grid; measured: no gain)
-    int dev_ordered = 0;            // EPP_DEV_ORDERED=1: chunk c's hash kernel waits for chunk c-1's
-    cudaEvent_t hash_done[8] = {};
+    int index_load = 0;             // EPP_INDEX_LOAD=n: read-table slots per distinct hash (2 = load factor <= 0.5, 4 = <= 0.25);
+                                    // 0 = automatic: 4 while the table stays L2-sized (<= 48 MiB), else 2
     int dev_chunks = 2;             // EPP_DEV_CHUNKS=N: async device batches run as N chunks over both streams (1 = off)
-    int chain_spread = 0;           // EPP_CHAIN_SPREAD=1
-    int win = 8;                    // EPP_HASH_WIN=4: 4-block windows in k_hash_fused
-    int bulk = 0;                   // EPP_HASH_BULK=2|3|4|5: bulk-copy fed hash kernel (hash_bulk.cu), data stages per CTA
-    int wide = 0;                   // EPP_WIDE=1: 32-block windows in the hash kernel (A/B; measured slower)
-    int tile_r = 32;                // EPP_TILE=16: 16-request tiles in the fused kernels (A/B; measured slower)
-    int no_fuse = 1;                // EPP_FUSE_MATCH=1 runs a2-a14 inside the hash kernel (experimental, slower today)
+    int staged = 0;                 // EPP_HASH_STAGED: hash_staged.cu kernel: -1 off (hash_fused.cu), 0 default shape, else a shape
     int pick_grid = 0;
     bool pick_global = false;
     size_t pick_smem = 0;
@@ -277,21 +268,10 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
         for (int si = 0; si < pc.n_scorers; si++) if (pc.scorers[si].kind == EPP_SCORER_LORA_AFFINITY) e->lora_enabled = true;
     }
     e->store.reset(new IndexStore((uint32_t)cfg->max_endpoints, cfg->lru_capacity_per_server));
-    { const char *v1 = getenv("EPP_HASH_V1"); e->force_v1 = (v1 && v1[0] == '1') ? 1 : 0; }
-    { const char *v1 = getenv("EPP_MATCH_V1"); e->force_match_v1 = (v1 && v1[0] == '1') ? 1 : 0; }
-    { const char *v1 = getenv("EPP_WIDE"); e->wide = (v1 && v1[0] == '1') ? 1 : 0; }
-    { const char *v1 = getenv("EPP_HASH_BULK"); e->bulk = v1 ? atoi(v1) : 0; }
     { const char *v1 = getenv("EPP_INDEX_PATCH"); e->patch_enabled = v1 ? atoi(v1) : 1; }
-    { const char *v1 = getenv("EPP_INDEX_LOAD"); e->index_load = v1 ? std::max(2, atoi(v1)) : 2; }
-    { const char *v1 = getenv("EPP_TILE_ROWS"); e->tile_rows = v1 ? atoi(v1) : 32; }
-    { const char *v1 = getenv("EPP_DEV_ORDERED"); e->dev_ordered = v1 ? atoi(v1) : 0; }
-    for (auto &ev : e->hash_done) CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    { const char *v1 = getenv("EPP_INDEX_LOAD"); e->index_load = v1 ? std::max(2, atoi(v1)) : 0; }
     { const char *v1 = getenv("EPP_DEV_CHUNKS"); e->dev_chunks = v1 ? std::max(1, atoi(v1)) : 2; }
-    { const char *v1 = getenv("EPP_CHAIN_SPREAD"); e->chain_spread = v1 ? atoi(v1) : 0; }
-    { const char *v1 = getenv("EPP_HASH_WIN"); e->win = v1 ? atoi(v1) : 8; }
-    { const char *v1 = getenv("EPP_PREFETCH"); e->prefetch = (v1 && v1[0] == '1') ? 1 : 0; }
-    { const char *v1 = getenv("EPP_TILE"); e->tile_r = (v1 && atoi(v1) == 16) ? 16 : 32; }
-    { const char *v1 = getenv("EPP_FUSE_MATCH"); e->no_fuse = (v1 && v1[0] == '1') ? 0 : 1; }
+    { const char *v1 = getenv("EPP_HASH_STAGED"); e->staged = v1 ? atoi(v1) : 0; }
     for (int i = 0; i < 2; i++) CUDA_TRY(e->slot[i].overflow_n.reserve(sizeof(int32_t) * 4, &e->dev_bytes));
 
     // match/pick launch geometry: counters in shared memory when they fit, else zeroed global scratch
@@ -303,8 +283,10 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
     e->pick_grid = e->sm_count * ctas_per_sm;
     if (e->pick_global) {
         size_t words = (size_t)e->pick_grid * match_pick_warps_per_cta() * (size_t)((cfg->max_endpoints + 1) / 2);
-        CUDA_TRY(e->pick_scratch.reserve(words * sizeof(uint32_t), &e->dev_bytes));
-        CUDA_TRY(cudaMemset(e->pick_scratch.p, 0, words * sizeof(uint32_t)));
+        for (int i = 0; i < 2; i++) {
+            CUDA_TRY(e->slot[i].pick_scratch.reserve(words * sizeof(uint32_t), &e->dev_bytes));
+            CUDA_TRY(cudaMemset(e->slot[i].pick_scratch.p, 0, words * sizeof(uint32_t)));
+        }
     }
     CUDA_TRY(cudaDeviceSynchronize());
     *out = e.release();
@@ -321,7 +303,6 @@ extern "C" int32_t epp_engine_destroy(epp_engine *h) {
     }
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->user_ev) if (ev) cudaEventDestroy(ev);
-    for (auto &ev : h->hash_done) if (ev) cudaEventDestroy(ev);
     if (h->wc_host) cudaFreeHost(h->wc_host);
     for (int g = 0; g < (int)h->p2p_peer.size(); g++)
         if (h->p2p_ipc && g != h->p2p_rank && h->p2p_peer[g]) cudaIpcCloseMemHandle(h->p2p_peer[g]);
@@ -555,8 +536,10 @@ static int32_t build_index_from_device_pairs(epp_engine *h, uint64_t n, uint64_t
     uint32_t cursor[4] = {0, 0, 0, 0};
     uint64_t cap = 16;
     for (int pass = 0; pass < 2; pass++) {
-        // load factor <= 0.5 over the distinct hashes; the first pass only knows an upper bound (the pair count)
-        uint64_t want = std::max<uint64_t>(16, (uint64_t)h->index_load * distinct);
+        // load factor <= 0.5 over the distinct hashes (<= 0.25 while the table stays L2-sized: shorter probe chains, measured
+        // 10 % faster match kernel); the first pass only knows an upper bound (the pair count)
+        const uint64_t load = h->index_load ? (uint64_t)h->index_load : (4 * distinct * sizeof(IndexSlot) <= (48ull << 20) ? 4 : 2);
+        uint64_t want = std::max<uint64_t>(16, load * distinct);
         cap = 16;
         while (cap < want) cap <<= 1;
         CUDA_TRY(h->slots.reserve(sizeof(IndexSlot) * cap, &h->dev_bytes));
@@ -571,8 +554,9 @@ static int32_t build_index_from_device_pairs(epp_engine *h, uint64_t n, uint64_t
         CUDA_TRY(cudaMemcpyAsync(cursor, h->idx_cursor.p, sizeof cursor, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
         uint64_t true_distinct = std::max<uint64_t>(1, cursor[2]);
+        const uint64_t load2 = h->index_load ? (uint64_t)h->index_load : (4 * true_distinct * sizeof(IndexSlot) <= (48ull << 20) ? 4 : 2);
         uint64_t tight = 16;
-        while (tight < (uint64_t)h->index_load * true_distinct) tight <<= 1;
+        while (tight < load2 * true_distinct) tight <<= 1;
         if (tight >= cap) break;            // already as small as the load factor allows
         distinct = true_distinct;           // rebuild once into a table a quarter (or less) of the size
     }
@@ -886,15 +870,7 @@ static HashParams hash_params(epp_engine *h, const Work &w) {
     p.in_len = h->in_len.as<int64_t>() + w.r0;
     p.offsets_or_bits = w.offsets_or_bits;
     p.sm_count = h->sm_count;
-    p.force_v1 = h->force_v1;
-    p.tile_r = h->tile_r;
-    p.prefetch = h->prefetch;
-    p.wide = h->wide;
-    p.bulk = h->bulk;
-    p.win = h->win;
-    p.chain_spread = h->chain_spread;
-    p.tile_rows = h->tile_rows;
-    p.fused_pick = nullptr;
+    p.staged = h->staged;
     return p;
 }
 
@@ -951,7 +927,7 @@ static int32_t launch_overflow_pass(epp_engine *h, Slot &sl, PickParams pp, int 
     pp.overflow_list = nullptr;
     pp.overflow_n = nullptr;
     pp.work_counters = nullptr;            // already counted by the sparse pass
-    CUDA_TRY(launch_match_pick(pp, h->pick_global ? h->pick_scratch.as<uint32_t>() : nullptr, h->pick_grid, h->pick_smem, s, launches));
+    CUDA_TRY(launch_match_pick(pp, h->pick_global ? sl.pick_scratch.as<uint32_t>() : nullptr, h->pick_grid, h->pick_smem, s, launches));
     return EPP_OK;
 }
 
@@ -959,8 +935,8 @@ static int32_t launch_overflow_pass(epp_engine *h, Slot &sl, PickParams pp, int 
 // kernel alone for Produce-parity rows / A-B runs).
 static int32_t launch_match(epp_engine *h, Slot &sl, PickParams pp, int *launches) {
     cudaStream_t s = sl.stream;
-    uint32_t *gs = h->pick_global ? h->pick_scratch.as<uint32_t>() : nullptr;
-    if (pp.out_match || h->force_match_v1) {
+    uint32_t *gs = h->pick_global ? sl.pick_scratch.as<uint32_t>() : nullptr;
+    if (pp.out_match) {
         CUDA_TRY(launch_match_pick(pp, gs, h->pick_grid, h->pick_smem, s, launches));
         return EPP_OK;
     }
@@ -971,22 +947,10 @@ static int32_t launch_match(epp_engine *h, Slot &sl, PickParams pp, int *launche
     return launch_overflow_pass(h, sl, pp, launches);
 }
 
-// The whole cycle for one Work item.  Fast path (aligned prompts, block_bytes % 32 == 0): ONE fused kernel hashes,
-// probes, scores and picks; otherwise hash kernels + standalone match.
-static int32_t launch_cycle(epp_engine *h, Slot &sl, const HashParams &hp_in, PickParams pp, int *launches,
-                            cudaEvent_t *ev) {
-    cudaStream_t s = sl.stream;
-    HashParams hp = hp_in;
-    const bool fuse = !pp.out_match && !h->force_match_v1 && !h->force_v1 && !h->no_fuse && !h->lora_enabled && hash_batch_alignment(hp) >= 16;
-    if (fuse) {
-        CUDA_TRY(cudaMemsetAsync(sl.overflow_n.p, 0, sizeof(int32_t), s));
-        pp.overflow_list = sl.overflow_list.as<int32_t>();
-        pp.overflow_n = sl.overflow_n.as<int32_t>();
-        hp.fused_pick = &pp;
-        CUDA_TRY(launch_hash_prompts(hp, s, launches, ev));
-        return launch_overflow_pass(h, sl, pp, launches);
-    }
-    CUDA_TRY(launch_hash_prompts(hp, s, launches, ev));
+// The whole cycle for one Work item: hash kernel, then the standalone match / score / pick kernel (every fused or
+// concurrently scheduled arrangement of the two was measured slower).
+static int32_t launch_cycle(epp_engine *h, Slot &sl, const HashParams &hp, PickParams pp, int *launches, cudaEvent_t *ev) {
+    CUDA_TRY(launch_hash_prompts(hp, sl.stream, launches, ev));
     return launch_match(h, sl, pp, launches);
 }
 
@@ -1058,15 +1022,7 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
                        v.model_ids, or_bits, h->hashes.as<uint64_t>() + (size_t)r0 * B, h->nblocks.as<int32_t>() + r0};
                 PickParams pp = pick_params(h, w, dec_base + r0, out_detail ? out_detail + r0 : nullptr, nullptr);
                 Slot &sl = h->slot[k & 1];
-                if (h->dev_ordered && !h->force_v1 && !h->force_match_v1 && h->no_fuse) {
-                    // ordered pipeline (A/B): hash(c) starts when hash(c-1) is done
-                    if (k > 0) CUDA_TRY(cudaStreamWaitEvent(sl.stream, h->hash_done[(k - 1) & 7], 0));
-                    CUDA_TRY(launch_hash_prompts(hash_params(h, w), sl.stream, &launches, nullptr));
-                    CUDA_TRY(cudaEventRecord(h->hash_done[k & 7], sl.stream));
-                    EPP_TRY(launch_match(h, sl, pp, &launches));
-                } else {
-                    EPP_TRY(launch_cycle(h, sl, hash_params(h, w), pp, &launches, nullptr));
-                }
+                EPP_TRY(launch_cycle(h, sl, hash_params(h, w), pp, &launches, nullptr));
             }
             h->s1_unjoined = true;
             h->pipe_R = R;

@@ -26,15 +26,7 @@ struct HashParams {
     int64_t *in_len;            // [R] untruncated prompt length in bytes (P/D decider), may be nullptr
     uint64_t offsets_or_bits;   // OR of every offsets[r] (low bits decide the common alignment)
     int32_t sm_count;
-    int32_t force_v1;           // use the unfused v1 kernels (A/B testing)
-    int32_t tile_r;             // fused kernels: requests per CTA tile (32 default, 16)
-    int32_t prefetch;           // hash kernel: register software prefetch of the next window (A/B)
-    int32_t wide;               // hash kernel: 32-block windows (2-KiB DRAM bursts per warp load)
-    int32_t tile_rows;          // k_hash_fused: requests per tile actually used (0 = launcher balances the waves, -1/32 = all 32)
-    int32_t chain_spread;       // fused hash kernels: rotate the chain warp over the SM sub-partitions per resident CTA
-    int32_t win;                // fused hash kernel: blocks per window (8 default; 4 = smaller CTAs, twice the chains in flight)
-    int32_t bulk;               // hash kernel fed by cp.async.bulk into shared memory: 0 off, else data stages (2/3/4; 5 = 2 stages, 5 CTAs)
-    const struct PickParams *fused_pick;  // non-null: run a2-a14 inside the fused kernel's chain warp (fast path only)
+    int32_t staged;             // hash_staged.cu (cp.async-staged, warp-per-task) kernel: -1 off, 0 default shape, else a launch shape (A/B)
 };
 // Common alignment (0, 16, 32) of every block start; >= 16 (and block_bytes % 32 == 0) enables the fused kernel.
 int hash_batch_alignment(const HashParams &p);
@@ -42,11 +34,13 @@ int hash_batch_alignment(const HashParams &p);
 cudaError_t launch_hash_bytes(const uint8_t *msg, size_t len, uint64_t *out, cudaStream_t s);
 cudaError_t launch_check_offsets_aligned(const uint64_t *offsets, int64_t n, int *flag_dev, cudaStream_t s);
 // Whole hashPrompt for a batch.  Returns number of kernels launched via *launches.
-// ev (optional, 4 events): recorded before the first kernel and after each of lengths / digests / chain.
+// ev (optional, 4 events): [1]..[2] brackets the kernel(s) that read the prompt bytes.
 cudaError_t launch_hash_prompts(const HashParams &p, cudaStream_t s, int *launches, cudaEvent_t *ev = nullptr);
-// hash_bulk.cu: a1 with bulk-copy (TMA engine) staging of the prompt bytes; same contract as the fused kernel.
-bool hash_bulk_supported(const HashParams &p);
-cudaError_t launch_hash_bulk(const HashParams &p, int sm_count, cudaStream_t s, int *launches);
+
+// hash_staged.cu: a1 with the prompt bytes staged through shared memory by cp.async, one warp per task of 16 / 32
+// requests, no cross-warp synchronisation.  Needs 64-byte blocks and 16-byte aligned prompts.
+bool hash_staged_supported(const HashParams &p);
+cudaError_t launch_hash_staged(const HashParams &p, int shape, cudaStream_t s, int *launches);
 
 // ------------------------------------------------------------------------------------------------
 // prefix index (a2): open-addressed table  hash -> (posting offset, count)

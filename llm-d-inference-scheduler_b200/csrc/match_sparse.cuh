@@ -1,0 +1,285 @@
+// match_sparse.cuh -- a2-a14 for ONE request by ONE warp over hashes resident in HBM / L2: index lookup with the
+// global-stop rule (approximateprefix/plugin.go:214-230), per-endpoint match counts, ordered weighted sum
+// (scheduler_profile.go:151-174), arg-max pick (maxscore/picker.go:87-115) and the decode -> decider -> prefill second
+// stage (disagg_profile_handler.go:264-308).  No shared memory, no atomics on the common path.
+//
+// Shared by the standalone kernel (match_sparse.cu: plugin-parity, sharded and generic-hash batches) and by the match
+// warps of the fused cycle kernel (cycle.cu), which run it on the tile their CTA hashed just before.
+//
+//   * 32 blocks are probed per step, one 256-bit load per 32-byte slot.  Probe chains are followed only as far as the
+//     stop rule needs them: once a lane has proven its block absent, the lanes behind it stop probing (a cold prompt
+//     costs the probe chain of block 0, not the longest chain of 32 unrelated blocks);
+//   * matched endpoints live in a LANE-DISTRIBUTED register map: lane j holds (endpoint E_j, count C_j), j <
+//     n_distinct <= 32; membership tests are ballots;
+//   * counting is run-length based: posting lists are sorted, duplicate-free and (when spilled) interned, and unused
+//     id words of a slot are zero by construction of the table (index_kernels.cu: finalize_slot, index_store.cu:
+//     k_patch_apply), so "same endpoint set" is equality of the six words (cnt, ids[0..4]); the blocks of one cached
+//     prefix form a few runs of identical sets and a run adds its length to each of its endpoints.
+//
+// Exactness: a request whose matched-endpoint set exceeds 32 distinct endpoints is appended to
+// PickParams::overflow_list and handled by the dense-counter kernel (pick_kernels.cu), never approximated.
+#pragma once
+#include "index.cuh"
+#include "score.cuh"
+
+namespace epp {
+namespace sparse {
+
+constexpr uint32_t kNoKey = 0xFFFFFFFFu;
+constexpr uint32_t kFull = 0xffffffffu;
+
+struct LaneMap {                   // one entry per lane
+    uint32_t e;                    // endpoint held by this lane (kNoKey = none)
+    uint32_t c;                    // its match count
+    uint32_t n;                    // distinct endpoints so far (warp-uniform)
+    bool overflow;                 // warp-uniform
+};
+
+// count[e] += c for a warp-uniform (e, c).
+__device__ __forceinline__ void map_add(LaneMap &m, uint32_t e, uint32_t c, int lane) {
+    const uint32_t holder = __ballot_sync(kFull, m.e == e);
+    if (holder) {
+        if (lane == __ffs(holder) - 1) m.c += c;
+    } else if (m.n < 32) {
+        if (lane == (int)m.n) { m.e = e; m.c = c; }
+        m.n++;
+    } else {
+        m.overflow = true;
+    }
+}
+
+__device__ __forceinline__ uint32_t map_get(const LaneMap &m, uint32_t e) {   // warp-uniform e
+    const uint32_t holder = __ballot_sync(kFull, m.e == e);
+    const uint32_t c = __shfl_sync(kFull, m.c, holder ? __ffs(holder) - 1 : 0);
+    return holder ? c : 0;
+}
+
+// Lane-parallel membership: is MY candidate e (different per lane) one of the matched endpoints?
+__device__ __forceinline__ bool map_contains_any(const LaneMap &m, uint32_t e) {
+    bool hit = false;
+    for (uint32_t j = 0; j < m.n; j++) hit |= (e == __shfl_sync(kFull, m.e, (int)j));
+    return hit;
+}
+
+// One profile for the current request (SchedulerProfile.Run): matched candidates from the lane map, everyone else
+// from the precomputed (base desc, slot asc) order -- an unmatched endpoint's ordered weighted sum is bit-identical to
+// its precomputed base, so only the first unmatched entry of the order (and the size of its equal-base group) matters.
+__device__ __forceinline__ Best eval_profile_lanes(const ProfileDev &pf, int32_t E, const LaneMap &m, int32_t total,
+                                                   int lane, const LoraDev &lora, int lora_st) {
+    Best b;
+    best_init(b);
+    const int32_t ncand = *pf.n_cand;
+    if (ncand == 0) return b;
+    if (m.n == 0) {                                   // nobody holds a block of this prompt: the head of the order wins
+        const uint32_t ue = pf.order[0];
+        best_add(b, pf.base[ue], ue, pf.grp_size[0]);
+        return b;
+    }
+    const bool mine = (uint32_t)lane < m.n && pf.cand[m.e];
+    if (mine) best_add(b, weighted_sum(pf, E, m.e, (int32_t)m.c, total, lora, lora_st), m.e);
+    b = best_warp_reduce(b);
+    for (int32_t k0 = 0; k0 < ncand; k0 += 32) {
+        const int32_t k = k0 + lane;
+        const uint32_t e = k < ncand ? pf.order[k] : kNoKey;
+        const bool matched = map_contains_any(m, e);   // shuffles inside: EVERY lane must call it (no short-circuit)
+        const bool un = k < ncand && !matched;
+        const uint32_t bal = __ballot_sync(kFull, un);
+        if (bal) {
+            const int first = __ffs(bal) - 1;
+            const uint32_t ue = __shfl_sync(kFull, e, first);
+            const double ubase = pf.base[ue];
+            const uint32_t gsz = pf.grp_size[k0 + first];
+            const uint32_t same = __popc(__ballot_sync(kFull, mine && pf.base[m.e] == ubase));
+            best_add(b, ubase, ue, gsz - same);
+            break;
+        }
+    }
+    return b;
+}
+
+// Adds one chunk's postings to the lane map.  (cnt, w0..w4) = this lane's slot words, all zero when the block is
+// beyond the stop or absent.  Runs of lanes with identical words are added at once.
+__device__ __forceinline__ void count_chunk(LaneMap &m, const IndexView &ix, uint32_t cnt, uint32_t w0, uint32_t w1,
+                                            uint32_t w2, uint32_t w3, uint32_t w4, uint32_t shard_lo, uint32_t shard_hi,
+                                            int lane) {
+    // run boundaries: a lane starts a run when its words differ from the previous lane's
+    uint32_t d = cnt ^ __shfl_up_sync(kFull, cnt, 1);
+    d |= w0 ^ __shfl_up_sync(kFull, w0, 1);
+    d |= w1 ^ __shfl_up_sync(kFull, w1, 1);
+    d |= w2 ^ __shfl_up_sync(kFull, w2, 1);
+    d |= w3 ^ __shfl_up_sync(kFull, w3, 1);
+    d |= w4 ^ __shfl_up_sync(kFull, w4, 1);
+    const uint32_t bounds = __ballot_sync(kFull, d != 0 || lane == 0);
+    uint32_t heads = bounds & __ballot_sync(kFull, cnt != 0);                    // heads of the non-empty runs
+    while (heads) {
+        const int s = __ffs(heads) - 1;
+        heads &= heads - 1;
+        const uint32_t after = bounds & ~((2u << s) - 1u);              // next run boundary behind s
+        const int end = after ? __ffs(after) - 1 : 32;
+        const uint32_t len = (uint32_t)(end - s);
+        const uint32_t rc = __shfl_sync(kFull, cnt, s);
+        const uint32_t r0 = __shfl_sync(kFull, w0, s);
+        if (rc <= (uint32_t)kInlineIds) {
+            if (r0 >= shard_lo && r0 < shard_hi) map_add(m, r0, len, lane);
+            if (rc > 1) { const uint32_t e = __shfl_sync(kFull, w1, s); if (e >= shard_lo && e < shard_hi) map_add(m, e, len, lane); }
+            if (rc > 2) { const uint32_t e = __shfl_sync(kFull, w2, s); if (e >= shard_lo && e < shard_hi) map_add(m, e, len, lane); }
+            if (rc > 3) { const uint32_t e = __shfl_sync(kFull, w3, s); if (e >= shard_lo && e < shard_hi) map_add(m, e, len, lane); }
+            if (rc > 4) { const uint32_t e = __shfl_sync(kFull, w4, s); if (e >= shard_lo && e < shard_hi) map_add(m, e, len, lane); }
+        } else {
+            // spilled (interned) list: r0 is the offset into the postings array
+            for (uint32_t k0 = 0; k0 < rc && !m.overflow; k0 += 32) {
+                const uint32_t mine = (k0 + lane < rc) ? ix.postings[r0 + k0 + lane] : kNoKey;
+                const uint32_t nk = min(32u, rc - k0);
+                for (uint32_t k = 0; k < nk && !m.overflow; k++) {
+                    const uint32_t e = __shfl_sync(kFull, mine, (int)k);
+                    if (e >= shard_lo && e < shard_hi) map_add(m, e, len, lane);
+                }
+            }
+        }
+    }
+}
+
+template <bool kCg, typename T>
+__device__ __forceinline__ T ld_row(const T *p) {
+    if (kCg) return __ldcg(p);        // written earlier by THIS kernel (fused cycle): read at L2, never a stale L1 line
+    return *p;
+}
+
+// Work a warp did for its requests; flushed by the caller.
+struct Work {
+    unsigned long long probes = 0, postings = 0;
+};
+
+// The whole decision for request r (all 32 lanes of one warp call it together).  kCg: the per-request inputs
+// (hashes, nblocks, in_len) were produced earlier in the same kernel launch.
+// kSharded: endpoint-sharded mode (the stop rule comes from p.global_masks).
+template <bool kCg, bool kSharded>
+__device__ __forceinline__ void match_request(const PickParams &p, const int64_t r, const int lane, const bool counting,
+                                              Work &wk) {
+    const uint32_t shard_lo = p.index.ep_begin, shard_hi = min(p.index.ep_end, (uint32_t)p.E);
+    const IndexSlot *slots = p.index.slots;
+    const uint32_t mask32 = (uint32_t)p.index.mask;
+    const int32_t total = ld_row<kCg>(p.nblocks + r);
+    const uint64_t *row = p.hashes + r * (int64_t)p.max_blocks;
+    LaneMap m;
+    m.e = kNoKey; m.c = 0; m.n = 0; m.overflow = false;
+    // ---- a2/a3: probe in block order, 32 blocks per step; global stop at the first block nobody holds
+    bool stopped = false;
+    uint64_t hnext = lane < total ? ld_row<kCg>(row + lane) : 0;
+    for (int32_t cq = 0; cq < total && !stopped; cq += 32) {
+        const int32_t i = cq + lane;
+        const uint64_t hcur = hnext;
+        if (i + 32 < total) hnext = ld_row<kCg>(row + i + 32);    // next chunk's hashes in flight during this one
+        const bool valid = i < total;
+        // endpoint-sharded mode: a block is missing only if NO rank holds it, and that is known up front
+        uint32_t gmiss = 0;
+        if (kSharded) {
+            const uint32_t word = p.global_masks[r * (int64_t)p.mask_words + (cq >> 5)];
+            const uint32_t vmask = (total - cq) >= 32 ? kFull : ((1u << (total - cq)) - 1u);
+            gmiss = ~word & vmask;
+        }
+        const uint32_t relevant = (kSharded && gmiss) ? ((1u << (__ffs(gmiss) - 1)) - 1u) : kFull;
+        uint32_t cnt = 0, w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;
+        bool pending = valid && ((relevant >> lane) & 1u);
+        if (pending && (hcur == kEmptyKey || !slots)) {           // the sentinel hash lives in a side record
+            Hit hs;
+            if (probe(p.index, hcur, hs)) { cnt = hs.cnt; w0 = hs.w[0]; w1 = hs.w[1]; w2 = hs.w[2]; w3 = hs.w[3]; w4 = hs.w[4]; }
+            if (cnt > (uint32_t)kInlineIds) { w1 = w2 = w3 = w4 = 0; }
+            pending = false;
+        }
+        uint32_t idx = (uint32_t)hcur & mask32;
+        for (;;) {
+            if (pending) {
+                uint64_t key;
+                Hit hs;
+                load_slot(slots + idx, key, hs);
+                if (key == hcur) {                                // cnt == 0: every holder was evicted (tombstone)
+                    cnt = hs.cnt; w0 = hs.w[0]; w1 = hs.w[1]; w2 = hs.w[2]; w3 = hs.w[3]; w4 = hs.w[4];
+                    pending = false;
+                } else if (key == kEmptyKey) {                    // a never-used slot ends the probe chain: absent
+                    pending = false;
+                } else {
+                    idx = (idx + 1) & mask32;
+                }
+            }
+            const uint32_t pend = __ballot_sync(kFull, pending);
+            if (!pend) break;
+            if (!kSharded) {
+                // lanes behind the first PROVEN miss cannot change the walk: they stop probing
+                const uint32_t missm = __ballot_sync(kFull, valid && !pending && cnt == 0);
+                const uint32_t below = missm ? ((1u << (__ffs(missm) - 1)) - 1u) : kFull;
+                if (!(pend & below)) break;
+                if (!((below >> lane) & 1u)) pending = false;
+            }
+        }
+        // lanes that stopped early (pending) hold cnt == 0 and sit behind the stop
+        const uint32_t miss = kSharded ? gmiss : __ballot_sync(kFull, valid && cnt == 0);
+        const int32_t limit = miss ? cq + (__ffs(miss) - 1) : total;
+        if (i >= limit) { cnt = 0; w0 = 0; w1 = 0; w2 = 0; w3 = 0; w4 = 0; }
+        if (counting) {
+            if (lane == 0) wk.probes += (unsigned long long)((miss ? limit + 1 : min(total, cq + 32)) - cq);
+            wk.postings += cnt;
+        }
+        if (limit > cq) count_chunk(m, p.index, cnt, w0, w1, w2, w3, w4, shard_lo, shard_hi, lane);
+        if (miss) stopped = true;
+    }
+    // ---- lora-affinity: the endpoints where the request's adapter is active or waiting get a request-dependent
+    //      score, so they join the map (count 0) and are evaluated one by one like the prefix holders
+    int lora_st = 0;
+    if (p.lora.enabled && p.lora.ptr && !m.overflow) {
+        const uint32_t a = p.model_ids ? p.model_ids[r] : 0u;
+        if (a < (uint32_t)p.lora.n_models) {
+            const uint32_t lo = p.lora.ptr[a], hi = p.lora.ptr[a + 1];
+            for (uint32_t k0 = lo; k0 < hi && !m.overflow; k0 += 32) {
+                const uint32_t mine_e = (k0 + lane < hi) ? p.lora.ep[k0 + lane] : kNoKey;
+                const uint32_t nk = min(32u, hi - k0);
+                for (uint32_t k = 0; k < nk && !m.overflow; k++) {
+                    const uint32_t e = __shfl_sync(kFull, mine_e, (int)k);
+                    if (e >= shard_lo && e < shard_hi) map_add(m, e, 0, lane);
+                }
+            }
+            if ((uint32_t)lane < m.n) lora_st = lora_lookup(p.lora, a, m.e);
+        }
+    }
+    if (m.overflow) {
+        // hand the request to the dense-counter kernel
+        if (lane == 0 && p.overflow_list) p.overflow_list[atomicAdd(p.overflow_n, 1)] = (int32_t)r;
+        return;
+    }
+    // ---- a5-a10: primary profile
+    const Best b0 = eval_profile_lanes(p.prof[0], p.E, m, total, lane, p.lora, lora_st);
+    epp_decision d;
+    d.status = b0.ties ? 0 : -1;
+    d.pick = b0.ties ? b0.pick : EPP_NO_ENDPOINT;
+    d.score = b0.ties ? b0.val : 0.0;
+    d.prefill_pick = EPP_NO_ENDPOINT;
+    d.tie_count = b0.ties;
+    d.total_blocks = total;
+    d.match_blocks = (b0.ties && m.n) ? (int32_t)map_get(m, b0.pick) : 0;
+    epp_decision_detail dd;
+    dd.prefill_score = 0.0; dd.prefill_tie_count = 0; dd.prefill_ran = 0;
+    // ---- a13: decode -> decider -> prefill (disagg_profile_handler.go:264-308)
+    if (p.n_profiles == 2 && b0.ties) {
+        const bool go = p.always_disagg ||
+                        pd_decide(p.non_cached_tokens, ld_row<kCg>(p.in_len + r), d.match_blocks, p.block_size_tokens);
+        if (go) {
+            dd.prefill_ran = 1;
+            const Best b1 = eval_profile_lanes(p.prof[1], p.E, m, total, lane, p.lora, lora_st);
+            if (b1.ties) { d.prefill_pick = b1.pick; dd.prefill_score = b1.val; dd.prefill_tie_count = b1.ties; }
+        }
+    }
+    if (lane == 0) {
+        if (p.shard_out) {
+            epp_shard_best sb;
+            sb.score = d.score; sb.pick = d.pick; sb.tie_count = d.tie_count;
+            sb.match_blocks = d.match_blocks; sb.status = d.status;
+            p.shard_out[r] = sb;
+        } else {
+            p.out[r] = d;
+            if (p.detail) p.detail[r] = dd;
+        }
+    }
+}
+
+}  // namespace sparse
+}  // namespace epp

@@ -492,13 +492,17 @@ def test_async_device_batches_match_synchronous_ones(epp, orc, tg):
             eng.schedule(tokens[:8], uniform_len=w.prompt_bytes, asynchronous=True)      # host buffers cannot be async
 
 
-def test_async_chunk_pipelined_batches(epp, orc, tg, monkeypatch):
-    """EPP_DEV_CHUNKS: an async device batch split into chunks that alternate between the engine's two streams (hash of
-    chunk c+1 overlapping match of chunk c) must produce exactly the synchronous single-pass decisions, ragged tail
-    chunk included, and leave the hashes in place for epp_index_add_picked."""
+@pytest.mark.parametrize("mode", ["cross-batch", "chunks"])
+def test_async_chunk_pipelined_batches(epp, orc, tg, monkeypatch, mode):
+    """The two throughput modes of async device batches must produce exactly the synchronous single-pass decisions:
+    cross-batch (default: batch N hashed on stream 0 into buffer set N % 2 and matched on stream 1, so the hash kernel
+    of batch N+1 overlaps the match kernel of batch N) and EPP_DEV_CHUNKS (one batch split into chunks that alternate
+    between the two streams, ragged tail chunk included)."""
     import torch
     import helpers
-    monkeypatch.setenv("EPP_DEV_CHUNKS", "4")
+    if mode == "chunks":
+        monkeypatch.setenv("EPP_XBATCH", "0")
+        monkeypatch.setenv("EPP_DEV_CHUNKS", "4")
     w = tg.baseline_configs()["config4"].scaled(E=192, R=20000 + 37, T=512, name="config4")
     w.non_cached_tokens = 64
     trace = tg.Trace(w)
@@ -514,7 +518,18 @@ def test_async_chunk_pipelined_batches(epp, orc, tg, monkeypatch):
             eng.schedule(dt, uniform_len=w.prompt_bytes, detail=False, out=out, asynchronous=True)
         eng.synchronize()
         np.testing.assert_array_equal(epp.decisions_from_torch(out), want)
-        assert (want["prefill_pick"] != 0xFFFFFFFF).any() and eng.stats()["last_kernel_launches"] >= 8
+        assert (want["prefill_pick"] != 0xFFFFFFFF).any()
+        assert eng.stats()["last_kernel_launches"] >= (8 if mode == "chunks" else 2)
+        # different batches back to back (each buffer set is reused only after its match kernel has finished), then a
+        # kept batch: PreRequest must index the hashes of the LAST batch
+        outs = [torch.zeros((w.R, 32), dtype=torch.uint8, device="cuda") for _ in range(4)]
+        dts = [torch.roll(dt, shifts=7 * i, dims=0) for i in range(4)]
+        torch.cuda.synchronize()
+        for i in range(4):
+            eng.schedule(dts[i], uniform_len=w.prompt_bytes, detail=False, out=outs[i], asynchronous=True)
+        eng.synchronize()
+        for i in range(4):
+            np.testing.assert_array_equal(epp.decisions_from_torch(outs[i]), np.roll(want, 7 * i))
         # ragged offsets through the same path
         offs = torch.arange(w.R + 1, dtype=torch.int64, device="cuda") * w.prompt_bytes
         out.zero_()

@@ -12,13 +12,12 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def main():
     import torch
     import epp_b200 as epp
-    import helpers
+    from tools import workload_setup as helpers
     from tools import tracegen as tg
     w = tg.baseline_configs()["config3"].scaled(R=16384, name="config3")
     trace = tg.Trace(w)
