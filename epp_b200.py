@@ -22,3 +22,4 @@ DECISION_DTYPE = _pkg.DECISION_DTYPE
 DETAIL_DTYPE = _pkg.DETAIL_DTYPE
 SHARD_BEST_DTYPE = _pkg.SHARD_BEST_DTYPE
 decisions_from_torch = _pkg.decisions_from_torch
+Batcher = _pkg.Batcher

@@ -28,9 +28,17 @@
  * all R requests against ONE frozen snapshot (pool state + prefix index).  Index updates (PreRequest)
  * are applied between batches.
  *
- * Tie rule: the reference's max-score picker returns a uniformly random member of the arg-max set
- * (picker/maxscore/picker.go:91-102).  The engine returns the LOWEST slot id of that set, the bit pattern
- * of the max score and the size of the set.
+ * Tie rule: the reference's max-score picker shuffles with math/rand before its stable sort, i.e. it returns a
+ * uniformly random member of the arg-max set (picker/maxscore/picker.go:91-102).  The engine always returns the bit
+ * pattern of the max score and the size of the set, and as the pick
+ *   epp_config.tie_seed == 0: the LOWEST slot id of the set (deterministic; what the parity tests compare), or
+ *   epp_config.tie_seed != 0: the member of rank ((mix64(tie_seed ^ mix64(key)) >> 32) * |set|) >> 32 of the set in
+ *       ascending slot order, mix64 = the SplitMix64 output function, key = 4 * (ordinal of the request since the
+ *       engine was created = epp_stats.n_decisions before the call + index in the batch) + profile index (0 primary /
+ *       decode, 1 prefill, 2 encode): uniform over the set like the reference, reproducible by the oracle
+ *       (oracle/epp_oracle.c: orc_tie_rank).  Without it every tied request of a batch (cold prompts on a balanced
+ *       pool) would land on the same endpoint.  The P/D decider reads the match count of the member picked, as the
+ *       reference does (disagg_profile_handler.go:300).  Endpoint-sharded mode always uses the lowest slot.
  */
 #ifndef EPP_ENGINE_H
 #define EPP_ENGINE_H
@@ -48,7 +56,7 @@ extern "C" {
 #define EPP_API
 #endif
 
-#define EPP_ABI_VERSION 3
+#define EPP_ABI_VERSION 4
 #define EPP_MAX_SCORERS 8
 #define EPP_NO_ENDPOINT 0xFFFFFFFFu
 
@@ -138,10 +146,16 @@ typedef struct {
     int32_t always_disagg;         /* always-disagg-pd-decider (always_disagg_pd_decider.go:48-50)        */
     int64_t non_cached_tokens;     /* prefix-based-pd-decider nonCachedTokens (0 disables)               */
     int32_t n_ext_cols;            /* number of EPP_SCORER_EXTERNAL columns                              */
-    int32_t reserved0;
+    int32_t pick_k;                /* max-score-picker maxNumOfEndpoints (picker/common.go:36, maxscore/picker.go:104-115);
+                                      0 or 1 = one endpoint; > 1: epp_schedule_topk returns the k best                */
     epp_profile_cfg primary;       /* the single profile, or the decode profile under EPP_HANDLER_DISAGG */
     epp_profile_cfg prefill;       /* the prefill profile (EPP_HANDLER_DISAGG only)                      */
-    uint64_t reserved1[4];
+    epp_profile_cfg encode;        /* the encode profile (EPP_HANDLER_DISAGG with encode_enabled != 0):
+                                      disagg_profile_handler.go:284-295                                   */
+    uint64_t tie_seed;             /* 0 = lowest slot of the arg-max set; else the reproducible random tie rule above */
+    int32_t encode_enabled;        /* an "encode" profile + always-disagg-multimodal-decider are configured */
+    int32_t reserved0;
+    uint64_t reserved1[2];
 } epp_config;
 
 /* One routing decision (32 bytes).  status: 0 = ok, -1 = no endpoint available for the primary profile
@@ -156,16 +170,26 @@ typedef struct {
     int32_t match_blocks;      /* PrefixCacheMatchInfo.matchBlocks of the primary pick              */
 } epp_decision;
 
-/* Optional second record per decision (16 bytes), for tests and metrics. */
+/* Optional second record per decision (40 bytes): the other stages of the disagg handler, for the shim's
+ * SchedulingResult.ProfileResults, tests and metrics. */
 typedef struct {
     double prefill_score;
     uint32_t prefill_tie_count;
-    uint32_t prefill_ran;      /* the decider asked for the prefill stage                            */
+    uint32_t prefill_ran;      /* the P/D decider asked for the prefill stage                        */
+    double encode_score;
+    uint32_t encode_pick;      /* encode pick, EPP_NO_ENDPOINT when the stage did not run / found nobody */
+    uint32_t encode_tie_count;
+    uint32_t encode_ran;       /* the encode decider asked for the encode stage (multimodal request) */
+    uint32_t reserved;
 } epp_decision_detail;
 
 #define EPP_BATCH_DEVICE_PTRS 1u   /* data / offsets / model_ids and all outputs are DEVICE pointers */
 #define EPP_BATCH_ASYNC 2u         /* epp_schedule + DEVICE_PTRS: enqueue and return; outputs (and epp_stats.last_*)
                                     * are complete after epp_synchronize().  Batches enqueue in call order.       */
+#define EPP_BATCH_LENGTHS_EXCEED_ROWS 4u /* lengths[r] may exceed the row offsets[r+1] - offsets[r]: a row then holds only the
+                                    * first min(lengths[r], max_prefix_blocks * block_size_tokens * 4) bytes of its prompt --
+                                    * everything hashPrompt reads (hashing.go:63-66) -- while lengths[r] stays the prompt's
+                                    * true length (input of the P/D decider).  Saves shipping the tail of long prompts.  */
 
 /* A batch of prompts.  Prompt r is data[offsets[r] .. offsets[r+1]) (bytes), or data[offsets[r] .. offsets[r] +
  * lengths[r]) when `lengths` is given (lets ragged prompts START on 32-byte boundaries, which selects the 256-bit-load
@@ -180,6 +204,8 @@ typedef struct {
     uint32_t flags;                /* EPP_BATCH_* */
     uint32_t reserved;
     const uint64_t *lengths;       /* [n_requests] or NULL */
+    const uint8_t *multimodal;     /* [n_requests] or NULL: != 0 = the request carries image / video / audio content blocks
+                                      (hasMultimodalContent, disagg/multimodal_helpers.go): input of the encode decider */
 } epp_batch;
 
 typedef struct {
@@ -325,6 +351,40 @@ EPP_API int32_t epp_shard_merge(epp_engine *h, int64_t n_requests, int32_t n_ran
 EPP_API int32_t epp_shard_p2p_export(epp_engine *h, int64_t max_requests, uint8_t *out_handle, uint64_t *out_ptr);
 EPP_API int32_t epp_shard_p2p_connect(epp_engine *h, int32_t n_ranks, int32_t rank, const void *peers, int32_t ipc_handles);
 EPP_API int32_t epp_shard_schedule_p2p(epp_engine *h, const epp_batch *batch, epp_decision *out);
+
+/* The configuration the engine was created with. */
+EPP_API int32_t epp_get_config(epp_engine *h, epp_config *out);
+
+/* ---- micro-batcher: one request in, one decision out ------------------------------------------
+ * The reference calls Scheduler.Schedule(ctx, *InferenceRequest, []Endpoint) once per in-flight request, from one
+ * goroutine each (requestcontrol/director.go:69-71, 243; handlers/server.go:168).  epp_submit / epp_wait give a shim
+ * exactly that shape: any number of threads submit single prompts; a flusher thread inside the library closes a batch
+ * when it holds max_batch requests or its oldest request has waited max_delay_us, evaluates it against ONE frozen
+ * snapshot (epp_schedule) and -- with index_picks -- applies PreRequest (epp_index_add_picked,
+ * approximateprefix/plugin.go:164-200) before the next batch; epp_wait blocks until the ticket's batch is done.
+ * A batcher must be destroyed before its engine; other threads may keep calling epp_pool_set etc. on the engine
+ * (the scrape loop) -- every flush sees the snapshot current at its start. */
+typedef struct epp_batcher epp_batcher;
+typedef struct {
+    uint32_t struct_size;
+    int32_t max_batch;             /* requests per flush at most                                          */
+    int32_t max_delay_us;          /* a batch closes when its oldest request has waited this long (0 = flush at once) */
+    int32_t index_picks;           /* != 0: PreRequest after every flush (the picks' prefix hashes enter the index) */
+} epp_batcher_cfg;
+typedef struct {
+    uint64_t n_flushes, n_requests, n_full_flushes, n_pending;
+} epp_batcher_stats_t;
+EPP_API int32_t epp_batcher_create(epp_engine *h, const epp_batcher_cfg *cfg, epp_batcher **out);
+EPP_API int32_t epp_batcher_destroy(epp_batcher *b);     /* flushes what is pending, then stops the flusher   */
+/* prompt: the request's bytes (a uint32 token array = 4 bytes per token, hashing.go:49), copied before the call returns
+ * (only the first max_prefix_blocks blocks are kept); multimodal: hasMultimodalContent (encode decider).  Each ticket is
+ * good for ONE epp_wait; a batch's results are dropped when all its tickets were served, or 4096 flushes later.
+ * Every epp_wait must have returned before epp_batcher_destroy. */
+EPP_API int32_t epp_submit(epp_batcher *b, uint32_t model_id, const void *prompt, uint64_t prompt_len,
+                           uint32_t multimodal, uint64_t *out_ticket);
+EPP_API int32_t epp_wait(epp_batcher *b, uint64_t ticket, epp_decision *out, epp_decision_detail *out_detail);
+EPP_API int32_t epp_batcher_stats(epp_batcher *b, epp_batcher_stats_t *out);
+EPP_API const char *epp_batcher_last_error(void);
 
 #ifdef __cplusplus
 }

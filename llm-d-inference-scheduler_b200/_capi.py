@@ -13,6 +13,7 @@ EPP_MAX_SCORERS = 8
 EPP_NO_ENDPOINT = 0xFFFFFFFF
 EPP_BATCH_DEVICE_PTRS = 1
 EPP_BATCH_ASYNC = 2
+EPP_BATCH_LENGTHS_EXCEED_ROWS = 4
 
 EPP_OK, EPP_ERR_INVALID, EPP_ERR_CUDA, EPP_ERR_NO_DEVICE, EPP_ERR_CAPACITY, EPP_ERR_STATE, EPP_ERR_NCCL = \
     0, -1, -2, -3, -4, -5, -6
@@ -37,8 +38,9 @@ class Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("max_endpoints", C.c_int32),
                 ("block_size_tokens", C.c_int32), ("max_prefix_blocks", C.c_int32),
                 ("lru_capacity_per_server", C.c_int32), ("handler", C.c_int32), ("always_disagg", C.c_int32),
-                ("non_cached_tokens", C.c_int64), ("n_ext_cols", C.c_int32), ("reserved0", C.c_int32),
-                ("primary", ProfileCfg), ("prefill", ProfileCfg), ("reserved1", C.c_uint64 * 4)]
+                ("non_cached_tokens", C.c_int64), ("n_ext_cols", C.c_int32), ("pick_k", C.c_int32),
+                ("primary", ProfileCfg), ("prefill", ProfileCfg), ("encode", ProfileCfg), ("tie_seed", C.c_uint64),
+                ("encode_enabled", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_uint64 * 2)]
 
 
 class Decision(C.Structure):
@@ -47,13 +49,15 @@ class Decision(C.Structure):
 
 
 class DecisionDetail(C.Structure):
-    _fields_ = [("prefill_score", C.c_double), ("prefill_tie_count", C.c_uint32), ("prefill_ran", C.c_uint32)]
+    _fields_ = [("prefill_score", C.c_double), ("prefill_tie_count", C.c_uint32), ("prefill_ran", C.c_uint32),
+                ("encode_score", C.c_double), ("encode_pick", C.c_uint32), ("encode_tie_count", C.c_uint32),
+                ("encode_ran", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class Batch(C.Structure):
     _fields_ = [("n_requests", C.c_int64), ("data", C.c_void_p), ("offsets", C.c_void_p),
                 ("uniform_len", C.c_uint64), ("model_ids", C.c_void_p), ("flags", C.c_uint32),
-                ("reserved", C.c_uint32), ("lengths", C.c_void_p)]
+                ("reserved", C.c_uint32), ("lengths", C.c_void_p), ("multimodal", C.c_void_p)]
 
 
 class Stats(C.Structure):
@@ -66,12 +70,22 @@ class Stats(C.Structure):
                 ("last_index_items", C.c_uint64), ("last_index_launches", C.c_uint64), ("last_index_patched", C.c_uint64)]
 
 
+class BatcherCfg(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("max_batch", C.c_int32), ("max_delay_us", C.c_int32),
+                ("index_picks", C.c_int32)]
+
+
+class BatcherStats(C.Structure):
+    _fields_ = [("n_flushes", C.c_uint64), ("n_requests", C.c_uint64), ("n_full_flushes", C.c_uint64),
+                ("n_pending", C.c_uint64)]
+
+
 class ShardBest(C.Structure):
     _fields_ = [("score", C.c_double), ("pick", C.c_uint32), ("tie_count", C.c_uint32),
                 ("match_blocks", C.c_int32), ("status", C.c_int32)]
 
 
-assert C.sizeof(Decision) == 32 and C.sizeof(DecisionDetail) == 16 and C.sizeof(ShardBest) == 24
+assert C.sizeof(Decision) == 32 and C.sizeof(DecisionDetail) == 40 and C.sizeof(ShardBest) == 24
 
 # name -> (restype, argtypes): every symbol include/epp_engine.h declares
 SIGNATURES = {
@@ -114,6 +128,13 @@ SIGNATURES = {
     "epp_shard_p2p_export": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_uint64)]),
     "epp_shard_p2p_connect": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "epp_shard_schedule_p2p": (C.c_int32, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
+    "epp_get_config": (C.c_int32, [C.c_void_p, C.POINTER(Config)]),
+    "epp_batcher_create": (C.c_int32, [C.c_void_p, C.POINTER(BatcherCfg), C.POINTER(C.c_void_p)]),
+    "epp_batcher_destroy": (C.c_int32, [C.c_void_p]),
+    "epp_submit": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "epp_wait": (C.c_int32, [C.c_void_p, C.c_uint64, C.POINTER(Decision), C.POINTER(DecisionDetail)]),
+    "epp_batcher_stats": (C.c_int32, [C.c_void_p, C.POINTER(BatcherStats)]),
+    "epp_batcher_last_error": (C.c_char_p, []),
 }
 
 _lib = None

@@ -68,7 +68,8 @@ struct Slot {                       // per-stream staging for host-pointer batch
 struct epp_engine {
     std::mutex mu;
     epp_config cfg;
-    int n_profiles = 1;
+    int n_profiles = 1;             // profiles of the P/D handler: 1 (single) or 2 (decode + prefill)
+    int n_alloc_profiles = 1;       // + the encode profile ([2]) when configured
     int sm_count = 148;
     int32_t Epad = 0;
     size_t dev_bytes = 0;
@@ -117,12 +118,12 @@ struct epp_engine {
     uint32_t shard_begin = 0, shard_end = 0xFFFFFFFFu;
 
     // batch buffers (sized for the largest batch seen)
-    DevBuf offsets, lengths, model_ids, hashes, nblocks, eff_len, in_len, decisions, details, flag;
+    DevBuf offsets, lengths, model_ids, multimodal, hashes, nblocks, eff_len, in_len, decisions, details, flag;
     DevBuf dense_match, dense_total, dense_scores;
     int index_load = 0;             // EPP_INDEX_LOAD=n: read-table slots per distinct hash (2 = load factor <= 0.5, 4 = <= 0.25);
                                     // 0 = automatic: 4 while the table stays L2-sized (<= 48 MiB), else 2
     int dev_chunks = 2;             // EPP_DEV_CHUNKS=N: async device batches run as N chunks over both streams (1 = off)
-    int staged = 0;                 // EPP_HASH_STAGED: hash_staged.cu kernel: -1 off (hash_fused.cu), 0 default shape, else a shape
+    int staged = 0;                 // EPP_HASH_STAGED: 0 = hash_fused.cu (default), 1 = hash_staged.cu default shape, else a shape
     int pick_grid = 0;
     bool pick_global = false;
     size_t pick_smem = 0;
@@ -222,6 +223,11 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
     if (cfg->non_cached_tokens < 0) return fail(EPP_ERR_INVALID, "non_cached_tokens must be >= 0");
     EPP_TRY(validate_profile(cfg->primary, cfg->n_ext_cols, "primary profile"));
     if (cfg->handler == EPP_HANDLER_DISAGG) EPP_TRY(validate_profile(cfg->prefill, cfg->n_ext_cols, "prefill profile"));
+    if (cfg->encode_enabled) {
+        if (cfg->handler != EPP_HANDLER_DISAGG) return fail(EPP_ERR_INVALID, "encode_enabled needs the disagg handler");
+        EPP_TRY(validate_profile(cfg->encode, cfg->n_ext_cols, "encode profile"));
+    }
+    if (cfg->pick_k < 0 || cfg->pick_k > 64) return fail(EPP_ERR_INVALID, "pick_k %d out of range [0,64]", cfg->pick_k);
 
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -232,6 +238,7 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
     std::unique_ptr<epp_engine> e(new epp_engine());
     e->cfg = *cfg;
     e->n_profiles = cfg->handler == EPP_HANDLER_DISAGG ? 2 : 1;
+    e->n_alloc_profiles = cfg->encode_enabled ? 3 : e->n_profiles;
     CUDA_TRY(cudaSetDevice(cfg->device));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
@@ -255,7 +262,7 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
     CUDA_TRY(e->waiting.reserve(sizeof(int32_t) * E, &e->dev_bytes));
     CUDA_TRY(e->running.reserve(sizeof(int32_t) * E, &e->dev_bytes));
     if (cfg->n_ext_cols) CUDA_TRY(e->ext.reserve(sizeof(double) * E * (size_t)cfg->n_ext_cols, &e->dev_bytes));
-    for (int p = 0; p < e->n_profiles; p++) EPP_TRY(alloc_profile(e.get(), e->prof[p]));
+    for (int p = 0; p < e->n_alloc_profiles; p++) EPP_TRY(alloc_profile(e.get(), e->prof[p]));
     CUDA_TRY(e->idx_cursor.reserve(sizeof(uint32_t) * 4, &e->dev_bytes));
     CUDA_TRY(e->idx_special.reserve(sizeof(IndexSlot), &e->dev_bytes));
     CUDA_TRY(e->get_out.reserve(sizeof(uint32_t) * 4096 + 16, &e->dev_bytes));
@@ -263,8 +270,8 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
     CUDA_TRY(e->work_counters.reserve(sizeof(unsigned long long) * 2, &e->dev_bytes));
     memset(&e->idx_special_host, 0, sizeof(IndexSlot));
     e->idx_special_host.key = kEmptyKey;
-    for (int pi = 0; pi < (cfg->handler == EPP_HANDLER_DISAGG ? 2 : 1); pi++) {
-        const epp_profile_cfg &pc = pi == 0 ? cfg->primary : cfg->prefill;
+    for (int pi = 0; pi < e->n_alloc_profiles; pi++) {
+        const epp_profile_cfg &pc = pi == 0 ? cfg->primary : (pi == 1 ? cfg->prefill : cfg->encode);
         for (int si = 0; si < pc.n_scorers; si++) if (pc.scorers[si].kind == EPP_SCORER_LORA_AFFINITY) e->lora_enabled = true;
     }
     e->store.reset(new IndexStore((uint32_t)cfg->max_endpoints, cfg->lru_capacity_per_server));
@@ -388,7 +395,7 @@ static PoolArrays pool_arrays(epp_engine *h) {
 
 static ProfileDev profile_dev(epp_engine *h, int p) {
     ProfileDev pd;
-    pd.cfg = p == 0 ? h->cfg.primary : h->cfg.prefill;
+    pd.cfg = p == 0 ? h->cfg.primary : (p == 1 ? h->cfg.prefill : h->cfg.encode);
     pd.cand = h->prof[p].cand.as<uint8_t>();
     pd.contrib = h->prof[p].contrib.as<double>();
     pd.base = h->prof[p].base.as<double>();
@@ -403,7 +410,7 @@ static int32_t derive_pool(epp_engine *h) {
     cudaStream_t s = h->slot[0].stream;
     PoolArrays pa = pool_arrays(h);
     int launches = 0;
-    for (int p = 0; p < h->n_profiles; p++) {
+    for (int p = 0; p < h->n_alloc_profiles; p++) {
         ProfileDerived d;
         d.cand = h->prof[p].cand.as<uint8_t>();
         d.contrib = h->prof[p].contrib.as<double>();
@@ -413,7 +420,7 @@ static int32_t derive_pool(epp_engine *h) {
         d.sort_key = h->prof[p].sort_key.as<uint64_t>();
         d.n_cand = h->prof[p].n_cand.as<int32_t>();
         d.qminmax = h->prof[p].qminmax.as<int64_t>();
-        CUDA_TRY(launch_pool_prepare(pa, p == 0 ? h->cfg.primary : h->cfg.prefill, d, h->Epad, h->shard_begin, h->shard_end, s, &launches));
+        CUDA_TRY(launch_pool_prepare(pa, p == 0 ? h->cfg.primary : (p == 1 ? h->cfg.prefill : h->cfg.encode), d, h->Epad, h->shard_begin, h->shard_end, s, &launches));
     }
     return EPP_OK;
 }
@@ -782,6 +789,7 @@ struct BatchView {
     const uint64_t *lengths = nullptr;
     uint64_t uniform_len = 0;
     const uint32_t *model_ids = nullptr;
+    const uint8_t *multimodal = nullptr;
     uint64_t total_bytes = 0;      // host batches only
     uint64_t offsets_or_bits = 0;
 };
@@ -800,6 +808,7 @@ static int32_t check_batch(epp_engine *h, const epp_batch *b, BatchView &v) {
     if (v.lengths && !v.offsets) return fail(EPP_ERR_INVALID, "lengths needs offsets");
     v.uniform_len = b->uniform_len;
     v.model_ids = b->model_ids;
+    v.multimodal = b->multimodal;
     if (v.R == 0) return EPP_OK;
     if (!v.offsets && v.uniform_len > 0 && !v.data) return fail(EPP_ERR_INVALID, "data is NULL");
     if (!v.device) {
@@ -807,7 +816,13 @@ static int32_t check_batch(epp_engine *h, const epp_batch *b, BatchView &v) {
             uint64_t bits = 0;
             for (int64_t r = 0; r < v.R; r++) {
                 if (v.offsets[r + 1] < v.offsets[r]) return fail(EPP_ERR_INVALID, "offsets not monotonic at request %lld", (long long)r);
-                if (v.lengths && v.offsets[r] + v.lengths[r] > v.offsets[r + 1]) return fail(EPP_ERR_INVALID, "request %lld: offsets[r] + lengths[r] exceeds offsets[r+1]", (long long)r);
+                if (v.lengths && v.offsets[r] + v.lengths[r] > v.offsets[r + 1]) {
+                    // EPP_BATCH_LENGTHS_EXCEED_ROWS: the row must still hold every byte hashPrompt reads
+                    const uint64_t cap = (uint64_t)h->cfg.max_prefix_blocks * (uint64_t)h->cfg.block_size_tokens * 4;
+                    const uint64_t need = std::min<uint64_t>(v.lengths[r], cap);
+                    if (!(b->flags & EPP_BATCH_LENGTHS_EXCEED_ROWS) || v.offsets[r] + need > v.offsets[r + 1])
+                        return fail(EPP_ERR_INVALID, "request %lld: offsets[r] + lengths[r] exceeds offsets[r+1]", (long long)r);
+                }
                 bits |= v.offsets[r];
             }
             v.offsets_or_bits = bits;
@@ -850,6 +865,7 @@ struct Work {
     uint64_t offsets_or_bits;      // OR of all offsets (alignment of the batch layout)
     uint64_t *hashes_out;          // row r0 of the destination
     int32_t *nblocks_out;
+    const uint8_t *multimodal_dev = nullptr;   // absolute, or nullptr
 };
 
 static HashParams hash_params(epp_engine *h, const Work &w) {
@@ -882,9 +898,13 @@ static PickParams pick_params(epp_engine *h, const Work &w, epp_decision *out, e
     p.max_blocks = h->cfg.max_prefix_blocks;
     p.block_size_tokens = h->cfg.block_size_tokens;
     p.n_profiles = h->n_profiles;
+    p.encode_on = h->cfg.encode_enabled ? 1 : 0;
+    p.multimodal = w.multimodal_dev ? w.multimodal_dev + w.r0 : nullptr;
     p.always_disagg = h->cfg.always_disagg;
     p.non_cached_tokens = h->cfg.non_cached_tokens;
-    for (int i = 0; i < h->n_profiles; i++) p.prof[i] = profile_dev(h, i);
+    for (int i = 0; i < h->n_alloc_profiles; i++) p.prof[i] = profile_dev(h, i);
+    p.tie_seed = h->shard_end != 0xFFFFFFFFu || h->shard_begin != 0 ? 0 : h->cfg.tie_seed;      // sharded mode: lowest slot
+    p.tie_base = h->stats.n_decisions + (uint64_t)w.r0;
     p.hashes = w.hashes_out;
     p.nblocks = w.nblocks_out;
     p.in_len = h->in_len.as<int64_t>() + w.r0;
@@ -997,7 +1017,8 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
         if (v.offsets) EPP_TRY(device_offsets_or_bits(h, v.offsets, R, s0, &or_bits));
         Work w{0, R, v.data, v.offsets, v.lengths, v.uniform_len, v.model_ids, or_bits,
                (mode == Mode::HashOnly && out_hashes) ? out_hashes : h->hashes.as<uint64_t>(),
-               (mode == Mode::HashOnly && out_nblocks) ? out_nblocks : (mode == Mode::Match && out_total ? out_total : h->nblocks.as<int32_t>())};
+               (mode == Mode::HashOnly && out_nblocks) ? out_nblocks : (mode == Mode::Match && out_total ? out_total : h->nblocks.as<int32_t>()),
+               v.multimodal};
         CUDA_TRY(cudaMemsetAsync(h->work_counters.p, 0, sizeof(unsigned long long) * 2, s0));
         const int64_t min_chunk = 4096;
         if (pipelined) {
@@ -1019,7 +1040,7 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
             for (int64_t r0 = 0; r0 < R; r0 += per, k++) {
                 const int64_t r1 = std::min(R, r0 + per);
                 Work w{r0, r1, v.offsets ? v.data : v.data + (uint64_t)r0 * v.uniform_len, v.offsets, v.lengths, v.uniform_len,
-                       v.model_ids, or_bits, h->hashes.as<uint64_t>() + (size_t)r0 * B, h->nblocks.as<int32_t>() + r0};
+                       v.model_ids, or_bits, h->hashes.as<uint64_t>() + (size_t)r0 * B, h->nblocks.as<int32_t>() + r0, v.multimodal};
                 PickParams pp = pick_params(h, w, dec_base + r0, out_detail ? out_detail + r0 : nullptr, nullptr);
                 Slot &sl = h->slot[k & 1];
                 EPP_TRY(launch_cycle(h, sl, hash_params(h, w), pp, &launches, nullptr));
@@ -1047,6 +1068,10 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
     if (v.offsets) CUDA_TRY(cudaMemcpyAsync(h->offsets.p, v.offsets, sizeof(uint64_t) * (size_t)(R + 1), cudaMemcpyHostToDevice, s0));
     if (v.lengths) CUDA_TRY(cudaMemcpyAsync(h->lengths.p, v.lengths, sizeof(uint64_t) * (size_t)R, cudaMemcpyHostToDevice, s0));
     if (v.model_ids) CUDA_TRY(cudaMemcpyAsync(h->model_ids.p, v.model_ids, sizeof(uint32_t) * (size_t)R, cudaMemcpyHostToDevice, s0));
+    if (v.multimodal) {
+        CUDA_TRY(h->multimodal.reserve((size_t)R, &h->dev_bytes));
+        CUDA_TRY(cudaMemcpyAsync(h->multimodal.p, v.multimodal, (size_t)R, cudaMemcpyHostToDevice, s0));
+    }
     CUDA_TRY(cudaEventRecord(h->slot[0].done, s0));
     CUDA_TRY(cudaStreamWaitEvent(h->slot[1].stream, h->slot[0].done, 0));
 
@@ -1102,6 +1127,7 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
         }
         w.uniform_len = v.uniform_len;
         w.model_ids_dev = v.model_ids ? h->model_ids.as<uint32_t>() : nullptr;
+        w.multimodal_dev = v.multimodal ? h->multimodal.as<uint8_t>() : nullptr;
         w.hashes_out = h->hashes.as<uint64_t>() + (size_t)c.r0 * B;
         w.nblocks_out = h->nblocks.as<int32_t>() + c.r0;
         if (mode == Mode::HashOnly) {
@@ -1163,6 +1189,7 @@ extern "C" int32_t epp_schedule(epp_engine *h, const epp_batch *batch, epp_decis
     EPP_TRY(set_device(h));
     BatchView v;
     EPP_TRY(check_batch(h, batch, v));
+    if (h->cfg.encode_enabled && v.multimodal && !detail) return fail(EPP_ERR_INVALID, "an encode profile is configured and the batch flags multimodal requests: `detail` (which carries the encode pick) must not be NULL");
     h->kept_R = 0;
     EPP_TRY(run_batch(h, v, Mode::Schedule, nullptr, nullptr, out, detail, nullptr, nullptr));
     h->stats.n_batches++;
@@ -1210,8 +1237,8 @@ extern "C" int32_t epp_score(epp_engine *h, int64_t n_requests, const int32_t *m
     EPP_TRY(set_device(h));
     EPP_TRY(join_streams(h));
     if (!h->pool_ready) return fail(EPP_ERR_STATE, "epp_pool_set has not been called");
-    if (profile < 0 || profile >= h->n_profiles) return fail(EPP_ERR_INVALID, "profile %d out of range", profile);
-    const epp_profile_cfg &pc = profile == 0 ? h->cfg.primary : h->cfg.prefill;
+    if (profile < 0 || profile >= h->n_alloc_profiles) return fail(EPP_ERR_INVALID, "profile %d out of range", profile);
+    const epp_profile_cfg &pc = profile == 0 ? h->cfg.primary : (profile == 1 ? h->cfg.prefill : h->cfg.encode);
     if (scorer_index < -1 || scorer_index >= pc.n_scorers) return fail(EPP_ERR_INVALID, "scorer_index %d out of range", scorer_index);
     if (n_requests == 0) return EPP_OK;
     const size_t E = (size_t)h->cfg.max_endpoints, n = (size_t)n_requests * E;
@@ -1260,11 +1287,15 @@ extern "C" int32_t epp_schedule_with_match(epp_engine *h, int64_t n_requests, co
     p.E = h->cfg.max_endpoints;
     p.block_size_tokens = block_size_tokens > 0 ? block_size_tokens : h->cfg.block_size_tokens;
     p.n_profiles = h->n_profiles;
+    p.encode_on = 0;                              // the injected-match entry point has no multimodal flags
+    p.multimodal = nullptr;
     p.always_disagg = h->cfg.always_disagg;
     p.non_cached_tokens = h->cfg.non_cached_tokens;
-    for (int i = 0; i < h->n_profiles; i++) p.prof[i] = profile_dev(h, i);
+    for (int i = 0; i < h->n_alloc_profiles; i++) p.prof[i] = profile_dev(h, i);
     p.lora = lora_dev(h);
     p.model_ids = model_ids;
+    p.tie_seed = h->cfg.tie_seed;
+    p.tie_base = h->stats.n_decisions;
     if (dev) {
         p.match = match; p.total = total; p.in_len = input_len_bytes; p.out = out; p.detail = detail;
     } else {
@@ -1294,6 +1325,14 @@ extern "C" int32_t epp_schedule_with_match(epp_engine *h, int64_t n_requests, co
     }
     CUDA_TRY(cudaStreamSynchronize(s));
     h->kept_R = 0;
+    h->stats.n_decisions += (uint64_t)n_requests;          // request ordinals (tie rule) advance here too
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_get_config(epp_engine *h, epp_config *out) {
+    if (!h || !out) return fail(EPP_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    *out = h->cfg;
     return EPP_OK;
 }
 

@@ -1,7 +1,7 @@
 // hash_kernels.cu -- a1: batched chained XXH64 prefix-block hashing (approximateprefix/hashing.go:35-99): the dispatcher
 // and the generic path.
-//   launch_hash_prompts : 64-byte blocks + 16-byte aligned prompts (every BASELINE config) -> hash_staged.cu;
-//                         other block sizes that are a multiple of 32 bytes, aligned -> hash_fused.cu;
+//   launch_hash_prompts : block sizes that are a multiple of 32 bytes + 16-byte aligned prompts (every BASELINE
+//                         config) -> hash_fused.cu (or, EPP_HASH_STAGED=1 and 64-byte blocks, hash_staged.cu);
 //                         anything else -> the two kernels below
 //   k_prompt_lengths    : per request, truncation + block count                     (hashing.go:58-66)
 //   k_hash_generic      : any block size / alignment, one thread per request, fully serial
@@ -116,7 +116,7 @@ cudaError_t launch_hash_prompts(const HashParams &p, cudaStream_t s, int *launch
     if (align >= 16) {                          // one kernel: lengths + digests + chain
         if (ev) { cudaEventRecord(ev[0], s); cudaEventRecord(ev[1], s); }
         cudaError_t e;
-        if (p.staged >= 0 && hash_staged_supported(p)) e = launch_hash_staged(p, p.staged, s, launches);
+        if (p.staged > 0 && hash_staged_supported(p)) e = launch_hash_staged(p, p.staged, s, launches);
         else e = launch_hash_fused(p, align, p.sm_count, s, launches);
         if (ev) { cudaEventRecord(ev[2], s); cudaEventRecord(ev[3], s); }
         return e;

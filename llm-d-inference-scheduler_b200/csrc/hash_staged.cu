@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(32 * WPC) k_hash_staged(HashParams p, int n_ta
 }
 
 
+
 namespace {
 template <int TR, int DS, int WPC>
 cudaError_t launch_shape(const HashParams &p, cudaStream_t s) {
@@ -216,7 +217,7 @@ bool hash_staged_supported(const HashParams &p) {
     return (bits & 15) == 0;
 }
 
-// shape: 0 = default; else requests per task * 100 + ring slots * 10 + warps per CTA (A/B runs).
+// shape: 1 = default (1644); else requests per task * 100 + ring slots * 10 + warps per CTA (A/B runs).
 cudaError_t launch_hash_staged(const HashParams &p, int shape, cudaStream_t s, int *launches) {
     if (p.R <= 0) return cudaSuccess;
     cudaError_t e;

@@ -26,7 +26,7 @@ struct HashParams {
     int64_t *in_len;            // [R] untruncated prompt length in bytes (P/D decider), may be nullptr
     uint64_t offsets_or_bits;   // OR of every offsets[r] (low bits decide the common alignment)
     int32_t sm_count;
-    int32_t staged;             // hash_staged.cu (cp.async-staged, warp-per-task) kernel: -1 off, 0 default shape, else a launch shape (A/B)
+    int32_t staged;             // hash_staged.cu (cp.async-staged, warp-per-task) kernel: 0 off, 1 default shape, else a launch shape (A/B)
 };
 // Common alignment (0, 16, 32) of every block start; >= 16 (and block_bytes % 32 == 0) enables the fused kernel.
 int hash_batch_alignment(const HashParams &p);
@@ -78,7 +78,7 @@ cudaError_t launch_index_get(const IndexView &ix, uint64_t hash, uint32_t *out_e
 // ------------------------------------------------------------------------------------------------
 // pool state -> request-independent scorer terms (a5-a9 precompute)
 // ------------------------------------------------------------------------------------------------
-constexpr int kMaxProfiles = 2;
+constexpr int kMaxProfiles = 3;            // [0] primary / decode, [1] prefill, [2] encode
 // LoRA adapter residency (fwkdl.Metrics.ActiveModels / WaitingModels / MaxActiveModels) for lora-affinity-scorer:
 // per endpoint the adapter capacity, per adapter (= registered model id) the endpoints where it is active (1) or
 // waiting (2), sorted by endpoint.  ptr == nullptr: no LoRA state (every endpoint scores 0.0 / its capacity tier).
@@ -134,6 +134,8 @@ struct PickParams {
     int32_t max_blocks;
     int32_t block_size_tokens;
     int32_t n_profiles;        // 1 or 2 (2 => disagg: [0]=decode, [1]=prefill)
+    int32_t encode_on;         // disagg with an encode profile ([2]): runs for requests flagged in `multimodal`
+    const uint8_t *multimodal; // [R] or nullptr (encode decider input: hasMultimodalContent)
     int32_t always_disagg;
     int64_t non_cached_tokens;
     ProfileDev prof[kMaxProfiles];
@@ -157,6 +159,9 @@ struct PickParams {
     // v2 (sparse) kernel only: requests whose matched-endpoint set overflowed the per-warp map are appended here
     int32_t *overflow_list;
     int32_t *overflow_n;
+    // tie rule: 0 = lowest slot of the arg-max set; else the member of rank tie_rank(seed, 4 * (tie_base + r) + profile)
+    uint64_t tie_seed;
+    uint64_t tie_base;         // ordinal of request 0 of this launch
 };
 // Fused lookup + match + score + pick, one warp per request.  Per-warp match counters live in shared memory
 // (smem = match_pick_smem_bytes(E, false)) or, when E is too large for that, in a zero-initialised global
@@ -174,6 +179,8 @@ struct DensePickParams {
     int32_t E;
     int32_t block_size_tokens;
     int32_t n_profiles;
+    int32_t encode_on;
+    const uint8_t *multimodal;
     int32_t always_disagg;
     int64_t non_cached_tokens;
     ProfileDev prof[kMaxProfiles];
@@ -184,6 +191,8 @@ struct DensePickParams {
     LoraDev lora;
     epp_decision *out;
     epp_decision_detail *detail;
+    uint64_t tie_seed;
+    uint64_t tie_base;
 };
 cudaError_t launch_dense_pick(const DensePickParams &p, cudaStream_t s, int *launches);
 // Scorer.Score parity: out[R][E].  scorer_index -1 => weighted ordered sum (-1.0 for non-candidates).

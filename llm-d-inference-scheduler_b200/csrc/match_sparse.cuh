@@ -7,8 +7,8 @@
 // warps of the fused cycle kernel (cycle.cu), which run it on the tile their CTA hashed just before.
 //
 //   * 32 blocks are probed per step, one 256-bit load per 32-byte slot.  Probe chains are followed only as far as the
-//     stop rule needs them: once a lane has proven its block absent, the lanes behind it stop probing (a cold prompt
-//     costs the probe chain of block 0, not the longest chain of 32 unrelated blocks);
+//     stop rule needs them: once a lane has proven its block absent, the lanes behind it (which cannot change the walk)
+//     stop probing -- a cold prompt costs the probe chain of block 0, not the longest chain of 32 unrelated blocks;
 //   * matched endpoints live in a LANE-DISTRIBUTED register map: lane j holds (endpoint E_j, count C_j), j <
 //     n_distinct <= 32; membership tests are ballots;
 //   * counting is run-length based: posting lists are sorted, duplicate-free and (when spilled) interned, and unused
@@ -61,11 +61,56 @@ __device__ __forceinline__ bool map_contains_any(const LaneMap &m, uint32_t e) {
     return hit;
 }
 
+// The member of rank k (ascending slot order) of the arg-max set S = A u U (see eval_profile_lanes): one lower bound
+// per A lane in parallel and, failing that, one warp-uniform binary search over the equal-base group G.  Rare path
+// (ties only): kept out of line so that it costs the common path no registers.
+__device__ __noinline__ uint32_t select_tied(const ProfileDev &pf, const LaneMap &m, int lane, bool in_a, bool in_x_all,
+                                             bool have_u, uint32_t gpos, uint32_t ue, uint32_t k) {
+    const bool in_x = in_x_all && have_u;
+    const uint32_t mask_a = __ballot_sync(kFull, in_a), mask_x = __ballot_sync(kFull, in_x);
+    // G = order[gs .. gs + gsz): the X members with a smaller slot than ue precede it inside the group
+    const uint32_t gs = have_u ? gpos - __popc(__ballot_sync(kFull, in_x && m.e < ue)) : 0u;
+    const uint32_t gsz = have_u ? pf.grp_size[gpos] : 0u;
+    uint32_t ca = 0, cx = 0;
+    for (uint32_t j = 0; j < m.n; j++) {
+        const uint32_t ej = __shfl_sync(kFull, m.e, (int)j);
+        ca += ((mask_a >> j) & 1u) && ej < m.e;
+        cx += ((mask_x >> j) & 1u) && ej < m.e;
+    }
+    uint32_t pos = 0;
+    if (in_a && have_u) {                          // lower bound of my slot in G
+        uint32_t lo = 0, hi = gsz;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (pf.order[gs + mid] < m.e) lo = mid + 1; else hi = mid;
+        }
+        pos = lo;
+    }
+    const uint32_t found = __ballot_sync(kFull, in_a && ca + pos - (have_u ? cx : 0u) == k);
+    if (found) return __shfl_sync(kFull, m.e, __ffs(found) - 1);
+    // the member is an unmatched entry of G: the largest position of rank <= k
+    uint32_t lo = 0, hi = gsz - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        const uint32_t x = pf.order[gs + mid];
+        const uint32_t f = mid - __popc(__ballot_sync(kFull, in_x && m.e < x)) + __popc(__ballot_sync(kFull, in_a && m.e < x));
+        if (f <= k) lo = mid; else hi = mid - 1;
+    }
+    return pf.order[gs + lo];
+}
+
 // One profile for the current request (SchedulerProfile.Run): matched candidates from the lane map, everyone else
 // from the precomputed (base desc, slot asc) order -- an unmatched endpoint's ordered weighted sum is bit-identical to
 // its precomputed base, so only the first unmatched entry of the order (and the size of its equal-base group) matters.
+// tie_seed != 0: the pick is the member of rank tie_rank(...) of the arg-max set in ascending slot order (score.cuh).
+// The set is S = A u U: A = matched candidates whose score is the maximum, U = the unmatched members of the equal-base
+// group G of the order (only when that base IS the maximum); X = matched candidates sitting inside G.  G is sorted by
+// slot, |A|, |X| <= 32: the rank of a slot x in S is #{a in A: a < x} + lower_bound_G(x) - #{x' in X: x' < x}, so the
+// member is found with one lower bound per A lane (in parallel) and, failing that, one warp-uniform binary search over G.
+template <bool kTie>
 __device__ __forceinline__ Best eval_profile_lanes(const ProfileDev &pf, int32_t E, const LaneMap &m, int32_t total,
-                                                   int lane, const LoraDev &lora, int lora_st) {
+                                                   int lane, const LoraDev &lora, int lora_st, uint64_t tie_seed,
+                                                   uint64_t tie_key) {
     Best b;
     best_init(b);
     const int32_t ncand = *pf.n_cand;
@@ -73,11 +118,20 @@ __device__ __forceinline__ Best eval_profile_lanes(const ProfileDev &pf, int32_t
     if (m.n == 0) {                                   // nobody holds a block of this prompt: the head of the order wins
         const uint32_t ue = pf.order[0];
         best_add(b, pf.base[ue], ue, pf.grp_size[0]);
+        if (kTie && tie_seed && b.ties > 1) b.pick = pf.order[tie_rank(tie_seed, tie_key, b.ties)];
         return b;
     }
     const bool mine = (uint32_t)lane < m.n && pf.cand[m.e];
-    if (mine) best_add(b, weighted_sum(pf, E, m.e, (int32_t)m.c, total, lora, lora_st), m.e);
+    double myv = 0.0;
+    if (mine) {
+        myv = weighted_sum(pf, E, m.e, (int32_t)m.c, total, lora, lora_st);
+        best_add(b, myv, m.e);
+    }
     b = best_warp_reduce(b);
+    bool have_u = false;
+    bool in_x = false;
+    uint32_t gpos = 0, ue = kNoKey;
+    double ubase = 0.0;
     for (int32_t k0 = 0; k0 < ncand; k0 += 32) {
         const int32_t k = k0 + lane;
         const uint32_t e = k < ncand ? pf.order[k] : kNoKey;
@@ -86,14 +140,20 @@ __device__ __forceinline__ Best eval_profile_lanes(const ProfileDev &pf, int32_t
         const uint32_t bal = __ballot_sync(kFull, un);
         if (bal) {
             const int first = __ffs(bal) - 1;
-            const uint32_t ue = __shfl_sync(kFull, e, first);
-            const double ubase = pf.base[ue];
-            const uint32_t gsz = pf.grp_size[k0 + first];
-            const uint32_t same = __popc(__ballot_sync(kFull, mine && pf.base[m.e] == ubase));
+            ue = __shfl_sync(kFull, e, first);
+            ubase = pf.base[ue];
+            gpos = (uint32_t)(k0 + first);
+            const uint32_t gsz = pf.grp_size[gpos];
+            in_x = mine && pf.base[m.e] == ubase;
+            const uint32_t same = __popc(__ballot_sync(kFull, in_x));
             best_add(b, ubase, ue, gsz - same);
+            have_u = true;
             break;
         }
     }
+    if (kTie && tie_seed && b.ties > 1)
+        b.pick = select_tied(pf, m, lane, mine && myv == b.val, in_x, have_u && ubase == b.val, gpos, ue,
+                             tie_rank(tie_seed, tie_key, b.ties));
     return b;
 }
 
@@ -153,7 +213,9 @@ struct Work {
 // The whole decision for request r (all 32 lanes of one warp call it together).  kCg: the per-request inputs
 // (hashes, nblocks, in_len) were produced earlier in the same kernel launch.
 // kSharded: endpoint-sharded mode (the stop rule comes from p.global_masks).
-template <bool kCg, bool kSharded>
+// kTie: the reproducible random tie rule is compiled in (epp_config.tie_seed != 0); the deterministic lowest-slot
+// build carries none of its code or registers.
+template <bool kCg, bool kSharded, bool kTie>
 __device__ __forceinline__ void match_request(const PickParams &p, const int64_t r, const int lane, const bool counting,
                                               Work &wk) {
     const uint32_t shard_lo = p.index.ep_begin, shard_hi = min(p.index.ep_end, (uint32_t)p.E);
@@ -189,6 +251,14 @@ __device__ __forceinline__ void match_request(const PickParams &p, const int64_t
         }
         uint32_t idx = (uint32_t)hcur & mask32;
         for (;;) {
+            const uint32_t pend0 = __ballot_sync(kFull, pending);
+            if (!pend0) break;
+            if (!kSharded) {
+                const uint32_t missm0 = __ballot_sync(kFull, valid && !pending && cnt == 0);
+                const uint32_t below0 = missm0 ? ((1u << (__ffs(missm0) - 1)) - 1u) : kFull;
+                if (!(pend0 & below0)) break;
+                if (!((below0 >> lane) & 1u)) pending = false;
+            }
             if (pending) {
                 uint64_t key;
                 Hit hs;
@@ -201,15 +271,6 @@ __device__ __forceinline__ void match_request(const PickParams &p, const int64_t
                 } else {
                     idx = (idx + 1) & mask32;
                 }
-            }
-            const uint32_t pend = __ballot_sync(kFull, pending);
-            if (!pend) break;
-            if (!kSharded) {
-                // lanes behind the first PROVEN miss cannot change the walk: they stop probing
-                const uint32_t missm = __ballot_sync(kFull, valid && !pending && cnt == 0);
-                const uint32_t below = missm ? ((1u << (__ffs(missm) - 1)) - 1u) : kFull;
-                if (!(pend & below)) break;
-                if (!((below >> lane) & 1u)) pending = false;
             }
         }
         // lanes that stopped early (pending) hold cnt == 0 and sit behind the stop
@@ -246,28 +307,12 @@ __device__ __forceinline__ void match_request(const PickParams &p, const int64_t
         if (lane == 0 && p.overflow_list) p.overflow_list[atomicAdd(p.overflow_n, 1)] = (int32_t)r;
         return;
     }
-    // ---- a5-a10: primary profile
-    const Best b0 = eval_profile_lanes(p.prof[0], p.E, m, total, lane, p.lora, lora_st);
+    // ---- a5-a14: the profiles of the handler
     epp_decision d;
-    d.status = b0.ties ? 0 : -1;
-    d.pick = b0.ties ? b0.pick : EPP_NO_ENDPOINT;
-    d.score = b0.ties ? b0.val : 0.0;
-    d.prefill_pick = EPP_NO_ENDPOINT;
-    d.tie_count = b0.ties;
-    d.total_blocks = total;
-    d.match_blocks = (b0.ties && m.n) ? (int32_t)map_get(m, b0.pick) : 0;
     epp_decision_detail dd;
-    dd.prefill_score = 0.0; dd.prefill_tie_count = 0; dd.prefill_ran = 0;
-    // ---- a13: decode -> decider -> prefill (disagg_profile_handler.go:264-308)
-    if (p.n_profiles == 2 && b0.ties) {
-        const bool go = p.always_disagg ||
-                        pd_decide(p.non_cached_tokens, ld_row<kCg>(p.in_len + r), d.match_blocks, p.block_size_tokens);
-        if (go) {
-            dd.prefill_ran = 1;
-            const Best b1 = eval_profile_lanes(p.prof[1], p.E, m, total, lane, p.lora, lora_st);
-            if (b1.ties) { d.prefill_pick = b1.pick; dd.prefill_score = b1.val; dd.prefill_tie_count = b1.ties; }
-        }
-    }
+    decide_stages(p, r, total, p.n_profiles >= 2 ? ld_row<kCg>(p.in_len + r) : 0,
+                  [&](int pi, uint64_t key) { return eval_profile_lanes<kTie>(p.prof[pi], p.E, m, total, lane, p.lora, lora_st, p.tie_seed, key); },
+                  [&](uint32_t e) { return m.n ? (int32_t)map_get(m, e) : 0; }, d, dd);
     if (lane == 0) {
         if (p.shard_out) {
             epp_shard_best sb;

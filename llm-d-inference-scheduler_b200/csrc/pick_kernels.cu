@@ -181,8 +181,27 @@ __device__ __forceinline__ uint32_t cnt_get(const uint32_t *cnt32, uint32_t e) {
 
 // Evaluate one profile for the current request.  cnt32 holds the per-endpoint match counts; list/nl the
 // distinct matched endpoints (nl > kListCap => overflow => dense scan).
+__device__ inline Best eval_profile_inner(const ProfileDev &pf, int32_t E, const uint32_t *cnt32, const uint32_t *list,
+                                          uint32_t nl, int32_t total, int lane, const LoraDev &lora, uint32_t adapter);
+
+// + the tie rule (score.cuh): the member of rank k of the arg-max set, found by one more scan over the slots
 __device__ inline Best eval_profile(const ProfileDev &pf, int32_t E, const uint32_t *cnt32, const uint32_t *list,
-                                    uint32_t nl, int32_t total, int lane, const LoraDev &lora, uint32_t adapter) {
+                                    uint32_t nl, int32_t total, int lane, const LoraDev &lora, uint32_t adapter,
+                                    uint64_t tie_seed, uint64_t tie_key) {
+    Best b = eval_profile_inner(pf, E, cnt32, list, nl, total, lane, lora, adapter);
+    if (tie_seed && b.ties > 1) {
+        const bool use_lora = lora.enabled && lora.ptr;
+        b.pick = select_kth_scan(pf, E, b.val, tie_rank(tie_seed, tie_key, b.ties), lane, [&](uint32_t e) {
+            const uint32_t c = cnt_get(cnt32, e);
+            if (use_lora) return weighted_sum(pf, E, e, (int32_t)c, total, lora, lora_lookup(lora, adapter, e));
+            return c ? weighted_sum(pf, E, e, (int32_t)c, total) : pf.base[e];
+        });
+    }
+    return b;
+}
+
+__device__ inline Best eval_profile_inner(const ProfileDev &pf, int32_t E, const uint32_t *cnt32, const uint32_t *list,
+                                          uint32_t nl, int32_t total, int lane, const LoraDev &lora, uint32_t adapter) {
     Best b;
     best_init(b);
     int32_t ncand = *pf.n_cand;
@@ -301,28 +320,13 @@ __global__ void __launch_bounds__(kPickWarps * 32) k_match_pick(PickParams p, in
         __syncwarp();
         const uint32_t nl = *list_n;
 
-        // ---- a5-a10: primary profile
+        // ---- a5-a14: the profiles of the handler
         const uint32_t adapter = p.model_ids ? p.model_ids[r] : 0u;
-        Best b0 = eval_profile(p.prof[0], p.E, cnt32, list, nl, total, lane, p.lora, adapter);
         epp_decision d;
-        d.status = b0.ties ? 0 : -1;
-        d.pick = b0.ties ? b0.pick : EPP_NO_ENDPOINT;
-        d.score = b0.ties ? b0.val : 0.0;
-        d.prefill_pick = EPP_NO_ENDPOINT;
-        d.tie_count = b0.ties;
-        d.total_blocks = total;
-        d.match_blocks = b0.ties ? (int32_t)cnt_get(cnt32, b0.pick) : 0;
         epp_decision_detail dd;
-        dd.prefill_score = 0.0; dd.prefill_tie_count = 0; dd.prefill_ran = 0;
-        // ---- a13: decode -> decider -> prefill (disagg_profile_handler.go:264-308)
-        if (p.n_profiles == 2 && b0.ties) {
-            bool go = p.always_disagg || pd_decide(p.non_cached_tokens, p.in_len[r], d.match_blocks, p.block_size_tokens);
-            if (go) {
-                dd.prefill_ran = 1;
-                Best b1 = eval_profile(p.prof[1], p.E, cnt32, list, nl, total, lane, p.lora, adapter);
-                if (b1.ties) { d.prefill_pick = b1.pick; dd.prefill_score = b1.val; dd.prefill_tie_count = b1.ties; }
-            }
-        }
+        decide_stages(p, r, total, p.n_profiles >= 2 ? p.in_len[r] : 0,
+                      [&](int pi, uint64_t key) { return eval_profile(p.prof[pi], p.E, cnt32, list, nl, total, lane, p.lora, adapter, p.tie_seed, key); },
+                      [&](uint32_t e) { return (int32_t)cnt_get(cnt32, e); }, d, dd);
         if (lane == 0) {
             if (p.shard_out) {
                 epp_shard_best sb;
@@ -389,15 +393,21 @@ cudaError_t launch_match_pick(const PickParams &p, uint32_t *gscratch, int grid,
 // decision logic on injected dense match info (KAT / plugin-parity mode)
 // ------------------------------------------------------------------------------------------------
 __device__ inline Best eval_profile_dense(const ProfileDev &pf, int32_t E, const int32_t *mrow, int32_t total,
-                                          int lane, const LoraDev &lora, uint32_t adapter) {
+                                          int lane, const LoraDev &lora, uint32_t adapter, uint64_t tie_seed,
+                                          uint64_t tie_key) {
     Best b;
     best_init(b);
     const bool use_lora = lora.enabled && lora.ptr;
+    auto score_of = [&](uint32_t e) {
+        return weighted_sum(pf, E, e, mrow[e], total, lora, use_lora ? lora_lookup(lora, adapter, e) : 0);
+    };
     for (uint32_t e = lane; e < (uint32_t)E; e += 32) {
         if (!pf.cand[e]) continue;
-        best_add(b, weighted_sum(pf, E, e, mrow[e], total, lora, use_lora ? lora_lookup(lora, adapter, e) : 0), e);
+        best_add(b, score_of(e), e);
     }
-    return best_warp_reduce(b);
+    b = best_warp_reduce(b);
+    if (tie_seed && b.ties > 1) b.pick = select_kth_scan(pf, E, b.val, tie_rank(tie_seed, tie_key, b.ties), lane, score_of);
+    return b;
 }
 
 __global__ void __launch_bounds__(256) k_dense_pick(DensePickParams p) {
@@ -407,26 +417,11 @@ __global__ void __launch_bounds__(256) k_dense_pick(DensePickParams p) {
     const int32_t *mrow = p.match + r * (int64_t)p.E;
     int32_t total = p.total[r];
     const uint32_t adapter = p.model_ids ? p.model_ids[r] : 0u;
-    Best b0 = eval_profile_dense(p.prof[0], p.E, mrow, total, lane, p.lora, adapter);
     epp_decision d;
-    d.status = b0.ties ? 0 : -1;
-    d.pick = b0.ties ? b0.pick : EPP_NO_ENDPOINT;
-    d.score = b0.ties ? b0.val : 0.0;
-    d.prefill_pick = EPP_NO_ENDPOINT;
-    d.tie_count = b0.ties;
-    d.total_blocks = total;
-    d.match_blocks = b0.ties ? mrow[b0.pick] : 0;
     epp_decision_detail dd;
-    dd.prefill_score = 0.0; dd.prefill_tie_count = 0; dd.prefill_ran = 0;
-    if (p.n_profiles == 2 && b0.ties) {
-        bool go = p.always_disagg || pd_decide(p.non_cached_tokens, p.in_len ? p.in_len[r] : 0, d.match_blocks,
-                                                p.block_size_tokens);
-        if (go) {
-            dd.prefill_ran = 1;
-            Best b1 = eval_profile_dense(p.prof[1], p.E, mrow, total, lane, p.lora, adapter);
-            if (b1.ties) { d.prefill_pick = b1.pick; dd.prefill_score = b1.val; dd.prefill_tie_count = b1.ties; }
-        }
-    }
+    decide_stages(p, r, total, p.in_len ? p.in_len[r] : 0,
+                  [&](int pi, uint64_t key) { return eval_profile_dense(p.prof[pi], p.E, mrow, total, lane, p.lora, adapter, p.tie_seed, key); },
+                  [&](uint32_t e) { return mrow[e]; }, d, dd);
     if (lane == 0) {
         p.out[r] = d;
         if (p.detail) p.detail[r] = dd;

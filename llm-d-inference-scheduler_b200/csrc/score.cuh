@@ -164,6 +164,39 @@ __device__ __forceinline__ Best best_warp_reduce(Best b) {
     return r;
 }
 
+// ------------------------------------------------------------------------------------------------
+// tie rule (include/epp_engine.h, "Tie rule"): with tie_seed != 0 the pick is the member of rank
+// tie_rank(seed, key, |arg-max set|) of the set in ascending slot order, key = 4 * request ordinal + profile index --
+// a reproducible stand-in for the shuffle of maxscore/picker.go:91-102 (uniform over the set).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {           // SplitMix64 output function
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint32_t tie_rank(uint64_t seed, uint64_t key, uint32_t n) {
+    const uint64_t m = mix64(seed ^ mix64(key));
+    return (uint32_t)(((m >> 32) * (uint64_t)n) >> 32);
+}
+// The candidate of rank k (ascending slot id) among those whose score equals val: one warp scans all E slots.
+// score_of(e) must reproduce the value the evaluation compared (bit for bit).
+template <typename F>
+__device__ inline uint32_t select_kth_scan(const ProfileDev &pf, int32_t E, double val, uint32_t k, int lane, F score_of) {
+    for (uint32_t e0 = 0; e0 < (uint32_t)E; e0 += 32) {
+        const uint32_t e = e0 + lane;
+        const bool hit = e < (uint32_t)E && pf.cand[e] && score_of(e) == val;
+        uint32_t bal = __ballot_sync(0xffffffffu, hit);
+        const uint32_t c = __popc(bal);
+        if (k < c) {
+            for (uint32_t i = 0; i < k; i++) bal &= bal - 1;
+            return e0 + (uint32_t)__ffs(bal) - 1u;
+        }
+        k -= c;
+    }
+    return EPP_NO_ENDPOINT;
+}
+
 // PrefixBasedPDDecider.disaggregate, prefix_based_pd_decider.go:99-149
 __device__ __forceinline__ bool pd_decide(int64_t nct, int64_t in_len_bytes, int32_t match_blocks, int32_t bst) {
     if (nct == 0) return false;
@@ -171,6 +204,40 @@ __device__ __forceinline__ bool pd_decide(int64_t nct, int64_t in_len_bytes, int
     if (tokens < nct) return false;
     int64_t hit = (int64_t)match_blocks * (int64_t)bst;
     return (tokens - hit) >= nct;
+}
+
+// The stages of one decision after the matching (Scheduler.Schedule with the single / disagg profile handler):
+// primary (decode) pick -> [encode stage for multimodal requests, disagg_profile_handler.go:284-295] -> [P/D decider ->
+// prefill stage, :296-308].  eval(profile index, tie key) runs one SchedulerProfile for the request (all lanes call it
+// together), match_of(slot) returns the request's matchBlocks on a slot.  P = PickParams or DensePickParams.
+template <typename P, typename Eval, typename MatchOf>
+__device__ __forceinline__ void decide_stages(const P &p, int64_t r, int32_t total, int64_t in_len, Eval eval,
+                                              MatchOf match_of, epp_decision &d, epp_decision_detail &dd) {
+    const uint64_t key = 4 * (p.tie_base + (uint64_t)r);
+    const Best b0 = eval(0, key);
+    d.status = b0.ties ? 0 : -1;
+    d.pick = b0.ties ? b0.pick : EPP_NO_ENDPOINT;
+    d.score = b0.ties ? b0.val : 0.0;
+    d.prefill_pick = EPP_NO_ENDPOINT;
+    d.tie_count = b0.ties;
+    d.total_blocks = total;
+    d.match_blocks = b0.ties ? match_of(b0.pick) : 0;
+    dd.prefill_score = 0.0; dd.prefill_tie_count = 0; dd.prefill_ran = 0;
+    dd.encode_score = 0.0; dd.encode_pick = EPP_NO_ENDPOINT; dd.encode_tie_count = 0; dd.encode_ran = 0; dd.reserved = 0;
+    if (!b0.ties) return;                                 // no decode endpoint: the cycle ends (ProcessResults :335-338)
+    if (p.encode_on && p.multimodal && p.multimodal[r]) {
+        dd.encode_ran = 1;
+        const Best b2 = eval(2, key + 2);
+        if (b2.ties) { dd.encode_pick = b2.pick; dd.encode_score = b2.val; dd.encode_tie_count = b2.ties; }
+    }
+    if (p.n_profiles >= 2) {
+        const bool go = p.always_disagg || pd_decide(p.non_cached_tokens, in_len, d.match_blocks, p.block_size_tokens);
+        if (go) {
+            dd.prefill_ran = 1;
+            const Best b1 = eval(1, key + 1);
+            if (b1.ties) { d.prefill_pick = b1.pick; dd.prefill_score = b1.val; dd.prefill_tie_count = b1.ties; }
+        }
+    }
 }
 
 }  // namespace epp

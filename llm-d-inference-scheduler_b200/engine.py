@@ -12,10 +12,12 @@ from . import _capi as capi
 
 DECISION_DTYPE = np.dtype([("status", "<i4"), ("pick", "<u4"), ("score", "<f8"), ("prefill_pick", "<u4"),
                            ("tie_count", "<u4"), ("total_blocks", "<i4"), ("match_blocks", "<i4")])
-DETAIL_DTYPE = np.dtype([("prefill_score", "<f8"), ("prefill_tie_count", "<u4"), ("prefill_ran", "<u4")])
+DETAIL_DTYPE = np.dtype([("prefill_score", "<f8"), ("prefill_tie_count", "<u4"), ("prefill_ran", "<u4"),
+                         ("encode_score", "<f8"), ("encode_pick", "<u4"), ("encode_tie_count", "<u4"),
+                         ("encode_ran", "<u4"), ("reserved", "<u4")])
 SHARD_BEST_DTYPE = np.dtype([("score", "<f8"), ("pick", "<u4"), ("tie_count", "<u4"), ("match_blocks", "<i4"),
                              ("status", "<i4")])
-assert DECISION_DTYPE.itemsize == 32 and DETAIL_DTYPE.itemsize == 16 and SHARD_BEST_DTYPE.itemsize == 24
+assert DECISION_DTYPE.itemsize == 32 and DETAIL_DTYPE.itemsize == 40 and SHARD_BEST_DTYPE.itemsize == 24
 
 
 class EngineError(RuntimeError):
@@ -72,7 +74,7 @@ class Engine:
     def __init__(self, max_endpoints: int, primary: ProfileSpec | None = None, prefill: ProfileSpec | None = None,
                  *, device: int = 0, block_size_tokens: int = 16, max_prefix_blocks: int = 256,
                  lru_capacity_per_server: int = 31250, non_cached_tokens: int = 0, always_disagg: bool = False,
-                 n_ext_cols: int = 0):
+                 n_ext_cols: int = 0, tie_seed: int = 0, encode: ProfileSpec | None = None, pick_k: int = 0):
         self._lib = capi.load()
         cfg = capi.Config()
         self._lib.epp_config_default(C.byref(cfg))
@@ -89,6 +91,11 @@ class Engine:
         if prefill is not None:
             cfg.handler = capi.HANDLER_DISAGG
             _fill_profile(cfg.prefill, prefill)
+        if encode is not None:
+            cfg.encode_enabled = 1
+            _fill_profile(cfg.encode, encode)
+        cfg.tie_seed = tie_seed
+        cfg.pick_k = pick_k
         self.cfg = cfg
         self.E = max_endpoints
         self.B = max_prefix_blocks
@@ -170,7 +177,7 @@ class Engine:
         self._check(self._lib.epp_index_add_picked(self._h))
 
     # ---- batches ----
-    def _batch(self, data, offsets=None, uniform_len=None, model_ids=None, n_requests=None, lengths=None):
+    def _batch(self, data, offsets=None, uniform_len=None, model_ids=None, n_requests=None, lengths=None, multimodal=None):
         """data: bytes-like numpy array / torch CUDA tensor (any dtype, viewed as bytes)."""
         b = capi.Batch()
         dev = _is_torch(data)
@@ -209,6 +216,11 @@ class Engine:
                 lengths = np.ascontiguousarray(lengths, dtype=np.uint64)
             keep.append(lengths)
             b.lengths = _ptr(lengths)
+        if multimodal is not None:
+            if not dev:
+                multimodal = np.ascontiguousarray(multimodal, dtype=np.uint8)
+            keep.append(multimodal)
+            b.multimodal = _ptr(multimodal)
         b.n_requests = R
         return b, R, dev, keep
 
@@ -262,16 +274,16 @@ class Engine:
                                                 _ptr(mep), _ptr(mmo), _ptr(mst)))
 
     def schedule(self, data, offsets=None, uniform_len=None, model_ids=None, n_requests=None, keep_hashes=False,
-                 detail=True, out=None, lengths=None, asynchronous=False):
+                 detail=True, out=None, lengths=None, asynchronous=False, multimodal=None):
         """a1-a14 Scheduler.Schedule for a batch -> (decisions, details).  asynchronous=True (CUDA tensors only)
         enqueues the batch and returns; the outputs are complete after synchronize()."""
-        b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests, lengths)
+        b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests, lengths, multimodal)
         if asynchronous:
             b.flags |= capi.EPP_BATCH_ASYNC
         if dev:
             import torch
             dec = out if out is not None else torch.empty((max(R, 1), 32), dtype=torch.uint8, device=data.device)
-            det = torch.empty((max(R, 1), 16), dtype=torch.uint8, device=data.device) if detail else None
+            det = torch.empty((max(R, 1), 40), dtype=torch.uint8, device=data.device) if detail else None
         else:
             dec = np.zeros(R, dtype=DECISION_DTYPE) if out is None else out
             det = np.zeros(R, dtype=DETAIL_DTYPE) if detail else None
@@ -342,6 +354,69 @@ class Engine:
 
     def shard_merge(self, n_requests, n_ranks, all_best, out_decisions):
         self._check(self._lib.epp_shard_merge(self._h, n_requests, n_ranks, _ptr(all_best), _ptr(out_decisions)))
+
+
+class Batcher:
+    """The in-library micro-batcher (epp_submit / epp_wait): any number of threads submit single prompts and block for
+    their decision; batches are formed and flushed inside libepp_engine.so (csrc/batcher.cu)."""
+
+    def __init__(self, engine: Engine, max_batch: int = 256, max_delay_us: int = 200, index_picks: bool = False):
+        self._lib = engine._lib
+        self._engine = engine                      # keep the engine alive: the batcher must be destroyed first
+        cfg = capi.BatcherCfg()
+        cfg.struct_size = C.sizeof(capi.BatcherCfg)
+        cfg.max_batch = max_batch
+        cfg.max_delay_us = max_delay_us
+        cfg.index_picks = int(index_picks)
+        self._b = C.c_void_p()
+        self._check(self._lib.epp_batcher_create(engine._h, C.byref(cfg), C.byref(self._b)))
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise EngineError(rc, (self._lib.epp_batcher_last_error() or b"").decode())
+
+    def submit(self, prompt, model_id: int = 0, multimodal: bool = False) -> int:
+        buf = np.ascontiguousarray(prompt).view(np.uint8).reshape(-1) if not isinstance(prompt, (bytes, bytearray)) else prompt
+        n = len(buf)
+        ptr = buf.ctypes.data_as(C.c_void_p) if isinstance(buf, np.ndarray) else C.cast(C.c_char_p(bytes(buf)), C.c_void_p)
+        t = C.c_uint64()
+        self._check(self._lib.epp_submit(self._b, model_id, ptr, n, int(multimodal), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket: int):
+        """-> (decision, detail) as 1-element structured arrays."""
+        d = capi.Decision()
+        dd = capi.DecisionDetail()
+        self._check(self._lib.epp_wait(self._b, ticket, C.byref(d), C.byref(dd)))
+        dec = np.frombuffer(bytes(d), dtype=DECISION_DTYPE)[0]
+        det = np.frombuffer(bytes(dd), dtype=DETAIL_DTYPE)[0]
+        return dec, det
+
+    def schedule(self, prompt, model_id: int = 0, multimodal: bool = False):
+        """Scheduler.Schedule for ONE request (what a goroutine of the reference calls): submit + wait."""
+        return self.wait(self.submit(prompt, model_id, multimodal))
+
+    def stats(self) -> dict:
+        st = capi.BatcherStats()
+        self._check(self._lib.epp_batcher_stats(self._b, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in capi.BatcherStats._fields_}
+
+    def close(self):
+        if getattr(self, "_b", None) and self._b.value:
+            self._lib.epp_batcher_destroy(self._b)
+            self._b = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def decisions_from_torch(t) -> np.ndarray:

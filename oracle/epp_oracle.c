@@ -584,19 +584,35 @@ static inline double enforce_score_range(double s) {
     return s;
 }
 
+/* Tie rule of the BUILD (not of the reference): MaxScorePicker.Pick shuffles with math/rand before its stable sort
+ * (maxscore/picker.go:91-102), i.e. the winner is a uniformly random member of the arg-max set.  With tie_seed == 0
+ * engine and oracle report the LOWEST slot of the set; with tie_seed != 0 both pick the member of rank
+ * orc_tie_rank(seed, key, |set|) in ascending slot order, key = 4 * (request ordinal) + profile index
+ * (0 primary / decode, 1 prefill, 2 encode) -- uniform over the set, reproducible on both sides. */
+static inline uint64_t mix64(uint64_t z) {            /* SplitMix64 output function */
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+uint32_t orc_tie_rank(uint64_t seed, uint64_t key, uint32_t n) {
+    uint64_t m = mix64(seed ^ mix64(key));
+    return (uint32_t)(((m >> 32) * (uint64_t)n) >> 32);
+}
+
 /* =====================================================================================
  * A.5 SchedulerProfile.Run -- scheduling/scheduler_profile.go:117-192 + maxscore picker
  * ===================================================================================== */
 static int profile_run_scratch(const orc_profile *p, const orc_pool *pool, const int32_t *match, int32_t total,
                                double *out_scores, double *out_max, int32_t *out_pick, int32_t *argmax_set,
-                               uint8_t *cand, double *col);
+                               uint8_t *cand, double *col, uint64_t tie_seed, uint64_t tie_key);
 
 int orc_profile_run(const orc_profile *p, const orc_pool *pool, const int32_t *match, int32_t total,
                     double *out_scores, double *out_max, int32_t *out_pick, int32_t *argmax_set) {
     int n = pool->n;
     uint8_t *cand = (uint8_t *)malloc((size_t)n + 1);
     double *col = (double *)malloc(sizeof(double) * ((size_t)n + 1));
-    int r = profile_run_scratch(p, pool, match, total, out_scores, out_max, out_pick, argmax_set, cand, col);
+    int r = profile_run_scratch(p, pool, match, total, out_scores, out_max, out_pick, argmax_set, cand, col, 0, 0);
     free(cand); free(col);
     return r;
 }
@@ -605,7 +621,7 @@ int orc_profile_run(const orc_profile *p, const orc_pool *pool, const int32_t *m
  * makes the baseline FASTER than the reference. */
 static int profile_run_scratch(const orc_profile *p, const orc_pool *pool, const int32_t *match, int32_t total,
                                double *out_scores, double *out_max, int32_t *out_pick, int32_t *argmax_set,
-                               uint8_t *cand, double *col) {
+                               uint8_t *cand, double *col, uint64_t tie_seed, uint64_t tie_key) {
     int n = pool->n;
     int n_cand = 0;
     for (int e = 0; e < n; e++) {                       /* runFilterPlugins, :130-149 */
@@ -644,6 +660,16 @@ static int profile_run_scratch(const orc_profile *p, const orc_pool *pool, const
             cnt++;
         }
     }
+    if (tie_seed && cnt > 1) {                           /* the build's reproducible stand-in for the shuffle */
+        uint32_t k = orc_tie_rank(tie_seed, tie_key, (uint32_t)cnt);
+        for (int e = 0; e < n; e++) {
+            if (!cand[e]) continue;
+            if (!(out_scores[e] < mx) && !(out_scores[e] > mx)) {
+                if (k == 0) { first = e; break; }
+                k--;
+            }
+        }
+    }
     if (out_max) *out_max = mx;
     if (out_pick) *out_pick = first;
     return cnt;
@@ -665,7 +691,8 @@ int orc_pd_decide(int64_t non_cached_tokens, int64_t input_len_bytes, int32_t ma
 static void schedule_scratch(const orc_profile *primary, const orc_profile *prefill, const orc_pool *pool,
                              const int32_t *match, int32_t total, int32_t block_size_tokens, int64_t input_len_bytes,
                              int64_t non_cached_tokens, int always_disagg, double *scratch_scores, orc_decision *out,
-                             uint8_t *cand, double *col);
+                             uint8_t *cand, double *col, uint64_t tie_seed, uint64_t tie_req,
+                             const orc_profile *encode, int multimodal);
 
 void orc_schedule(const orc_profile *primary, const orc_profile *prefill, const orc_pool *pool,
                   const int32_t *match, int32_t total, int32_t block_size_tokens,
@@ -674,30 +701,38 @@ void orc_schedule(const orc_profile *primary, const orc_profile *prefill, const 
     uint8_t *cand = (uint8_t *)malloc((size_t)pool->n + 1);
     double *col = (double *)malloc(sizeof(double) * ((size_t)pool->n + 1));
     schedule_scratch(primary, prefill, pool, match, total, block_size_tokens, input_len_bytes, non_cached_tokens,
-                     always_disagg, scratch_scores, out, cand, col);
+                     always_disagg, scratch_scores, out, cand, col, 0, 0, NULL, 0);
     free(cand); free(col);
 }
 
 static void schedule_scratch(const orc_profile *primary, const orc_profile *prefill, const orc_pool *pool,
                              const int32_t *match, int32_t total, int32_t block_size_tokens, int64_t input_len_bytes,
                              int64_t non_cached_tokens, int always_disagg, double *scratch_scores, orc_decision *out,
-                             uint8_t *cand, double *col) {
+                             uint8_t *cand, double *col, uint64_t tie_seed, uint64_t tie_req,
+                             const orc_profile *encode, int multimodal) {
     memset(out, 0, sizeof *out);
-    out->pick = -1; out->prefill_pick = -1;
+    out->pick = -1; out->prefill_pick = -1; out->encode_pick = -1;
     double mx; int32_t pick;
-    int ties = profile_run_scratch(primary, pool, match, total, scratch_scores, &mx, &pick, NULL, cand, col);
+    int ties = profile_run_scratch(primary, pool, match, total, scratch_scores, &mx, &pick, NULL, cand, col, tie_seed, 4 * tie_req);
     if (ties == 0) {            /* disagg ProcessResults :335-338 / single ProcessResults: error */
         out->status = -1;
         return;
     }
     out->pick = pick; out->tie_count = ties; out->score = mx;
+    out->encode_pick = -1;
+    if (encode && multimodal) { /* disagg_profile_handler.go:284-295 + always_disagg_mm_decider.go:47-49 */
+        double emx; int32_t epick;
+        out->encode_ran = 1;
+        int et = profile_run_scratch(encode, pool, match, total, scratch_scores, &emx, &epick, NULL, cand, col, tie_seed, 4 * tie_req + 2);
+        if (et > 0) { out->encode_pick = epick; out->encode_tie_count = et; out->encode_score = emx; }
+    }
     if (prefill) {              /* disagg_profile_handler.go:296-308 */
         int go = always_disagg ? 1
                                : orc_pd_decide(non_cached_tokens, input_len_bytes, match[pick], block_size_tokens);
         out->prefill_ran = go;
         if (go) {
             double pmx; int32_t ppick;
-            int pt = profile_run_scratch(prefill, pool, match, total, scratch_scores, &pmx, &ppick, NULL, cand, col);
+            int pt = profile_run_scratch(prefill, pool, match, total, scratch_scores, &pmx, &ppick, NULL, cand, col, tie_seed, 4 * tie_req + 1);
             if (pt > 0) { out->prefill_pick = ppick; out->prefill_tie_count = pt; out->prefill_score = pmx; }
         }
     }
@@ -706,14 +741,15 @@ static void schedule_scratch(const orc_profile *primary, const orc_profile *pref
 static void cycle_scratch(const orc_cycle_cfg *cfg, const orc_indexer *ix, const orc_profile *primary,
                           const orc_profile *prefill, const orc_pool *pool, const uint8_t *prompt, size_t prompt_len,
                           uint64_t *scratch_hashes, int32_t *scratch_match, double *scratch_scores, orc_decision *out,
-                          int32_t *out_total, uint8_t *cand, double *col) {
+                          int32_t *out_total, uint8_t *cand, double *col, uint64_t tie_req) {
     int cap = cfg->max_prefix_blocks + 1;
     int total = orc_hash_prompt(prompt, prompt_len, cfg->model, cfg->model_len, NULL, 0,
                                 cfg->block_size_tokens, cfg->max_prefix_blocks, scratch_hashes, cap);
     memset(scratch_match, 0, sizeof(int32_t) * (size_t)pool->n);
     orc_match_longest_prefix(ix, scratch_hashes, total, scratch_match, pool->n);
     schedule_scratch(primary, prefill, pool, scratch_match, total, cfg->block_size_tokens, (int64_t)prompt_len,
-                     cfg->non_cached_tokens, cfg->always_disagg, scratch_scores, out, cand, col);
+                     cfg->non_cached_tokens, cfg->always_disagg, scratch_scores, out, cand, col, cfg->tie_seed, tie_req,
+                     cfg->encode, cfg->multimodal ? cfg->multimodal[tie_req - cfg->tie_base] : 0);
     if (out_total) *out_total = total;
 }
 
@@ -748,7 +784,7 @@ static void *batch_worker(void *arg) {
     for (int64_t r = j->lo; r < j->hi; r++) {
         cycle_scratch(j->cfg, j->ix, j->primary, j->prefill, j->pool, j->data + j->offsets[r],
                       (size_t)(j->offsets[r + 1] - j->offsets[r]), hashes, match, scores, &j->out[r],
-                      j->out_total ? &j->out_total[r] : NULL, cand, col);
+                      j->out_total ? &j->out_total[r] : NULL, cand, col, j->cfg->tie_base + (uint64_t)r);
     }
     free(hashes); free(match); free(scores); free(cand); free(col);
     return NULL;

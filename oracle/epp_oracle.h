@@ -151,6 +151,11 @@ typedef struct {
     int32_t prefill_ran;         /* decider said disaggregate                               */
     double score;
     double prefill_score;
+    int32_t encode_pick;         /* -1 = no encode stage result (disagg_profile_handler.go:284-295)    */
+    int32_t encode_tie_count;
+    int32_t encode_ran;          /* the encode decider said disaggregate (multimodal request)           */
+    int32_t _pad;
+    double encode_score;
 } orc_decision;
 
 /* Scheduler.Schedule with the single-profile handler (single_profile_handler.go:66-99) when
@@ -172,7 +177,14 @@ typedef struct {
     int32_t _pad;
     const uint8_t *model;
     size_t model_len;
+    uint64_t tie_seed;           /* 0: lowest-slot representative; else the build's reproducible random tie rule   */
+    uint64_t tie_base;           /* ordinal of request 0 of the batch (orc_cycle_batch: request r has ordinal base+r) */
+    const orc_profile *encode;   /* the "encode" profile of the disagg handler, or NULL                             */
+    const uint8_t *multimodal;   /* [R] hasMultimodalContent per request (multimodal_helpers.go), or NULL; orc_cycle_batch only */
 } orc_cycle_cfg;
+/* Rank (in ascending slot order) of the arg-max-set member the build picks when tie_seed != 0:
+ * ((mix64(seed ^ mix64(key)) >> 32) * n) >> 32 with the SplitMix64 output function, key = 4 * ordinal + profile index. */
+uint32_t orc_tie_rank(uint64_t seed, uint64_t key, uint32_t n);
 void orc_cycle(const orc_cycle_cfg *cfg, const orc_indexer *ix, const orc_profile *primary,
                const orc_profile *prefill, const orc_pool *pool, const uint8_t *prompt, size_t prompt_len,
                uint64_t *scratch_hashes, int32_t *scratch_match, double *scratch_scores,

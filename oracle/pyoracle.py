@@ -41,18 +41,22 @@ class Pool(C.Structure):
 class Decision(C.Structure):
     _fields_ = [("status", C.c_int32), ("pick", C.c_int32), ("tie_count", C.c_int32),
                 ("prefill_pick", C.c_int32), ("prefill_tie_count", C.c_int32), ("prefill_ran", C.c_int32),
-                ("score", C.c_double), ("prefill_score", C.c_double)]
+                ("score", C.c_double), ("prefill_score", C.c_double), ("encode_pick", C.c_int32),
+                ("encode_tie_count", C.c_int32), ("encode_ran", C.c_int32), ("_pad", C.c_int32),
+                ("encode_score", C.c_double)]
 
 
 class CycleCfg(C.Structure):
     _fields_ = [("block_size_tokens", C.c_int32), ("max_prefix_blocks", C.c_int32),
                 ("non_cached_tokens", C.c_int64), ("always_disagg", C.c_int32), ("_pad", C.c_int32),
-                ("model", C.c_char_p), ("model_len", C.c_size_t)]
+                ("model", C.c_char_p), ("model_len", C.c_size_t), ("tie_seed", C.c_uint64), ("tie_base", C.c_uint64),
+                ("encode", C.POINTER(Profile)), ("multimodal", C.c_void_p)]
 
 
 DECISION_DTYPE = np.dtype([("status", "<i4"), ("pick", "<i4"), ("tie_count", "<i4"), ("prefill_pick", "<i4"),
                            ("prefill_tie_count", "<i4"), ("prefill_ran", "<i4"), ("score", "<f8"),
-                           ("prefill_score", "<f8")])
+                           ("prefill_score", "<f8"), ("encode_pick", "<i4"), ("encode_tie_count", "<i4"),
+                           ("encode_ran", "<i4"), ("_pad", "<i4"), ("encode_score", "<f8")])
 assert DECISION_DTYPE.itemsize == C.sizeof(Decision)
 
 
@@ -107,6 +111,8 @@ def lib():
         L.orc_pd_decide.argtypes = [C.c_int64, C.c_int64, C.c_int32, C.c_int32]
         L.orc_schedule.argtypes = [C.POINTER(Profile), C.POINTER(Profile), C.POINTER(Pool), C.c_void_p, C.c_int32,
                                    C.c_int32, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.POINTER(Decision)]
+        L.orc_tie_rank.restype = C.c_uint32
+        L.orc_tie_rank.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
         L.orc_cycle_batch.argtypes = [C.POINTER(CycleCfg), C.c_void_p, C.POINTER(Profile), C.POINTER(Profile),
                                       C.POINTER(Pool), C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                       C.c_void_p]
@@ -260,6 +266,11 @@ def score_column(scorer: tuple, pool: PoolState, cand, match, total: int):
     return out
 
 
+def tie_rank(seed: int, key: int, n: int) -> int:
+    """Rank of the arg-max-set member picked under the build's reproducible tie rule (oracle/epp_oracle.h)."""
+    return int(lib().orc_tie_rank(seed, key, n))
+
+
 def pd_decide(nct: int, input_len_bytes: int, match_blocks: int, block_size_tokens: int) -> bool:
     return bool(lib().orc_pd_decide(nct, input_len_bytes, match_blocks, block_size_tokens))
 
@@ -277,7 +288,8 @@ def schedule(primary: Profile, prefill: Profile | None, pool: PoolState, match, 
 
 def cycle_batch(model: bytes, block_size_tokens: int, max_prefix_blocks: int, nct: int, always_disagg: bool,
                 indexer: Indexer, primary: Profile, prefill: Profile | None, pool: PoolState,
-                data: np.ndarray, offsets: np.ndarray, n_threads: int = 1):
+                data: np.ndarray, offsets: np.ndarray, n_threads: int = 1, tie_seed: int = 0, tie_base: int = 0,
+                encode: Profile | None = None, multimodal=None):
     """Whole cycle (hash -> match -> schedule) for R prompts against a frozen index.
     Returns (decisions structured array [R], totals int32[R])."""
     cfg = CycleCfg()
@@ -287,6 +299,14 @@ def cycle_batch(model: bytes, block_size_tokens: int, max_prefix_blocks: int, nc
     cfg.always_disagg = int(always_disagg)
     cfg.model = model
     cfg.model_len = len(model)
+    cfg.tie_seed = tie_seed
+    cfg.tie_base = tie_base
+    mm = None
+    if encode is not None:
+        cfg.encode = C.pointer(encode)
+        if multimodal is not None:
+            mm = np.ascontiguousarray(multimodal, dtype=np.uint8)
+            cfg.multimodal = mm.ctypes.data
     data = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
     offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
     R = offsets.shape[0] - 1

@@ -592,6 +592,137 @@ def test_many_matched_endpoints_dense_fallback(epp, orc):
             np.testing.assert_array_equal(m[r], want)
 
 
+def _tied_pool(rng, E, n_levels):
+    """A pool where many endpoints share a load level, so that arg-max sets are large."""
+    kv = rng.integers(0, n_levels, E) / float(n_levels)
+    waiting = rng.integers(0, 2, E).astype(np.int32)
+    return kv, waiting
+
+
+@pytest.mark.parametrize("tie_seed", [0x5EED, 1])
+def test_random_tie_rule_vs_oracle(epp, orc, tie_seed):
+    """epp_config.tie_seed != 0: the pick is the member of rank orc_tie_rank(seed, 4 * ordinal + profile, |set|) of the
+    arg-max set in ascending slot order (include/epp_engine.h, "Tie rule") -- through the sparse kernel (matched and
+    unmatched members mixed), the dense-counter kernel (> 32 matched endpoints) and the injected-match entry point;
+    the ordinal keeps counting across batches.  The reference draws a uniformly random member
+    (picker/maxscore/picker.go:91-102): the picks of a batch of equal requests must spread over the set."""
+    import helpers
+    E, bst, B = 96, 2, 16
+    rng = np.random.default_rng(41)
+    primary_spec = [epp.ScorerSpec(2, 1.0), epp.ScorerSpec(1, 1.0), epp.ScorerSpec(0, 2.0)]
+    with epp.Engine(E, epp.ProfileSpec(1, primary_spec), epp.ProfileSpec(2, [epp.ScorerSpec(2, 1.0), epp.ScorerSpec(0, 1.0)]),
+                    block_size_tokens=bst, max_prefix_blocks=B, non_cached_tokens=4, tie_seed=tie_seed) as eng:
+        eng.register_model(b"m")
+        kv, waiting = _tied_pool(rng, E, 2)
+        role = np.where(np.arange(E) % 3 == 0, 2, 1).astype(np.uint8)        # a third prefill, the rest decode
+        eng.pool_set(np.arange(E), role, kv, waiting)
+        fam = [bytes(rng.integers(0, 256, 8 * B, dtype=np.uint8)) for _ in range(6)]
+        pairs_h, pairs_e = [], []
+        for g, p in enumerate(fam):
+            h = orc.hash_prompt(p, b"m", bst, B)
+            holders = rng.choice(E, size=[2, 5, 9, 20, 40, 70][g], replace=False)   # the last two overflow the 32-entry map
+            for e in holders:
+                depth = int(rng.choice([len(h) // 2, len(h)]))          # few distinct depths: equal scores among holders
+                pairs_h += h[:depth]
+                pairs_e += [int(e)] * depth
+        ix = orc.Indexer()
+        ix.load_pairs(pairs_h, pairs_e)
+        eng.index_load_snapshot(pairs_h, pairs_e)
+        pool = orc.PoolState(role, kv, waiting)
+        prim = orc.make_profile(1, [(2, 1.0, 0), (1, 1.0, 0), (0, 2.0, 0)])
+        pref = orc.make_profile(2, [(2, 1.0, 0), (0, 1.0, 0)])
+        spread = set()
+        for batch in range(3):
+            prompts = []
+            for _ in range(400):
+                g = int(rng.integers(0, len(fam) + 2))
+                if g >= len(fam):
+                    prompts.append(bytes(rng.integers(0, 256, 8 * B, dtype=np.uint8)))      # cold: the whole top group ties
+                else:
+                    keep = int(rng.integers(1, B + 1)) * 8
+                    prompts.append(fam[g][:keep] + bytes(rng.integers(0, 256, 8 * B - keep, dtype=np.uint8)))
+            d, offs = _pack(prompts)
+            base = eng.stats()["n_decisions"]
+            assert base == 400 * batch
+            dec, det = eng.schedule(d, offsets=offs)
+            odec, ototal = orc.cycle_batch(b"m", bst, B, 4, False, ix, prim, pref, pool, d, offs, 2, tie_seed=tie_seed, tie_base=base)
+            helpers.assert_decisions_equal(dec, det, odec, ototal, where=f"tie rule, batch {batch}")
+            assert (dec["tie_count"] > 1).sum() > 100 and (det["prefill_tie_count"] > 1).any()
+            spread |= set(int(x) for x in dec["pick"][dec["tie_count"] > 6])
+        assert len(spread) > 6                                  # not one hot endpoint
+        # injected match rows (dense pick kernel): same rule, ordinals keep counting
+        match = rng.integers(0, 3, size=(64, E)).astype(np.int32) * 4
+        total = np.full(64, B, np.int32)
+        base = eng.stats()["n_decisions"]
+        dec2, det2 = eng.schedule_with_match(match, total, input_len_bytes=np.full(64, 8 * B, np.int64))
+        scratch = np.zeros(E)
+        for r in range(64):
+            want = orc.schedule(prim, pref, pool, match[r], B, bst, 8 * B, 4)
+            scores, mx, lowest, amax = orc.profile_run(prim, pool, match[r], B)
+            k = orc.tie_rank(tie_seed, 4 * (base + r), len(amax))
+            assert dec2["pick"][r] == amax[k] and dec2["tie_count"][r] == len(amax) and dec2["score"][r] == mx
+        assert eng.stats()["n_decisions"] == base + 64
+
+
+def test_encode_stage_vs_oracle(epp, orc):
+    """The optional encode stage of the disagg handler (disagg_profile_handler.go:284-295): decode pick, then -- for
+    requests with multimodal content (always-disagg-multimodal-decider) -- the encode profile (encode-filter + scorers),
+    then the P/D decider and the prefill profile.  EPD style (no prefill stage) = nonCachedTokens 0."""
+    import helpers
+    E, bst, B = 80, 2, 16
+    rng = np.random.default_rng(43)
+    enc_spec = epp.ProfileSpec(3, [epp.ScorerSpec(2, 1.0), epp.ScorerSpec(1, 2.0)])
+    for nct in (4, 0):
+        with epp.Engine(E, epp.ProfileSpec(1, [epp.ScorerSpec(2, 1.0), epp.ScorerSpec(0, 2.0)]),
+                        epp.ProfileSpec(2, [epp.ScorerSpec(2, 1.0), epp.ScorerSpec(0, 1.0)]), block_size_tokens=bst,
+                        max_prefix_blocks=B, non_cached_tokens=nct, encode=enc_spec) as eng:
+            eng.register_model(b"m")
+            kv = rng.integers(0, 11, E) / 10.0
+            waiting = rng.integers(0, 4, E).astype(np.int32)
+            role = rng.choice([1, 2, 3, 5, 6, 7, 0, 8], size=E).astype(np.uint8)     # every role of roles.go:25-44
+            eng.pool_set(np.arange(E), role, kv, waiting)
+            fam = [bytes(rng.integers(0, 256, 8 * B, dtype=np.uint8)) for _ in range(4)]
+            pairs_h, pairs_e = [], []
+            for p in fam:
+                h = orc.hash_prompt(p, b"m", bst, B)
+                for e in rng.choice(E, size=6, replace=False):
+                    depth = int(rng.integers(1, len(h) + 1))
+                    pairs_h += h[:depth]
+                    pairs_e += [int(e)] * depth
+            ix = orc.Indexer()
+            ix.load_pairs(pairs_h, pairs_e)
+            eng.index_load_snapshot(pairs_h, pairs_e)
+            prompts = []
+            for _ in range(300):
+                g = int(rng.integers(0, 5))
+                keep = int(rng.integers(1, B + 1)) * 8
+                prompts.append((fam[g][:keep] if g < 4 else b"") + bytes(rng.integers(0, 256, 8 * B - (keep if g < 4 else 0), dtype=np.uint8)))
+            d, offs = _pack(prompts)
+            mm = (rng.random(300) < 0.4).astype(np.uint8)
+            dec, det = eng.schedule(d, offsets=offs, multimodal=mm)
+            pool = orc.PoolState(role, kv, waiting)
+            odec, ototal = orc.cycle_batch(b"m", bst, B, nct, False, ix, orc.make_profile(1, [(2, 1.0, 0), (0, 2.0, 0)]),
+                                           orc.make_profile(2, [(2, 1.0, 0), (0, 1.0, 0)]), pool, d, offs, 2,
+                                           encode=orc.make_profile(3, [(2, 1.0, 0), (1, 2.0, 0)]), multimodal=mm)
+            helpers.assert_decisions_equal(dec, det, odec, ototal, where=f"encode stage nct={nct}")
+            ok = dec["status"] == 0
+            np.testing.assert_array_equal(det["encode_ran"][ok], mm[ok].astype(np.uint32))
+            assert (det["encode_pick"][ok & (mm == 1)] != 0xFFFFFFFF).all()
+            if nct == 0:
+                assert (det["prefill_ran"] == 0).all()             # EPD: encode + decode only
+            else:
+                assert (det["prefill_ran"] == 1).any()
+            # the same batch through device pointers
+            import torch
+            dd, do = torch.from_numpy(d).cuda(), torch.from_numpy(offs.view(np.int64)).cuda()
+            ddec, ddet = eng.schedule(dd, offsets=do, multimodal=torch.from_numpy(mm).cuda())
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(epp.decisions_from_torch(ddec), dec)
+            np.testing.assert_array_equal(ddet.cpu().numpy().view(epp.DETAIL_DTYPE).reshape(-1), det)
+            with pytest.raises(epp.EngineError):
+                eng.schedule(d, offsets=offs, multimodal=mm, detail=False)      # the encode pick needs the detail record
+
+
 def test_large_pool_global_counters(epp, orc, tg):
     """E too large for per-warp shared-memory counters -> zeroed global scratch path (config-5-sized pool on 1 GPU)."""
     import helpers

@@ -59,11 +59,12 @@ def setup_oracle(orc, w: tg.Workload, trace: tg.Trace):
     return pool, ix, primary, prefill, (hs, es)
 
 
-def oracle_decisions(orc, w, pool, ix, primary, prefill, tokens: np.ndarray, n_threads: int = 4):
+def oracle_decisions(orc, w, pool, ix, primary, prefill, tokens: np.ndarray, n_threads: int = 4, **kw):
+    """kw: tie_seed / tie_base (the reproducible random tie rule), encode / multimodal (the encode stage)."""
     R = tokens.shape[0]
     offs = np.arange(R + 1, dtype=np.uint64) * np.uint64(w.prompt_bytes)
     return orc.cycle_batch(tg.MODEL, w.block_size_tokens, w.max_prefix_blocks, w.non_cached_tokens, False, ix, primary,
-                           prefill, pool, tokens, offs, n_threads)
+                           prefill, pool, tokens, offs, n_threads, **kw)
 
 
 def assert_decisions_equal(dec, det, odec, ototal, *, where=""):
@@ -85,3 +86,11 @@ def assert_decisions_equal(dec, det, odec, ototal, *, where=""):
         has = ok & (odec["prefill_pick"] >= 0)
         np.testing.assert_array_equal(det["prefill_score"][has].view(np.uint64), odec["prefill_score"][has].view(np.uint64), err_msg=where + " prefill score bits")
         np.testing.assert_array_equal(det["prefill_tie_count"][has].astype(np.int64), odec["prefill_tie_count"][has].astype(np.int64), err_msg=where + " prefill ties")
+        if "encode_ran" in odec.dtype.names:
+            np.testing.assert_array_equal(det["encode_ran"][ok].astype(np.int64), odec["encode_ran"][ok].astype(np.int64), err_msg=where + " encode_ran")
+            eng_en = det["encode_pick"].astype(np.int64)
+            eng_en[eng_en == 0xFFFFFFFF] = -1
+            np.testing.assert_array_equal(eng_en[ok], odec["encode_pick"][ok].astype(np.int64), err_msg=where + " encode_pick")
+            hase = ok & (odec["encode_pick"] >= 0)
+            np.testing.assert_array_equal(det["encode_score"][hase].view(np.uint64), odec["encode_score"][hase].view(np.uint64), err_msg=where + " encode score bits")
+            np.testing.assert_array_equal(det["encode_tie_count"][hase].astype(np.int64), odec["encode_tie_count"][hase].astype(np.int64), err_msg=where + " encode ties")
