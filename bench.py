@@ -27,9 +27,9 @@ import time
 
 import numpy as np
 
-# stdout carries exactly ONE JSON line: keep NCCL's version banner (printed on stdout at NCCL_DEBUG=VERSION/INFO) out
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly ONE JSON line: NCCL's log (communicator set-up at NCCL_DEBUG=INFO) goes to stderr instead,
+# unchanged, so that the driver can still read it
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -151,16 +151,18 @@ def _config_json(w, n_gpus, extra=None):
     return c
 
 
-def _best_thread_count(run, n_max: int) -> int:
+def _best_thread_count(run, n_max: int):
     """The host may expose more logical CPUs than it lets this container use: probe a few thread counts on a short
-    sample and keep the fastest (the baseline must be the CPU's best, not an oversubscribed run)."""
+    sample and keep the fastest (the baseline must be the CPU's best, not an oversubscribed run).  Returns the winner
+    and the whole table {threads: decisions/s} (the rate moves a lot from box to box)."""
     cands = sorted({max(1, n_max >> k) for k in range(0, 6)} | {min(n_max, 8)}, reverse=True)
-    best, best_rate = cands[0], 0.0
+    best, best_rate, table = cands[0], 0.0, {}
     for nt in cands:
         rate = run(nt)
+        table[str(nt)] = round(rate, 1)
         if rate > best_rate * 1.05:
             best, best_rate = nt, rate
-    return best
+    return best, table
 
 
 def cpu_baseline(w, trace, n_threads: int, target_s: float = 12.0, tokens: np.ndarray | None = None):
@@ -178,19 +180,20 @@ def cpu_baseline(w, trace, n_threads: int, target_s: float = 12.0, tokens: np.nd
         return probe_n / (time.perf_counter() - t0)
 
     probe(n_threads)                                   # warm caches / page in
-    nt = _best_thread_count(probe, n_threads)
+    nt, table = _best_thread_count(probe, n_threads)
     passes, dt = 0, 0.0
+    odec = None
     while dt < target_s and passes < 1000:      # repeat the batch until ~target_s of CPU work has been timed
         t0 = time.perf_counter()
-        helpers.oracle_decisions(orc, w, pool, ix, primary, prefill, tk, nt)
+        odec, _ = helpers.oracle_decisions(orc, w, pool, ix, primary, prefill, tk, nt)
         dt += time.perf_counter() - t0
         passes += 1
     n_total = n * passes
-    return {"value": n_total / dt, "unit": UNIT, "cores": nt, "kind": "port",
+    return {"value": n_total / dt, "unit": UNIT, "cores": nt, "kind": "port", "threads_probed": table,
             "sample": f"{passes} passes over the first {n} requests of the step's batch ({n_total} decisions), "
                       f"{nt} host threads (fastest of the probed counts; os.cpu_count() = {n_threads}), {dt:.2f} s; "
                       "C restatement of the reference Go loops (oracle/epp_oracle.c) -- the Go toolchain is not "
-                      "installable here"}, (n_total, dt)
+                      "installable here"}, odec
 
 
 def run_reference(args, rank, world):
@@ -214,7 +217,7 @@ def run_reference(args, rank, world):
 
     probe_rate(n_threads)
     n_cpu = n_threads
-    n_threads = _best_thread_count(probe_rate, n_threads)
+    n_threads, table = _best_thread_count(probe_rate, n_threads)
     # size one step so that (warmup + steps) steps take about 60 s in total
     per_req = 1.0 / probe_rate(n_threads)
     n = int(min(w.R, max(n_threads, 60.0 / max(1, args.steps + args.warmup) / per_req)))
@@ -234,8 +237,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 (XXH64) + f64 (scores)", "data": "synthetic",
-        "config": _config_json(w, args.gpus, {"reference_step_requests": n}),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": n_threads, "kind": "port", "sample": sample},
+        "config": _config_json(w, args.gpus),
+        "reference_step_requests": n,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": n_threads, "kind": "port", "sample": sample,
+                         "threads_probed": table},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -384,6 +389,17 @@ def run_gpu(args, rank, world, local_rank):
     wall = max_over_ranks(wall)
     timed_ms = max_over_ranks(timed_ms)
     value = world * R * args.steps / (timed_ms * 1e-3)
+    # ---- the same loop for >= 1 s (a burst of K steps is only a few ms): what the clocks settle at
+    n_sus = max(args.steps, int(1.1e3 / max(timed_ms / args.steps, 1e-3)))
+    barrier()
+    eng.event_record(0)
+    for _ in range(n_sus):
+        eng.schedule(dev_tokens, detail=False, out=dev_dec, asynchronous=True, **sched_kw)
+    eng.event_record(1)
+    eng.synchronize()
+    sus_ms = max_over_ranks(eng.event_elapsed_ms())
+    value_sustained = world * R * n_sus / (sus_ms * 1e-3)
+    dev_dec_async = epp.decisions_from_torch(dev_dec)      # what the timed (pipelined, detail-less) configuration decided
     # ---- per-kernel pass: the same K steps again, one at a time, each kernel bracketed by CUDA events on the launch
     # stream (roofline.launch_ms); repeated until the clock sampler has seen the GPU under this load
     kms = np.zeros(8)
@@ -407,7 +423,7 @@ def run_gpu(args, rank, world, local_rank):
 
     # ---- e2e: host buffers through the C ABI (H2D of the prompts + D2H of the decisions inside the timed region)
     e2e_steps = max(1, min(args.steps, 10))
-    e2e_wall, e2e_value = float("nan"), None
+    e2e_wall, e2e_value, h2d_peak = float("nan"), None, None
     if not args.no_e2e:
         for _ in range(max(1, min(args.warmup, 3))):
             eng.schedule(host_tokens, uniform_len=w.prompt_bytes, detail=False, out=host_dec)
@@ -420,8 +436,29 @@ def run_gpu(args, rank, world, local_rank):
         barrier()
         e2e_value = world * R * e2e_steps / e2e_wall
         # sanity: device-pointer and host-pointer paths agree
-        np.testing.assert_array_equal(epp.decisions_from_torch(dev_dec), host_dec)
+        np.testing.assert_array_equal(dev_dec_async, host_dec)
+        # what the link can do: a plain pinned -> device copy of the same bytes, timed with CUDA events
+        pin_t = torch.from_numpy(host_tokens.view(np.int32))
+        stage = torch.empty_like(dev_tokens[:, : w.T]) if args.pitch_pad else torch.empty_like(dev_tokens)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = float("inf")
+        for _ in range(4):
+            barrier()
+            ev0.record()
+            stage.copy_(pin_t, non_blocking=True)
+            ev1.record()
+            ev1.synchronize()
+            best = min(best, ev0.elapsed_time(ev1))
+        h2d_peak = nbytes / (max_over_ranks(best) * 1e-3) / 1e9
+        del stage
 
+    full_index = None
+    if world == 1 and not args.no_full_index and args.index_fill == 0:
+        full_index = full_index_leg(args, w, trace, dev_tokens, dev_dec, dev_dec_async, local_rank, sched_kw, args.steps, epp, helpers)
+        full_index["vs_small_index"] = full_index["value"] / value
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        sharded = sharded_leg(args, rank, world, local_rank, max(3, min(args.steps, 10)), 3)
     if rank == 0:
         peak, peak_src = _peaks()
         kms /= args.steps
@@ -441,7 +478,23 @@ def run_gpu(args, rank, world, local_rank):
                 pass
         n_threads = os.cpu_count() or 1
         os.sched_setaffinity(0, all_cpus)            # the CPU leg gets every host core again
-        cpu, _ = cpu_baseline(w, trace, n_threads, tokens=host_tokens) if not args.no_cpu else ({"value": None}, None)
+        cpu, odec = cpu_baseline(w, trace, n_threads, tokens=host_tokens) if not args.no_cpu else ({"value": None}, None)
+        # ---- parity IN THIS RUN: the decisions of the timed configurations (async device batches; host-buffer e2e batches)
+        # against the oracle decisions the CPU leg just computed for the same batch
+        parity = None
+        if odec is not None:
+            def same(dec):
+                ok = odec["status"] == 0
+                pf = dec["prefill_pick"].astype(np.int64)
+                pf[pf == 0xFFFFFFFF] = -1
+                return bool((dec["status"] == odec["status"]).all()
+                            and (dec["pick"][ok].astype(np.int64) == odec["pick"][ok]).all()
+                            and (dec["score"][ok].view(np.uint64) == odec["score"][ok].view(np.uint64)).all()
+                            and (dec["tie_count"][ok].astype(np.int64) == odec["tie_count"][ok]).all()
+                            and (pf[ok] == odec["prefill_pick"][ok]).all())
+            parity = {"requests_checked": int(odec.shape[0]), "fields": "status, pick, score bits, tie_count, prefill_pick",
+                      "async_device_batches_vs_oracle": same(dev_dec_async[: odec.shape[0]]),
+                      "e2e_host_batches_vs_oracle": same(host_dec[: odec.shape[0]]) if not args.no_e2e else None}
         index_write = None
         if world == 1 and not args.no_index_write:
             try:
@@ -454,16 +507,27 @@ def run_gpu(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": timed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 (XXH64) + f64 (scores)", "data": "synthetic",
-            "config": _config_json(w, world, {"numa_node_of_rank0": numa_node}),
+            "config": _config_json(w, world),
+            "numa_node_of_rank0": numa_node,
+            "value_sustained": value_sustained,
+            "sustained": {"steps": n_sus, "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / n_sus},
+            "parity_in_run": parity,
+            "full_index": full_index,
+            "sharded": sharded,
             "timing": "CUDA events on the engine launch stream around K back-to-back (EPP_BATCH_ASYNC) batches, max over ranks",
             "wall_ms_per_step": wall / args.steps * 1e3,
             "device_ms_per_step": dev_ms / args.steps,
             "kernel_ms_per_step": {"k_hash_fused (lengths+digests+chain)": kms[1] + kms[0] + kms[2], "match+score+pick (k_match_pick_sparse + overflow pass)": kms[3]},
+            "kernel_times_how": "synchronous device batches, every kernel bracketed by CUDA events on the engine's stream",
             "algorithmic_bytes_per_step": int(algo_total),
             "algorithmic_gbs_whole_step": algo_total / (timed_ms / args.steps * 1e-3) / 1e9,
             "whole_step_frac_of_peak": (algo_total / (timed_ms / args.steps * 1e-3) / 1e9) / peak if peak else None,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(R * 32),
-                    "steps": e2e_steps, "ms_per_step": e2e_wall / e2e_steps * 1e3},
+                    "steps": e2e_steps, "ms_per_step": e2e_wall / e2e_steps * 1e3,
+                    "h2d_peak_gbs": h2d_peak,
+                    "h2d_peak_how": "plain pinned -> device copy of the same bytes (torch copy_, CUDA events, best of 4), same run",
+                    "achieved_gbs": (nbytes + R * 32) / (e2e_wall / e2e_steps) / 1e9 if e2e_value else None,
+                    "frac_of_pcie": ((nbytes + R * 32) / (e2e_wall / e2e_steps) / 1e9) / h2d_peak if e2e_value and h2d_peak else None},
             "gpu_launches": int(timed_launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_hash_fused", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -484,9 +548,11 @@ def run_gpu(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def run_gpu_sharded(args, rank, world, local_rank):
-    """BASELINE config 5: the endpoint index sharded across the GPUs (4 096 endpoints per GPU), every rank hashes the
-    same batch, two small NCCL exchanges per batch (presence masks, best records).  value = R decisions per step."""
+def sharded_leg(args, rank, world, local_rank, steps, warmup):
+    """BASELINE config 5: the endpoint index sharded across the GPUs (4 096 endpoints per GPU, E = 4 096 x N), every
+    rank schedules the same batch of R requests; per batch two small exchanges (presence masks, best records) over
+    NVLink peer memory (default) or NCCL (--sharded-nccl).  torch.distributed must be initialised when world > 1.
+    Returns the result dict on rank 0, None elsewhere.  value = R decisions per step (the ranks decide TOGETHER)."""
     import importlib
 
     import torch
@@ -497,11 +563,6 @@ def run_gpu_sharded(args, rank, world, local_rank):
     from tools import tracegen as tg
     sh = importlib.import_module("llm-d-inference-scheduler_b200.sharded")
 
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    epp.build.build()
-    tg.build()
     base = tg.baseline_configs()["config5"]
     w = base.scaled(E=4096 * world, R=args.requests or base.R, name="config5")
     trace = tg.Trace(w)
@@ -534,12 +595,15 @@ def run_gpu_sharded(args, rank, world, local_rank):
         step = lambda: sh.schedule_sharded_p2p(eng, dev_tokens, w.prompt_bytes, out=out_dec)
     else:
         step = lambda: sh.schedule_sharded(eng, dev_tokens, w.prompt_bytes, d)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         dec = step()
     barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    ev0.record()
+    for _ in range(steps):
         dec = step()
+    ev1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     barrier()
@@ -561,25 +625,80 @@ def run_gpu_sharded(args, rank, world, local_rank):
                       and (got["score"].view(np.uint64) == ref_dec["score"].view(np.uint64)).all()
                       and (got["tie_count"] == ref_dec["tie_count"]).all())
         full.close()
+    res = None
     if rank == 0:
         W = (w.max_prefix_blocks + 31) // 32
-        print(json.dumps({
-            "metric": METRIC + " (endpoint-sharded index)", "value": R * args.steps / wall, "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64 (XXH64) + f64 (scores)", "data": "synthetic",
-            "config": _config_json(w, world, {
-                "parallelism": f"endpoint index sharded over {world} GPUs ({4096} endpoints each), every rank hashes the "
-                               f"batch; per batch two exchanges: OR of {R * W * 4} B of presence masks per rank, merge of "
-                               f"{R * 24} B of best records per rank -- "
-                               + ("read straight from the peers' memory over NVLink by the engine's own kernels "
-                                  "(CUDA IPC, release/acquire flags; no NCCL on the data path)" if use_p2p else
-                                  "NCCL all-gathers + torch OR (--sharded-nccl)")}),
-            "decisions_ok": int((epp.decisions_from_torch(dec)["status"] == 0).sum()),
-            "parity_vs_unsharded_engine": parity,
-        }), flush=True)
+        res = {"value": R * steps / wall, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+               "ms_per_step": wall / steps * 1e3, "timing": "host clock around K blocking steps, max over ranks (every step ends with a stream synchronisation)",
+               "endpoints": w.E, "batch_requests": R,
+               "exchange": ("NVLink peer memory: masks OR-reduced and best records merged straight out of the peers' buffers by "
+                            "the engine's own kernels (CUDA IPC, release/acquire flags; no NCCL on the data path)" if use_p2p
+                            else "NCCL all-gathers + torch OR (--sharded-nccl)"),
+               "exchange_bytes_per_rank_per_step": {"presence_masks": int(R * W * 4), "best_records": int(R * 24)},
+               "decisions_ok": int((epp.decisions_from_torch(dec)["status"] == 0).sum()),
+               "parity_vs_unsharded": parity, "parity_requests_checked": min(R, 4096),
+               "config": _config_json(w, world, {
+                   "parallelism": f"endpoint index sharded over {world} GPUs (4096 endpoints each); every rank schedules the same batch"})}
     eng.close()
+    del dev_tokens
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_gpu_sharded(args, rank, world, local_rank):
+    """--workload config5: only the endpoint-sharded leg, as its own JSON line."""
+    import torch
+    import torch.distributed as dist
+
+    import epp_b200 as epp
+    from tools import tracegen as tg
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    epp.build.build()
+    tg.build()
+    res = sharded_leg(args, rank, world, local_rank, args.steps, args.warmup)
+    if rank == 0:
+        out = {"metric": METRIC + " (endpoint-sharded index)", "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "u64 (XXH64) + f64 (scores)", "data": "synthetic"}
+        out.update(res)
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def full_index_leg(args, w, trace, dev_tokens, dev_dec, ref_dec, local_rank, sched_kw, steps, epp, helpers):
+    """The same batch against a PRODUCTION-SIZE index: every endpoint's LRU full (31 250 blocks per endpoint, the
+    reference default, approximateprefix/types.go:110) -> 1.29e8 pairs, a table far larger than L2.  The filler
+    hashes never match a prompt, so the decisions must not change."""
+    import torch
+    per = 31250
+    eng = helpers.make_engine(w, device=local_rank)
+    t0 = time.perf_counter()
+    helpers.setup_engine(eng, w, trace, filler_per_endpoint=per)
+    setup_s = time.perf_counter() - t0
+    st = eng.stats()
+    for _ in range(3):
+        eng.schedule(dev_tokens, detail=False, out=dev_dec, **sched_kw)
+    torch.cuda.synchronize()
+    eng.event_record(0)
+    for _ in range(steps):
+        eng.schedule(dev_tokens, detail=False, out=dev_dec, asynchronous=True, **sched_kw)
+    eng.event_record(1)
+    eng.synchronize()
+    ms = eng.event_elapsed_ms() / steps
+    same = bool((epp.decisions_from_torch(dev_dec).view(np.uint8) == ref_dec.view(np.uint8)).all())
+    eng.schedule(dev_tokens, detail=False, out=dev_dec, **sched_kw)
+    k = eng.stats()["last_kernel_ms"]
+    out = {"value": w.R / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "filler_per_endpoint": per,
+           "index_pairs": int(st["index_pairs"]), "index_slots": int(st["index_slots"]),
+           "index_table_bytes": int(st["index_slots"]) * 32, "device_bytes": int(st["device_bytes"]),
+           "decisions_equal_to_small_index": same, "setup_s": setup_s,
+           "kernel_ms": {"hash": k[0] + k[1] + k[2], "match+score+pick": k[3]}}
+    eng.close()
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -595,6 +714,8 @@ def main():
                     help="config5: exchange masks / records with NCCL all-gathers instead of the peer-memory kernels")
     ap.add_argument("--no-index-write", action="store_true", help="skip the index write-side leg (SURVEY 8(f).1)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs only)")
+    ap.add_argument("--no-full-index", action="store_true", help="skip the production-size-index leg")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the endpoint-sharded (config 5) leg")
     ap.add_argument("--index-fill", type=int, default=0,
                     help="extra never-matching index entries per endpoint (31250 = every endpoint's LRU full: 1.28e8 pairs, "
                          "a table far larger than L2); decisions are unchanged")

@@ -215,7 +215,8 @@ struct Work {
 // kSharded: endpoint-sharded mode (the stop rule comes from p.global_masks).
 // kTie: the reproducible random tie rule is compiled in (epp_config.tie_seed != 0); the deterministic lowest-slot
 // build carries none of its code or registers.
-template <bool kCg, bool kSharded, bool kTie>
+// kStages: stages of the handler compiled in (score.cuh: decide_stages).
+template <bool kCg, bool kSharded, bool kTie, int kStages>
 __device__ __forceinline__ void match_request(const PickParams &p, const int64_t r, const int lane, const bool counting,
                                               Work &wk) {
     const uint32_t shard_lo = p.index.ep_begin, shard_hi = min(p.index.ep_end, (uint32_t)p.E);
@@ -310,7 +311,7 @@ __device__ __forceinline__ void match_request(const PickParams &p, const int64_t
     // ---- a5-a14: the profiles of the handler
     epp_decision d;
     epp_decision_detail dd;
-    decide_stages(p, r, total, p.n_profiles >= 2 ? ld_row<kCg>(p.in_len + r) : 0,
+    decide_stages<kStages>(p, r, total, (kStages >= 2 && p.n_profiles >= 2) ? ld_row<kCg>(p.in_len + r) : 0,
                   [&](int pi, uint64_t key) { return eval_profile_lanes<kTie>(p.prof[pi], p.E, m, total, lane, p.lora, lora_st, p.tie_seed, key); },
                   [&](uint32_t e) { return m.n ? (int32_t)map_get(m, e) : 0; }, d, dd);
     if (lane == 0) {

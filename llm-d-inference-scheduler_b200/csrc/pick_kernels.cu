@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kPickWarps * 32) k_match_pick(PickParams p, in
         const uint32_t adapter = p.model_ids ? p.model_ids[r] : 0u;
         epp_decision d;
         epp_decision_detail dd;
-        decide_stages(p, r, total, p.n_profiles >= 2 ? p.in_len[r] : 0,
+        decide_stages<3>(p, r, total, p.n_profiles >= 2 ? p.in_len[r] : 0,
                       [&](int pi, uint64_t key) { return eval_profile(p.prof[pi], p.E, cnt32, list, nl, total, lane, p.lora, adapter, p.tie_seed, key); },
                       [&](uint32_t e) { return (int32_t)cnt_get(cnt32, e); }, d, dd);
         if (lane == 0) {
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(256) k_dense_pick(DensePickParams p) {
     const uint32_t adapter = p.model_ids ? p.model_ids[r] : 0u;
     epp_decision d;
     epp_decision_detail dd;
-    decide_stages(p, r, total, p.in_len ? p.in_len[r] : 0,
+    decide_stages<3>(p, r, total, p.in_len ? p.in_len[r] : 0,
                   [&](int pi, uint64_t key) { return eval_profile_dense(p.prof[pi], p.E, mrow, total, lane, p.lora, adapter, p.tie_seed, key); },
                   [&](uint32_t e) { return mrow[e]; }, d, dd);
     if (lane == 0) {

@@ -210,7 +210,8 @@ __device__ __forceinline__ bool pd_decide(int64_t nct, int64_t in_len_bytes, int
 // primary (decode) pick -> [encode stage for multimodal requests, disagg_profile_handler.go:284-295] -> [P/D decider ->
 // prefill stage, :296-308].  eval(profile index, tie key) runs one SchedulerProfile for the request (all lanes call it
 // together), match_of(slot) returns the request's matchBlocks on a slot.  P = PickParams or DensePickParams.
-template <typename P, typename Eval, typename MatchOf>
+// kStages: how many stages are compiled in (1 = single profile, 2 = + P/D decider and prefill, 3 = + encode).
+template <int kStages, typename P, typename Eval, typename MatchOf>
 __device__ __forceinline__ void decide_stages(const P &p, int64_t r, int32_t total, int64_t in_len, Eval eval,
                                               MatchOf match_of, epp_decision &d, epp_decision_detail &dd) {
     const uint64_t key = 4 * (p.tie_base + (uint64_t)r);
@@ -225,12 +226,12 @@ __device__ __forceinline__ void decide_stages(const P &p, int64_t r, int32_t tot
     dd.prefill_score = 0.0; dd.prefill_tie_count = 0; dd.prefill_ran = 0;
     dd.encode_score = 0.0; dd.encode_pick = EPP_NO_ENDPOINT; dd.encode_tie_count = 0; dd.encode_ran = 0; dd.reserved = 0;
     if (!b0.ties) return;                                 // no decode endpoint: the cycle ends (ProcessResults :335-338)
-    if (p.encode_on && p.multimodal && p.multimodal[r]) {
+    if (kStages >= 3 && p.encode_on && p.multimodal && p.multimodal[r]) {
         dd.encode_ran = 1;
         const Best b2 = eval(2, key + 2);
         if (b2.ties) { dd.encode_pick = b2.pick; dd.encode_score = b2.val; dd.encode_tie_count = b2.ties; }
     }
-    if (p.n_profiles >= 2) {
+    if (kStages >= 2 && p.n_profiles >= 2) {
         const bool go = p.always_disagg || pd_decide(p.non_cached_tokens, in_len, d.match_blocks, p.block_size_tokens);
         if (go) {
             dd.prefill_ran = 1;
