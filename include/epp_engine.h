@@ -351,6 +351,12 @@ EPP_API int32_t epp_shard_merge(epp_engine *h, int64_t n_requests, int32_t n_ran
 EPP_API int32_t epp_shard_p2p_export(epp_engine *h, int64_t max_requests, uint8_t *out_handle, uint64_t *out_ptr);
 EPP_API int32_t epp_shard_p2p_connect(epp_engine *h, int32_t n_ranks, int32_t rank, const void *peers, int32_t ipc_handles);
 EPP_API int32_t epp_shard_schedule_p2p(epp_engine *h, const epp_batch *batch, epp_decision *out);
+/* The same batch ONE phase at a time (0: hashes + local masks + flag 1; 1: OR of the peers' masks + local best records +
+ * flag 2; 2: gather + merge -> out), each call synchronising before it returns: for ranks that share a GPU, whose
+ * device-side waits could starve each other -- step all ranks through phase 0, then all through 1, then 2.
+ * A peer that times out (or whose flags are poisoned) breaks the exchange for good: every later call fails with
+ * EPP_ERR_STATE until epp_shard_p2p_export / _connect are called again on every rank. */
+EPP_API int32_t epp_shard_p2p_phase(epp_engine *h, const epp_batch *batch, epp_decision *out, int32_t phase);
 
 /* The configuration the engine was created with. */
 EPP_API int32_t epp_get_config(epp_engine *h, epp_config *out);

@@ -128,6 +128,7 @@ SIGNATURES = {
     "epp_shard_p2p_export": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_uint64)]),
     "epp_shard_p2p_connect": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "epp_shard_schedule_p2p": (C.c_int32, [C.c_void_p, C.POINTER(Batch), C.c_void_p]),
+    "epp_shard_p2p_phase": (C.c_int32, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_int32]),
     "epp_get_config": (C.c_int32, [C.c_void_p, C.POINTER(Config)]),
     "epp_batcher_create": (C.c_int32, [C.c_void_p, C.POINTER(BatcherCfg), C.POINTER(C.c_void_p)]),
     "epp_batcher_destroy": (C.c_int32, [C.c_void_p]),

@@ -138,6 +138,8 @@ struct epp_engine {
     std::vector<void *> p2p_peer;   // peers' buffers in this process's address space (own buffer at [p2p_rank])
     DevBuf p2p_peer_dev, p2p_gmasks, p2p_allbest, p2p_err;
     unsigned long long p2p_epoch = 0;
+    bool p2p_broken = false;        // a wait timed out: the ranks are out of step until the buffers are connected again
+    int p2p_launches = 0;
 
     epp_stats stats{};
 };
@@ -1454,7 +1456,17 @@ extern "C" int32_t epp_shard_p2p_export(epp_engine *h, int64_t max_requests, uin
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
     EPP_TRY(join_streams(h));
-    if (h->p2p_buf) return fail(EPP_ERR_STATE, "the exchange buffer is already exported");
+    if (h->p2p_buf && !h->p2p_broken) return fail(EPP_ERR_STATE, "the exchange buffer is already exported");
+    if (h->p2p_buf) {                                           // broken exchange: start over with a fresh buffer
+        for (int g = 0; g < (int)h->p2p_peer.size(); g++)
+            if (h->p2p_ipc && g != h->p2p_rank && h->p2p_peer[g]) cudaIpcCloseMemHandle(h->p2p_peer[g]);
+        h->p2p_peer.clear();
+        cudaFree(h->p2p_buf);
+        h->dev_bytes -= h->p2p_bytes;
+        h->p2p_buf = nullptr;
+        h->p2p_broken = false;
+        h->p2p_epoch = 0;
+    }
     const size_t W = (size_t)mask_words_of(h);
     h->p2p_masks_off = kP2pHeader;
     h->p2p_best_off = (kP2pHeader + (size_t)max_requests * W * sizeof(uint32_t) + 255) & ~(size_t)255;
@@ -1507,65 +1519,124 @@ extern "C" int32_t epp_shard_p2p_connect(epp_engine *h, int32_t n_ranks, int32_t
 
 // One batch of the sharded protocol with both exchanges done by this rank's own kernels over peer memory.  Every rank
 // calls it with the same batch; the decisions (identical on every rank) land in `out` (device pointer).
-extern "C" int32_t epp_shard_schedule_p2p(epp_engine *h, const epp_batch *batch, epp_decision *out) {
-    if (!h || !out) return fail(EPP_ERR_INVALID, "NULL argument");
-    std::lock_guard<std::mutex> lk(h->mu);
-    EPP_TRY(set_device(h));
-    EPP_TRY(join_streams(h));
-    if (h->p2p_peer.empty()) return fail(EPP_ERR_STATE, "epp_shard_p2p_connect has not been called");
-    if (!h->pool_ready) return fail(EPP_ERR_STATE, "epp_pool_set has not been called (after epp_shard_set)");
-    BatchView v;
-    EPP_TRY(check_batch(h, batch, v));
-    if (!v.device) return fail(EPP_ERR_INVALID, "epp_shard_schedule_p2p takes device-pointer batches (EPP_BATCH_DEVICE_PTRS)");
-    if (v.R > h->p2p_R) return fail(EPP_ERR_CAPACITY, "batch of %lld requests exceeds the exported exchange buffer (%lld)", (long long)v.R, (long long)h->p2p_R);
-    if (v.R == 0) return EPP_OK;
-    v.async = false;
-    h->kept_R = 0;
-    h->shard_R = 0;
-    EPP_TRY(commit_locked(h));
-    EPP_TRY(run_batch(h, v, Mode::HashOnly, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+// The protocol is three phases; epp_shard_schedule_p2p runs them back to back (the waits happen ON THE DEVICE, the host
+// only waits at the end), epp_shard_p2p_phase runs ONE phase and synchronises, so that ranks which share a GPU -- whose
+// spin-wait kernels could starve each other -- can be stepped phase by phase from one host thread (tests, small setups).
+static constexpr unsigned long long kP2pPoison = ~0ull;
+
+static unsigned long long p2p_timeout_ns() {
+    unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
+    if (const char *tv = getenv("EPP_P2P_TIMEOUT_MS")) timeout_ns = (unsigned long long)std::max(1, atoi(tv)) * 1000ull * 1000ull;
+    return timeout_ns;
+}
+
+// A wait that timed out (or met a poisoned flag) leaves the ranks out of step for good: the exchange is marked broken,
+// this rank's flags are poisoned so that the peers fail too instead of reading half-written buffers, and every later
+// call fails until the buffers are exported / connected again.
+static int32_t p2p_check(epp_engine *h, cudaStream_t s, unsigned long long epoch) {
+    int err = 0;
+    CUDA_TRY(cudaMemcpyAsync(&err, h->p2p_err.p, sizeof err, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (!err) return EPP_OK;
+    h->p2p_broken = true;
+    uint8_t *own = static_cast<uint8_t *>(h->p2p_buf);
+    CUDA_TRY(launch_p2p_signal(reinterpret_cast<unsigned long long *>(own + kP2pFlag1), kP2pPoison, s));
+    CUDA_TRY(launch_p2p_signal(reinterpret_cast<unsigned long long *>(own + kP2pFlag2), kP2pPoison, s));
+    CUDA_TRY(cudaMemsetAsync(h->p2p_err.p, 0, sizeof(int), s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    const bool poisoned = err > 64;
+    return fail(EPP_ERR_NCCL, poisoned ? "peer rank %d reported a broken sharded exchange (batch %llu); re-export and re-connect the exchange buffers"
+                                       : "peer rank %d did not reach batch %llu of the sharded exchange within %llu ms; the exchange is broken until the buffers are exported and connected again",
+                (poisoned ? err - 64 : err) - 1, epoch, p2p_timeout_ns() / 1000000ull);
+}
+
+static int32_t p2p_phase(epp_engine *h, const BatchView &v, epp_decision *out, int phase) {
     const int64_t R = v.R;
     const int n = h->p2p_ranks;
     const size_t W = (size_t)mask_words_of(h);
-    const unsigned long long epoch = ++h->p2p_epoch;
-    unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
-    if (const char *tv = getenv("EPP_P2P_TIMEOUT_MS")) timeout_ns = (unsigned long long)std::max(1, atoi(tv)) * 1000ull * 1000ull;
     cudaStream_t s = h->slot[0].stream;
     uint8_t *own = static_cast<uint8_t *>(h->p2p_buf);
     unsigned char *const *peers = h->p2p_peer_dev.as<unsigned char *>();
-    int launches = 0;
     const size_t mask_bytes = ((size_t)R * W * sizeof(uint32_t) + 15) & ~(size_t)15;
-    CUDA_TRY(h->p2p_gmasks.reserve(mask_bytes, &h->dev_bytes));
-    CUDA_TRY(h->p2p_allbest.reserve(sizeof(epp_shard_best) * (size_t)R * (size_t)n, &h->dev_bytes));
-    // phase 1: local presence masks -> own exchange buffer, raise flag 1
-    CUDA_TRY(launch_shard_probe(R, h->cfg.max_prefix_blocks, h->hashes.as<uint64_t>(), h->nblocks.as<int32_t>(), index_view(h),
-                                reinterpret_cast<uint32_t *>(own + h->p2p_masks_off), (int32_t)W, s, &launches));
-    CUDA_TRY(launch_p2p_signal(reinterpret_cast<unsigned long long *>(own + kP2pFlag1), epoch, s));
-    // exchange 1: OR of every rank's masks, read straight from the peers
-    CUDA_TRY(launch_p2p_wait(peers, n, kP2pFlag1, epoch, h->p2p_err.as<int>(), timeout_ns, s));
-    CUDA_TRY(launch_p2p_or_masks(peers, n, h->p2p_masks_off, mask_bytes, h->p2p_gmasks.p, s));
-    // phase 2: global stop rule on the local counts -> local best record in the own exchange buffer, raise flag 2
-    Work w{0, R, nullptr, nullptr, nullptr, 0, nullptr, 0, h->hashes.as<uint64_t>(), h->nblocks.as<int32_t>()};
-    PickParams pp = pick_params(h, w, h->decisions.as<epp_decision>(), nullptr, nullptr);
-    pp.model_ids = v.model_ids;
-    pp.global_masks = h->p2p_gmasks.as<uint32_t>();
-    pp.mask_words = (int32_t)W;
-    pp.shard_out = reinterpret_cast<epp_shard_best *>(own + h->p2p_best_off);
-    EPP_TRY(launch_match(h, h->slot[0], pp, &launches));
-    CUDA_TRY(launch_p2p_signal(reinterpret_cast<unsigned long long *>(own + kP2pFlag2), epoch, s));
+    const unsigned long long timeout_ns = p2p_timeout_ns();
+    int launches = 0;
+    if (phase == 0) {
+        // phase 1: hashes + local presence masks -> own exchange buffer, raise flag 1
+        h->kept_R = 0;
+        h->shard_R = 0;
+        EPP_TRY(commit_locked(h));
+        EPP_TRY(run_batch(h, v, Mode::HashOnly, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+        ++h->p2p_epoch;
+        CUDA_TRY(h->p2p_gmasks.reserve(mask_bytes, &h->dev_bytes));
+        CUDA_TRY(h->p2p_allbest.reserve(sizeof(epp_shard_best) * (size_t)R * (size_t)n, &h->dev_bytes));
+        CUDA_TRY(launch_shard_probe(R, h->cfg.max_prefix_blocks, h->hashes.as<uint64_t>(), h->nblocks.as<int32_t>(), index_view(h),
+                                    reinterpret_cast<uint32_t *>(own + h->p2p_masks_off), (int32_t)W, s, &launches));
+        CUDA_TRY(launch_p2p_signal(reinterpret_cast<unsigned long long *>(own + kP2pFlag1), h->p2p_epoch, s));
+        h->p2p_launches = launches + 1;
+        return EPP_OK;
+    }
+    const unsigned long long epoch = h->p2p_epoch;
+    if (phase == 1) {
+        // exchange 1: OR of every rank's masks, read straight from the peers; phase 2: global stop rule on the local
+        // counts -> local best record in the own exchange buffer, raise flag 2
+        CUDA_TRY(launch_p2p_wait(peers, n, kP2pFlag1, epoch, h->p2p_err.as<int>(), timeout_ns, s));
+        CUDA_TRY(launch_p2p_or_masks(peers, n, h->p2p_masks_off, mask_bytes, h->p2p_gmasks.p, s));
+        Work w{0, R, nullptr, nullptr, nullptr, 0, nullptr, 0, h->hashes.as<uint64_t>(), h->nblocks.as<int32_t>()};
+        PickParams pp = pick_params(h, w, h->decisions.as<epp_decision>(), nullptr, nullptr);
+        pp.model_ids = v.model_ids;
+        pp.global_masks = h->p2p_gmasks.as<uint32_t>();
+        pp.mask_words = (int32_t)W;
+        pp.shard_out = reinterpret_cast<epp_shard_best *>(own + h->p2p_best_off);
+        EPP_TRY(launch_match(h, h->slot[0], pp, &launches));
+        // a rank whose wait failed must NOT publish records computed from an incomplete OR: the signal kernel checks
+        CUDA_TRY(launch_p2p_signal_unless(reinterpret_cast<unsigned long long *>(own + kP2pFlag2), epoch, h->p2p_err.as<int>(), s));
+        h->p2p_launches += launches + 3;
+        return EPP_OK;
+    }
     // exchange 2 + phase 3: gather every rank's records from the peers and merge
     CUDA_TRY(launch_p2p_wait(peers, n, kP2pFlag2, epoch, h->p2p_err.as<int>(), timeout_ns, s));
     CUDA_TRY(launch_p2p_gather(peers, n, h->p2p_best_off, sizeof(epp_shard_best) * (size_t)R, h->p2p_allbest.p, s));
     CUDA_TRY(launch_shard_merge(R, n, h->p2p_allbest.as<epp_shard_best>(), h->nblocks.as<int32_t>(), out, s, &launches));
-    int err = 0;
-    CUDA_TRY(cudaMemcpyAsync(&err, h->p2p_err.p, sizeof err, cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    h->stats.last_kernel_launches = (uint64_t)launches + 6;
-    if (err) {
-        CUDA_TRY(cudaMemset(h->p2p_err.p, 0, sizeof(int)));
-        return fail(EPP_ERR_NCCL, "peer rank %d did not reach batch %llu of the sharded exchange within %llu ms", err - 1, epoch, timeout_ns / 1000000ull);
-    }
+    h->stats.last_kernel_launches = (uint64_t)(h->p2p_launches + launches + 2);
+    EPP_TRY(p2p_check(h, s, epoch));
     h->stats.n_batches++;
     h->stats.n_decisions += (uint64_t)R;
+    return EPP_OK;
+}
+
+static int32_t p2p_prepare(epp_engine *h, const epp_batch *batch, epp_decision *out, BatchView &v) {
+    if (!h || !out) return fail(EPP_ERR_INVALID, "NULL argument");
+    EPP_TRY(set_device(h));
+    EPP_TRY(join_streams(h));
+    if (h->p2p_peer.empty()) return fail(EPP_ERR_STATE, "epp_shard_p2p_connect has not been called");
+    if (h->p2p_broken) return fail(EPP_ERR_STATE, "the sharded exchange is broken (an earlier batch timed out): export and connect the buffers again");
+    if (h->shard_begin == 0 && h->shard_end == 0xFFFFFFFFu) return fail(EPP_ERR_STATE, "epp_shard_set has not been called: every rank would count every endpoint");
+    if (!h->pool_ready) return fail(EPP_ERR_STATE, "epp_pool_set has not been called (after epp_shard_set)");
+    EPP_TRY(check_batch(h, batch, v));
+    if (!v.device) return fail(EPP_ERR_INVALID, "the sharded peer-memory entry points take device-pointer batches (EPP_BATCH_DEVICE_PTRS)");
+    if (v.R > h->p2p_R) return fail(EPP_ERR_CAPACITY, "batch of %lld requests exceeds the exported exchange buffer (%lld)", (long long)v.R, (long long)h->p2p_R);
+    v.async = false;
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_shard_schedule_p2p(epp_engine *h, const epp_batch *batch, epp_decision *out) {
+    if (!h) return fail(EPP_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    BatchView v;
+    EPP_TRY(p2p_prepare(h, batch, out, v));
+    if (v.R == 0) return EPP_OK;
+    for (int phase = 0; phase < 3; phase++) EPP_TRY(p2p_phase(h, v, out, phase));
+    return EPP_OK;
+}
+
+extern "C" int32_t epp_shard_p2p_phase(epp_engine *h, const epp_batch *batch, epp_decision *out, int32_t phase) {
+    if (!h) return fail(EPP_ERR_INVALID, "NULL argument");
+    if (phase < 0 || phase > 2) return fail(EPP_ERR_INVALID, "phase %d out of range [0,2]", phase);
+    std::lock_guard<std::mutex> lk(h->mu);
+    BatchView v;
+    EPP_TRY(p2p_prepare(h, batch, out, v));
+    if (v.R == 0) return EPP_OK;
+    EPP_TRY(p2p_phase(h, v, out, phase));
+    if (phase < 2) CUDA_TRY(cudaStreamSynchronize(h->slot[0].stream));      // phase 2 synchronises in p2p_check
     return EPP_OK;
 }

@@ -211,6 +211,7 @@ cudaError_t launch_shard_merge(int64_t R, int32_t n_ranks, const epp_shard_best 
 
 // shard_p2p.cu: exchanges of the endpoint-sharded mode over NVLink peer memory (no NCCL)
 cudaError_t launch_p2p_signal(unsigned long long *flag, unsigned long long epoch, cudaStream_t s);
+cudaError_t launch_p2p_signal_unless(unsigned long long *flag, unsigned long long epoch, const int *err_dev, cudaStream_t s);
 cudaError_t launch_p2p_wait(unsigned char *const *peers_dev, int n, size_t flag_off, unsigned long long epoch, int *err_dev,
                             unsigned long long timeout_ns, cudaStream_t s);
 cudaError_t launch_p2p_or_masks(unsigned char *const *peers_dev, int n, size_t masks_off, unsigned long long n_bytes,

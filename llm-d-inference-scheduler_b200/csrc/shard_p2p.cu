@@ -32,6 +32,14 @@ __global__ void k_p2p_signal(unsigned long long *flag, unsigned long long epoch)
     st_release_sys(flag, epoch);
 }
 
+// The same, unless an earlier wait of this batch failed (*err != 0): records computed from an incomplete OR of the masks
+// must never be published.
+__global__ void k_p2p_signal_unless(unsigned long long *flag, unsigned long long epoch, const int *err) {
+    if (*err) return;
+    __threadfence_system();
+    st_release_sys(flag, epoch);
+}
+
 // One thread per peer: wait until its flag reaches `epoch`.  A peer that never arrives must not hang the GPU: after
 // timeout_ns the wait gives up and reports the rank in *err (the host turns it into an error code).
 __global__ void k_p2p_wait(unsigned char *const *peers, int n, size_t flag_off, unsigned long long epoch, int *err,
@@ -40,7 +48,13 @@ __global__ void k_p2p_wait(unsigned char *const *peers, int n, size_t flag_off, 
     if (g >= n) return;
     const unsigned long long *f = reinterpret_cast<const unsigned long long *>(peers[g] + flag_off);
     const unsigned long long t0 = globaltimer_ns();
-    while (ld_acquire_sys(f) < epoch) {
+    for (;;) {
+        const unsigned long long v = ld_acquire_sys(f);
+        if (v == ~0ull) {                              // the peer poisoned its flags: its exchange is broken
+            atomicExch(err, 64 + g + 1);
+            return;
+        }
+        if (v >= epoch) return;
         __nanosleep(256);
         if (globaltimer_ns() - t0 > timeout_ns) {
             atomicExch(err, g + 1);
@@ -75,6 +89,10 @@ __global__ void k_p2p_gather(unsigned char *const *peers, int n, size_t best_off
 
 cudaError_t launch_p2p_signal(unsigned long long *flag, unsigned long long epoch, cudaStream_t s) {
     k_p2p_signal<<<1, 1, 0, s>>>(flag, epoch);
+    return cudaGetLastError();
+}
+cudaError_t launch_p2p_signal_unless(unsigned long long *flag, unsigned long long epoch, const int *err_dev, cudaStream_t s) {
+    k_p2p_signal_unless<<<1, 1, 0, s>>>(flag, epoch, err_dev);
     return cudaGetLastError();
 }
 cudaError_t launch_p2p_wait(unsigned char *const *peers_dev, int n, size_t flag_off, unsigned long long epoch, int *err_dev,

@@ -352,6 +352,13 @@ class Engine:
         self._check(self._lib.epp_shard_schedule_p2p(self._h, C.byref(b), _ptr(out_decisions)))
         return R
 
+    def shard_p2p_phase(self, data, out_decisions, phase: int, offsets=None, uniform_len=None, model_ids=None,
+                        n_requests=None, lengths=None):
+        """One phase (0, 1, 2) of shard_schedule_p2p, synchronised: for ranks that share a GPU."""
+        b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests, lengths)
+        self._check(self._lib.epp_shard_p2p_phase(self._h, C.byref(b), _ptr(out_decisions), phase))
+        return R
+
     def shard_merge(self, n_requests, n_ranks, all_best, out_decisions):
         self._check(self._lib.epp_shard_merge(self._h, n_requests, n_ranks, _ptr(all_best), _ptr(out_decisions)))
 

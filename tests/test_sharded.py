@@ -251,21 +251,20 @@ def _p2p_engines_one_gpu(epp, w, trace, world, R_max):
 
 @pytest.mark.gpu
 def test_sharded_p2p_exchange_one_gpu(orc, monkeypatch):
-    """The peer-memory exchange (flags, OR of the masks, gather + merge of the records) with two shard engines on one
-    GPU, each driven by its own host thread like a rank: three consecutive batches (buffer reuse across epochs), every
-    rank's decisions identical and equal to the oracle's."""
-    import threading
+    """The peer-memory exchange (flags, OR of the masks, gather + merge of the records) with THREE shard engines on one
+    GPU, stepped phase by phase from one host thread (epp_shard_p2p_phase: ranks that share a GPU must not spin-wait
+    for each other on the device): three consecutive batches (buffer reuse across epochs), every rank's decisions
+    identical and equal to the oracle's.  Same kernels, same buffers, same flags as epp_shard_schedule_p2p."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     import epp_b200 as epp
     import helpers
     from tools import tracegen as tg
-    monkeypatch.setenv("EPP_P2P_TIMEOUT_MS", "4000")      # co-resident ranks may be serialised (see the skip below)
-    w = _workload(E=512, R=384, T=1024)
+    w = _workload(E=510, R=384, T=1024)
     trace = tg.Trace(w)
     pool, ix, primary, prefill, _ = helpers.setup_oracle(orc, w, trace)
-    world = 2
+    world = 3
     engines = _p2p_engines_one_gpu(epp, w, trace, world, R_max=512)
     try:
         for b in range(3):
@@ -273,32 +272,58 @@ def test_sharded_p2p_exchange_one_gpu(orc, monkeypatch):
             odec, ototal = helpers.oracle_decisions(orc, w, pool, ix, primary, None, tokens)
             dt = torch.from_numpy(tokens.view(np.int32)).cuda()
             outs = [torch.zeros((w.R, 32), dtype=torch.uint8, device="cuda") for _ in range(world)]
-            errs = []
-
-            def run(g):
-                try:
-                    engines[g].shard_schedule_p2p(dt, outs[g], uniform_len=w.prompt_bytes)
-                except Exception as e:          # noqa: BLE001
-                    errs.append((g, e))
             torch.cuda.synchronize()
-            ths = [threading.Thread(target=run, args=(g,)) for g in range(world)]
-            for t in ths:
-                t.start()
-            for t in ths:
-                t.join(timeout=120)
-            if errs and all("did not reach batch" in str(e) for _, e in errs):
-                # ranks that share ONE GPU can be serialised behind each other's wait kernel when their streams map to
-                # the same hardware queue (the engine then reports the missing peer after its time-out instead of
-                # hanging); with one GPU per rank -- test_sharded_two_gpus_p2p -- that cannot happen
-                pytest.skip("co-resident engines were serialised by the GPU's hardware queues: " + str(errs[0][1]))
-            assert not errs, errs
+            for phase in range(3):
+                for g in range(world):
+                    engines[g].shard_p2p_phase(dt, outs[g], phase, uniform_len=w.prompt_bytes)
             decs = [epp.decisions_from_torch(o) for o in outs]
             for d in decs[1:]:
                 np.testing.assert_array_equal(d, decs[0])
             helpers.assert_decisions_equal(decs[0], None, odec, ototal, where=f"p2p sharded x{world}, batch {b}")
+            assert (decs[0]["match_blocks"] > 0).any()
     finally:
         for e in engines:
             e.close()
+
+
+@pytest.mark.gpu
+def test_sharded_p2p_missing_peer_breaks_the_exchange(orc, monkeypatch):
+    """A peer that never shows up: the waiting rank gets EPP_ERR_NCCL after the time-out instead of hanging, poisons its
+    flags, and every later call on it -- and on a peer that meets the poison -- fails until the buffers are exported and
+    connected again; a rank without a shard range is rejected."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import epp_b200 as epp
+    import helpers
+    from tools import tracegen as tg
+    monkeypatch.setenv("EPP_P2P_TIMEOUT_MS", "200")
+    w = _workload(E=128, R=64, T=256)
+    trace = tg.Trace(w)
+    engines = _p2p_engines_one_gpu(epp, w, trace, 2, R_max=64)
+    try:
+        tokens, _, _ = trace.requests(0, w.R)
+        dt = torch.from_numpy(tokens.view(np.int32)).cuda()
+        out = torch.zeros((w.R, 32), dtype=torch.uint8, device="cuda")
+        with pytest.raises(epp.EngineError, match="did not reach batch"):
+            engines[0].shard_schedule_p2p(dt, out, uniform_len=w.prompt_bytes)      # rank 1 never calls
+        with pytest.raises(epp.EngineError, match="broken"):
+            engines[0].shard_schedule_p2p(dt, out, uniform_len=w.prompt_bytes)      # sticky
+        with pytest.raises(epp.EngineError, match="broken sharded exchange|did not reach"):
+            engines[1].shard_schedule_p2p(dt, out, uniform_len=w.prompt_bytes)      # meets rank 0's poisoned flags
+    finally:
+        for e in engines:
+            e.close()
+    with helpers.make_engine(w) as eng:
+        eng.register_model(b"synthetic-model")
+        role, kv, waiting, running = trace.pool()
+        eng.pool_set(np.arange(w.E, dtype=np.uint32), role, kv, waiting, running)
+        _, ptr = eng.shard_p2p_export(64)
+        eng.shard_p2p_connect(1, 0, np.array([ptr], dtype=np.uint64), ipc_handles=False)
+        tokens, _, _ = trace.requests(0, w.R)
+        with pytest.raises(epp.EngineError, match="epp_shard_set"):
+            eng.shard_schedule_p2p(torch.from_numpy(tokens.view(np.int32)).cuda(), torch.zeros((w.R, 32), dtype=torch.uint8, device="cuda"),
+                                   uniform_len=w.prompt_bytes)
 
 
 def _p2p_worker(rank, world, port, q):
