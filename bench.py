@@ -247,67 +247,80 @@ def run_reference(args, rank, world):
 
 def index_write_leg(args, w, trace, dev_tokens, dev_dec, local_rank, epp, helpers, orc_mod):
     """SURVEY 8(f).1 -- PreRequest at batch rate: schedule a batch, index its picks ON THE DEVICE (indexer.Add + LRU
-    eviction for 65 536 x 256 hashes), rebuild the read table.  The engine's index is seeded through indexer.Add (not a
-    snapshot), LRU capacity is the reference default (31 250 per endpoint).  The CPU number beside it is the oracle's
-    indexer (one mutex, like indexer.go) applying a bounded sample of the same Adds."""
+    eviction for 65 536 x 256 hashes), bring the read table up to date.  The engine's index is seeded through
+    indexer.Add (not a snapshot), LRU capacity is the reference default (31 250 per endpoint).  Two tie rules:
+    the reproducible random one (tie_seed != 0, what a deployment runs: tied requests spread over the arg-max set like
+    the reference's shuffle) and the deterministic lowest-slot one (tie_seed = 0: EVERY cold request of a batch picks
+    the same endpoint, millions of Adds to one LRU -- the worst case for the write side).  The CPU number beside it is
+    the oracle's indexer (one mutex, like indexer.go) applying a bounded sample of the same Adds."""
     import torch
     from tools import tracegen as tg
-    eng = helpers.make_engine(w, device=local_rank)
-    eng.register_model(tg.MODEL)
     role, kv, waiting, running = trace.pool()
-    eng.pool_set(np.arange(w.E, dtype=np.uint32), role, kv, waiting, running)
-    fh, _ = eng.hash_prompts(trace.family_tokens(), uniform_len=w.prompt_bytes)
-    hs, es = trace.index_pairs(fh)
-    order = np.argsort(es, kind="stable")
-    hs, es = hs[order], es[order]
-    cuts = np.flatnonzero(np.diff(es)) + 1
-    for seg_h, seg_e in zip(np.split(hs, cuts), np.split(es, cuts)):
-        if len(seg_e):
-            eng.index_add(int(seg_e[0]), seg_h)
-    if args.index_fill > 0:                      # production-size index: every endpoint's LRU (nearly) full
-        fhs, _ = helpers.filler_pairs(w.E, args.index_fill)
-        for e in range(w.E):
-            eng.index_add(e, fhs[e * args.index_fill:(e + 1) * args.index_fill])
-    eng.index_commit()
-    cycles = []
-    R = w.R
-    for k in range(3):
-        eng.schedule(dev_tokens, uniform_len=w.prompt_bytes, detail=False, out=dev_dec, keep_hashes=True)
-        t0 = time.perf_counter()
-        eng.index_add_picked()
-        eng.index_commit()
-        wall = time.perf_counter() - t0
-        st = eng.stats()
-        cycles.append({"apply_ms": st["last_index_apply_ms"], "build_ms": st["last_index_build_ms"], "wall_ms": wall * 1e3,
-                       "hashes_added": int(st["last_index_items"]), "pairs_after": int(st["index_pairs"]),
-                       "read_table": "patched from the change log" if st["last_index_patched"] else "bulk rebuild"})
-    last = cycles[-1]
-    out = {"what": "epp_index_add_picked + epp_index_commit after a config-3 batch (65 536 picks x up to 256 block hashes)",
-           "cycles": cycles, "adds_per_s": last["hashes_added"] / (last["apply_ms"] * 1e-3),
-           "adds_per_s_incl_read_table_build": last["hashes_added"] / (last["wall_ms"] * 1e-3),
-           "kernels_per_apply": int(eng.stats()["last_index_launches"]),
-           "store_device_bytes": int(eng.stats()["device_bytes"])}
-    # CPU: the oracle's indexer applying the Adds of the first requests of the same batch to the same seeded index
-    if orc_mod is not None:
-        ix = orc_mod.Indexer()
+    out = {"what": "epp_schedule(keep_hashes) + epp_index_add_picked + epp_index_commit per config-3 batch (65 536 picks x up to 256 block hashes)"}
+    hs = es = cuts = None
+    for label, seed in (("random_ties", 0x7153ED), ("lowest_slot_ties", 0)):
+        eng = helpers.make_engine(w, device=local_rank, tie_seed=seed)
+        eng.register_model(tg.MODEL)
+        eng.pool_set(np.arange(w.E, dtype=np.uint32), role, kv, waiting, running)
+        fh, _ = eng.hash_prompts(trace.family_tokens(), uniform_len=w.prompt_bytes)
+        hs, es = trace.index_pairs(fh)
+        order = np.argsort(es, kind="stable")
+        hs, es = hs[order], es[order]
+        cuts = np.flatnonzero(np.diff(es)) + 1
         for seg_h, seg_e in zip(np.split(hs, cuts), np.split(es, cuts)):
             if len(seg_e):
-                ix.add(seg_h, int(seg_e[0]))
+                eng.index_add(int(seg_e[0]), seg_h)
+        if args.index_fill > 0:                      # production-size index: every endpoint's LRU (nearly) full
+            fhs, _ = helpers.filler_pairs(w.E, args.index_fill)
+            for e in range(w.E):
+                eng.index_add(e, fhs[e * args.index_fill:(e + 1) * args.index_fill])
+        eng.index_commit()
+        cycles = []
+        R = w.R
+        for k in range(4):
+            torch.cuda.synchronize()
+            t_all = time.perf_counter()
+            eng.schedule(dev_tokens, uniform_len=w.prompt_bytes, detail=False, out=dev_dec, keep_hashes=True)
+            t0 = time.perf_counter()
+            eng.index_add_picked()
+            eng.index_commit()
+            t1 = time.perf_counter()
+            st = eng.stats()
+            cycles.append({"schedule_ms": (t0 - t_all) * 1e3, "apply_ms": st["last_index_apply_ms"], "build_ms": st["last_index_build_ms"],
+                           "write_wall_ms": (t1 - t0) * 1e3, "cycle_wall_ms": (t1 - t_all) * 1e3,
+                           "hashes_added": int(st["last_index_items"]), "pairs_after": int(st["index_pairs"]),
+                           "read_table": "patched from the change log" if st["last_index_patched"] else "bulk rebuild"})
+        last = cycles[-1]
         dec = epp.decisions_from_torch(dev_dec)
-        n_s = min(R, 8192)
-        hh, nb = eng.hash_prompts(dev_tokens[:n_s], uniform_len=w.prompt_bytes)
-        hh = hh.cpu().numpy().view(np.uint64) if hasattr(hh, "cpu") else hh
-        nb = nb.cpu().numpy() if hasattr(nb, "cpu") else nb
-        t0 = time.perf_counter()
-        tot = 0
-        for r in range(n_s):
-            if dec["status"][r] == 0:
-                ix.add(hh[r, : nb[r]], int(dec["pick"][r]))
-                tot += int(nb[r])
-        dt = time.perf_counter() - t0
-        out["cpu_adds_per_s"] = tot / dt
-        out["cpu_sample"] = f"oracle indexer (C port of indexer.go Add + golang-lru), 1 thread, Adds of the first {n_s} requests"
-    eng.close()
+        ok = dec["status"] == 0
+        out[label] = {"tie_seed": seed, "cycles": cycles,
+                      "full_cycle_decisions_per_s": R / (last["cycle_wall_ms"] * 1e-3),
+                      "adds_per_s": last["hashes_added"] / (last["apply_ms"] * 1e-3),
+                      "adds_per_s_incl_read_table": last["hashes_added"] / (last["write_wall_ms"] * 1e-3),
+                      "distinct_endpoints_picked": int(np.unique(dec["pick"][ok]).shape[0]),
+                      "max_picks_on_one_endpoint": int(np.bincount(dec["pick"][ok].astype(np.int64)).max()),
+                      "kernels_per_apply": int(eng.stats()["last_index_launches"]),
+                      "store_device_bytes": int(eng.stats()["device_bytes"])}
+        if label == "lowest_slot_ties" and orc_mod is not None:
+            # CPU: the oracle's indexer applying the Adds of the first requests of the same batch to the same seeded index
+            ix = orc_mod.Indexer()
+            for seg_h, seg_e in zip(np.split(hs, cuts), np.split(es, cuts)):
+                if len(seg_e):
+                    ix.add(seg_h, int(seg_e[0]))
+            n_s = min(R, 8192)
+            hh, nb = eng.hash_prompts(dev_tokens[:n_s], uniform_len=w.prompt_bytes)
+            hh = hh.cpu().numpy().view(np.uint64) if hasattr(hh, "cpu") else hh
+            nb = nb.cpu().numpy() if hasattr(nb, "cpu") else nb
+            t0 = time.perf_counter()
+            tot = 0
+            for r in range(n_s):
+                if dec["status"][r] == 0:
+                    ix.add(hh[r, : nb[r]], int(dec["pick"][r]))
+                    tot += int(nb[r])
+            dt = time.perf_counter() - t0
+            out["cpu_adds_per_s"] = tot / dt
+            out["cpu_sample"] = f"oracle indexer (C port of indexer.go Add + golang-lru), 1 thread, Adds of the first {n_s} requests"
+        eng.close()
     return out
 
 
