@@ -18,6 +18,7 @@ Engine = _pkg.Engine
 EngineError = _pkg.EngineError
 ProfileSpec = _pkg.ProfileSpec
 ScorerSpec = _pkg.ScorerSpec
+AffinityFilterSpec = _pkg.AffinityFilterSpec
 DECISION_DTYPE = _pkg.DECISION_DTYPE
 DETAIL_DTYPE = _pkg.DETAIL_DTYPE
 SHARD_BEST_DTYPE = _pkg.SHARD_BEST_DTYPE

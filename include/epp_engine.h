@@ -39,6 +39,17 @@
  *       (oracle/epp_oracle.c: orc_tie_rank).  Without it every tied request of a batch (cold prompts on a balanced
  *       pool) would land on the same endpoint.  The P/D decider reads the match count of the member picked, as the
  *       reference does (disagg_profile_handler.go:300).  Endpoint-sharded mode always uses the lowest slot.
+ *
+ * Top-k (epp_config.pick_k > 1, epp_schedule_topk): maxscore/picker.go:91-110 shuffles, stable-sorts by score descending
+ * and keeps the first k, i.e. the endpoints come out group by group in descending score order and every group of equal
+ * scores in uniformly random order.  The engine emits pick j (j = 0 .. k-1) as the member of rank
+ *   tie_seed == 0: 0 (the lowest remaining slot), or
+ *   tie_seed != 0: ((mix64((tie_seed + j * 0x9E3779B97F4A7C15) ^ mix64(key)) >> 32) * n_j) >> 32
+ * among the n_j members of the current group not emitted yet (ascending slot order); pick 0 is the pick of the rule above.
+ *
+ * Exploration draw of the prefix-cache-affinity-filter (rand.Float64() < explorationProbability,
+ * filter/prefixcacheaffinity/plugin.go:113): u = (mix64((tie_seed ^ 0xA0761D6478BD642F) ^ mix64(key)) >> 11) * 2^-53 when
+ * tie_seed != 0; with tie_seed == 0 (the deterministic mode) the filter never explores.
  */
 #ifndef EPP_ENGINE_H
 #define EPP_ENGINE_H
@@ -56,7 +67,7 @@ extern "C" {
 #define EPP_API
 #endif
 
-#define EPP_ABI_VERSION 4
+#define EPP_ABI_VERSION 5
 #define EPP_MAX_SCORERS 8
 #define EPP_NO_ENDPOINT 0xFFFFFFFFu
 
@@ -125,12 +136,24 @@ typedef struct {
     double param2;
 } epp_scorer_cfg;
 
-/* One SchedulerProfile (scheduling/scheduler_profile.go:117-128): role filter -> scorers IN ORDER ->
- * max-score picker (k = 1). */
+/* One SchedulerProfile (scheduling/scheduler_profile.go:117-128): role filter -> [prefix-cache-affinity-filter] ->
+ * scorers IN ORDER -> max-score picker. */
 typedef struct {
     int32_t filter;            /* epp_filter_kind */
     int32_t n_scorers;
     epp_scorer_cfg scorers[EPP_MAX_SCORERS];
+    /* "prefix-cache-affinity-filter" after the role filter (filter/prefixcacheaffinity/plugin.go:105-151): with
+     * probability 1 - exploration_probability the candidates are narrowed to the STICKY endpoints (matchBlocks /
+     * totalBlocks >= affinity_threshold) unless there is none, or the best predicted TTFT among them exceeds the best
+     * among the others by more than max_ttft_penalty_ms.  The scorers then normalise over the narrowed set
+     * (queue / running min-max, active-request max).  affinity_threshold <= 0: no such filter (plugin.go:108).
+     * The reference's defaults are 0.80 / 0.01 / 5000 (plugin.go:62-66). */
+    double affinity_threshold;
+    double exploration_probability;    /* [0, 1]                                                              */
+    double max_ttft_penalty_ms;        /* >= 0; 0 = always stick                                              */
+    int32_t ttft_column;               /* ext column holding LatencyPredictionInfo.TTFT per endpoint; < 0 = no
+                                          prediction attached (the gate then never breaks stickiness, :169-180) */
+    int32_t reserved;
 } epp_profile_cfg;
 
 /* Mirrors the EndpointPickerConfig fields that define this path (apix/config/v1alpha1, and
@@ -147,12 +170,14 @@ typedef struct {
     int64_t non_cached_tokens;     /* prefix-based-pd-decider nonCachedTokens (0 disables)               */
     int32_t n_ext_cols;            /* number of EPP_SCORER_EXTERNAL columns                              */
     int32_t pick_k;                /* max-score-picker maxNumOfEndpoints (picker/common.go:36, maxscore/picker.go:104-115);
-                                      0 or 1 = one endpoint; > 1: epp_schedule_topk returns the k best                */
+                                      0 or 1 = one endpoint; 2..64: epp_schedule_topk / epp_schedule_with_match_topk also
+                                      return the k best of every profile that ran                                     */
     epp_profile_cfg primary;       /* the single profile, or the decode profile under EPP_HANDLER_DISAGG */
     epp_profile_cfg prefill;       /* the prefill profile (EPP_HANDLER_DISAGG only)                      */
     epp_profile_cfg encode;        /* the encode profile (EPP_HANDLER_DISAGG with encode_enabled != 0):
                                       disagg_profile_handler.go:284-295                                   */
-    uint64_t tie_seed;             /* 0 = lowest slot of the arg-max set; else the reproducible random tie rule above */
+    uint64_t tie_seed;             /* seed of every reproducible random draw (ties, top-k order, exploration); 0 = the
+                                      deterministic mode: lowest slot of the arg-max set, no exploration              */
     int32_t encode_enabled;        /* an "encode" profile + always-disagg-multimodal-decider are configured */
     int32_t reserved0;
     uint64_t reserved1[2];
@@ -309,6 +334,26 @@ EPP_API int32_t epp_schedule(epp_engine *h, const epp_batch *batch, epp_decision
 EPP_API int32_t epp_schedule_with_match(epp_engine *h, int64_t n_requests, const int32_t *match, const int32_t *total,
                                 const uint32_t *model_ids, const int64_t *input_len_bytes, int32_t block_size_tokens, epp_decision *out,
                                 epp_decision_detail *detail, uint32_t flags);
+
+/* maxNumOfEndpoints > 1 (maxscore/picker.go:104-115): the k = epp_config.pick_k best endpoints of every profile that ran
+ * for the request, in picker order (see "Top-k" above); rows are padded with EPP_NO_ENDPOINT / 0.0 when a profile has
+ * fewer candidates than k or did not run.  primary[r*k] == out[r].pick, prefill[r*k] == out[r].prefill_pick,
+ * encode[r*k] == detail[r].encode_pick.  Host pointers for host batches, device pointers with EPP_BATCH_DEVICE_PTRS;
+ * any of the arrays may be NULL. */
+typedef struct {
+    uint32_t struct_size;          /* sizeof(epp_topk_out)                                              */
+    int32_t k;                     /* row stride; must equal epp_config.pick_k                           */
+    uint32_t *primary;             /* [R][k] slot ids                                                    */
+    double *primary_scores;        /* [R][k] their weighted scores                                       */
+    uint32_t *prefill;             /* [R][k]                                                             */
+    uint32_t *encode;              /* [R][k]                                                             */
+} epp_topk_out;
+EPP_API int32_t epp_schedule_topk(epp_engine *h, const epp_batch *batch, epp_decision *out, epp_decision_detail *detail,
+                          int32_t keep_hashes, const epp_topk_out *topk);
+EPP_API int32_t epp_schedule_with_match_topk(epp_engine *h, int64_t n_requests, const int32_t *match, const int32_t *total,
+                                     const uint32_t *model_ids, const int64_t *input_len_bytes, int32_t block_size_tokens,
+                                     epp_decision *out, epp_decision_detail *detail, uint32_t flags,
+                                     const epp_topk_out *topk);
 
 /* PreRequest (approximateprefix/plugin.go:164-200): index the hashes of the LAST epp_schedule batch
  * (keep_hashes=1) for each request's primary pick and prefill pick. */

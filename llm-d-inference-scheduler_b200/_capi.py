@@ -31,7 +31,9 @@ class ScorerCfg(C.Structure):
 
 
 class ProfileCfg(C.Structure):
-    _fields_ = [("filter", C.c_int32), ("n_scorers", C.c_int32), ("scorers", ScorerCfg * EPP_MAX_SCORERS)]
+    _fields_ = [("filter", C.c_int32), ("n_scorers", C.c_int32), ("scorers", ScorerCfg * EPP_MAX_SCORERS),
+                ("affinity_threshold", C.c_double), ("exploration_probability", C.c_double),
+                ("max_ttft_penalty_ms", C.c_double), ("ttft_column", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Config(C.Structure):
@@ -68,6 +70,11 @@ class Stats(C.Structure):
                 ("device_bytes", C.c_uint64), ("last_kernel_ms", C.c_double * 8), ("last_probes", C.c_uint64),
                 ("last_postings", C.c_uint64), ("last_index_apply_ms", C.c_double), ("last_index_build_ms", C.c_double),
                 ("last_index_items", C.c_uint64), ("last_index_launches", C.c_uint64), ("last_index_patched", C.c_uint64)]
+
+
+class TopkOut(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("k", C.c_int32), ("primary", C.c_void_p), ("primary_scores", C.c_void_p),
+                ("prefill", C.c_void_p), ("encode", C.c_void_p)]
 
 
 class BatcherCfg(C.Structure):
@@ -116,6 +123,9 @@ SIGNATURES = {
     "epp_schedule": (C.c_int32, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_int32]),
     "epp_schedule_with_match": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                             C.c_void_p, C.c_void_p, C.c_uint32]),
+    "epp_schedule_topk": (C.c_int32, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(TopkOut)]),
+    "epp_schedule_with_match_topk": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_int32, C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(TopkOut)]),
     "epp_index_add_picked": (C.c_int32, [C.c_void_p]),
     "epp_get_stats": (C.c_int32, [C.c_void_p, C.POINTER(Stats)]),
     "epp_synchronize": (C.c_int32, [C.c_void_p]),

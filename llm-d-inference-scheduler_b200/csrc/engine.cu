@@ -127,6 +127,10 @@ struct epp_engine {
     int pick_grid = 0;
     bool pick_global = false;
     size_t pick_smem = 0;
+    bool general = false;           // a profile configures the prefix-cache-affinity-filter or pick_k > 1: every batch takes
+                                    // the dense-counter kernel with the full-scan evaluation of pick_general.cuh
+    const epp_topk_out *cur_topk = nullptr;   // top-k destination of the call in progress (under mu)
+    DevBuf topk_picks[kMaxProfiles], topk_scores;   // device staging of the lists for host batches
     int64_t kept_R = 0;             // rows of `hashes` valid for epp_index_add_picked
     int64_t shard_R = 0;            // rows of `hashes` valid for epp_shard_pick / epp_shard_merge
     // endpoint-sharded mode over NVLink peer memory (shard_p2p.cu)
@@ -183,6 +187,7 @@ extern "C" void epp_config_default(epp_config *cfg) {
     cfg->primary.scorers[0] = {EPP_SCORER_QUEUE, 0, 2.0, 0.0, 0.0};
     cfg->primary.scorers[1] = {EPP_SCORER_KV_UTIL, 0, 2.0, 0.0, 0.0};
     cfg->primary.scorers[2] = {EPP_SCORER_PREFIX, 0, 3.0, 0.0, 0.0};
+    cfg->primary.ttft_column = cfg->prefill.ttft_column = cfg->encode.ttft_column = -1;   // no affinity filter, no TTFT column
 }
 
 static int32_t validate_profile(const epp_profile_cfg &p, int n_ext, const char *name) {
@@ -196,6 +201,11 @@ static int32_t validate_profile(const epp_profile_cfg &p, int n_ext, const char 
             return fail(EPP_ERR_INVALID, "%s: scorer %d reads ext column %d, out of range [0,%d)", name, s, sc.column, n_ext);
         if (sc.kind == EPP_SCORER_EXTERNAL && (sc.param < 0 || sc.param >= n_ext)) return fail(EPP_ERR_INVALID, "%s: scorer %d external column %g out of range [0,%d)", name, s, sc.param, n_ext);
     }
+    // prefix-cache-affinity-filter: Config.validate, filter/prefixcacheaffinity/plugin.go:87-98
+    if (std::isnan(p.affinity_threshold) || p.affinity_threshold > 1.0) return fail(EPP_ERR_INVALID, "%s: affinityThreshold must be <= 1.0, got %f", name, p.affinity_threshold);
+    if (!(p.exploration_probability >= 0.0 && p.exploration_probability <= 1.0)) return fail(EPP_ERR_INVALID, "%s: explorationProbability must be in [0, 1], got %f", name, p.exploration_probability);
+    if (!(p.max_ttft_penalty_ms >= 0.0)) return fail(EPP_ERR_INVALID, "%s: maxTTFTPenaltyMs must be >= 0, got %f", name, p.max_ttft_penalty_ms);
+    if (p.affinity_threshold > 0.0 && p.ttft_column >= n_ext) return fail(EPP_ERR_INVALID, "%s: ttft_column %d out of range [0,%d)", name, p.ttft_column, n_ext);
     return EPP_OK;
 }
 
@@ -275,6 +285,11 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
     for (int pi = 0; pi < e->n_alloc_profiles; pi++) {
         const epp_profile_cfg &pc = pi == 0 ? cfg->primary : (pi == 1 ? cfg->prefill : cfg->encode);
         for (int si = 0; si < pc.n_scorers; si++) if (pc.scorers[si].kind == EPP_SCORER_LORA_AFFINITY) e->lora_enabled = true;
+    }
+    e->general = cfg->pick_k > 1;
+    for (int pi = 0; pi < e->n_alloc_profiles; pi++) {
+        const epp_profile_cfg &pc = pi == 0 ? cfg->primary : (pi == 1 ? cfg->prefill : cfg->encode);
+        if (pc.affinity_threshold > 0.0) e->general = true;
     }
     e->store.reset(new IndexStore((uint32_t)cfg->max_endpoints, cfg->lru_capacity_per_server));
     { const char *v1 = getenv("EPP_INDEX_PATCH"); e->patch_enabled = v1 ? atoi(v1) : 1; }
@@ -892,6 +907,22 @@ static HashParams hash_params(epp_engine *h, const Work &w) {
     return p;
 }
 
+// General-evaluation view; the top-k rows are attached by the caller (they depend on where the batch's rows live).
+static GenView gen_view(epp_engine *h) {
+    GenView g;
+    memset(&g, 0, sizeof g);
+    g.on = h->general ? 1 : 0;
+    g.pool = pool_arrays(h);
+    return g;
+}
+// Rows [r0, ...) of the top-k lists of the call in progress, in `base` arrays of row stride k.
+static void attach_topk(epp_engine *h, GenView &g, uint32_t *const picks[kMaxProfiles], double *scores, int64_t r0) {
+    const int32_t k = h->cfg.pick_k;
+    g.topk = k;
+    for (int i = 0; i < kMaxProfiles; i++) g.topk_picks[i] = picks[i] ? picks[i] + (size_t)r0 * (size_t)k : nullptr;
+    g.topk_scores = scores ? scores + (size_t)r0 * (size_t)k : nullptr;
+}
+
 static PickParams pick_params(epp_engine *h, const Work &w, epp_decision *out, epp_decision_detail *detail,
                               int32_t *out_match) {
     PickParams p;
@@ -924,6 +955,7 @@ static PickParams pick_params(epp_engine *h, const Work &w, epp_decision *out, e
     p.req_list_n = nullptr;
     p.overflow_list = nullptr;
     p.overflow_n = nullptr;
+    p.gen = gen_view(h);
     return p;
 }
 
@@ -958,7 +990,7 @@ static int32_t launch_overflow_pass(epp_engine *h, Slot &sl, PickParams pp, int 
 static int32_t launch_match(epp_engine *h, Slot &sl, PickParams pp, int *launches) {
     cudaStream_t s = sl.stream;
     uint32_t *gs = h->pick_global ? sl.pick_scratch.as<uint32_t>() : nullptr;
-    if (pp.out_match) {
+    if (pp.out_match || pp.gen.on) {
         CUDA_TRY(launch_match_pick(pp, gs, h->pick_grid, h->pick_smem, s, launches));
         return EPP_OK;
     }
@@ -1008,6 +1040,29 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
         EPP_TRY(commit_locked(h));
     }
     if (h->async_pending && !(v.device && v.async)) EPP_TRY(finish_async(h));
+    // top-k lists of the call in progress: the caller's device arrays, or device staging for a host batch
+    const epp_topk_out *tk = mode == Mode::Schedule ? h->cur_topk : nullptr;
+    const size_t K = (size_t)h->cfg.pick_k;
+    uint32_t *tk_picks[kMaxProfiles] = {nullptr, nullptr, nullptr};
+    uint32_t *tk_host[kMaxProfiles] = {nullptr, nullptr, nullptr};
+    double *tk_scores = nullptr;
+    if (tk) {
+        tk_host[0] = tk->primary; tk_host[1] = tk->prefill; tk_host[2] = tk->encode;
+        if (v.device) {
+            for (int i = 0; i < kMaxProfiles; i++) tk_picks[i] = tk_host[i];
+            tk_scores = tk->primary_scores;
+        } else {
+            for (int i = 0; i < kMaxProfiles; i++)
+                if (tk_host[i]) {
+                    CUDA_TRY(h->topk_picks[i].reserve(sizeof(uint32_t) * (size_t)R * K, &h->dev_bytes));
+                    tk_picks[i] = h->topk_picks[i].as<uint32_t>();
+                }
+            if (tk->primary_scores) {
+                CUDA_TRY(h->topk_scores.reserve(sizeof(double) * (size_t)R * K, &h->dev_bytes));
+                tk_scores = h->topk_scores.as<double>();
+            }
+        }
+    }
     const bool pipelined = v.device && v.async && mode == Mode::Schedule && h->dev_chunks > 1 && R >= 2 * 4096 && !h->pick_global;
     if (!pipelined) EPP_TRY(join_streams(h));
     EPP_TRY(reserve_batch(h, R));
@@ -1044,6 +1099,7 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
                 Work w{r0, r1, v.offsets ? v.data : v.data + (uint64_t)r0 * v.uniform_len, v.offsets, v.lengths, v.uniform_len,
                        v.model_ids, or_bits, h->hashes.as<uint64_t>() + (size_t)r0 * B, h->nblocks.as<int32_t>() + r0, v.multimodal};
                 PickParams pp = pick_params(h, w, dec_base + r0, out_detail ? out_detail + r0 : nullptr, nullptr);
+                if (tk) attach_topk(h, pp.gen, tk_picks, tk_scores, r0);
                 Slot &sl = h->slot[k & 1];
                 EPP_TRY(launch_cycle(h, sl, hash_params(h, w), pp, &launches, nullptr));
             }
@@ -1056,6 +1112,7 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
             epp_decision *dec = (mode == Mode::Schedule && out_dec) ? out_dec : h->decisions.as<epp_decision>();
             PickParams pp = pick_params(h, w, dec, mode == Mode::Schedule ? out_detail : nullptr, mode == Mode::Match ? out_match : nullptr);
             pp.work_counters = h->work_counters.as<unsigned long long>();
+            if (tk) attach_topk(h, pp.gen, tk_picks, tk_scores, 0);
             EPP_TRY(launch_cycle(h, h->slot[0], hash_params(h, w), pp, &launches, h->ev));
         }
         CUDA_TRY(cudaEventRecord(h->ev[4], s0));
@@ -1141,10 +1198,17 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
             epp_decision *dec = h->decisions.as<epp_decision>() + c.r0;
             epp_decision_detail *det = h->details.as<epp_decision_detail>() + c.r0;
             PickParams pp = pick_params(h, w, dec, det, dm);
+            if (tk) attach_topk(h, pp.gen, tk_picks, tk_scores, c.r0);
             EPP_TRY(launch_cycle(h, sl, hash_params(h, w), pp, &launches, nullptr));
             if (mode == Mode::Schedule) {
                 if (out_dec) CUDA_TRY(cudaMemcpyAsync(out_dec + c.r0, dec, sizeof(epp_decision) * nreq, cudaMemcpyDeviceToHost, s));
                 if (out_detail) CUDA_TRY(cudaMemcpyAsync(out_detail + c.r0, det, sizeof(epp_decision_detail) * nreq, cudaMemcpyDeviceToHost, s));
+                if (tk) {
+                    const size_t o = (size_t)c.r0 * K;
+                    for (int i = 0; i < kMaxProfiles; i++)
+                        if (tk_host[i]) CUDA_TRY(cudaMemcpyAsync(tk_host[i] + o, tk_picks[i] + o, sizeof(uint32_t) * nreq * K, cudaMemcpyDeviceToHost, s));
+                    if (tk_scores) CUDA_TRY(cudaMemcpyAsync(tk->primary_scores + o, tk_scores + o, sizeof(double) * nreq * K, cudaMemcpyDeviceToHost, s));
+                }
             } else {
                 if (out_match) CUDA_TRY(cudaMemcpyAsync(out_match + (size_t)c.r0 * E, dm, sizeof(int32_t) * nreq * E, cudaMemcpyDeviceToHost, s));
                 if (out_total) CUDA_TRY(cudaMemcpyAsync(out_total + c.r0, w.nblocks_out, sizeof(int32_t) * nreq, cudaMemcpyDeviceToHost, s));
@@ -1183,17 +1247,29 @@ extern "C" int32_t epp_prefix_match(epp_engine *h, const epp_batch *batch, int32
     return run_batch(h, v, Mode::Match, nullptr, nullptr, nullptr, nullptr, out_match, out_total);
 }
 
-extern "C" int32_t epp_schedule(epp_engine *h, const epp_batch *batch, epp_decision *out, epp_decision_detail *detail,
-                                int32_t keep_hashes) {
+static int32_t check_topk(epp_engine *h, const epp_topk_out *topk) {
+    if (!topk) return fail(EPP_ERR_INVALID, "topk is NULL");
+    if (topk->struct_size != sizeof(epp_topk_out)) return fail(EPP_ERR_INVALID, "epp_topk_out.struct_size %u != %zu", topk->struct_size, sizeof(epp_topk_out));
+    if (h->cfg.pick_k <= 1) return fail(EPP_ERR_STATE, "the engine was created with pick_k = %d: nothing but the pick to return", h->cfg.pick_k);
+    if (topk->k != h->cfg.pick_k) return fail(EPP_ERR_INVALID, "epp_topk_out.k %d != epp_config.pick_k %d", topk->k, h->cfg.pick_k);
+    return EPP_OK;
+}
+
+static int32_t schedule_impl(epp_engine *h, const epp_batch *batch, epp_decision *out, epp_decision_detail *detail,
+                             int32_t keep_hashes, const epp_topk_out *topk) {
     if (!h) return fail(EPP_ERR_INVALID, "NULL engine");
     if (!out) return fail(EPP_ERR_INVALID, "out is NULL");
     std::lock_guard<std::mutex> lk(h->mu);
     EPP_TRY(set_device(h));
     BatchView v;
     EPP_TRY(check_batch(h, batch, v));
+    if (topk) EPP_TRY(check_topk(h, topk));
     if (h->cfg.encode_enabled && v.multimodal && !detail) return fail(EPP_ERR_INVALID, "an encode profile is configured and the batch flags multimodal requests: `detail` (which carries the encode pick) must not be NULL");
     h->kept_R = 0;
-    EPP_TRY(run_batch(h, v, Mode::Schedule, nullptr, nullptr, out, detail, nullptr, nullptr));
+    h->cur_topk = topk;
+    const int32_t rc = run_batch(h, v, Mode::Schedule, nullptr, nullptr, out, detail, nullptr, nullptr);
+    h->cur_topk = nullptr;
+    EPP_TRY(rc);
     h->stats.n_batches++;
     h->stats.n_decisions += (uint64_t)v.R;
     if (keep_hashes && v.R) {
@@ -1207,6 +1283,17 @@ extern "C" int32_t epp_schedule(epp_engine *h, const epp_batch *batch, epp_decis
         h->kept_R = v.R;
     }
     return EPP_OK;
+}
+
+extern "C" int32_t epp_schedule(epp_engine *h, const epp_batch *batch, epp_decision *out, epp_decision_detail *detail,
+                                int32_t keep_hashes) {
+    return schedule_impl(h, batch, out, detail, keep_hashes, nullptr);
+}
+
+extern "C" int32_t epp_schedule_topk(epp_engine *h, const epp_batch *batch, epp_decision *out, epp_decision_detail *detail,
+                                     int32_t keep_hashes, const epp_topk_out *topk) {
+    if (!topk) return fail(EPP_ERR_INVALID, "topk is NULL");
+    return schedule_impl(h, batch, out, detail, keep_hashes, topk);
 }
 
 // PreRequest: approximateprefix/plugin.go:164-200 (primary target + "prefill" profile target).
@@ -1272,11 +1359,12 @@ extern "C" int32_t epp_score(epp_engine *h, int64_t n_requests, const int32_t *m
     return EPP_OK;
 }
 
-extern "C" int32_t epp_schedule_with_match(epp_engine *h, int64_t n_requests, const int32_t *match, const int32_t *total,
-                                           const uint32_t *model_ids, const int64_t *input_len_bytes, int32_t block_size_tokens, epp_decision *out,
-                                           epp_decision_detail *detail, uint32_t flags) {
+static int32_t with_match_impl(epp_engine *h, int64_t n_requests, const int32_t *match, const int32_t *total,
+                               const uint32_t *model_ids, const int64_t *input_len_bytes, int32_t block_size_tokens, epp_decision *out,
+                               epp_decision_detail *detail, uint32_t flags, const epp_topk_out *topk) {
     if (!h || n_requests < 0 || (n_requests && (!match || !total || !out))) return fail(EPP_ERR_INVALID, "bad arguments");
     std::lock_guard<std::mutex> lk(h->mu);
+    if (topk) EPP_TRY(check_topk(h, topk));
     EPP_TRY(set_device(h));
     EPP_TRY(join_streams(h));
     if (!h->pool_ready) return fail(EPP_ERR_STATE, "epp_pool_set has not been called");
@@ -1298,6 +1386,27 @@ extern "C" int32_t epp_schedule_with_match(epp_engine *h, int64_t n_requests, co
     p.model_ids = model_ids;
     p.tie_seed = h->cfg.tie_seed;
     p.tie_base = h->stats.n_decisions;
+    p.gen = gen_view(h);
+    const size_t K = (size_t)h->cfg.pick_k;
+    uint32_t *tk_host[kMaxProfiles] = {nullptr, nullptr, nullptr};
+    uint32_t *tk_picks[kMaxProfiles] = {nullptr, nullptr, nullptr};
+    double *tk_scores = nullptr;
+    if (topk) {
+        tk_host[0] = topk->primary; tk_host[1] = topk->prefill; tk_host[2] = topk->encode;
+        for (int i = 0; i < kMaxProfiles; i++) {
+            tk_picks[i] = tk_host[i];
+            if (!dev && tk_host[i]) {
+                CUDA_TRY(h->topk_picks[i].reserve(sizeof(uint32_t) * R * K, &h->dev_bytes));
+                tk_picks[i] = h->topk_picks[i].as<uint32_t>();
+            }
+        }
+        tk_scores = topk->primary_scores;
+        if (!dev && tk_scores) {
+            CUDA_TRY(h->topk_scores.reserve(sizeof(double) * R * K, &h->dev_bytes));
+            tk_scores = h->topk_scores.as<double>();
+        }
+        attach_topk(h, p.gen, tk_picks, tk_scores, 0);
+    }
     if (dev) {
         p.match = match; p.total = total; p.in_len = input_len_bytes; p.out = out; p.detail = detail;
     } else {
@@ -1324,11 +1433,28 @@ extern "C" int32_t epp_schedule_with_match(epp_engine *h, int64_t n_requests, co
     if (!dev) {
         CUDA_TRY(cudaMemcpyAsync(out, p.out, sizeof(epp_decision) * R, cudaMemcpyDeviceToHost, s));
         if (detail) CUDA_TRY(cudaMemcpyAsync(detail, p.detail, sizeof(epp_decision_detail) * R, cudaMemcpyDeviceToHost, s));
+        for (int i = 0; i < kMaxProfiles; i++)
+            if (tk_host[i]) CUDA_TRY(cudaMemcpyAsync(tk_host[i], tk_picks[i], sizeof(uint32_t) * R * K, cudaMemcpyDeviceToHost, s));
+        if (topk && topk->primary_scores) CUDA_TRY(cudaMemcpyAsync(topk->primary_scores, tk_scores, sizeof(double) * R * K, cudaMemcpyDeviceToHost, s));
     }
     CUDA_TRY(cudaStreamSynchronize(s));
     h->kept_R = 0;
     h->stats.n_decisions += (uint64_t)n_requests;          // request ordinals (tie rule) advance here too
     return EPP_OK;
+}
+
+extern "C" int32_t epp_schedule_with_match(epp_engine *h, int64_t n_requests, const int32_t *match, const int32_t *total,
+                                           const uint32_t *model_ids, const int64_t *input_len_bytes, int32_t block_size_tokens, epp_decision *out,
+                                           epp_decision_detail *detail, uint32_t flags) {
+    return with_match_impl(h, n_requests, match, total, model_ids, input_len_bytes, block_size_tokens, out, detail, flags, nullptr);
+}
+
+extern "C" int32_t epp_schedule_with_match_topk(epp_engine *h, int64_t n_requests, const int32_t *match, const int32_t *total,
+                                                const uint32_t *model_ids, const int64_t *input_len_bytes, int32_t block_size_tokens,
+                                                epp_decision *out, epp_decision_detail *detail, uint32_t flags,
+                                                const epp_topk_out *topk) {
+    if (!topk) return fail(EPP_ERR_INVALID, "topk is NULL");
+    return with_match_impl(h, n_requests, match, total, model_ids, input_len_bytes, block_size_tokens, out, detail, flags, topk);
 }
 
 extern "C" int32_t epp_get_config(epp_engine *h, epp_config *out) {
@@ -1379,12 +1505,13 @@ extern "C" int32_t epp_event_elapsed_ms(epp_engine *h, double *out_ms) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// endpoint-sharded mode (see shard_kernels.cu)
+// endpoint-sharded mode (kernels: pick_kernels.cu k_shard_*, shard_p2p.cu)
 // ------------------------------------------------------------------------------------------------
 extern "C" int32_t epp_shard_set(epp_engine *h, uint32_t ep_begin, uint32_t ep_end) {
     if (!h || ep_begin > ep_end) return fail(EPP_ERR_INVALID, "bad shard range");
     std::lock_guard<std::mutex> lk(h->mu);
     if (h->cfg.handler != EPP_HANDLER_SINGLE) return fail(EPP_ERR_INVALID, "endpoint-sharded mode supports the single-profile handler only");
+    if (h->general) return fail(EPP_ERR_INVALID, "endpoint-sharded mode supports neither pick_k > 1 nor the prefix-cache-affinity-filter (both need every candidate's score on one rank)");
     h->shard_begin = ep_begin;
     h->shard_end = ep_end;
     h->pool_ready = false;          // candidates are derived per shard: epp_pool_set must follow

@@ -128,6 +128,14 @@ struct ProfileDev {            // what the pick kernels read (device pointers + 
     const uint32_t *grp_size;
     const int32_t *n_cand;
 };
+// General evaluation (pick_general.cuh): set when a profile configures the prefix-cache-affinity-filter or pick_k > 1.
+struct GenView {
+    int32_t on;                // every profile evaluation of the launch goes through gen::eval
+    int32_t topk;              // k of the lists below (<= 1: no lists)
+    PoolArrays pool;           // raw pool arrays (scores over a narrowed candidate set are not in the snapshot columns)
+    uint32_t *topk_picks[kMaxProfiles];   // [R][topk] per profile, or nullptr
+    double *topk_scores;       // [R][topk] scores of the primary list, or nullptr
+};
 struct PickParams {
     int64_t R;
     int32_t E;
@@ -162,6 +170,7 @@ struct PickParams {
     // tie rule: 0 = lowest slot of the arg-max set; else the member of rank tie_rank(seed, 4 * (tie_base + r) + profile)
     uint64_t tie_seed;
     uint64_t tie_base;         // ordinal of request 0 of this launch
+    GenView gen;
 };
 // Fused lookup + match + score + pick, one warp per request.  Per-warp match counters live in shared memory
 // (smem = match_pick_smem_bytes(E, false)) or, when E is too large for that, in a zero-initialised global
@@ -193,6 +202,7 @@ struct DensePickParams {
     epp_decision_detail *detail;
     uint64_t tie_seed;
     uint64_t tie_base;
+    GenView gen;
 };
 cudaError_t launch_dense_pick(const DensePickParams &p, cudaStream_t s, int *launches);
 // Scorer.Score parity: out[R][E].  scorer_index -1 => weighted ordered sum (-1.0 for non-candidates).

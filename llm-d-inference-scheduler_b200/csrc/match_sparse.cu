@@ -1,6 +1,5 @@
 // match_sparse.cu -- a2-a14 as a STANDALONE kernel over precomputed hashes (plugin-parity modes, endpoint-sharded
-// mode, generic-hash-path batches): one warp per request, the per-request work is match_sparse.cuh.  (The main path
-// runs the same function in the match warps of the fused cycle kernel: cycle.cu.)
+// mode, generic-hash-path batches): one warp per request, the per-request work is match_sparse.cuh.
 #include <cstdlib>
 
 #include "match_sparse.cuh"

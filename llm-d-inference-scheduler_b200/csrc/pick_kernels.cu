@@ -16,6 +16,7 @@
 #include <climits>
 
 #include "index.cuh"
+#include "pick_general.cuh"
 #include "score.cuh"
 
 namespace epp {
@@ -252,6 +253,22 @@ __device__ inline Best eval_profile_inner(const ProfileDev &pf, int32_t E, const
     return b;
 }
 
+// gen::eval for profile pi of request r, with the request's top-k rows (all rows are reset first: a stage that does
+// not run leaves EPP_NO_ENDPOINT).
+template <typename P, typename CntOf>
+__device__ inline Best gen_eval_profile(const P &p, int pi, int64_t r, int32_t total, int lane, uint32_t adapter,
+                                        uint64_t key, CntOf cnt_of) {
+    const int32_t k = p.gen.topk > 1 ? p.gen.topk : 1;
+    if (pi == 0 && k > 1) {
+        for (int q = 0; q < kMaxProfiles; q++)
+            if (p.gen.topk_picks[q]) for (int j = lane; j < k; j += 32) p.gen.topk_picks[q][r * k + j] = EPP_NO_ENDPOINT;
+        __syncwarp();
+    }
+    return gen::eval(p.prof[pi], p.gen, p.E, total, lane, p.lora, adapter, p.tie_seed, key, cnt_of, k,
+                     (k > 1 && p.gen.topk_picks[pi]) ? p.gen.topk_picks[pi] + r * k : nullptr,
+                     (k > 1 && pi == 0 && p.gen.topk_scores) ? p.gen.topk_scores + r * k : nullptr);
+}
+
 __global__ void __launch_bounds__(kPickWarps * 32) k_match_pick(PickParams p, int32_t cnt_words,
                                                                 uint32_t *gscratch) {
     extern __shared__ uint32_t smem[];
@@ -324,9 +341,16 @@ __global__ void __launch_bounds__(kPickWarps * 32) k_match_pick(PickParams p, in
         const uint32_t adapter = p.model_ids ? p.model_ids[r] : 0u;
         epp_decision d;
         epp_decision_detail dd;
-        decide_stages<3>(p, r, total, p.n_profiles >= 2 ? p.in_len[r] : 0,
-                      [&](int pi, uint64_t key) { return eval_profile(p.prof[pi], p.E, cnt32, list, nl, total, lane, p.lora, adapter, p.tie_seed, key); },
-                      [&](uint32_t e) { return (int32_t)cnt_get(cnt32, e); }, d, dd);
+        auto cnt_of = [&](uint32_t e) { return (int32_t)cnt_get(cnt32, e); };
+        if (p.gen.on) {       // affinity filter / top-k: full-scan evaluation (pick_general.cuh)
+            decide_stages<3>(p, r, total, p.n_profiles >= 2 ? p.in_len[r] : 0,
+                          [&](int pi, uint64_t key) { return gen_eval_profile(p, pi, r, total, lane, adapter, key, cnt_of); },
+                          cnt_of, d, dd);
+        } else {
+            decide_stages<3>(p, r, total, p.n_profiles >= 2 ? p.in_len[r] : 0,
+                          [&](int pi, uint64_t key) { return eval_profile(p.prof[pi], p.E, cnt32, list, nl, total, lane, p.lora, adapter, p.tie_seed, key); },
+                          cnt_of, d, dd);
+        }
         if (lane == 0) {
             if (p.shard_out) {
                 epp_shard_best sb;
@@ -419,9 +443,16 @@ __global__ void __launch_bounds__(256) k_dense_pick(DensePickParams p) {
     const uint32_t adapter = p.model_ids ? p.model_ids[r] : 0u;
     epp_decision d;
     epp_decision_detail dd;
-    decide_stages<3>(p, r, total, p.in_len ? p.in_len[r] : 0,
-                  [&](int pi, uint64_t key) { return eval_profile_dense(p.prof[pi], p.E, mrow, total, lane, p.lora, adapter, p.tie_seed, key); },
-                  [&](uint32_t e) { return mrow[e]; }, d, dd);
+    auto cnt_of = [&](uint32_t e) { return mrow[e]; };
+    if (p.gen.on) {
+        decide_stages<3>(p, r, total, p.in_len ? p.in_len[r] : 0,
+                      [&](int pi, uint64_t key) { return gen_eval_profile(p, pi, r, total, lane, adapter, key, cnt_of); },
+                      cnt_of, d, dd);
+    } else {
+        decide_stages<3>(p, r, total, p.in_len ? p.in_len[r] : 0,
+                      [&](int pi, uint64_t key) { return eval_profile_dense(p.prof[pi], p.E, mrow, total, lane, p.lora, adapter, p.tie_seed, key); },
+                      cnt_of, d, dd);
+    }
     if (lane == 0) {
         p.out[r] = d;
         if (p.detail) p.detail[r] = dd;

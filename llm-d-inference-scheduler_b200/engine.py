@@ -37,10 +37,20 @@ class ScorerSpec:
 
 
 @dataclass
+class AffinityFilterSpec:
+    """prefix-cache-affinity-filter (filter/prefixcacheaffinity/plugin.go:62-66 for the defaults)."""
+    affinity_threshold: float = 0.80
+    exploration_probability: float = 0.01
+    max_ttft_penalty_ms: float = 5000.0
+    ttft_column: int = -1    # ext column holding the predicted TTFT per endpoint; -1 = no prediction attached
+
+
+@dataclass
 class ProfileSpec:
-    """One SchedulerProfile: role filter -> scorers in order -> max-score picker."""
+    """One SchedulerProfile: role filter -> [prefix-cache-affinity-filter] -> scorers in order -> max-score picker."""
     filter: int = capi.FILTER_NONE
     scorers: list = field(default_factory=list)
+    affinity: AffinityFilterSpec | None = None
 
 
 def _fill_profile(dst: capi.ProfileCfg, spec: ProfileSpec):
@@ -56,6 +66,11 @@ def _fill_profile(dst: capi.ProfileCfg, spec: ProfileSpec):
         dst.scorers[i].param = s.param
         dst.scorers[i].column = s.column
         dst.scorers[i].param2 = s.param2
+    dst.ttft_column = -1
+    if spec.affinity is not None:
+        a = spec.affinity
+        dst.affinity_threshold, dst.exploration_probability = a.affinity_threshold, a.exploration_probability
+        dst.max_ttft_penalty_ms, dst.ttft_column = a.max_ttft_penalty_ms, a.ttft_column
 
 
 def _is_torch(x) -> bool:
@@ -274,9 +289,11 @@ class Engine:
                                                 _ptr(mep), _ptr(mmo), _ptr(mst)))
 
     def schedule(self, data, offsets=None, uniform_len=None, model_ids=None, n_requests=None, keep_hashes=False,
-                 detail=True, out=None, lengths=None, asynchronous=False, multimodal=None):
+                 detail=True, out=None, lengths=None, asynchronous=False, multimodal=None, topk=False):
         """a1-a14 Scheduler.Schedule for a batch -> (decisions, details).  asynchronous=True (CUDA tensors only)
-        enqueues the batch and returns; the outputs are complete after synchronize()."""
+        enqueues the batch and returns; the outputs are complete after synchronize().  topk=True (engines created with
+        pick_k > 1) also returns the dict of the pickers' first-k lists (maxscore/picker.go:104-115): "primary",
+        "primary_scores", "prefill", "encode", each [R][pick_k], padded with EPP_NO_ENDPOINT / 0."""
         b, R, dev, keep = self._batch(data, offsets, uniform_len, model_ids, n_requests, lengths, multimodal)
         if asynchronous:
             b.flags |= capi.EPP_BATCH_ASYNC
@@ -287,10 +304,33 @@ class Engine:
         else:
             dec = np.zeros(R, dtype=DECISION_DTYPE) if out is None else out
             det = np.zeros(R, dtype=DETAIL_DTYPE) if detail else None
-        self._check(self._lib.epp_schedule(self._h, C.byref(b), _ptr(dec), _ptr(det), int(keep_hashes)))
-        return dec, det
+        if not topk:
+            self._check(self._lib.epp_schedule(self._h, C.byref(b), _ptr(dec), _ptr(det), int(keep_hashes)))
+            return dec, det
+        lists, tk = self._topk_out(R, data.device if dev else None)
+        self._check(self._lib.epp_schedule_topk(self._h, C.byref(b), _ptr(dec), _ptr(det), int(keep_hashes), C.byref(tk)))
+        return dec, det, lists
 
-    def schedule_with_match(self, match, total, input_len_bytes=None, block_size_tokens: int = 0, model_ids=None):
+    def _topk_out(self, R: int, device=None):
+        """Destination arrays of the pickers' first-k lists (numpy, or torch on `device`) + the epp_topk_out record."""
+        k = int(self.cfg.pick_k)
+        n = max(R, 1)
+        if device is not None:
+            import torch
+            lists = {name: torch.empty((n, k), dtype=torch.int32, device=device) for name in ("primary", "prefill", "encode")}
+            lists["primary_scores"] = torch.empty((n, k), dtype=torch.float64, device=device)
+        else:
+            lists = {name: np.zeros((R, k), dtype=np.uint32) for name in ("primary", "prefill", "encode")}
+            lists["primary_scores"] = np.zeros((R, k), dtype=np.float64)
+        tk = capi.TopkOut()
+        tk.struct_size = C.sizeof(capi.TopkOut)
+        tk.k = k
+        for name in ("primary", "primary_scores", "prefill", "encode"):
+            setattr(tk, name, _ptr(lists[name]).value if R else None)
+        return lists, tk
+
+    def schedule_with_match(self, match, total, input_len_bytes=None, block_size_tokens: int = 0, model_ids=None,
+                            topk=False):
         match = np.ascontiguousarray(match, dtype=np.int32).reshape(-1, self.E)
         total = np.ascontiguousarray(total, dtype=np.int32)
         R = match.shape[0]
@@ -298,9 +338,14 @@ class Engine:
         dec = np.zeros(R, dtype=DECISION_DTYPE)
         det = np.zeros(R, dtype=DETAIL_DTYPE)
         mids = None if model_ids is None else np.ascontiguousarray(model_ids, dtype=np.uint32)
-        self._check(self._lib.epp_schedule_with_match(self._h, R, _ptr(match), _ptr(total), _ptr(mids), _ptr(il),
-                                                      block_size_tokens, _ptr(dec), _ptr(det), 0))
-        return dec, det
+        if not topk:
+            self._check(self._lib.epp_schedule_with_match(self._h, R, _ptr(match), _ptr(total), _ptr(mids), _ptr(il),
+                                                          block_size_tokens, _ptr(dec), _ptr(det), 0))
+            return dec, det
+        lists, tk = self._topk_out(R)
+        self._check(self._lib.epp_schedule_with_match_topk(self._h, R, _ptr(match), _ptr(total), _ptr(mids), _ptr(il),
+                                                           block_size_tokens, _ptr(dec), _ptr(det), 0, C.byref(tk)))
+        return dec, det, lists
 
     def synchronize(self):
         self._check(self._lib.epp_synchronize(self._h))

@@ -6,6 +6,7 @@
  */
 #include "epp_oracle.h"
 
+#include <float.h>
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
@@ -603,31 +604,85 @@ uint32_t orc_tie_rank(uint64_t seed, uint64_t key, uint32_t n) {
 /* =====================================================================================
  * A.5 SchedulerProfile.Run -- scheduling/scheduler_profile.go:117-192 + maxscore picker
  * ===================================================================================== */
+typedef struct { int k; int32_t *picks; double *scores; int32_t n; } topk_req;   /* the first k of the picker, optional */
 static int profile_run_scratch(const orc_profile *p, const orc_pool *pool, const int32_t *match, int32_t total,
                                double *out_scores, double *out_max, int32_t *out_pick, int32_t *argmax_set,
-                               uint8_t *cand, double *col, uint64_t tie_seed, uint64_t tie_key);
+                               uint8_t *cand, double *col, uint64_t tie_seed, uint64_t tie_key, topk_req *tk);
 
 int orc_profile_run(const orc_profile *p, const orc_pool *pool, const int32_t *match, int32_t total,
                     double *out_scores, double *out_max, int32_t *out_pick, int32_t *argmax_set) {
     int n = pool->n;
     uint8_t *cand = (uint8_t *)malloc((size_t)n + 1);
     double *col = (double *)malloc(sizeof(double) * ((size_t)n + 1));
-    int r = profile_run_scratch(p, pool, match, total, out_scores, out_max, out_pick, argmax_set, cand, col, 0, 0);
+    int r = profile_run_scratch(p, pool, match, total, out_scores, out_max, out_pick, argmax_set, cand, col, 0, 0, NULL);
     free(cand); free(col);
     return r;
+}
+
+int orc_profile_run_topk(const orc_profile *p, const orc_pool *pool, const int32_t *match, int32_t total,
+                         uint64_t tie_seed, uint64_t tie_key, int k, int32_t *topk_picks, double *topk_scores,
+                         int32_t *out_n_picks, double *out_scores) {
+    int n = pool->n;
+    uint8_t *cand = (uint8_t *)malloc((size_t)n + 1);
+    double *col = (double *)malloc(sizeof(double) * ((size_t)n + 1));
+    double *scores = out_scores ? out_scores : (double *)malloc(sizeof(double) * ((size_t)n + 1));
+    topk_req tk = {k, topk_picks, topk_scores, 0};
+    double mx; int32_t pick;
+    int r = profile_run_scratch(p, pool, match, total, scores, &mx, &pick, NULL, cand, col, tie_seed, tie_key, &tk);
+    if (out_n_picks) *out_n_picks = tk.n;
+    if (!out_scores) free(scores);
+    free(cand); free(col);
+    return r;
+}
+
+double orc_explore_u(uint64_t seed, uint64_t key) {
+    return (double)(mix64((seed ^ 0xA0761D6478BD642FULL) ^ mix64(key)) >> 11) * 0x1.0p-53;
+}
+
+/* Plugin.Filter -- filter/prefixcacheaffinity/plugin.go:105-151: narrows cand[] to the sticky endpoints. */
+static void affinity_filter(const orc_profile *p, const orc_pool *pool, const int32_t *match, int32_t total,
+                            uint8_t *cand, int n_cand, uint64_t tie_seed, uint64_t tie_key) {
+    int n = pool->n;
+    if (n_cand <= 1 || !(p->affinity_threshold > 0)) return;                           /* :108-110 */
+    if (tie_seed && orc_explore_u(tie_seed, tie_key) < p->exploration_probability) return;   /* :113-117 */
+    const double *ttft = (p->ttft_column >= 0 && p->ttft_column < pool->n_ext_cols)
+                             ? pool->ext + (size_t)p->ttft_column * (size_t)n : NULL;
+    int n_sticky = 0, n_non = 0;
+    double best_sticky = DBL_MAX, best_non = DBL_MAX;                                   /* bestTTFT, :173-184 */
+    for (int e = 0; e < n; e++) {
+        if (!cand[e]) continue;
+        double score = 0;                                                              /* prefixCacheScore, :160-171 */
+        if (total > 0) score = (double)match[e] / (double)total;
+        double t = ttft ? ttft[e] : DBL_MAX;
+        if (score >= p->affinity_threshold) { n_sticky++; if (t < best_sticky) best_sticky = t; }
+        else { n_non++; if (t < best_non) best_non = t; }
+    }
+    if (n_sticky == 0) return;                                                          /* :130-134 */
+    if (p->max_ttft_penalty_ms > 0 && n_non > 0 && best_sticky - best_non > p->max_ttft_penalty_ms) return;   /* :137-146 */
+    for (int e = 0; e < n; e++) {
+        if (!cand[e]) continue;
+        double score = 0;
+        if (total > 0) score = (double)match[e] / (double)total;
+        if (!(score >= p->affinity_threshold)) cand[e] = 0;
+    }
 }
 
 /* The Go code allocates fresh maps per call; the timed CPU baseline reuses per-thread scratch instead, which only
  * makes the baseline FASTER than the reference. */
 static int profile_run_scratch(const orc_profile *p, const orc_pool *pool, const int32_t *match, int32_t total,
                                double *out_scores, double *out_max, int32_t *out_pick, int32_t *argmax_set,
-                               uint8_t *cand, double *col, uint64_t tie_seed, uint64_t tie_key) {
+                               uint8_t *cand, double *col, uint64_t tie_seed, uint64_t tie_key, topk_req *tk) {
     int n = pool->n;
     int n_cand = 0;
-    for (int e = 0; e < n; e++) {                       /* runFilterPlugins, :130-149 */
+    if (tk) {
+        tk->n = 0;
+        for (int j = 0; j < tk->k; j++) { if (tk->picks) tk->picks[j] = -1; if (tk->scores) tk->scores[j] = 0; }
+    }
+    for (int e = 0; e < n; e++) {                       /* runFilterPlugins, :130-149: the role filter ... */
         cand[e] = (uint8_t)orc_role_filter_keeps(p->filter, pool->role[e]);
         n_cand += cand[e];
     }
+    affinity_filter(p, pool, match, total, cand, n_cand, tie_seed, tie_key);   /* ... then the affinity filter */
     if (n_cand == 0) {                                  /* :119-121 */
         for (int e = 0; e < n; e++) out_scores[e] = -1.0;
         if (out_max) *out_max = 0;
@@ -672,6 +727,40 @@ static int profile_run_scratch(const orc_profile *p, const orc_pool *pool, const
     }
     if (out_max) *out_max = mx;
     if (out_pick) *out_pick = first;
+    if (tk && tk->k > 0) {
+        /* the first k of shuffle + stable sort (maxscore/picker.go:91-110): group after group in descending score
+         * order; col[] is free now and marks the endpoints already emitted */
+        for (int e = 0; e < n; e++) col[e] = 0;
+        double v = 0; int have_v = 0; int rem = 0;
+        for (int j = 0; j < tk->k; j++) {
+            if (rem == 0) {
+                double best = 0; int hb = 0;
+                for (int e = 0; e < n; e++) {
+                    if (!cand[e] || col[e] != 0) continue;
+                    if (have_v && !(out_scores[e] < v)) continue;
+                    if (!hb || out_scores[e] > best) { best = out_scores[e]; hb = 1; }
+                }
+                if (!hb) break;
+                v = best; have_v = 1;
+                for (int e = 0; e < n; e++)
+                    if (cand[e] && col[e] == 0 && !(out_scores[e] < v) && !(out_scores[e] > v)) rem++;
+            }
+            uint32_t rank = tie_seed ? orc_tie_rank(tie_seed + (uint64_t)j * 0x9E3779B97F4A7C15ULL, tie_key, (uint32_t)rem) : 0;
+            int pick = -1;
+            for (int e = 0; e < n; e++) {
+                if (!cand[e] || col[e] != 0) continue;
+                if (out_scores[e] < v || out_scores[e] > v) continue;
+                if (rank == 0) { pick = e; break; }
+                rank--;
+            }
+            if (pick < 0) break;
+            col[pick] = 1;
+            rem--;
+            if (tk->picks) tk->picks[j] = pick;
+            if (tk->scores) tk->scores[j] = v;
+            tk->n = j + 1;
+        }
+    }
     return cnt;
 }
 
@@ -692,7 +781,7 @@ static void schedule_scratch(const orc_profile *primary, const orc_profile *pref
                              const int32_t *match, int32_t total, int32_t block_size_tokens, int64_t input_len_bytes,
                              int64_t non_cached_tokens, int always_disagg, double *scratch_scores, orc_decision *out,
                              uint8_t *cand, double *col, uint64_t tie_seed, uint64_t tie_req,
-                             const orc_profile *encode, int multimodal);
+                             const orc_profile *encode, int multimodal, topk_req *tk);
 
 void orc_schedule(const orc_profile *primary, const orc_profile *prefill, const orc_pool *pool,
                   const int32_t *match, int32_t total, int32_t block_size_tokens,
@@ -701,7 +790,7 @@ void orc_schedule(const orc_profile *primary, const orc_profile *prefill, const 
     uint8_t *cand = (uint8_t *)malloc((size_t)pool->n + 1);
     double *col = (double *)malloc(sizeof(double) * ((size_t)pool->n + 1));
     schedule_scratch(primary, prefill, pool, match, total, block_size_tokens, input_len_bytes, non_cached_tokens,
-                     always_disagg, scratch_scores, out, cand, col, 0, 0, NULL, 0);
+                     always_disagg, scratch_scores, out, cand, col, 0, 0, NULL, 0, NULL);
     free(cand); free(col);
 }
 
@@ -709,11 +798,13 @@ static void schedule_scratch(const orc_profile *primary, const orc_profile *pref
                              const int32_t *match, int32_t total, int32_t block_size_tokens, int64_t input_len_bytes,
                              int64_t non_cached_tokens, int always_disagg, double *scratch_scores, orc_decision *out,
                              uint8_t *cand, double *col, uint64_t tie_seed, uint64_t tie_req,
-                             const orc_profile *encode, int multimodal) {
+                             const orc_profile *encode, int multimodal, topk_req *tk) {
     memset(out, 0, sizeof *out);
+    if (tk) for (int q = 1; q < 3; q++)          /* stages that do not run leave empty lists */
+        for (int j = 0; j < tk[q].k; j++) { if (tk[q].picks) tk[q].picks[j] = -1; if (tk[q].scores) tk[q].scores[j] = 0; }
     out->pick = -1; out->prefill_pick = -1; out->encode_pick = -1;
     double mx; int32_t pick;
-    int ties = profile_run_scratch(primary, pool, match, total, scratch_scores, &mx, &pick, NULL, cand, col, tie_seed, 4 * tie_req);
+    int ties = profile_run_scratch(primary, pool, match, total, scratch_scores, &mx, &pick, NULL, cand, col, tie_seed, 4 * tie_req, tk ? &tk[0] : NULL);
     if (ties == 0) {            /* disagg ProcessResults :335-338 / single ProcessResults: error */
         out->status = -1;
         return;
@@ -723,7 +814,7 @@ static void schedule_scratch(const orc_profile *primary, const orc_profile *pref
     if (encode && multimodal) { /* disagg_profile_handler.go:284-295 + always_disagg_mm_decider.go:47-49 */
         double emx; int32_t epick;
         out->encode_ran = 1;
-        int et = profile_run_scratch(encode, pool, match, total, scratch_scores, &emx, &epick, NULL, cand, col, tie_seed, 4 * tie_req + 2);
+        int et = profile_run_scratch(encode, pool, match, total, scratch_scores, &emx, &epick, NULL, cand, col, tie_seed, 4 * tie_req + 2, tk ? &tk[2] : NULL);
         if (et > 0) { out->encode_pick = epick; out->encode_tie_count = et; out->encode_score = emx; }
     }
     if (prefill) {              /* disagg_profile_handler.go:296-308 */
@@ -732,7 +823,7 @@ static void schedule_scratch(const orc_profile *primary, const orc_profile *pref
         out->prefill_ran = go;
         if (go) {
             double pmx; int32_t ppick;
-            int pt = profile_run_scratch(prefill, pool, match, total, scratch_scores, &pmx, &ppick, NULL, cand, col, tie_seed, 4 * tie_req + 1);
+            int pt = profile_run_scratch(prefill, pool, match, total, scratch_scores, &pmx, &ppick, NULL, cand, col, tie_seed, 4 * tie_req + 1, tk ? &tk[1] : NULL);
             if (pt > 0) { out->prefill_pick = ppick; out->prefill_tie_count = pt; out->prefill_score = pmx; }
         }
     }
@@ -747,9 +838,16 @@ static void cycle_scratch(const orc_cycle_cfg *cfg, const orc_indexer *ix, const
                                 cfg->block_size_tokens, cfg->max_prefix_blocks, scratch_hashes, cap);
     memset(scratch_match, 0, sizeof(int32_t) * (size_t)pool->n);
     orc_match_longest_prefix(ix, scratch_hashes, total, scratch_match, pool->n);
+    const int64_t row = (int64_t)(tie_req - cfg->tie_base);
+    topk_req tk[3];
+    const int k = cfg->topk > 1 ? cfg->topk : 0;
+    tk[0] = (topk_req){k, cfg->topk_primary ? cfg->topk_primary + row * k : NULL,
+                       cfg->topk_primary_scores ? cfg->topk_primary_scores + row * k : NULL, 0};
+    tk[1] = (topk_req){k, cfg->topk_prefill ? cfg->topk_prefill + row * k : NULL, NULL, 0};
+    tk[2] = (topk_req){k, cfg->topk_encode ? cfg->topk_encode + row * k : NULL, NULL, 0};
     schedule_scratch(primary, prefill, pool, scratch_match, total, cfg->block_size_tokens, (int64_t)prompt_len,
                      cfg->non_cached_tokens, cfg->always_disagg, scratch_scores, out, cand, col, cfg->tie_seed, tie_req,
-                     cfg->encode, cfg->multimodal ? cfg->multimodal[tie_req - cfg->tie_base] : 0);
+                     cfg->encode, cfg->multimodal ? cfg->multimodal[row] : 0, k ? tk : NULL);
     if (out_total) *out_total = total;
 }
 

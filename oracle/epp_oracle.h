@@ -104,9 +104,16 @@ typedef struct {
 
 #define ORC_MAX_SCORERS 8
 typedef struct {
-    int32_t filter;              /* ORC_FILTER_* (one role filter per profile; chains of one) */
+    int32_t filter;              /* ORC_FILTER_* role filter, first in the profile's filter chain */
     int32_t n_scorers;
     orc_scorer scorers[ORC_MAX_SCORERS];
+    /* prefix-cache-affinity-filter after the role filter (filter/prefixcacheaffinity/plugin.go:105-151);
+     * affinity_threshold <= 0: not configured (:108). */
+    double affinity_threshold;
+    double exploration_probability;
+    double max_ttft_penalty_ms;
+    int32_t ttft_column;         /* ext column with LatencyPredictionInfo.TTFT per endpoint; < 0: attribute absent */
+    int32_t _pad;
 } orc_profile;
 
 /* Pool-state snapshot (fwkdl.Metrics + role label), struct-of-arrays, n endpoints. */
@@ -132,6 +139,18 @@ typedef struct {
  * representative of maxscore/picker.go:87-115's random tie-break); argmax_set (cap n) optional. */
 int orc_profile_run(const orc_profile *p, const orc_pool *pool, const int32_t *match, int32_t total,
                     double *out_scores, double *out_max, int32_t *out_pick, int32_t *argmax_set);
+
+/* The same run with the build's reproducible random draws (tie_seed != 0; key = 4 * request ordinal + profile index) and
+ * the first k endpoints of MaxScorePicker.Pick (maxscore/picker.go:87-115: shuffle, stable sort by score descending,
+ * first k): groups of equal score in descending order, inside a group pick j is the member of rank
+ * orc_tie_rank(tie_seed + j * 0x9E3779B97F4A7C15, key, members left) among the members not emitted yet (ascending slot
+ * order), or the lowest remaining slot when tie_seed == 0.  topk_picks / topk_scores: k entries, padded with -1 / 0.
+ * Returns the size of the arg-max set; *out_n_picks = number of endpoints emitted. */
+int orc_profile_run_topk(const orc_profile *p, const orc_pool *pool, const int32_t *match, int32_t total,
+                         uint64_t tie_seed, uint64_t tie_key, int k, int32_t *topk_picks, double *topk_scores,
+                         int32_t *out_n_picks, double *out_scores);
+/* Exploration draw of the affinity filter: u in [0, 1) = (mix64((seed ^ 0xA0761D6478BD642F) ^ mix64(key)) >> 11) * 2^-53. */
+double orc_explore_u(uint64_t seed, uint64_t key);
 
 /* Individual scorer columns (plugin-parity mode for Scorer.Score).  cand[e]!=0 marks the filtered
  * candidate list the scorer sees; non-candidates get 0. */
@@ -181,6 +200,12 @@ typedef struct {
     uint64_t tie_base;           /* ordinal of request 0 of the batch (orc_cycle_batch: request r has ordinal base+r) */
     const orc_profile *encode;   /* the "encode" profile of the disagg handler, or NULL                             */
     const uint8_t *multimodal;   /* [R] hasMultimodalContent per request (multimodal_helpers.go), or NULL; orc_cycle_batch only */
+    int32_t topk;                /* maxNumOfEndpoints of the pickers (<= 1: one endpoint); orc_cycle_batch only       */
+    int32_t _pad2;
+    int32_t *topk_primary;       /* [R][topk] (-1 padded) or NULL                                                    */
+    double *topk_primary_scores; /* [R][topk] or NULL                                                                */
+    int32_t *topk_prefill;       /* [R][topk] or NULL                                                                */
+    int32_t *topk_encode;        /* [R][topk] or NULL                                                                */
 } orc_cycle_cfg;
 /* Rank (in ascending slot order) of the arg-max-set member the build picks when tie_seed != 0:
  * ((mix64(seed ^ mix64(key)) >> 32) * n) >> 32 with the SplitMix64 output function, key = 4 * ordinal + profile index. */

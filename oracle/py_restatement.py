@@ -224,11 +224,50 @@ def score(kind, param, endpoints, match, total):
     raise ValueError(kind)
 
 
-def profile_run(filter_kind, scorers, endpoints, match, total):
+def affinity_filter(cfg, cand, endpoints, match, total, explore_draw):
+    """Plugin.Filter, filter/prefixcacheaffinity/plugin.go:105-151.  cfg = (affinityThreshold, explorationProbability,
+    maxTTFTPenaltyMs); endpoints[i].get("ttft") = predicted TTFT or None (attribute absent); explore_draw = the value
+    rand.Float64() returned.  Returns the surviving candidate indices."""
+    thr, eps, max_penalty = cfg
+    if len(cand) <= 1 or thr <= 0:                                # :108-110
+        return cand
+    if explore_draw < eps:                                        # :113-117
+        return cand
+
+    def prefix_cache_score(i):                                    # :160-171
+        return match[i] / total if total > 0 else 0.0
+
+    def best_ttft(idx):                                           # :173-184
+        best = 1.7976931348623157e308
+        for i in idx:
+            t = endpoints[i].get("ttft")
+            if t is not None and t < best:
+                best = t
+        return best
+
+    sticky = [i for i in cand if prefix_cache_score(i) >= thr]   # :120-127
+    non_sticky = [i for i in cand if not prefix_cache_score(i) >= thr]
+    if not sticky:                                                # :130-134
+        return cand
+    if max_penalty > 0 and non_sticky and best_ttft(sticky) - best_ttft(non_sticky) > max_penalty:   # :137-146
+        return cand
+    return sticky
+
+
+def pick_first_k(acc, cand, k, shuffled):
+    """MaxScorePicker.Pick, picker/maxscore/picker.go:87-115: `shuffled` is the candidate list after
+    ShuffleScoredEndpoints (any permutation of cand); stable sort by score descending; first k."""
+    assert sorted(shuffled) == sorted(cand)
+    return sorted(shuffled, key=lambda i: -acc[i])[:k]           # Python's sort is stable, like slices.SortStableFunc
+
+
+def profile_run(filter_kind, scorers, endpoints, match, total, affinity=None, explore_draw=1.0):
     """scheduler_profile.go:117-192; returns (dict idx->score, max, argmax set) or None if no candidates."""
     cand = [i for i, e in enumerate(endpoints) if role_filter(filter_kind, e.get("role"))]
     if not cand:
         return None
+    if affinity is not None:
+        cand = affinity_filter(affinity, cand, endpoints, match, total, explore_draw)
     acc = {i: 0.0 for i in cand}
     sub = [endpoints[i] for i in cand]
     subm = [match[i] for i in cand]

@@ -29,7 +29,9 @@ class Scorer(C.Structure):
 
 
 class Profile(C.Structure):
-    _fields_ = [("filter", C.c_int32), ("n_scorers", C.c_int32), ("scorers", Scorer * MAX_SCORERS)]
+    _fields_ = [("filter", C.c_int32), ("n_scorers", C.c_int32), ("scorers", Scorer * MAX_SCORERS),
+                ("affinity_threshold", C.c_double), ("exploration_probability", C.c_double),
+                ("max_ttft_penalty_ms", C.c_double), ("ttft_column", C.c_int32), ("_pad", C.c_int32)]
 
 
 class Pool(C.Structure):
@@ -50,7 +52,9 @@ class CycleCfg(C.Structure):
     _fields_ = [("block_size_tokens", C.c_int32), ("max_prefix_blocks", C.c_int32),
                 ("non_cached_tokens", C.c_int64), ("always_disagg", C.c_int32), ("_pad", C.c_int32),
                 ("model", C.c_char_p), ("model_len", C.c_size_t), ("tie_seed", C.c_uint64), ("tie_base", C.c_uint64),
-                ("encode", C.POINTER(Profile)), ("multimodal", C.c_void_p)]
+                ("encode", C.POINTER(Profile)), ("multimodal", C.c_void_p), ("topk", C.c_int32), ("_pad2", C.c_int32),
+                ("topk_primary", C.c_void_p), ("topk_primary_scores", C.c_void_p), ("topk_prefill", C.c_void_p),
+                ("topk_encode", C.c_void_p)]
 
 
 DECISION_DTYPE = np.dtype([("status", "<i4"), ("pick", "<i4"), ("tie_count", "<i4"), ("prefill_pick", "<i4"),
@@ -113,6 +117,11 @@ def lib():
                                    C.c_int32, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.POINTER(Decision)]
         L.orc_tie_rank.restype = C.c_uint32
         L.orc_tie_rank.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
+        L.orc_profile_run_topk.restype = C.c_int
+        L.orc_profile_run_topk.argtypes = [C.POINTER(Profile), C.POINTER(Pool), C.c_void_p, C.c_int32, C.c_uint64,
+                                           C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
+        L.orc_explore_u.restype = C.c_double
+        L.orc_explore_u.argtypes = [C.c_uint64, C.c_uint64]
         L.orc_cycle_batch.argtypes = [C.POINTER(CycleCfg), C.c_void_p, C.POINTER(Profile), C.POINTER(Profile),
                                       C.POINTER(Pool), C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                       C.c_void_p]
@@ -140,10 +149,16 @@ def hash_prompt(data: bytes, model: bytes, block_size_tokens: int, max_prefix_bl
     return [int(x) for x in out[:n]]
 
 
-def make_profile(filter_kind: int, scorers: list[tuple]) -> Profile:
+def make_profile(filter_kind: int, scorers: list[tuple], affinity: tuple | None = None) -> Profile:
+    """affinity = (affinityThreshold, explorationProbability, maxTTFTPenaltyMs[, ttft ext column]) of a
+    prefix-cache-affinity-filter placed after the role filter, or None."""
     p = Profile()
     p.filter = filter_kind
     p.n_scorers = len(scorers)
+    p.ttft_column = -1
+    if affinity is not None:
+        p.affinity_threshold, p.exploration_probability, p.max_ttft_penalty_ms = affinity[:3]
+        p.ttft_column = int(affinity[3]) if len(affinity) > 3 else -1
     for i, sc in enumerate(scorers):              # (kind, weight, param[, column[, param2]])
         kind, weight, param = sc[:3]
         p.scorers[i].kind = kind
@@ -266,6 +281,23 @@ def score_column(scorer: tuple, pool: PoolState, cand, match, total: int):
     return out
 
 
+def profile_run_topk(profile: Profile, pool: PoolState, match, total: int, k: int, tie_seed: int = 0, tie_key: int = 0):
+    """SchedulerProfile.Run with the build's reproducible draws -> (picks list (<= k), their scores, arg-max set size,
+    scores[E] with -1 for endpoints the role filter dropped)."""
+    m = np.ascontiguousarray(match, dtype=np.int32)
+    picks = np.full(max(k, 1), -1, dtype=np.int32)
+    sc = np.zeros(max(k, 1), dtype=np.float64)
+    scores = np.zeros(pool.n, dtype=np.float64)
+    n = C.c_int32(0)
+    ties = lib().orc_profile_run_topk(C.byref(profile), C.byref(pool.c), _ptr(m), total, tie_seed, tie_key, k, _ptr(picks),
+                                      _ptr(sc), C.byref(n), _ptr(scores))
+    return [int(x) for x in picks[:n.value]], [float(x) for x in sc[:n.value]], ties, scores
+
+
+def explore_u(seed: int, key: int) -> float:
+    return float(lib().orc_explore_u(seed, key))
+
+
 def tie_rank(seed: int, key: int, n: int) -> int:
     """Rank of the arg-max-set member picked under the build's reproducible tie rule (oracle/epp_oracle.h)."""
     return int(lib().orc_tie_rank(seed, key, n))
@@ -289,9 +321,10 @@ def schedule(primary: Profile, prefill: Profile | None, pool: PoolState, match, 
 def cycle_batch(model: bytes, block_size_tokens: int, max_prefix_blocks: int, nct: int, always_disagg: bool,
                 indexer: Indexer, primary: Profile, prefill: Profile | None, pool: PoolState,
                 data: np.ndarray, offsets: np.ndarray, n_threads: int = 1, tie_seed: int = 0, tie_base: int = 0,
-                encode: Profile | None = None, multimodal=None):
+                encode: Profile | None = None, multimodal=None, topk: int = 0):
     """Whole cycle (hash -> match -> schedule) for R prompts against a frozen index.
-    Returns (decisions structured array [R], totals int32[R])."""
+    Returns (decisions structured array [R], totals int32[R]); with topk > 1 also a dict of the pickers' first-k lists
+    {"primary": int32[R][k] (-1 padded), "primary_scores": f64[R][k], "prefill": ..., "encode": ...}."""
     cfg = CycleCfg()
     cfg.block_size_tokens = block_size_tokens
     cfg.max_prefix_blocks = max_prefix_blocks
@@ -312,7 +345,18 @@ def cycle_batch(model: bytes, block_size_tokens: int, max_prefix_blocks: int, nc
     R = offsets.shape[0] - 1
     out = np.zeros(R, dtype=DECISION_DTYPE)
     totals = np.zeros(R, dtype=np.int32)
+    lists = None
+    if topk > 1:
+        cfg.topk = topk
+        lists = {"primary": np.full((R, topk), -1, np.int32), "primary_scores": np.zeros((R, topk), np.float64),
+                 "prefill": np.full((R, topk), -1, np.int32), "encode": np.full((R, topk), -1, np.int32)}
+        cfg.topk_primary = lists["primary"].ctypes.data
+        cfg.topk_primary_scores = lists["primary_scores"].ctypes.data
+        cfg.topk_prefill = lists["prefill"].ctypes.data
+        cfg.topk_encode = lists["encode"].ctypes.data
     lib().orc_cycle_batch(C.byref(cfg), indexer.h, C.byref(primary),
                           C.byref(prefill) if prefill is not None else None, C.byref(pool.c), _ptr(data),
                           _ptr(offsets), R, n_threads, _ptr(out), _ptr(totals))
+    if lists is not None:
+        return out, totals, lists
     return out, totals

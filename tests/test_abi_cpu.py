@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported(epp):
     # and the ctypes table binds exactly the declared set
     assert sorted(epp.capi.SIGNATURES) == declared
     lib = epp.capi.load()
-    assert lib.epp_abi_version() == 4
+    assert lib.epp_abi_version() == 5
 
 
 def test_library_contains_sm100a_code(epp):

@@ -439,3 +439,103 @@ def test_new_scorers_random_vs_python_restatement(orc):
         assert mx == wmx and aset == wset and pick == wset[0]
         for i in range(n):
             assert scores[i] == (acc[i] if i in acc else -1.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# max-score picker, first k (picker/maxscore/picker_test.go:30-128) and prefix-cache-affinity-filter
+# (filter/prefixcacheaffinity/plugin_test.go:50-118)
+# ------------------------------------------------------------------------------------------------
+PICKER_KATS = [
+    ("Single max score", 1, [10, 25, 15], [1], 0),
+    ("Multiple max scores, all are equally scored", 2, [50, 50, 30], [0, 1], 2),
+    ("Multiple results sorted by highest score, more pods than needed", 2, [20, 25, 30], [2, 1], 0),
+    ("Multiple results sorted by highest score, less pods than needed", 4, [20, 25, 30], [2, 1, 0], 0),
+    ("Multiple results sorted by highest score, num of pods exactly needed", 3, [30, 25, 30], [0, 2, 1], 2),
+]
+
+
+@pytest.mark.parametrize("seed", [0, 9, 10, 11])
+@pytest.mark.parametrize("name,k,scores,want,n_tie", PICKER_KATS, ids=[c[0] for c in PICKER_KATS])
+def test_reference_TestPickMaxScorePicker(orc, name, k, scores, want, n_tie, seed):
+    pool = _pool(orc, role=[0, 0, 0], kv=[0, 0, 0], waiting=[0, 0, 0], ext=[[x / 100.0 for x in scores]])
+    prof = orc.make_profile(orc.FILTER_NONE, [(orc.SCORER_EXTERNAL, 1.0, 0)])
+    picks, sc, ties, _ = orc.profile_run_topk(prof, pool, [0, 0, 0], 0, k, tie_seed=seed, tie_key=12)
+    assert len(picks) == len(want) and sc == [scores[e] / 100.0 for e in picks]
+    assert sorted(picks[:n_tie]) == sorted(want[:n_tie]) and picks[n_tie:] == want[n_tie:]
+    assert ties == max(n_tie, 1)
+
+
+AFFINITY_KATS = [
+    ("AffinityThresholdDisabled", (0.0, 0.0, 0.0), [(0, 10), (90, 20)], 2),
+    ("SingleEndpoint", (0.80, 0.0, 0.0), [(90, 10)], 1),
+    ("NoStickyEndpoints", (0.80, 0.0, 0.0), [(10, 10), (20, 20), (50, 30)], 3),
+    ("NarrowToSticky", (0.80, 0.0, 5000.0), [(90, 100), (85, 120), (10, 50)], 2),
+    ("TTFTPenaltyBreaksStickiness", (0.80, 0.0, 100.0), [(90, 500), (10, 50)], 2),
+    ("ExplorationProbability", (0.80, 1.0, 0.0), [(90, 100), (10, 50)], 2),
+]
+
+
+@pytest.mark.parametrize("name,cfg,eps,kept", AFFINITY_KATS, ids=[c[0] for c in AFFINITY_KATS])
+def test_reference_affinity_filter(orc, name, cfg, eps, kept):
+    n = len(eps)
+    pool = _pool(orc, role=[0] * n, kv=[0] * n, waiting=[0] * n, ext=[[t for _, t in eps]])
+    prof = orc.make_profile(orc.FILTER_NONE, [], affinity=cfg + (0,))
+    _, _, ties, _ = orc.profile_run_topk(prof, pool, [m for m, _ in eps], 100, 1, tie_seed=3, tie_key=0)
+    assert ties == kept                      # no scorer: every surviving candidate scores 0.0
+    got = pr.affinity_filter(cfg, list(range(n)), [{"ttft": t} for _, t in eps], [m for m, _ in eps], 100,
+                             explore_draw=0.5)
+    assert len(got) == kept
+
+
+def test_affinity_and_topk_random_vs_python_restatement(orc):
+    """C oracle vs the independent restatement: filter outcome, renormalised scores, and the first k endpoints -- the
+    oracle's reproducible order must be what the reference's shuffle + stable sort yields for SOME shuffle, namely the
+    one that lists the endpoints in the oracle's own order."""
+    import random
+    rng = random.Random(31)
+    labels = {orc.ROLE_NONE: None, orc.ROLE_DECODE: "decode", orc.ROLE_PREFILL: "prefill", orc.ROLE_BOTH: "both"}
+    fnames = {orc.FILTER_NONE: "none", orc.FILTER_DECODE: "decode", orc.FILTER_PREFILL: "prefill"}
+    kinds = {orc.SCORER_PREFIX: "prefix", orc.SCORER_KV_UTIL: "kv", orc.SCORER_QUEUE: "queue", orc.SCORER_RUNNING: "running"}
+    narrowed = explored = 0
+    for it in range(300):
+        n = rng.randint(1, 30)
+        roles = [rng.choice(list(labels)) for _ in range(n)]
+        kv = [rng.randrange(4) / 4.0 for _ in range(n)]
+        waiting = [rng.choice([0, 0, 3, rng.randint(1, 9)]) for _ in range(n)]
+        running = [rng.randint(0, 5) for _ in range(n)]
+        ttft = [float(rng.randint(0, 100)) for _ in range(n)]
+        requests = [rng.choice([0, 1, rng.randint(2, 9)]) for _ in range(n)]
+        total = rng.choice([0, 4, 10])
+        match = [rng.choice([0, 0, rng.randint(0, total)]) for _ in range(n)]
+        sc = [(rng.choice(list(kinds)), rng.choice([1.0, 2.0, 0.5]), 0) for _ in range(rng.randint(0, 4))]
+        use_ar = rng.random() < 0.5
+        c_sc = list(sc) + ([(orc.SCORER_ACTIVE_REQUEST, 1.0, 1.0, 1, 1.0)] if use_ar else [])
+        p_sc = [(kinds[k], w, p) for k, w, p in sc] + ([("active_request", 1.0, (1.0, 1.0))] if use_ar else [])
+        aff = (rng.choice([0.0, 0.3, 0.5, 1.0]), rng.choice([0.0, 0.2, 1.0]), rng.choice([0.0, 20.0, 5000.0]))
+        with_ttft = rng.random() < 0.7
+        fk = rng.choice(list(fnames))
+        seed, key, k = rng.choice([0, 1, 0xFEED]), rng.randrange(1 << 40), rng.randint(1, 6)
+        pool = _pool(orc, role=roles, kv=kv, waiting=waiting, running=running, ext=[ttft, requests])
+        prof = orc.make_profile(fk, c_sc, affinity=aff + ((0,) if with_ttft else ()))
+        picks, pscores, ties, scores = orc.profile_run_topk(prof, pool, match, total, k, tie_seed=seed, tie_key=key)
+        draw = orc.explore_u(seed, key) if seed else 1.0         # deterministic mode never explores
+        eps = [{"role": labels[r], "kv": kv[i], "waiting": waiting[i], "running": running[i], "requests": requests[i],
+                "ttft": ttft[i] if with_ttft else None} for i, r in enumerate(roles)]
+        want = pr.profile_run(fnames[fk], p_sc, eps, match, total, affinity=aff, explore_draw=draw)
+        if want is None:
+            assert ties == 0 and picks == []
+            continue
+        acc, wmx, wset = want
+        plain = pr.profile_run(fnames[fk], p_sc, eps, match, total)
+        narrowed += len(acc) < len(plain[0])
+        explored += seed != 0 and draw < aff[1]
+        assert ties == len(wset) and pscores[0] == wmx and picks[0] in wset
+        assert len(picks) == min(k, len(acc)) and len(set(picks)) == len(picks)
+        for e, v in zip(picks, pscores):
+            assert acc[e] == v
+        rest = [i for i in acc if i not in picks]
+        assert picks == pr.pick_first_k(acc, list(acc), k, picks + rest)      # a shuffle the reference could have drawn
+        assert all(acc[i] <= pscores[-1] for i in rest)
+        if seed == 0:                                             # deterministic mode: ascending slots inside a group
+            assert picks == sorted(picks, key=lambda i: (-acc[i], i))
+    assert narrowed > 30 and explored > 10
