@@ -8,6 +8,8 @@ Reference interfaces mirrored (paths relative to the reference root):
   NewWeightedScorer                                       pkg/epp/scheduling/weighted_scorer.go:24-40
   SchedulerProfile (WithFilters/WithScorers/WithPicker)   pkg/epp/scheduling/scheduler_profile.go
   Scheduler.Schedule                                      pkg/epp/scheduling/scheduler.go:54-102
+  MaxScorePicker (maxNumOfEndpoints)                      .../picker/maxscore/picker.go:58-115
+  prefix-cache-affinity-filter                            .../filter/prefixcacheaffinity/plugin.go:45-151
   approximateprefix dataProducer Produce / PreRequest     .../approximateprefix/plugin.go:135-200
 """
 from __future__ import annotations
@@ -17,7 +19,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _capi as capi
-from .engine import Engine, ProfileSpec, ScorerSpec
+from .engine import AffinityFilterSpec, Engine, ProfileSpec, ScorerSpec
 
 RoleLabel = "llm-d.ai/role"
 _ROLE_BY_LABEL = {
@@ -179,13 +181,23 @@ def NewEncodeRole():
     return _RoleFilter(capi.FILTER_ENCODE)
 
 
-class MaxScorePicker:                            # picker/maxscore (k = 1); tie rule: lowest slot id
-    pass
+@dataclass
+class PrefixCacheAffinityFilter:                 # filter/prefixcacheaffinity "prefix-cache-affinity-filter"; DefaultConfig :62-66
+    affinityThreshold: float = 0.80
+    explorationProbability: float = 0.01
+    maxTTFTPenaltyMs: float = 5000.0
+    ttft_column: int = -1                        # ext column carrying LatencyPredictionInfo.TTFT (-1: attribute absent)
+
+
+@dataclass
+class MaxScorePicker:                            # picker/maxscore; tie rule: include/epp_engine.h "Tie rule" / "Top-k"
+    maxNumOfEndpoints: int = 1
 
 
 def NewMaxScorePicker(maxNumOfEndpoints: int = 1):
-    assert maxNumOfEndpoints == 1, "the engine implements the default top-1 picker"
-    return MaxScorePicker()
+    if maxNumOfEndpoints <= 0:                   # picker.go:59-61: invalid value -> DefaultMaxNumOfEndpoints
+        maxNumOfEndpoints = 1
+    return MaxScorePicker(maxNumOfEndpoints)
 
 
 class SchedulerProfile:
@@ -195,7 +207,11 @@ class SchedulerProfile:
         self.picker = MaxScorePicker()
 
     def WithFilters(self, *filters):
-        assert len(filters) <= 1, "one role filter per profile"
+        roles = [f for f in filters if isinstance(f, _RoleFilter)]
+        aff = [f for f in filters if isinstance(f, PrefixCacheAffinityFilter)]
+        assert len(roles) <= 1 and len(aff) <= 1 and len(roles) + len(aff) == len(filters), \
+            "a profile's filter chain is: [one role filter] [one prefix-cache-affinity-filter]"
+        assert not (roles and aff) or filters.index(roles[0]) < filters.index(aff[0]), "the role filter comes first"
         self.filters = list(filters)
         return self
 
@@ -207,8 +223,10 @@ class SchedulerProfile:
         for p in plugins:
             if isinstance(p, WeightedScorer):
                 self.scorers.append(p)
-            elif isinstance(p, _RoleFilter):
+            elif isinstance(p, (_RoleFilter, PrefixCacheAffinityFilter)):
                 self.filters.append(p)
+            elif isinstance(p, MaxScorePicker):
+                self.picker = p
         return None
 
     def WithPicker(self, picker):
@@ -216,9 +234,13 @@ class SchedulerProfile:
         return self
 
     def spec(self) -> ProfileSpec:
-        return ProfileSpec(self.filters[0].kind if self.filters else capi.FILTER_NONE,
+        roles = [f for f in self.filters if isinstance(f, _RoleFilter)]
+        aff = [f for f in self.filters if isinstance(f, PrefixCacheAffinityFilter)]
+        return ProfileSpec(roles[0].kind if roles else capi.FILTER_NONE,
                            [ScorerSpec(ws.scorer.kind, ws.weight, ws.scorer.param, ws.scorer.column, ws.scorer.param2)
-                            for ws in self.scorers])
+                            for ws in self.scorers],
+                           AffinityFilterSpec(aff[0].affinityThreshold, aff[0].explorationProbability,
+                                              aff[0].maxTTFTPenaltyMs, aff[0].ttft_column) if aff else None)
 
 
 def NewSchedulerProfile():
@@ -276,7 +298,7 @@ class Scheduler:
     tests do (disagg/scheduler_test.go:264-268); otherwise pass match info via `produce`."""
 
     def __init__(self, profileHandler, profiles: dict, *, max_endpoints: int = 64, block_size_tokens: int = 16,
-                 max_prefix_blocks: int = 256, ext_columns: int = 0, device: int = 0):
+                 max_prefix_blocks: int = 256, ext_columns: int = 0, device: int = 0, tie_seed: int = 0):
         self.handler = profileHandler
         self.profiles = profiles
         if isinstance(profileHandler, DisaggProfileHandler):
@@ -293,9 +315,12 @@ class Scheduler:
             (self.primary_name, prof), = profiles.items()
             primary, prefill, nct, always = prof.spec(), None, 0, False
             self.prefill_name = None
+        ks = {p.picker.maxNumOfEndpoints for p in profiles.values()}
+        assert len(ks) == 1, "the engine has one maxNumOfEndpoints for all profiles"
+        self.pick_k = ks.pop()
         self.engine = Engine(max_endpoints, primary, prefill, device=device, block_size_tokens=block_size_tokens,
                              max_prefix_blocks=max_prefix_blocks, non_cached_tokens=nct, always_disagg=always,
-                             n_ext_cols=ext_columns)
+                             n_ext_cols=ext_columns, tie_seed=tie_seed, pick_k=self.pick_k)
         self.block_size_tokens = block_size_tokens
 
     def _push_pool(self, endpoints, ext=None):
@@ -323,17 +348,22 @@ class Scheduler:
                 total[:] = info.TotalBlocks()
                 bst = info.BlockSizeTokens()
         in_len = np.array([len(r.Prompt) for r in reqs], dtype=np.int64)
-        dec, det = self.engine.schedule_with_match(match, total, in_len, bst)
-        out = [self._result(dec[i], det[i], eps) for i in range(len(reqs))]
+        if self.pick_k > 1:
+            dec, det, lists = self.engine.schedule_with_match(match, total, in_len, bst, topk=True)
+        else:
+            dec, det = self.engine.schedule_with_match(match, total, in_len, bst)
+            lists = {"primary": dec["pick"].reshape(-1, 1), "prefill": dec["prefill_pick"].reshape(-1, 1)}
+        out = [self._result(dec[i], det[i], eps, lists["primary"][i], lists["prefill"][i]) for i in range(len(reqs))]
         return out[0] if single else out
 
-    def _result(self, d, dd, eps):
+    def _result(self, d, dd, eps, primary, prefill):
         if d["status"] != 0:
             raise SchedulingError("failed to find available decode workers" if self.prefill_name
                                   else "no endpoints available for the given request")
-        res = {self.primary_name: ProfileRunResult([eps[int(d["pick"])]], float(d["score"]), int(d["tie_count"]))}
+        targets = lambda row: [eps[int(s)] for s in row if int(s) != capi.EPP_NO_ENDPOINT]     # picker order, k at most
+        res = {self.primary_name: ProfileRunResult(targets(primary), float(d["score"]), int(d["tie_count"]))}
         if self.prefill_name and d["prefill_pick"] != capi.EPP_NO_ENDPOINT:
-            res[self.prefill_name] = ProfileRunResult([eps[int(d["prefill_pick"])]], float(dd["prefill_score"]),
+            res[self.prefill_name] = ProfileRunResult(targets(prefill), float(dd["prefill_score"]),
                                                       int(dd["prefill_tie_count"]))
         return SchedulingResult(res, self.primary_name)
 

@@ -275,3 +275,27 @@ def test_affinity_filter_vs_oracle(epp, orc, tie_seed):
             picks, scores, ties, _ = orc.profile_run_topk(oprim, pool, match[r], B, 1, tie_seed=tie_seed, tie_key=4 * (base + r))
             assert picks == [int(dec3["pick"][r])] and ties == int(dec3["tie_count"][r])
             assert np.float64(scores[0]).view(np.uint64) == dec3["score"][r].view(np.uint64)
+
+
+def test_mirror_scheduler_with_affinity_filter_and_two_targets(epp):
+    """Through the reference-interface mirror (plugins.py), written like filter/prefixcacheaffinity/plugin_test.go:
+    endpoints a / b hold 90 % / 85 % of the prompt, c 10 %; the filter narrows to {a, b}, the queue scorer then
+    normalises over those two only (b has the shorter queue), and the picker returns both in score order."""
+    P = epp.plugins
+    def make_endpoint(name, prefix_match, waiting):
+        ep = P.NewEndpoint(P.EndpointMetadata(name), P.Metrics(WaitingQueueSize=waiting))
+        ep.Put(P.PrefixCacheMatchInfoKey, P.NewPrefixCacheMatchInfo(prefix_match, 100, 16))
+        return ep
+    endpoints = [make_endpoint("a", 90, 7), make_endpoint("b", 85, 3), make_endpoint("c", 10, 0)]
+    profile = P.NewSchedulerProfile().WithFilters(P.PrefixCacheAffinityFilter(0.80, 0.0, 5000.0)) \
+        .WithScorers(P.NewWeightedScorer(P.QueueScorer(), 1.0)).WithPicker(P.NewMaxScorePicker(2))
+    sched = P.Scheduler(P.SingleProfileHandler(), {"default": profile}, max_endpoints=3)
+    got = sched.Schedule(P.InferenceRequest(RequestID="r", TargetModel="m", Prompt=b"x" * 64), endpoints)
+    res = got.ProfileResults["default"]
+    assert [e.GetMetadata().Name for e in res.TargetEndpoints] == ["b", "a"]
+    assert res.Score == 1.0 and res.TieCount == 1
+    # without the filter c (empty queue) wins and b, a follow
+    plain = P.NewSchedulerProfile().WithScorers(P.NewWeightedScorer(P.QueueScorer(), 1.0)).WithPicker(P.NewMaxScorePicker(3))
+    got = P.Scheduler(P.SingleProfileHandler(), {"default": plain}, max_endpoints=3).Schedule(
+        P.InferenceRequest(RequestID="r", TargetModel="m", Prompt=b"x" * 64), endpoints)
+    assert [e.GetMetadata().Name for e in got.ProfileResults["default"].TargetEndpoints] == ["c", "b", "a"]
