@@ -45,10 +45,19 @@ type ScorerSpec struct {
 	Param2 float64
 }
 
-// ProfileSpec mirrors epp_profile_cfg: role filter -> scorers in order -> max-score picker.
+// AffinitySpec mirrors the prefix-cache-affinity-filter parameters (filter/prefixcacheaffinity/plugin.go:45-66).
+type AffinitySpec struct {
+	AffinityThreshold      float64
+	ExplorationProbability float64
+	MaxTTFTPenaltyMs       float64
+	TTFTColumn             int // ext column carrying LatencyPredictionInfo.TTFT; -1 = attribute absent
+}
+
+// ProfileSpec mirrors epp_profile_cfg: role filter -> [prefix-cache-affinity-filter] -> scorers in order -> max-score picker.
 type ProfileSpec struct {
-	Filter  int // C.EPP_FILTER_*
-	Scorers []ScorerSpec
+	Filter   int // C.EPP_FILTER_*
+	Scorers  []ScorerSpec
+	Affinity *AffinitySpec
 }
 
 // Config mirrors epp_config (EndpointPickerConfig fields that define this path).
@@ -61,6 +70,7 @@ type Config struct {
 	NonCachedTokens      int64
 	AlwaysDisagg         bool
 	TieSeed              uint64 // 0 = lowest slot of the arg-max set (tests); production: any non-zero value
+	PickK                int    // max-score-picker maxNumOfEndpoints; <= 1: one target endpoint per profile
 	Primary              ProfileSpec
 	Prefill              *ProfileSpec // non-nil: disagg handler (decode -> decider -> prefill)
 	Encode               *ProfileSpec // non-nil (with Prefill): encode stage for multimodal requests
@@ -98,6 +108,13 @@ func fillProfile(dst *C.epp_profile_cfg, p ProfileSpec) error {
 		dst.scorers[i].param = C.double(s.Param)
 		dst.scorers[i].param2 = C.double(s.Param2)
 	}
+	dst.ttft_column = -1
+	if a := p.Affinity; a != nil {
+		dst.affinity_threshold = C.double(a.AffinityThreshold)
+		dst.exploration_probability = C.double(a.ExplorationProbability)
+		dst.max_ttft_penalty_ms = C.double(a.MaxTTFTPenaltyMs)
+		dst.ttft_column = C.int32_t(a.TTFTColumn)
+	}
 	return nil
 }
 
@@ -122,6 +139,9 @@ func New(cfg Config) (*Engine, error) {
 		c.always_disagg = 1
 	}
 	c.tie_seed = C.uint64_t(cfg.TieSeed)
+	if cfg.PickK > 1 {
+		c.pick_k = C.int32_t(cfg.PickK)
+	}
 	if err := fillProfile(&c.primary, cfg.Primary); err != nil {
 		return nil, err
 	}
@@ -290,6 +310,8 @@ type Decision struct {
 	TieCount                        uint32
 	MatchBlocks, TotalBlocks        int32
 	PrefillRan, EncodeRan           bool
+	// PickK > 1: the first-k slots of each profile in picker order (maxscore/picker.go:104-115); nil otherwise
+	Primary, Prefill, Encode []uint32
 }
 
 const NoEndpoint = uint32(C.EPP_NO_ENDPOINT)
@@ -313,11 +335,22 @@ func (e *Engine) schedule(model uint32, prompt []byte, multimodal bool) (Decisio
 	}
 	var d C.epp_decision
 	var dd C.epp_decision_detail
-	if rc := C.epp_wait(e.b, ticket, &d, &dd); rc != C.EPP_OK {
+	var lists [3][]uint32
+	if k := e.cfg.PickK; k > 1 {
+		buf := make([]C.uint32_t, 3*k) // plain integers: a Go allocation without Go pointers may be passed to C
+		if rc := C.epp_wait_topk(e.b, ticket, &d, &dd, &buf[0], &buf[k], &buf[2*k]); rc != C.EPP_OK {
+			return Decision{}, errors.New(C.GoString(C.epp_batcher_last_error()))
+		}
+		for q := 0; q < 3; q++ {
+			for j := 0; j < k && uint32(buf[q*k+j]) != NoEndpoint; j++ {
+				lists[q] = append(lists[q], uint32(buf[q*k+j]))
+			}
+		}
+	} else if rc := C.epp_wait(e.b, ticket, &d, &dd); rc != C.EPP_OK {
 		return Decision{}, errors.New(C.GoString(C.epp_batcher_last_error()))
 	}
 	return Decision{Status: int32(d.status), Pick: uint32(d.pick), PrefillPick: uint32(d.prefill_pick),
 		EncodePick: uint32(dd.encode_pick), Score: float64(d.score), TieCount: uint32(d.tie_count),
 		MatchBlocks: int32(d.match_blocks), TotalBlocks: int32(d.total_blocks), PrefillRan: dd.prefill_ran != 0,
-		EncodeRan: dd.encode_ran != 0}, nil
+		EncodeRan: dd.encode_ran != 0, Primary: lists[0], Prefill: lists[1], Encode: lists[2]}, nil
 }

@@ -77,20 +77,32 @@ func (s *Scheduler) Schedule(ctx context.Context, request *scheduling.InferenceR
 	}
 	res := &scheduling.SchedulingResult{PrimaryProfileName: s.Names.Primary,
 		ProfileResults: map[string]*scheduling.ProfileRunResult{}}
-	put := func(profile string, slot uint32) {
-		if profile == "" || slot == NoEndpoint {
+	// TargetEndpoints: the pick, or with maxNumOfEndpoints > 1 the first-k list in picker order (the pick first)
+	put := func(profile string, pick uint32, list []uint32) {
+		if profile == "" || pick == NoEndpoint {
 			return
 		}
+		if list == nil {
+			list = []uint32{pick}
+		}
+		var targets []scheduling.Endpoint
 		s.Engine.mu.RLock()
-		name := s.Engine.nameOf[slot]
+		for _, slot := range list {
+			if ep, ok := byName[s.Engine.nameOf[slot]]; ok {
+				targets = append(targets, ep)
+			} else if slot == pick {
+				targets = nil // the pick left the pool since the snapshot
+				break
+			}
+		}
 		s.Engine.mu.RUnlock()
-		if ep, ok := byName[name]; ok {
-			res.ProfileResults[profile] = &scheduling.ProfileRunResult{TargetEndpoints: []scheduling.Endpoint{ep}}
+		if len(targets) > 0 {
+			res.ProfileResults[profile] = &scheduling.ProfileRunResult{TargetEndpoints: targets}
 		}
 	}
-	put(s.Names.Primary, d.Pick)
-	put(s.Names.Prefill, d.PrefillPick)
-	put(s.Names.Encode, d.EncodePick)
+	put(s.Names.Primary, d.Pick, d.Primary)
+	put(s.Names.Prefill, d.PrefillPick, d.Prefill)
+	put(s.Names.Encode, d.EncodePick, d.Encode)
 	if _, ok := res.ProfileResults[s.Names.Primary]; !ok {
 		return nil, errors.New("failed to find available decode workers") // the pick left the pool since the snapshot
 	}

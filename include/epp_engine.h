@@ -434,6 +434,11 @@ EPP_API int32_t epp_batcher_destroy(epp_batcher *b);     /* flushes what is pend
 EPP_API int32_t epp_submit(epp_batcher *b, uint32_t model_id, const void *prompt, uint64_t prompt_len,
                            uint32_t multimodal, uint64_t *out_ticket);
 EPP_API int32_t epp_wait(epp_batcher *b, uint64_t ticket, epp_decision *out, epp_decision_detail *out_detail);
+/* The same on an engine created with pick_k > 1, plus the request's first-k lists (ProfileRunResult.TargetEndpoints of
+ * each profile, see epp_topk_out): primary / prefill / encode receive pick_k slot ids each (EPP_NO_ENDPOINT padded); any
+ * of them may be NULL. */
+EPP_API int32_t epp_wait_topk(epp_batcher *b, uint64_t ticket, epp_decision *out, epp_decision_detail *out_detail,
+                              uint32_t *primary, uint32_t *prefill, uint32_t *encode);
 EPP_API int32_t epp_batcher_stats(epp_batcher *b, epp_batcher_stats_t *out);
 EPP_API const char *epp_batcher_last_error(void);
 

@@ -144,6 +144,8 @@ SIGNATURES = {
     "epp_batcher_destroy": (C.c_int32, [C.c_void_p]),
     "epp_submit": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]),
     "epp_wait": (C.c_int32, [C.c_void_p, C.c_uint64, C.POINTER(Decision), C.POINTER(DecisionDetail)]),
+    "epp_wait_topk": (C.c_int32, [C.c_void_p, C.c_uint64, C.POINTER(Decision), C.POINTER(DecisionDetail), C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
     "epp_batcher_stats": (C.c_int32, [C.c_void_p, C.POINTER(BatcherStats)]),
     "epp_batcher_last_error": (C.c_char_p, []),
 }

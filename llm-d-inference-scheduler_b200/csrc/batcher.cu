@@ -35,6 +35,7 @@ struct Staging {
     uint8_t *multimodal = nullptr;
     epp_decision *dec = nullptr;
     epp_decision_detail *det = nullptr;
+    uint32_t *topk[3] = {nullptr, nullptr, nullptr};   // [max_batch][pick_k] primary / prefill / encode lists (pick_k > 1)
     int32_t n = 0;
 };
 // Results of one flushed batch, kept until every ticket has been waited for or kResults later batches were flushed.
@@ -44,6 +45,7 @@ struct Result {
     int32_t remaining = 0;                     // tickets not yet waited for
     std::vector<epp_decision> dec;
     std::vector<epp_decision_detail> det;
+    std::vector<uint32_t> topk;                // [3][n][pick_k] when the engine's pick_k > 1
 };
 }  // namespace
 
@@ -51,6 +53,7 @@ struct epp_batcher {
     epp_engine *eng = nullptr;
     epp_batcher_cfg cfg{};
     uint64_t row_cap = 0;                      // bytes of a prompt that hashPrompt can read (hashing.go:63-66)
+    int32_t pick_k = 0;                        // the engine's maxNumOfEndpoints (> 1: flushes also fetch the first-k lists)
     Staging buf[kBufs];
     std::vector<Result> results;
     bool in_flight[kBufs] = {false, false};    // the flusher is running epp_schedule on the buffer
@@ -105,7 +108,17 @@ static void flusher_main(epp_batcher *b) {
         batch.model_ids = st.model_ids;
         batch.multimodal = st.multimodal;
         batch.flags = EPP_BATCH_LENGTHS_EXCEED_ROWS;
-        int32_t rc = epp_schedule(b->eng, &batch, st.dec, st.det, b->cfg.index_picks ? 1 : 0);
+        int32_t rc;
+        if (b->pick_k > 1) {
+            epp_topk_out tk;
+            memset(&tk, 0, sizeof tk);
+            tk.struct_size = sizeof tk;
+            tk.k = b->pick_k;
+            tk.primary = st.topk[0]; tk.prefill = st.topk[1]; tk.encode = st.topk[2];
+            rc = epp_schedule_topk(b->eng, &batch, st.dec, st.det, b->cfg.index_picks ? 1 : 0, &tk);
+        } else {
+            rc = epp_schedule(b->eng, &batch, st.dec, st.det, b->cfg.index_picks ? 1 : 0);
+        }
         std::string err;
         if (rc != EPP_OK) err = epp_last_error();
         if (rc == EPP_OK && b->cfg.index_picks) {
@@ -119,6 +132,9 @@ static void flusher_main(epp_batcher *b) {
         res.remaining = n;
         res.dec.assign(st.dec, st.dec + n);
         res.det.assign(st.det, st.det + n);
+        res.topk.clear();
+        if (b->pick_k > 1)
+            for (int q = 0; q < 3; q++) res.topk.insert(res.topk.end(), st.topk[q], st.topk[q] + (size_t)n * (size_t)b->pick_k);
         b->in_flight[mine] = false;
         if (rc != EPP_OK) b->last_error = err;
         b->seq_done = seq + 1;
@@ -151,6 +167,7 @@ extern "C" int32_t epp_batcher_create(epp_engine *h, const epp_batcher_cfg *cfg,
     // every byte hashPrompt can read: maxPrefixBlocks blocks of blockSizeTokens * 4 bytes (hashing.go:49, 63-66);
     // rows start on 32-byte boundaries (selects the aligned hash kernels)
     b->row_cap = ((uint64_t)ec.max_prefix_blocks * (uint64_t)ec.block_size_tokens * 4 + 31) & ~31ull;
+    b->pick_k = ec.pick_k;
     b->results.resize(kResults);
     const size_t mb = (size_t)cfg->max_batch;
     for (int i = 0; i < kBufs; i++) {
@@ -170,6 +187,16 @@ extern "C" int32_t epp_batcher_create(epp_engine *h, const epp_batcher_cfg *cfg,
             *dst[k] = p;
         }
         for (size_t r = 0; r <= mb; r++) st.offsets[r] = (uint64_t)r * b->row_cap;
+        if (b->pick_k > 1)
+            for (int q = 0; q < 3; q++) {
+                rc = epp_host_alloc(sizeof(uint32_t) * mb * (size_t)b->pick_k, &p);
+                if (rc != EPP_OK) {
+                    g_batcher_error = epp_last_error();
+                    epp_batcher_destroy(b);
+                    return rc;
+                }
+                st.topk[q] = (uint32_t *)p;
+            }
     }
     b->flusher = std::thread(flusher_main, b);
     *out = b;
@@ -188,7 +215,7 @@ extern "C" int32_t epp_batcher_destroy(epp_batcher *b) {
     b->cv_done.notify_all();
     for (int i = 0; i < kBufs; i++) {
         Staging &st = b->buf[i];
-        void *ps[7] = {st.data, st.offsets, st.lengths, st.model_ids, st.multimodal, st.dec, st.det};
+        void *ps[10] = {st.data, st.offsets, st.lengths, st.model_ids, st.multimodal, st.dec, st.det, st.topk[0], st.topk[1], st.topk[2]};
         for (void *p : ps) if (p) epp_host_free(p);
     }
     delete b;
@@ -219,7 +246,13 @@ extern "C" int32_t epp_submit(epp_batcher *b, uint32_t model_id, const void *pro
 }
 
 extern "C" int32_t epp_wait(epp_batcher *b, uint64_t ticket, epp_decision *out, epp_decision_detail *out_detail) {
+    return epp_wait_topk(b, ticket, out, out_detail, nullptr, nullptr, nullptr);
+}
+
+extern "C" int32_t epp_wait_topk(epp_batcher *b, uint64_t ticket, epp_decision *out, epp_decision_detail *out_detail,
+                                 uint32_t *primary, uint32_t *prefill, uint32_t *encode) {
     if (!b || !out) return bfail(EPP_ERR_INVALID, "NULL argument");
+    if ((primary || prefill || encode) && b->pick_k <= 1) return bfail(EPP_ERR_STATE, "the engine was created with pick_k <= 1: there are no lists");
     const uint64_t seq = ticket >> 20;
     const uint32_t idx = (uint32_t)(ticket & 0xFFFFFu);
     std::unique_lock<std::mutex> lk(b->mu);
@@ -234,11 +267,16 @@ extern "C" int32_t epp_wait(epp_batcher *b, uint64_t ticket, epp_decision *out, 
     } else {
         *out = res.dec[idx];
         if (out_detail) *out_detail = res.det[idx];
+        uint32_t *dst[3] = {primary, prefill, encode};
+        const size_t k = (size_t)b->pick_k, n = res.dec.size();
+        for (int q = 0; q < 3; q++)
+            if (dst[q]) memcpy(dst[q], res.topk.data() + ((size_t)q * n + idx) * k, sizeof(uint32_t) * k);
     }
     if (--res.remaining == 0) {                    // every ticket served: release the memory early
         res.seq = ~0ull;
         std::vector<epp_decision>().swap(res.dec);
         std::vector<epp_decision_detail>().swap(res.det);
+        std::vector<uint32_t>().swap(res.topk);
     }
     return rc;
 }

@@ -444,6 +444,18 @@ class Batcher:
         det = np.frombuffer(bytes(dd), dtype=DETAIL_DTYPE)[0]
         return dec, det
 
+    def wait_topk(self, ticket: int):
+        """-> (decision, detail, {"primary": [...], "prefill": [...], "encode": [...]}): the first-k lists of the
+        request's profiles (engines created with pick_k > 1), EPP_NO_ENDPOINT entries dropped."""
+        d = capi.Decision()
+        dd = capi.DecisionDetail()
+        k = int(self._engine.cfg.pick_k)
+        rows = {name: np.zeros(max(k, 1), dtype=np.uint32) for name in ("primary", "prefill", "encode")}
+        self._check(self._lib.epp_wait_topk(self._b, ticket, C.byref(d), C.byref(dd), _ptr(rows["primary"]),
+                                            _ptr(rows["prefill"]), _ptr(rows["encode"])))
+        lists = {n: [int(x) for x in r if int(x) != capi.EPP_NO_ENDPOINT] for n, r in rows.items()}
+        return np.frombuffer(bytes(d), dtype=DECISION_DTYPE)[0], np.frombuffer(bytes(dd), dtype=DETAIL_DTYPE)[0], lists
+
     def schedule(self, prompt, model_id: int = 0, multimodal: bool = False):
         """Scheduler.Schedule for ONE request (what a goroutine of the reference calls): submit + wait."""
         return self.wait(self.submit(prompt, model_id, multimodal))

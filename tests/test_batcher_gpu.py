@@ -117,3 +117,43 @@ def test_batch_of_one_with_prerequest_is_the_reference_order(epp, orc, tg):
                     ix.add(orc.hash_prompt(tokens[r].tobytes(), tg.MODEL, w.block_size_tokens, w.max_prefix_blocks), int(od["pick"][0]))
         eng.index_commit()
         assert eng.stats()["index_pairs"] == len(ix.export()[0])
+
+
+def test_batcher_returns_the_first_k_lists(epp, orc, tg):
+    """pick_k = 3 through epp_submit / epp_wait_topk from 16 threads: the lists are the oracle's first-k of the request's
+    profiles (deterministic tie mode, so the answer does not depend on how the flusher grouped the requests)."""
+    import helpers
+    K = 3
+    w = tg.baseline_configs()["config4"].scaled(E=96, R=16 * 20, T=256, name="config4")
+    w.non_cached_tokens = 32
+    trace = tg.Trace(w)
+    tokens, _, _ = trace.requests()
+    pool, ix, primary, prefill, _ = helpers.setup_oracle(orc, w, trace)
+    odec, ototal, olists = helpers.oracle_decisions(orc, w, pool, ix, primary, prefill, tokens, topk=K)
+    with helpers.make_engine(w, pick_k=K) as eng:
+        helpers.setup_engine(eng, w, trace)
+        got = np.zeros(w.R, dtype=epp.DECISION_DTYPE)
+        gdet = np.zeros(w.R, dtype=epp.DETAIL_DTYPE)
+        glists = [None] * w.R
+        errors = []
+        with epp.Batcher(eng, max_batch=24, max_delay_us=200) as bt:
+            def worker(t):
+                try:
+                    for r in range(t, w.R, 16):
+                        got[r], gdet[r], glists[r] = bt.wait_topk(bt.submit(tokens[r]))
+                except Exception as e:      # noqa: BLE001
+                    errors.append(e)
+            th = [threading.Thread(target=worker, args=(t,)) for t in range(16)]
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
+        assert not errors, errors[:1]
+        helpers.assert_decisions_equal(got, gdet, odec, ototal, where="batcher top-k")
+        for r in range(w.R):
+            if odec["status"][r] != 0:
+                continue
+            for name in ("primary", "prefill"):
+                assert glists[r][name] == [int(x) for x in olists[name][r] if x >= 0], (r, name)
+            assert glists[r]["encode"] == []
+        assert any(len(l["prefill"]) == K for l in glists if l)
