@@ -19,6 +19,7 @@ EngineError = _pkg.EngineError
 ProfileSpec = _pkg.ProfileSpec
 ScorerSpec = _pkg.ScorerSpec
 AffinityFilterSpec = _pkg.AffinityFilterSpec
+PinnedBuffer = _pkg.PinnedBuffer
 DECISION_DTYPE = _pkg.DECISION_DTYPE
 DETAIL_DTYPE = _pkg.DETAIL_DTYPE
 SHARD_BEST_DTYPE = _pkg.SHARD_BEST_DTYPE

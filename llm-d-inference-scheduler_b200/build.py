@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libepp_engine.so")
-SOURCES = ["engine.cu", "batcher.cu", "hash_kernels.cu", "hash_fused.cu", "hash_staged.cu", "index_kernels.cu", "index_store.cu", "pick_kernels.cu", "match_sparse.cu", "shard_p2p.cu"]
+SOURCES = ["engine.cu", "batcher.cu", "hash_kernels.cu", "hash_fused.cu", "hash_staged.cu", "index_kernels.cu", "index_store.cu", "pick_kernels.cu", "match_sparse.cu", "cycle_small.cu", "shard_p2p.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

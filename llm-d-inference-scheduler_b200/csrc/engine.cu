@@ -127,6 +127,20 @@ struct epp_engine {
     int pick_grid = 0;
     bool pick_global = false;
     size_t pick_smem = 0;
+    // small host batches: one zero-copy kernel, no copy engine, no stream synchronisation (cycle_small.cu)
+    int small_max = 1024;           // EPP_SMALL_BATCH=n: largest batch that takes the path (0 = off)
+    int small_zc_max = 8;           // EPP_SMALL_ZEROCOPY=n: largest batch whose prompts the kernel reads over PCIe itself
+    int64_t small_cap = 0;          // requests the pinned staging below is sized for
+    uint8_t *small_host = nullptr;  // one pinned + mapped allocation: 2 x {offsets, lengths, model_ids, multimodal}, dec, det, flags
+    uint64_t *small_offsets[2] = {}, *small_lengths[2] = {};
+    uint32_t *small_models[2] = {};
+    uint8_t *small_mm[2] = {};
+    epp_decision *small_dec = nullptr;
+    epp_decision_detail *small_det = nullptr;
+    uint32_t *small_flags = nullptr;
+    uint32_t small_epoch = 0;
+    DevBuf small_overflow_n;        // stays zero between batches (reset by the overflow pass)
+    bool small_stats_pending = false;   // ev[0] / ev[1] bracket the last small batch; read lazily by epp_get_stats
     bool general = false;           // a profile configures the prefix-cache-affinity-filter or pick_k > 1: every batch takes
                                     // the dense-counter kernel with the full-scan evaluation of pick_general.cuh
     const epp_topk_out *cur_topk = nullptr;   // top-k destination of the call in progress (under mu)
@@ -296,6 +310,10 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
     { const char *v1 = getenv("EPP_INDEX_LOAD"); e->index_load = v1 ? std::max(2, atoi(v1)) : 0; }
     { const char *v1 = getenv("EPP_DEV_CHUNKS"); e->dev_chunks = v1 ? std::max(1, atoi(v1)) : 2; }
     { const char *v1 = getenv("EPP_HASH_STAGED"); e->staged = v1 ? atoi(v1) : 0; }
+    { const char *v1 = getenv("EPP_SMALL_BATCH"); e->small_max = v1 ? std::max(0, atoi(v1)) : 1024; }
+    { const char *v1 = getenv("EPP_SMALL_ZEROCOPY"); e->small_zc_max = v1 ? std::max(0, atoi(v1)) : 8; }
+    CUDA_TRY(e->small_overflow_n.reserve(sizeof(int32_t) * 4, &e->dev_bytes));
+    CUDA_TRY(cudaMemset(e->small_overflow_n.p, 0, sizeof(int32_t) * 4));
     for (int i = 0; i < 2; i++) CUDA_TRY(e->slot[i].overflow_n.reserve(sizeof(int32_t) * 4, &e->dev_bytes));
 
     // match/pick launch geometry: counters in shared memory when they fit, else zeroed global scratch
@@ -328,6 +346,7 @@ extern "C" int32_t epp_engine_destroy(epp_engine *h) {
     for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->user_ev) if (ev) cudaEventDestroy(ev);
     if (h->wc_host) cudaFreeHost(h->wc_host);
+    if (h->small_host) cudaFreeHost(h->small_host);
     for (int g = 0; g < (int)h->p2p_peer.size(); g++)
         if (h->p2p_ipc && g != h->p2p_rank && h->p2p_peer[g]) cudaIpcCloseMemHandle(h->p2p_peer[g]);
     if (h->p2p_buf) cudaFree(h->p2p_buf);
@@ -1027,6 +1046,146 @@ static int32_t finish_async(epp_engine *h) {
     return EPP_OK;
 }
 
+// ---- small host batches (cycle_small.cu) -------------------------------------------------------------------------
+static int32_t small_reserve(epp_engine *h, int64_t R) {
+    if (R <= h->small_cap) return EPP_OK;
+    const int64_t cap = std::max<int64_t>(64, std::min<int64_t>(h->small_max, R * 2));
+    if (h->small_host) { CUDA_TRY(cudaStreamSynchronize(h->slot[0].stream)); CUDA_TRY(cudaFreeHost(h->small_host)); h->small_host = nullptr; h->small_cap = 0; }
+    const size_t n = (size_t)cap;
+    const size_t per_set = sizeof(uint64_t) * (n + 1) + sizeof(uint64_t) * n + sizeof(uint32_t) * n + ((n + 7) & ~(size_t)7);
+    const size_t total = 2 * per_set + sizeof(epp_decision) * n + sizeof(epp_decision_detail) * n + sizeof(uint32_t) * n + 64;
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&h->small_host), total, cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(h->small_host, 0, total);
+    uint8_t *q = h->small_host;
+    for (int i = 0; i < 2; i++) {
+        h->small_offsets[i] = reinterpret_cast<uint64_t *>(q); q += sizeof(uint64_t) * (n + 1);
+        h->small_lengths[i] = reinterpret_cast<uint64_t *>(q); q += sizeof(uint64_t) * n;
+        h->small_models[i] = reinterpret_cast<uint32_t *>(q); q += sizeof(uint32_t) * n;
+        h->small_mm[i] = q; q += (n + 7) & ~(size_t)7;
+    }
+    q = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(q) + 15) & ~(uintptr_t)15);
+    h->small_dec = reinterpret_cast<epp_decision *>(q); q += sizeof(epp_decision) * n;
+    h->small_det = reinterpret_cast<epp_decision_detail *>(q); q += sizeof(epp_decision_detail) * n;
+    h->small_flags = reinterpret_cast<uint32_t *>(q);
+    h->small_cap = cap;
+    return EPP_OK;
+}
+
+// Device view of a pointer into pinned host memory (cudaHostAlloc / cudaHostRegister), or nullptr.
+static const uint8_t *device_view_of_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return nullptr;
+    return reinterpret_cast<const uint8_t *>(a.devicePointer);
+}
+
+// Is this host batch one for the single-launch path?  Returns 0 = no; 1 = the kernel reads the prompts from the
+// caller's pinned memory over PCIe (*data_dev = their device view); 2 = one DMA copy into HBM first (SM-issued PCIe
+// reads top out near 20 GB/s, the copy engine reaches 55: beyond a handful of prompts the copy wins).
+static int small_batch_mode(epp_engine *h, const BatchView &v, const uint8_t **data_dev, int *align) {
+    if (v.device || h->small_max <= 0 || v.R > h->small_max || h->general) return 0;
+    if (h->shard_begin != 0 || h->shard_end != 0xFFFFFFFFu) return 0;
+    const int64_t bs = (int64_t)h->cfg.block_size_tokens * 4;
+    if ((bs & 31) || (size_t)h->cfg.max_prefix_blocks > cycle_small_max_blocks()) return 0;
+    const uint64_t layout_bits = v.offsets ? v.offsets_or_bits : v.uniform_len;
+    if (v.R <= h->small_zc_max || !v.total_bytes) {
+        *data_dev = v.total_bytes ? device_view_of_pinned(v.data) : nullptr;
+        if (*data_dev || !v.total_bytes) {
+            const uint64_t bits = reinterpret_cast<uintptr_t>(*data_dev) | layout_bits;
+            *align = (bits & 31) == 0 ? 32 : ((bits & 15) == 0 ? 16 : 0);
+            if (*align >= 16) return 1;
+        }
+    }
+    // the staged copy keeps the caller's layout modulo 32 (see run_batch), so only the layout decides the alignment
+    *align = (layout_bits & 31) == 0 ? 32 : ((layout_bits & 15) == 0 ? 16 : 0);
+    return *align >= 16 ? 2 : 0;
+}
+
+static int32_t run_small(epp_engine *h, const BatchView &v, int mode, const uint8_t *data_dev, int align,
+                         epp_decision *out_dec, epp_decision_detail *out_detail) {
+    const int64_t R = v.R;
+    cudaStream_t s0 = h->slot[0].stream;
+    EPP_TRY(reserve_batch(h, R));
+    EPP_TRY(small_reserve(h, R));
+    if (mode == 2) {
+        const uint64_t start = v.offsets ? v.offsets[0] : 0;
+        CUDA_TRY(h->slot[0].data.reserve(v.total_bytes + 64, &h->dev_bytes));
+        uint8_t *stage = h->slot[0].data.as<uint8_t>() + (start & 31);
+        CUDA_TRY(cudaMemcpyAsync(stage, v.data + start, v.total_bytes, cudaMemcpyHostToDevice, s0));
+        data_dev = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(stage) - (uintptr_t)start);   // + offsets[r]
+    }
+    uint32_t epoch = h->small_epoch + 1;
+    if (epoch > 0x7fffffffu) epoch = 1;
+    h->small_epoch = epoch;
+    const int set = (int)(epoch & 1);              // the kernel of the batch before may still be finishing its chains
+    if (v.offsets) memcpy(h->small_offsets[set], v.offsets, sizeof(uint64_t) * (size_t)(R + 1));
+    if (v.lengths) memcpy(h->small_lengths[set], v.lengths, sizeof(uint64_t) * (size_t)R);
+    if (v.model_ids) memcpy(h->small_models[set], v.model_ids, sizeof(uint32_t) * (size_t)R);
+    if (v.multimodal) memcpy(h->small_mm[set], v.multimodal, (size_t)R);
+    Work w;
+    w.r0 = 0;
+    w.r1 = R;
+    w.data_base = data_dev;
+    w.offsets_dev = v.offsets ? h->small_offsets[set] : nullptr;       // pinned + mapped: host address == device address (UVA)
+    w.lengths_dev = v.lengths ? h->small_lengths[set] : nullptr;
+    w.uniform_len = v.uniform_len;
+    w.model_ids_dev = v.model_ids ? h->small_models[set] : nullptr;
+    w.offsets_or_bits = v.offsets_or_bits;
+    w.hashes_out = h->hashes.as<uint64_t>();
+    w.nblocks_out = h->nblocks.as<int32_t>();
+    w.multimodal_dev = v.multimodal ? h->small_mm[set] : nullptr;
+    PickParams pp = pick_params(h, w, h->decisions.as<epp_decision>(), h->details.as<epp_decision_detail>(), nullptr);
+    pp.overflow_list = h->slot[0].overflow_list.as<int32_t>();
+    pp.overflow_n = h->small_overflow_n.as<int32_t>();
+    SmallOut so{h->small_dec, h->small_det, h->small_flags, epoch};
+    int launches = 0;
+    CUDA_TRY(cudaEventRecord(h->ev[0], s0));
+    CUDA_TRY(launch_cycle_small(hash_params(h, w), pp, so, align, s0, &launches));
+    CUDA_TRY(cudaEventRecord(h->ev[1], s0));
+
+    // wait for the flag word of every request (written after a system-scope fence behind its decision)
+    volatile uint32_t *flags = h->small_flags;
+    uint32_t overflowed = 0, spins = 0;
+    bool finished_once = false;
+    for (int64_t next = 0; next < R;) {
+        const uint32_t x = flags[next];
+        if ((x & 0x7fffffffu) == epoch) { overflowed |= x >> 31; next++; continue; }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((++spins & 0x3fff) == 0) {             // a faulted launch never raises its flags
+            const cudaError_t q = cudaStreamQuery(s0);
+            if (q == cudaSuccess) {
+                if (finished_once) return fail(EPP_ERR_CUDA, "small-batch kernel finished without publishing request %lld", (long long)next);
+                finished_once = true;
+            } else if (q != cudaErrorNotReady) {
+                return fail(EPP_ERR_CUDA, "small-batch kernel failed: %s", cudaGetErrorString(q));
+            }
+        }
+    }
+    if (overflowed) {
+        // > 48 endpoints hold a part of some prompt: those requests go through the dense-counter kernel, then the whole
+        // batch is read back the ordinary way
+        Slot &sl = h->slot[0];
+        PickParams po = pp;
+        po.req_list = sl.overflow_list.as<int32_t>();
+        po.req_list_n = h->small_overflow_n.as<int32_t>();
+        po.overflow_list = nullptr;
+        po.overflow_n = nullptr;
+        CUDA_TRY(launch_match_pick(po, h->pick_global ? sl.pick_scratch.as<uint32_t>() : nullptr, h->pick_grid, h->pick_smem, s0, &launches));
+        CUDA_TRY(cudaMemsetAsync(h->small_overflow_n.p, 0, sizeof(int32_t), s0));
+        CUDA_TRY(cudaMemcpyAsync(h->small_dec, h->decisions.p, sizeof(epp_decision) * (size_t)R, cudaMemcpyDeviceToHost, s0));
+        CUDA_TRY(cudaMemcpyAsync(h->small_det, h->details.p, sizeof(epp_decision_detail) * (size_t)R, cudaMemcpyDeviceToHost, s0));
+        CUDA_TRY(cudaStreamSynchronize(s0));
+    }
+    memcpy(out_dec, h->small_dec, sizeof(epp_decision) * (size_t)R);
+    if (out_detail) memcpy(out_detail, h->small_det, sizeof(epp_decision_detail) * (size_t)R);
+    h->small_stats_pending = true;
+    h->stats.last_hash_ms = h->stats.last_match_pick_ms = 0;
+    h->stats.last_kernel_launches = (uint64_t)launches;
+    return EPP_OK;
+}
+
 // Runs hashing (+ match/pick) for a batch.  Host batches are split into chunks whose H2D copy overlaps the
 // kernels of the previous chunk (two streams, two staging buffers); device batches run in one pass.
 static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t *out_hashes, int32_t *out_nblocks,
@@ -1121,6 +1280,14 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
         h->async_launches = launches;
         if (v.async && mode == Mode::Schedule) return EPP_OK;      // epp_synchronize() completes it
         return finish_async(h);
+    }
+
+    // ---- small host batch in pinned memory: one zero-copy launch, no copy engine, no stream synchronisation
+    if (mode == Mode::Schedule && !tk && out_dec) {
+        const uint8_t *data_dev = nullptr;
+        int align = 0;
+        const int sm = small_batch_mode(h, v, &data_dev, &align);
+        if (sm) return run_small(h, v, sm, data_dev, align, out_dec, out_detail);
     }
 
     // ---- host batch: upload the small per-request arrays once, then pipeline the prompt bytes
@@ -1279,7 +1446,7 @@ static int32_t schedule_impl(epp_engine *h, const epp_batch *batch, epp_decision
         CUDA_TRY(h->kept_dec.reserve(sizeof(epp_decision) * (size_t)v.R, &h->dev_bytes));
         const void *src = v.device ? (const void *)out : (const void *)h->decisions.p;
         CUDA_TRY(cudaMemcpyAsync(h->kept_dec.p, src, sizeof(epp_decision) * (size_t)v.R, cudaMemcpyDeviceToDevice, s0));
-        if (!v.async) CUDA_TRY(cudaStreamSynchronize(s0));
+        if (v.device && !v.async) CUDA_TRY(cudaStreamSynchronize(s0));     // `out` is the caller's again when we return
         h->kept_R = v.R;
     }
     return EPP_OK;
@@ -1468,6 +1635,15 @@ extern "C" int32_t epp_get_stats(epp_engine *h, epp_stats *out) {
     if (!h || !out) return fail(EPP_ERR_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lk(h->mu);
     if (h->async_pending) { EPP_TRY(set_device(h)); EPP_TRY(finish_async(h)); }
+    if (h->small_stats_pending) {
+        EPP_TRY(set_device(h));
+        float t = 0;
+        CUDA_TRY(cudaEventSynchronize(h->ev[1]));
+        cudaEventElapsedTime(&t, h->ev[0], h->ev[1]);
+        h->stats.last_kernels_ms = t;
+        for (int i = 0; i < 8; i++) h->stats.last_kernel_ms[i] = i == 0 ? t : 0.0;
+        h->small_stats_pending = false;
+    }
     h->stats.device_bytes = h->dev_bytes + h->store->device_bytes();
     *out = h->stats;
     return EPP_OK;

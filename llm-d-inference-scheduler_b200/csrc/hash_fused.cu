@@ -12,8 +12,8 @@
 //       m + len, one 8-byte round with h_{i-1}, avalanche), in place.
 //   Stages are handed over with named barriers (bar.arrive / bar.sync), 4-deep ring: full (digest -> chain), empty
 //   (chain -> digest).
+#include "hash_blocks.cuh"
 #include "kernels.h"
-#include "xxh64.cuh"
 
 namespace epp {
 
@@ -26,19 +26,6 @@ constexpr int kHashMinCtas = 4;
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-// One 32-byte XXH64 stripe -> four little-endian u64 lanes.  kAlign32: a single 256-bit load (LDG.E.256, exactly one
-// DRAM sector per instruction per lane); else two 128-bit loads.
-template <bool kAlign32>
-__device__ __forceinline__ void load_stripe(const uint8_t *p, uint64_t x[4]) {
-    if (kAlign32) {
-        asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(x[0]), "=l"(x[1]), "=l"(x[2]), "=l"(x[3]) : "l"(p));
-    } else {
-        uint4 a = __ldg(reinterpret_cast<const uint4 *>(p)), c = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
-        x[0] = ((uint64_t)a.y << 32) | a.x; x[1] = ((uint64_t)a.w << 32) | a.z;
-        x[2] = ((uint64_t)c.y << 32) | c.x; x[3] = ((uint64_t)c.w << 32) | c.z;
-    }
-}
 
 // Per-request lengths (hashing.go:58-66) for one tile; called by the first warp.
 __device__ __forceinline__ void tile_lengths(const HashParams &p, int64_t r0, int t, uint64_t *s_off, int64_t *s_eff,
@@ -74,30 +61,6 @@ __device__ __forceinline__ void tile_lengths(const HashParams &p, int64_t r0, in
     if (t == 0) *s_maxfull = mx;
 }
 
-// Stripe rounds + merge of one full block (part A of xxh64.cuh).
-template <bool kAlign32>
-__device__ __forceinline__ uint64_t block_digest(const uint8_t *src, int n_stripes) {
-    uint64_t v[4];
-    xxh_init(v);
-    if (n_stripes == 2) {   // the default 64-byte block: both stripes in flight at once
-        uint64_t x0[4], x1[4];
-        load_stripe<kAlign32>(src, x0);
-        load_stripe<kAlign32>(src + 32, x1);
-#pragma unroll
-        for (int q = 0; q < 4; q++) v[q] = xxh_round(v[q], x0[q]);
-#pragma unroll
-        for (int q = 0; q < 4; q++) v[q] = xxh_round(v[q], x1[q]);
-    } else {
-        for (int st = 0; st < n_stripes; st++) {
-            uint64_t x[4];
-            load_stripe<kAlign32>(src + 32 * st, x);
-#pragma unroll
-            for (int q = 0; q < 4; q++) v[q] = xxh_round(v[q], x[q]);
-        }
-    }
-    return xxh_merge_all(v);
-}
-
 // Chain warp, one window: the serial part of the digest for 32 requests at once, in place, then the 8 hashes of
 // each request written as one 64-byte segment.
 template <int TR, int W = kWin>
@@ -114,8 +77,8 @@ __device__ __forceinline__ uint64_t chain_window(uint64_t (*sm)[W + 1], const in
         }
     }
     __syncwarp();
-#pragma unroll
     constexpr int kRows = 32 / W;                 // request rows written per warp instruction
+#pragma unroll
     for (int it = 0; it < TR / kRows; it++) {
         int rr = it * kRows + lane / W, jj = lane % W;
         int b = k * W + jj;

@@ -182,6 +182,18 @@ cudaError_t launch_match_pick(const PickParams &p, uint32_t *gscratch, int grid,
 // v2: the same decision per request with a per-warp sparse endpoint map (48 matched endpoints max; requests that
 // overflow are appended to p.overflow_list for the v1 kernel).  16 warps per CTA, high occupancy.
 cudaError_t launch_match_pick_sparse(const PickParams &p, int sm_count, cudaStream_t s, int *launches);
+// cycle_small.cu: a1-a14 of a small host batch in ONE launch, one CTA per request, prompts read from and decisions
+// written to PINNED HOST memory (zero-copy); flags[r] = epoch (| 0x80000000 when the request overflowed the sparse map and
+// was appended to pp.overflow_list instead of being decided) is written last, after a system-scope fence.
+struct SmallOut {
+    epp_decision *dec;             // [R] device view of pinned host memory
+    epp_decision_detail *det;      // [R]
+    uint32_t *flags;               // [R]
+    uint32_t epoch;                // 1 .. 0x7fffffff
+};
+size_t cycle_small_max_blocks();
+cudaError_t launch_cycle_small(const HashParams &hp, const PickParams &pp, const SmallOut &so, int align, cudaStream_t s,
+                               int *launches);
 // Decision logic on injected dense match info (plugin parity / KAT mode).
 struct DensePickParams {
     int64_t R;

@@ -64,7 +64,7 @@ __device__ __forceinline__ bool map_contains_any(const LaneMap &m, uint32_t e) {
 // The member of rank k (ascending slot order) of the arg-max set S = A u U (see eval_profile_lanes): one lower bound
 // per A lane in parallel and, failing that, one warp-uniform binary search over the equal-base group G.  Rare path
 // (ties only): kept out of line so that it costs the common path no registers.
-__device__ __noinline__ uint32_t select_tied(const ProfileDev &pf, const LaneMap &m, int lane, bool in_a, bool in_x_all,
+static __device__ __noinline__ uint32_t select_tied(const ProfileDev &pf, const LaneMap &m, int lane, bool in_a, bool in_x_all,
                                              bool have_u, uint32_t gpos, uint32_t ue, uint32_t k) {
     const bool in_x = in_x_all && have_u;
     const uint32_t mask_a = __ballot_sync(kFull, in_a), mask_x = __ballot_sync(kFull, in_x);
@@ -216,9 +216,17 @@ struct Work {
 // kTie: the reproducible random tie rule is compiled in (epp_config.tie_seed != 0); the deterministic lowest-slot
 // build carries none of its code or registers.
 // kStages: stages of the handler compiled in (score.cuh: decide_stages).
-template <bool kCg, bool kSharded, bool kTie, int kStages>
-__device__ __forceinline__ void match_request(const PickParams &p, const int64_t r, const int lane, const bool counting,
-                                              Work &wk) {
+// Follow: the request's hashes are still being produced by another warp of the CTA (cycle_small.cu): wait(n) returns
+// once hashes [0, n) can be read with hash(i) (shared memory).  NoFollow: they are all in the row p.hashes.
+struct NoFollow {
+    static constexpr bool kOn = false;
+    __device__ __forceinline__ void wait(int32_t) const {}
+    __device__ __forceinline__ uint64_t hash(int32_t) const { return 0; }
+};
+// Returns false when the request was handed to the dense-counter kernel (p.overflow_list) instead of being decided.
+template <bool kCg, bool kSharded, bool kTie, int kStages, typename Follow = NoFollow>
+__device__ __forceinline__ bool match_request(const PickParams &p, const int64_t r, const int lane, const bool counting,
+                                              Work &wk, const Follow fw = Follow()) {
     const uint32_t shard_lo = p.index.ep_begin, shard_hi = min(p.index.ep_end, (uint32_t)p.E);
     const IndexSlot *slots = p.index.slots;
     const uint32_t mask32 = (uint32_t)p.index.mask;
@@ -228,11 +236,17 @@ __device__ __forceinline__ void match_request(const PickParams &p, const int64_t
     m.e = kNoKey; m.c = 0; m.n = 0; m.overflow = false;
     // ---- a2/a3: probe in block order, 32 blocks per step; global stop at the first block nobody holds
     bool stopped = false;
-    uint64_t hnext = lane < total ? ld_row<kCg>(row + lane) : 0;
+    uint64_t hnext = (!Follow::kOn && lane < total) ? ld_row<kCg>(row + lane) : 0;
     for (int32_t cq = 0; cq < total && !stopped; cq += 32) {
         const int32_t i = cq + lane;
-        const uint64_t hcur = hnext;
-        if (i + 32 < total) hnext = ld_row<kCg>(row + i + 32);    // next chunk's hashes in flight during this one
+        uint64_t hcur;
+        if (Follow::kOn) {
+            fw.wait(min(total, cq + 32));
+            hcur = i < total ? fw.hash(i) : 0;
+        } else {
+            hcur = hnext;
+            if (i + 32 < total) hnext = ld_row<kCg>(row + i + 32);    // next chunk's hashes in flight during this one
+        }
         const bool valid = i < total;
         // endpoint-sharded mode: a block is missing only if NO rank holds it, and that is known up front
         uint32_t gmiss = 0;
@@ -306,7 +320,7 @@ __device__ __forceinline__ void match_request(const PickParams &p, const int64_t
     if (m.overflow) {
         // hand the request to the dense-counter kernel
         if (lane == 0 && p.overflow_list) p.overflow_list[atomicAdd(p.overflow_n, 1)] = (int32_t)r;
-        return;
+        return false;
     }
     // ---- a5-a14: the profiles of the handler
     epp_decision d;
@@ -325,6 +339,7 @@ __device__ __forceinline__ void match_request(const PickParams &p, const int64_t
             if (p.detail) p.detail[r] = dd;
         }
     }
+    return true;
 }
 
 }  // namespace sparse

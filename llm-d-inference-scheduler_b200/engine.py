@@ -483,6 +483,31 @@ class Batcher:
             pass
 
 
+class PinnedBuffer:
+    """Pinned host memory from epp_host_alloc as a numpy uint8 array (`.array`): what a shim stages prompts in.  Small
+    batches whose prompts live in such memory take the engine's single-launch zero-copy path (csrc/cycle_small.cu)."""
+
+    def __init__(self, nbytes: int):
+        self._lib = capi.load()
+        self._p = C.c_void_p()
+        rc = self._lib.epp_host_alloc(max(int(nbytes), 1), C.byref(self._p))
+        if rc != 0:
+            raise EngineError(rc, (self._lib.epp_last_error() or b"").decode())
+        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_uint8)), shape=(max(int(nbytes), 1),))
+
+    def close(self):
+        if getattr(self, "_p", None) and self._p.value:
+            self.array = None
+            self._lib.epp_host_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def decisions_from_torch(t) -> np.ndarray:
     """View a [R, 32] uint8 CUDA tensor of epp_decision records as a host structured array."""
     return t.cpu().numpy().view(DECISION_DTYPE).reshape(-1)

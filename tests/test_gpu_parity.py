@@ -723,6 +723,92 @@ def test_encode_stage_vs_oracle(epp, orc):
                 eng.schedule(d, offsets=offs, multimodal=mm, detail=False)      # the encode pick needs the detail record
 
 
+@pytest.mark.parametrize("tie_seed", [0, 99])
+def test_small_batch_zero_copy_path_vs_oracle(epp, orc, tie_seed, monkeypatch):
+    """Host batches of 1 .. 600 requests whose prompts live in pinned memory take the single-launch path of
+    csrc/cycle_small.cu (one CTA per request, prompts read over PCIe, decisions written to pinned memory, no copy
+    engine): ragged prompts incl. empty / shorter than a block / partial trailing block / longer than the cap, P/D and
+    encode stages, > 48 holders (dense-counter pass), both tie rules -- all equal to the oracle and to the ordinary
+    path (EPP_SMALL_BATCH=0)."""
+    import helpers
+    E, bst, B = 96, 8, 24                          # 32-byte blocks
+    rng = np.random.default_rng(71)
+    bb = 4 * bst
+    kv = rng.integers(0, 3, E) / 3.0
+    waiting = rng.integers(0, 3, E).astype(np.int32)
+    role = rng.choice([1, 2, 3, 5, 7, 0], size=E).astype(np.uint8)
+    prim, pref, enc = [(2, 1.0, 0), (1, 1.0, 0), (0, 2.0, 0)], [(2, 1.0, 0), (0, 1.0, 0)], [(1, 1.0, 0)]
+    spec = lambda f, sc: epp.ProfileSpec(f, [epp.ScorerSpec(k, w, p) for k, w, p in sc])
+    fam = [bytes(rng.integers(0, 256, bb * B, dtype=np.uint8)) for _ in range(5)]
+    pairs_h, pairs_e = [], []
+    for g, p in enumerate(fam):
+        h = orc.hash_prompt(p, b"m", bst, B)
+        for e in rng.choice(E, size=[2, 6, 12, 30, 70][g], replace=False):     # the last family overflows the sparse map
+            depth = int(rng.choice([len(h) // 2, len(h)]))
+            pairs_h += h[:depth]
+            pairs_e += [int(e)] * depth
+    ix = orc.Indexer()
+    ix.load_pairs(pairs_h, pairs_e)
+    pool = orc.PoolState(role, kv, waiting)
+
+    def make_batch(n):
+        prompts = []
+        for i in range(n):
+            g = int(rng.integers(0, len(fam) + 2))
+            kind = int(rng.integers(0, 8))
+            if kind == 0:
+                prompts.append(b"" if i % 2 else bytes(rng.integers(0, 256, bb - 1, dtype=np.uint8)))   # no hash at all
+            elif g >= len(fam):
+                prompts.append(bytes(rng.integers(0, 256, int(rng.integers(bb, bb * B + 40)), dtype=np.uint8)))
+            else:
+                keep = int(rng.integers(1, B + 1)) * bb
+                tail = int(rng.integers(0, 2 * bb))                # partial trailing block / beyond the cap
+                prompts.append(fam[g][:keep] + bytes(rng.integers(0, 256, tail, dtype=np.uint8)))
+        starts, pos = [], 0
+        for p in prompts:                                          # rows start on 32-byte boundaries, like the batcher's
+            starts.append(pos)
+            pos += (len(p) + 31) & ~31
+        buf = epp.PinnedBuffer(pos + 64)
+        offs = np.array(starts + [pos], dtype=np.uint64)
+        lens = np.array([len(p) for p in prompts], dtype=np.uint64)
+        for p, st in zip(prompts, starts):
+            buf.array[st: st + len(p)] = np.frombuffer(p, dtype=np.uint8)
+        d, o = _pack(prompts)
+        return buf, offs, lens, d, o
+
+    results = {}
+    for small in ("1024", "0"):
+        monkeypatch.setenv("EPP_SMALL_BATCH", small)
+        rng = np.random.default_rng(72)
+        with epp.Engine(E, spec(1, prim), spec(2, pref), block_size_tokens=bst, max_prefix_blocks=B, non_cached_tokens=8,
+                        encode=spec(3, enc), tie_seed=tie_seed) as eng:
+            eng.register_model(b"m")
+            eng.pool_set(np.arange(E), role, kv, waiting)
+            eng.index_load_snapshot(pairs_h, pairs_e)
+            got = []
+            for n in (1, 2, 33, 600, 1):
+                buf, offs, lens, d, o = make_batch(n)
+                mm = (rng.random(n) < 0.5).astype(np.uint8)
+                base = eng.stats()["n_decisions"]
+                dec, det = eng.schedule(buf.array, offsets=offs, lengths=lens, multimodal=mm, n_requests=n)
+                st = eng.stats()
+                if small != "0":
+                    assert st["last_kernel_launches"] in (1, 2), st["last_kernel_launches"]   # 2: + the dense-counter pass
+                    assert st["last_kernels_ms"] > 0
+                else:
+                    assert st["last_kernel_launches"] >= 3
+                odec, ototal = orc.cycle_batch(b"m", bst, B, 8, False, ix, orc.make_profile(1, prim), orc.make_profile(2, pref),
+                                               pool, d, o, 2, tie_seed=tie_seed, tie_base=base,
+                                               encode=orc.make_profile(3, enc), multimodal=mm)
+                helpers.assert_decisions_equal(dec, det, odec, ototal, where=f"small={small} n={n}")
+                got.append((dec.copy(), det.copy()))
+                buf.close()
+            results[small] = got
+    for (a, ad), (b, bd) in zip(results["1024"], results["0"]):
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(ad, bd)
+
+
 def test_large_pool_global_counters(epp, orc, tg):
     """E too large for per-warp shared-memory counters -> zeroed global scratch path (config-5-sized pool on 1 GPU)."""
     import helpers
