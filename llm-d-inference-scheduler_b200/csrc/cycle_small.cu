@@ -84,11 +84,21 @@ __global__ void __launch_bounds__(kThreads) k_cycle_small(HashParams hp, PickPar
             uint64_t *row = hp.hashes + r * (int64_t)hp.max_blocks;
             const uint64_t lenp8 = (uint64_t)bs + 8;
             volatile uint64_t *sh = s_m;
-            for (int32_t b = 0; b < nfull; b++) {
+            int32_t b = 0;
+            for (; b + 32 <= nfull; b += 32) {     // 32 blocks per hand-over, nothing but the dependent multiplies inside
+#pragma unroll 8
+                for (int j = 0; j < 32; j++) {
+                    prev = xxh_chain_step32_lat(s_m[b + j], lenp8, prev);
+                    row[b + j] = prev;             // the stash PreRequest reads (stream-ordered, after this kernel)
+                    sh[b + j] = prev;              // what the match warp of this CTA reads
+                }
+                __threadfence_block();
+                s_progress = b + 32;
+            }
+            for (; b < nfull; b++) {
                 prev = xxh_chain_step32_lat(s_m[b], lenp8, prev);
-                row[b] = prev;                     // the stash PreRequest reads (stream-ordered, after this kernel)
-                sh[b] = prev;                      // what the match warp of this CTA reads
-                if ((b & 31) == 31) { __threadfence_block(); s_progress = b + 1; }
+                row[b] = prev;
+                sh[b] = prev;
             }
             if ((int64_t)nfull * bs < s_eff) {     // trailing partial block (hashing.go:90-96)
                 prev = hash_block_generic(hp.data + s_off + (uint64_t)nfull * (uint64_t)bs, s_eff - (int64_t)nfull * bs, prev);
