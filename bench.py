@@ -465,6 +465,31 @@ def run_gpu(args, rank, world, local_rank):
         h2d_peak = nbytes / (max_over_ranks(best) * 1e-3) / 1e9
         del stage
 
+    # ---- small batches: ONE synchronous epp_schedule call per batch on the raw C ABI, pinned host buffers in and out
+    # (what a flush of the micro-batcher costs): median latency, decisions compared with the e2e batch's
+    small = None
+    if rank == 0 and not args.no_e2e:
+        import ctypes as C
+        small = {"how": "median of 200 synchronous epp_schedule calls per size, pinned host prompts in / decisions out, "
+                        "raw C ABI (ctypes), same engine and index as `value`", "us": {}, "decisions_equal_e2e_batch": True}
+        sb = epp.capi.Batch()
+        sb.uniform_len = w.prompt_bytes
+        sb.data = host_tokens.ctypes.data
+        small_dec = np.zeros(256, dtype=epp.DECISION_DTYPE)
+        for n in (1, 16, 256):
+            sb.n_requests = n
+            call = lambda: lib.epp_schedule(eng._h, C.byref(sb), small_dec.ctypes.data_as(C.c_void_p), None, 0)
+            for _ in range(20):
+                assert call() == 0
+            ts = []
+            for _ in range(200):
+                t0 = time.perf_counter()
+                call()
+                ts.append(time.perf_counter() - t0)
+            small["us"][str(n)] = float(np.median(ts) * 1e6)
+            small["decisions_equal_e2e_batch"] &= bool((small_dec[:n] == host_dec[:n]).all())
+        small["launches_per_call"] = int(eng.stats()["last_kernel_launches"])
+
     full_index = None
     if world == 1 and not args.no_full_index and args.index_fill == 0:
         full_index = full_index_leg(args, w, trace, dev_tokens, dev_dec, dev_dec_async, local_rank, sched_kw, args.steps, epp, helpers)
@@ -541,6 +566,7 @@ def run_gpu(args, rank, world, local_rank):
                     "h2d_peak_how": "plain pinned -> device copy of the same bytes (torch copy_, CUDA events, best of 4), same run",
                     "achieved_gbs": (nbytes + R * 32) / (e2e_wall / e2e_steps) / 1e9 if e2e_value else None,
                     "frac_of_pcie": ((nbytes + R * 32) / (e2e_wall / e2e_steps) / 1e9) / h2d_peak if e2e_value and h2d_peak else None},
+            "small_batch_latency": small,
             "gpu_launches": int(timed_launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_hash_fused", "achieved": achieved, "peak": peak, "unit": "GB/s",
