@@ -31,6 +31,8 @@ def main():
     args = ap.parse_args()
     sizes = [int(x) for x in args.sizes.split(",")]
     import torch
+    import bench
+    numa_node, _ = bench._bind_to_gpu_numa_node(0)       # pinned buffers first-touched next to the GPU, like the bench
     import epp_b200 as epp
     from epp_b200 import capi
     from tools import workload_setup as helpers
@@ -81,7 +83,7 @@ def main():
                 row[name + "_decisions_per_s"] = R / float(np.median(ts) * 1e-6)
             out[R] = row
     print(json.dumps({"workload": "config3 shape (4096 endpoints, 16 KiB prompts), one synchronous epp_schedule call per "
-                      "batch on the raw C ABI, %d calls per size" % args.reps, "latency": out}))
+                      "batch on the raw C ABI, %d calls per size" % args.reps, "numa_node": numa_node, "latency": out}))
 
 
 if __name__ == "__main__":
