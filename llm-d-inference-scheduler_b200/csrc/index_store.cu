@@ -959,9 +959,8 @@ cudaError_t IndexStore::grow_pair_table(uint64_t incoming, cudaStream_t s) {
     const uint64_t alive = ctr_host_[kCtrAlive];
     uint64_t want = 1024;
     while (want < (alive + incoming) * 5 / 2) want <<= 1;
-    DevBuf fresh;
-    size_t fresh_bytes = 0;
-    ST_TRY(fresh.reserve(sizeof(StoreEntry) * want, &fresh_bytes));
+    DevBuf &fresh = pt_spare_;
+    ST_TRY(fresh.reserve(sizeof(StoreEntry) * want, &bytes_));
     k_store_pt_clear<<<blocks_for(want, 256), 256, 0, s>>>(fresh.as<StoreEntry>(), want);
     ST_TRY(cudaMemsetAsync(&v.ctr[kCtrPtUsed], 0, sizeof(unsigned long long), s));
     View nv = v;
@@ -970,10 +969,8 @@ cudaError_t IndexStore::grow_pair_table(uint64_t incoming, cudaStream_t s) {
     k_store_rehash<<<blocks_for(pt_cap_, 256), 256, 0, s>>>(v.pt, pt_cap_, nv);
     ST_TRY(cudaGetLastError());
     ST_TRY(cudaStreamSynchronize(s));
-    bytes_ -= pt_.cap;
     std::swap(pt_.p, fresh.p);
     std::swap(pt_.cap, fresh.cap);
-    bytes_ += pt_.cap;
     pt_cap_ = want;
     pt_used_ = alive;
     last_launches += 3;
@@ -981,7 +978,7 @@ cudaError_t IndexStore::grow_pair_table(uint64_t incoming, cudaStream_t s) {
     return cudaSuccess;
 }
 
-// Moves every endpoint's live log entries, in order, into a fresh segment sized for twice (live + incoming).
+// Moves every endpoint's live log entries, in order, into a fresh segment sized for four times (live + incoming).
 cudaError_t IndexStore::repack_logs(cudaStream_t s) {
     View v;
     fill_view(v);
@@ -996,27 +993,25 @@ cudaError_t IndexStore::repack_logs(cudaStream_t s) {
     uint64_t total = 0;
     for (uint32_t e = 0; e < E_; e++) {
         uint64_t need = (uint64_t)live[e] + h_inc_[e];
-        uint64_t c = need ? ((2 * need + 256 + 255) & ~255ull) : 0;      // whole eviction blocks
+        uint64_t c = need ? ((4 * need + 256 + 255) & ~255ull) : 0;      // whole eviction blocks; room for three more batches
+                                                                           // of this size before the next compaction
         h_off_[e] = total;
         h_cap_[e] = c;
         total += c;
     }
     ST_TRY(cudaMemcpyAsync(new_off_.p, h_off_.data(), sizeof(unsigned long long) * E_, cudaMemcpyHostToDevice, s));
     ST_TRY(cudaMemcpyAsync(new_cap_.p, h_cap_.data(), sizeof(unsigned long long) * E_, cudaMemcpyHostToDevice, s));
-    DevBuf nh, ns;
-    size_t nb = 0;
-    ST_TRY(nh.reserve(sizeof(unsigned long long) * std::max<uint64_t>(total, 64), &nb));
-    ST_TRY(ns.reserve(sizeof(unsigned long long) * std::max<uint64_t>(total, 64), &nb));
+    DevBuf &nh = log_hash_spare_, &ns = log_seq_spare_;
+    ST_TRY(nh.reserve(sizeof(unsigned long long) * std::max<uint64_t>(total, 64), &bytes_));
+    ST_TRY(ns.reserve(sizeof(unsigned long long) * std::max<uint64_t>(total, 64), &bytes_));
     k_store_repack<<<blocks_for((uint64_t)E_ * 32, 256), 256, 0, s>>>(v, new_off_.as<unsigned long long>(), new_cap_.as<unsigned long long>(),
                                                                      nh.as<unsigned long long>(), ns.as<unsigned long long>());
     ST_TRY(cudaGetLastError());
     ST_TRY(cudaStreamSynchronize(s));
-    bytes_ -= log_hash_.cap + log_seq_.cap;
     std::swap(log_hash_.p, nh.p);
     std::swap(log_hash_.cap, nh.cap);
     std::swap(log_seq_.p, ns.p);
     std::swap(log_seq_.cap, ns.cap);
-    bytes_ += log_hash_.cap + log_seq_.cap;
     log_cap_ = total;
     last_launches += 1;
     last_repacked = true;

@@ -101,6 +101,8 @@ class IndexStore {
     size_t bytes_ = 0;
     uint64_t pt_cap_ = 0, log_cap_ = 0, in_map_ = 0, pt_used_ = 0;
     DevBuf pt_, log_hash_, log_seq_;
+    DevBuf pt_spare_, log_hash_spare_, log_seq_spare_;   // the previous generation of the three big buffers: rehash / repack
+                                                          // ping-pong between the pairs instead of cudaMalloc + cudaFree
     DevBuf cap_, live_, firstcall_, seg_off_, seg_cap_, head_, tail_, inc_, next_seq_, sp_seq_, sp_in_map_, ctr_;
     DevBuf hist_, off_, new_off_, new_cap_, cut_, blockcnt_, list_e_, list_start_;
     // touch log + scratch of patch_read_table
