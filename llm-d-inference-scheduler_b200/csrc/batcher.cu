@@ -4,14 +4,17 @@
 // layer turns the one into the other INSIDE the library, so that a cgo shim is a two-call wrapper
 // (epp_submit + epp_wait) with no batching logic of its own:
 //
-//   epp_submit   copies the prompt into the pinned staging buffer that is currently being filled and returns a ticket;
+//   epp_submit   reserves a row of the pinned staging buffer that is currently being filled (under the lock), copies the
+//                prompt into it (outside the lock) and returns a ticket;
 //   the flusher  (one thread per batcher) closes a batch when it holds max_batch requests or its oldest request has
 //                waited max_delay_us, runs epp_schedule on it (ONE frozen snapshot per flush, App. A.8), then -- when
 //                index_picks is set -- epp_index_add_picked (PreRequest, approximateprefix/plugin.go:164-200), so index
 //                updates land BETWEEN flushes; meanwhile the submitters fill the next staging buffer;
-//   epp_wait     blocks until the ticket's batch has been flushed and returns its decision.
+//   epp_wait     returns the ticket's decision once its batch has been flushed: it spins on the flush counter for a few
+//                tens of microseconds (a flush is ONE 30-130 us kernel launch) before it blocks on the condition variable.
 //
 // It is built on the public C ABI only (include/epp_engine.h): no engine internals, no CPU compute path.
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cstring>
@@ -57,6 +60,10 @@ struct epp_batcher {
     Staging buf[kBufs];
     std::vector<Result> results;
     bool in_flight[kBufs] = {false, false};    // the flusher is running epp_schedule on the buffer
+    std::atomic<int32_t> writers[kBufs];       // submitters still copying their prompt into the buffer (outside the lock)
+    std::atomic<uint64_t> done_seq{0};         // = seq_done, readable without the lock (epp_wait spins on it)
+    std::atomic<int32_t> sleepers{0};          // waiters blocked on cv_done
+    std::atomic<int32_t> spinners{0};          // waiters polling done_seq
     std::mutex mu;
     std::condition_variable cv_flush, cv_done, cv_space;
     int cur = 0;                               // buffer being filled
@@ -98,6 +105,7 @@ static void flusher_main(epp_batcher *b) {
         b->seq_filling++;
         lk.unlock();
         b->cv_space.notify_all();
+        while (b->writers[mine].load(std::memory_order_acquire) != 0) {}      // rows reserved before the swap: a 16 KiB memcpy each
 
         epp_batch batch;
         memset(&batch, 0, sizeof batch);
@@ -130,7 +138,7 @@ static void flusher_main(epp_batcher *b) {
         res.seq = seq;
         res.status = rc;
         res.remaining = n;
-        res.dec.assign(st.dec, st.dec + n);
+        res.dec.assign(st.dec, st.dec + n);                   // the vectors keep their capacity from round to round of the ring
         res.det.assign(st.det, st.det + n);
         res.topk.clear();
         if (b->pick_k > 1)
@@ -138,9 +146,10 @@ static void flusher_main(epp_batcher *b) {
         b->in_flight[mine] = false;
         if (rc != EPP_OK) b->last_error = err;
         b->seq_done = seq + 1;
+        b->done_seq.store(seq + 1, std::memory_order_release);
         b->n_flushes++;
         b->n_requests += (uint64_t)n;
-        b->cv_done.notify_all();
+        if (b->sleepers.load(std::memory_order_acquire) > 0) b->cv_done.notify_all();
         b->cv_space.notify_all();
     }
 }
@@ -169,6 +178,7 @@ extern "C" int32_t epp_batcher_create(epp_engine *h, const epp_batcher_cfg *cfg,
     b->row_cap = ((uint64_t)ec.max_prefix_blocks * (uint64_t)ec.block_size_tokens * 4 + 31) & ~31ull;
     b->pick_k = ec.pick_k;
     b->results.resize(kResults);
+    for (int i = 0; i < kBufs; i++) b->writers[i].store(0);
     const size_t mb = (size_t)cfg->max_batch;
     for (int i = 0; i < kBufs; i++) {
         Staging &st = b->buf[i];
@@ -229,10 +239,9 @@ extern "C" int32_t epp_submit(epp_batcher *b, uint32_t model_id, const void *pro
     // full: the flusher is about to take this buffer; in flight: the previous flush still reads the buffer we would fill
     while (!b->stop && (b->n_cur >= b->cfg.max_batch || b->in_flight[b->cur])) b->cv_space.wait(lk);
     if (b->stop) return bfail(EPP_ERR_STATE, "the batcher is shutting down");
-    Staging &st = b->buf[b->cur];
+    const int mine = b->cur;
+    Staging &st = b->buf[mine];
     const int32_t idx = b->n_cur;
-    const uint64_t n_copy = prompt_len < b->row_cap ? prompt_len : b->row_cap;
-    if (n_copy) memcpy(st.data + (size_t)idx * b->row_cap, prompt, n_copy);
     st.lengths[idx] = prompt_len;                  // the TRUE length: the P/D decider counts it (prefix_based_pd_decider.go:152-167)
     st.model_ids[idx] = model_id;
     st.multimodal[idx] = multimodal ? 1 : 0;
@@ -240,8 +249,12 @@ extern "C" int32_t epp_submit(epp_batcher *b, uint32_t model_id, const void *pro
     b->n_cur = idx + 1;
     *out_ticket = (b->seq_filling << 20) | (uint64_t)idx;
     const bool wake = idx == 0 || b->n_cur >= b->cfg.max_batch;
+    b->writers[mine].fetch_add(1, std::memory_order_acq_rel);      // the flusher waits for this copy before it reads the row
     lk.unlock();
     if (wake) b->cv_flush.notify_one();
+    const uint64_t n_copy = prompt_len < b->row_cap ? prompt_len : b->row_cap;
+    if (n_copy) memcpy(st.data + (size_t)idx * b->row_cap, prompt, n_copy);
+    b->writers[mine].fetch_sub(1, std::memory_order_release);
     return EPP_OK;
 }
 
@@ -255,9 +268,23 @@ extern "C" int32_t epp_wait_topk(epp_batcher *b, uint64_t ticket, epp_decision *
     if ((primary || prefill || encode) && b->pick_k <= 1) return bfail(EPP_ERR_STATE, "the engine was created with pick_k <= 1: there are no lists");
     const uint64_t seq = ticket >> 20;
     const uint32_t idx = (uint32_t)(ticket & 0xFFFFFu);
+    // a flush is one 30-130 us launch: up to four waiters spin on the flush counter for about that long before they
+    // block (more spinners than that only take cores away from the flusher and from each other)
+    if (b->spinners.fetch_add(1, std::memory_order_acq_rel) < 4) {
+        for (int spin = 0; spin < 4000 && b->done_seq.load(std::memory_order_acquire) <= seq; spin++) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+    }
+    b->spinners.fetch_sub(1, std::memory_order_acq_rel);
     std::unique_lock<std::mutex> lk(b->mu);
     if (seq > b->seq_filling || (seq == b->seq_filling && (int32_t)idx >= b->n_cur)) return bfail(EPP_ERR_INVALID, "unknown ticket");
-    while (b->seq_done <= seq) b->cv_done.wait(lk);          // a closing batcher still flushes what is pending
+    while (b->seq_done <= seq) {                             // a closing batcher still flushes what is pending
+        b->sleepers.fetch_add(1, std::memory_order_acq_rel);
+        b->cv_done.wait(lk);
+        b->sleepers.fetch_sub(1, std::memory_order_acq_rel);
+    }
     Result &res = b->results[seq % kResults];
     if (res.seq != seq) return bfail(EPP_ERR_STATE, "ticket expired: its batch was flushed more than 4096 flushes ago, or every ticket of it was already waited for");
     if ((size_t)idx >= res.dec.size()) return bfail(EPP_ERR_INVALID, "unknown ticket");
@@ -274,9 +301,11 @@ extern "C" int32_t epp_wait_topk(epp_batcher *b, uint64_t ticket, epp_decision *
     }
     if (--res.remaining == 0) {                    // every ticket served: release the memory early
         res.seq = ~0ull;
-        std::vector<epp_decision>().swap(res.dec);
-        std::vector<epp_decision_detail>().swap(res.det);
-        std::vector<uint32_t>().swap(res.topk);
+        if (res.dec.capacity() > 4096) {            // big batches give their memory back, small ones keep it for the next lap
+            std::vector<epp_decision>().swap(res.dec);
+            std::vector<epp_decision_detail>().swap(res.det);
+            std::vector<uint32_t>().swap(res.topk);
+        }
     }
     return rc;
 }
