@@ -71,6 +71,7 @@ type Config struct {
 	AlwaysDisagg         bool
 	TieSeed              uint64 // 0 = lowest slot of the arg-max set (tests); production: any non-zero value
 	PickK                int    // max-score-picker maxNumOfEndpoints; <= 1: one target endpoint per profile
+	IndexCommitMicros    int    // picks become visible to later requests at most this much later (0 = before the next batch)
 	Primary              ProfileSpec
 	Prefill              *ProfileSpec // non-nil: disagg handler (decode -> decider -> prefill)
 	Encode               *ProfileSpec // non-nil (with Prefill): encode stage for multimodal requests
@@ -142,6 +143,7 @@ func New(cfg Config) (*Engine, error) {
 	if cfg.PickK > 1 {
 		c.pick_k = C.int32_t(cfg.PickK)
 	}
+	c.index_commit_interval_us = C.int32_t(cfg.IndexCommitMicros)
 	if err := fillProfile(&c.primary, cfg.Primary); err != nil {
 		return nil, err
 	}

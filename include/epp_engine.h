@@ -179,7 +179,12 @@ typedef struct {
     uint64_t tie_seed;             /* seed of every reproducible random draw (ties, top-k order, exploration); 0 = the
                                       deterministic mode: lowest slot of the arg-max set, no exploration              */
     int32_t encode_enabled;        /* an "encode" profile + always-disagg-multimodal-decider are configured */
-    int32_t reserved0;
+    int32_t index_commit_interval_us; /* 0: every scheduling call first makes all earlier index updates (epp_index_add,
+                                      epp_index_add_picked) visible -- exact sequential semantics, what the parity tests use;
+                                      > 0: a scheduling call does that only if the last one that did is at least this long
+                                      ago, i.e. picks become visible to later requests with a bounded delay, like the
+                                      reference's asynchronous PreRequest (approximateprefix/plugin.go:189-194).
+                                      epp_index_commit / epp_index_get always commit.                              */
     uint64_t reserved1[2];
 } epp_config;
 
@@ -411,8 +416,9 @@ EPP_API int32_t epp_get_config(epp_engine *h, epp_config *out);
  * goroutine each (requestcontrol/director.go:69-71, 243; handlers/server.go:168).  epp_submit / epp_wait give a shim
  * exactly that shape: any number of threads submit single prompts; a flusher thread inside the library closes a batch
  * when it holds max_batch requests or its oldest request has waited max_delay_us, evaluates it against ONE frozen
- * snapshot (epp_schedule) and -- with index_picks -- applies PreRequest (epp_index_add_picked,
- * approximateprefix/plugin.go:164-200) before the next batch; epp_wait blocks until the ticket's batch is done.
+ * snapshot (epp_schedule), hands out the decisions and -- with index_picks -- applies PreRequest (epp_index_add_picked,
+ * approximateprefix/plugin.go:164-200; off the request path like the reference's, :189-194) before the next batch;
+ * epp_wait blocks until the ticket's batch is done.
  * A batcher must be destroyed before its engine; other threads may keep calling epp_pool_set etc. on the engine
  * (the scrape loop) -- every flush sees the snapshot current at its start. */
 typedef struct epp_batcher epp_batcher;
@@ -424,13 +430,16 @@ typedef struct {
 } epp_batcher_cfg;
 typedef struct {
     uint64_t n_flushes, n_requests, n_full_flushes, n_pending;
+    uint64_t n_index_errors;       /* flushes whose PreRequest (epp_index_add_picked) failed: it runs after the decisions
+                                      were handed out, so its error reaches epp_batcher_stats / the log, not the waiters */
 } epp_batcher_stats_t;
 EPP_API int32_t epp_batcher_create(epp_engine *h, const epp_batcher_cfg *cfg, epp_batcher **out);
 EPP_API int32_t epp_batcher_destroy(epp_batcher *b);     /* flushes what is pending, then stops the flusher   */
 /* prompt: the request's bytes (a uint32 token array = 4 bytes per token, hashing.go:49), copied before the call returns
- * (only the first max_prefix_blocks blocks are kept); multimodal: hasMultimodalContent (encode decider).  Each ticket is
- * good for ONE epp_wait; a batch's results are dropped when all its tickets were served, or 4096 flushes later.
- * Every epp_wait must have returned before epp_batcher_destroy. */
+ * (only the first max_prefix_blocks blocks are kept); multimodal: hasMultimodalContent (encode decider).  A ticket can
+ * be waited for (any number of times, from any thread) until 4096 later batches have been flushed; after that
+ * epp_wait returns EPP_ERR_STATE.  Every epp_wait must have returned before epp_batcher_destroy.
+ * Neither call takes a lock: a submit is one compare-and-swap + the copy, a wait polls / sleeps on the flush counter. */
 EPP_API int32_t epp_submit(epp_batcher *b, uint32_t model_id, const void *prompt, uint64_t prompt_len,
                            uint32_t multimodal, uint64_t *out_ticket);
 EPP_API int32_t epp_wait(epp_batcher *b, uint64_t ticket, epp_decision *out, epp_decision_detail *out_detail);

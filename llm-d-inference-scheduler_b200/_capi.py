@@ -42,7 +42,7 @@ class Config(C.Structure):
                 ("lru_capacity_per_server", C.c_int32), ("handler", C.c_int32), ("always_disagg", C.c_int32),
                 ("non_cached_tokens", C.c_int64), ("n_ext_cols", C.c_int32), ("pick_k", C.c_int32),
                 ("primary", ProfileCfg), ("prefill", ProfileCfg), ("encode", ProfileCfg), ("tie_seed", C.c_uint64),
-                ("encode_enabled", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_uint64 * 2)]
+                ("encode_enabled", C.c_int32), ("index_commit_interval_us", C.c_int32), ("reserved1", C.c_uint64 * 2)]
 
 
 class Decision(C.Structure):
@@ -84,7 +84,7 @@ class BatcherCfg(C.Structure):
 
 class BatcherStats(C.Structure):
     _fields_ = [("n_flushes", C.c_uint64), ("n_requests", C.c_uint64), ("n_full_flushes", C.c_uint64),
-                ("n_pending", C.c_uint64)]
+                ("n_pending", C.c_uint64), ("n_index_errors", C.c_uint64)]
 
 
 class ShardBest(C.Structure):

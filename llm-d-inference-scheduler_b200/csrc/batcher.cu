@@ -4,19 +4,29 @@
 // layer turns the one into the other INSIDE the library, so that a cgo shim is a two-call wrapper
 // (epp_submit + epp_wait) with no batching logic of its own:
 //
-//   epp_submit   reserves a row of the pinned staging buffer that is currently being filled (under the lock), copies the
-//                prompt into it (outside the lock) and returns a ticket;
+//   epp_submit   reserves a row of the batch being filled with ONE atomic compare-and-swap (no lock), copies the prompt
+//                into the batch's pinned staging buffer and returns a ticket;
 //   the flusher  (one thread per batcher) closes a batch when it holds max_batch requests or its oldest request has
-//                waited max_delay_us, runs epp_schedule on it (ONE frozen snapshot per flush, App. A.8), then -- when
-//                index_picks is set -- epp_index_add_picked (PreRequest, approximateprefix/plugin.go:164-200), so index
-//                updates land BETWEEN flushes; meanwhile the submitters fill the next staging buffer;
-//   epp_wait     returns the ticket's decision once its batch has been flushed: it spins on the flush counter for a few
-//                tens of microseconds (a flush is ONE 30-130 us kernel launch) before it blocks on the condition variable.
+//                waited max_delay_us, runs epp_schedule on it (ONE frozen snapshot per flush, App. A.8), publishes the
+//                decisions, then -- when index_picks is set -- runs epp_index_add_picked (PreRequest,
+//                approximateprefix/plugin.go:164-200), so index updates land BETWEEN flushes; meanwhile the submitters fill
+//                the next staging buffers;
+//   epp_wait     returns the ticket's decision once its batch has been flushed: a few waiters poll the flush counter
+//                (a flush is ONE 30-130 us kernel launch), the others sleep on it (futex) -- nobody takes a lock.
+//
+// Hot-path synchronisation is three atomics: `fill` = (sequence number of the batch being filled << 20 | rows reserved),
+// `ready` (per staging buffer) = rows whose prompt copy is complete, `done` = batches flushed.  Batch k uses staging
+// buffer k % 4 and result slot k % 4096; a submitter of batch k waits until batch k - 4 has been flushed.
 //
 // It is built on the public C ABI only (include/epp_engine.h): no engine internals, no CPU compute path.
+#include <linux/futex.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
+#include <algorithm>
 #include <atomic>
 #include <chrono>
-#include <condition_variable>
+#include <climits>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -26,9 +36,25 @@
 #include "../../include/epp_engine.h"
 
 namespace {
-constexpr int kBufs = 2;                       // staging buffers: one being filled while the other is in flight
+constexpr int kBufs = 4;                       // staging buffers: batches k .. k+3 can be filling / in flight at once
 constexpr int kResults = 4096;                 // flushed batches whose results are kept for epp_wait (ring)
+constexpr uint64_t kCountMask = (1ull << 20) - 1;
 using Clock = std::chrono::steady_clock;
+
+inline void cpu_relax() {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+}
+inline void futex_wait(std::atomic<uint32_t> *a, uint32_t expected, const timespec *timeout) {
+    syscall(SYS_futex, reinterpret_cast<uint32_t *>(a), FUTEX_WAIT_PRIVATE, expected, timeout, nullptr, 0);
+}
+inline void futex_wake_all(std::atomic<uint32_t> *a) {
+    syscall(SYS_futex, reinterpret_cast<uint32_t *>(a), FUTEX_WAKE_PRIVATE, INT_MAX, nullptr, nullptr, 0);
+}
+inline int64_t now_ns() {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now().time_since_epoch()).count();
+}
 
 struct Staging {
     uint8_t *data = nullptr;                   // [max_batch][row_cap] pinned
@@ -39,13 +65,16 @@ struct Staging {
     epp_decision *dec = nullptr;
     epp_decision_detail *det = nullptr;
     uint32_t *topk[3] = {nullptr, nullptr, nullptr};   // [max_batch][pick_k] primary / prefill / encode lists (pick_k > 1)
-    int32_t n = 0;
+    std::atomic<int32_t> ready{0};             // rows of the batch using this buffer whose copy is complete
+    std::atomic<int64_t> first_arrival_ns{0};  // when row 0 of that batch was reserved
 };
-// Results of one flushed batch, kept until every ticket has been waited for or kResults later batches were flushed.
+// Results of one flushed batch, kept until kResults later batches were flushed.
 struct Result {
-    uint64_t seq = ~0ull;
+    std::atomic<uint64_t> seq{~0ull};          // which batch the arrays hold (~0: being rewritten)
+    std::atomic<int32_t> readers{0};           // epp_wait calls copying out of the arrays: the flusher waits for them before
+                                               // it rewrites the slot (4096 flushes later)
     int32_t status = EPP_OK;                   // return code of the batch's epp_schedule / epp_index_add_picked
-    int32_t remaining = 0;                     // tickets not yet waited for
+    int32_t n = 0;
     std::vector<epp_decision> dec;
     std::vector<epp_decision_detail> det;
     std::vector<uint32_t> topk;                // [3][n][pick_k] when the engine's pick_k > 1
@@ -59,53 +88,61 @@ struct epp_batcher {
     int32_t pick_k = 0;                        // the engine's maxNumOfEndpoints (> 1: flushes also fetch the first-k lists)
     Staging buf[kBufs];
     std::vector<Result> results;
-    bool in_flight[kBufs] = {false, false};    // the flusher is running epp_schedule on the buffer
-    std::atomic<int32_t> writers[kBufs];       // submitters still copying their prompt into the buffer (outside the lock)
-    std::atomic<uint64_t> done_seq{0};         // = seq_done, readable without the lock (epp_wait spins on it)
-    std::atomic<int32_t> sleepers{0};          // waiters blocked on cv_done
-    std::atomic<int32_t> spinners{0};          // waiters polling done_seq
-    std::mutex mu;
-    std::condition_variable cv_flush, cv_done, cv_space;
-    int cur = 0;                               // buffer being filled
-    int32_t n_cur = 0;
-    uint64_t seq_filling = 0, seq_done = 0;    // batches [0, seq_done) have been flushed
-    Clock::time_point first_arrival;
-    bool stop = false;
+    std::atomic<uint64_t> fill{0};             // (sequence number of the batch being filled << 20) | rows reserved in it
+    std::atomic<uint64_t> done{0};             // batches [0, done) have been flushed
+    std::atomic<uint32_t> done32{0};           // low word of `done` (futex word of the waiters)
+    std::atomic<uint32_t> work32{0};           // bumped by whoever gives the flusher something to do (its futex word)
+    std::atomic<int32_t> sleepers{0};          // waiters asleep on done32
+    std::atomic<int32_t> spinners{0};          // waiters polling `done`
+    std::atomic<bool> flusher_asleep{false};
+    std::atomic<bool> stop{false};
     std::thread flusher;
-    uint64_t n_flushes = 0, n_requests = 0, n_full = 0;
+    std::atomic<uint64_t> n_flushes{0}, n_requests{0}, n_full{0}, index_errors{0};
+    std::mutex err_mu;
     std::string last_error;
 };
 
 static thread_local std::string g_batcher_error;
 
+static void wake_flusher(epp_batcher *b) {
+    b->work32.fetch_add(1, std::memory_order_seq_cst);
+    if (b->flusher_asleep.load(std::memory_order_seq_cst)) futex_wake_all(&b->work32);
+}
+
 static void flusher_main(epp_batcher *b) {
-    std::unique_lock<std::mutex> lk(b->mu);
+    const int64_t delay_ns = (int64_t)b->cfg.max_delay_us * 1000;
     for (;;) {
-        // wait for a batch to close: full, or its oldest request has waited max_delay_us
-        for (;;) {
-            if (b->stop && b->n_cur == 0) return;
-            if (b->n_cur >= b->cfg.max_batch || (b->n_cur > 0 && b->stop)) break;
-            if (b->n_cur > 0) {
-                const auto deadline = b->first_arrival + std::chrono::microseconds(b->cfg.max_delay_us);
-                if (Clock::now() >= deadline) break;
-                b->cv_flush.wait_until(lk, deadline);
-            } else {
-                b->cv_flush.wait(lk);
+        // ---- wait for a batch to close: full, or non-empty and its oldest request has waited max_delay_us
+        uint64_t f;
+        for (int idle = 0;; idle++) {
+            f = b->fill.load(std::memory_order_acquire);
+            const uint64_t n = f & kCountMask;
+            const bool stopping = b->stop.load(std::memory_order_acquire);
+            if (n >= (uint64_t)b->cfg.max_batch || (n > 0 && stopping)) break;
+            if (n == 0 && stopping) return;
+            if (n > 0) {
+                const int64_t t0 = b->buf[(f >> 20) % kBufs].first_arrival_ns.load(std::memory_order_acquire);
+                if (delay_ns == 0 || (t0 && now_ns() - t0 >= delay_ns)) break;
+                cpu_relax();                                   // the deadline is microseconds away: poll
+                continue;
             }
+            if (idle < 2000) { cpu_relax(); continue; }        // some tens of microseconds of polling before sleeping
+            const uint32_t w = b->work32.load(std::memory_order_acquire);
+            b->flusher_asleep.store(true, std::memory_order_seq_cst);
+            if ((b->fill.load(std::memory_order_seq_cst) & kCountMask) == 0 && !b->stop.load(std::memory_order_acquire)) {
+                timespec ts{0, 50 * 1000 * 1000};              // a lost wake-up costs 50 ms at most
+                futex_wait(&b->work32, w, &ts);
+            }
+            b->flusher_asleep.store(false, std::memory_order_release);
+            idle = 0;
         }
-        Staging &st = b->buf[b->cur];
-        const int32_t n = b->n_cur;
-        const uint64_t seq = b->seq_filling;
-        st.n = n;
-        if (n >= b->cfg.max_batch) b->n_full++;
-        const int mine = b->cur;
-        b->in_flight[mine] = true;
-        b->cur = (b->cur + 1) % kBufs;          // the other buffer is free: its flush completed before this one began
-        b->n_cur = 0;
-        b->seq_filling++;
-        lk.unlock();
-        b->cv_space.notify_all();
-        while (b->writers[mine].load(std::memory_order_acquire) != 0) {}      // rows reserved before the swap: a 16 KiB memcpy each
+        // ---- close it: from now on submitters reserve rows of batch seq + 1
+        const uint64_t seq = f >> 20;
+        f = b->fill.exchange((seq + 1) << 20, std::memory_order_acq_rel);
+        const int32_t n = (int32_t)std::min<uint64_t>(f & kCountMask, (uint64_t)b->cfg.max_batch);
+        Staging &st = b->buf[seq % kBufs];
+        while (st.ready.load(std::memory_order_acquire) < n) cpu_relax();     // rows reserved before the close: a 16 KiB memcpy each
+        if (n >= b->cfg.max_batch) b->n_full.fetch_add(1, std::memory_order_relaxed);
 
         epp_batch batch;
         memset(&batch, 0, sizeof batch);
@@ -127,30 +164,40 @@ static void flusher_main(epp_batcher *b) {
         } else {
             rc = epp_schedule(b->eng, &batch, st.dec, st.det, b->cfg.index_picks ? 1 : 0);
         }
-        std::string err;
-        if (rc != EPP_OK) err = epp_last_error();
-        if (rc == EPP_OK && b->cfg.index_picks) {
-            const int32_t rc2 = epp_index_add_picked(b->eng);      // PreRequest: visible to the NEXT flush
-            if (rc2 != EPP_OK) { rc = rc2; err = epp_last_error(); }
+        if (rc != EPP_OK) {
+            std::lock_guard<std::mutex> lk(b->err_mu);
+            b->last_error = epp_last_error();
         }
-        lk.lock();
+        // ---- publish the results, then the flush counter
         Result &res = b->results[seq % kResults];
-        res.seq = seq;
+        res.seq.store(~0ull, std::memory_order_seq_cst);           // late readers of the slot's previous batch see it expire ...
+        while (res.readers.load(std::memory_order_seq_cst) != 0) cpu_relax();   // ... and those inside finish first
         res.status = rc;
-        res.remaining = n;
-        res.dec.assign(st.dec, st.dec + n);                   // the vectors keep their capacity from round to round of the ring
+        res.n = n;
+        res.dec.assign(st.dec, st.dec + n);                       // the vectors keep their capacity from lap to lap of the ring
         res.det.assign(st.det, st.det + n);
         res.topk.clear();
         if (b->pick_k > 1)
             for (int q = 0; q < 3; q++) res.topk.insert(res.topk.end(), st.topk[q], st.topk[q] + (size_t)n * (size_t)b->pick_k);
-        b->in_flight[mine] = false;
-        if (rc != EPP_OK) b->last_error = err;
-        b->seq_done = seq + 1;
-        b->done_seq.store(seq + 1, std::memory_order_release);
-        b->n_flushes++;
-        b->n_requests += (uint64_t)n;
-        if (b->sleepers.load(std::memory_order_acquire) > 0) b->cv_done.notify_all();
-        b->cv_space.notify_all();
+        res.seq.store(seq, std::memory_order_release);
+        st.ready.store(0, std::memory_order_relaxed);
+        st.first_arrival_ns.store(0, std::memory_order_relaxed);
+        b->n_flushes.fetch_add(1, std::memory_order_relaxed);
+        b->n_requests.fetch_add((uint64_t)n, std::memory_order_relaxed);
+        b->done.store(seq + 1, std::memory_order_seq_cst);        // also frees staging buffer seq % kBufs for batch seq + kBufs
+        b->done32.store((uint32_t)(seq + 1), std::memory_order_seq_cst);
+        if (b->sleepers.load(std::memory_order_seq_cst) > 0) futex_wake_all(&b->done32);
+        // ---- PreRequest for the whole batch, off the waiters' path like the reference's (plugin.go:189-194: "Update
+        // indexer asynchronously to avoid blocking the request path"); the next flush sees it (or a later one, see
+        // epp_config.index_commit_interval_us)
+        if (rc == EPP_OK && b->cfg.index_picks) {
+            const int32_t rc2 = epp_index_add_picked(b->eng);
+            if (rc2 != EPP_OK) {
+                std::lock_guard<std::mutex> lk(b->err_mu);
+                b->last_error = epp_last_error();
+                b->index_errors.fetch_add(1, std::memory_order_relaxed);
+            }
+        }
     }
 }
 
@@ -165,7 +212,7 @@ extern "C" int32_t epp_batcher_create(epp_engine *h, const epp_batcher_cfg *cfg,
     if (!h || !cfg || !out) return bfail(EPP_ERR_INVALID, "NULL argument");
     *out = nullptr;
     if (cfg->struct_size != sizeof(epp_batcher_cfg)) return bfail(EPP_ERR_INVALID, "epp_batcher_cfg.struct_size mismatch");
-    if (cfg->max_batch <= 0 || cfg->max_batch > (1 << 20)) return bfail(EPP_ERR_INVALID, "max_batch out of range [1, 2^20]");
+    if (cfg->max_batch <= 0 || cfg->max_batch > (1 << 19)) return bfail(EPP_ERR_INVALID, "max_batch out of range [1, 2^19]");
     if (cfg->max_delay_us < 0) return bfail(EPP_ERR_INVALID, "max_delay_us must be >= 0");
     epp_config ec;
     int32_t rc = epp_get_config(h, &ec);
@@ -177,8 +224,7 @@ extern "C" int32_t epp_batcher_create(epp_engine *h, const epp_batcher_cfg *cfg,
     // rows start on 32-byte boundaries (selects the aligned hash kernels)
     b->row_cap = ((uint64_t)ec.max_prefix_blocks * (uint64_t)ec.block_size_tokens * 4 + 31) & ~31ull;
     b->pick_k = ec.pick_k;
-    b->results.resize(kResults);
-    for (int i = 0; i < kBufs; i++) b->writers[i].store(0);
+    b->results = std::vector<Result>(kResults);
     const size_t mb = (size_t)cfg->max_batch;
     for (int i = 0; i < kBufs; i++) {
         Staging &st = b->buf[i];
@@ -215,14 +261,11 @@ extern "C" int32_t epp_batcher_create(epp_engine *h, const epp_batcher_cfg *cfg,
 
 extern "C" int32_t epp_batcher_destroy(epp_batcher *b) {
     if (!b) return EPP_OK;
-    {
-        std::lock_guard<std::mutex> lk(b->mu);
-        b->stop = true;
-    }
-    b->cv_flush.notify_all();
-    b->cv_space.notify_all();
+    b->stop.store(true, std::memory_order_seq_cst);
+    wake_flusher(b);
+    futex_wake_all(&b->work32);
     if (b->flusher.joinable()) b->flusher.join();            // drains the batch being filled
-    b->cv_done.notify_all();
+    futex_wake_all(&b->done32);
     for (int i = 0; i < kBufs; i++) {
         Staging &st = b->buf[i];
         void *ps[10] = {st.data, st.offsets, st.lengths, st.model_ids, st.multimodal, st.dec, st.det, st.topk[0], st.topk[1], st.topk[2]};
@@ -235,26 +278,42 @@ extern "C" int32_t epp_batcher_destroy(epp_batcher *b) {
 extern "C" int32_t epp_submit(epp_batcher *b, uint32_t model_id, const void *prompt, uint64_t prompt_len,
                               uint32_t multimodal, uint64_t *out_ticket) {
     if (!b || !out_ticket || (prompt_len && !prompt)) return bfail(EPP_ERR_INVALID, "NULL argument");
-    std::unique_lock<std::mutex> lk(b->mu);
-    // full: the flusher is about to take this buffer; in flight: the previous flush still reads the buffer we would fill
-    while (!b->stop && (b->n_cur >= b->cfg.max_batch || b->in_flight[b->cur])) b->cv_space.wait(lk);
-    if (b->stop) return bfail(EPP_ERR_STATE, "the batcher is shutting down");
-    const int mine = b->cur;
-    Staging &st = b->buf[mine];
-    const int32_t idx = b->n_cur;
+    const uint64_t max_batch = (uint64_t)b->cfg.max_batch;
+    uint64_t seq, idx;
+    for (int spin = 0;; spin++) {
+        if (b->stop.load(std::memory_order_acquire)) return bfail(EPP_ERR_STATE, "the batcher is shutting down");
+        uint64_t f = b->fill.load(std::memory_order_acquire);
+        // full: the flusher is about to close it; or its staging buffer is still in flight (batch seq - 4 not flushed yet)
+        if ((f & kCountMask) >= max_batch || (f >> 20) >= b->done.load(std::memory_order_acquire) + kBufs) {
+            if (spin == 0) wake_flusher(b);
+            if (spin < 200) {
+                cpu_relax();
+            } else {                                           // sleep until the next flush completes (it frees a batch)
+                const uint32_t d = b->done32.load(std::memory_order_seq_cst);
+                b->sleepers.fetch_add(1, std::memory_order_seq_cst);
+                if (b->fill.load(std::memory_order_seq_cst) == f) {
+                    timespec ts{0, 2 * 1000 * 1000};
+                    futex_wait(&b->done32, d, &ts);
+                }
+                b->sleepers.fetch_sub(1, std::memory_order_seq_cst);
+            }
+            continue;
+        }
+        if (!b->fill.compare_exchange_weak(f, f + 1, std::memory_order_seq_cst)) continue;
+        seq = f >> 20;
+        idx = f & kCountMask;
+        break;
+    }
+    Staging &st = b->buf[seq % kBufs];
+    if (idx == 0) st.first_arrival_ns.store(now_ns(), std::memory_order_release);
+    if (idx == 0 || idx + 1 >= max_batch) wake_flusher(b);
     st.lengths[idx] = prompt_len;                  // the TRUE length: the P/D decider counts it (prefix_based_pd_decider.go:152-167)
     st.model_ids[idx] = model_id;
     st.multimodal[idx] = multimodal ? 1 : 0;
-    if (idx == 0) b->first_arrival = Clock::now();
-    b->n_cur = idx + 1;
-    *out_ticket = (b->seq_filling << 20) | (uint64_t)idx;
-    const bool wake = idx == 0 || b->n_cur >= b->cfg.max_batch;
-    b->writers[mine].fetch_add(1, std::memory_order_acq_rel);      // the flusher waits for this copy before it reads the row
-    lk.unlock();
-    if (wake) b->cv_flush.notify_one();
     const uint64_t n_copy = prompt_len < b->row_cap ? prompt_len : b->row_cap;
     if (n_copy) memcpy(st.data + (size_t)idx * b->row_cap, prompt, n_copy);
-    b->writers[mine].fetch_sub(1, std::memory_order_release);
+    st.ready.fetch_add(1, std::memory_order_release);              // the flusher waits for this before it reads the row
+    *out_ticket = (seq << 20) | idx;
     return EPP_OK;
 }
 
@@ -267,55 +326,68 @@ extern "C" int32_t epp_wait_topk(epp_batcher *b, uint64_t ticket, epp_decision *
     if (!b || !out) return bfail(EPP_ERR_INVALID, "NULL argument");
     if ((primary || prefill || encode) && b->pick_k <= 1) return bfail(EPP_ERR_STATE, "the engine was created with pick_k <= 1: there are no lists");
     const uint64_t seq = ticket >> 20;
-    const uint32_t idx = (uint32_t)(ticket & 0xFFFFFu);
-    // a flush is one 30-130 us launch: up to four waiters spin on the flush counter for about that long before they
-    // block (more spinners than that only take cores away from the flusher and from each other)
-    if (b->spinners.fetch_add(1, std::memory_order_acq_rel) < 4) {
-        for (int spin = 0; spin < 4000 && b->done_seq.load(std::memory_order_acquire) <= seq; spin++) {
-#if defined(__x86_64__)
-            __builtin_ia32_pause();
-#endif
-        }
+    const uint32_t idx = (uint32_t)(ticket & kCountMask);
+    {
+        const uint64_t f = b->fill.load(std::memory_order_acquire);
+        if (seq > (f >> 20) || (seq == (f >> 20) && idx >= (f & kCountMask))) return bfail(EPP_ERR_INVALID, "unknown ticket");
     }
-    b->spinners.fetch_sub(1, std::memory_order_acq_rel);
-    std::unique_lock<std::mutex> lk(b->mu);
-    if (seq > b->seq_filling || (seq == b->seq_filling && (int32_t)idx >= b->n_cur)) return bfail(EPP_ERR_INVALID, "unknown ticket");
-    while (b->seq_done <= seq) {                             // a closing batcher still flushes what is pending
-        b->sleepers.fetch_add(1, std::memory_order_acq_rel);
-        b->cv_done.wait(lk);
-        b->sleepers.fetch_sub(1, std::memory_order_acq_rel);
+    // a flush is one 30-130 us launch: up to four waiters poll the flush counter for about that long, everybody else
+    // (and they, afterwards) sleeps on it -- more pollers than that only take cores away from the flusher
+    if (b->done.load(std::memory_order_acquire) <= seq) {
+        if (b->spinners.fetch_add(1, std::memory_order_acq_rel) < 4)
+            for (int spin = 0; spin < 4000 && b->done.load(std::memory_order_acquire) <= seq; spin++) cpu_relax();
+        b->spinners.fetch_sub(1, std::memory_order_acq_rel);
+        while (b->done.load(std::memory_order_seq_cst) <= seq) {      // a closing batcher still flushes what is pending
+            const uint32_t d = b->done32.load(std::memory_order_seq_cst);
+            b->sleepers.fetch_add(1, std::memory_order_seq_cst);
+            if (b->done.load(std::memory_order_seq_cst) <= seq) {
+                timespec ts{0, 20 * 1000 * 1000};
+                futex_wait(&b->done32, d, &ts);
+            }
+            b->sleepers.fetch_sub(1, std::memory_order_seq_cst);
+        }
     }
     Result &res = b->results[seq % kResults];
-    if (res.seq != seq) return bfail(EPP_ERR_STATE, "ticket expired: its batch was flushed more than 4096 flushes ago, or every ticket of it was already waited for");
-    if ((size_t)idx >= res.dec.size()) return bfail(EPP_ERR_INVALID, "unknown ticket");
-    int32_t rc = res.status;
+    res.readers.fetch_add(1, std::memory_order_seq_cst);
+    if (res.seq.load(std::memory_order_seq_cst) != seq) {
+        res.readers.fetch_sub(1, std::memory_order_seq_cst);
+        return bfail(EPP_ERR_STATE, "ticket expired: its batch was flushed more than 4096 flushes ago");
+    }
+    if ((int32_t)idx >= res.n) {
+        res.readers.fetch_sub(1, std::memory_order_seq_cst);
+        return bfail(EPP_ERR_INVALID, "unknown ticket");
+    }
+    const int32_t rc = res.status;
+    epp_decision d{};
+    epp_decision_detail dd{};
+    uint32_t lists[3][64];
+    const size_t k = (size_t)b->pick_k, n = (size_t)res.n;
+    if (rc == EPP_OK) {
+        d = res.dec[idx];
+        dd = res.det[idx];
+        if (k > 1 && res.topk.size() >= 3 * n * k)
+            for (int q = 0; q < 3; q++) memcpy(lists[q], res.topk.data() + ((size_t)q * n + idx) * k, sizeof(uint32_t) * k);
+    }
+    res.readers.fetch_sub(1, std::memory_order_seq_cst);
     if (rc != EPP_OK) {
+        std::lock_guard<std::mutex> lk(b->err_mu);
         g_batcher_error = b->last_error;
-    } else {
-        *out = res.dec[idx];
-        if (out_detail) *out_detail = res.det[idx];
-        uint32_t *dst[3] = {primary, prefill, encode};
-        const size_t k = (size_t)b->pick_k, n = res.dec.size();
-        for (int q = 0; q < 3; q++)
-            if (dst[q]) memcpy(dst[q], res.topk.data() + ((size_t)q * n + idx) * k, sizeof(uint32_t) * k);
+        return rc;
     }
-    if (--res.remaining == 0) {                    // every ticket served: release the memory early
-        res.seq = ~0ull;
-        if (res.dec.capacity() > 4096) {            // big batches give their memory back, small ones keep it for the next lap
-            std::vector<epp_decision>().swap(res.dec);
-            std::vector<epp_decision_detail>().swap(res.det);
-            std::vector<uint32_t>().swap(res.topk);
-        }
-    }
-    return rc;
+    *out = d;
+    if (out_detail) *out_detail = dd;
+    uint32_t *dst[3] = {primary, prefill, encode};
+    for (int q = 0; q < 3; q++)
+        if (dst[q]) memcpy(dst[q], lists[q], sizeof(uint32_t) * k);
+    return EPP_OK;
 }
 
 extern "C" int32_t epp_batcher_stats(epp_batcher *b, epp_batcher_stats_t *out) {
     if (!b || !out) return bfail(EPP_ERR_INVALID, "NULL argument");
-    std::lock_guard<std::mutex> lk(b->mu);
-    out->n_flushes = b->n_flushes;
-    out->n_requests = b->n_requests;
-    out->n_full_flushes = b->n_full;
-    out->n_pending = (uint64_t)b->n_cur;
+    out->n_flushes = b->n_flushes.load(std::memory_order_relaxed);
+    out->n_requests = b->n_requests.load(std::memory_order_relaxed);
+    out->n_full_flushes = b->n_full.load(std::memory_order_relaxed);
+    out->n_pending = b->fill.load(std::memory_order_acquire) & kCountMask;
+    out->n_index_errors = b->index_errors.load(std::memory_order_relaxed);
     return EPP_OK;
 }

@@ -141,6 +141,8 @@ struct epp_engine {
     uint32_t small_epoch = 0;
     DevBuf small_overflow_n;        // stays zero between batches (reset by the overflow pass)
     bool small_stats_pending = false;   // ev[0] / ev[1] bracket the last small batch; read lazily by epp_get_stats
+    std::chrono::steady_clock::time_point last_commit{};   // last commit done by a scheduling call (index_commit_interval_us)
+    bool committed_once = false;
     bool general = false;           // a profile configures the prefix-cache-affinity-filter or pick_k > 1: every batch takes
                                     // the dense-counter kernel with the full-scan evaluation of pick_general.cuh
     const epp_topk_out *cur_topk = nullptr;   // top-k destination of the call in progress (under mu)
@@ -253,6 +255,7 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
         if (cfg->handler != EPP_HANDLER_DISAGG) return fail(EPP_ERR_INVALID, "encode_enabled needs the disagg handler");
         EPP_TRY(validate_profile(cfg->encode, cfg->n_ext_cols, "encode profile"));
     }
+    if (cfg->index_commit_interval_us < 0) return fail(EPP_ERR_INVALID, "index_commit_interval_us must be >= 0");
     if (cfg->pick_k < 0 || cfg->pick_k > 64) return fail(EPP_ERR_INVALID, "pick_k %d out of range [0,64]", cfg->pick_k);
 
     int ndev = 0;
@@ -1196,7 +1199,16 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
     if (R == 0) return EPP_OK;
     if (mode != Mode::HashOnly) {
         if (!h->pool_ready) return fail(EPP_ERR_STATE, "epp_pool_set has not been called");
-        EPP_TRY(commit_locked(h));
+        // index updates become visible here -- or, with index_commit_interval_us, at most that much later: the reference
+        // applies PreRequest in a goroutine of its own "to avoid blocking the request path" (approximateprefix/plugin.go:189-194),
+        // so a scheduling cycle may well run against an index that lacks the last few picks
+        const bool due = h->cfg.index_commit_interval_us <= 0 || !h->committed_once ||
+                         ms_since(h->last_commit) * 1000.0 >= (double)h->cfg.index_commit_interval_us;
+        if (due) {
+            EPP_TRY(commit_locked(h));
+            h->last_commit = std::chrono::steady_clock::now();
+            h->committed_once = true;
+        }
     }
     if (h->async_pending && !(v.device && v.async)) EPP_TRY(finish_async(h));
     // top-k lists of the call in progress: the caller's device arrays, or device staging for a host batch

@@ -89,7 +89,8 @@ class Engine:
     def __init__(self, max_endpoints: int, primary: ProfileSpec | None = None, prefill: ProfileSpec | None = None,
                  *, device: int = 0, block_size_tokens: int = 16, max_prefix_blocks: int = 256,
                  lru_capacity_per_server: int = 31250, non_cached_tokens: int = 0, always_disagg: bool = False,
-                 n_ext_cols: int = 0, tie_seed: int = 0, encode: ProfileSpec | None = None, pick_k: int = 0):
+                 n_ext_cols: int = 0, tie_seed: int = 0, encode: ProfileSpec | None = None, pick_k: int = 0,
+                 index_commit_interval_us: int = 0):
         self._lib = capi.load()
         cfg = capi.Config()
         self._lib.epp_config_default(C.byref(cfg))
@@ -111,6 +112,7 @@ class Engine:
             _fill_profile(cfg.encode, encode)
         cfg.tie_seed = tie_seed
         cfg.pick_k = pick_k
+        cfg.index_commit_interval_us = index_commit_interval_us
         self.cfg = cfg
         self.E = max_endpoints
         self.B = max_prefix_blocks

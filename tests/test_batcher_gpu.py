@@ -64,7 +64,7 @@ def test_64_threads_one_request_each_vs_oracle(epp, orc, tg):
 
 def test_submit_many_then_wait_and_ticket_rules(epp, orc, tg):
     """submit() returns at once; tickets of one thread come back in order; full batches flush without waiting for the
-    delay; a ticket is good for one wait; prompts longer than the hashed prefix keep their true length for the P/D
+    delay; a ticket can be waited for again; prompts longer than the hashed prefix keep their true length for the P/D
     decider (EPP_BATCH_LENGTHS_EXCEED_ROWS)."""
     import helpers
     w = tg.baseline_configs()["config4"].scaled(E=96, R=512, T=256, name="config4")
@@ -85,8 +85,8 @@ def test_submit_many_then_wait_and_ticket_rules(epp, orc, tg):
             gdet = np.zeros(w.R, dtype=epp.DETAIL_DTYPE)
             for r in reversed(range(w.R)):               # any order
                 got[r], gdet[r] = bt.wait(tickets[r])
-            with pytest.raises(epp.EngineError):
-                bt.wait(tickets[0])                      # a ticket is good for one wait
+            again, _ = bt.wait(tickets[0])               # a ticket stays good until 4096 later batches were flushed
+            assert again == got[0]
             with pytest.raises(epp.EngineError):
                 bt.wait(tickets[-1] + 7)                 # never issued
             st = bt.stats()

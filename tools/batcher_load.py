@@ -44,6 +44,8 @@ def main():
     ap.add_argument("--prompts", type=int, default=8192)
     ap.add_argument("--index-picks", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true")
+    ap.add_argument("--commit-us", type=int, default=0, help="epp_config.index_commit_interval_us")
+    ap.add_argument("--tie-seed", type=int, default=0, help="epp_config.tie_seed (non-zero: random member of the arg-max set)")
     args = ap.parse_args()
     import bench
     import epp_b200 as epp
@@ -58,7 +60,7 @@ def main():
     trace = tg.Trace(w)
     tokens, _, _ = trace.requests()
     prompts = np.ascontiguousarray(tokens).view(np.uint8).reshape(-1)
-    with helpers.make_engine(w) as eng:
+    with helpers.make_engine(w, index_commit_interval_us=args.commit_us, tie_seed=args.tie_seed) as eng:
         if args.index_picks:                      # PreRequest needs an incrementally built index: start empty, the picks fill it
             eng.register_model(tg.MODEL)
             role, kv, waiting, running = trace.pool()
@@ -83,9 +85,10 @@ def main():
                                   "engine_message": (lib.epp_last_error() or b"").decode()}), flush=True)
                 continue
             seen = picks["total_blocks"] > 0
-            same = bool((picks[seen] == want[seen]).all()) if not args.index_picks else None
+            same = bool((picks[seen] == want[seen]).all()) if not (args.index_picks or args.tie_seed) else None
             print(json.dumps({"threads": nt, "seconds": args.seconds, "max_batch": args.max_batch, "max_delay_us": args.delay_us,
-                              "index_picks": bool(args.index_picks), "errors": int(err),
+                              "index_picks": bool(args.index_picks), "index_commit_interval_us": args.commit_us, "tie_seed": args.tie_seed, "errors": int(err),
+                              "index_errors": int(st["n_index_errors"]),
                               "decisions_per_s": float(done.sum() / args.seconds),
                               "latency_us": {"p50": float(np.percentile(l, 50)), "p90": float(np.percentile(l, 90)),
                                              "p99": float(np.percentile(l, 99)), "mean": float(l.mean())},
