@@ -1167,7 +1167,7 @@ static int32_t run_small(epp_engine *h, const BatchView &v, int mode, const uint
         }
     }
     if (overflowed) {
-        // > 48 endpoints hold a part of some prompt: those requests go through the dense-counter kernel, then the whole
+        // > 32 endpoints hold a part of some prompt: those requests go through the dense-counter kernel, then the whole
         // batch is read back the ordinary way
         Slot &sl = h->slot[0];
         PickParams po = pp;

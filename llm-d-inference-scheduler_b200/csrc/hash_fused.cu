@@ -1,6 +1,7 @@
 // hash_fused.cu -- a1 (hashPrompt, approximateprefix/hashing.go:35-99) as one CTA-cooperative kernel with register-fed
-// 128/256-bit global loads: the path for block sizes other than 64 bytes (any multiple of 32 bytes, 16-byte aligned
-// prompts) and the A/B reference of hash_staged.cu (EPP_HASH_STAGED=-1).
+// 128/256-bit global loads: the DEFAULT hash kernel of the throughput path (block sizes that are a multiple of 32
+// bytes, 16-byte aligned prompts; everything else takes the generic kernels of hash_kernels.cu).  hash_staged.cu is the
+// cp.async-staged alternative behind EPP_HASH_STAGED=1 (measured slower).
 //
 // HBM traffic per request: every prompt byte is read exactly once, the 8-byte pre-chain digests never leave the SM
 // (shared-memory ring), the block hashes are written once (the PluginState stash PreRequest needs, plugin.go:150-157).

@@ -161,10 +161,10 @@ struct PickParams {
     const uint32_t *global_masks;       // [R][mask_words]
     int32_t mask_words;
     epp_shard_best *shard_out;          // [R] local best record instead of `out`
-    // v1 kernel only: process the requests listed in req_list[0 .. *req_list_n) (the sparse kernel's overflows)
+    // dense-counter kernel (k_match_pick) only: process the requests listed in req_list[0 .. *req_list_n) (the sparse kernel's overflows)
     const int32_t *req_list;
     const int32_t *req_list_n;
-    // v2 (sparse) kernel only: requests whose matched-endpoint set overflowed the per-warp map are appended here
+    // sparse kernels only: requests whose matched-endpoint set overflowed the per-warp map are appended here
     int32_t *overflow_list;
     int32_t *overflow_n;
     // tie rule: 0 = lowest slot of the arg-max set; else the member of rank tie_rank(seed, 4 * (tie_base + r) + profile)
@@ -179,8 +179,8 @@ size_t match_pick_smem_bytes(int32_t E, bool global_counts);
 int match_pick_warps_per_cta();
 cudaError_t launch_match_pick(const PickParams &p, uint32_t *gscratch, int grid, size_t smem, cudaStream_t s,
                               int *launches);
-// v2: the same decision per request with a per-warp sparse endpoint map (48 matched endpoints max; requests that
-// overflow are appended to p.overflow_list for the v1 kernel).  16 warps per CTA, high occupancy.
+// The same decision per request with a lane-distributed register map of the matched endpoints (requests whose set
+// overflows it are appended to p.overflow_list for the dense-counter kernel).  8 warps per CTA, 6-8 CTAs per SM.
 cudaError_t launch_match_pick_sparse(const PickParams &p, int sm_count, cudaStream_t s, int *launches);
 // cycle_small.cu: a1-a14 of a small host batch in ONE launch, one CTA per request, prompts read from and decisions
 // written to PINNED HOST memory (zero-copy); flags[r] = epoch (| 0x80000000 when the request overflowed the sparse map and

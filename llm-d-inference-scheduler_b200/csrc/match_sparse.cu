@@ -1,5 +1,5 @@
-// match_sparse.cu -- a2-a14 as a STANDALONE kernel over precomputed hashes (plugin-parity modes, endpoint-sharded
-// mode, generic-hash-path batches): one warp per request, the per-request work is match_sparse.cuh.
+// match_sparse.cu -- a2-a14 over the hash rows of a batch: the match / score / pick kernel of the throughput path (and of
+// the endpoint-sharded mode): one warp per request, the per-request work is match_sparse.cuh.
 #include <cstdlib>
 
 #include "match_sparse.cuh"

@@ -3,8 +3,9 @@
 // (scheduler_profile.go:151-174), arg-max pick (maxscore/picker.go:87-115) and the decode -> decider -> prefill second
 // stage (disagg_profile_handler.go:264-308).  No shared memory, no atomics on the common path.
 //
-// Shared by the standalone kernel (match_sparse.cu: plugin-parity, sharded and generic-hash batches) and by the match
-// warps of the fused cycle kernel (cycle.cu), which run it on the tile their CTA hashed just before.
+// Shared by the throughput kernel (match_sparse.cu: one warp per request over the hash rows of a whole batch, incl. the
+// endpoint-sharded variant) and by the latency kernel (cycle_small.cu: one warp of the request's CTA follows the hash
+// chain as it is produced).
 //
 //   * 32 blocks are probed per step, one 256-bit load per 32-byte slot.  Probe chains are followed only as far as the
 //     stop rule needs them: once a lane has proven its block absent, the lanes behind it (which cannot change the walk)
@@ -16,7 +17,7 @@
 //     k_patch_apply), so "same endpoint set" is equality of the six words (cnt, ids[0..4]); the blocks of one cached
 //     prefix form a few runs of identical sets and a run adds its length to each of its endpoints.
 //
-// Exactness: a request whose matched-endpoint set exceeds 32 distinct endpoints is appended to
+// Exactness: a request whose matched-endpoint set exceeds the map's capacity is appended to
 // PickParams::overflow_list and handled by the dense-counter kernel (pick_kernels.cu), never approximated.
 #pragma once
 #include "index.cuh"

@@ -492,17 +492,13 @@ def test_async_device_batches_match_synchronous_ones(epp, orc, tg):
             eng.schedule(tokens[:8], uniform_len=w.prompt_bytes, asynchronous=True)      # host buffers cannot be async
 
 
-@pytest.mark.parametrize("mode", ["cross-batch", "chunks"])
-def test_async_chunk_pipelined_batches(epp, orc, tg, monkeypatch, mode):
-    """The two throughput modes of async device batches must produce exactly the synchronous single-pass decisions:
-    cross-batch (default: batch N hashed on stream 0 into buffer set N % 2 and matched on stream 1, so the hash kernel
-    of batch N+1 overlaps the match kernel of batch N) and EPP_DEV_CHUNKS (one batch split into chunks that alternate
-    between the two streams, ragged tail chunk included)."""
+@pytest.mark.parametrize("chunks", [2, 4])
+def test_async_chunk_pipelined_batches(epp, orc, tg, monkeypatch, chunks):
+    """Async device batches run as EPP_DEV_CHUNKS chunks alternating between the engine's two streams (default 2; ragged
+    tail chunk included) and must produce exactly the synchronous single-pass decisions."""
     import torch
     import helpers
-    if mode == "chunks":
-        monkeypatch.setenv("EPP_XBATCH", "0")
-        monkeypatch.setenv("EPP_DEV_CHUNKS", "4")
+    monkeypatch.setenv("EPP_DEV_CHUNKS", str(chunks))
     w = tg.baseline_configs()["config4"].scaled(E=192, R=20000 + 37, T=512, name="config4")
     w.non_cached_tokens = 64
     trace = tg.Trace(w)
@@ -519,7 +515,7 @@ def test_async_chunk_pipelined_batches(epp, orc, tg, monkeypatch, mode):
         eng.synchronize()
         np.testing.assert_array_equal(epp.decisions_from_torch(out), want)
         assert (want["prefill_pick"] != 0xFFFFFFFF).any()
-        assert eng.stats()["last_kernel_launches"] >= (8 if mode == "chunks" else 2)
+        assert eng.stats()["last_kernel_launches"] >= 2 * chunks
         # different batches back to back (each buffer set is reused only after its match kernel has finished), then a
         # kept batch: PreRequest must index the hashes of the LAST batch
         outs = [torch.zeros((w.R, 32), dtype=torch.uint8, device="cuda") for _ in range(4)]
@@ -728,7 +724,7 @@ def test_small_batch_zero_copy_path_vs_oracle(epp, orc, tie_seed, monkeypatch):
     """Host batches of 1 .. 600 requests whose prompts live in pinned memory take the single-launch path of
     csrc/cycle_small.cu (one CTA per request, prompts read over PCIe, decisions written to pinned memory, no copy
     engine): ragged prompts incl. empty / shorter than a block / partial trailing block / longer than the cap, P/D and
-    encode stages, > 48 holders (dense-counter pass), both tie rules -- all equal to the oracle and to the ordinary
+    encode stages, > 32 holders (dense-counter pass), both tie rules -- all equal to the oracle and to the ordinary
     path (EPP_SMALL_BATCH=0)."""
     import helpers
     E, bst, B = 96, 8, 24                          # 32-byte blocks
