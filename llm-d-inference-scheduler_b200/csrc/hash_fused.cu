@@ -62,30 +62,32 @@ __device__ __forceinline__ void tile_lengths(const HashParams &p, int64_t r0, in
     if (t == 0) *s_maxfull = mx;
 }
 
-// Chain warp, one window: the serial part of the digest for 32 requests at once, in place, then the 8 hashes of
-// each request written as one 64-byte segment.
+// Chain warp, one window: the serial part of the digest for 32 requests at once (lane = request); every lane then
+// writes its request's 8 hashes straight from registers (64 bytes = two full sectors per lane, 128-bit stores when the
+// row pitch allows) -- no transpose through shared memory.
 template <int TR, int W = kWin>
 __device__ __forceinline__ uint64_t chain_window(uint64_t (*sm)[W + 1], const int32_t *s_nfull, const HashParams &p,
                                                  int64_t r0, int k, int lane, int32_t nfull, uint64_t lenp8,
                                                  uint64_t prev) {
-    if (lane < TR) {
+    (void)s_nfull;
+    const int32_t n_here = min(W, nfull - k * W);              // hashes of this window for my request (<= 0: none)
+    if (lane >= TR || n_here <= 0) return prev;
+    uint64_t hv[W];
 #pragma unroll
-        for (int j = 0; j < W; j++) {
-            if (k * W + j < nfull) {
-                prev = xxh_chain_step32(sm[lane][j], lenp8, prev);
-                sm[lane][j] = prev;
-            }
-        }
+    for (int j = 0; j < W; j++) {
+        if (j < n_here) prev = xxh_chain_step32(sm[lane][j], lenp8, prev);
+        hv[j] = prev;
     }
-    __syncwarp();
-    constexpr int kRows = 32 / W;                 // request rows written per warp instruction
+    uint64_t *dst = p.hashes + (r0 + lane) * (int64_t)p.max_blocks + (int64_t)k * W;
+    if (n_here == W && !(p.max_blocks & 1) && !(reinterpret_cast<uintptr_t>(p.hashes) & 15)) {   // the window starts 16-byte aligned
 #pragma unroll
-    for (int it = 0; it < TR / kRows; it++) {
-        int rr = it * kRows + lane / W, jj = lane % W;
-        int b = k * W + jj;
-        if (b < s_nfull[rr]) p.hashes[(r0 + rr) * (int64_t)p.max_blocks + b] = sm[rr][jj];
+        for (int j = 0; j < W; j += 2)
+            asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + j), "l"(hv[j]), "l"(hv[j + 1]) : "memory");
+    } else {
+#pragma unroll
+        for (int j = 0; j < W; j++)
+            if (j < n_here) dst[j] = hv[j];
     }
-    __syncwarp();
     return prev;
 }
 }  // namespace
