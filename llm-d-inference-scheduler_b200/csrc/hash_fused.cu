@@ -119,14 +119,14 @@ __global__ void __launch_bounds__(32 * kWin + 32, kHashMinCtas) k_hash_fused(Has
         if (warp < kDigestWarps) {
             const int r = t / W, j = t % W;
             const int32_t nfull = s_nfull[r];
-            const uint8_t *base = p.data + s_off[r] + (uint64_t)j * (uint64_t)bs;
-            for (int k = 0; k < n_win; k++) {
+            const uint8_t *src = p.data + s_off[r] + (uint64_t)j * (uint64_t)bs;     // block j of window 0; + W blocks per window
+            const uint64_t win_bytes = (uint64_t)W * (uint64_t)bs;
+            int32_t left = nfull - j;                                            // > 0: my block of this window is a full one
+            for (int k = 0; k < n_win; k++, src += win_bytes, left -= W) {
                 const int s = k % kStages;
                 if (k >= kStages) bar_sync(kBarEmpty + s, kProducers);
-                if (k * W + j < nfull)
-                    s_m[s][r][j] = block_digest<kAlign32>(base + (uint64_t)k * (uint64_t)(W * bs), n_stripes);
-                __threadfence_block();
-                bar_arrive(kBarFull + s, kProducers);
+                if (left > 0) s_m[s][r][j] = block_digest<kAlign32>(src, n_stripes);
+                bar_arrive(kBarFull + s, kProducers);     // bar.arrive orders the store above for the threads of the barrier
             }
             const int first = n_win > kStages ? n_win - kStages : 0;
             for (int k = first; k < n_win; k++) bar_sync(kBarEmpty + (k % kStages), kProducers);
