@@ -496,41 +496,118 @@ __global__ void k_evict_finish(View v) {
     }
 }
 
-// In-place compaction of one endpoint's log window to the start of its segment (keeps order; writes trail reads).
-// Runs for the endpoints whose segment cannot take the batch's appends; if that is still not enough the host
-// re-allocates every segment (k_store_repack).
-__global__ void k_store_compact(View v) {
+// Log compaction for endpoints whose segment cannot take the batch's entries (head + inc > cap): the LIVE entries of
+// [tail, head) move, in order, to the front of the segment.  The logs are append-only (a re-Add of a cached pair appends
+// a new entry and kills the old one), and one skewed batch can hand millions of entries to ONE endpoint, so the walk is a
+// flat space of 256-entry blocks spread over the whole grid, like the eviction (k_evict_*): list the endpoints and their
+// block ranges -> per block: liveness mask + count -> per endpoint: exclusive scan of the counts -> per block: scatter
+// into the spare log buffers -> copy the compacted prefix back -> new head / tail.  If the segment is still too small
+// the whole log space is re-allocated afterwards (k_store_repack).
+__device__ __forceinline__ bool needs_compaction(const View &v, uint32_t e) {
+    const unsigned long long inc = v.inc[e];
+    return inc != 0 && v.head[e] + inc > v.seg_cap[e];
+}
+__global__ void k_compact_list(View v, uint32_t *list_e, unsigned long long *list_start) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= v.E || !needs_compaction(v, e)) return;
+    const unsigned long long tail = v.tail[e], head = v.head[e];
+    const unsigned long long nb = (head + kEvictBlock - 1) / kEvictBlock - tail / kEvictBlock;
+    const unsigned long long old = atomicAdd(&v.ctr[kCtrEvict], (1ull << kEvictPackShift) | nb);
+    list_e[old >> kEvictPackShift] = e;
+    list_start[old >> kEvictPackShift] = old & ((1ull << kEvictPackShift) - 1);
+}
+// blockcnt[b] = live entries of block b, blockmask[8 b + w] = liveness of its entries 32 w .. 32 w + 31.
+__global__ void __launch_bounds__(kEvictBlock) k_compact_count(View v, const uint32_t *list_e, const unsigned long long *list_start,
+                                                                uint32_t *blockcnt, uint32_t *blockmask) {
+    const unsigned long long packed = v.ctr[kCtrEvict];
+    const uint32_t n = (uint32_t)(packed >> kEvictPackShift);
+    const unsigned long long total = packed & ((1ull << kEvictPackShift) - 1);
+    for (unsigned long long g = blockIdx.x; g < total; g += gridDim.x) {
+        uint32_t e;
+        unsigned long long b;
+        evict_locate(v, list_e, list_start, n, g, e, b);
+        const unsigned long long seg = v.seg_off[e], tail = v.tail[e], head = v.head[e];
+        const unsigned long long idx = b * kEvictBlock + threadIdx.x;
+        bool is_live = false, leak;
+        EntryRef r;
+        if (idx >= tail && idx < head) is_live = log_entry_live(v, e, seg + idx, r, leak);
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, is_live);
+        if ((threadIdx.x & 31) == 0) blockmask[(seg / kEvictBlock + b) * (kEvictBlock / 32) + (threadIdx.x >> 5)] = m;
+        const int cnt = __syncthreads_count(is_live);
+        if (threadIdx.x == 0) blockcnt[seg / kEvictBlock + b] = (uint32_t)cnt;
+    }
+}
+// Per compacted endpoint: blockcnt -> exclusive prefix (position of the block's first live entry in the compacted log);
+// new_head[e] = number of live entries.
+__global__ void k_compact_scan(View v, uint32_t *blockcnt, unsigned long long *new_head) {
     const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < v.E; e += warps) {
-        const unsigned long long inc = v.inc[e], head = v.head[e], cap = v.seg_cap[e], seg = v.seg_off[e];
-        if (inc == 0 || head + inc <= cap) continue;
-        unsigned long long w = 0;
-        for (unsigned long long pos = v.tail[e]; pos < head; pos += 32) {
-            const unsigned long long idx = pos + lane;
-            bool is_live = false, leak;
-            unsigned long long hsh = 0, sq = 0;
-            if (idx < head) {
-                hsh = v.log_hash[seg + idx];
-                sq = v.log_seq[seg + idx];
-                EntryRef r;
-                is_live = log_entry_live(v, e, seg + idx, r, leak);
+        if (!needs_compaction(v, e)) continue;
+        const unsigned long long seg = v.seg_off[e], tail = v.tail[e], head = v.head[e];
+        const unsigned long long b0 = tail / kEvictBlock, b1 = (head + kEvictBlock - 1) / kEvictBlock;
+        uint32_t *bc = blockcnt + seg / kEvictBlock;
+        unsigned long long run = 0;
+        for (unsigned long long b = b0; b < b1; b += 32) {
+            const uint32_t c = b + lane < b1 ? bc[b + lane] : 0u;
+            uint32_t incl = c;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if ((int)lane >= o) incl += t;
             }
-            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, is_live);
-            __syncwarp();
-            if (is_live) {
-                const unsigned long long at = seg + w + __popc(ballot & ((1u << lane) - 1u));
-                v.log_hash[at] = hsh;
-                v.log_seq[at] = sq;
-            }
-            __syncwarp();
-            w += __popc(ballot);
+            if (b + lane < b1) bc[b + lane] = (uint32_t)(run + incl - c);      // fits: a segment holds < 2^32 entries
+            run += __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
-        if (lane == 0) {
-            v.head[e] = w;
-            v.tail[e] = 0;
-            if (w + inc > cap) atomicOr(&v.ctr[kCtrNeedRepack], 1ull);
-        }
+        if (lane == 0) new_head[e] = run;
     }
+}
+__global__ void __launch_bounds__(kEvictBlock) k_compact_scatter(View v, const uint32_t *list_e, const unsigned long long *list_start,
+                                                                  const uint32_t *blockoff, const uint32_t *blockmask,
+                                                                  unsigned long long *spare_hash, unsigned long long *spare_seq) {
+    const unsigned long long packed = v.ctr[kCtrEvict];
+    const uint32_t n = (uint32_t)(packed >> kEvictPackShift);
+    const unsigned long long total = packed & ((1ull << kEvictPackShift) - 1);
+    const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (unsigned long long g = blockIdx.x; g < total; g += gridDim.x) {
+        uint32_t e;
+        unsigned long long b;
+        evict_locate(v, list_e, list_start, n, g, e, b);
+        const unsigned long long seg = v.seg_off[e];
+        const uint32_t *bm = blockmask + (seg / kEvictBlock + b) * (kEvictBlock / 32);
+        const uint32_t mine = bm[w];
+        if (!((mine >> lane) & 1u)) continue;
+        uint32_t rank = __popc(mine & ((1u << lane) - 1u));
+        for (uint32_t k = 0; k < w; k++) rank += __popc(bm[k]);
+        const unsigned long long src = seg + b * kEvictBlock + threadIdx.x, dst = seg + blockoff[seg / kEvictBlock + b] + rank;
+        spare_hash[dst] = v.log_hash[src];
+        spare_seq[dst] = v.log_seq[src];
+    }
+}
+// The compacted prefix [0, new_head) back into the log (the flat block space of the OLD range covers it).
+__global__ void __launch_bounds__(kEvictBlock) k_compact_copyback(View v, const uint32_t *list_e, const unsigned long long *list_start,
+                                                                   const unsigned long long *new_head,
+                                                                   const unsigned long long *spare_hash, const unsigned long long *spare_seq) {
+    const unsigned long long packed = v.ctr[kCtrEvict];
+    const uint32_t n = (uint32_t)(packed >> kEvictPackShift);
+    const unsigned long long total = packed & ((1ull << kEvictPackShift) - 1);
+    for (unsigned long long g = blockIdx.x; g < total; g += gridDim.x) {
+        uint32_t e;
+        unsigned long long b;
+        evict_locate(v, list_e, list_start, n, g, e, b);
+        const unsigned long long idx = (b - v.tail[e] / kEvictBlock) * kEvictBlock + threadIdx.x;
+        if (idx >= new_head[e]) continue;
+        const unsigned long long at = v.seg_off[e] + idx;
+        v.log_hash[at] = spare_hash[at];
+        v.log_seq[at] = spare_seq[at];
+    }
+}
+__global__ void k_compact_finish(View v, const unsigned long long *new_head) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= v.E || !needs_compaction(v, e)) return;
+    const unsigned long long w = new_head[e];
+    const bool still_short = w + v.inc[e] > v.seg_cap[e];
+    v.head[e] = w;
+    v.tail[e] = 0;
+    if (still_short) atomicOr(&v.ctr[kCtrNeedRepack], 1ull);
 }
 
 // RemovePod (indexer.go:167-182): every key of the endpoint's LRU goes through the eviction callback, the LRU is
@@ -1065,11 +1142,36 @@ cudaError_t IndexStore::apply(const StoreCalls &calls, cudaStream_t s) {
     k_store_hist<<<blocks_for(M, 256), 256, 0, s>>>(v, M, calls.ep, calls.n, hist);
     k_store_plan<<<blocks_for(E_, 128), 128, 0, s>>>(v, n_chunks, hist, calls.nb);
     tm.mark("plan");
-    k_store_compact<<<blocks_for((uint64_t)E_ * 32, 256), 256, 0, s>>>(v);
-    tm.mark("compact");
+    // log compaction (flat over 256-entry blocks): list the endpoints whose segment cannot take the batch; the read-back
+    // below (needed anyway for the table sizes) tells whether there is anything to compact
+    ST_TRY(list_e_.reserve(sizeof(uint32_t) * E_, &bytes_));
+    ST_TRY(list_start_.reserve(sizeof(unsigned long long) * E_, &bytes_));
+    ST_TRY(cudaMemsetAsync(&v.ctr[kCtrEvict], 0, sizeof(unsigned long long), s));
+    k_compact_list<<<blocks_for(E_, 256), 256, 0, s>>>(v, list_e_.as<uint32_t>(), list_start_.as<unsigned long long>());
     ST_TRY(cudaMemcpyAsync(ctr_host_, v.ctr, sizeof(unsigned long long) * kCtrN, cudaMemcpyDeviceToHost, s));
     ST_TRY(cudaStreamSynchronize(s));
     last_launches += 4;
+    if (ctr_host_[kCtrEvict] >> kEvictPackShift) {                 // endpoints listed (a brand-new one lists zero blocks)
+        ST_TRY(blockcnt_.reserve(sizeof(uint32_t) * (log_cap_ / kEvictBlock + 1), &bytes_));
+        ST_TRY(blockmask_.reserve(sizeof(uint32_t) * (log_cap_ / kEvictBlock + 1) * (kEvictBlock / 32), &bytes_));
+        ST_TRY(log_hash_spare_.reserve(sizeof(unsigned long long) * std::max<uint64_t>(log_cap_, 64), &bytes_));
+        ST_TRY(log_seq_spare_.reserve(sizeof(unsigned long long) * std::max<uint64_t>(log_cap_, 64), &bytes_));
+        const unsigned cg = 148 * 8;
+        unsigned long long *nh = new_off_.as<unsigned long long>();          // scratch until repack_logs rewrites it
+        k_compact_count<<<cg, kEvictBlock, 0, s>>>(v, list_e_.as<uint32_t>(), list_start_.as<unsigned long long>(),
+                                                   blockcnt_.as<uint32_t>(), blockmask_.as<uint32_t>());
+        k_compact_scan<<<blocks_for((uint64_t)E_ * 32, 256), 256, 0, s>>>(v, blockcnt_.as<uint32_t>(), nh);
+        k_compact_scatter<<<cg, kEvictBlock, 0, s>>>(v, list_e_.as<uint32_t>(), list_start_.as<unsigned long long>(),
+                                                     blockcnt_.as<uint32_t>(), blockmask_.as<uint32_t>(),
+                                                     log_hash_spare_.as<unsigned long long>(), log_seq_spare_.as<unsigned long long>());
+        k_compact_copyback<<<cg, kEvictBlock, 0, s>>>(v, list_e_.as<uint32_t>(), list_start_.as<unsigned long long>(), nh,
+                                                      log_hash_spare_.as<unsigned long long>(), log_seq_spare_.as<unsigned long long>());
+        k_compact_finish<<<blocks_for(E_, 256), 256, 0, s>>>(v, nh);
+        ST_TRY(cudaMemcpyAsync(ctr_host_, v.ctr, sizeof(unsigned long long) * kCtrN, cudaMemcpyDeviceToHost, s));
+        ST_TRY(cudaStreamSynchronize(s));
+        last_launches += 5;
+    }
+    tm.mark("compact");
     const uint64_t total = ctr_host_[kCtrTotalItems];
     last_items = total;
     pt_used_ = ctr_host_[kCtrPtUsed];

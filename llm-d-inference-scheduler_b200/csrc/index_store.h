@@ -104,7 +104,7 @@ class IndexStore {
     DevBuf pt_spare_, log_hash_spare_, log_seq_spare_;   // the previous generation of the three big buffers: rehash / repack
                                                           // ping-pong between the pairs instead of cudaMalloc + cudaFree
     DevBuf cap_, live_, firstcall_, seg_off_, seg_cap_, head_, tail_, inc_, next_seq_, sp_seq_, sp_in_map_, ctr_;
-    DevBuf hist_, off_, new_off_, new_cap_, cut_, blockcnt_, list_e_, list_start_;
+    DevBuf hist_, off_, new_off_, new_cap_, cut_, blockcnt_, blockmask_, list_e_, list_start_;
     // touch log + scratch of patch_read_table
     DevBuf touch_hash_, touch_ep_, patch_next_, patch_dirty_;
     uint64_t touch_cap_ = 0, touch_upper_ = 0;      // allocated entries; host upper bound of the entries logged so far
