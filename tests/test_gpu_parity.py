@@ -805,6 +805,30 @@ def test_small_batch_zero_copy_path_vs_oracle(epp, orc, tie_seed, monkeypatch):
         np.testing.assert_array_equal(ad, bd)
 
 
+def test_index_commit_interval_bounds_the_staleness(epp, orc):
+    """epp_config.index_commit_interval_us: with a long interval a scheduling call keeps reading the table of the last
+    commit (the reference applies PreRequest in a goroutine of its own, approximateprefix/plugin.go:189-194), an
+    explicit epp_index_commit makes the picks visible at once; with interval 0 the next call sees them."""
+    E, bst, B = 16, 8, 8
+    rng = np.random.default_rng(5)
+    prompts = [bytes(rng.integers(0, 256, 4 * bst * B, dtype=np.uint8)) for _ in range(40)]
+    d, offs = _pack(prompts)
+    for interval, stale in ((10_000_000, True), (0, False)):
+        with epp.Engine(E, epp.ProfileSpec(0, [epp.ScorerSpec(0, 1.0)]), block_size_tokens=bst, max_prefix_blocks=B,
+                        index_commit_interval_us=interval) as eng:
+            eng.register_model(b"m")
+            eng.pool_set(np.arange(E), np.zeros(E, np.uint8), np.zeros(E), np.zeros(E, np.int32))
+            dec0, _ = eng.schedule(d, offsets=offs, keep_hashes=True)          # first call: commits (nothing to commit)
+            assert (dec0["match_blocks"] == 0).all()
+            eng.index_add_picked()
+            dec1, _ = eng.schedule(d, offsets=offs)
+            if stale:
+                np.testing.assert_array_equal(dec1, dec0)                       # the picks are not visible yet
+                eng.index_commit()
+                dec1, _ = eng.schedule(d, offsets=offs)
+            assert (dec1["match_blocks"] == B).all() and (dec1["pick"] == dec0["pick"]).all()
+
+
 def test_large_pool_global_counters(epp, orc, tg):
     """E too large for per-warp shared-memory counters -> zeroed global scratch path (config-5-sized pool on 1 GPU)."""
     import helpers
