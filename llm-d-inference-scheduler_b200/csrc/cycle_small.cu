@@ -140,12 +140,14 @@ cudaError_t launch_cycle_small(const HashParams &hp, const PickParams &pp, const
                                int *launches) {
     if (hp.R <= 0) return cudaSuccess;
     const size_t smem = sizeof(uint64_t) * (size_t)hp.max_blocks;
-    static bool attr_set = false;
-    if (!attr_set) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool attr_set[64] = {};                 // function attributes are per device: engines of one process may sit on several GPUs
+    if (!attr_set[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(k_cycle_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cycle_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_set[dev & 63] = true;
     }
     if (align >= 32) k_cycle_small<true><<<(unsigned)hp.R, kThreads, smem, s>>>(hp, pp, so);
     else k_cycle_small<false><<<(unsigned)hp.R, kThreads, smem, s>>>(hp, pp, so);

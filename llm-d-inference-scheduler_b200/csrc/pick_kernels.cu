@@ -401,11 +401,13 @@ int match_pick_warps_per_cta() { return kPickWarps; }
 
 cudaError_t launch_match_pick(const PickParams &p, uint32_t *gscratch, int grid, size_t smem, cudaStream_t s,
                                   int *launches) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool attr_set[64] = {};                 // function attributes are per device: engines of one process may sit on several GPUs
+    if (!attr_set[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(k_match_pick, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_set[dev & 63] = true;
     }
     int32_t cnt_words = (p.E + 1) / 2;
     k_match_pick<<<grid, kPickWarps * 32, smem, s>>>(p, cnt_words, gscratch);

@@ -444,3 +444,45 @@ def test_sharded_two_gpus_nccl(orc):
     d1 = np.frombuffer(res[1], dtype=epp.DECISION_DTYPE)
     np.testing.assert_array_equal(d0, d1)
     helpers.assert_decisions_equal(d0, None, odec, ototal, where="sharded nccl x2")
+
+
+@pytest.mark.gpu
+def test_two_engines_on_two_devices_in_one_process(orc):
+    """Replicas inside ONE process (what the Go shim does: one engine per GPU): per-device state of the launchers
+    (occupancy caches, opt-in shared-memory attributes of the dense-counter and the small-batch kernel) must not leak
+    from device 0 to device 1.  Host batches (single-launch path), device batches (throughput kernels) and the
+    dense-counter kernel (Produce rows) on both devices, decisions equal to the oracle's."""
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import epp_b200 as epp
+    import helpers
+    from tools import tracegen as tg
+    tg.build()
+    w = tg.baseline_configs()["config3"].scaled(E=4096, R=2048, T=1024, name="config3")
+    trace = tg.Trace(w)
+    tokens, _, _ = trace.requests()
+    pool, ix, primary, prefill, _ = helpers.setup_oracle(orc, w, trace)
+    odec, ototal = helpers.oracle_decisions(orc, w, pool, ix, primary, prefill, tokens)
+    engines = []
+    try:
+        for dev in (0, 1):
+            eng = helpers.make_engine(w, device=dev)
+            helpers.setup_engine(eng, w, trace)
+            engines.append(eng)
+        for dev, eng in enumerate(engines):
+            dec, det = eng.schedule(tokens[:512], uniform_len=w.prompt_bytes)                 # one launch: k_cycle_small
+            helpers.assert_decisions_equal(dec, det, odec[:512], ototal[:512], where=f"device {dev}, small host batch")
+            dec, det = eng.schedule(tokens, uniform_len=w.prompt_bytes)                       # chunked host path
+            helpers.assert_decisions_equal(dec, det, odec, ototal, where=f"device {dev}, host batch")
+            with torch.cuda.device(dev):
+                dt = torch.from_numpy(tokens.view(np.int32)).to(f"cuda:{dev}")
+                ddec, ddet = eng.schedule(dt, uniform_len=w.prompt_bytes)
+                torch.cuda.synchronize(dev)
+                helpers.assert_decisions_equal(epp.decisions_from_torch(ddec), None, odec, ototal, where=f"device {dev}, device batch")
+            match, total = eng.prefix_match(tokens[:64], uniform_len=w.prompt_bytes)          # dense-counter kernel, 69 KiB of smem
+            np.testing.assert_array_equal(total, ototal[:64])
+            assert (match.max(axis=1) >= 0).all()
+    finally:
+        for e in engines:
+            e.close()
