@@ -1290,7 +1290,8 @@ static int32_t run_batch(epp_engine *h, const BatchView &v, Mode mode, uint64_t 
         CUDA_TRY(cudaMemcpyAsync(h->wc_host, h->work_counters.p, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, s0));
         h->async_pending = true;
         h->async_launches = launches;
-        if (v.async && mode == Mode::Schedule) return EPP_OK;      // epp_synchronize() completes it
+        if (v.async && mode != Mode::Match) return EPP_OK;         // epp_synchronize() (or the next call that needs the
+                                                                   // results on the host) completes it
         return finish_async(h);
     }
 
@@ -1411,6 +1412,7 @@ extern "C" int32_t epp_hash_prompts(epp_engine *h, const epp_batch *batch, uint6
     EPP_TRY(set_device(h));
     BatchView v;
     EPP_TRY(check_batch(h, batch, v));
+    v.async = false;                               // EPP_BATCH_ASYNC is an epp_schedule flag: hashes are complete on return
     h->kept_R = 0;
     return run_batch(h, v, Mode::HashOnly, out_hashes, out_nblocks, nullptr, nullptr, nullptr, nullptr);
 }
@@ -1880,7 +1882,9 @@ static int32_t p2p_phase(epp_engine *h, const BatchView &v, epp_decision *out, i
         h->kept_R = 0;
         h->shard_R = 0;
         EPP_TRY(commit_locked(h));
-        EPP_TRY(run_batch(h, v, Mode::HashOnly, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
+        BatchView hv = v;
+        hv.async = true;                           // no host round trip between the hash kernel and the probe kernel
+        EPP_TRY(run_batch(h, hv, Mode::HashOnly, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
         ++h->p2p_epoch;
         CUDA_TRY(h->p2p_gmasks.reserve(mask_bytes, &h->dev_bytes));
         CUDA_TRY(h->p2p_allbest.reserve(sizeof(epp_shard_best) * (size_t)R * (size_t)n, &h->dev_bytes));
