@@ -55,16 +55,21 @@ int main(void) {
          sizeof(epp_decision), sizeof(epp_decision_detail), sizeof(epp_batch), sizeof(epp_stats), sizeof(epp_shard_best));
   printf("%zu %zu %zu %zu\n", offsetof(epp_config, non_cached_tokens), offsetof(epp_config, primary),
          offsetof(epp_config, prefill), offsetof(epp_decision, score));
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(epp_topk_out), sizeof(epp_batcher_cfg), sizeof(epp_batcher_stats_t),
+         offsetof(epp_profile_cfg, affinity_threshold), offsetof(epp_config, tie_seed), offsetof(epp_config, index_commit_interval_us));
   return 0; }''')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
-    l1, l2 = subprocess.check_output([str(exe)], text=True).splitlines()
+    l1, l2, l3 = subprocess.check_output([str(exe)], text=True).splitlines()
     c = epp.capi
     assert [int(x) for x in l1.split()] == [C.sizeof(c.Config), C.sizeof(c.ProfileCfg), C.sizeof(c.ScorerCfg),
                                             C.sizeof(c.Decision), C.sizeof(c.DecisionDetail), C.sizeof(c.Batch),
                                             C.sizeof(c.Stats), C.sizeof(c.ShardBest)]
     assert [int(x) for x in l2.split()] == [c.Config.non_cached_tokens.offset, c.Config.primary.offset,
                                             c.Config.prefill.offset, c.Decision.score.offset]
+    assert [int(x) for x in l3.split()] == [C.sizeof(c.TopkOut), C.sizeof(c.BatcherCfg), C.sizeof(c.BatcherStats),
+                                            c.ProfileCfg.affinity_threshold.offset, c.Config.tie_seed.offset,
+                                            c.Config.index_commit_interval_us.offset]
     assert epp.DECISION_DTYPE.itemsize == C.sizeof(c.Decision)
 
 
