@@ -11,8 +11,8 @@
 //       accumulator chains over the block's 32-byte stripes, merge -> m, stored to the stage's [r][j] cell.
 //   warp 8 (chain): lane = request.  Walks the window's 8 blocks in order (the only serial part of the digest:
 //       m + len, one 8-byte round with h_{i-1}, avalanche), in place.
-//   Stages are handed over with named barriers (bar.arrive / bar.sync), 4-deep ring: full (digest -> chain), empty
-//   (chain -> digest).
+//   Stages are handed over with named barriers (bar.arrive / bar.sync), 4-deep ring of stages of TWO windows each: full
+//   (digest -> chain), empty (chain -> digest).
 #include "hash_blocks.cuh"
 #include "kernels.h"
 
@@ -21,6 +21,7 @@ namespace epp {
 namespace {
 constexpr int kWin = 8;
 constexpr int kStages = 4;
+constexpr int kSub = 2;                   // windows per ring stage (one barrier hand-over per kSub windows)
 constexpr int kBarFull = 1;               // named barrier ids 1..4
 constexpr int kBarEmpty = 1 + kStages;    // 5..8
 constexpr int kHashMinCtas = 4;
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(32 * kWin + 32, kHashMinCtas) k_hash_fused(Has
     constexpr int TR = 32, W = kWin;
     constexpr int kDigestWarps = TR * W / 32;
     constexpr int kProducers = TR * W + 32;
-    __shared__ uint64_t s_m[kStages][TR][(W + 1)];
+    __shared__ uint64_t s_m[kStages][kSub][TR][(W + 1)];
     __shared__ uint64_t s_off[TR];
     __shared__ int64_t s_eff[TR];
     __shared__ int32_t s_nfull[TR];
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(32 * kWin + 32, kHashMinCtas) k_hash_fused(Has
         if (t < 32) tile_lengths(p, r0, t, s_off, s_eff, s_nfull, &s_maxfull);
         __syncthreads();
         const int n_win = (s_maxfull + W - 1) / W;
+        const int n_st = (n_win + kSub - 1) / kSub;                              // ring hand-overs of this tile
 
         if (warp < kDigestWarps) {
             const int r = t / W, j = t % W;
@@ -122,23 +124,27 @@ __global__ void __launch_bounds__(32 * kWin + 32, kHashMinCtas) k_hash_fused(Has
             const uint8_t *src = p.data + s_off[r] + (uint64_t)j * (uint64_t)bs;     // block j of window 0; + W blocks per window
             const uint64_t win_bytes = (uint64_t)W * (uint64_t)bs;
             int32_t left = nfull - j;                                            // > 0: my block of this window is a full one
-            for (int k = 0; k < n_win; k++, src += win_bytes, left -= W) {
+            for (int k = 0; k < n_st; k++) {
                 const int s = k % kStages;
                 if (k >= kStages) bar_sync(kBarEmpty + s, kProducers);
-                if (left > 0) s_m[s][r][j] = block_digest<kAlign32>(src, n_stripes);
-                bar_arrive(kBarFull + s, kProducers);     // bar.arrive orders the store above for the threads of the barrier
+#pragma unroll
+                for (int u = 0; u < kSub; u++, src += win_bytes, left -= W)
+                    if (left > 0) s_m[s][u][r][j] = block_digest<kAlign32>(src, n_stripes);
+                bar_arrive(kBarFull + s, kProducers);     // bar.arrive orders the stores above for the threads of the barrier
             }
-            const int first = n_win > kStages ? n_win - kStages : 0;
-            for (int k = first; k < n_win; k++) bar_sync(kBarEmpty + (k % kStages), kProducers);
+            const int first = n_st > kStages ? n_st - kStages : 0;
+            for (int k = first; k < n_st; k++) bar_sync(kBarEmpty + (k % kStages), kProducers);
         } else {
             const int64_t r = r0 + lane;
             const int32_t nfull = s_nfull[lane];
             uint64_t prev = 0;
             if (r < p.R) prev = p.seeds[p.model_ids ? p.model_ids[r] : 0];
-            for (int k = 0; k < n_win; k++) {
+            for (int k = 0; k < n_st; k++) {
                 const int s = k % kStages;
                 bar_sync(kBarFull + s, kProducers);
-                prev = chain_window<TR, W>(s_m[s], s_nfull, p, r0, k, lane, nfull, lenp8, prev);
+#pragma unroll
+                for (int u = 0; u < kSub; u++)
+                    prev = chain_window<TR, W>(s_m[s][u], s_nfull, p, r0, k * kSub + u, lane, nfull, lenp8, prev);
                 bar_arrive(kBarEmpty + s, kProducers);
             }
             if (r < p.R) {                           // trailing partial block (hashing.go:90-96): generic tail, rare
