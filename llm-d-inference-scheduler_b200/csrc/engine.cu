@@ -158,6 +158,7 @@ struct epp_engine {
     std::vector<void *> p2p_peer;   // peers' buffers in this process's address space (own buffer at [p2p_rank])
     DevBuf p2p_peer_dev, p2p_gmasks, p2p_allbest, p2p_err;
     unsigned long long p2p_epoch = 0;
+    uint64_t p2p_or_bits = 0;       // offsets alignment of the batch being stepped through epp_shard_p2p_phase
     bool p2p_broken = false;        // a wait timed out: the ranks are out of step until the buffers are connected again
     int p2p_launches = 0;
 
@@ -1766,7 +1767,9 @@ extern "C" int32_t epp_shard_merge(epp_engine *h, int64_t n_requests, int32_t n_
 }
 
 // ---- endpoint-sharded mode with the exchanges over NVLink peer memory (shard_p2p.cu) ------------------------------
-static constexpr size_t kP2pFlag1 = 0, kP2pFlag2 = 128, kP2pHeader = 256;
+// flags of chunk c of a batch: flag 1 at c * 256, flag 2 at c * 256 + 128 (two chunks: the halves of a batch travel through
+// the exchange on the engine's two streams, so that a rank computes on one half while it waits for its peers on the other)
+static constexpr size_t kP2pFlag1 = 0, kP2pFlag2 = 128, kP2pChunkFlags = 256, kP2pChunks = 2, kP2pHeader = kP2pChunkFlags * kP2pChunks;
 
 extern "C" int32_t epp_shard_p2p_export(epp_engine *h, int64_t max_requests, uint8_t *out_handle, uint64_t *out_ptr) {
     if (!h || max_requests <= 0 || !out_handle || !out_ptr) return fail(EPP_ERR_INVALID, "bad arguments");
@@ -1857,8 +1860,10 @@ static int32_t p2p_check(epp_engine *h, cudaStream_t s, unsigned long long epoch
     if (!err) return EPP_OK;
     h->p2p_broken = true;
     uint8_t *own = static_cast<uint8_t *>(h->p2p_buf);
-    CUDA_TRY(launch_p2p_signal(reinterpret_cast<unsigned long long *>(own + kP2pFlag1), kP2pPoison, s));
-    CUDA_TRY(launch_p2p_signal(reinterpret_cast<unsigned long long *>(own + kP2pFlag2), kP2pPoison, s));
+    for (size_t c = 0; c < kP2pChunks; c++) {
+        CUDA_TRY(launch_p2p_signal(reinterpret_cast<unsigned long long *>(own + c * kP2pChunkFlags + kP2pFlag1), kP2pPoison, s));
+        CUDA_TRY(launch_p2p_signal(reinterpret_cast<unsigned long long *>(own + c * kP2pChunkFlags + kP2pFlag2), kP2pPoison, s));
+    }
     CUDA_TRY(cudaMemsetAsync(h->p2p_err.p, 0, sizeof(int), s));
     CUDA_TRY(cudaStreamSynchronize(s));
     const bool poisoned = err > 64;
@@ -1867,62 +1872,85 @@ static int32_t p2p_check(epp_engine *h, cudaStream_t s, unsigned long long epoch
                 (poisoned ? err - 64 : err) - 1, epoch, p2p_timeout_ns() / 1000000ull);
 }
 
-static int32_t p2p_phase(epp_engine *h, const BatchView &v, epp_decision *out, int phase) {
-    const int64_t R = v.R;
+// One phase of the exchange for rows [r0, r1) of the batch (chunk c: its own flag words, stream of slot c).  Phase 0
+// expects ++p2p_epoch and the commit to have happened; the caller checks p2p_err after phase 2 of every chunk.
+static int32_t p2p_phase_rows(epp_engine *h, const BatchView &v, epp_decision *out, int phase, int c, int64_t r0, int64_t r1,
+                              uint64_t or_bits) {
+    const int64_t R = r1 - r0;
     const int n = h->p2p_ranks;
-    const size_t W = (size_t)mask_words_of(h);
-    cudaStream_t s = h->slot[0].stream;
+    const size_t W = (size_t)mask_words_of(h), B = (size_t)h->cfg.max_prefix_blocks;
+    Slot &sl = h->slot[c];
+    cudaStream_t s = sl.stream;
     uint8_t *own = static_cast<uint8_t *>(h->p2p_buf);
     unsigned char *const *peers = h->p2p_peer_dev.as<unsigned char *>();
+    const size_t flag1 = (size_t)c * kP2pChunkFlags + kP2pFlag1, flag2 = (size_t)c * kP2pChunkFlags + kP2pFlag2;
+    const size_t mask_off = h->p2p_masks_off + (size_t)r0 * W * sizeof(uint32_t);
     const size_t mask_bytes = ((size_t)R * W * sizeof(uint32_t) + 15) & ~(size_t)15;
+    const size_t best_off = h->p2p_best_off + (size_t)r0 * sizeof(epp_shard_best);
     const unsigned long long timeout_ns = p2p_timeout_ns();
+    const unsigned long long epoch = h->p2p_epoch;
+    uint64_t *hashes = h->hashes.as<uint64_t>() + (size_t)r0 * B;
+    int32_t *nbs = h->nblocks.as<int32_t>() + r0;
+    uint32_t *gmasks = h->p2p_gmasks.as<uint32_t>() + (size_t)r0 * W;
+    epp_shard_best *allbest = h->p2p_allbest.as<epp_shard_best>() + (size_t)r0 * (size_t)n;   // this chunk's own [n][R] matrix
     int launches = 0;
     if (phase == 0) {
-        // phase 1: hashes + local presence masks -> own exchange buffer, raise flag 1
-        h->kept_R = 0;
-        h->shard_R = 0;
-        EPP_TRY(commit_locked(h));
-        BatchView hv = v;
-        hv.async = true;                           // no host round trip between the hash kernel and the probe kernel
-        EPP_TRY(run_batch(h, hv, Mode::HashOnly, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr));
-        ++h->p2p_epoch;
-        CUDA_TRY(h->p2p_gmasks.reserve(mask_bytes, &h->dev_bytes));
-        CUDA_TRY(h->p2p_allbest.reserve(sizeof(epp_shard_best) * (size_t)R * (size_t)n, &h->dev_bytes));
-        CUDA_TRY(launch_shard_probe(R, h->cfg.max_prefix_blocks, h->hashes.as<uint64_t>(), h->nblocks.as<int32_t>(), index_view(h),
-                                    reinterpret_cast<uint32_t *>(own + h->p2p_masks_off), (int32_t)W, s, &launches));
-        CUDA_TRY(launch_p2p_signal(reinterpret_cast<unsigned long long *>(own + kP2pFlag1), h->p2p_epoch, s));
-        h->p2p_launches = launches + 1;
+        // hashes + local presence masks -> own exchange buffer, raise flag 1
+        Work w{r0, r1, v.offsets ? v.data : v.data + (uint64_t)r0 * v.uniform_len, v.offsets, v.lengths, v.uniform_len, v.model_ids,
+               or_bits, hashes, nbs, nullptr};
+        CUDA_TRY(launch_hash_prompts(hash_params(h, w), s, &launches));
+        CUDA_TRY(launch_shard_probe(R, h->cfg.max_prefix_blocks, hashes, nbs, index_view(h),
+                                    reinterpret_cast<uint32_t *>(own + mask_off), (int32_t)W, s, &launches));
+        CUDA_TRY(launch_p2p_signal(reinterpret_cast<unsigned long long *>(own + flag1), epoch, s));
+        h->p2p_launches += launches + 1;
         return EPP_OK;
     }
-    const unsigned long long epoch = h->p2p_epoch;
     if (phase == 1) {
-        // exchange 1: OR of every rank's masks, read straight from the peers; phase 2: global stop rule on the local
-        // counts -> local best record in the own exchange buffer, raise flag 2
-        CUDA_TRY(launch_p2p_wait(peers, n, kP2pFlag1, epoch, h->p2p_err.as<int>(), timeout_ns, s));
-        CUDA_TRY(launch_p2p_or_masks(peers, n, h->p2p_masks_off, mask_bytes, h->p2p_gmasks.p, s));
-        Work w{0, R, nullptr, nullptr, nullptr, 0, nullptr, 0, h->hashes.as<uint64_t>(), h->nblocks.as<int32_t>()};
-        PickParams pp = pick_params(h, w, h->decisions.as<epp_decision>(), nullptr, nullptr);
-        pp.model_ids = v.model_ids;
-        pp.global_masks = h->p2p_gmasks.as<uint32_t>();
+        // exchange 1: OR of every rank's masks, read straight from the peers; then the global stop rule on the local counts ->
+        // local best record in the own exchange buffer, raise flag 2
+        CUDA_TRY(launch_p2p_wait(peers, n, flag1, epoch, h->p2p_err.as<int>(), timeout_ns, s));
+        CUDA_TRY(launch_p2p_or_masks(peers, n, mask_off, mask_bytes, gmasks, s));
+        Work w{r0, r1, nullptr, nullptr, nullptr, 0, nullptr, 0, hashes, nbs};
+        PickParams pp = pick_params(h, w, h->decisions.as<epp_decision>() + r0, nullptr, nullptr);
+        pp.model_ids = v.model_ids ? v.model_ids + r0 : nullptr;
+        pp.global_masks = gmasks;
         pp.mask_words = (int32_t)W;
-        pp.shard_out = reinterpret_cast<epp_shard_best *>(own + h->p2p_best_off);
-        EPP_TRY(launch_match(h, h->slot[0], pp, &launches));
+        pp.shard_out = reinterpret_cast<epp_shard_best *>(own + best_off);
+        EPP_TRY(launch_match(h, sl, pp, &launches));
         // a rank whose wait failed must NOT publish records computed from an incomplete OR: the signal kernel checks
-        CUDA_TRY(launch_p2p_signal_unless(reinterpret_cast<unsigned long long *>(own + kP2pFlag2), epoch, h->p2p_err.as<int>(), s));
+        CUDA_TRY(launch_p2p_signal_unless(reinterpret_cast<unsigned long long *>(own + flag2), epoch, h->p2p_err.as<int>(), s));
         h->p2p_launches += launches + 3;
         return EPP_OK;
     }
-    // exchange 2 + phase 3: gather every rank's records from the peers and merge
-    CUDA_TRY(launch_p2p_wait(peers, n, kP2pFlag2, epoch, h->p2p_err.as<int>(), timeout_ns, s));
-    CUDA_TRY(launch_p2p_gather(peers, n, h->p2p_best_off, sizeof(epp_shard_best) * (size_t)R, h->p2p_allbest.p, s));
-    CUDA_TRY(launch_shard_merge(R, n, h->p2p_allbest.as<epp_shard_best>(), h->nblocks.as<int32_t>(), out, s, &launches));
-    h->stats.last_kernel_launches = (uint64_t)(h->p2p_launches + launches + 2);
-    EPP_TRY(p2p_check(h, s, epoch));
+    // exchange 2: gather every rank's records from the peers and merge
+    CUDA_TRY(launch_p2p_wait(peers, n, flag2, epoch, h->p2p_err.as<int>(), timeout_ns, s));
+    CUDA_TRY(launch_p2p_gather(peers, n, best_off, sizeof(epp_shard_best) * (size_t)R, allbest, s));
+    CUDA_TRY(launch_shard_merge(R, n, allbest, nbs, out + r0, s, &launches));
+    h->p2p_launches += launches + 2;
+    return EPP_OK;
+}
+
+// Start / end of a batch of the exchange.
+static int32_t p2p_begin(epp_engine *h, const BatchView &v, uint64_t *or_bits) {
+    h->kept_R = 0;
+    h->shard_R = 0;
+    EPP_TRY(commit_locked(h));
+    if (h->async_pending) EPP_TRY(finish_async(h));
+    EPP_TRY(join_streams(h));
+    EPP_TRY(reserve_batch(h, v.R));
+    *or_bits = 0;
+    if (v.offsets) EPP_TRY(device_offsets_or_bits(h, v.offsets, v.R, h->slot[0].stream, or_bits));
+    ++h->p2p_epoch;
+    h->p2p_launches = 0;
+    return EPP_OK;
+}
+static int32_t p2p_end(epp_engine *h, int64_t R) {
+    h->stats.last_kernel_launches = (uint64_t)h->p2p_launches;
+    EPP_TRY(p2p_check(h, h->slot[0].stream, h->p2p_epoch));
     h->stats.n_batches++;
     h->stats.n_decisions += (uint64_t)R;
     return EPP_OK;
 }
-
 static int32_t p2p_prepare(epp_engine *h, const epp_batch *batch, epp_decision *out, BatchView &v) {
     if (!h || !out) return fail(EPP_ERR_INVALID, "NULL argument");
     EPP_TRY(set_device(h));
@@ -1944,10 +1972,25 @@ extern "C" int32_t epp_shard_schedule_p2p(epp_engine *h, const epp_batch *batch,
     BatchView v;
     EPP_TRY(p2p_prepare(h, batch, out, v));
     if (v.R == 0) return EPP_OK;
-    for (int phase = 0; phase < 3; phase++) EPP_TRY(p2p_phase(h, v, out, phase));
-    return EPP_OK;
+    uint64_t or_bits = 0;
+    EPP_TRY(p2p_begin(h, v, &or_bits));
+    // two halves on the engine's two streams: while one half waits for the peers' flags, the other half computes
+    const bool split = h->dev_chunks > 1 && v.R >= 2 * 4096 && !h->pick_global;
+    const int64_t half = split ? (((v.R + 1) / 2 + 31) & ~(int64_t)31) : v.R;
+    if (split) {
+        CUDA_TRY(cudaEventRecord(h->slot[0].done, h->slot[0].stream));
+        CUDA_TRY(cudaStreamWaitEvent(h->slot[1].stream, h->slot[0].done, 0));
+    }
+    for (int phase = 0; phase < 3; phase++) {
+        EPP_TRY(p2p_phase_rows(h, v, out, phase, 0, 0, half, or_bits));
+        if (split) EPP_TRY(p2p_phase_rows(h, v, out, phase, 1, half, v.R, or_bits));
+    }
+    if (split) {
+        h->s1_unjoined = true;
+        EPP_TRY(join_streams(h));
+    }
+    return p2p_end(h, v.R);
 }
-
 extern "C" int32_t epp_shard_p2p_phase(epp_engine *h, const epp_batch *batch, epp_decision *out, int32_t phase) {
     if (!h) return fail(EPP_ERR_INVALID, "NULL argument");
     if (phase < 0 || phase > 2) return fail(EPP_ERR_INVALID, "phase %d out of range [0,2]", phase);
@@ -1955,7 +1998,9 @@ extern "C" int32_t epp_shard_p2p_phase(epp_engine *h, const epp_batch *batch, ep
     BatchView v;
     EPP_TRY(p2p_prepare(h, batch, out, v));
     if (v.R == 0) return EPP_OK;
-    EPP_TRY(p2p_phase(h, v, out, phase));
-    if (phase < 2) CUDA_TRY(cudaStreamSynchronize(h->slot[0].stream));      // phase 2 synchronises in p2p_check
+    if (phase == 0) EPP_TRY(p2p_begin(h, v, &h->p2p_or_bits));
+    EPP_TRY(p2p_phase_rows(h, v, out, phase, 0, 0, v.R, h->p2p_or_bits));
+    if (phase == 2) return p2p_end(h, v.R);
+    CUDA_TRY(cudaStreamSynchronize(h->slot[0].stream));
     return EPP_OK;
 }
