@@ -1975,7 +1975,7 @@ extern "C" int32_t epp_shard_schedule_p2p(epp_engine *h, const epp_batch *batch,
     uint64_t or_bits = 0;
     EPP_TRY(p2p_begin(h, v, &or_bits));
     // two halves on the engine's two streams: while one half waits for the peers' flags, the other half computes
-    const bool split = h->dev_chunks > 1 && v.R >= 2 * 4096 && !h->pick_global;
+    const bool split = h->dev_chunks > 1 && v.R >= 2 * 4096;       // (the dense-counter scratch is per stream)
     const int64_t half = split ? (((v.R + 1) / 2 + 31) & ~(int64_t)31) : v.R;
     if (split) {
         CUDA_TRY(cudaEventRecord(h->slot[0].done, h->slot[0].stream));
