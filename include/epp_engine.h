@@ -396,7 +396,8 @@ EPP_API int32_t epp_shard_merge(epp_engine *h, int64_t n_requests, int32_t n_ran
  * exports one exchange buffer (CUDA IPC handle, 64 bytes; out_ptr is the raw device pointer for ranks that share a
  * process), connects to all peers' buffers (peers: n_ranks x 64-byte handles when ipc_handles != 0, else n_ranks
  * uint64 pointers), then calls epp_shard_schedule_p2p with the SAME device batch on every rank: presence masks are
- * OR-reduced and best records merged straight out of the peers' memory, ordered by release/acquire flags; `out`
+ * OR-reduced and best records merged straight out of the peers' memory, ordered by release/acquire flags (the two halves
+ * of a batch pipelined through the exchange on the engine's two streams); `out`
  * ([R] device) is identical on every rank.  A peer that does not show up within 20 s (EPP_P2P_TIMEOUT_MS) yields EPP_ERR_NCCL. */
 EPP_API int32_t epp_shard_p2p_export(epp_engine *h, int64_t max_requests, uint8_t *out_handle, uint64_t *out_ptr);
 EPP_API int32_t epp_shard_p2p_connect(epp_engine *h, int32_t n_ranks, int32_t rank, const void *peers, int32_t ipc_handles);

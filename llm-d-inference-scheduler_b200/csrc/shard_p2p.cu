@@ -2,8 +2,9 @@
 // NCCL: every rank exposes one buffer {flags, presence masks, best records} through CUDA IPC; the consumers read the
 // peers' copies directly with P2P loads and reduce on the fly (bitwise OR of the masks -- a reduction NCCL does not
 // have -- and the max / lowest-slot / tie-sum merge of the records).  Cross-rank ordering is two monotonically
-// increasing flags per rank, written with st.release.sys after the producing kernel and polled with ld.acquire.sys;
-// everything is stream-ordered on the engine's stream, the host only waits at the end of the batch.
+// increasing flags per rank and batch half, written with st.release.sys after the producing kernel and polled with
+// ld.acquire.sys; everything is stream-ordered -- the two halves of a batch on the engine's two streams, so that a rank
+// computes on one half while it waits for its peers on the other -- and the host only waits at the end of the batch.
 //
 // Buffer reuse needs no second buffer: a rank overwrites its masks of batch k+1 only after its own merge of batch k,
 // which waited for every peer's flag2(k), which each peer raises after it has finished reading the masks of batch k;
