@@ -4,9 +4,10 @@
 // This is the latency path of the micro-batcher (csrc/batcher.cu): a flush of 1 .. 1024 requests.
 //
 // One CTA per request, 9 warps:
-//   warps 0-7  digest: every thread reads whole 32-byte stripes of "its" blocks over PCIe (zero-copy, 128/256-bit
-//              loads) and leaves the merged stripe state of each FULL block in shared memory -- one round trip for a
-//              4 096-token prompt (256 blocks, one per thread);
+//   thread 0   stages the prompt: ONE cp.async.bulk (TMA) + mbarrier brings all its full blocks -- 16 KiB for a 4 096-token
+//              prompt -- into shared memory, from HBM or straight from the caller's pinned host memory over PCIe;
+//   warps 0-7  digest: every thread hashes the 32-byte stripes of "its" blocks out of shared memory and leaves the merged
+//              stripe state of each FULL block there (256 blocks = one per thread);
 //   warp 8     chain: ONE lane walks the blocks in order (the serial part of hashPrompt, hashing.go:80-96; ~70 ns per
 //              block: five dependent 64-bit multiplies), stores every hash to the request's row in HBM (the stash
 //              PreRequest needs) and over the block's stripe state in shared memory, and publishes its progress there
@@ -36,6 +37,46 @@ __device__ __forceinline__ int32_t ld_acquire_cta(const int32_t *p) {
     asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
     return v;
 }
+// ---- bulk-copy (TMA) staging of the request's prompt: one cp.async.bulk brings all its full blocks into shared memory
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *b, uint32_t tx) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(tx) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(b)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// Stripe rounds + merge of one full block whose bytes are in shared memory (part A of xxh64.cuh).
+__device__ __forceinline__ uint64_t block_digest_smem(const uint8_t *src, int n_stripes) {
+    uint64_t v[4];
+    xxh_init(v);
+    const uint32_t a = smem_u32(src);
+    for (int st = 0; st < n_stripes; st++) {
+        uint64_t x[4];
+        asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(x[0]), "=l"(x[1]) : "r"(a + 32u * st));
+        asm volatile("ld.shared.v2.u64 {%0,%1}, [%2];" : "=l"(x[2]), "=l"(x[3]) : "r"(a + 32u * st + 16u));
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[q] = xxh_round(v[q], x[q]);
+    }
+    return xxh_merge_all(v);
+}
+
 struct ChainFollower {
     static constexpr bool kOn = true;
     const int32_t *progress;                   // hashes [0, *progress) are in `h`
@@ -46,9 +87,13 @@ struct ChainFollower {
     __device__ __forceinline__ uint64_t hash(int32_t i) const { return h[i]; }
 };
 
-template <bool kAlign32>
-__global__ void __launch_bounds__(kThreads) k_cycle_small(HashParams hp, PickParams pp, SmallOut so) {
-    extern __shared__ uint64_t s_m[];              // [max_blocks] merged stripe state of every full block
+// kStage: the prompt is staged into shared memory by ONE bulk copy (TMA) per request; else the digest threads load their
+// blocks themselves (prompts too long for the staging buffer).
+template <bool kAlign32, bool kStage>
+__global__ void __launch_bounds__(kThreads) k_cycle_small(HashParams hp, PickParams pp, SmallOut so, uint32_t stage_off) {
+    extern __shared__ __align__(128) uint64_t s_m[];   // [max_blocks] merged stripe state of every full block; then (kStage)
+                                                       // at byte stage_off the prompt's full blocks
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint64_t s_off;
     __shared__ int64_t s_eff;
     __shared__ int32_t s_nfull, s_nb;
@@ -77,14 +122,33 @@ __global__ void __launch_bounds__(kThreads) k_cycle_small(HashParams hp, PickPar
         s_off = off; s_eff = eff; s_nfull = nfull; s_nb = nb;
         s_progress = 0;
         __threadfence();                           // the match warp reads nblocks / in_len at L2
+        if (kStage) {
+            mbar_init(&s_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (nfull > 0) {                       // every full block of the prompt in one transaction (16-byte aligned, size % 32 == 0)
+                const uint32_t bytes = (uint32_t)nfull * (uint32_t)bs;
+                mbar_arrive_expect_tx(&s_bar, bytes);
+                bulk_g2s(reinterpret_cast<uint8_t *>(s_m) + stage_off, hp.data + off, bytes, &s_bar);
+            }
+        }
     }
     __syncthreads();
     const int32_t nfull = s_nfull;
     if (warp < kDigestThreads / 32) {
-        const uint8_t *base = hp.data + s_off;
         const int n_stripes = (int)(bs >> 5);
-        for (int32_t b = t; b < nfull; b += kDigestThreads)
-            s_m[b] = block_digest<kAlign32>(base + (uint64_t)b * (uint64_t)bs, n_stripes);
+        if (kStage) {
+            if (nfull > 0) {
+                mbar_wait(&s_bar, 0);
+                const uint8_t *base = reinterpret_cast<const uint8_t *>(s_m) + stage_off;
+                for (int32_t b = t; b < nfull; b += kDigestThreads)
+                    s_m[b] = block_digest_smem(base + (size_t)b * (size_t)bs, n_stripes);
+            }
+        } else {
+            const uint8_t *base = hp.data + s_off;
+            for (int32_t b = t; b < nfull; b += kDigestThreads)
+                s_m[b] = block_digest<kAlign32>(base + (uint64_t)b * (uint64_t)bs, n_stripes);
+        }
     }
     __syncthreads();                               // the prompt bytes are consumed: nothing below reads host input data
 
@@ -139,18 +203,30 @@ size_t cycle_small_max_blocks() { return 8192; }   // 64 KiB of stripe states pe
 cudaError_t launch_cycle_small(const HashParams &hp, const PickParams &pp, const SmallOut &so, int align, cudaStream_t s,
                                int *launches) {
     if (hp.R <= 0) return cudaSuccess;
-    const size_t smem = sizeof(uint64_t) * (size_t)hp.max_blocks;
+    const size_t m_bytes = (sizeof(uint64_t) * (size_t)hp.max_blocks + 127) & ~(size_t)127;
+    const size_t stage_bytes = (size_t)hp.max_blocks * (size_t)hp.block_bytes;
+    const bool stage = m_bytes + stage_bytes <= 160 * 1024;           // longer prompts: the digest threads load their blocks themselves
+    const size_t smem = stage ? m_bytes + stage_bytes : m_bytes;
     int dev = 0;
     cudaGetDevice(&dev);
     static bool attr_set[64] = {};                 // function attributes are per device: engines of one process may sit on several GPUs
     if (!attr_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(k_cycle_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cycle_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(k_cycle_small<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cycle_small<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cycle_small<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cycle_small<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev & 63] = true;
     }
-    if (align >= 32) k_cycle_small<true><<<(unsigned)hp.R, kThreads, smem, s>>>(hp, pp, so);
-    else k_cycle_small<false><<<(unsigned)hp.R, kThreads, smem, s>>>(hp, pp, so);
+    const unsigned grid = (unsigned)hp.R;
+    const uint32_t off = (uint32_t)m_bytes;
+    if (stage) {
+        if (align >= 32) k_cycle_small<true, true><<<grid, kThreads, smem, s>>>(hp, pp, so, off);
+        else k_cycle_small<false, true><<<grid, kThreads, smem, s>>>(hp, pp, so, off);
+    } else {
+        if (align >= 32) k_cycle_small<true, false><<<grid, kThreads, smem, s>>>(hp, pp, so, off);
+        else k_cycle_small<false, false><<<grid, kThreads, smem, s>>>(hp, pp, so, off);
+    }
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
