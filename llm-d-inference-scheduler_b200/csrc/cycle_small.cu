@@ -37,6 +37,14 @@ __device__ __forceinline__ int32_t ld_acquire_cta(const int32_t *p) {
     asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
     return v;
 }
+// Poll word written by the copy stream (device memory, so L2 is the point of coherence).  Relaxed on purpose: an acquire at
+// system scope is a MEMBAR.SYS per poll, and a thousand CTAs issuing those while the copy engine streams the prompts in
+// cut its rate by a third to a half; one GPU-scope fence after the wait orders the reads behind it.
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 // ---- bulk-copy (TMA) staging of the request's prompt: one cp.async.bulk brings all its full blocks into shared memory
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) {
@@ -122,10 +130,14 @@ __global__ void __launch_bounds__(kThreads) k_cycle_small(HashParams hp, PickPar
         s_off = off; s_eff = eff; s_nfull = nfull; s_nb = nb;
         s_progress = 0;
         __threadfence();                           // the match warp reads nblocks / in_len at L2
+        if (so.arrive) {                           // the prompts may still be in flight: wait for the copy that carries them
+            while (ld_relaxed_gpu(so.arrive) != so.epoch) __nanosleep(100);
+            __threadfence();
+        }
         if (kStage) {
             mbar_init(&s_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("fence.proxy.async;" ::: "memory");        // barrier init (shared) and, behind `arrive`, the copied prompt (global)
             if (nfull > 0) {                       // every full block of the prompt in one transaction (16-byte aligned, size % 32 == 0)
                 const uint32_t bytes = (uint32_t)nfull * (uint32_t)bs;
                 mbar_arrive_expect_tx(&s_bar, bytes);

@@ -4,6 +4,7 @@
 //
 // There is NO CPU compute path in this file: without a CUDA device epp_engine_create fails with
 // EPP_ERR_NO_DEVICE, and every data-path entry point only stages buffers and launches kernels.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -140,6 +141,10 @@ struct epp_engine {
     uint32_t *small_flags = nullptr;
     uint32_t small_epoch = 0;
     DevBuf small_overflow_n;        // stays zero between batches (reset by the overflow pass)
+    int small_pipe_min = 1;         // EPP_SMALL_PIPELINE=n: DMA-copied batches of >= n requests start their kernel BEFORE the copy
+                                    // lands (copy on the second stream, one stream-ordered flag write behind it); 0 = off
+    DevBuf small_arrive;            // epoch word: the prompts of the batch have arrived
+    uint32_t *small_epoch_host = nullptr;   // pinned source of those words when the driver has no stream write-value
     bool small_stats_pending = false;   // ev[0] / ev[1] bracket the last small batch; read lazily by epp_get_stats
     std::chrono::steady_clock::time_point last_commit{};   // last commit done by a scheduling call (index_commit_interval_us)
     bool committed_once = false;
@@ -316,6 +321,10 @@ extern "C" int32_t epp_engine_create(const epp_config *cfg, epp_engine **out) {
     { const char *v1 = getenv("EPP_HASH_STAGED"); e->staged = v1 ? atoi(v1) : 0; }
     { const char *v1 = getenv("EPP_SMALL_BATCH"); e->small_max = v1 ? std::max(0, atoi(v1)) : 1024; }
     { const char *v1 = getenv("EPP_SMALL_ZEROCOPY"); e->small_zc_max = v1 ? std::max(0, atoi(v1)) : 8; }
+    { const char *v1 = getenv("EPP_SMALL_PIPELINE"); e->small_pipe_min = v1 ? std::max(0, atoi(v1)) : 1; }
+    CUDA_TRY(e->small_arrive.reserve(sizeof(uint32_t) * 16, &e->dev_bytes));
+    CUDA_TRY(cudaMemset(e->small_arrive.p, 0, sizeof(uint32_t) * 16));
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&e->small_epoch_host), 64, cudaHostAllocDefault));
     CUDA_TRY(e->small_overflow_n.reserve(sizeof(int32_t) * 4, &e->dev_bytes));
     CUDA_TRY(cudaMemset(e->small_overflow_n.p, 0, sizeof(int32_t) * 4));
     for (int i = 0; i < 2; i++) CUDA_TRY(e->slot[i].overflow_n.reserve(sizeof(int32_t) * 4, &e->dev_bytes));
@@ -351,6 +360,7 @@ extern "C" int32_t epp_engine_destroy(epp_engine *h) {
     for (auto &ev : h->user_ev) if (ev) cudaEventDestroy(ev);
     if (h->wc_host) cudaFreeHost(h->wc_host);
     if (h->small_host) cudaFreeHost(h->small_host);
+    if (h->small_epoch_host) cudaFreeHost(h->small_epoch_host);
     for (int g = 0; g < (int)h->p2p_peer.size(); g++)
         if (h->p2p_ipc && g != h->p2p_rank && h->p2p_peer[g]) cudaIpcCloseMemHandle(h->p2p_peer[g]);
     if (h->p2p_buf) cudaFree(h->p2p_buf);
@@ -1105,22 +1115,60 @@ static int small_batch_mode(epp_engine *h, const BatchView &v, const uint8_t **d
     return *align >= 16 ? 2 : 0;
 }
 
+// cuStreamWriteValue32 through the runtime's driver-entry-point lookup (no link against libcuda); nullptr when absent.
+typedef CUresult (*StreamWriteValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static StreamWriteValue32 stream_write_value32() {
+    static const StreamWriteValue32 fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return reinterpret_cast<StreamWriteValue32>(p);
+    }();
+    return fn;
+}
+
 static int32_t run_small(epp_engine *h, const BatchView &v, int mode, const uint8_t *data_dev, int align,
                          epp_decision *out_dec, epp_decision_detail *out_detail) {
     const int64_t R = v.R;
     cudaStream_t s0 = h->slot[0].stream;
     EPP_TRY(reserve_batch(h, R));
     EPP_TRY(small_reserve(h, R));
+    uint32_t epoch = h->small_epoch + 1;
+    if (epoch > 0x7fffffffu) {
+        epoch = 1;
+        CUDA_TRY(cudaMemsetAsync(h->small_arrive.p, 0, sizeof(uint32_t), s0));
+        CUDA_TRY(cudaStreamSynchronize(s0));
+    }
+    h->small_epoch = epoch;
+    const uint32_t *arrive = nullptr;
     if (mode == 2) {
         const uint64_t start = v.offsets ? v.offsets[0] : 0;
         CUDA_TRY(h->slot[0].data.reserve(v.total_bytes + 64, &h->dev_bytes));
         uint8_t *stage = h->slot[0].data.as<uint8_t>() + (start & 31);
-        CUDA_TRY(cudaMemcpyAsync(stage, v.data + start, v.total_bytes, cudaMemcpyHostToDevice, s0));
         data_dev = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(stage) - (uintptr_t)start);   // + offsets[r]
+        if (h->small_pipe_min > 0 && R >= h->small_pipe_min) {
+            // The copy goes to the second stream with a stream-ordered 32-bit write of the epoch behind it; the kernel is
+            // launched on s0 at once and thread 0 of every CTA waits for that word, so the launch latency (and the stream's
+            // copy -> kernel hand-over) hides under the transfer.  The staging buffer is free: every request of the batch
+            // before raised its flag, which it does after its last read of the prompt.
+            cudaStream_t s1 = h->slot[1].stream;
+            uint32_t *arr = h->small_arrive.as<uint32_t>();
+            CUDA_TRY(cudaMemcpyAsync(stage, v.data + start, v.total_bytes, cudaMemcpyHostToDevice, s1));
+            if (const StreamWriteValue32 wv = stream_write_value32()) {
+                if (wv(s1, reinterpret_cast<CUdeviceptr>(arr), epoch, 0) != CUDA_SUCCESS) return fail(EPP_ERR_CUDA, "cuStreamWriteValue32 failed");
+            } else {
+                *h->small_epoch_host = epoch;      // read by the copy below before this (synchronous) call returns
+                CUDA_TRY(cudaMemcpyAsync(arr, h->small_epoch_host, sizeof(uint32_t), cudaMemcpyHostToDevice, s1));
+            }
+            arrive = arr;
+            h->s1_unjoined = true;
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(stage, v.data + start, v.total_bytes, cudaMemcpyHostToDevice, s0));
+        }
     }
-    uint32_t epoch = h->small_epoch + 1;
-    if (epoch > 0x7fffffffu) epoch = 1;
-    h->small_epoch = epoch;
     const int set = (int)(epoch & 1);              // the kernel of the batch before may still be finishing its chains
     if (v.offsets) memcpy(h->small_offsets[set], v.offsets, sizeof(uint64_t) * (size_t)(R + 1));
     if (v.lengths) memcpy(h->small_lengths[set], v.lengths, sizeof(uint64_t) * (size_t)R);
@@ -1141,7 +1189,7 @@ static int32_t run_small(epp_engine *h, const BatchView &v, int mode, const uint
     PickParams pp = pick_params(h, w, h->decisions.as<epp_decision>(), h->details.as<epp_decision_detail>(), nullptr);
     pp.overflow_list = h->slot[0].overflow_list.as<int32_t>();
     pp.overflow_n = h->small_overflow_n.as<int32_t>();
-    SmallOut so{h->small_dec, h->small_det, h->small_flags, epoch};
+    SmallOut so{h->small_dec, h->small_det, h->small_flags, epoch, arrive};
     int launches = 0;
     CUDA_TRY(cudaEventRecord(h->ev[0], s0));
     CUDA_TRY(launch_cycle_small(hash_params(h, w), pp, so, align, s0, &launches));

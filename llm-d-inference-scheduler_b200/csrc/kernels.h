@@ -190,6 +190,9 @@ struct SmallOut {
     epp_decision_detail *det;      // [R]
     uint32_t *flags;               // [R]
     uint32_t epoch;                // 1 .. 0x7fffffff
+    // Prompts still on their way when the kernel starts (the copy runs on another stream): the rows may be read once
+    // *arrive == epoch (a stream-ordered 32-bit write behind the copy).  nullptr: resident at launch.
+    const uint32_t *arrive;        // device
 };
 size_t cycle_small_max_blocks();
 cudaError_t launch_cycle_small(const HashParams &hp, const PickParams &pp, const SmallOut &so, int align, cudaStream_t s,

@@ -773,8 +773,9 @@ def test_small_batch_zero_copy_path_vs_oracle(epp, orc, tie_seed, monkeypatch):
         return buf, offs, lens, d, o
 
     results = {}
-    for small in ("1024", "0"):
+    for small, pipe in (("1024", "16"), ("1024", "0"), ("0", "16")):
         monkeypatch.setenv("EPP_SMALL_BATCH", small)
+        monkeypatch.setenv("EPP_SMALL_PIPELINE", pipe)     # kernel started before the copies land (1 / 2 / 4 copies) or behind one copy
         rng = np.random.default_rng(72)
         with epp.Engine(E, spec(1, prim), spec(2, pref), block_size_tokens=bst, max_prefix_blocks=B, non_cached_tokens=8,
                         encode=spec(3, enc), tie_seed=tie_seed) as eng:
@@ -782,7 +783,7 @@ def test_small_batch_zero_copy_path_vs_oracle(epp, orc, tie_seed, monkeypatch):
             eng.pool_set(np.arange(E), role, kv, waiting)
             eng.index_load_snapshot(pairs_h, pairs_e)
             got = []
-            for n in (1, 2, 33, 600, 1):
+            for n in (1, 2, 20, 33, 130, 600, 1):
                 buf, offs, lens, d, o = make_batch(n)
                 mm = (rng.random(n) < 0.5).astype(np.uint8)
                 base = eng.stats()["n_decisions"]
@@ -796,13 +797,14 @@ def test_small_batch_zero_copy_path_vs_oracle(epp, orc, tie_seed, monkeypatch):
                 odec, ototal = orc.cycle_batch(b"m", bst, B, 8, False, ix, orc.make_profile(1, prim), orc.make_profile(2, pref),
                                                pool, d, o, 2, tie_seed=tie_seed, tie_base=base,
                                                encode=orc.make_profile(3, enc), multimodal=mm)
-                helpers.assert_decisions_equal(dec, det, odec, ototal, where=f"small={small} n={n}")
+                helpers.assert_decisions_equal(dec, det, odec, ototal, where=f"small={small} pipeline={pipe} n={n}")
                 got.append((dec.copy(), det.copy()))
                 buf.close()
-            results[small] = got
-    for (a, ad), (b, bd) in zip(results["1024"], results["0"]):
-        np.testing.assert_array_equal(a, b)
-        np.testing.assert_array_equal(ad, bd)
+            results[small, pipe] = got
+    for other in (("1024", "0"), ("0", "16")):
+        for (a, ad), (b, bd) in zip(results["1024", "16"], results[other]):
+            np.testing.assert_array_equal(a, b)
+            np.testing.assert_array_equal(ad, bd)
 
 
 def test_index_commit_interval_bounds_the_staleness(epp, orc):
