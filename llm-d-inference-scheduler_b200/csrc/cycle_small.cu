@@ -99,8 +99,8 @@ struct ChainFollower {
 // blocks themselves (prompts too long for the staging buffer).
 template <bool kAlign32, bool kStage>
 __global__ void __launch_bounds__(kThreads) k_cycle_small(HashParams hp, PickParams pp, SmallOut so, uint32_t stage_off) {
-    extern __shared__ __align__(128) uint64_t s_m[];   // [max_blocks] merged stripe state of every full block; then (kStage)
-                                                       // at byte stage_off the prompt's full blocks
+    extern __shared__ __align__(128) uint64_t s_m[];   // [max_blocks] merged stripe state of every full block; then, at byte
+                                                       // stage_off, (kStage) the prompt's full blocks and its trailing partial block
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint64_t s_off;
     __shared__ int64_t s_eff;
@@ -161,6 +161,20 @@ __global__ void __launch_bounds__(kThreads) k_cycle_small(HashParams hp, PickPar
             for (int32_t b = t; b < nfull; b += kDigestThreads)
                 s_m[b] = block_digest<kAlign32>(base + (uint64_t)b * (uint64_t)bs, n_stripes);
         }
+    } else if (warp == kDigestThreads / 32) {
+        // The trailing partial block is hashed LAST, long after a cold request may have raised its flag (global stop), and
+        // the caller -- or the next batch's copy into the staging buffer -- may rewrite the prompt bytes from then on: the
+        // chain warp, idle until the digests are done, brings them into shared memory now (behind the full blocks of the
+        // staged prompt, else behind the stripe states).
+        const int64_t tail_n = s_eff - (int64_t)nfull * bs;
+        if (tail_n > 0) {
+            const uint8_t *src = hp.data + s_off + (uint64_t)nfull * (uint64_t)bs;
+            uint8_t *dst = reinterpret_cast<uint8_t *>(s_m) + stage_off + (kStage ? (size_t)nfull * (size_t)bs : 0);
+            const int64_t n16 = tail_n >> 4;       // rows and blocks are 16-byte aligned on this path
+            for (int64_t i = lane; i < n16; i += 32)
+                reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+            for (int64_t i = (n16 << 4) + lane; i < tail_n; i += 32) dst[i] = src[i];
+        }
     }
     __syncthreads();                               // the prompt bytes are consumed: nothing below reads host input data
 
@@ -186,7 +200,8 @@ __global__ void __launch_bounds__(kThreads) k_cycle_small(HashParams hp, PickPar
                 sh[b] = prev;
             }
             if ((int64_t)nfull * bs < s_eff) {     // trailing partial block (hashing.go:90-96)
-                prev = hash_block_generic(hp.data + s_off + (uint64_t)nfull * (uint64_t)bs, s_eff - (int64_t)nfull * bs, prev);
+                const uint8_t *tail = reinterpret_cast<const uint8_t *>(s_m) + stage_off + (kStage ? (size_t)nfull * (size_t)bs : 0);
+                prev = hash_block_generic(tail, s_eff - (int64_t)nfull * bs, prev);
                 row[nfull] = prev;
                 sh[nfull] = prev;
             }
@@ -212,21 +227,27 @@ __global__ void __launch_bounds__(kThreads) k_cycle_small(HashParams hp, PickPar
 
 size_t cycle_small_max_blocks() { return 8192; }   // 64 KiB of stripe states per CTA
 
+bool cycle_small_stages_prompt(int32_t max_blocks, int32_t block_bytes) {
+    const size_t m_bytes = (sizeof(uint64_t) * (size_t)max_blocks + 127) & ~(size_t)127;
+    return m_bytes + (size_t)max_blocks * (size_t)block_bytes <= 160 * 1024;
+}
+
 cudaError_t launch_cycle_small(const HashParams &hp, const PickParams &pp, const SmallOut &so, int align, cudaStream_t s,
                                int *launches) {
     if (hp.R <= 0) return cudaSuccess;
     const size_t m_bytes = (sizeof(uint64_t) * (size_t)hp.max_blocks + 127) & ~(size_t)127;
     const size_t stage_bytes = (size_t)hp.max_blocks * (size_t)hp.block_bytes;
-    const bool stage = m_bytes + stage_bytes <= 160 * 1024;           // longer prompts: the digest threads load their blocks themselves
-    const size_t smem = stage ? m_bytes + stage_bytes : m_bytes;
+    const bool stage = cycle_small_stages_prompt(hp.max_blocks, hp.block_bytes);   // longer prompts: the digest threads load their blocks themselves
+    const size_t smem = m_bytes + (stage ? stage_bytes : (size_t)hp.block_bytes);     // unstaged: room for the trailing partial block
+    if (smem > 160 * 1024) return cudaErrorInvalidValue;
     int dev = 0;
     cudaGetDevice(&dev);
     static bool attr_set[64] = {};                 // function attributes are per device: engines of one process may sit on several GPUs
     if (!attr_set[dev & 63]) {
         cudaError_t e = cudaFuncSetAttribute(k_cycle_small<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cycle_small<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cycle_small<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cycle_small<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cycle_small<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cycle_small<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev & 63] = true;
     }

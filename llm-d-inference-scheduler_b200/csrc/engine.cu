@@ -1100,7 +1100,7 @@ static int small_batch_mode(epp_engine *h, const BatchView &v, const uint8_t **d
     if (v.device || h->small_max <= 0 || v.R > h->small_max || h->general) return 0;
     if (h->shard_begin != 0 || h->shard_end != 0xFFFFFFFFu) return 0;
     const int64_t bs = (int64_t)h->cfg.block_size_tokens * 4;
-    if ((bs & 31) || (size_t)h->cfg.max_prefix_blocks > cycle_small_max_blocks()) return 0;
+    if ((bs & 31) || bs > 64 * 1024 || (size_t)h->cfg.max_prefix_blocks > cycle_small_max_blocks()) return 0;
     const uint64_t layout_bits = v.offsets ? v.offsets_or_bits : v.uniform_len;
     if (v.R <= h->small_zc_max || !v.total_bytes) {
         *data_dev = v.total_bytes ? device_view_of_pinned(v.data) : nullptr;
@@ -1149,11 +1149,13 @@ static int32_t run_small(epp_engine *h, const BatchView &v, int mode, const uint
         CUDA_TRY(h->slot[0].data.reserve(v.total_bytes + 64, &h->dev_bytes));
         uint8_t *stage = h->slot[0].data.as<uint8_t>() + (start & 31);
         data_dev = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(stage) - (uintptr_t)start);   // + offsets[r]
-        if (h->small_pipe_min > 0 && R >= h->small_pipe_min) {
+        if (h->small_pipe_min > 0 && R >= h->small_pipe_min &&
+            cycle_small_stages_prompt(h->cfg.max_prefix_blocks, h->cfg.block_size_tokens * 4)) {
             // The copy goes to the second stream with a stream-ordered 32-bit write of the epoch behind it; the kernel is
             // launched on s0 at once and thread 0 of every CTA waits for that word, so the launch latency (and the stream's
-            // copy -> kernel hand-over) hides under the transfer.  The staging buffer is free: every request of the batch
-            // before raised its flag, which it does after its last read of the prompt.
+            // copy -> kernel hand-over) hides under the transfer.  The staging buffer is free although the kernel of the batch
+            // before may still be walking chains: it keeps a whole prompt in shared memory (cycle_small_stages_prompt),
+            // so every request raised its flag after its last read of these bytes.
             cudaStream_t s1 = h->slot[1].stream;
             uint32_t *arr = h->small_arrive.as<uint32_t>();
             CUDA_TRY(cudaMemcpyAsync(stage, v.data + start, v.total_bytes, cudaMemcpyHostToDevice, s1));

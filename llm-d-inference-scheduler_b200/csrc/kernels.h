@@ -195,6 +195,9 @@ struct SmallOut {
     const uint32_t *arrive;        // device
 };
 size_t cycle_small_max_blocks();
+// Does the kernel bring a whole prompt into shared memory (one bulk copy) before it hashes?  Then a request's flag is
+// raised only after its last read of the prompt bytes, and the staging buffer may be refilled as soon as all flags are up.
+bool cycle_small_stages_prompt(int32_t max_blocks, int32_t block_bytes);
 cudaError_t launch_cycle_small(const HashParams &hp, const PickParams &pp, const SmallOut &so, int align, cudaStream_t s,
                                int *launches);
 // Decision logic on injected dense match info (plugin parity / KAT mode).

@@ -807,6 +807,51 @@ def test_small_batch_zero_copy_path_vs_oracle(epp, orc, tie_seed, monkeypatch):
             np.testing.assert_array_equal(ad, bd)
 
 
+def test_small_batch_prompt_buffer_may_be_rewritten_when_the_call_returns(epp, orc):
+    """A cold request is decided by the global-stop rule long before its hash chain has reached the end of the prompt,
+    and epp_schedule returns as soon as every request is decided.  From then on the caller may rewrite its prompt
+    buffer, and the next batch's copy may refill the engine's staging buffer -- the hashes PreRequest indexes afterwards
+    (incl. the one of the trailing PARTIAL block, hashing.go:90-96, which the chain reaches last) must still be those
+    of the prompts that were scheduled.  1 request = the kernel reads the caller's pinned buffer; 24 = DMA-copied."""
+    E, bst, B = 8, 8, 2048                         # 64 KiB prompts: the chain runs for > 100 us
+    bb = 4 * bst
+    rng = np.random.default_rng(99)
+    role = np.full(E, 3, dtype=np.uint8)
+    spec = epp.ProfileSpec(1, [epp.ScorerSpec(2, 1.0, 0)])
+    for n in (1, 24):
+        with epp.Engine(E, spec, None, block_size_tokens=bst, max_prefix_blocks=B, lru_capacity_per_server=100000) as eng:
+            eng.register_model(b"m")
+            eng.pool_set(np.arange(E), role, np.zeros(E), np.zeros(E, dtype=np.int32))
+            row = bb * B
+            buf = epp.PinnedBuffer(2 * n * row)
+            batches = []
+            for k in range(2):
+                prompts = [bytes(rng.integers(0, 256, row - int(rng.integers(1, bb)), dtype=np.uint8)) for _ in range(n)]
+                batches.append(prompts)
+            offs = np.arange(n + 1, dtype=np.uint64) * np.uint64(row)
+
+            def fill(prompts):
+                for i, p in enumerate(prompts):
+                    buf.array[i * row: i * row + len(p)] = np.frombuffer(p, dtype=np.uint8)
+                return np.array([len(p) for p in prompts], dtype=np.uint64)
+
+            lens = fill(batches[0])
+            dec0, _ = eng.schedule(buf.array, offsets=offs, lengths=lens, n_requests=n, keep_hashes=True)
+            buf.array[: n * row] = 0xA5             # the caller's buffer is the caller's again
+            eng.index_add_picked()                  # PreRequest of batch 0 (stream-ordered behind its kernel)
+            lens = fill(batches[1])
+            dec1, _ = eng.schedule(buf.array, offsets=offs, lengths=lens, n_requests=n, keep_hashes=True)   # refills the staging buffer
+            eng.index_commit()
+            assert (dec0["status"] == 0).all() and (dec1["status"] == 0).all()
+            assert (dec0["match_blocks"] == 0).all()
+            for i, p in enumerate(batches[0]):
+                hs = orc.hash_prompt(p, b"m", bst, B)
+                assert len(hs) == B                # B - 1 full blocks + the partial one
+                for j in (0, B // 2, B - 2, B - 1):
+                    assert eng.index_get(int(hs[j])) == {int(dec0["pick"][i])}, (n, i, j)
+            buf.close()
+
+
 def test_index_commit_interval_bounds_the_staleness(epp, orc):
     """epp_config.index_commit_interval_us: with a long interval a scheduling call keeps reading the table of the last
     commit (the reference applies PreRequest in a goroutine of its own, approximateprefix/plugin.go:189-194), an
