@@ -1,4 +1,4 @@
-// Package eppcuda binds libepp_engine.so (include/epp_engine.h, C ABI v4) into the llm-d EPP and implements the
+// Package eppcuda binds libepp_engine.so (include/epp_engine.h, C ABI v5) into the llm-d EPP and implements the
 // reference's own interfaces on top of it:
 //
 //	requestcontrol.Scheduler    pkg/epp/requestcontrol/director.go:69-71          -> Scheduler (scheduler.go)
