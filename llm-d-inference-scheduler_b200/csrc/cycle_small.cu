@@ -1,6 +1,8 @@
-// cycle_small.cu -- the whole scheduling cycle (a1-a14) of a SMALL host batch as ONE kernel launch that reads the
-// prompts straight from the caller's pinned host memory and writes the decisions straight into pinned host memory:
-// no copy-engine transfer before or after, no stream synchronisation -- the host polls one flag word per request.
+// cycle_small.cu -- the whole scheduling cycle (a1-a14) of a SMALL host batch as ONE kernel launch that writes the
+// decisions straight into pinned host memory: no copy back, no stream synchronisation -- the host polls one flag word
+// per request.  The prompts of a handful of requests are read straight from the caller's pinned memory over PCIe (no
+// copy engine at all); a larger batch is DMA-copied into HBM on the engine's second stream while this kernel, launched
+// at the same time, waits for the word the copy stream writes behind the copy (SmallOut::arrive).
 // This is the latency path of the micro-batcher (csrc/batcher.cu): a flush of 1 .. 1024 requests.
 //
 // One CTA per request, 9 warps:
@@ -8,7 +10,7 @@
 //              prompt -- into shared memory, from HBM or straight from the caller's pinned host memory over PCIe;
 //   warps 0-7  digest: every thread hashes the 32-byte stripes of "its" blocks out of shared memory and leaves the merged
 //              stripe state of each FULL block there (256 blocks = one per thread);
-//   warp 8     chain: ONE lane walks the blocks in order (the serial part of hashPrompt, hashing.go:80-96; ~70 ns per
+//   warp 8     chain: ONE lane walks the blocks in order (the serial part of hashPrompt, hashing.go:80-96; ~84 ns per
 //              block: five dependent 64-bit multiplies), stores every hash to the request's row in HBM (the stash
 //              PreRequest needs) and over the block's stripe state in shared memory, and publishes its progress there
 //              every 32 blocks (no global fence on the critical path);
@@ -16,7 +18,9 @@
 //              a time as soon as the chain has produced them, so the table and posting-list latencies hide under the
 //              chain, and the global-stop rule (plugin.go:219-223) lets it decide a cold prompt after the first chunk
 //              while the chain is still hashing.  It then copies the decision to host memory and raises the flag.
-// The critical path is the chain (256 blocks x ~75 ns for a 16 KiB prompt) + one PCIe round trip each way.
+// Every prompt byte is consumed before the chain starts (the trailing partial block is parked in shared memory by the idle
+// chain warp): once a request's flag is up, its input may be overwritten.
+// The critical path is the chain (256 blocks x ~84 ns for a 16 KiB prompt) + one PCIe round trip each way.
 #include "hash_blocks.cuh"
 #include "match_sparse.cuh"
 
