@@ -144,7 +144,8 @@ struct epp_engine {
     int small_pipe_min = 1;         // EPP_SMALL_PIPELINE=n: DMA-copied batches of >= n requests start their kernel BEFORE the copy
                                     // lands (copy on the second stream, one stream-ordered flag write behind it); 0 = off
     DevBuf small_arrive;            // epoch word: the prompts of the batch have arrived
-    uint32_t *small_epoch_host = nullptr;   // pinned source of those words when the driver has no stream write-value
+    uint32_t *small_epoch_host = nullptr;   // pinned source of that word when the driver has no stream write-value
+    bool small_no_write_value = false;
     bool small_stats_pending = false;   // ev[0] / ev[1] bracket the last small batch; read lazily by epp_get_stats
     std::chrono::steady_clock::time_point last_commit{};   // last commit done by a scheduling call (index_commit_interval_us)
     bool committed_once = false;
@@ -1159,9 +1160,9 @@ static int32_t run_small(epp_engine *h, const BatchView &v, int mode, const uint
             cudaStream_t s1 = h->slot[1].stream;
             uint32_t *arr = h->small_arrive.as<uint32_t>();
             CUDA_TRY(cudaMemcpyAsync(stage, v.data + start, v.total_bytes, cudaMemcpyHostToDevice, s1));
-            if (const StreamWriteValue32 wv = stream_write_value32()) {
-                if (wv(s1, reinterpret_cast<CUdeviceptr>(arr), epoch, 0) != CUDA_SUCCESS) return fail(EPP_ERR_CUDA, "cuStreamWriteValue32 failed");
-            } else {
+            const StreamWriteValue32 wv = h->small_no_write_value ? nullptr : stream_write_value32();
+            if (!wv || wv(s1, reinterpret_cast<CUdeviceptr>(arr), epoch, 0) != CUDA_SUCCESS) {
+                h->small_no_write_value = true;    // no stream memory operations in this driver / context: a 4-byte copy does it
                 *h->small_epoch_host = epoch;      // read by the copy below before this (synchronous) call returns
                 CUDA_TRY(cudaMemcpyAsync(arr, h->small_epoch_host, sizeof(uint32_t), cudaMemcpyHostToDevice, s1));
             }
