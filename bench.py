@@ -471,7 +471,7 @@ def run_gpu(args, rank, world, local_rank):
     if rank == 0 and not args.no_e2e:
         import ctypes as C
         small = {"how": "median of 200 synchronous epp_schedule calls per size, pinned host prompts in / decisions out, "
-                        "raw C ABI (ctypes), same engine and index as `value`", "us": {}, "decisions_equal_e2e_batch": True}
+                        "raw C ABI (ctypes), same engine and index as `value`", "us": {}, "us_p99": {}, "decisions_equal_e2e_batch": True}
         sb = epp.capi.Batch()
         sb.uniform_len = w.prompt_bytes
         sb.data = host_tokens.ctypes.data
@@ -487,6 +487,7 @@ def run_gpu(args, rank, world, local_rank):
                 call()
                 ts.append(time.perf_counter() - t0)
             small["us"][str(n)] = float(np.median(ts) * 1e6)
+            small["us_p99"][str(n)] = float(np.percentile(ts, 99) * 1e6)
             small["decisions_equal_e2e_batch"] &= bool((small_dec[:n] == host_dec[:n]).all())
         small["launches_per_call"] = int(eng.stats()["last_kernel_launches"])
 
